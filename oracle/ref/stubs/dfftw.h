@@ -1,0 +1,1 @@
+#include "fftw_stub.h"

@@ -1,0 +1,218 @@
+"""ctypes driver for oracle/_ref/libg2ref_<variant>.so — TEST INFRASTRUCTURE ONLY.
+
+The libraries are the UNMODIFIED reference sources compiled by oracle/ref/Makefile.  The reference keeps
+all state in globals and can be initialised once per image, so every RefOracle instance loads a private
+copy of the shared object.
+"""
+import ctypes as C
+import os
+import shutil
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(HERE, "_ref")
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def available(variant):
+    return os.path.exists(os.path.join(REF_DIR, f"libg2ref_{variant}.so"))
+
+
+class RefOracle:
+    """One single-rank instance of the reference code (variant = compile-time flag set)."""
+
+    def __init__(self, variant, maxpart, boxsize=0.0, G=1.0, theta=0.5, errtol=0.005, criterion=1,
+                 softening=(0.0, 1.0, 1.0, 1.0, 1.0, 1.0), gravity=(0, 0, 1, 0, 0, 0), tree_alloc=1.5,
+                 buffer_mb=32):
+        src = os.path.join(REF_DIR, f"libg2ref_{variant}.so")
+        if not os.path.exists(src):
+            raise FileNotFoundError(src)
+        fd, self._tmp = tempfile.mkstemp(suffix=".so", prefix=f"g2ref_{variant}_")
+        os.close(fd)
+        shutil.copyfile(src, self._tmp)
+        self.lib = lib = C.CDLL(self._tmp)
+        os.unlink(self._tmp)
+        cfg = np.zeros(16, dtype=np.int32)
+        lib.g2ref_config(cfg.ctypes.data_as(C.c_void_p))
+        self.D, self.float_bytes, self.periodic, self.pmgrid, self.ntab, self.unequal, self.forcetest = (
+            int(x) for x in cfg[:7])
+        self.sizeof_particle, self.sizeof_node, self.sizeof_extnode, self.bits = (int(x) for x in cfg[7:11])
+        self.fdtype = np.float32 if self.float_bytes == 4 else np.float64
+        par = np.zeros(20)
+        par[0] = maxpart
+        par[1] = boxsize
+        par[2] = G
+        par[3] = theta
+        par[4] = errtol
+        par[5] = criterion
+        par[6:12] = softening
+        par[12:18] = gravity
+        par[18] = tree_alloc
+        par[19] = buffer_mb
+        lib.g2ref_walk_threads.restype = C.c_double
+        lib.g2ref_peano_key.restype = C.c_longlong
+        lib.g2ref_accel.restype = C.c_double
+        lib.g2ref_spline.restype = C.c_double
+        lib.g2ref_accel.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
+        lib.g2ref_spline.argtypes = lib.g2ref_accel.argtypes
+        # the reference prints progress with printf; silence fd 1 during calls
+        rc = self._quiet(lib.g2ref_setup, par.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("g2ref_setup failed")
+        self.maxpart = maxpart
+        self.n = 0
+
+    @staticmethod
+    def _quiet(fn, *args):
+        import sys
+        if os.environ.get("G2REF_VERBOSE"):
+            return fn(*args)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            return fn(*args)
+        finally:
+            C.CDLL(None).fflush(None)
+            os.dup2(saved, 1)
+            os.close(saved)
+            os.close(devnull)
+
+    # ---- inputs -------------------------------------------------------------------------------------
+    def load(self, pos, mass, ptype, vel=None):
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        mass = np.ascontiguousarray(mass, dtype=np.float64)
+        ptype = np.ascontiguousarray(ptype, dtype=np.int32)
+        n = len(mass)
+        velp = None
+        if vel is not None:
+            vel = np.ascontiguousarray(vel, dtype=np.float64)
+            velp = vel.ctypes.data_as(C.c_void_p)
+        rc = self.lib.g2ref_load(n, pos.ctypes.data_as(C.c_void_p), velp, mass.ctypes.data_as(C.c_void_p),
+                                 ptype.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError(f"g2ref_load failed ({rc})")
+        self.n = n
+
+    def set_active(self, active):
+        a = np.ascontiguousarray(active, dtype=np.int32)
+        self.lib.g2ref_set_active(a.ctypes.data_as(C.c_void_p))
+
+    def set_opening(self, theta, errtol, criterion):
+        self.lib.g2ref_set_opening(C.c_double(theta), C.c_double(errtol), int(criterion))
+
+    def set_oldacc(self, oldacc):
+        a = np.ascontiguousarray(oldacc, dtype=np.float64)
+        self.lib.g2ref_set_oldacc(a.ctypes.data_as(C.c_void_p))
+
+    # ---- reference entry points -----------------------------------------------------------------------
+    def domain(self):
+        """domain_Decomposition(): extent, keys, top tree, species-major PH reorder of P[]."""
+        self._quiet(self.lib.g2ref_domain)
+
+    def gravity(self):
+        """gravity_tree(): build if flagged + walk of active particles + OldAcc + G scaling."""
+        self._quiet(self.lib.g2ref_gravity)
+
+    def treebuild(self):
+        return self._quiet(self.lib.g2ref_treebuild)
+
+    def force_rebuild(self):
+        self.lib.g2ref_force_rebuild()
+
+    def walk_threads(self, nthreads, lo=0, hi=None):
+        cost = C.c_double(0)
+        hi = self.n if hi is None else hi
+        dt = self.lib.g2ref_walk_threads(int(lo), int(hi), int(nthreads), C.byref(cost))
+        return dt, cost.value
+
+    # ---- outputs --------------------------------------------------------------------------------------
+    def keys(self):
+        k = np.zeros(self.n, dtype=np.int64)
+        self.lib.g2ref_keys(k.ctypes.data_as(C.c_void_p))
+        return k
+
+    def peano_key(self, x, y, z, bits):
+        return int(self.lib.g2ref_peano_key(int(x), int(y), int(z), int(bits)))
+
+    def domain_info(self):
+        d = np.zeros(8)
+        self.lib.g2ref_get_domain(d.ctypes.data_as(C.c_void_p))
+        return dict(corner=d[0:3].copy(), center=d[3:6].copy(), len=d[6], fac=d[7])
+
+    def particles(self):
+        n = self.n
+        pos = np.zeros((n, 3))
+        mass = np.zeros(n)
+        ptype = np.zeros(n, dtype=np.int32)
+        pid = np.zeros(n, dtype=np.uint32)
+        acc = np.zeros((n, 3))
+        cost = np.zeros(n, dtype=np.float32)
+        oldacc = np.zeros(n)
+        self.lib.g2ref_get_particles(*(a.ctypes.data_as(C.c_void_p) for a in (pos, mass, ptype, pid, acc, cost, oldacc)))
+        return dict(pos=pos, mass=mass, type=ptype, id=pid, acc=acc, cost=cost, oldacc=oldacc)
+
+    def topnodes(self):
+        nt = self.lib.g2ref_ntopnodes()
+        nl = self.lib.g2ref_ntopleaves()
+        tn = np.zeros((nt, 7), dtype=np.int64)
+        dni = np.zeros(nl, dtype=np.int32)
+        self.lib.g2ref_get_topnodes(tn.ctypes.data_as(C.c_void_p), dni.ctypes.data_as(C.c_void_p))
+        return dict(daughter=tn[:, 0].copy(), leaf=tn[:, 3].copy(), size=tn[:, 4].copy(), startkey=tn[:, 5].copy(),
+                    count=tn[:, 6].copy(), domain_node_index=dni, ntopleaves=nl)
+
+    def tree(self):
+        nn = self.lib.g2ref_numnodes()
+        D = self.D
+        geom = np.zeros((nn, 4))
+        s = np.zeros((nn, 3, D))
+        mass = np.zeros((nn, D))
+        vs = np.zeros((nn, 3, D))
+        link = np.zeros((nn, 4), dtype=np.int32)
+        nextnode = np.zeros(self.n, dtype=np.int32)
+        father = np.zeros(self.n, dtype=np.int32)
+        self.lib.g2ref_get_tree(*(a.ctypes.data_as(C.c_void_p) for a in (geom, s, mass, vs, link, nextnode, father)))
+        return dict(numnodes=nn, maxpart=self.maxpart, len=geom[:, 0].copy(), center=geom[:, 1:4].copy(), s=s, mass=mass,
+                    vs=vs, bitflags=link[:, 0].copy(), sibling=link[:, 1].copy(), nextnode=link[:, 2].copy(),
+                    father=link[:, 3].copy(), p_nextnode=nextnode, p_father=father)
+
+    def srtable(self):
+        if not self.pmgrid:
+            return None
+        t = np.zeros((self.D, self.D, self.ntab))
+        self.lib.g2ref_get_srtable(t.ctypes.data_as(C.c_void_p))
+        return t
+
+    def pm_split(self):
+        d = np.zeros(2)
+        self.lib.g2ref_get_pm_split(d.ctypes.data_as(C.c_void_p))
+        return d[0], d[1]
+
+    def softening(self):
+        d = np.zeros(6)
+        self.lib.g2ref_get_softening(d.ctypes.data_as(C.c_void_p))
+        return d
+
+    def timings(self):
+        d = np.zeros(6)
+        self.lib.g2ref_timings(d.ctypes.data_as(C.c_void_p))
+        return dict(domain=d[0], gravity=d[1], build=d[2], walk=d[3], peano=d[4], cpu_domain=d[5])
+
+    def accel(self, tgt, src, pm, m, r2, r, n=1):
+        return self.lib.g2ref_accel(tgt, src, pm, m, r2, r, n)
+
+    def spline(self, tgt, src, pm, m, h, r, n=1):
+        return self.lib.g2ref_spline(tgt, src, pm, m, h, r, n)
+
+    def direct(self, targets):
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        acc = np.zeros((len(t), 3))
+        rc = self.lib.g2ref_direct(len(t), t.ctypes.data_as(C.c_void_p), acc.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("this oracle variant has no direct summation (needs FORCETEST, non-periodic)")
+        return acc
