@@ -1,0 +1,632 @@
+// g2_api.cu — the C ABI (include/g2gpu.h): context life cycle, uploads, downloads, stage entry points.
+#include "g2_common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+
+char g2_errbuf[512] = "";
+
+int g2_fail(int code, const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g2_errbuf, sizeof(g2_errbuf), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" const char *g2gpu_last_error(void) { return g2_errbuf; }
+
+extern "C" int g2gpu_device_count(void)
+{
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess)
+    return 0;
+  return n;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t count)
+{
+  cudaError_t e = cudaMalloc((void **) p, sizeof(T) * (count ? count : 1));
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", sizeof(T) * count, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
+{
+  if(!out || !cfg)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  *out = nullptr;
+  if(cfg->n_gravs < 1 || cfg->n_gravs > G2GPU_MAX_GRAVS || cfg->max_part < 1 || cfg->max_nodes < 8)
+    return g2_fail(G2GPU_ERR_ARG, "bad configuration (n_gravs=%d max_part=%d max_nodes=%d)", cfg->n_gravs, cfg->max_part, cfg->max_nodes);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if(e != cudaSuccess || ndev == 0)
+    return g2_fail(G2GPU_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+  if(cfg->device < 0 || cfg->device >= ndev)
+    return g2_fail(G2GPU_ERR_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+  G2_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  G2_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if(prop.major < 10)
+    return g2_fail(G2GPU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+  g2gpu_ctx *c = (g2gpu_ctx *) calloc(1, sizeof(g2gpu_ctx));
+  if(!c)
+    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
+  c->cfg = *cfg;
+  if(c->cfg.nranks < 1)
+    c->cfg.nranks = 1;
+  c->D = cfg->n_gravs;
+  c->nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : G2_NSM_FALLBACK;
+  c->acc_double = 1;
+  for(int t = 0; t < 6; t++)
+    c->force_softening[t] = 1.0;
+  G2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for(int i = 0; i < 16; i++)
+    G2_CUDA(cudaEventCreate(&c->ev[i]));
+
+  const size_t np = (size_t) cfg->max_part, nn = (size_t) cfg->max_nodes;
+  const size_t cap = (np > nn ? np : nn) + G2_MAXTOP + 8;
+  const int R = 2 + c->D;
+  int rc = 0;
+  rc |= dalloc(&c->in_pm, np); rc |= dalloc(&c->in_type, np); rc |= dalloc(&c->in_oldacc, np); rc |= dalloc(&c->in_active, np);
+  rc |= dalloc(&c->pm, np); rc |= dalloc(&c->ptype, np); rc |= dalloc(&c->oldacc, np); rc |= dalloc(&c->active, np);
+  rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np);
+  rc |= dalloc(&c->skey[0], np); rc |= dalloc(&c->skey[1], np); rc |= dalloc(&c->sval[0], np); rc |= dalloc(&c->sval[1], np);
+  c->tilehist_elems = (size_t) ((np + 4095) / 4096) * 512 + 8;
+  rc |= dalloc(&c->tilehist, c->tilehist_elems);
+  c->scan_tmp_elems = cap / 2048 + 16 + c->tilehist_elems / 2048;
+  rc |= dalloc(&c->scan_tmp, c->scan_tmp_elems);
+  rc |= dalloc(&c->d_domain, (size_t) 16); rc |= dalloc(&c->d_minmax, (size_t) 8); rc |= dalloc(&c->d_top, (size_t) 1);
+  rc |= dalloc(&c->d_species_start, (size_t) 16);
+  rc |= dalloc(&c->tm, np + 1); rc |= dalloc(&c->ttl, np + 1); rc |= dalloc(&c->tbase, np + 2); rc |= dalloc(&c->tcnt, cap + 2);
+  rc |= dalloc(&c->c_a, nn); rc |= dalloc(&c->c_b, nn); rc |= dalloc(&c->c_d, nn); rc |= dalloc(&c->c_suns, nn * 8);
+  rc |= dalloc(&c->c_father, nn); rc |= dalloc(&c->p_parent, np); rc |= dalloc(&c->c_ready, nn + 1); rc |= dalloc(&c->c_nchild, nn);
+  rc |= dalloc(&c->c_npart, nn); rc |= dalloc(&c->c_min1, nn); rc |= dalloc(&c->c_min2, nn); rc |= dalloc(&c->c_poff, cap + 2);
+  rc |= dalloc(&c->c_refid, nn);
+  rc |= dalloc(&c->t_suns, (size_t) G2_MAXTOP * 8); rc |= dalloc(&c->t_first, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_last, (size_t) G2_MAXTOP);
+  rc |= dalloc(&c->t_min1, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_min2, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_ready, (size_t) G2_MAXTOP);
+  rc |= dalloc(&c->t_npart, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_nchild, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_ubase, (size_t) G2_MAXTOP);
+  rc |= dalloc(&c->wcells, (nn + G2_MAXTOP) * R); rc |= dalloc(&c->wpart, np);
+  rc |= dalloc(&c->hist2, np + 2); rc |= dalloc(&c->hist2_scan, np + 2); rc |= dalloc(&c->dmin, np + 2);
+  rc |= dalloc(&c->d_err, (size_t) 8);
+  rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
+  rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
+  rc |= dalloc(&c->d_counters, (size_t) 8);
+  if(rc)
+    {
+      g2gpu_destroy(c);
+      return G2GPU_ERR_NOMEM;
+    }
+  if(cudaMallocHost((void **) &c->h_err, 16 * sizeof(int)) != cudaSuccess || cudaMallocHost((void **) &c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess
+     || cudaMallocHost((void **) &c->h_top, sizeof(G2TopTree)) != cudaSuccess)
+    {
+      g2gpu_destroy(c);
+      return g2_fail(G2GPU_ERR_NOMEM, "pinned host allocation failed");
+    }
+  G2_CUDA(cudaMemset(c->acc, 0, sizeof(float) * 3 * np));
+  G2_CUDA(cudaMemset(c->cost, 0, sizeof(float) * np));
+  G2_CUDA(cudaMemset(c->oldacc_out, 0, sizeof(float) * np));
+  *out = c;
+  return 0;
+}
+
+extern "C" void g2gpu_destroy(g2gpu_ctx *c)
+{
+  if(!c)
+    return;
+  cudaSetDevice(c->cfg.device);
+  if(c->stream)
+    cudaStreamSynchronize(c->stream);
+  void *ptrs[] = { c->in_pm, c->in_type, c->in_oldacc, c->in_active, c->in_vel, c->in_gravpm, c->pm, c->ptype, c->oldacc, c->active, c->vel, c->gravpm,
+    c->phkey, c->perm, c->skey[0], c->skey[1], c->sval[0], c->sval[1], c->tilehist, c->scan_tmp, c->d_domain, c->d_minmax, c->d_top, c->d_topscratch,
+    c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
+    c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
+    c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
+    c->d_srtable, c->d_srtable_f };
+  for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
+    if(ptrs[i])
+      cudaFree(ptrs[i]);
+  if(c->h_err)
+    cudaFreeHost(c->h_err);
+  if(c->h_counters)
+    cudaFreeHost(c->h_counters);
+  if(c->h_top)
+    cudaFreeHost(c->h_top);
+  if(c->h_stage)
+    cudaFreeHost(c->h_stage);
+  for(int i = 0; i < 16; i++)
+    if(c->ev[i])
+      cudaEventDestroy(c->ev[i]);
+  if(c->stream)
+    cudaStreamDestroy(c->stream);
+  free(c);
+}
+
+extern "C" int g2gpu_set_species(g2gpu_ctx *c, const int type_to_grav[6], const double force_softening[6])
+{
+  if(!c || !type_to_grav || !force_softening)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  for(int t = 0; t < 6; t++)
+    {
+      if(type_to_grav[t] < 0 || type_to_grav[t] >= c->D)	// ngravs_core.c:270-279
+	return g2_fail(G2GPU_ERR_ARG, "native interaction %d declared for type %d does not exist", type_to_grav[t], t);
+      c->type_to_grav[t] = type_to_grav[t];
+      c->force_softening[t] = force_softening[t];
+    }
+  return 0;
+}
+
+extern "C" int g2gpu_set_laws(g2gpu_ctx *c, const int *accel_id, const int *spline_id, const double *params)
+{
+  if(!c || !accel_id || !spline_id)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  const int D = c->D;
+  for(int i = 0; i < D * D; i++)
+    {
+      int a = accel_id[i], s = spline_id[i];
+      if(a < G2GPU_LAW_NONE || a > G2GPU_LAW_SOURCEBARYONBAM)	// ngravs_core.c:326-365: every slot must be wired
+	return g2_fail(G2GPU_ERR_LAW, "AccelFxns[%d][%d] is not a registered law (%d)", i / D, i % D, a);
+      if(s < G2GPU_SPLINE_NONE || s > G2GPU_SPLINE_SOURCEBARYONBAM)
+	return g2_fail(G2GPU_ERR_LAW, "AccelSplines[%d][%d] is not a registered spline (%d)", i / D, i % D, s);
+      c->laws.accel[i] = a;
+      c->laws.spline[i] = s;
+      for(int k = 0; k < 4; k++)
+	c->laws.par[i][k] = params ? (float) params[4 * i + k] : 0.0f;
+    }
+  c->laws_set = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
+{
+  if(!c || !table)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  const int D = c->D, ntab = c->cfg.ntab;
+  if(ntab <= 0)
+    return g2_fail(G2GPU_ERR_ARG, "ntab not configured");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  // identical pair tables are stored once (stock wiring: all D*D tables are the Newtonian one)
+  int nu = 0;
+  int first[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  for(int i = 0; i < D * D; i++)
+    {
+      int found = -1;
+      for(int u = 0; u < nu && found < 0; u++)
+	if(memcmp(table + (size_t) first[u] * ntab, table + (size_t) i * ntab, sizeof(double) * ntab) == 0)
+	  found = u;
+      if(found < 0)
+	{
+	  first[nu] = i;
+	  found = nu++;
+	}
+      c->sr_tabmap[i] = (unsigned char) found;
+    }
+  c->sr_ntables = nu;
+  float *hf = (float *) malloc(sizeof(float) * (size_t) nu * ntab);
+  if(!hf)
+    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
+  for(int u = 0; u < nu; u++)
+    for(int k = 0; k < ntab; k++)
+      hf[(size_t) u * ntab + k] = (float) table[(size_t) first[u] * ntab + k];
+  if(c->d_srtable_f)
+    cudaFree(c->d_srtable_f);
+  c->d_srtable_f = nullptr;
+  int rc = dalloc(&c->d_srtable_f, (size_t) nu * ntab);
+  if(rc == 0 && cudaMemcpy(c->d_srtable_f, hf, sizeof(float) * (size_t) nu * ntab, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = g2_fail(G2GPU_ERR_CUDA, "table upload failed");
+  free(hf);
+  if(rc)
+    return rc;
+  if((size_t) nu * ntab * sizeof(float) > 200 * 1024)
+    return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range tables do not fit in shared memory", nu);
+  c->srtable_set = 1;
+  return 0;
+}
+
+// ---- uploads --------------------------------------------------------------------------------------------------
+static int ensure_stage(g2gpu_ctx *c, size_t bytes)
+{
+  if(c->h_stage_bytes >= bytes)
+    return 0;
+  if(c->h_stage)
+    cudaFreeHost(c->h_stage);
+  c->h_stage = nullptr;
+  c->h_stage_bytes = 0;
+  if(cudaMallocHost(&c->h_stage, bytes) != cudaSuccess)
+    return g2_fail(G2GPU_ERR_NOMEM, "pinned staging allocation of %zu bytes failed", bytes);
+  c->h_stage_bytes = bytes;
+  return 0;
+}
+
+static int ensure_opt(g2gpu_ctx *c, int want_vel, int want_gravpm)
+{
+  const size_t np = (size_t) c->cfg.max_part;
+  if(want_vel && !c->in_vel)
+    {
+      G2_TRY(dalloc(&c->in_vel, 3 * np));
+      G2_TRY(dalloc(&c->vel, 3 * np));
+    }
+  if(want_gravpm && !c->in_gravpm)
+    {
+      G2_TRY(dalloc(&c->in_gravpm, 3 * np));
+      G2_TRY(dalloc(&c->gravpm, 3 * np));
+    }
+  return 0;
+}
+
+extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
+			    const float *vel, const float *gravpm, const int *active)
+{
+  if(!c || !pos || !mass || !type)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(npart < 1 || npart > c->cfg.max_part)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  G2_TRY(ensure_opt(c, vel != nullptr, gravpm != nullptr));
+  const size_t n = (size_t) npart;
+  // pack into one pinned staging buffer: float4 pos+mass | int type | float oldacc | u8 active
+  size_t bytes = n * (16 + 4 + 4 + 1) + 64;
+  G2_TRY(ensure_stage(c, bytes));
+  float4 *s_pm = (float4 *) c->h_stage;
+  int *s_type = (int *) (s_pm + n);
+  float *s_old = (float *) (s_type + n);
+  unsigned char *s_act = (unsigned char *) (s_old + n);
+  for(size_t i = 0; i < n; i++)
+    {
+      s_pm[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]);
+      int t = type[i];
+      if(t < 0 || t > 5)
+	return g2_fail(G2GPU_ERR_ARG, "particle %zu has type %d", i, t);
+      s_type[i] = t;
+      s_old[i] = oldacc ? oldacc[i] : 0.0f;
+      s_act[i] = active ? (active[i] != 0) : 1;
+    }
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaEventRecord(c->ev[9], st));
+  G2_CUDA(cudaMemcpyAsync(c->in_pm, s_pm, n * 16, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(c->in_type, s_type, n * 4, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(c->in_oldacc, s_old, n * 4, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(c->in_active, s_act, n, cudaMemcpyHostToDevice, st));
+  if(vel)
+    G2_CUDA(cudaMemcpyAsync(c->in_vel, vel, n * 12, cudaMemcpyHostToDevice, st));
+  if(gravpm)
+    G2_CUDA(cudaMemcpyAsync(c->in_gravpm, gravpm, n * 12, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaEventRecord(c->ev[10], st));
+  G2_CUDA(cudaStreamSynchronize(st));	// the staging buffer is reused by the next call
+  c->have_vel = vel != nullptr;
+  c->have_gravpm = gravpm != nullptr;
+  c->npart = npart;
+  c->stage = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
+				int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current)
+{
+  if(!c || !P)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(npart < 1 || npart > c->cfg.max_part)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  if(float_bytes != 4 && float_bytes != 8)
+    return g2_fail(G2GPU_ERR_ARG, "float_bytes must be 4 or 8");
+  const size_t n = (size_t) npart;
+  float *buf = (float *) malloc(sizeof(float) * n * 11 + sizeof(int) * n * 2);
+  if(!buf)
+    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
+  float *pos = buf, *mass = pos + 3 * n, *old = mass + n, *vel = old + n, *gpm = vel + 3 * n;
+  int *type = (int *) (gpm + 3 * n), *act = type + n;
+  const char *base = (const char *) P;
+#define G2_RD(off, k) (float_bytes == 4 ? ((const float *) (q + (off)))[k] : (float) ((const double *) (q + (off)))[k])
+  for(size_t i = 0; i < n; i++)
+    {
+      const char *q = base + i * stride;
+      for(int k = 0; k < 3; k++)
+	{
+	  pos[3 * i + k] = G2_RD(off_pos, k);
+	  if(off_vel >= 0)
+	    vel[3 * i + k] = G2_RD(off_vel, k);
+	  if(off_gravpm >= 0)
+	    gpm[3 * i + k] = G2_RD(off_gravpm, k);
+	}
+      mass[i] = G2_RD(off_mass, 0);
+      old[i] = off_oldacc >= 0 ? G2_RD(off_oldacc, 0) : 0.0f;
+      type[i] = *(const int *) (q + off_type);
+      act[i] = off_ti_endstep >= 0 ? (*(const int *) (q + off_ti_endstep) == ti_current) : 1;
+    }
+#undef G2_RD
+  int rc = g2gpu_upload(c, npart, pos, mass, type, old, off_vel >= 0 ? vel : nullptr, off_gravpm >= 0 ? gpm : nullptr, act);
+  free(buf);
+  return rc;
+}
+
+extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **ptrs)
+{
+  if(!c || !ptrs)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(npart < 1 || npart > c->cfg.max_part)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  ptrs[0] = c->in_pm;
+  ptrs[1] = c->in_type;
+  ptrs[2] = c->in_oldacc;
+  ptrs[3] = c->in_active;
+  return 0;
+}
+
+extern "C" int g2gpu_inputs_ready(g2gpu_ctx *c, int npart)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(npart < 1 || npart > c->cfg.max_part)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  c->have_vel = 0;
+  c->have_gravpm = 0;
+  c->npart = npart;
+  c->stage = 1;
+  return 0;
+}
+
+// ---- stages ---------------------------------------------------------------------------------------------------
+static float ev_ms(g2gpu_ctx *c, int a, int b)
+{
+  float ms = 0;
+  if(cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return 0;
+    }
+  return ms;
+}
+
+extern "C" int g2gpu_domain(g2gpu_ctx *c)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 1)
+    return g2_fail(G2GPU_ERR_STATE, "domain: no particles uploaded");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_stage_domain(c);
+}
+
+extern "C" int g2gpu_treebuild(g2gpu_ctx *c, int *numnodes)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  G2_TRY(g2_stage_treebuild(c));
+  if(numnodes)
+    *numnodes = c->numnodes;
+  return 0;
+}
+
+extern "C" int g2gpu_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
+{
+  if(!c || !wp)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_stage_walk(c, wp);
+}
+
+extern "C" int g2gpu_sync(g2gpu_ctx *c)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" void *g2gpu_stream(g2gpu_ctx *c) { return c ? (void *) c->stream : nullptr; }
+
+extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
+{
+  if(!c || !name)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(strcmp(name, "acc_double") == 0)
+    c->acc_double = value;
+  else if(strcmp(name, "rank") == 0)
+    c->cfg.rank = value;
+  else if(strcmp(name, "nranks") == 0)
+    c->cfg.nranks = value < 1 ? 1 : value;
+  else
+    return g2_fail(G2GPU_ERR_ARG, "unknown option %s", name);
+  return 0;
+}
+
+// ---- downloads --------------------------------------------------------------------------------------------------
+extern "C" int g2gpu_get_domain(g2gpu_ctx *c, double out[8])
+{
+  if(!c || !out)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_domain has not run");
+  G2_CUDA(cudaMemcpyAsync(out, c->d_domain, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int g2gpu_get_keys(g2gpu_ctx *c, long long *keys)
+{
+  if(!c || !keys)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_domain has not run");
+  G2_CUDA(cudaMemcpyAsync(keys, c->phkey, sizeof(long long) * (size_t) c->npart, cudaMemcpyDeviceToHost, c->stream));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int g2gpu_get_order(g2gpu_ctx *c, int *perm)
+{
+  if(!c || !perm)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_domain has not run");
+  G2_CUDA(cudaMemcpyAsync(perm, c->perm, sizeof(int) * (size_t) c->npart, cudaMemcpyDeviceToHost, c->stream));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int g2gpu_get_topnodes(g2gpu_ctx *c, int *ntopnodes, int *ntopleaves, int *daughter, int *leaf, long long *startkey,
+				  long long *size, long long *count, int *domain_node_index)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_domain has not run");
+  G2_CUDA(cudaMemcpyAsync(c->h_top, c->d_top, sizeof(G2TopTree), cudaMemcpyDeviceToHost, c->stream));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  const G2TopTree *t = c->h_top;
+  if(t->err)
+    return g2_fail(G2GPU_ERR_TOPNODES, "top-level tree exceeds %d nodes", G2_MAXTOP);
+  if(ntopnodes)
+    *ntopnodes = t->ntopnodes;
+  if(ntopleaves)
+    *ntopleaves = t->ntopleaves;
+  for(int i = 0; i < t->ntopnodes; i++)
+    {
+      if(daughter)
+	daughter[i] = t->daughter[i];
+      if(leaf)
+	leaf[i] = t->leaf[i];
+      if(startkey)
+	startkey[i] = t->startkey[i];
+      if(size)
+	size[i] = 1LL << t->shift[i];
+      if(count)
+	count[i] = t->count[i];
+    }
+  if(domain_node_index)
+    for(int i = 0; i < t->ntopleaves; i++)
+      domain_node_index[i] = c->cfg.max_part + t->dni[i];
+  return 0;
+}
+
+extern "C" int g2gpu_download_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,
+				   int *nextnode, int *father, int *p_nextnode, int *p_father)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_export_tree(c, len, center, s, mass, bitflags, sibling, nextnode, father, p_nextnode, p_father);
+}
+
+extern "C" int g2gpu_download_acc(g2gpu_ctx *c, float *acc, float *cost, float *oldacc)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(c->stage < 4)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_walk has not run");
+  const size_t n = (size_t) c->npart;
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaEventRecord(c->ev[11], st));
+  if(acc)
+    G2_CUDA(cudaMemcpyAsync(acc, c->acc, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, st));
+  if(cost)
+    G2_CUDA(cudaMemcpyAsync(cost, c->cost, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  if(oldacc)
+    G2_CUDA(cudaMemcpyAsync(oldacc, c->oldacc_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaEventRecord(c->ev[12], st));
+  G2_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int g2gpu_slice(g2gpu_ctx *c, int *lo, int *hi)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(lo)
+    *lo = c->w_lo;
+  if(hi)
+    *hi = c->w_hi;
+  return 0;
+}
+
+extern "C" int g2gpu_gravity_tree(g2gpu_ctx *c, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
+				  const int *active, const g2gpu_walk_params *wp, float *acc, float *cost, float *oldacc_out, int *perm)
+{
+  G2_TRY(g2gpu_upload(c, npart, pos, mass, type, oldacc, nullptr, nullptr, active));
+  G2_TRY(g2gpu_domain(c));
+  G2_TRY(g2gpu_treebuild(c, nullptr));
+  G2_TRY(g2gpu_walk(c, wp));
+  G2_TRY(g2gpu_download_acc(c, acc, cost, oldacc_out));
+  if(perm)
+    G2_TRY(g2gpu_get_order(c, perm));
+  return 0;
+}
+
+extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[4])
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  if(ms)
+    {
+      ms[0] = c->stage >= 2 ? ev_ms(c, 0, 3) : 0;
+      ms[1] = c->stage >= 3 ? ev_ms(c, 4, 5) : 0;
+      ms[2] = c->stage >= 4 ? ev_ms(c, 6, 8) : 0;
+      ms[3] = c->stage >= 4 ? ev_ms(c, 7, 8) : 0;
+      ms[4] = c->stage >= 2 ? ev_ms(c, 1, 2) : 0;
+      ms[5] = c->stage >= 1 ? ev_ms(c, 9, 10) : 0;
+      ms[6] = c->stage >= 4 ? ev_ms(c, 11, 12) : 0;
+      ms[7] = 0;
+    }
+  if(counters)
+    {
+      counters[0] = c->launches;
+      counters[1] = counters[2] = counters[3] = 0;
+      if(c->stage >= 4)
+	{
+	  G2_CUDA(cudaMemcpy(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	  counters[1] = (long long) c->h_counters[0];
+	  counters[2] = (long long) c->h_counters[1];
+	  counters[3] = c->w_hi - c->w_lo;
+	}
+    }
+  return 0;
+}
+
+extern "C" void g2gpu_reset_counters(g2gpu_ctx *c)
+{
+  if(c)
+    c->launches = 0;
+}
+
+// ---- stand-alone kernels for parity tests ------------------------------------------------------------------------
+extern "C" int g2gpu_peano_keys(g2gpu_ctx *c, int n, const int *xyz, int bits, long long *keys)
+{
+  if(!c || !xyz || !keys || n < 1 || bits < 1 || bits > 21)
+    return g2_fail(G2GPU_ERR_ARG, "bad argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_peano_keys_standalone(c, n, xyz, bits, keys);
+}
+
+extern "C" int g2gpu_sort_pairs(g2gpu_ctx *c, int n, unsigned long long *keys, unsigned int *vals, int begin_bit, int end_bit)
+{
+  if(!c || !keys || !vals || n < 1 || n > c->cfg.max_part || begin_bit < 0 || end_bit > 64 || end_bit < begin_bit)
+    return g2_fail(G2GPU_ERR_ARG, "bad argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaMemcpyAsync(c->skey[0], keys, sizeof(unsigned long long) * (size_t) n, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(c->sval[0], vals, sizeof(unsigned int) * (size_t) n, cudaMemcpyHostToDevice, st));
+  unsigned long long *k = c->skey[0];
+  unsigned int *v = c->sval[0];
+  G2_CUDA(cudaEventRecord(c->ev[13], st));
+  G2_TRY(g2_radix_sort_pairs(c, n, &k, &v, c->skey[1], c->sval[1], begin_bit, end_bit));
+  G2_CUDA(cudaEventRecord(c->ev[14], st));
+  G2_CUDA(cudaMemcpyAsync(keys, k, sizeof(unsigned long long) * (size_t) n, cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemcpyAsync(vals, v, sizeof(unsigned int) * (size_t) n, cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaStreamSynchronize(st));
+  c->stage = 0;			// the sort scratch held the particle order
+  return 0;
+}
+
+extern "C" int g2gpu_eval_pairs(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+				const int *npart_in_node, float *fac)
+{
+  if(!c || !pm || !m || !r || !h || !fac || n < 1 || tgt < 0 || src < 0 || tgt >= c->D || src >= c->D)
+    return g2_fail(G2GPU_ERR_ARG, "bad argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_eval_pairs_standalone(c, n, tgt, src, pm, m, r, h, npart_in_node, fac);
+}

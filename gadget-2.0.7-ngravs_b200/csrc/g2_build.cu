@@ -1,0 +1,1034 @@
+// g2_build.cu — stage 2: the oct-tree of force_treebuild (forcetree.c:61-281) built in parallel.
+//
+// The reference inserts particles one by one (forcetree.c:136-257).  The resulting tree is a pure function
+// of the particle set: every octree cell below a top-level leaf that holds >= 2 particles is a node, and the
+// octant of a particle in a cell is decided by `Pos > center` on FLOAT centres obtained by repeated
+// center +- 0.25*len (forcetree.c:160-165, 188-206).  We reproduce exactly that geometry:
+//   1. tree key = octant path of the particle (3 bits/level, G2_MAXDEPTH levels): the top-level part comes from
+//      the integer PH key (forcetree.c:144-153), the rest from the float comparisons;
+//   2. radix sort by tree key -> depth-first (slot-order) sequence of particles;
+//   3. common-prefix depths of neighbours give every cell with >= 2 particles (no path compression);
+//   4. a top-down pass finds each cell's children, a bottom-up pass (last-arriving child continues upward)
+//      accumulates per-species monopoles in FP64 exactly like force_update_node_recursive (forcetree.c:451-743),
+//      children in slot order 0..7, children's values re-read as rounded FLOATs;
+//   5. cells are laid out in depth-first order (index U) for the walk; the reference's insertion-order node
+//      numbers are derived on request (g2_stage_renumber) from the second-smallest particle index per cell.
+#include "g2_common.cuh"
+
+#define KEYBITS (3 * G2_MAXDEPTH)
+
+struct G2Soft
+{
+  int t2g[6];
+  double fsoft[6];		// All.ForceSoftening
+  int unequal;
+};
+
+// ---------------------------------------------------------------- helpers ----------------------------------
+__device__ __forceinline__ int top_leaf_of_key(const G2TopTree *__restrict__ tt, long long key)
+{
+  // forcetree.c:148-150
+  int no = 0;
+  while(tt->daughter[no] >= 0)
+    no = tt->daughter[no] + (int) ((key - tt->startkey[no]) >> (tt->shift[no] - 3));
+  return no;
+}
+
+__device__ __forceinline__ unsigned int digit_at(unsigned long long key, int level)	// level 1..G2_MAXDEPTH
+{
+  return (unsigned int) (key >> (3 * (G2_MAXDEPTH - level))) & 7u;
+}
+
+__device__ __forceinline__ unsigned long long prefix_of(unsigned long long key, int depth)
+{
+  return depth >= G2_MAXDEPTH ? key : (key >> (3 * (G2_MAXDEPTH - depth)));
+}
+
+// child geometry: forcetree.c:188-206 (lenhalf is double, centres are stored FLOAT)
+__device__ __forceinline__ void descend(float &cx, float &cy, float &cz, float &len, unsigned int sub)
+{
+  double q = __dmul_rn(0.25, (double) len);
+  cx = (float) __dadd_rn((double) cx, (sub & 1) ? q : -q);
+  cy = (float) __dadd_rn((double) cy, (sub & 2) ? q : -q);
+  cz = (float) __dadd_rn((double) cz, (sub & 4) ? q : -q);
+  len = 0.5f * len;
+}
+
+// ---------------------------------------------------------------- 1. tree keys -------------------------------
+__global__ void __launch_bounds__(256) treekey_kernel(const float4 *__restrict__ pm, const long long *__restrict__ phkey, int n,
+						      const G2TopTree *__restrict__ tt, unsigned long long *__restrict__ tkey,
+						      unsigned int *__restrict__ tval, unsigned short *__restrict__ ptl)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  int leaf = top_leaf_of_key(tt, phkey[i]);
+  int k = tt->fnode[leaf];
+  float cx = tt->fcx[k], cy = tt->fcy[k], cz = tt->fcz[k], len = tt->flen[k];
+  int t = tt->fdepth[k];
+  unsigned long long path = tt->fmorton[k];
+  float4 p = pm[i];
+  for(int lvl = t + 1; lvl <= G2_MAXDEPTH; lvl++)
+    {
+      unsigned int sub = (p.x > cx ? 1u : 0u) | (p.y > cy ? 2u : 0u) | (p.z > cz ? 4u : 0u);
+      path = (path << 3) | sub;
+      descend(cx, cy, cz, len, sub);
+    }
+  tkey[i] = path;
+  tval[i] = (unsigned int) i;
+  ptl[i] = (unsigned short) k;
+}
+
+// ---------------------------------------------------------------- 2. neighbour depths ------------------------
+// tm[p] = number of common levels of sorted positions p and p+1, or 255 if they lie in different top-level
+// leaves (or p is the last particle); tl[p] = top node of position p.
+__global__ void __launch_bounds__(256) pair_depth_kernel(const unsigned long long *__restrict__ tkey, const unsigned int *__restrict__ tq,
+							 const unsigned short *__restrict__ ptl, int n, unsigned char *__restrict__ tm,
+							 unsigned short *__restrict__ tl, int *__restrict__ err)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= n)
+    return;
+  unsigned short k = ptl[tq[p]];
+  tl[p] = k;
+  unsigned char m = 255;
+  if(p + 1 < n && ptl[tq[p + 1]] == k)
+    {
+      unsigned long long x = tkey[p] ^ tkey[p + 1];
+      if(x == 0)
+	{
+	  m = G2_MAXDEPTH;
+	  atomicExch(&err[0], G2GPU_ERR_TREE_DEPTH);
+	}
+      else
+	m = (unsigned char) ((__clzll((long long) x) - (64 - KEYBITS)) / 3);
+    }
+  tm[p] = m;
+}
+
+// number of cells owned by pair p = cells whose leftmost particle is p:
+// depths max(m[p-1], t)+1 .. m[p]   (t = depth of the top-level leaf)
+__device__ __forceinline__ int first_depth(const unsigned char *__restrict__ tm, const unsigned short *__restrict__ tl,
+					   const G2TopTree *__restrict__ tt, int p)
+{
+  int t = tt->fdepth[tl[p]];
+  int mprev = -1;
+  if(p > 0)
+    {
+      unsigned char v = tm[p - 1];
+      if(v != 255)
+	mprev = v;
+    }
+  return (mprev > t ? mprev : t) + 1;
+}
+
+__global__ void __launch_bounds__(256) cell_count_kernel(const unsigned char *__restrict__ tm, const unsigned short *__restrict__ tl,
+							 const G2TopTree *__restrict__ tt, int n, unsigned int *__restrict__ cnt)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= n)
+    return;
+  int c = 0;
+  unsigned char m = tm[p];
+  if(m != 255)
+    {
+      c = (int) m - first_depth(tm, tl, tt, p) + 1;
+      if(c < 0)
+	c = 0;
+    }
+  cnt[p] = (unsigned int) c;
+}
+
+// ---------------------------------------------------------------- 3. cells -----------------------------------
+__global__ void __launch_bounds__(256) cell_init_kernel(const unsigned char *__restrict__ tm, const unsigned short *__restrict__ tl,
+							const G2TopTree *__restrict__ tt, const unsigned int *__restrict__ tbase, int n,
+							int max_cells, unsigned int *__restrict__ c_a, unsigned char *__restrict__ c_d,
+							int *__restrict__ err)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= n)
+    return;
+  unsigned int b0 = tbase[p], b1 = tbase[p + 1];
+  if(b1 == b0)
+    return;
+  if(b1 > (unsigned int) max_cells)
+    {
+      atomicExch(&err[1], G2GPU_ERR_MAXNODES);
+      return;
+    }
+  int fd = first_depth(tm, tl, tt, p);
+  for(unsigned int c = b0; c < b1; c++)
+    {
+      c_a[c] = (unsigned int) p;
+      c_d[c] = (unsigned char) (fd + (int) (c - b0));
+    }
+}
+
+// last position in [pos, hi] sharing the first `depth` digits with position pos (keys sorted ascending)
+__device__ __forceinline__ unsigned int run_end(const unsigned long long *__restrict__ tkey, unsigned int pos, unsigned int hi, int depth)
+{
+  const unsigned long long pre = prefix_of(tkey[pos], depth);
+  unsigned int step = 1, lo = pos;	// invariant: lo is inside the run
+  while(lo + step <= hi && prefix_of(tkey[lo + step], depth) == pre)
+    {
+      lo += step;
+      step <<= 1;
+    }
+  unsigned int top = lo + step - 1;	// first candidate known (or assumed) outside is lo+step
+  if(top > hi)
+    top = hi;
+  // binary search in (lo, top] for the last inside
+  while(lo < top)
+    {
+      unsigned int mid = lo + (top - lo + 1) / 2;
+      if(prefix_of(tkey[mid], depth) == pre)
+	lo = mid;
+      else
+	top = mid - 1;
+    }
+  return lo;
+}
+
+// enumerate the children of the cell [a,b] at depth d: suns[slot] = particle position (>= 0), -(cell+2), or -1
+__device__ __forceinline__ void find_children(const unsigned long long *__restrict__ tkey, const unsigned char *__restrict__ tm,
+					      const unsigned short *__restrict__ tl, const G2TopTree *__restrict__ tt,
+					      const unsigned int *__restrict__ tbase, unsigned int a, unsigned int b, int d,
+					      int self_code, int *__restrict__ suns, int *__restrict__ c_father, int *__restrict__ p_parent,
+					      int &nchild, int &npart)
+{
+  nchild = 0;
+  npart = 0;
+#pragma unroll
+  for(int s = 0; s < 8; s++)
+    suns[s] = -1;
+  unsigned int pos = a;
+  while(pos <= b)
+    {
+      unsigned int slot = digit_at(tkey[pos], d + 1);
+      unsigned int e = run_end(tkey, pos, b, d + 1);
+      if(e == pos)
+	{
+	  suns[slot] = (int) pos;
+	  p_parent[pos] = self_code;
+	  npart++;
+	}
+      else
+	{
+	  unsigned int cc = tbase[pos] + (unsigned int) ((d + 1) - first_depth(tm, tl, tt, (int) pos));
+	  suns[slot] = -((int) cc + 2);
+	  c_father[cc] = self_code;
+	  nchild++;
+	}
+      pos = e + 1;
+    }
+}
+
+// father / p_parent codes: >= 0 regular cell id, <= -2 top node k = -(code+2)
+__global__ void __launch_bounds__(128) topdown_kernel(const unsigned long long *__restrict__ tkey, const unsigned char *__restrict__ tm,
+						      const unsigned short *__restrict__ tl, const G2TopTree *__restrict__ tt,
+						      const unsigned int *__restrict__ tbase, int n, int max_cells,
+						      const unsigned int *__restrict__ c_a, const unsigned char *__restrict__ c_d,
+						      unsigned int *__restrict__ c_b, int *__restrict__ c_suns, int *__restrict__ c_father,
+						      int *__restrict__ p_parent, unsigned char *__restrict__ c_nchild,
+						      unsigned char *__restrict__ c_npart, unsigned int *__restrict__ u_npart)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int ncells = (int) tbase[n];
+  if(c >= ncells || c >= max_cells)
+    return;
+  unsigned int a = c_a[c];
+  int d = c_d[c];
+  unsigned int b = run_end(tkey, a, (unsigned int) (n - 1), d);
+  c_b[c] = b;
+  int suns[8], nchild, npart;
+  find_children(tkey, tm, tl, tt, tbase, a, b, d, c, suns, c_father, p_parent, nchild, npart);
+#pragma unroll
+  for(int s = 0; s < 8; s++)
+    c_suns[8 * (size_t) c + s] = suns[s];
+  c_nchild[c] = (unsigned char) nchild;
+  c_npart[c] = (unsigned char) npart;
+  int U = c + tt->fdfs[tl[a]] + 1;
+  u_npart[U] = (unsigned int) npart;
+}
+
+// top-level nodes: particle range, children of top leaves, U index
+__global__ void __launch_bounds__(128) top_children_kernel(const unsigned long long *__restrict__ tkey, const unsigned char *__restrict__ tm,
+							   const unsigned short *__restrict__ tl, const G2TopTree *__restrict__ tt,
+							   const unsigned int *__restrict__ tbase, int n, int *__restrict__ t_suns,
+							   int *__restrict__ c_father, int *__restrict__ p_parent, unsigned int *__restrict__ t_first,
+							   unsigned int *__restrict__ t_last, unsigned char *__restrict__ t_nchild,
+							   unsigned char *__restrict__ t_npart, unsigned int *__restrict__ t_u,
+							   unsigned int *__restrict__ u_npart)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= tt->ntopnodes)
+    return;
+  int t = tt->fdepth[k];
+  // positions whose key starts with this node's slot path
+  unsigned long long lo_key = t == 0 ? 0ull : (tt->fmorton[k] << (3 * (G2_MAXDEPTH - t)));
+  unsigned long long hi_key = t == 0 ? (1ull << KEYBITS) : ((tt->fmorton[k] + 1ull) << (3 * (G2_MAXDEPTH - t)));
+  unsigned int lo = 0, hi = (unsigned int) n;
+  while(lo < hi)
+    {
+      unsigned int mid = (lo + hi) >> 1;
+      if(tkey[mid] < lo_key)
+	lo = mid + 1;
+      else
+	hi = mid;
+    }
+  unsigned int first = lo;
+  hi = (unsigned int) n;
+  while(lo < hi)
+    {
+      unsigned int mid = (lo + hi) >> 1;
+      if(tkey[mid] < hi_key)
+	lo = mid + 1;
+      else
+	hi = mid;
+    }
+  unsigned int end = lo;	// one past the last
+  t_first[k] = first;
+  t_last[k] = end;		// exclusive end
+  unsigned int U = (unsigned int) tt->fdfs[k] + tbase[first];
+  t_u[k] = U;
+  int nchild = 0, npart = 0;
+  int suns[8];
+#pragma unroll
+  for(int s = 0; s < 8; s++)
+    suns[s] = -1;
+  if(tt->fisleaf[k] && end > first)
+    find_children(tkey, tm, tl, tt, tbase, first, end - 1, t, -(k + 2), suns, c_father, p_parent, nchild, npart);
+#pragma unroll
+  for(int s = 0; s < 8; s++)
+    t_suns[8 * k + s] = suns[s];
+  t_nchild[k] = (unsigned char) nchild;
+  t_npart[k] = (unsigned char) npart;
+  u_npart[U] = (unsigned int) npart;
+}
+
+// ---------------------------------------------------------------- 4. moments, bottom-up ------------------------
+// Walk record of a cell, (2+D) float4, index U (depth-first order):
+//   [0]       len, center x, y, z                        (struct NODE len, center; allvars.h:620-621)
+//   [1+g]     s[0][g], s[1][g], s[2][g], mass[g]         (u.d.s, u.d.mass; allvars.h:642-643)
+//   [1+D]     as uint: sibling U | particle offset | pinfo | flags
+//             pinfo = count (4 bits) | type of direct particle j at bits 4+3j
+//             flags = maxsofttype<<2 | diffsoft<<5 (u.d.bitflags layout, forcetree.c:706) | 1<<8 if top-level
+template <int D>
+struct Moments
+{
+  double mass[D], sx[D], sy[D], sz[D];
+  int maxsofttype, diffsoft;
+  unsigned int min1, min2;
+};
+
+template <int D>
+__device__ __forceinline__ void mom_init(Moments<D> &M)
+{
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    M.mass[g] = M.sx[g] = M.sy[g] = M.sz[g] = 0.0;
+  M.maxsofttype = 7;
+  M.diffsoft = 0;
+  M.min1 = M.min2 = 0xffffffffu;
+}
+
+__device__ __forceinline__ void min2_insert(unsigned int &m1, unsigned int &m2, unsigned int v)
+{
+  if(v < m1)
+    {
+      m2 = m1;
+      m1 = v;
+    }
+  else if(v < m2)
+    m2 = v;
+}
+
+// forcetree.c:571-597 / 629-646: running (maxsofttype, diffsoftflag) update with one more type
+__device__ __forceinline__ void soft_update(int &maxsofttype, int &diffsoft, int type, const G2Soft &S)
+{
+  if(maxsofttype == 7)
+    maxsofttype = type;
+  else if(type != 7)
+    {
+      if(S.fsoft[type] > S.fsoft[maxsofttype])
+	{
+	  maxsofttype = type;
+	  diffsoft = 1;
+	}
+      else if(S.fsoft[type] < S.fsoft[maxsofttype])
+	diffsoft = 1;
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void mom_add_particle(Moments<D> &M, float4 p, int type, unsigned int idx, const G2Soft &S)
+{
+  int g = S.t2g[type];
+  double m = (double) p.w;
+#pragma unroll
+  for(int gg = 0; gg < D; gg++)
+    if(gg == g)
+      {
+	M.mass[gg] = __dadd_rn(M.mass[gg], m);
+	M.sx[gg] = __dadd_rn(M.sx[gg], __dmul_rn(m, (double) p.x));
+	M.sy[gg] = __dadd_rn(M.sy[gg], __dmul_rn(m, (double) p.y));
+	M.sz[gg] = __dadd_rn(M.sz[gg], __dmul_rn(m, (double) p.z));
+      }
+  if(S.unequal)
+    soft_update(M.maxsofttype, M.diffsoft, type, S);
+  min2_insert(M.min1, M.min2, idx);
+}
+
+template <int D>
+__device__ __forceinline__ void mom_add_cell(Moments<D> &M, const float4 *__restrict__ rec, unsigned int cmin1, unsigned int cmin2,
+					     const G2Soft &S)
+{
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    {
+      float4 q = __ldcg(&rec[1 + g]);
+      double m = (double) q.w;
+      M.mass[g] = __dadd_rn(M.mass[g], m);
+      M.sx[g] = __dadd_rn(M.sx[g], __dmul_rn(m, (double) q.x));
+      M.sy[g] = __dadd_rn(M.sy[g], __dmul_rn(m, (double) q.y));
+      M.sz[g] = __dadd_rn(M.sz[g], __dmul_rn(m, (double) q.z));
+    }
+  if(S.unequal)
+    {
+      uint4 w = __ldcg((const uint4 *) &rec[1 + D]);
+      int ctype = (w.w >> 2) & 7;
+      M.diffsoft |= (w.w >> 5) & 1;	// forcetree.c:571
+      if(M.maxsofttype == 7)
+	M.maxsofttype = ctype;
+      else if(ctype != 7)
+	{
+	  if(S.fsoft[ctype] > S.fsoft[M.maxsofttype])
+	    {
+	      M.maxsofttype = ctype;
+	      M.diffsoft = 1;
+	    }
+	  else if(S.fsoft[ctype] < S.fsoft[M.maxsofttype])
+	    M.diffsoft = 1;
+	}
+    }
+  min2_insert(M.min1, M.min2, cmin1);
+  min2_insert(M.min1, M.min2, cmin2);
+}
+
+template <int D>
+__device__ __forceinline__ void mom_store(const Moments<D> &M, float4 *__restrict__ rec, float len, float cx, float cy, float cz,
+					  unsigned int sibU, unsigned int poff, unsigned int pinfo, unsigned int extra_flags,
+					  const G2Soft &S)
+{
+  rec[0] = make_float4(len, cx, cy, cz);
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    {
+      float4 q;
+      if(M.mass[g] > 0)
+	{			// forcetree.c:667-677
+	  q.x = (float) __ddiv_rn(M.sx[g], M.mass[g]);
+	  q.y = (float) __ddiv_rn(M.sy[g], M.mass[g]);
+	  q.z = (float) __ddiv_rn(M.sz[g], M.mass[g]);
+	}
+      else
+	{			// forcetree.c:678-683: empty species sits at the geometric centre
+	  q.x = cx;
+	  q.y = cy;
+	  q.z = cz;
+	}
+      q.w = (float) M.mass[g];
+      rec[1 + g] = q;
+    }
+  unsigned int flags = S.unequal ? (unsigned int) (4 * M.maxsofttype + 32 * M.diffsoft) : 0u;
+  uint4 w = make_uint4(sibU, poff, pinfo, flags | extra_flags);
+  *((uint4 *) &rec[1 + D]) = w;
+}
+
+struct BuildArrays
+{
+  const unsigned long long *tkey;
+  const unsigned int *tq;
+  const unsigned short *tl;
+  const unsigned int *tbase;
+  const float4 *pm;
+  const unsigned char *ptype;
+  const unsigned int *c_a, *c_b;
+  const unsigned char *c_d;
+  const int *c_suns, *c_father;
+  const unsigned char *c_nchild;
+  unsigned int *c_ready;
+  unsigned int *c_min1, *c_min2;
+  const int *t_suns;
+  const unsigned int *t_first, *t_last, *t_u;
+  const unsigned char *t_nchild;
+  unsigned int *t_ready;
+  unsigned int *t_min1, *t_min2;
+  const unsigned int *u_poff;	// exclusive scan of u_npart
+  float4 *wcells;
+  float4 *wpart;
+  int n;
+  int numnodes_cap;
+};
+
+// process one regular cell c; returns its father code
+template <int D>
+__device__ int process_cell(const BuildArrays &A, const G2TopTree *__restrict__ tt, const G2Soft &S, int c)
+{
+  const unsigned int a = A.c_a[c], b = A.c_b[c];
+  const int d = A.c_d[c];
+  const int leafk = A.tl[a];
+  const unsigned int U = (unsigned int) c + (unsigned int) tt->fdfs[leafk] + 1u;
+  // geometry from the top-level leaf down (forcetree.c:188-206)
+  float cx = tt->fcx[leafk], cy = tt->fcy[leafk], cz = tt->fcz[leafk], len = tt->flen[leafk];
+  const unsigned long long key = A.tkey[a];
+  for(int lvl = tt->fdepth[leafk] + 1; lvl <= d; lvl++)
+    descend(cx, cy, cz, len, digit_at(key, lvl));
+
+  Moments<D> M;
+  mom_init(M);
+  unsigned int poff = A.u_poff[U], pinfo = 0, np = 0;
+  for(int s = 0; s < 8; s++)	// slot order 0..7 (forcetree.c:526)
+    {
+      int v = A.c_suns[8 * (size_t) c + s];
+      if(v == -1)
+	continue;
+      if(v >= 0)
+	{
+	  unsigned int idx = A.tq[v];
+	  float4 p = A.pm[idx];
+	  int type = A.ptype[idx];
+	  mom_add_particle<D>(M, p, type, idx, S);
+	  A.wpart[poff + np] = p;
+	  pinfo |= (unsigned int) type << (4 + 3 * np);
+	  np++;
+	}
+      else
+	{
+	  int cc = -(v + 2);
+	  unsigned int Uc = (unsigned int) cc + (unsigned int) tt->fdfs[leafk] + 1u;
+	  mom_add_cell<D>(M, A.wcells + (size_t) Uc * (2 + D), __ldcg(&A.c_min1[cc]), __ldcg(&A.c_min2[cc]), S);
+	}
+    }
+  pinfo |= np;
+  unsigned int sibU = U + (A.tbase[b + 1] - (unsigned int) c);
+  mom_store<D>(M, A.wcells + (size_t) U * (2 + D), len, cx, cy, cz, sibU, poff, pinfo, 0u, S);
+  A.c_min1[c] = M.min1;
+  A.c_min2[c] = M.min2;
+  return A.c_father[c];
+}
+
+// process top-level node k
+template <int D>
+__device__ int process_top(const BuildArrays &A, const G2TopTree *__restrict__ tt, const G2Soft &S, int k)
+{
+  const unsigned int U = A.t_u[k];
+  Moments<D> M;
+  mom_init(M);
+  unsigned int poff = A.u_poff[U], pinfo = 0, np = 0;
+  const int isleaf = tt->fisleaf[k];
+  for(int s = 0; s < 8; s++)
+    {
+      if(isleaf)
+	{
+	  int v = A.t_suns[8 * k + s];
+	  if(v == -1)
+	    continue;
+	  if(v >= 0)
+	    {
+	      unsigned int idx = A.tq[v];
+	      float4 p = A.pm[idx];
+	      int type = A.ptype[idx];
+	      mom_add_particle<D>(M, p, type, idx, S);
+	      A.wpart[poff + np] = p;
+	      pinfo |= (unsigned int) type << (4 + 3 * np);
+	      np++;
+	    }
+	  else
+	    {
+	      int cc = -(v + 2);
+	      unsigned int Uc = (unsigned int) cc + (unsigned int) tt->fdfs[k] + 1u;
+	      mom_add_cell<D>(M, A.wcells + (size_t) Uc * (2 + D), __ldcg(&A.c_min1[cc]), __ldcg(&A.c_min2[cc]), S);
+	    }
+	}
+      else
+	{
+	  int ch = tt->fsuns[k][s];
+	  if(ch < 0)
+	    continue;
+	  mom_add_cell<D>(M, A.wcells + (size_t) A.t_u[ch] * (2 + D), __ldcg(&A.t_min1[ch]), __ldcg(&A.t_min2[ch]), S);
+	}
+    }
+  pinfo |= np;
+  // next top-level node in walk order that is not a descendant: skip this node's top subtree
+  unsigned int sibU;
+  {
+    // size of the top subtree = number of top nodes whose slot path starts with this node's path; they are
+    // contiguous in fdfs order, so find the end by scanning fdfs successors' depth
+    int r = tt->fdfs[k] + 1;
+    const int t = tt->fdepth[k];
+    while(r < tt->ntopnodes && tt->fdepth[tt->fdfs_inv[r]] > t)
+      r++;
+    sibU = (r < tt->ntopnodes) ? A.t_u[tt->fdfs_inv[r]] : (unsigned int) (tt->ntopnodes + (int) A.tbase[A.n]);
+  }
+  mom_store<D>(M, A.wcells + (size_t) U * (2 + D), tt->flen[k], tt->fcx[k], tt->fcy[k], tt->fcz[k], sibU, poff, pinfo, 1u << 8, S);
+  A.t_min1[k] = M.min1;
+  A.t_min2[k] = M.min2;
+  return tt->ffather[k] >= 0 ? -(tt->ffather[k] + 2) : -1;
+}
+
+// One thread per node; only nodes without child cells start, the last child to arrive continues with the father
+// (every cell is processed exactly once, after all its children).
+template <int D>
+__global__ void __launch_bounds__(128) bottomup_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, G2Soft S)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncells = (int) A.tbase[A.n];
+  const int ntop = tt->ntopnodes;
+  int code;			// >= 0 regular cell, <= -2 top node
+  if(tid < ncells)
+    {
+      if(A.c_nchild[tid] != 0)
+	return;
+      code = tid;
+    }
+  else if(tid < ncells + ntop)
+    {
+      int k = tid - ncells;
+      if(!(tt->fisleaf[k] && A.t_nchild[k] == 0))
+	return;
+      code = -(k + 2);
+    }
+  else
+    return;
+
+  while(true)
+    {
+      int father = code >= 0 ? process_cell<D>(A, tt, S, code) : process_top<D>(A, tt, S, -(code + 2));
+      if(father == -1)
+	break;			// root done
+      __threadfence();
+      unsigned int need, old;
+      if(father >= 0)
+	{
+	  need = A.c_nchild[father];
+	  old = atomicAdd(&A.c_ready[father], 1u);
+	}
+      else
+	{
+	  int fk = -(father + 2);
+	  need = tt->fisleaf[fk] ? (unsigned int) A.t_nchild[fk] : 8u;
+	  old = atomicAdd(&A.t_ready[fk], 1u);
+	}
+      if(old + 1u < need)
+	break;
+      __threadfence();
+      code = father;
+    }
+}
+
+// ---------------------------------------------------------------- 5. reference numbering -----------------------
+// The reference creates the internal nodes of one insertion (particle i meeting particle j < i) as a chain of
+// consecutive depths; these are exactly the cells whose second-smallest particle index is i (forcetree.c:183-247).
+// Node number = NTopnodes + #cells with smaller second-min + (depth - shallowest depth of the chain).
+__global__ void __launch_bounds__(256) renum_hist_kernel(const unsigned int *__restrict__ c_min2, const unsigned char *__restrict__ c_d,
+							 const unsigned int *__restrict__ tbase, int n, unsigned int *__restrict__ hist,
+							 unsigned int *__restrict__ dmin)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if(c >= (int) tbase[n])
+    return;
+  unsigned int i2 = c_min2[c];
+  atomicAdd(&hist[i2], 1u);
+  atomicMin(&dmin[i2], (unsigned int) c_d[c]);
+}
+
+__global__ void __launch_bounds__(256) renum_assign_kernel(const unsigned int *__restrict__ c_min2, const unsigned char *__restrict__ c_d,
+							   const unsigned int *__restrict__ tbase, int n, const unsigned int *__restrict__ hscan,
+							   const unsigned int *__restrict__ dmin, int ntop, unsigned int *__restrict__ c_refid)
+{
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if(c >= (int) tbase[n])
+    return;
+  unsigned int i2 = c_min2[c];
+  c_refid[c] = (unsigned int) ntop + hscan[i2] + ((unsigned int) c_d[c] - dmin[i2]);
+}
+
+__global__ void fill_u32_kernel(unsigned int *p, unsigned int v, size_t n)
+{
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+    p[i] = v;
+}
+
+// ---------------------------------------------------------------- 6. export in the reference's form -------------
+struct ExportArrays
+{
+  float *len, *center, *s, *mass;
+  int *bitflags, *sibling, *nextnode, *father, *p_nextnode, *p_father;
+};
+
+// reference index (MaxPart-relative node number, or particle index) of the DFS successor of sorted position b's
+// subtree end: the node visited after everything up to and including position b, given b ends a subtree whose
+// enclosing cell has depth tm[b] (forcetree.c:499-512 `nextsib`).  Returns node numbers offset by maxpart.
+__device__ int successor_after(const BuildArrays &A, const unsigned char *__restrict__ tm, const G2TopTree *__restrict__ tt,
+			       const unsigned int *__restrict__ c_refid, const int *__restrict__ top_sibling, int maxpart, unsigned int b)
+{
+  unsigned char m = tm[b];
+  if(m == 255)
+    return top_sibling[A.tl[b]];	// last particle of its top-level leaf: continue after that leaf
+  // the child of the depth-m cell that starts at b+1 has depth m+1
+  unsigned char m2 = tm[b + 1];
+  if(m2 != 255 && (int) m2 >= (int) m + 1)
+    return maxpart + (int) c_refid[A.tbase[b + 1]];	// a cell: first cell owned by pair b+1
+  return (int) A.tq[b + 1];	// a single particle
+}
+
+// reference-style sibling / nextnode of every top-level node (small, one thread)
+__global__ void export_top_links_kernel(BuildArrays A, const unsigned char *__restrict__ tm, const G2TopTree *__restrict__ tt,
+					const unsigned int *__restrict__ c_refid, int maxpart, int *__restrict__ top_sibling,
+					int *__restrict__ top_nextnode)
+{
+  if(threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  const int ntop = tt->ntopnodes;
+  // sibling: next existing slot under the father, else the father's sibling (root: -1); fdfs order guarantees
+  // fathers come first
+  for(int r = 0; r < ntop; r++)
+    {
+      int k = tt->fdfs_inv[r];
+      int f = tt->ffather[k];
+      int sib = -1;
+      if(f >= 0)
+	{
+	  int myslot = (int) (tt->fmorton[k] & 7ull);
+	  sib = top_sibling[f];
+	  for(int s = myslot + 1; s < 8; s++)
+	    if(tt->fsuns[f][s] >= 0)
+	      {
+		sib = maxpart + tt->fsuns[f][s];
+		break;
+	      }
+	}
+      top_sibling[k] = sib;
+    }
+  for(int k = 0; k < ntop; k++)
+    {
+      int nx;
+      if(!tt->fisleaf[k])
+	{
+	  nx = -1;
+	  for(int s = 0; s < 8; s++)
+	    if(tt->fsuns[k][s] >= 0)
+	      {
+		nx = maxpart + tt->fsuns[k][s];
+		break;
+	      }
+	}
+      else
+	{
+	  unsigned int first = A.t_first[k], end = A.t_last[k];
+	  if(end <= first)
+	    nx = top_sibling[k];	// empty leaf: the next node visited is its successor
+	  else
+	    {
+	      unsigned char m = tm[first];
+	      if(m != 255 && (int) m >= tt->fdepth[k] + 1)
+		nx = maxpart + (int) c_refid[A.tbase[first]];
+	      else
+		nx = (int) A.tq[first];
+	    }
+	}
+      top_nextnode[k] = nx;
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) export_kernel(BuildArrays A, const unsigned char *__restrict__ tm, const G2TopTree *__restrict__ tt,
+						     const unsigned int *__restrict__ c_refid, const int *__restrict__ p_parent,
+						     const int *__restrict__ top_sibling, const int *__restrict__ top_nextnode, int maxpart,
+						     ExportArrays E)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncells = (int) A.tbase[A.n];
+  const int ntop = tt->ntopnodes;
+  if(tid < ncells + ntop)
+    {
+      int ref, sib, nxt, fat;
+      unsigned int U;
+      unsigned int extra = 0;
+      if(tid < ncells)
+	{
+	  int c = tid;
+	  ref = (int) c_refid[c];
+	  unsigned int a = A.c_a[c], b = A.c_b[c];
+	  int d = A.c_d[c];
+	  U = (unsigned int) c + (unsigned int) tt->fdfs[A.tl[a]] + 1u;
+	  sib = successor_after(A, tm, tt, c_refid, top_sibling, maxpart, b);
+	  unsigned char m = tm[a];
+	  if(m != 255 && (int) m >= d + 1)
+	    nxt = maxpart + (int) c_refid[c + 1];	// first child is the next cell of the same chain
+	  else
+	    nxt = (int) A.tq[a];
+	  int fc = A.c_father[c];
+	  fat = fc >= 0 ? maxpart + (int) c_refid[fc] : maxpart + (-(fc + 2));
+	}
+      else
+	{
+	  int k = tid - ncells;
+	  ref = k;
+	  U = A.t_u[k];
+	  sib = top_sibling[k];
+	  nxt = top_nextnode[k];
+	  fat = tt->ffather[k] >= 0 ? maxpart + tt->ffather[k] : -1;
+	  extra = 3;		// force_flag_localnodes (forcetree.c:954-996): bits 0,1 on every top-level node
+	}
+      const float4 *rec = A.wcells + (size_t) U * (2 + D);
+      float4 q0 = rec[0];
+      if(E.len)
+	E.len[ref] = q0.x;
+      if(E.center)
+	{
+	  E.center[3 * (size_t) ref + 0] = q0.y;
+	  E.center[3 * (size_t) ref + 1] = q0.z;
+	  E.center[3 * (size_t) ref + 2] = q0.w;
+	}
+      for(int g = 0; g < D; g++)
+	{
+	  float4 q = rec[1 + g];
+	  if(E.s)
+	    {
+	      E.s[(3 * (size_t) ref + 0) * D + g] = q.x;
+	      E.s[(3 * (size_t) ref + 1) * D + g] = q.y;
+	      E.s[(3 * (size_t) ref + 2) * D + g] = q.z;
+	    }
+	  if(E.mass)
+	    E.mass[(size_t) ref * D + g] = q.w;
+	}
+      uint4 w = *((const uint4 *) &rec[1 + D]);
+      if(E.bitflags)
+	E.bitflags[ref] = (int) ((w.w & 0xfcu) | extra);
+      if(E.sibling)
+	E.sibling[ref] = sib;
+      if(E.nextnode)
+	E.nextnode[ref] = nxt;
+      if(E.father)
+	E.father[ref] = fat;
+    }
+  else if(tid < ncells + ntop + A.n)
+    {
+      unsigned int p = (unsigned int) (tid - ncells - ntop);
+      unsigned int idx = A.tq[p];
+      if(E.p_father)
+	{
+	  int pc = p_parent[p];
+	  E.p_father[idx] = pc >= 0 ? maxpart + (int) c_refid[pc] : maxpart + (-(pc + 2));
+	}
+      if(E.p_nextnode)
+	{
+	  // a particle is a subtree of its own: successor at depth max(tm[p-1], tm[p]) ... use the right neighbour
+	  // rule: the enclosing cell that ends at p has depth tm[p] (common levels with p+1)
+	  E.p_nextnode[idx] = successor_after(A, tm, tt, c_refid, top_sibling, maxpart, p);
+	}
+    }
+}
+
+// ---------------------------------------------------------------- stage drivers -------------------------------
+static G2Soft make_soft(const g2gpu_ctx *c)
+{
+  G2Soft S;
+  for(int t = 0; t < 6; t++)
+    {
+      S.t2g[t] = c->type_to_grav[t];
+      S.fsoft[t] = c->force_softening[t];
+    }
+  S.unequal = c->cfg.unequal_softenings;
+  return S;
+}
+
+static BuildArrays make_arrays(g2gpu_ctx *c)
+{
+  BuildArrays A;
+  A.tkey = c->tkey; A.tq = c->tq; A.tl = c->ttl; A.tbase = c->tbase; A.pm = c->pm; A.ptype = c->ptype;
+  A.c_a = c->c_a; A.c_b = c->c_b; A.c_d = c->c_d; A.c_suns = c->c_suns; A.c_father = c->c_father;
+  A.c_nchild = c->c_nchild; A.c_ready = c->c_ready; A.c_min1 = c->c_min1; A.c_min2 = c->c_min2;
+  A.t_suns = c->t_suns; A.t_first = c->t_first; A.t_last = c->t_last; A.t_u = c->t_ubase; A.t_nchild = c->t_nchild;
+  A.t_ready = c->t_ready; A.t_min1 = c->t_min1; A.t_min2 = c->t_min2; A.u_poff = c->c_poff;
+  A.wcells = c->wcells; A.wpart = c->wpart; A.n = c->npart; A.numnodes_cap = c->cfg.max_nodes;
+  return A;
+}
+
+int g2_stage_treebuild(g2gpu_ctx *c)
+{
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "treebuild: g2gpu_domain has not run");
+  const int n = c->npart;
+  const int maxcells = c->cfg.max_nodes;
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaEventRecord(c->ev[4], st));
+  G2_CUDA(cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), st));
+
+  // 1. keys + sort (keys live in the sort ping-pong buffers)
+  unsigned short *ptl = (unsigned short *) c->w_flags;	// per-particle top node, scratch reuse (n * 2 bytes)
+  treekey_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->pm, c->phkey, n, c->d_top, c->skey[0], c->sval[0], ptl);
+  c->launches++;
+  unsigned long long *k = c->skey[0];
+  unsigned int *v = c->sval[0];
+  G2_TRY(g2_radix_sort_pairs(c, n, &k, &v, c->skey[1], c->sval[1], 0, KEYBITS));
+  c->tkey = k;
+  c->tq = v;
+
+  // 2-3. cells
+  pair_depth_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tkey, c->tq, ptl, n, c->tm, c->ttl, c->d_err);
+  cell_count_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tm, c->ttl, c->d_top, n, c->tcnt);
+  c->launches += 2;
+  G2_TRY(g2_scan_exclusive_u32(c, c->tcnt, c->tbase, (size_t) n));
+  cell_init_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tm, c->ttl, c->d_top, c->tbase, n, maxcells, c->c_a, c->c_d, c->d_err);
+  c->launches++;
+
+  // the cell count is needed on the host for grid sizes and the MaxNodes check (forcetree.c:249-255)
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[4], c->tbase + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[5], &c->d_top->ntopnodes, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[0], c->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaStreamSynchronize(st));
+  if(c->h_err[7])
+    return g2_fail(G2GPU_ERR_TOPNODES, "top-level tree exceeds %d nodes", G2_MAXTOP);
+  if(c->h_err[0])
+    return g2_fail(G2GPU_ERR_TREE_DEPTH, "two particles share all %d octree levels (coincident particles?)", G2_MAXDEPTH);
+  c->ncells = c->h_err[4];
+  const int ntop = c->h_err[5];
+  c->numnodes = ntop + c->ncells;
+  if(c->h_err[1] || c->numnodes >= c->cfg.max_nodes)
+    return g2_fail(G2GPU_ERR_MAXNODES, "maximum number %d of tree-nodes reached (need %d)", c->cfg.max_nodes, c->numnodes);
+  const int ncells = c->ncells;
+  const int numnodes = c->numnodes;
+
+  // 4. children, particle groups
+  G2_CUDA(cudaMemsetAsync(c->c_ready, 0, sizeof(unsigned int) * (size_t) (ncells + 1), st));
+  G2_CUDA(cudaMemsetAsync(c->t_ready, 0, sizeof(unsigned int) * G2_MAXTOP, st));
+  if(ncells > 0)
+    topdown_kernel<<<g2_cdiv(ncells, 128), 128, 0, st>>>(c->tkey, c->tm, c->ttl, c->d_top, c->tbase, n, maxcells, c->c_a, c->c_d, c->c_b,
+							  c->c_suns, c->c_father, c->p_parent, c->c_nchild, c->c_npart, c->tcnt);
+  top_children_kernel<<<g2_cdiv(ntop, 128), 128, 0, st>>>(c->tkey, c->tm, c->ttl, c->d_top, c->tbase, n, c->t_suns, c->c_father, c->p_parent,
+							   c->t_first, c->t_last, c->t_nchild, c->t_npart, c->t_ubase, c->tcnt);
+  c->launches += 2;
+  G2_TRY(g2_scan_exclusive_u32(c, c->tcnt, c->c_poff, (size_t) numnodes));
+
+  // 5. moments
+  BuildArrays A = make_arrays(c);
+  G2Soft S = make_soft(c);
+  const int nthreads = ncells + ntop;
+  const int grid = g2_cdiv(nthreads, 128);
+  switch (c->D)
+    {
+    case 1: bottomup_kernel<1><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    case 2: bottomup_kernel<2><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    case 3: bottomup_kernel<3><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    case 4: bottomup_kernel<4><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    case 5: bottomup_kernel<5><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    case 6: bottomup_kernel<6><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
+    default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", c->D);
+    }
+  c->launches++;
+  G2_CUDA(cudaEventRecord(c->ev[5], st));
+  G2_CUDA(cudaGetLastError());
+  c->renumbered = 0;
+  c->stage = 3;
+  return 0;
+}
+
+int g2_stage_renumber(g2gpu_ctx *c)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "tree has not been built");
+  if(c->renumbered)
+    return 0;
+  const int n = c->npart, ncells = c->ncells;
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaMemsetAsync(c->hist2, 0, sizeof(unsigned int) * (size_t) (n + 1), st));
+  fill_u32_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->dmin, 0xffffffffu, (size_t) n);
+  c->launches++;
+  if(ncells > 0)
+    {
+      renum_hist_kernel<<<g2_cdiv(ncells, 256), 256, 0, st>>>(c->c_min2, c->c_d, c->tbase, n, c->hist2, c->dmin);
+      c->launches++;
+    }
+  G2_TRY(g2_scan_exclusive_u32(c, c->hist2, c->hist2_scan, (size_t) n));
+  if(ncells > 0)
+    {
+      renum_assign_kernel<<<g2_cdiv(ncells, 256), 256, 0, st>>>(c->c_min2, c->c_d, c->tbase, n, c->hist2_scan, c->dmin,
+								 c->numnodes - ncells, c->c_refid);
+      c->launches++;
+    }
+  G2_CUDA(cudaGetLastError());
+  c->renumbered = 1;
+  return 0;
+}
+
+template <typename T>
+static int dl(g2gpu_ctx *c, T *host, const T *dev, size_t count)
+{
+  if(host)
+    G2_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, c->stream));
+  return 0;
+}
+
+int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling, int *nextnode,
+		   int *father, int *p_nextnode, int *p_father)
+{
+  G2_TRY(g2_stage_renumber(c));
+  const int n = c->npart, nn = c->numnodes, D = c->D, ntop = nn - c->ncells;
+  cudaStream_t st = c->stream;
+  // device staging
+  size_t fbytes = sizeof(float) * (size_t) nn * (4 + 4 * (size_t) D);
+  size_t ibytes = sizeof(int) * ((size_t) nn * 4 + (size_t) n * 2 + 2 * G2_MAXTOP);
+  char *buf;
+  G2_CUDA(cudaMalloc(&buf, fbytes + ibytes));
+  ExportArrays E;
+  E.len = (float *) buf;
+  E.center = E.len + nn;
+  E.s = E.center + 3 * (size_t) nn;
+  E.mass = E.s + 3 * (size_t) nn * D;
+  E.bitflags = (int *) (buf + fbytes);
+  E.sibling = E.bitflags + nn;
+  E.nextnode = E.sibling + nn;
+  E.father = E.nextnode + nn;
+  E.p_nextnode = E.father + nn;
+  E.p_father = E.p_nextnode + n;
+  int *top_sibling = E.p_father + n;
+  int *top_nextnode = top_sibling + G2_MAXTOP;
+  BuildArrays A = make_arrays(c);
+  export_top_links_kernel<<<1, 32, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->cfg.max_part, top_sibling, top_nextnode);
+  int total = nn + n;
+  int grid = g2_cdiv(total, 128);
+  switch (D)
+    {
+    case 1: export_kernel<1><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 2: export_kernel<2><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 3: export_kernel<3><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 4: export_kernel<4><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 5: export_kernel<5><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 6: export_kernel<6><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    default: cudaFree(buf); return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
+    }
+  c->launches += 2;
+  (void) ntop;
+  int rc = 0;
+  rc |= dl(c, len, E.len, (size_t) nn);
+  rc |= dl(c, center, E.center, 3 * (size_t) nn);
+  rc |= dl(c, s, E.s, 3 * (size_t) nn * D);
+  rc |= dl(c, mass, E.mass, (size_t) nn * D);
+  rc |= dl(c, bitflags, E.bitflags, (size_t) nn);
+  rc |= dl(c, sibling, E.sibling, (size_t) nn);
+  rc |= dl(c, nextnode, E.nextnode, (size_t) nn);
+  rc |= dl(c, father, E.father, (size_t) nn);
+  rc |= dl(c, p_nextnode, E.p_nextnode, (size_t) n);
+  rc |= dl(c, p_father, E.p_father, (size_t) n);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if(rc)
+    return rc;
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "export: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -1,0 +1,194 @@
+// g2_common.cuh — shared declarations of the g2gpu CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/g2gpu.h"
+
+#define G2_MAXTOP 32768		// cap on top-level tree nodes held on the device (reference MAXTOPNODES = 200000)
+#define G2_MAXDEPTH 21		// 3*21 = 63 key bits: deepest supported octree level below the root
+#define G2_PH_BITS 18		// BITS_PER_DIMENSION (allvars.h:34)
+#define G2_NSM_FALLBACK 148
+
+extern char g2_errbuf[512];
+int g2_fail(int code, const char *fmt, ...);
+
+#define G2_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if(e__ != cudaSuccess)                                                                              \
+      return g2_fail(G2GPU_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+  } while(0)
+
+#define G2_TRY(call)                                                                                    \
+  do {                                                                                                  \
+    int r__ = (call);                                                                                   \
+    if(r__ != 0)                                                                                        \
+      return r__;                                                                                       \
+  } while(0)
+
+static inline int g2_cdiv(long long a, long long b) { return (int) ((a + b - 1) / b); }
+
+// ---- device copy of the top-level tree (domain.c TopNodes + forcetree.c top-level nodes) ----
+struct G2TopTree
+{
+  int ntopnodes;		// NTopnodes
+  int ntopleaves;		// NTopleaves
+  int err;			// != 0: overflow
+  int pad;
+  // TopNodes[] (allvars.h:252-262)
+  int daughter[G2_MAXTOP];
+  int leaf[G2_MAXTOP];
+  int shift[G2_MAXTOP];		// Size = 1 << shift  (Size is a power of 8)
+  long long startkey[G2_MAXTOP];
+  long long count[G2_MAXTOP];
+  // force-tree node created for each TopNode by force_create_empty_nodes (forcetree.c:292-336)
+  int fnode[G2_MAXTOP];		// reference node index - MaxPart (root = 0), indexed by TopNode
+  // indexed by force-tree top node number k (0..ntopnodes-1, creation order = reference numbering)
+  float flen[G2_MAXTOP];
+  float fcx[G2_MAXTOP], fcy[G2_MAXTOP], fcz[G2_MAXTOP];
+  int fdepth[G2_MAXTOP];	// depth below root
+  unsigned long long fmorton[G2_MAXTOP];	// slot digits from the root, 3 bits per level (depth digits)
+  int ffather[G2_MAXTOP];	// top node k's father (k index) or -1
+  int fsuns[G2_MAXTOP][8];	// children (k index) by spatial slot, -1 = none (leaf)
+  int fisleaf[G2_MAXTOP];	// 1 if it corresponds to a TopNodes leaf
+  int fdfs[G2_MAXTOP];		// rank of top node k in the slot-order DFS (walk order)
+  int fdfs_inv[G2_MAXTOP];	// inverse of fdfs
+  int dni[G2_MAXTOP];		// DomainNodeIndex[leaf] - MaxPart  (k index)
+};
+
+// ---- walk constants ----
+struct G2LawTable
+{
+  int accel[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  int spline[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  float par[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS][4];
+};
+
+struct g2gpu_ctx
+{
+  g2gpu_config cfg;
+  int D;			// n_gravs
+  int nsm;
+  cudaStream_t stream;
+  cudaEvent_t ev[16];
+
+  int npart;			// current particle count
+  int nactive;			// active particles (all ranks)
+  int stage;			// 0 created, 1 uploaded, 2 domain done, 3 tree built, 4 walked
+  int type_to_grav[6];
+  double force_softening[6];
+  G2LawTable laws;
+  int laws_set;
+  double *d_srtable;		// D*D*NTAB doubles
+  float *d_srtable_f;		// same as float
+  int srtable_set;
+  int sr_ntables;		// unique short-range tables (identical pair tables are stored once)
+  unsigned char sr_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  int acc_double;		// accumulate accelerations in FP64 (default) or FP32
+
+  // upload-order inputs
+  float4 *in_pm;
+  int *in_type;
+  float *in_oldacc;
+  float *in_vel;		// 3n, optional
+  float *in_gravpm;		// 3n, optional
+  unsigned char *in_active;
+  int have_vel, have_gravpm;
+
+  // current-order (species-major PH) particle arrays
+  float4 *pm;
+  unsigned char *ptype;
+  float *oldacc;
+  float *vel;
+  float *gravpm;
+  unsigned char *active;
+  long long *phkey;
+  int *perm;
+
+  // sort scratch (ping-pong)
+  unsigned long long *skey[2];
+  unsigned int *sval[2];
+  unsigned int *tilehist;	// NBINS * ntiles
+  size_t tilehist_elems;
+  unsigned int *scan_tmp;	// block sums for the device-wide scan
+  size_t scan_tmp_elems;
+
+  // domain
+  double *d_domain;		// corner[3], center[3], len, fac  (+ scratch)
+  float *d_minmax;		// 6 floats
+  G2TopTree *d_top;
+  void *d_topscratch;
+  G2TopTree *h_top;		// pinned host copy (filled on demand)
+  int *d_species_start;		// block boundaries in current order: D+2 ints (gas block, species blocks)
+
+  // tree (sorted-by-treekey order p)
+  unsigned long long *tkey;	// sorted tree keys
+  unsigned int *tq;		// particle index at sorted position p
+  unsigned char *tm;		// common depth of positions p,p+1 (levels from root), 255 = different top leaf
+  unsigned short *ttl;		// top-tree node k (force top node index) holding position p
+  unsigned int *tbase;		// exclusive scan of cells owned by pair p  (size n+1)
+  unsigned int *tcnt;
+  int ncells;			// regular (non-top) cells
+  int numnodes;			// ntopnodes + ncells
+  // per regular cell (provisional id c, DFS pre-order)
+  unsigned int *c_a, *c_b;	// sorted-position range [a,b]
+  unsigned char *c_d;		// depth
+  int *c_suns;			// 8 per cell: -1 none; >=0 particle sorted position; <= -2: cell id = -(v+2)
+  int *p_parent;		// per sorted position: parent code (same encoding as c_father)
+  int *c_father;		// provisional: >=0 regular cell id, <= -2: top node k = -(v+2)
+  unsigned int *c_ready;	// child-cell completion counters
+  unsigned char *c_nchild;	// number of child cells
+  unsigned char *c_npart;	// number of direct particle children
+  unsigned int *c_min1, *c_min2;	// smallest / second smallest particle index in the cell
+  unsigned int *c_poff;		// exclusive scan of c_npart (offset in the leaf-grouped particle array), incl. top nodes
+  unsigned int *c_refid;	// reference node number (k index, MaxPart-relative) of regular cell c
+  // top-node extras (size G2_MAXTOP)
+  int *t_suns;			// children of top LEAF nodes among regular cells/particles (8 per top node)
+  unsigned int *t_first, *t_last;	// sorted-position range of each top node's particles (first > last: empty)
+  unsigned int *t_min1, *t_min2;
+  unsigned int *t_ready;
+  unsigned char *t_npart, *t_nchild;
+  unsigned int *t_ubase;	// U index of top node k
+  // moments in provisional indexing (U order): the walk records
+  float4 *wcells;		// (2+D) float4 per cell, U order
+  float4 *wpart;		// leaf-grouped particle records
+  unsigned int *hist2, *hist2_scan;	// reference renumbering scratch (size n+1)
+  unsigned int *dmin;
+  int renumbered;
+  int *d_err;			// device error flags (4 ints)
+  int *h_err;			// pinned
+
+  // walk
+  unsigned int *w_targets;	// sorted positions of active targets (compacted)
+  unsigned int *w_flags;	// scratch for compaction
+  int w_ntargets;		// total active (all ranks)
+  int w_lo, w_hi;		// this rank's slice of w_targets
+  float *acc;			// 3n, current particle order
+  float *cost;			// n
+  float *oldacc_out;		// n
+  unsigned long long *d_counters;	// [0] sum cost, [1] node visits, [2] particle visits
+  unsigned long long *h_counters;
+
+  void *h_stage;		// pinned upload staging
+  size_t h_stage_bytes;
+  double ms[8];
+  long long launches;
+};
+
+// ---- cross-file entry points ----
+int g2_scan_exclusive_u32(g2gpu_ctx *c, const unsigned int *in, unsigned int *out, size_t n);
+int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io,
+			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit);
+int g2_stage_domain(g2gpu_ctx *c);
+int g2_stage_treebuild(g2gpu_ctx *c);
+int g2_stage_renumber(g2gpu_ctx *c);
+int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,
+		   int *nextnode, int *father, int *p_nextnode, int *p_father);
+int g2_peano_keys_standalone(g2gpu_ctx *c, int n, const int *xyz, int bits, long long *keys);
+int g2_eval_pairs_standalone(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r,
+			     const float *h, const int *nn, float *fac);
+
+#define G2_LAUNCH(c) ((c)->launches++)

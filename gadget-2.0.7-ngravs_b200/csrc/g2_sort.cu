@@ -1,0 +1,279 @@
+// g2_sort.cu — device-wide exclusive scan and stable LSD radix sort of (u64 key, u32 value) pairs.
+//
+// Replaces the reference's qsort() calls on the hot path: the Peano-Hilbert key sort of
+// domain_determineTopTree (domain.c:946) and the two-level (species, key) sort of peano_hilbert_order
+// (peano.c:100,124), and orders particles along the tree for the build.  HBM-bound integer work:
+// per pass  tile histogram (8 B/key read)  ->  scan of the bin-major tile histogram  ->  stable scatter
+// (12 B read + 12 B written per pair).  Digits are RADIX_BITS = 9 bits (512 bins) so that a 57..63-bit key
+// needs 7 passes.
+#include "g2_common.cuh"
+
+#define RADIX_BITS 9
+#define RADIX_BINS (1 << RADIX_BITS)
+#define SORT_THREADS 256
+#define SORT_ITEMS 16
+#define SORT_TILE (SORT_THREADS * SORT_ITEMS)	// 4096 pairs per CTA
+#define SORT_WARPS (SORT_THREADS / 32)
+
+// ------------------------------------------------------------------ exclusive scan (u32) -----------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v)
+{
+#pragma unroll
+  for(int o = 1; o < 32; o <<= 1)
+    {
+      unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      if((threadIdx.x & 31) >= o)
+	v += t;
+    }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ unsigned int block_excl_scan(unsigned int v, unsigned int *total, unsigned int *smem /* >= 33 */)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  unsigned int inc = warp_incl_scan(v);
+  if(lane == 31)
+    smem[warp] = inc;
+  __syncthreads();
+  if(warp == 0)
+    {
+      unsigned int w = (lane < nw) ? smem[lane] : 0;
+      unsigned int winc = warp_incl_scan(w);
+      smem[lane] = winc - w;
+      if(lane == 31)
+	smem[32] = winc;
+    }
+  __syncthreads();
+  unsigned int res = inc - v + smem[warp];
+  *total = smem[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const unsigned int *__restrict__ in, unsigned int *__restrict__ bsum, size_t n)
+{
+  __shared__ unsigned int sm[33];
+  size_t base = (size_t) blockIdx.x * SCAN_TILE;
+  unsigned int s = 0;
+#pragma unroll
+  for(int i = 0; i < SCAN_ITEMS; i++)
+    {
+      size_t idx = base + (size_t) i * SCAN_THREADS + threadIdx.x;
+      if(idx < n)
+	s += in[idx];
+    }
+  unsigned int tot;
+  block_excl_scan(s, &tot, sm);
+  if(threadIdx.x == 0)
+    bsum[blockIdx.x] = tot;
+}
+
+// single CTA: exclusive scan of nb block sums in place (nb arbitrary), writes grand total to bsum[nb]
+__global__ void __launch_bounds__(1024) scan_blocksums_kernel(unsigned int *bsum, int nb)
+{
+  __shared__ unsigned int sm[33];
+  __shared__ unsigned int carry;
+  if(threadIdx.x == 0)
+    carry = 0;
+  __syncthreads();
+  for(int start = 0; start < nb; start += 1024)
+    {
+      int i = start + threadIdx.x;
+      unsigned int v = (i < nb) ? bsum[i] : 0;
+      unsigned int tot;
+      unsigned int ex = block_excl_scan(v, &tot, sm);
+      unsigned int c = carry;
+      if(i < nb)
+	bsum[i] = ex + c;
+      __syncthreads();
+      if(threadIdx.x == 0)
+	carry = c + tot;
+      __syncthreads();
+    }
+  if(threadIdx.x == 0)
+    bsum[nb] = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned int *__restrict__ in, unsigned int *__restrict__ out,
+								   const unsigned int *__restrict__ bsum, size_t n, int nb)
+{
+  __shared__ unsigned int sm[33];
+  size_t base = (size_t) blockIdx.x * SCAN_TILE + (size_t) threadIdx.x * SCAN_ITEMS;	// blocked arrangement
+  unsigned int v[SCAN_ITEMS];
+  unsigned int s = 0;
+#pragma unroll
+  for(int i = 0; i < SCAN_ITEMS; i++)
+    {
+      size_t idx = base + i;
+      v[i] = (idx < n) ? in[idx] : 0;
+      s += v[i];
+    }
+  unsigned int tot;
+  unsigned int ex = block_excl_scan(s, &tot, sm) + bsum[blockIdx.x];
+#pragma unroll
+  for(int i = 0; i < SCAN_ITEMS; i++)
+    {
+      size_t idx = base + i;
+      if(idx < n)
+	out[idx] = ex;
+      ex += v[i];
+    }
+  // out[n] = grand total (callers allocate n+1)
+  if(blockIdx.x == nb - 1 && threadIdx.x == 0)
+    out[n] = bsum[nb];
+}
+
+// out has n+1 entries: out[i] = sum_{j<i} in[j], out[n] = total.  in == out is allowed.
+int g2_scan_exclusive_u32(g2gpu_ctx *c, const unsigned int *in, unsigned int *out, size_t n)
+{
+  if(n == 0)
+    {
+      G2_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned int), c->stream));
+      return 0;
+    }
+  int nb = g2_cdiv((long long) n, SCAN_TILE);
+  if((size_t) nb + 1 > c->scan_tmp_elems)
+    return g2_fail(G2GPU_ERR_ARG, "scan: %zu elements exceed scratch", n);
+  scan_reduce_kernel<<<nb, SCAN_THREADS, 0, c->stream>>>(in, c->scan_tmp, n);
+  scan_blocksums_kernel<<<1, 1024, 0, c->stream>>>(c->scan_tmp, nb);
+  scan_apply_kernel<<<nb, SCAN_THREADS, 0, c->stream>>>(in, out, c->scan_tmp, n, nb);
+  c->launches += 3;
+  G2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ radix sort ----------------------------
+__device__ __forceinline__ unsigned int digit_of(unsigned long long k, int shift, unsigned int mask)
+{
+  return (unsigned int) (k >> shift) & mask;
+}
+
+// per-tile digit histogram, stored bin-major: tilehist[bin * ntiles + tile]
+__global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const unsigned long long *__restrict__ keys, unsigned int *__restrict__ tilehist,
+								  int n, int ntiles, int shift, unsigned int mask)
+{
+  __shared__ unsigned int h[RADIX_BINS];
+  for(int i = threadIdx.x; i < RADIX_BINS; i += SORT_THREADS)
+    h[i] = 0;
+  __syncthreads();
+  const int tile = blockIdx.x;
+  const size_t base = (size_t) tile * SORT_TILE;
+#pragma unroll 4
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = base + (size_t) i * SORT_THREADS + threadIdx.x;
+      if(idx < (size_t) n)
+	atomicAdd(&h[digit_of(keys[idx], shift, mask)], 1u);
+    }
+  __syncthreads();
+  for(int i = threadIdx.x; i < RADIX_BINS; i += SORT_THREADS)
+    tilehist[(size_t) i * ntiles + tile] = h[i];
+}
+
+// stable scatter.  Element order inside a tile: warp w owns [w*512, (w+1)*512), iteration k takes 32
+// consecutive elements, so (warp, k, lane) is the input order.
+__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
+								     unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
+								     const unsigned int *__restrict__ tilescan, int n, int ntiles, int shift, unsigned int mask)
+{
+  __shared__ unsigned int wcnt[SORT_WARPS][RADIX_BINS];	// running per-warp digit counts -> warp offsets
+  __shared__ unsigned int gbase[RADIX_BINS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x;
+  for(int i = threadIdx.x; i < SORT_WARPS * RADIX_BINS; i += SORT_THREADS)
+    (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+
+  const size_t wbase = (size_t) tile * SORT_TILE + (size_t) warp * (32 * SORT_ITEMS);
+  unsigned long long k[SORT_ITEMS];
+  unsigned int r[SORT_ITEMS];
+  unsigned int d[SORT_ITEMS];
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      k[i] = (idx < (size_t) n) ? keys_in[idx] : ~0ull;
+    }
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      bool valid = idx < (size_t) n;
+      d[i] = valid ? digit_of(k[i], shift, mask) : RADIX_BINS;	// invalid lanes match only each other
+      unsigned int peers = __match_any_sync(0xffffffffu, d[i]);
+      unsigned int below = __popc(peers & ((1u << lane) - 1u));
+      unsigned int prev = 0;
+      int leader = __ffs(peers) - 1;
+      if(valid)
+	prev = wcnt[warp][d[i]];	// all peers read the same counter before the leader updates it
+      __syncwarp();
+      if(valid && lane == leader)
+	wcnt[warp][d[i]] = prev + __popc(peers);
+      __syncwarp();
+      r[i] = prev + below;
+    }
+  __syncthreads();
+  // exclusive scan over warps for every bin; fetch the global base of (bin, tile)
+  for(int b = threadIdx.x; b < RADIX_BINS; b += SORT_THREADS)
+    {
+      unsigned int run = 0;
+#pragma unroll
+      for(int w = 0; w < SORT_WARPS; w++)
+	{
+	  unsigned int t = wcnt[w][b];
+	  wcnt[w][b] = run;
+	  run += t;
+	}
+      gbase[b] = tilescan[(size_t) b * ntiles + tile];
+    }
+  __syncthreads();
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      if(idx < (size_t) n)
+	{
+	  unsigned int pos = gbase[d[i]] + wcnt[warp][d[i]] + r[i];
+	  keys_out[pos] = k[i];
+	  vals_out[pos] = vals_in[idx];
+	}
+    }
+}
+
+// Sorts n pairs by key bits [begin_bit, end_bit), stable.  *keys_io/*vals_io hold the input and are
+// updated to point at the buffers holding the result (ping-pong with keys_alt/vals_alt).
+int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io,
+			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit)
+{
+  if(n <= 1 || end_bit <= begin_bit)
+    return 0;
+  int ntiles = g2_cdiv(n, SORT_TILE);
+  if((size_t) ntiles * RADIX_BINS + 1 > c->tilehist_elems)
+    return g2_fail(G2GPU_ERR_ARG, "sort: %d pairs exceed scratch", n);
+  unsigned long long *kin = *keys_io, *kout = keys_alt;
+  unsigned int *vin = *vals_io, *vout = vals_alt;
+  int nbits = end_bit - begin_bit;
+  int npass = (nbits + RADIX_BITS - 1) / RADIX_BITS;
+  for(int p = 0; p < npass; p++)
+    {
+      int shift = begin_bit + p * RADIX_BITS;
+      int bits = end_bit - shift < RADIX_BITS ? end_bit - shift : RADIX_BITS;
+      unsigned int mask = (1u << bits) - 1u;
+      sort_hist_kernel<<<ntiles, SORT_THREADS, 0, c->stream>>>(kin, c->tilehist, n, ntiles, shift, mask);
+      c->launches++;
+      G2_TRY(g2_scan_exclusive_u32(c, c->tilehist, c->tilehist, (size_t) ntiles * RADIX_BINS));
+      sort_scatter_kernel<<<ntiles, SORT_THREADS, 0, c->stream>>>(kin, vin, kout, vout, c->tilehist, n, ntiles, shift, mask);
+      c->launches++;
+      unsigned long long *tk = kin; kin = kout; kout = tk;
+      unsigned int *tv = vin; vin = vout; vout = tv;
+    }
+  G2_CUDA(cudaGetLastError());
+  *keys_io = kin;
+  *vals_io = vin;
+  return 0;
+}

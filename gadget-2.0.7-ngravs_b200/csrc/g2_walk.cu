@@ -1,0 +1,487 @@
+// g2_walk.cu — stage 3: the tree walk of force_treeevaluate (forcetree.c:1244-1610) and
+// force_treeevaluate_shortrange (forcetree.c:1623-2052), with the gravity_tree epilogue (gravtree.c:304-358).
+//
+// One warp takes 32 targets that are adjacent along the tree order (hence in space) and walks the depth-first
+// cell array once for all of them: at every cell each lane takes ITS OWN decision (cull / accept / open) with the
+// reference's criteria; the warp descends if any lane opens (ballot), otherwise jumps to the cell's sibling.  A
+// lane that accepted or culled a cell sleeps until the warp's cursor has left that cell's subtree (cells are in
+// depth-first order, so this is one integer compare).  Direct particle children of an opened cell sit in a
+// contiguous group and are applied by the opening lanes only.  Per-lane interaction lists are therefore those of
+// the reference walk; only the summation order differs.
+//
+// Node records are (2+D) x 16 B, fetched with 128-bit loads (all lanes read the same address: one L1 broadcast).
+#include "g2_common.cuh"
+#include "g2_laws.cuh"
+
+#define WALK_THREADS 128
+#define WALK_WARPS (WALK_THREADS / 32)
+
+struct WalkArgs
+{
+  const float4 *__restrict__ cells;
+  const float4 *__restrict__ wpart;
+  const unsigned int *__restrict__ targets;	// sorted positions of active targets
+  const unsigned int *__restrict__ tq;		// particle index of a sorted position
+  const float4 *__restrict__ pm;
+  const unsigned char *__restrict__ ptype;
+  const float *__restrict__ oldacc;
+  const float *__restrict__ gravpm;
+  const float *__restrict__ srtable;		// unique tables, NTAB floats each
+  float *__restrict__ acc;
+  float *__restrict__ cost;
+  float *__restrict__ oldacc_out;
+  unsigned long long *__restrict__ counters;
+  unsigned int *__restrict__ work_counter;
+  int lo, hi;			// slice of targets
+  int numnodes;
+  int ntab;
+  int ntables;			// unique short-range tables held in shared memory
+  float theta2;			// ErrTolTheta^2, 0 => relative criterion
+  float errtol;			// ErrTolForceAcc
+  float boxsize, boxhalf;
+  float rcut, rcut2, asmthfac, utor2wpi;
+  double G, pos_fac_pre_g, pos_fac_post_g;
+  int use_gravpm;
+  float fsoft[6];
+  int t2g[6];
+  unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// [tgt*D+src] -> unique table
+  G2LawTable laws;
+};
+
+template <bool PERIODIC>
+__device__ __forceinline__ float nearest(float x, float boxsize, float boxhalf)
+{
+  if(PERIODIC)
+    {				// forcetree.c:43
+      if(x > boxhalf)
+	x -= boxsize;
+      else if(x < -boxhalf)
+	x += boxsize;
+    }
+  return x;
+}
+
+// one species term of an interaction: adds d*fac to the accumulators; returns whether it counted
+template <bool SR, bool STOCK, typename ACC>
+__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, int tg, int sg, int D, float pmass, float m, float dx,
+					  float dy, float dz, float r2, float h, ACC &ax, ACC &ay, ACC &az)
+{
+  float rinv = rsqrtf(fmaxf(r2, 1.0e-37f));
+  float r = r2 * rinv;
+  float fac;
+  if(SR)
+    {
+      int tabindex = (int) (A.asmthfac * r);	// forcetree.c:1962
+      if(tabindex >= A.ntab)
+	return false;
+      if(r >= h)
+	{
+	  float a = STOCK ? m * rinv * rinv : accel_over_r(A.laws.accel[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, r2, r, rinv, 1.0f) * r;
+	  float t = s_tab[(int) A.tabmap[tg * D + sg] * A.ntab + tabindex];
+	  fac = (a - m * A.utor2wpi * t) * rinv;	// forcetree.c:1972-1974
+	}
+      else
+	fac = STOCK ? law_plummer(m, h, r) : accel_spline(A.laws.spline[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, h, r, 1.0f);
+    }
+  else
+    {
+      if(r >= h)
+	fac = STOCK ? m * rinv * rinv * rinv : accel_over_r(A.laws.accel[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, r2, r, rinv, 1.0f);
+      else
+	fac = STOCK ? law_plummer(m, h, r) : accel_spline(A.laws.spline[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, h, r, 1.0f);
+    }
+  ax += (ACC) (dx * fac);
+  ay += (ACC) (dy * fac);
+  az += (ACC) (dz * fac);
+  return true;
+}
+
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
+{
+  extern __shared__ float s_tab[];
+  __shared__ unsigned int s_chunk[WALK_WARPS];
+  if(SR)
+    {
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
+	s_tab[i] = A.srtable[i];
+      __syncthreads();
+    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = 2 + D;
+  const int nchunks = (A.hi - A.lo + 31) >> 5;
+  unsigned long long tot_inter = 0, tot_visits = 0;
+
+  while(true)
+    {
+      // dynamic work distribution: one chunk of 32 consecutive targets per warp
+      if(lane == 0)
+	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+      __syncwarp();
+      const unsigned int chunk = s_chunk[warp];
+      __syncwarp();
+      if(chunk >= (unsigned int) nchunks)
+	break;
+      const int ti = A.lo + (int) chunk * 32 + lane;
+      const bool valid = ti < A.hi;
+      unsigned int idx = 0;
+      float px = 0, py = 0, pz = 0, pmass = 0, aold = 0;
+      int ptype = 1;
+      if(valid)
+	{
+	  idx = A.tq[A.targets[ti]];
+	  float4 p = A.pm[idx];
+	  px = p.x; py = p.y; pz = p.z; pmass = p.w;
+	  ptype = A.ptype[idx];
+	  aold = A.errtol * A.oldacc[idx];	// forcetree.c:1289
+	}
+      const int tg = A.t2g[ptype];
+      const float hself = A.fsoft[ptype];
+      ACC ax = 0, ay = 0, az = 0;
+      int ninter = 0;
+      unsigned int skip_until = valid ? 0u : 0xffffffffu;
+      unsigned int cur = 0;
+      const unsigned int end = (unsigned int) A.numnodes;
+
+      while(cur < end)
+	{
+	  const float4 *rec = A.cells + (size_t) cur * R;
+	  const float4 q0 = __ldg(rec);
+	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+	  bool open = false;
+	  if(cur >= skip_until)
+	    {
+	      float dx[D], dy[D], dz[D], r2[D], mass[D];
+	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
+#pragma unroll
+	      for(int g = 0; g < D; g++)
+		{
+		  const float4 q = __ldg(rec + 1 + g);
+		  mass[g] = q.w;
+		  summass += q.w;
+		  dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxhalf);
+		  dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxhalf);
+		  dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxhalf);
+		  r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
+		  r2min = fminf(r2min, r2[g]);
+		  r2max = fmaxf(r2max, r2[g]);
+		}
+	      const float len = q0.x;
+	      bool done = false;	// culled: skip the subtree without interaction
+	      if(SR)
+		{
+		  if(r2min > A.rcut2)
+		    {		// forcetree.c:1828-1862
+		      const float eff = A.rcut + 0.5f * len;
+		      float d0 = nearest<PERIODIC>(q0.y - px, A.boxsize, A.boxhalf);
+		      float d1 = nearest<PERIODIC>(q0.z - py, A.boxsize, A.boxhalf);
+		      float d2 = nearest<PERIODIC>(q0.w - pz, A.boxsize, A.boxhalf);
+		      if(d0 < -eff || d0 > eff || d1 < -eff || d1 > eff || d2 < -eff || d2 > eff)
+			done = true;
+		    }
+		}
+	      if(!done)
+		{
+		  if(A.theta2 > 0.0f)
+		    {		// Barnes-Hut, forcetree.c:1437-1445
+		      if(len * len > r2min * A.theta2)
+			open = true;
+		    }
+		  else
+		    {		// relative criterion, forcetree.c:1446-1472
+		      if(summass * len * len > r2min * r2min * aold)
+			open = true;
+		      else if(fabsf(q0.y - px) < 0.60f * len && fabsf(q0.z - py) < 0.60f * len && fabsf(q0.w - pz) < 0.60f * len)
+			open = true;
+		    }
+		}
+	      float h = hself;
+	      if(UNEQUAL && !done && !open)
+		{		// forcetree.c:1475-1501
+		  const int maxsofttype = (w.w >> 2) & 7;
+		  if(maxsofttype == 7)
+		    open = true;
+		  else if(h < A.fsoft[maxsofttype])
+		    {
+		      h = A.fsoft[maxsofttype];
+		      if(r2max < h * h && ((w.w >> 5) & 1))
+			open = true;
+		    }
+		}
+	      if(!open)
+		{
+		  skip_until = w.x;	// sleep until the cursor leaves this subtree
+		  if(!done)
+		    {
+		      bool any = false;
+#pragma unroll
+		      for(int g = 0; g < D; g++)
+			if(mass[g] != 0.0f)
+			  any |= pair_term<SR, STOCK, ACC>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, ax, ay, az);
+		      if(!SR || any)
+			ninter++;	// forcetree.c:1585 resp. 2031-2032
+		    }
+		}
+	    }
+	  tot_visits++;
+	  if(__any_sync(0xffffffffu, open))
+	    {
+	      // direct particle children of the opened cell, for the lanes that opened it
+	      const unsigned int np = w.z & 15u;
+	      for(unsigned int j = 0; j < np; j++)
+		{
+		  const float4 p = __ldg(A.wpart + w.y + j);
+		  if(open)
+		    {
+		      const int stype = (w.z >> (4 + 3 * j)) & 7;
+		      const int sg = A.t2g[stype];
+		      float h = hself;
+		      if(UNEQUAL)
+			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
+		      float ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxhalf);
+		      float ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxhalf);
+		      float ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxhalf);
+		      float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
+		      bool counted = pair_term<SR, STOCK, ACC>(A, s_tab, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, ax, ay, az);
+		      if(!SR || counted)
+			ninter++;
+		    }
+		}
+	      cur = cur + 1;
+	    }
+	  else
+	    cur = w.x;
+	}
+
+      if(valid)
+	{
+	  // gravity_tree epilogue: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
+	  float fx = (float) ax, fy = (float) ay, fz = (float) az;
+	  if(A.pos_fac_pre_g != 0.0)
+	    {
+	      fx = (float) ((double) fx + A.pos_fac_pre_g * (double) px);
+	      fy = (float) ((double) fy + A.pos_fac_pre_g * (double) py);
+	      fz = (float) ((double) fz + A.pos_fac_pre_g * (double) pz);
+	    }
+	  double sx = (double) fx, sy = (double) fy, sz = (double) fz;
+	  if(A.use_gravpm)
+	    {
+	      sx += (double) A.gravpm[3 * (size_t) idx + 0] / A.G;
+	      sy += (double) A.gravpm[3 * (size_t) idx + 1] / A.G;
+	      sz += (double) A.gravpm[3 * (size_t) idx + 2] / A.G;
+	    }
+	  A.oldacc_out[idx] = (float) sqrt(sx * sx + sy * sy + sz * sz);
+	  fx = (float) ((double) fx * A.G);
+	  fy = (float) ((double) fy * A.G);
+	  fz = (float) ((double) fz * A.G);
+	  if(A.pos_fac_post_g != 0.0)
+	    {
+	      fx = (float) ((double) fx + A.pos_fac_post_g * (double) px);
+	      fy = (float) ((double) fy + A.pos_fac_post_g * (double) py);
+	      fz = (float) ((double) fz + A.pos_fac_post_g * (double) pz);
+	    }
+	  A.acc[3 * (size_t) idx + 0] = fx;
+	  A.acc[3 * (size_t) idx + 1] = fy;
+	  A.acc[3 * (size_t) idx + 2] = fz;
+	  A.cost[idx] = (float) ninter;
+	  tot_inter += (unsigned long long) ninter;
+	}
+    }
+  // statistics: interactions (= sum of GravCost) and warp-level cell visits
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1)
+    tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
+  if(lane == 0)
+    {
+      atomicAdd(&A.counters[0], tot_inter);
+      atomicAdd(&A.counters[1], tot_visits);
+    }
+}
+
+// ---------------------------------------------------------------- active target list ---------------------------
+__global__ void __launch_bounds__(256) target_flag_kernel(const unsigned int *__restrict__ tq, const unsigned char *__restrict__ active, int n,
+							  unsigned int *__restrict__ flags)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p < n)
+    flags[p] = active[tq[p]] ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) target_compact_kernel(const unsigned char *__restrict__ active, const unsigned int *__restrict__ tq,
+							     const unsigned int *__restrict__ scan, int n, unsigned int *__restrict__ targets)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p < n && active[tq[p]])
+    targets[scan[p]] = (unsigned int) p;
+}
+
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
+static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, int acc_double)
+{
+  if(acc_double)
+    {
+      if(smem > 48 * 1024)
+	G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, double><<<grid, WALK_THREADS, smem, c->stream>>>(A);
+    }
+  else
+    {
+      if(smem > 48 * 1024)
+	G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, float><<<grid, WALK_THREADS, smem, c->stream>>>(A);
+    }
+  return 0;
+}
+
+template <int D>
+static int dispatch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd)
+{
+#define G2_W(SRv, PERv, UNEv, STv) return launch_walk<D, SRv, PERv, UNEv, STv>(c, A, grid, smem, accd)
+  if(sr)
+    {				// TreePM implies PERIODIC and equal softenings are not required; keep both UNEQUAL variants
+      if(unequal) { if(stock) G2_W(true, true, true, true); else G2_W(true, true, true, false); }
+      else        { if(stock) G2_W(true, true, false, true); else G2_W(true, true, false, false); }
+    }
+  else if(periodic)
+    {
+      if(unequal) { if(stock) G2_W(false, true, true, true); else G2_W(false, true, true, false); }
+      else        { if(stock) G2_W(false, true, false, true); else G2_W(false, true, false, false); }
+    }
+  else
+    {
+      if(unequal) { if(stock) G2_W(false, false, true, true); else G2_W(false, false, true, false); }
+      else        { if(stock) G2_W(false, false, false, true); else G2_W(false, false, false, false); }
+    }
+#undef G2_W
+}
+
+int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "walk: tree has not been built");
+  if(!c->laws_set)
+    return g2_fail(G2GPU_ERR_LAW, "walk: pair force laws not set (g2gpu_set_laws)");
+  const int n = c->npart, D = c->D;
+  const bool sr = c->cfg.shortrange != 0;
+  if(sr && !c->srtable_set)
+    return g2_fail(G2GPU_ERR_STATE, "walk: short-range table not set (g2gpu_set_srtable)");
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaEventRecord(c->ev[6], st));
+
+  // active targets in tree order (gravtree.c:113: Ti_endstep == Ti_Current), split into nranks equal slices
+  target_flag_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tq, c->active, n, c->w_flags);
+  c->launches++;
+  G2_TRY(g2_scan_exclusive_u32(c, c->w_flags, c->w_flags, (size_t) n));
+  target_compact_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->active, c->tq, c->w_flags, n, c->w_targets);
+  c->launches++;
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[4], c->w_flags + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  G2_CUDA(cudaStreamSynchronize(st));
+  c->w_ntargets = c->h_err[4];
+  const int nr = c->cfg.nranks > 0 ? c->cfg.nranks : 1, rk = c->cfg.rank;
+  c->w_lo = (int) ((long long) c->w_ntargets * rk / nr);
+  c->w_hi = (int) ((long long) c->w_ntargets * (rk + 1) / nr);
+
+  WalkArgs A;
+  memset(&A, 0, sizeof(A));
+  A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.tq = c->tq; A.pm = c->pm; A.ptype = c->ptype;
+  A.oldacc = c->oldacc; A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
+  A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
+  A.lo = c->w_lo; A.hi = c->w_hi; A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;
+  A.theta2 = (float) (wp->theta * wp->theta);
+  A.errtol = (float) wp->errtol_force_acc;
+  A.boxsize = (float) wp->boxsize; A.boxhalf = (float) (0.5 * wp->boxsize);
+  if(sr)
+    {
+      A.rcut = (float) wp->rcut; A.rcut2 = (float) (wp->rcut * wp->rcut);
+      A.asmthfac = (float) (0.5 / wp->asmth * (c->cfg.ntab / 3.0));	// forcetree.c:1708
+      A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
+    }
+  A.G = wp->G; A.pos_fac_pre_g = wp->pos_fac_pre_g; A.pos_fac_post_g = wp->pos_fac_post_g;
+  A.use_gravpm = wp->use_gravpm && c->have_gravpm;
+  for(int t = 0; t < 6; t++)
+    {
+      A.fsoft[t] = (float) c->force_softening[t];
+      A.t2g[t] = c->type_to_grav[t];
+    }
+  A.laws = c->laws;
+  A.ntables = c->sr_ntables;
+  memcpy(A.tabmap, c->sr_tabmap, sizeof(A.tabmap));
+  bool stock = true;
+  for(int i = 0; i < D * D; i++)
+    if(c->laws.accel[i] != G2GPU_LAW_NEWTONIAN || c->laws.spline[i] != G2GPU_SPLINE_PLUMMER)
+      stock = false;
+
+  size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
+  const int ntgt = c->w_hi - c->w_lo;
+  int grid = c->nsm * 8;
+  int need = g2_cdiv(g2_cdiv(ntgt, 32), WALK_WARPS);
+  if(grid > need)
+    grid = need;
+  G2_CUDA(cudaEventRecord(c->ev[7], st));
+  if(ntgt > 0)
+    {
+      const bool per = c->cfg.periodic != 0, uneq = c->cfg.unequal_softenings != 0;
+      int rc;
+      switch (D)
+	{
+	case 1: rc = dispatch_walk<1>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	case 2: rc = dispatch_walk<2>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	case 3: rc = dispatch_walk<3>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	case 4: rc = dispatch_walk<4>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	case 5: rc = dispatch_walk<5>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	case 6: rc = dispatch_walk<6>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
+	}
+      if(rc)
+	return rc;
+      c->launches++;
+    }
+  G2_CUDA(cudaEventRecord(c->ev[8], st));
+  G2_CUDA(cudaGetLastError());
+  c->stage = 4;
+  return 0;
+}
+
+// ---------------------------------------------------------------- stand-alone pair evaluation (tests) -----------
+__global__ void eval_pairs_kernel(int n, int accel_id, int spline_id, float p0, float p1, const float *__restrict__ pm, const float *__restrict__ m,
+				  const float *__restrict__ r, const float *__restrict__ h, const int *__restrict__ nn, float *__restrict__ fac)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  float par[4] = { p0, p1, 0, 0 };
+  float rr = r[i], r2 = rr * rr, rinv = rsqrtf(fmaxf(r2, 1.0e-37f));
+  float N = nn ? (float) nn[i] : 1.0f;
+  fac[i] = rr >= h[i] ? accel_over_r(accel_id, par, pm[i], m[i], r2, rr, rinv, N) : accel_spline(spline_id, par, pm[i], m[i], h[i], rr, N);
+}
+
+int g2_eval_pairs_standalone(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+			     const int *nn, float *fac)
+{
+  if(!c->laws_set)
+    return g2_fail(G2GPU_ERR_LAW, "pair force laws not set");
+  float *d;
+  int *dn = nullptr;
+  size_t fb = sizeof(float) * (size_t) n;
+  G2_CUDA(cudaMalloc(&d, 5 * fb));
+  G2_CUDA(cudaMemcpy(d, pm, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + n, m, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + 2 * (size_t) n, r, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + 3 * (size_t) n, h, fb, cudaMemcpyHostToDevice));
+  if(nn)
+    {
+      G2_CUDA(cudaMalloc(&dn, sizeof(int) * (size_t) n));
+      G2_CUDA(cudaMemcpy(dn, nn, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
+    }
+  int ij = tgt * c->D + src;
+  eval_pairs_kernel<<<g2_cdiv(n, 256), 256, 0, c->stream>>>(n, c->laws.accel[ij], c->laws.spline[ij], c->laws.par[ij][0], c->laws.par[ij][1], d, d + n,
+							    d + 2 * (size_t) n, d + 3 * (size_t) n, dn, d + 4 * (size_t) n);
+  c->launches++;
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  G2_CUDA(cudaMemcpy(fac, d + 4 * (size_t) n, fb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  if(dn)
+    cudaFree(dn);
+  return 0;
+}

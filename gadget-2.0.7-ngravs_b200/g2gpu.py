@@ -1,0 +1,271 @@
+"""ctypes mirror of include/g2gpu.h — the host-side (Python) view of the reference-facing C ABI.
+
+Names follow the reference: `gravity_tree`, `force_treebuild`, `peano_hilbert_order`, ... are thin methods of
+`TreeGravity` that call the corresponding C-ABI stage.  There is no CPU fallback: constructing `TreeGravity`
+raises if libg2gpu.so is missing or no sm_100 device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libg2gpu.so")
+
+LAW = dict(none=0, newtonian=1, neg_newtonian=2, yukawa=3, coloyuk=4, bambam=5, sourcebambaryon=6, sourcebaryonbam=7)
+SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebambaryon_spline=20,
+              sourcebaryonbam_spline=21)
+
+EXPORTED = [
+    "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
+    "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_domain",
+    "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree",
+    "g2gpu_walk", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
+    "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("n_gravs", C.c_int), ("periodic", C.c_int), ("shortrange", C.c_int),
+                ("ntab", C.c_int), ("unequal_softenings", C.c_int), ("max_part", C.c_int), ("max_nodes", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int)]
+
+
+class WalkParams(C.Structure):
+    _fields_ = [("theta", C.c_double), ("errtol_force_acc", C.c_double), ("boxsize", C.c_double), ("G", C.c_double),
+                ("asmth", C.c_double), ("rcut", C.c_double), ("pos_fac_pre_g", C.c_double),
+                ("pos_fac_post_g", C.c_double), ("use_gravpm", C.c_int)]
+
+
+class G2Error(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__(f"g2gpu error {code}: {text}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libg2gpu.so (built in-tree by __graft_entry__.build()); fails loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(LIB_PATH)
+        lib.g2gpu_last_error.restype = C.c_char_p
+        lib.g2gpu_stream.restype = C.c_void_p
+        _lib = lib
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class TreeGravity:
+    """One GPU's tree-gravity context (the device twin of the reference's global tree state)."""
+
+    def __init__(self, max_part, n_gravs=2, periodic=False, shortrange=False, ntab=2048, unequal_softenings=True,
+                 tree_alloc_factor=1.5, device=0, rank=0, nranks=1):
+        self.lib = load_library()
+        self.cfg = Config(device, n_gravs, int(periodic), int(shortrange), ntab, int(unequal_softenings), int(max_part),
+                          int(tree_alloc_factor * max_part), rank, nranks)
+        self.ctx = C.c_void_p()
+        self._chk(self.lib.g2gpu_create(C.byref(self.ctx), C.byref(self.cfg)))
+        self.D = n_gravs
+        self.max_part = int(max_part)
+        self.n = 0
+        self.numnodes = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise G2Error(rc, self.lib.g2gpu_last_error().decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.g2gpu_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- init_grav_maps / wire_grav_maps (ngravs_core.c:201, ngravs.c:64) -----------------------------------
+    def set_species(self, type_to_grav, force_softening):
+        t2g = _i32(type_to_grav)
+        fs = np.ascontiguousarray(force_softening, dtype=np.float64)
+        self._chk(self.lib.g2gpu_set_species(self.ctx, _p(t2g), _p(fs)))
+
+    def set_laws(self, accel="newtonian", spline="plummer", params=None):
+        """accel/spline: a name for all pairs, or a D x D nested list of names indexed [target][source]."""
+        D = self.D
+
+        def grid(x, table):
+            if isinstance(x, str):
+                return np.full((D, D), table[x], dtype=np.int32)
+            return np.array([[table[v] for v in row] for row in x], dtype=np.int32)
+        a = grid(accel, LAW)
+        s = grid(spline, SPLINE)
+        par = np.zeros((D, D, 4)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        self._chk(self.lib.g2gpu_set_laws(self.ctx, _p(a), _p(s), _p(par)))
+
+    def set_srtable(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (self.D, self.D, self.cfg.ntab)
+        self._chk(self.lib.g2gpu_set_srtable(self.ctx, _p(t)))
+
+    def set_option(self, name, value):
+        self._chk(self.lib.g2gpu_set_option(self.ctx, name.encode(), int(value)))
+
+    # ---- particle_data upload ----------------------------------------------------------------------------------
+    def upload(self, pos, mass, ptype, oldacc=None, vel=None, gravpm=None, active=None):
+        pos, mass, ptype = _f32(pos), _f32(mass), _i32(ptype)
+        n = len(mass)
+        self._chk(self.lib.g2gpu_upload(self.ctx, n, _p(pos), _p(mass), _p(ptype), _p(_f32(oldacc)), _p(_f32(vel)),
+                                        _p(_f32(gravpm)), _p(_i32(active))))
+        self.n = n
+
+    # ---- domain_Decomposition: extent + keys + top tree + peano_hilbert_order -------------------------------------
+    def domain(self):
+        self._chk(self.lib.g2gpu_domain(self.ctx))
+
+    peano_hilbert_order = domain
+
+    def domain_info(self):
+        d = np.zeros(8)
+        self._chk(self.lib.g2gpu_get_domain(self.ctx, _p(d)))
+        return dict(corner=d[0:3].copy(), center=d[3:6].copy(), len=d[6], fac=d[7])
+
+    def keys(self):
+        k = np.zeros(self.n, dtype=np.int64)
+        self._chk(self.lib.g2gpu_get_keys(self.ctx, _p(k)))
+        return k
+
+    def order(self):
+        p = np.zeros(self.n, dtype=np.int32)
+        self._chk(self.lib.g2gpu_get_order(self.ctx, _p(p)))
+        return p
+
+    def topnodes(self):
+        cap = 32768
+        nt, nl = C.c_int(), C.c_int()
+        d = np.zeros(cap, dtype=np.int32)
+        lf = np.zeros(cap, dtype=np.int32)
+        sk = np.zeros(cap, dtype=np.int64)
+        sz = np.zeros(cap, dtype=np.int64)
+        ct = np.zeros(cap, dtype=np.int64)
+        dni = np.zeros(cap, dtype=np.int32)
+        self._chk(self.lib.g2gpu_get_topnodes(self.ctx, C.byref(nt), C.byref(nl), _p(d), _p(lf), _p(sk), _p(sz), _p(ct), _p(dni)))
+        n, l = nt.value, nl.value
+        return dict(daughter=d[:n].astype(np.int64), leaf=lf[:n].astype(np.int64), startkey=sk[:n], size=sz[:n], count=ct[:n],
+                    domain_node_index=dni[:l].copy(), ntopleaves=l)
+
+    # ---- force_treebuild ----------------------------------------------------------------------------------------
+    def treebuild(self):
+        nn = C.c_int()
+        self._chk(self.lib.g2gpu_treebuild(self.ctx, C.byref(nn)))
+        self.numnodes = nn.value
+        return nn.value
+
+    force_treebuild = treebuild
+
+    def tree(self):
+        nn, D, n = self.numnodes, self.D, self.n
+        ln = np.zeros(nn, dtype=np.float32)
+        ce = np.zeros((nn, 3), dtype=np.float32)
+        s = np.zeros((nn, 3, D), dtype=np.float32)
+        m = np.zeros((nn, D), dtype=np.float32)
+        bf, sib, nxt, fat = (np.zeros(nn, dtype=np.int32) for _ in range(4))
+        pn, pf = (np.zeros(n, dtype=np.int32) for _ in range(2))
+        self._chk(self.lib.g2gpu_download_tree(self.ctx, _p(ln), _p(ce), _p(s), _p(m), _p(bf), _p(sib), _p(nxt), _p(fat), _p(pn), _p(pf)))
+        return dict(numnodes=nn, maxpart=self.max_part, len=ln, center=ce, s=s, mass=m, bitflags=bf, sibling=sib, nextnode=nxt,
+                    father=fat, p_nextnode=pn, p_father=pf)
+
+    # ---- gravity_tree -------------------------------------------------------------------------------------------
+    @staticmethod
+    def walk_params(theta=0.5, errtol=0.005, boxsize=0.0, G=1.0, asmth=0.0, rcut=0.0, use_gravpm=0):
+        return WalkParams(theta, errtol, boxsize, G, asmth, rcut, 0.0, 0.0, use_gravpm)
+
+    def walk(self, wp):
+        self._chk(self.lib.g2gpu_walk(self.ctx, C.byref(wp)))
+
+    def download_acc(self):
+        acc = np.zeros((self.n, 3), dtype=np.float32)
+        cost = np.zeros(self.n, dtype=np.float32)
+        old = np.zeros(self.n, dtype=np.float32)
+        self._chk(self.lib.g2gpu_download_acc(self.ctx, _p(acc), _p(cost), _p(old)))
+        return acc, cost, old
+
+    def gravity_tree(self, pos, mass, ptype, wp, oldacc=None, active=None):
+        """Whole step from host buffers (upload, domain, build, walk, download): the e2e path."""
+        pos, mass, ptype = _f32(pos), _f32(mass), _i32(ptype)
+        n = len(mass)
+        acc = np.zeros((n, 3), dtype=np.float32)
+        cost = np.zeros(n, dtype=np.float32)
+        old = np.zeros(n, dtype=np.float32)
+        perm = np.zeros(n, dtype=np.int32)
+        self._chk(self.lib.g2gpu_gravity_tree(self.ctx, n, _p(pos), _p(mass), _p(ptype), _p(_f32(oldacc)), _p(_i32(active)),
+                                              C.byref(wp), _p(acc), _p(cost), _p(old), _p(perm)))
+        self.n = n
+        return acc, cost, old, perm
+
+    def slice(self):
+        lo, hi = C.c_int(), C.c_int()
+        self._chk(self.lib.g2gpu_slice(self.ctx, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def input_buffers(self, n):
+        ptrs = (C.c_void_p * 4)()
+        self._chk(self.lib.g2gpu_input_buffers(self.ctx, int(n), ptrs))
+        return [int(p) for p in ptrs]
+
+    def inputs_ready(self, n):
+        self._chk(self.lib.g2gpu_inputs_ready(self.ctx, int(n)))
+        self.n = int(n)
+
+    def timings(self):
+        ms = np.zeros(8)
+        cnt = np.zeros(4, dtype=np.int64)
+        self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
+        return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6],
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), targets=int(cnt[3]))
+
+    def reset_counters(self):
+        self.lib.g2gpu_reset_counters(self.ctx)
+
+    def sync(self):
+        self._chk(self.lib.g2gpu_sync(self.ctx))
+
+    @property
+    def stream(self):
+        return self.lib.g2gpu_stream(self.ctx)
+
+    # ---- stand-alone kernels -------------------------------------------------------------------------------------
+    def peano_keys(self, xyz, bits):
+        xyz = _i32(xyz)
+        k = np.zeros(len(xyz), dtype=np.int64)
+        self._chk(self.lib.g2gpu_peano_keys(self.ctx, len(xyz), _p(xyz), int(bits), _p(k)))
+        return k
+
+    def sort_pairs(self, keys, vals, begin_bit=0, end_bit=64):
+        k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._chk(self.lib.g2gpu_sort_pairs(self.ctx, len(k), _p(k), _p(v), begin_bit, end_bit))
+        return k, v
+
+    def eval_pairs(self, tgt, src, pm, m, r, h, nn=None):
+        pm, m, r, h = _f32(pm), _f32(m), _f32(r), _f32(h)
+        fac = np.zeros(len(r), dtype=np.float32)
+        self._chk(self.lib.g2gpu_eval_pairs(self.ctx, len(r), tgt, src, _p(pm), _p(m), _p(r), _p(h), _p(_i32(nn)), _p(fac)))
+        return fac

@@ -1,0 +1,173 @@
+/* g2gpu.h — C ABI of the B200-native tree-gravity hot path for Gadget-2-ngravs.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only.  The reference's C entry points
+ * (gravity_tree gravtree.c:27, force_treebuild forcetree.c:61, force_treeallocate forcetree.c:3176,
+ * force_treefree forcetree.c:3411, peano_hilbert_order peano.c:36, peano_hilbert_key peano.c:356,
+ * init_grav_maps ngravs_core.c:201) keep their signatures in the host shim (host/ *.c) and call the
+ * functions below; see INTEGRATION.md.  There is no CPU fallback: every call that needs the GPU fails
+ * with G2GPU_ERR_CUDA when no sm_100 device is present.
+ *
+ * Index conventions are the reference's (forcetree.c:76-92): particles are [0, NumPart), tree nodes
+ * are [MaxPart, MaxPart+MaxNodes).  All functions return 0 on success or a negative G2GPU_ERR_* code
+ * (the host shim turns non-zero into endrun(code), endrun.c:24); g2gpu_last_error() gives the text.
+ */
+#ifndef G2GPU_H
+#define G2GPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2GPU_MAX_GRAVS 6	/* N_GRAVS upper bound: 6 particle types (allvars.h:132) */
+#define G2GPU_NTYPES 6
+
+enum g2gpu_error
+{
+  G2GPU_OK = 0,
+  G2GPU_ERR_CUDA = -1,		/* CUDA runtime failure or no usable device */
+  G2GPU_ERR_ARG = -2,		/* invalid argument / call order */
+  G2GPU_ERR_NOMEM = -3,		/* device or host allocation failed */
+  G2GPU_ERR_MAXNODES = -4,	/* more tree nodes than MaxNodes (forcetree.c:249-255 -> endrun(1)) */
+  G2GPU_ERR_TREE_DEPTH = -5,	/* two particles not separable within the supported tree depth */
+  G2GPU_ERR_TOPNODES = -6,	/* top-level tree larger than MAXTOPNODES (domain.c:1049 -> endrun(13213)) */
+  G2GPU_ERR_LAW = -7,		/* unknown / unwired pair force law (ngravs_core.c:326-365) */
+  G2GPU_ERR_STATE = -8		/* call made before its prerequisite stage */
+};
+
+/* Pair force laws shipped in ngravs.c, by registry id.  AccelFxns[tgt][src] takes (pm, m, r2, r, N),
+ * AccelSplines[tgt][src] takes (pm, m, h, r, N) (allvars.h:134-136, ngravs.c:332-861). */
+enum g2gpu_law
+{
+  G2GPU_LAW_NONE = 0,		/* none()            ngravs.c:344 */
+  G2GPU_LAW_NEWTONIAN = 1,	/* newtonian()       ngravs.c:351 */
+  G2GPU_LAW_NEG_NEWTONIAN = 2,	/* neg_newtonian()   ngravs.c:359 */
+  G2GPU_LAW_YUKAWA = 3,		/* yukawa()          ngravs.c:856, param[0] = YUKAWA_IMASS/BoxSize */
+  G2GPU_LAW_COLOYUK = 4,	/* coloyuk()         ngravs.c:826 */
+  G2GPU_LAW_BAMBAM = 5,		/* bambam()          ngravs.c:495, param[1] = BAM_EPSILON */
+  G2GPU_LAW_SOURCEBAMBARYON = 6,	/* sourcebambaryon() ngravs.c:590 */
+  G2GPU_LAW_SOURCEBARYONBAM = 7,	/* sourcebaryonbam() ngravs.c:646 */
+  G2GPU_SPLINE_NONE = 16,	/* none()            as a spline */
+  G2GPU_SPLINE_PLUMMER = 17,	/* plummer()         ngravs.c:420 */
+  G2GPU_SPLINE_NEG_PLUMMER = 18,	/* neg_plummer()     ngravs.c:438 */
+  G2GPU_SPLINE_BAMBAM = 19,	/* bambam_spline()   ngravs.c:531 */
+  G2GPU_SPLINE_SOURCEBAMBARYON = 20,	/* sourcebambaryon_spline() ngravs.c:562 */
+  G2GPU_SPLINE_SOURCEBARYONBAM = 21	/* sourcebaryonbam_spline() ngravs.c:616 */
+};
+
+/* Compile-time switches of the reference (Makefile.reference:49-135) become run-time configuration. */
+typedef struct g2gpu_config
+{
+  int device;			/* CUDA device ordinal */
+  int n_gravs;			/* N_GRAVS (D), 1..G2GPU_MAX_GRAVS */
+  int periodic;			/* PERIODIC: NEAREST() wrap in the walk (forcetree.c:43) */
+  int shortrange;		/* PMGRID != 0: force_treeevaluate_shortrange instead of force_treeevaluate */
+  int ntab;			/* NTAB, length of one short-range table (2048) */
+  int unequal_softenings;	/* UNEQUALSOFTENINGS */
+  int max_part;			/* All.MaxPart: index of the first tree node */
+  int max_nodes;		/* MaxNodes = TreeAllocFactor*MaxPart (init.c:151) */
+  int rank;			/* this process's rank among the GPUs sharing the particle set */
+  int nranks;			/* number of such GPUs; targets are split into nranks equal PH slices */
+} g2gpu_config;
+
+/* Per-call parameters of a force computation: the fields of `All` that gravity_tree() and the walks read
+ * (gravtree.c:27-460, forcetree.c:1244-2052). */
+typedef struct g2gpu_walk_params
+{
+  double theta;			/* All.ErrTolTheta; 0 selects the relative criterion (forcetree.c:1439) */
+  double errtol_force_acc;	/* All.ErrTolForceAcc */
+  double boxsize;		/* All.BoxSize (PERIODIC) */
+  double G;			/* All.G */
+  double asmth;			/* All.Asmth[0]  (short-range) */
+  double rcut;			/* All.Rcut[0]   (short-range) */
+  double pos_fac_pre_g;		/* added as fac*Pos before the G scaling (gravtree.c:304-316), normally 0 */
+  double pos_fac_post_g;	/* added as fac*Pos after the G scaling  (gravtree.c:346-358), normally 0 */
+  int use_gravpm;		/* OldAcc includes GravPM/G (gravtree.c:321-325) */
+} g2gpu_walk_params;
+
+typedef struct g2gpu_ctx g2gpu_ctx;
+
+/* ---- life cycle: force_treeallocate (forcetree.c:3176) / force_treefree (forcetree.c:3411) ---- */
+int g2gpu_create(g2gpu_ctx **ctx, const g2gpu_config *cfg);
+void g2gpu_destroy(g2gpu_ctx *ctx);
+const char *g2gpu_last_error(void);
+int g2gpu_device_count(void);
+
+/* ---- plug-in tables: init_grav_maps/wire_grav_maps (ngravs_core.c:201, ngravs.c:64) ---- */
+/* TypeToGrav[6] (allvars.h:132) and All.ForceSoftening[6] (gravtree.c:514). */
+int g2gpu_set_species(g2gpu_ctx *ctx, const int type_to_grav[G2GPU_NTYPES], const double force_softening[G2GPU_NTYPES]);
+/* accel_id / spline_id: D*D registry ids indexed [target][source] (ngravs.c:75-76); params: 4 doubles per pair. */
+int g2gpu_set_laws(g2gpu_ctx *ctx, const int *accel_id, const int *spline_id, const double *params);
+/* shortrange_fourier_force[target][source][NTAB] (forcetree.c:33, filled 3274-3354), as double. */
+int g2gpu_set_srtable(g2gpu_ctx *ctx, const double *table);
+
+/* ---- particle upload (struct particle_data, allvars.h:546-581) ---- */
+/* SoA, float32: pos[3n], mass[n], type[n], and optional oldacc[n], vel[3n], gravpm[3n], active[n]
+ * (active[i] != 0 <=> P[i].Ti_endstep == All.Ti_Current, gravtree.c:113; NULL = all active). */
+int g2gpu_upload(g2gpu_ctx *ctx, int npart, const float *pos, const float *mass, const int *type,
+		 const float *oldacc, const float *vel, const float *gravpm, const int *active);
+/* Same from the reference's AoS: base pointer, stride = sizeof(struct particle_data), byte offsets of
+ * Pos, Mass, Type, OldAcc, Vel, GravPM (-1 if absent), Ti_endstep; float_bytes = sizeof(FLOAT). */
+int g2gpu_upload_aos(g2gpu_ctx *ctx, int npart, const void *P, size_t stride, int float_bytes, int off_pos,
+		     int off_mass, int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep,
+		     int ti_current);
+/* Multi-GPU: upload only this rank's slice [lo,hi) of the SoA input into the device input buffers and expose
+ * them, so that the caller's collective (NCCL all-gather over NVLink) can fill in the other ranks' slices.
+ * ptrs[0..3] = device pointers of posmass (float4 n: x,y,z,mass), type (int n), oldacc (float n), active (u8 n). */
+int g2gpu_input_buffers(g2gpu_ctx *ctx, int npart, void **ptrs);
+int g2gpu_inputs_ready(g2gpu_ctx *ctx, int npart);	/* call after the all-gather: marks all active */
+
+/* ---- stage 1: domain_findExtent + key loop + top tree + peano_hilbert_order
+ *      (domain.c:882-924, 933-1138; peano.c:36-185, 356-398) ---- */
+int g2gpu_domain(g2gpu_ctx *ctx);
+int g2gpu_get_domain(g2gpu_ctx *ctx, double out[8]);	/* DomainCorner[3], DomainCenter[3], DomainLen, DomainFac */
+int g2gpu_get_keys(g2gpu_ctx *ctx, long long *keys);	/* Key[] in CURRENT particle order */
+int g2gpu_get_order(g2gpu_ctx *ctx, int *perm);	/* perm[i] = index at upload time of the particle now at i */
+/* TopNodes[] (allvars.h:252-262) as 4 arrays + DomainNodeIndex[NTopleaves]; pass NULL to skip an output. */
+int g2gpu_get_topnodes(g2gpu_ctx *ctx, int *ntopnodes, int *ntopleaves, int *daughter, int *leaf,
+		       long long *startkey, long long *size, long long *count, int *domain_node_index);
+
+/* ---- stage 2: force_treebuild (forcetree.c:61-281, 451-743, 954-996) ---- */
+int g2gpu_treebuild(g2gpu_ctx *ctx, int *numnodes);
+/* Host mirror in the reference's numbering and layout semantics (struct NODE after the moment pass,
+ * allvars.h:618-660): per node k (index MaxPart+k): len[k], center[3k], s[(3k+j)*D+g], mass[k*D+g],
+ * bitflags/sibling/nextnode/father[k]; per particle Nextnode[i], Father[i].  NULL skips an output. */
+int g2gpu_download_tree(g2gpu_ctx *ctx, float *len, float *center, float *s, float *mass, int *bitflags,
+			int *sibling, int *nextnode, int *father, int *p_nextnode, int *p_father);
+
+/* ---- stage 3: the walk + gravity_tree epilogue (gravtree.c:102-358; forcetree.c:1244-2052) ---- */
+int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
+/* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT
+ * particle order; only entries of active particles of this rank's slice are written. */
+int g2gpu_download_acc(g2gpu_ctx *ctx, float *acc, float *cost, float *oldacc);
+int g2gpu_slice(g2gpu_ctx *ctx, int *lo, int *hi);	/* this rank's slice of the walk-ordered active list */
+/* Whole step with host buffers: upload -> domain -> treebuild -> walk -> download (the e2e path). */
+int g2gpu_gravity_tree(g2gpu_ctx *ctx, int npart, const float *pos, const float *mass, const int *type,
+		       const float *oldacc, const int *active, const g2gpu_walk_params *wp, float *acc, float *cost,
+		       float *oldacc_out, int *perm);
+
+/* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks". */
+int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
+
+/* ---- instrumentation ---- */
+/* CUDA-event times (ms) of the last call of each stage: [0] domain [1] treebuild [2] walk
+ * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H; counters[0] = kernel launches since
+ * g2gpu_reset_counters, [1] = sum of GravCost of the last walk, [2] = node visits (if enabled). */
+int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[4]);
+void g2gpu_reset_counters(g2gpu_ctx *ctx);
+void *g2gpu_stream(g2gpu_ctx *ctx);	/* cudaStream_t all kernels are launched on */
+int g2gpu_sync(g2gpu_ctx *ctx);
+
+/* Stand-alone kernels exposed for parity tests. */
+int g2gpu_peano_keys(g2gpu_ctx *ctx, int n, const int *xyz, int bits, long long *keys);	/* peano.c:356 */
+int g2gpu_sort_pairs(g2gpu_ctx *ctx, int n, unsigned long long *keys, unsigned int *vals, int begin_bit, int end_bit);
+/* AccelFxns[tgt][src](pm,m,r2,r,N)/r resp. AccelSplines[tgt][src](pm,m,h,r,N) for r>=h resp. r<h, in the
+ * kernel's own arithmetic: out[i] = fac such that acc += d*fac (forcetree.c:1542-1544). */
+int g2gpu_eval_pairs(g2gpu_ctx *ctx, int n, int tgt, int src, const float *pm, const float *m, const float *r,
+		     const float *h, const int *npart_in_node, float *fac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+"""Shared helpers of the parity tests: synthetic particle sets and oracle/GPU drivers."""
+import numpy as np
+
+SOFT_NP = (0.0, 0.05, 0.02, 0.05, 0.05, 0.05)     # Plummer-equivalent softenings per type (types 1 and 2 differ)
+GRAV_D2 = (0, 0, 1, 0, 0, 0)                      # Gravity{Gas..Bndry}: type 2 -> species 1 (Configuration.reference)
+
+
+def hernquist(n, a=30.0, rmax=1000.0, seed=20261018, two_types=True):
+    """Two-species Hernquist halo: r = a sqrt(u)/(1-sqrt(u)), isotropic; float32 positions."""
+    rng = np.random.default_rng(seed)
+    umax = (rmax / (rmax + a)) ** 2
+    u = rng.uniform(0, umax, n)
+    r = a * np.sqrt(u) / (1 - np.sqrt(u))
+    mu = rng.uniform(-1, 1, n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    st = np.sqrt(1 - mu * mu)
+    pos = np.stack([r * st * np.cos(phi), r * st * np.sin(phi), r * mu], axis=1).astype(np.float32)
+    mass = np.full(n, 1.0e-4, dtype=np.float32)
+    ptype = np.ones(n, dtype=np.int32)
+    if two_types:
+        ptype[n // 2:] = 2
+    return pos, mass, ptype
+
+
+def gaussian_blobs(n, seed=3, types=(1, 2)):
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-50, 50, size=(4, 3))
+    which = rng.integers(0, 4, n)
+    pos = (centers[which] + rng.normal(size=(n, 3)) * rng.uniform(1, 8, size=(4, 1))[which]).astype(np.float32)
+    mass = rng.uniform(0.5e-3, 2e-3, n).astype(np.float32)
+    ptype = np.asarray(types, dtype=np.int32)[rng.integers(0, len(types), n)]
+    return pos, mass, ptype
+
+
+def periodic_poisson(n, box=100000.0, seed=42, ntypes=2):
+    """Periodic Poisson box: species by index parity (types 1/2), unit masses."""
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(0, box, size=(n, 3)).astype(np.float32)
+    pos = np.minimum(pos, np.float32(np.nextafter(np.float32(box), np.float32(0))))
+    mass = np.ones(n, dtype=np.float32)
+    if ntypes == 2:
+        ptype = np.where(np.arange(n) % 2 == 0, 1, 2).astype(np.int32)
+    else:
+        ptype = (np.arange(n) % 6).astype(np.int32)
+        ptype = np.sort(ptype, kind="stable")          # gas must sit at the head of P[] (peano.c:47-67)
+    return pos, mass, ptype
+
+
+def force_softening(soft):
+    return 2.8 * np.asarray(soft, dtype=np.float64)   # gravtree.c:514-515
+
+
+def rel_err(a, b):
+    """per-particle |a-b| / |b|"""
+    num = np.linalg.norm(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64), axis=1)
+    den = np.linalg.norm(np.asarray(b, dtype=np.float64), axis=1)
+    return num / np.maximum(den, 1e-300)
+
+
+def compare_tree(gt, rt, D):
+    """Returns a dict of mismatch counts between a GPU tree mirror and the oracle's tree (same numbering)."""
+    out = {}
+    out["numnodes"] = int(gt["numnodes"] != rt["numnodes"])
+    n = min(gt["numnodes"], rt["numnodes"])
+    out["len"] = int(np.sum(gt["len"][:n] != rt["len"][:n].astype(np.float32)))
+    out["center"] = int(np.sum(gt["center"][:n] != rt["center"][:n].astype(np.float32)))
+    out["mass"] = int(np.sum(gt["mass"][:n] != rt["mass"][:n].astype(np.float32)))
+    out["s"] = int(np.sum(gt["s"][:n] != rt["s"][:n].astype(np.float32)))
+    for k in ("bitflags", "sibling", "nextnode", "father"):
+        out[k] = int(np.sum(gt[k][:n] != rt[k][:n]))
+    out["p_nextnode"] = int(np.sum(gt["p_nextnode"] != rt["p_nextnode"]))
+    out["p_father"] = int(np.sum(gt["p_father"] != rt["p_father"]))
+    return out

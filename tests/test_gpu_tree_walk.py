@@ -1,0 +1,156 @@
+"""GPU parity, stages 2-3: tree topology / node numbering / moments (bit-exact) and accelerations
+(median relative error <= 1e-5, 99.9th percentile <= 1e-3, GravCost compared exactly) against the
+unmodified reference's own tree (oracle/_ref), on identical float32 inputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import g2test
+from refrun import RefOracle, available
+
+pytestmark = pytest.mark.gpu
+
+MEDIAN_TOL = 1.0e-5      # BASELINE.json north_star
+P999_TOL = 1.0e-3
+
+
+def run_reference(variant, pos, mass, ptype, soft, grav, box=0.0, theta=0.5, errtol=0.005, criterion=1):
+    n = len(mass)
+    ref = RefOracle(variant, int(1.1 * n) + 64, boxsize=box, softening=soft, gravity=grav, theta=theta, errtol=errtol,
+                    criterion=criterion)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    return ref
+
+
+def gpu_for(ref, n, periodic=False, shortrange=False, unequal=True):
+    from g2gpu import TreeGravity
+    t = TreeGravity(max_part=ref.maxpart, n_gravs=ref.D, periodic=periodic, shortrange=shortrange, unequal_softenings=unequal)
+    return t
+
+
+def dump(outdir, name, obj):
+    with open(os.path.join(outdir, name), "w") as f:
+        json.dump(obj, f, indent=1, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+
+
+def summarize(err):
+    return dict(median=float(np.median(err)), p99=float(np.percentile(err, 99)), p999=float(np.percentile(err, 99.9)),
+                max=float(err.max()))
+
+
+@pytest.mark.parametrize("case,n", [("blobs", 20000), ("hernquist", 100000)])
+def test_nonperiodic_tree_and_forces(case, n, outdir):
+    if not available("np_d2_f32"):
+        pytest.skip("oracle/_ref not built")
+    pos, mass, ptype = g2test.gaussian_blobs(n) if case == "blobs" else g2test.hernquist(n)
+    soft, grav = g2test.SOFT_NP, g2test.GRAV_D2
+    ref = run_reference("np_d2_f32", pos, mass, ptype, soft, grav)
+    rp = ref.particles()                     # reference order after peano_hilbert_order
+    # feed the GPU the reference-ordered particles: a stable sort keeps exactly this order (ties included)
+    tg = gpu_for(ref, n)
+    tg.set_species(grav, g2test.force_softening(soft))
+    tg.set_laws()
+    tg.upload(rp["pos"], rp["mass"], rp["type"])
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+
+    # ---- pass 1: Barnes-Hut (OldAcc = 0, ErrTolTheta = 0.5), as the first call of a run (accel.c:46)
+    ref.gravity()
+    rt = ref.tree()
+    r1 = ref.particles()
+    nn = tg.treebuild()
+    gt = tg.tree()
+    mism = g2test.compare_tree(gt, rt, ref.D)
+    dump(outdir, f"tree_{case}.json", dict(numnodes_gpu=nn, numnodes_ref=rt["numnodes"], mismatches=mism))
+    assert nn == rt["numnodes"]
+    assert all(v == 0 for v in mism.values()), mism
+    dni = tg.topnodes()["domain_node_index"]
+    assert np.array_equal(dni, ref.topnodes()["domain_node_index"])
+
+    wp = tg.walk_params(theta=0.5, errtol=0.005, G=1.0)
+    tg.walk(wp)
+    acc, cost, old = tg.download_acc()
+    e1 = g2test.rel_err(acc, r1["acc"])
+    s1 = summarize(e1)
+    s1["cost_mismatch"] = int(np.sum(cost != r1["cost"]))
+    s1["ia_per_part_gpu"] = float(cost.mean())
+    s1["ia_per_part_ref"] = float(r1["cost"].mean())
+
+    # ---- pass 2: relative criterion with OldAcc from pass 1 (gravtree.c:334-335 zeroes ErrTolTheta)
+    ref.set_opening(0.0, 0.005, 1)
+    ref.gravity()
+    r2 = ref.particles()
+    tg.upload(rp["pos"], rp["mass"], rp["type"], oldacc=r1["oldacc"])
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.0, errtol=0.005, G=1.0))
+    acc2, cost2, old2 = tg.download_acc()
+    e2 = g2test.rel_err(acc2, r2["acc"])
+    s2 = summarize(e2)
+    s2["cost_mismatch"] = int(np.sum(cost2 != r2["cost"]))
+    s2["ia_per_part_gpu"] = float(cost2.mean())
+    s2["ia_per_part_ref"] = float(r2["cost"].mean())
+    s2["oldacc_relerr_max"] = float(np.max(np.abs(old2 - r2["oldacc"]) / np.maximum(r2["oldacc"], 1e-30)))
+    dump(outdir, f"walk_{case}.json", dict(bh=s1, relative=s2, timings=tg.timings()))
+    tg.close()
+    for s in (s1, s2):
+        assert s["median"] <= MEDIAN_TOL, s
+        assert s["p999"] <= P999_TOL, s
+        assert s["cost_mismatch"] <= 0.002 * n, s
+
+
+@pytest.mark.parametrize("n", [32768])
+def test_periodic_treepm_shortrange(n, outdir):
+    if not available("pm_d2_f32"):
+        pytest.skip("oracle/_ref not built")
+    box = 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box)
+    eps = box / round(n ** (1 / 3)) / 30.0
+    soft = (eps,) * 6
+    grav = g2test.GRAV_D2
+    ref = run_reference("pm_d2_f32", pos, mass, ptype, soft, grav, box=box)
+    rp = ref.particles()
+    tg = gpu_for(ref, n, periodic=True, shortrange=True, unequal=False)
+    tg.set_species(grav, g2test.force_softening(soft))
+    tg.set_laws()
+    tg.set_srtable(ref.srtable())
+    asmth, rcut = ref.pm_split()
+    tg.upload(rp["pos"], rp["mass"], rp["type"])
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+    ref.gravity()
+    rt = ref.tree()
+    r1 = ref.particles()
+    nn = tg.treebuild()
+    gt = tg.tree()
+    mism = g2test.compare_tree(gt, rt, ref.D)
+    dump(outdir, "tree_periodic.json", dict(numnodes_gpu=nn, numnodes_ref=rt["numnodes"], mismatches=mism))
+    assert nn == rt["numnodes"]
+    assert all(v == 0 for v in mism.values()), mism
+    tg.walk(tg.walk_params(theta=0.5, errtol=0.005, boxsize=box, G=1.0, asmth=asmth, rcut=rcut))
+    acc, cost, old = tg.download_acc()
+    s1 = summarize(g2test.rel_err(acc, r1["acc"]))
+    s1["cost_mismatch"] = int(np.sum(cost != r1["cost"]))
+    s1["ia_per_part_gpu"] = float(cost.mean())
+    s1["ia_per_part_ref"] = float(r1["cost"].mean())
+    ref.set_opening(0.0, 0.005, 1)
+    ref.gravity()
+    r2 = ref.particles()
+    tg.upload(rp["pos"], rp["mass"], rp["type"], oldacc=r1["oldacc"])
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.0, errtol=0.005, boxsize=box, G=1.0, asmth=asmth, rcut=rcut))
+    acc2, cost2, old2 = tg.download_acc()
+    s2 = summarize(g2test.rel_err(acc2, r2["acc"]))
+    s2["cost_mismatch"] = int(np.sum(cost2 != r2["cost"]))
+    s2["ia_per_part_gpu"] = float(cost2.mean())
+    s2["ia_per_part_ref"] = float(r2["cost"].mean())
+    dump(outdir, "walk_periodic.json", dict(bh=s1, relative=s2, timings=tg.timings()))
+    tg.close()
+    for s in (s1, s2):
+        assert s["median"] <= MEDIAN_TOL, s
+        assert s["p999"] <= P999_TOL, s
+        assert s["cost_mismatch"] <= 0.002 * n, s
