@@ -369,10 +369,12 @@ __device__ __forceinline__ void mom_add_particle(Moments<D> &M, float4 p, int ty
   for(int gg = 0; gg < D; gg++)
     if(gg == g)
       {
+	// `pa->Mass * pa->Pos[k]` is a FLOAT*FLOAT product, rounded to float before it is added to the
+	// double accumulator (forcetree.c:611-619)
 	M.mass[gg] = __dadd_rn(M.mass[gg], m);
-	M.sx[gg] = __dadd_rn(M.sx[gg], __dmul_rn(m, (double) p.x));
-	M.sy[gg] = __dadd_rn(M.sy[gg], __dmul_rn(m, (double) p.y));
-	M.sz[gg] = __dadd_rn(M.sz[gg], __dmul_rn(m, (double) p.z));
+	M.sx[gg] = __dadd_rn(M.sx[gg], (double) __fmul_rn(p.w, p.x));
+	M.sy[gg] = __dadd_rn(M.sy[gg], (double) __fmul_rn(p.w, p.y));
+	M.sz[gg] = __dadd_rn(M.sz[gg], (double) __fmul_rn(p.w, p.z));
       }
   if(S.unequal)
     soft_update(M.maxsofttype, M.diffsoft, type, S);
@@ -388,10 +390,11 @@ __device__ __forceinline__ void mom_add_cell(Moments<D> &M, const float4 *__rest
     {
       float4 q = __ldcg(&rec[1 + g]);
       double m = (double) q.w;
+      // FLOAT*FLOAT products as in forcetree.c:555-567
       M.mass[g] = __dadd_rn(M.mass[g], m);
-      M.sx[g] = __dadd_rn(M.sx[g], __dmul_rn(m, (double) q.x));
-      M.sy[g] = __dadd_rn(M.sy[g], __dmul_rn(m, (double) q.y));
-      M.sz[g] = __dadd_rn(M.sz[g], __dmul_rn(m, (double) q.z));
+      M.sx[g] = __dadd_rn(M.sx[g], (double) __fmul_rn(q.w, q.x));
+      M.sy[g] = __dadd_rn(M.sy[g], (double) __fmul_rn(q.w, q.y));
+      M.sz[g] = __dadd_rn(M.sz[g], (double) __fmul_rn(q.w, q.z));
     }
   if(S.unequal)
     {

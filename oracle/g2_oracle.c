@@ -1,0 +1,1138 @@
+/* oracle/g2_oracle.c — CPU RESTATEMENT of the reference's tree-gravity hot path.  TEST INFRASTRUCTURE ONLY:
+ * nothing in the product (gadget-2.0.7-ngravs_b200/, include/) links, imports or executes this file; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may.
+ *
+ * Parity status: PINNED.  tests/test_oracle_port.py checks every stage of this file bit-for-bit (keys, order,
+ * TopNodes, node records, Nextnode/Father, GravCost) and the accelerations to 1e-12 against the UNMODIFIED
+ * reference compiled by oracle/ref/Makefile (oracle/_ref), and against the fixtures in tests/golden/ that were
+ * generated from that reference build (tests/golden/make_golden.py).
+ *
+ * It is a plain sequential C program with the reference's compile-time switches (N_GRAVS, PERIODIC, PMGRID,
+ * UNEQUALSOFTENINGS; Makefile.reference:49-135) turned into run-time fields, for FLOAT = float, one MPI rank
+ * (NTask = 1: no pseudo-particles, forcetree.c:366-368) and -DNOTREERND.  Every function cites the reference
+ * lines it restates.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <sys/time.h>
+
+#include "../include/g2_ph_table.h"
+
+#define MAXG 6
+#define PH_BITS 18			/* BITS_PER_DIMENSION, allvars.h:34 */
+#define MAXTOP 200000			/* MAXTOPNODES, allvars.h:29 */
+
+typedef long long peanokey;
+
+typedef struct
+{
+  int daughter, leaf;
+  peanokey size, startkey;
+  long long count;
+} topnode;
+
+typedef struct
+{
+  float len, center[3];
+  int suns[8];				/* build phase (the reference overlays this with the fields below) */
+  float s[3][MAXG], mass[MAXG];
+  int bitflags, sibling, nextnode, father;
+} node;
+
+typedef struct
+{
+  float pos[3], mass, oldacc, gravpm[3];
+  int type, id, active;
+  peanokey key;
+  float acc[3], cost;
+  double accd[3];			/* walk result before rounding to FLOAT (diagnostics) */
+} particle;
+
+typedef struct g2o
+{
+  int D, periodic, shortrange, unequal, ntab;
+  int maxpart, maxnodes;
+  int t2g[6];
+  double fsoft[6];			/* All.ForceSoftening */
+  int accel_id[MAXG][MAXG], spline_id[MAXG][MAXG];
+  double lawpar[MAXG][MAXG][4];
+  double *srtab;			/* [D][D][ntab] */
+  double boxsize, G, theta, errtol, asmth, rcut;
+  int n;
+  particle *P;
+  double corner[3], center[3], len, fac;
+  topnode *top;
+  int ntop, ntopleaves;
+  int *dni;				/* DomainNodeIndex */
+  node *nodes;				/* nodes[k] is reference node MaxPart+k */
+  int numnodes;
+  int *nextnode, *father;		/* per particle */
+  int last;
+  double t_domain, t_build, t_walk;
+} g2o;
+
+static const unsigned char ph_table[G2_PH_NSTATES * 8] = G2_PH_TABLE_INIT;
+
+static double wall(void)
+{
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return tv.tv_sec + 1e-6 * tv.tv_usec;
+}
+
+/* ---- peano_hilbert_key, peano.c:356-398, as the state machine of include/g2_ph_table.h ---- */
+peanokey g2o_peano_key(int x, int y, int z, int bits)
+{
+  unsigned st = 0;
+  peanokey key = 0;
+  int l;
+  for(l = bits - 1; l >= 0; l--)
+    {
+      unsigned o = (((x >> l) & 1) << 2) | (((y >> l) & 1) << 1) | ((z >> l) & 1);
+      unsigned e = ph_table[st * 8 + o];
+      key = (key << 3) | (e & 7);
+      st = e >> 3;
+    }
+  return key;
+}
+
+/* ---- pair laws, ngravs.c:344-861 (registry ids of include/g2gpu.h) ---- */
+static double plummer_law(double m, double h, double r)	/* ngravs.c:420-434 */
+{
+  double hinv = 1 / h, u = r * hinv;
+  if(u < 0.5)
+    return m * hinv * hinv * hinv * (10.666666666667 + u * u * (32.0 * u - 38.4));
+  return m * hinv * hinv * hinv * (21.333333333333 - 48.0 * u + 38.4 * u * u - 10.666666666667 * u * u * u -
+				   0.066666666667 / (u * u * u));
+}
+
+static double bam_accel(double rho, double eta, double r)	/* shared body of ngravs.c:495-529, 590-614, 646-670 */
+{
+  double reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
+  if(reta < 0.1)
+    return rho * eta3 * (2.0 * r / 3.0 - 4.0 * reta2 * r / 5.0 + 6.0 * reta2 * reta2 * r / 7.0);
+  return rho * eta3 * (atan(reta) / (reta2 * eta) - 1.0 / (reta * eta * (1 + reta2)));
+}
+
+static double bam_spline(double rho, double eta, double r)	/* ngravs.c:531-560, 562-588, 616-644 */
+{
+  double reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
+  if(reta < 0.1)
+    return rho * eta3 * (2.0 / 3.0 - 4.0 * reta2 / 5.0 + 6.0 * reta2 * reta2 / 7.0);
+  return rho * eta3 * (atan(reta) / (reta2 * reta) - 1.0 / (reta2 * (1 + reta2)));
+}
+
+/* AccelFxns[tg][sg](pm, m, r2, r, N) */
+static double accel_fxn(const g2o * o, int tg, int sg, double pm, double m, double r2, double r, long N)
+{
+  const double *par = o->lawpar[tg][sg];
+  switch (o->accel_id[tg][sg])
+    {
+    case 1: return m / r2;						/* newtonian      ngravs.c:351 */
+    case 2: return -m / r2;						/* neg_newtonian  ngravs.c:359 */
+    case 3: return m * exp(-r * par[0]) * (par[0] / r + 1.0 / r2);	/* yukawa         ngravs.c:856 */
+    case 4: return m * exp(-r * par[0]) * (par[0] / r + 1.0 / r2) + m / r2;	/* coloyuk ngravs.c:826 */
+    case 5: return bam_accel(2 * pm * m / M_PI, 4.0 * M_PI * par[1] / (pm + m / N), r);	/* bambam */
+    case 6: return bam_accel(2 * pm * m / M_PI, 4.0 * M_PI * par[1] * N / m, r);	/* sourcebambaryon */
+    case 7: return bam_accel(2 * pm * m / M_PI, 4.0 * M_PI * par[1] / pm, r);		/* sourcebaryonbam */
+    default: return 0.0;						/* none           ngravs.c:344 */
+    }
+}
+
+/* AccelSplines[tg][sg](pm, m, h, r, N) */
+static double accel_spline(const g2o * o, int tg, int sg, double pm, double m, double h, double r, long N)
+{
+  const double *par = o->lawpar[tg][sg];
+  switch (o->spline_id[tg][sg])
+    {
+    case 17: return plummer_law(m, h, r);
+    case 18: return -plummer_law(m, h, r);
+    case 19: return bam_spline(2 * pm * m / M_PI, 4.0 * M_PI * par[1] / (pm + m / N), r);
+    case 20: return bam_spline(2 * pm * m / M_PI, 4.0 * M_PI * par[1] * N / m, r);
+    case 21: return bam_spline(2 * pm * m / M_PI, 4.0 * M_PI * par[1] / pm, r);
+    default: return 0.0;
+    }
+}
+
+double g2o_accel(g2o * o, int tg, int sg, double pm, double m, double r2, double r, long N) { return accel_fxn(o, tg, sg, pm, m, r2, r, N); }
+double g2o_spline(g2o * o, int tg, int sg, double pm, double m, double h, double r, long N) { return accel_spline(o, tg, sg, pm, m, h, r, N); }
+
+/* ---- life cycle ---- */
+g2o *g2o_create(int D, int periodic, int shortrange, int unequal, int ntab, int maxpart, int maxnodes)
+{
+  g2o *o = calloc(1, sizeof(g2o));
+  int i, j;
+  o->D = D; o->periodic = periodic; o->shortrange = shortrange; o->unequal = unequal; o->ntab = ntab;
+  o->maxpart = maxpart; o->maxnodes = maxnodes;
+  o->P = calloc(maxpart, sizeof(particle));
+  o->top = calloc(MAXTOP, sizeof(topnode));
+  o->dni = calloc(MAXTOP, sizeof(int));
+  o->nodes = calloc((size_t) maxnodes + 1, sizeof(node));
+  o->nextnode = calloc(maxpart, sizeof(int));
+  o->father = calloc(maxpart, sizeof(int));
+  for(i = 0; i < MAXG; i++)
+    for(j = 0; j < MAXG; j++)
+      {
+	o->accel_id[i][j] = 1;
+	o->spline_id[i][j] = 17;
+      }
+  o->G = 1; o->theta = 0.5; o->errtol = 0.005;
+  return o;
+}
+
+void g2o_destroy(g2o * o)
+{
+  if(!o)
+    return;
+  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o);
+}
+
+void g2o_set_species(g2o * o, const int *t2g, const double *fsoft)
+{
+  int t;
+  for(t = 0; t < 6; t++)
+    {
+      o->t2g[t] = t2g[t];
+      o->fsoft[t] = fsoft[t];
+    }
+}
+
+void g2o_set_laws(g2o * o, const int *accel_id, const int *spline_id, const double *par)
+{
+  int i, j, k;
+  for(i = 0; i < o->D; i++)
+    for(j = 0; j < o->D; j++)
+      {
+	o->accel_id[i][j] = accel_id[i * o->D + j];
+	o->spline_id[i][j] = spline_id[i * o->D + j];
+	for(k = 0; k < 4; k++)
+	  o->lawpar[i][j][k] = par ? par[4 * (i * o->D + j) + k] : 0;
+      }
+}
+
+void g2o_set_srtable(g2o * o, const double *tab)
+{
+  size_t n = (size_t) o->D * o->D * o->ntab;
+  free(o->srtab);
+  o->srtab = malloc(sizeof(double) * n);
+  memcpy(o->srtab, tab, sizeof(double) * n);
+}
+
+void g2o_set_params(g2o * o, double boxsize, double G, double theta, double errtol, double asmth, double rcut)
+{
+  o->boxsize = boxsize; o->G = G; o->theta = theta; o->errtol = errtol; o->asmth = asmth; o->rcut = rcut;
+}
+
+int g2o_load(g2o * o, int n, const float *pos, const float *mass, const int *type, const float *oldacc, const int *active)
+{
+  int i, k;
+  if(n > o->maxpart)
+    return -1;
+  o->n = n;
+  for(i = 0; i < n; i++)
+    {
+      particle *p = &o->P[i];
+      memset(p, 0, sizeof(*p));
+      for(k = 0; k < 3; k++)
+	p->pos[k] = pos[3 * i + k];
+      p->mass = mass[i];
+      p->type = type[i];
+      p->id = i;
+      p->oldacc = oldacc ? oldacc[i] : 0;
+      p->active = active ? (active[i] != 0) : 1;
+    }
+  return 0;
+}
+
+/* ---- domain_findExtent, domain.c:882-924 ---- */
+static void find_extent(g2o * o)
+{
+  double xmin[3], xmax[3], len = 0;
+  int i, j;
+  for(j = 0; j < 3; j++)
+    {
+      xmin[j] = 1e37;
+      xmax[j] = -1e37;
+    }
+  for(i = 0; i < o->n; i++)
+    for(j = 0; j < 3; j++)
+      {
+	if(xmin[j] > o->P[i].pos[j])
+	  xmin[j] = o->P[i].pos[j];
+	if(xmax[j] < o->P[i].pos[j])
+	  xmax[j] = o->P[i].pos[j];
+      }
+  for(j = 0; j < 3; j++)
+    if(xmax[j] - xmin[j] > len)
+      len = xmax[j] - xmin[j];
+  len *= 1.001;
+  for(j = 0; j < 3; j++)
+    {
+      o->center[j] = 0.5 * (xmin[j] + xmax[j]);
+      o->corner[j] = 0.5 * (xmin[j] + xmax[j]) - 0.5 * len;
+    }
+  o->len = len;
+  o->fac = 1.0 / len * (((peanokey) 1) << PH_BITS);
+}
+
+static peanokey key_of(const g2o * o, const float *pos)	/* domain.c:940-943 == forcetree.c:144-146 */
+{
+  return g2o_peano_key((int) ((pos[0] - o->corner[0]) * o->fac), (int) ((pos[1] - o->corner[1]) * o->fac),
+		       (int) ((pos[2] - o->corner[2]) * o->fac), PH_BITS);
+}
+
+static int cmp_key(const void *a, const void *b)
+{
+  peanokey x = *(const peanokey *) a, y = *(const peanokey *) b;
+  return (x > y) - (x < y);
+}
+
+/* ---- domain_topsplit_local, domain.c:1019-1075 (NTask = 1: the global pass, 1086-1138, yields the same tree) ---- */
+static void topsplit(g2o * o, const peanokey * sorted, int node, int pstart, peanokey startkey)
+{
+  int i, p, sub, pst[8];
+  topnode *T = o->top;
+  if(T[node].size < 8)
+    return;
+  T[node].daughter = o->ntop;
+  for(i = 0; i < 8; i++)
+    {
+      if(o->ntop >= MAXTOP)
+	{
+	  fprintf(stderr, "g2o: out of top nodes\n");
+	  abort();
+	}
+      sub = T[node].daughter + i;
+      T[sub].size = T[node].size / 8;
+      T[sub].count = 0;
+      T[sub].daughter = -1;
+      T[sub].leaf = -1;
+      T[sub].startkey = startkey + i * T[sub].size;
+      pst[i] = pstart;
+      o->ntop++;
+    }
+  for(p = pstart; p < pstart + T[node].count; p++)
+    {
+      int bin = (int) ((sorted[p] - startkey) / (T[node].size / 8));
+      sub = T[node].daughter + bin;
+      if(T[sub].count == 0)
+	pst[bin] = p;
+      T[sub].count++;
+    }
+  for(i = 0; i < 8; i++)
+    {
+      sub = T[node].daughter + i;
+      if(T[sub].count > o->n / 20.0)	/* TOPNODEFACTOR, domain.c:29,1071 */
+	topsplit(o, sorted, sub, pst[i], T[sub].startkey);
+    }
+}
+
+static void walk_toptree(g2o * o, int no)	/* domain_walktoptree, domain.c:802-816 */
+{
+  int i;
+  if(o->top[no].daughter == -1)
+    o->top[no].leaf = o->ntopleaves++;
+  else
+    for(i = 0; i < 8; i++)
+      walk_toptree(o, o->top[no].daughter + i);
+}
+
+typedef struct { long long block; peanokey key; int index; } sortrec;
+static int cmp_rec(const void *a, const void *b)
+{
+  const sortrec *x = a, *y = b;
+  if(x->block != y->block)
+    return (x->block > y->block) - (x->block < y->block);
+  if(x->key != y->key)
+    return (x->key > y->key) - (x->key < y->key);
+  return (x->index > y->index) - (x->index < y->index);	/* the reference's qsort leaves ties unordered; we pick input order */
+}
+
+/* domain_Decomposition for one rank: extent, keys, top tree (domain.c:882-1138), then peano_hilbert_order
+ * (peano.c:36-185): gas block first, then species-major, Peano-Hilbert within a block. */
+void g2o_domain(g2o * o)
+{
+  double t0 = wall();
+  int i, n = o->n;
+  peanokey *sorted = malloc(sizeof(peanokey) * n);
+  sortrec *rec = malloc(sizeof(sortrec) * n);
+  particle *tmp = malloc(sizeof(particle) * n);
+  find_extent(o);
+  for(i = 0; i < n; i++)
+    sorted[i] = o->P[i].key = key_of(o, o->P[i].pos);
+  qsort(sorted, n, sizeof(peanokey), cmp_key);
+  o->ntop = 1;
+  o->top[0].daughter = -1;
+  o->top[0].leaf = -1;
+  o->top[0].size = ((peanokey) 1) << (3 * PH_BITS);
+  o->top[0].startkey = 0;
+  o->top[0].count = n;
+  topsplit(o, sorted, 0, 0, 0);
+  o->ntopleaves = 0;
+  walk_toptree(o, 0);
+  for(i = 0; i < n; i++)
+    {
+      rec[i].block = o->P[i].type == 0 ? 0 : 1 + o->t2g[o->P[i].type];
+      rec[i].key = o->P[i].key;
+      rec[i].index = i;
+    }
+  qsort(rec, n, sizeof(sortrec), cmp_rec);
+  for(i = 0; i < n; i++)
+    tmp[i] = o->P[rec[i].index];
+  memcpy(o->P, tmp, sizeof(particle) * n);
+  free(tmp);
+  free(rec);
+  free(sorted);
+  o->t_domain = wall() - t0;
+}
+
+/* ---- force_create_empty_nodes, forcetree.c:292-336 ---- */
+static void create_empty_nodes(g2o * o, int no, int topnode_, unsigned state, int *nextfree)
+{
+  int i, j, k, n;
+  if(o->top[topnode_].daughter < 0)
+    return;
+  for(i = 0; i < 2; i++)
+    for(j = 0; j < 2; j++)
+      for(k = 0; k < 2; k++)
+	{
+	  unsigned e = ph_table[state * 8 + (i << 2 | j << 1 | k)];	/* last digit of the child's PH key = TopNodes daughter */
+	  int sub = e & 7, count = i + 2 * j + 4 * k, nf = *nextfree;
+	  node *nd = &o->nodes[nf], *pa = &o->nodes[no];
+	  pa->suns[count] = o->maxpart + nf;
+	  nd->len = 0.5 * pa->len;
+	  nd->center[0] = pa->center[0] + (2 * i - 1) * 0.25 * pa->len;
+	  nd->center[1] = pa->center[1] + (2 * j - 1) * 0.25 * pa->len;
+	  nd->center[2] = pa->center[2] + (2 * k - 1) * 0.25 * pa->len;
+	  for(n = 0; n < 8; n++)
+	    nd->suns[n] = -1;
+	  if(o->top[o->top[topnode_].daughter + sub].daughter == -1)
+	    o->dni[o->top[o->top[topnode_].daughter + sub].leaf] = nf;
+	  *nextfree = nf + 1;
+	  if(*nextfree >= o->maxnodes)
+	    {
+	      fprintf(stderr, "g2o: maximum number of tree nodes reached\n");
+	      abort();
+	    }
+	  create_empty_nodes(o, nf, o->top[topnode_].daughter + sub, e >> 3, nextfree);
+	}
+}
+
+/* children are coded as in the reference but MaxPart-relative: v < 0 empty, v < maxpart particle, else node maxpart+k */
+#define IS_NODE(o, v) ((v) >= (o)->maxpart)
+#define NODE_OF(o, v) (&(o)->nodes[(v) - (o)->maxpart])
+
+/* ---- force_update_node_recursive, forcetree.c:451-743 ---- */
+static void set_next(g2o * o, int no)
+{
+  if(o->last >= 0)
+    {
+      if(IS_NODE(o, o->last))
+	NODE_OF(o, o->last)->nextnode = no;
+      else
+	o->nextnode[o->last] = no;
+    }
+  o->last = no;
+}
+
+static void update_node(g2o * o, int no, int sib, int father)
+{
+  int j, jj, g, p, pp, nextsib, suns[8], D = o->D;
+  double s[3][MAXG], mass[MAXG];
+  int maxsofttype = 7, diffsoftflag = 0;
+  node *nd;
+
+  if(!IS_NODE(o, no))
+    {
+      set_next(o, no);
+      o->father[no] = father;
+      return;
+    }
+  nd = NODE_OF(o, no);
+  for(j = 0; j < 8; j++)
+    suns[j] = nd->suns[j];
+  set_next(o, no);
+  for(g = 0; g < D; g++)
+    s[0][g] = s[1][g] = s[2][g] = mass[g] = 0;
+
+  for(j = 0; j < 8; j++)
+    {
+      if((p = suns[j]) < 0)
+	continue;
+      for(jj = j + 1; jj < 8; jj++)
+	if((pp = suns[jj]) >= 0)
+	  break;
+      nextsib = jj < 8 ? pp : sib;
+      update_node(o, p, nextsib, no);
+      if(IS_NODE(o, p))
+	{
+	  node *ch = NODE_OF(o, p);
+	  int ct = (ch->bitflags >> 2) & 7;
+	  for(g = 0; g < D; g++)
+	    {
+	      mass[g] += ch->mass[g];
+	      s[0][g] += ch->mass[g] * ch->s[0][g];
+	      s[1][g] += ch->mass[g] * ch->s[1][g];
+	      s[2][g] += ch->mass[g] * ch->s[2][g];
+	    }
+	  if(o->unequal)
+	    {			/* forcetree.c:570-597 */
+	      diffsoftflag |= (ch->bitflags >> 5) & 1;
+	      if(maxsofttype == 7)
+		maxsofttype = ct;
+	      else if(ct != 7)
+		{
+		  if(o->fsoft[ct] > o->fsoft[maxsofttype])
+		    {
+		      maxsofttype = ct;
+		      diffsoftflag = 1;
+		    }
+		  else if(o->fsoft[ct] < o->fsoft[maxsofttype])
+		    diffsoftflag = 1;
+		}
+	    }
+	}
+      else
+	{
+	  particle *pa = &o->P[p];
+	  g = o->t2g[pa->type];
+	  mass[g] += pa->mass;
+	  s[0][g] += pa->mass * pa->pos[0];
+	  s[1][g] += pa->mass * pa->pos[1];
+	  s[2][g] += pa->mass * pa->pos[2];
+	  if(o->unequal)
+	    {			/* forcetree.c:628-646 */
+	      if(maxsofttype == 7)
+		maxsofttype = pa->type;
+	      else if(o->fsoft[pa->type] > o->fsoft[maxsofttype])
+		{
+		  maxsofttype = pa->type;
+		  diffsoftflag = 1;
+		}
+	      else if(o->fsoft[pa->type] < o->fsoft[maxsofttype])
+		diffsoftflag = 1;
+	    }
+	}
+    }
+  for(g = 0; g < D; g++)
+    {
+      if(mass[g] > 0)
+	{
+	  s[0][g] /= mass[g];
+	  s[1][g] /= mass[g];
+	  s[2][g] /= mass[g];
+	}
+      else
+	{
+	  s[0][g] = nd->center[0];
+	  s[1][g] = nd->center[1];
+	  s[2][g] = nd->center[2];
+	}
+      nd->s[0][g] = s[0][g];
+      nd->s[1][g] = s[1][g];
+      nd->s[2][g] = s[2][g];
+      nd->mass[g] = mass[g];
+    }
+  nd->bitflags = o->unequal ? 4 * maxsofttype + 32 * diffsoftflag : 0;
+  nd->sibling = sib;
+  nd->father = father;
+}
+
+/* ---- force_treebuild, forcetree.c:61-281 + force_flag_localnodes 954-996 ---- */
+int g2o_treebuild(g2o * o)
+{
+  double t0 = wall();
+  int i, j, nfree, numnodes, subnode = 0, parent = -1, th, nn, no;
+  const int MP = o->maxpart;
+  node *root = &o->nodes[0];
+
+  root->len = o->len;
+  for(j = 0; j < 3; j++)
+    root->center[j] = o->center[j];
+  for(j = 0; j < 8; j++)
+    root->suns[j] = -1;
+  nfree = 1;
+  if(o->top[0].daughter == -1)
+    o->dni[o->top[0].leaf] = 0;
+  create_empty_nodes(o, 0, 0, 0, &nfree);
+  numnodes = nfree;
+  /* node indices below are reference-style (MaxPart-based); nfree counts MaxPart-relative */
+  for(i = 0; i < o->n; i++)
+    {
+      const float *pos = o->P[i].pos;
+      peanokey key = key_of(o, pos);
+      no = 0;
+      while(o->top[no].daughter >= 0)
+	no = o->top[no].daughter + (int) ((key - o->top[no].startkey) / (o->top[no].size / 8));
+      th = MP + o->dni[o->top[no].leaf];
+      while(1)
+	{
+	  if(th >= MP)
+	    {
+	      node *t = NODE_OF(o, th);
+	      subnode = (pos[0] > t->center[0]) + 2 * (pos[1] > t->center[1]) + 4 * (pos[2] > t->center[2]);
+	      nn = t->suns[subnode];
+	      if(nn >= 0)
+		{
+		  parent = th;
+		  th = nn;
+		}
+	      else
+		{
+		  t->suns[subnode] = i;
+		  break;
+		}
+	    }
+	  else
+	    {			/* a leaf holding particle th: make a node (forcetree.c:183-247) */
+	      node *pa = NODE_OF(o, parent), *nw = &o->nodes[nfree];
+	      double lenhalf = 0.25 * pa->len;
+	      pa->suns[subnode] = MP + nfree;
+	      nw->len = 0.5 * pa->len;
+	      nw->center[0] = (subnode & 1) ? pa->center[0] + lenhalf : pa->center[0] - lenhalf;
+	      nw->center[1] = (subnode & 2) ? pa->center[1] + lenhalf : pa->center[1] - lenhalf;
+	      nw->center[2] = (subnode & 4) ? pa->center[2] + lenhalf : pa->center[2] - lenhalf;
+	      for(j = 0; j < 8; j++)
+		nw->suns[j] = -1;
+	      subnode = (o->P[th].pos[0] > nw->center[0]) + 2 * (o->P[th].pos[1] > nw->center[1]) + 4 * (o->P[th].pos[2] > nw->center[2]);
+	      nw->suns[subnode] = th;
+	      th = MP + nfree;
+	      numnodes++;
+	      nfree++;
+	      if(numnodes >= o->maxnodes)
+		{
+		  fprintf(stderr, "g2o: maximum number %d of tree-nodes reached\n", o->maxnodes);
+		  abort();
+		}
+	    }
+	}
+    }
+  o->last = -1;
+  update_node(o, MP, -1, -1);
+  if(IS_NODE(o, o->last))
+    NODE_OF(o, o->last)->nextnode = -1;
+  else
+    o->nextnode[o->last] = -1;
+  /* force_flag_localnodes: with one rank every top-level node gets bits 0 and 1 */
+  for(i = 0; i < o->ntopleaves; i++)
+    {
+      no = MP + o->dni[i];
+      while(no >= 0 && !(NODE_OF(o, no)->bitflags & 1))
+	{
+	  NODE_OF(o, no)->bitflags |= 3;
+	  no = NODE_OF(o, no)->father;
+	}
+    }
+  o->numnodes = numnodes;
+  o->t_build = wall() - t0;
+  return numnodes;
+}
+
+/* ---- force_treeevaluate (forcetree.c:1244-1610) and force_treeevaluate_shortrange (1623-2052) ---- */
+#define NEAREST(x) (((x) > boxhalf) ? ((x) - boxsize) : (((x) < -boxhalf) ? ((x) + boxsize) : (x)))
+
+static int tree_evaluate(g2o * o, int target)
+{
+  const int D = o->D, MP = o->maxpart, SR = o->shortrange, PER = o->periodic;
+  const particle *tp = &o->P[target];
+  double r2[MAXG], dx[MAXG], dy[MAXG], dz[MAXG], mass[MAXG], r, fac, h;
+  double acc_x = 0, acc_y = 0, acc_z = 0;
+  const double pos_x = tp->pos[0], pos_y = tp->pos[1], pos_z = tp->pos[2];
+  const int ptype = tp->type, pg = o->t2g[ptype];
+  const double pmass = tp->mass, aold = o->errtol * tp->oldacc;
+  const double boxsize = o->boxsize, boxhalf = 0.5 * o->boxsize;
+  const double rcut = o->rcut, rcut2 = rcut * rcut, asmth = o->asmth;
+  const double asmthfac = SR ? 0.5 / asmth * (o->ntab / 3.0) : 0, utor2wpi = SR ? 1.0 / (M_PI * 4 * asmth * asmth) : 0;
+  int ninteractions = 0, no = MP, sG, g;
+  node *nop = 0;
+
+  h = o->fsoft[ptype];
+  while(no >= 0)
+    {
+      if(no < MP)
+	{
+	  const particle *sp = &o->P[no];
+	  sG = o->t2g[sp->type];
+	  mass[sG] = sp->mass;
+	  dx[sG] = sp->pos[0] - pos_x;
+	  dy[sG] = sp->pos[1] - pos_y;
+	  dz[sG] = sp->pos[2] - pos_z;
+	  if(PER)
+	    {
+	      dx[sG] = NEAREST(dx[sG]);
+	      dy[sG] = NEAREST(dy[sG]);
+	      dz[sG] = NEAREST(dz[sG]);
+	    }
+	  r2[sG] = dx[sG] * dx[sG] + dy[sG] * dy[sG] + dz[sG] * dz[sG];
+	  if(o->unequal)
+	    {
+	      h = o->fsoft[ptype];
+	      if(h < o->fsoft[sp->type])
+		h = o->fsoft[sp->type];
+	    }
+	  no = o->nextnode[no];
+	}
+      else
+	{
+	  double r2min = INFINITY, r2max = -INFINITY, summass = 0;
+	  nop = NODE_OF(o, no);
+	  for(g = 0; g < D; g++)
+	    {
+	      mass[g] = nop->mass[g];
+	      summass += nop->mass[g];
+	      dx[g] = nop->s[0][g] - pos_x;
+	      dy[g] = nop->s[1][g] - pos_y;
+	      dz[g] = nop->s[2][g] - pos_z;
+	      if(PER)
+		{
+		  dx[g] = NEAREST(dx[g]);
+		  dy[g] = NEAREST(dy[g]);
+		  dz[g] = NEAREST(dz[g]);
+		}
+	      r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
+	      if(r2[g] < r2min)
+		r2min = r2[g];
+	      if(r2[g] > r2max)
+		r2max = r2[g];
+	    }
+	  sG = -1;
+	  if(SR && r2min > rcut2)
+	    {			/* forcetree.c:1828-1862 */
+	      double eff_dist = rcut + 0.5 * nop->len, dist;
+	      int k, cull = 0;
+	      const double pp[3] = { pos_x, pos_y, pos_z };
+	      for(k = 0; k < 3 && !cull; k++)
+		{
+		  dist = nop->center[k] - pp[k];
+		  if(PER)
+		    dist = NEAREST(dist);
+		  if(dist < -eff_dist || dist > eff_dist)
+		    cull = 1;
+		}
+	      if(cull)
+		{
+		  no = nop->sibling;
+		  continue;
+		}
+	    }
+	  if(o->theta)
+	    {
+	      if(nop->len * nop->len > r2min * o->theta * o->theta)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  else
+	    {
+	      if(summass * nop->len * nop->len > r2min * r2min * aold)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	      if(fabs(nop->center[0] - pos_x) < 0.60 * nop->len && fabs(nop->center[1] - pos_y) < 0.60 * nop->len
+		 && fabs(nop->center[2] - pos_z) < 0.60 * nop->len)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  if(o->unequal)
+	    {			/* forcetree.c:1475-1501 */
+	      int maxsofttype = (nop->bitflags >> 2) & 7;
+	      h = o->fsoft[ptype];
+	      if(maxsofttype == 7)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	      if(h < o->fsoft[maxsofttype])
+		{
+		  h = o->fsoft[maxsofttype];
+		  if(r2max < h * h && ((nop->bitflags >> 5) & 1))
+		    {
+		      no = nop->nextnode;
+		      continue;
+		    }
+		}
+	    }
+	  no = nop->sibling;
+	}
+
+      if(!SR)
+	{			/* forcetree.c:1538-1585 */
+	  for(g = (sG > -1 ? sG : 0); g < (sG > -1 ? sG + 1 : D); g++)
+	    {
+	      if(sG < 0 && mass[g] == 0.0)
+		continue;
+	      r = sqrt(r2[g]);
+	      if(r >= h)
+		fac = accel_fxn(o, pg, g, pmass, mass[g], r2[g], r, 1) / r;
+	      else
+		fac = accel_spline(o, pg, g, pmass, mass[g], h, r, 1);
+	      acc_x += dx[g] * fac;
+	      acc_y += dy[g] * fac;
+	      acc_z += dz[g] * fac;
+	    }
+	  ninteractions++;
+	}
+      else
+	{			/* forcetree.c:1955-2032 */
+	  int nintflag = 0;
+	  for(g = (sG > -1 ? sG : 0); g < (sG > -1 ? sG + 1 : D); g++)
+	    {
+	      int tabindex;
+	      if(sG < 0 && mass[g] == 0.0)
+		continue;
+	      r = sqrt(r2[g]);
+	      tabindex = (int) (asmthfac * r);
+	      if(tabindex < o->ntab)
+		{
+		  if(r >= h)
+		    {
+		      fac = accel_fxn(o, pg, g, pmass, mass[g], r2[g], r, 1);
+		      fac -= mass[g] * utor2wpi * o->srtab[((size_t) pg * D + g) * o->ntab + tabindex];
+		      fac /= r;
+		    }
+		  else
+		    fac = accel_spline(o, pg, g, pmass, mass[g], h, r, 1);
+		  acc_x += dx[g] * fac;
+		  acc_y += dy[g] * fac;
+		  acc_z += dz[g] * fac;
+		  nintflag = 1;
+		}
+	    }
+	  if(nintflag)
+	    ninteractions++;
+	}
+    }
+  o->P[target].accd[0] = acc_x;
+  o->P[target].accd[1] = acc_y;
+  o->P[target].accd[2] = acc_z;
+  o->P[target].acc[0] = acc_x;
+  o->P[target].acc[1] = acc_y;
+  o->P[target].acc[2] = acc_z;
+  o->P[target].cost = ninteractions;
+  return ninteractions;
+}
+
+struct slice { g2o *o; int lo, hi; double cost; };
+static void *walk_slice(void *arg)
+{
+  struct slice *s = arg;
+  int i;
+  s->cost = 0;
+  for(i = s->lo; i < s->hi; i++)
+    if(s->o->P[i].active)
+      s->cost += tree_evaluate(s->o, i);
+  return NULL;
+}
+
+/* the walk loop of gravity_tree (gravtree.c:112-123) over targets [lo,hi), optionally on several threads
+ * (targets are independent: forcetree.c:1590-1596) */
+double g2o_walk_range(g2o * o, int lo, int hi, int nthreads, double *cost)
+{
+  pthread_t *th;
+  struct slice *sl;
+  int t, n = hi - lo;
+  double t0 = wall();
+  if(nthreads < 1)
+    nthreads = 1;
+  th = malloc(sizeof(pthread_t) * nthreads);
+  sl = malloc(sizeof(struct slice) * nthreads);
+  for(t = 0; t < nthreads; t++)
+    {
+      sl[t].o = o;
+      sl[t].lo = lo + (int) ((long long) n * t / nthreads);
+      sl[t].hi = lo + (int) ((long long) n * (t + 1) / nthreads);
+      pthread_create(&th[t], NULL, walk_slice, &sl[t]);
+    }
+  *cost = 0;
+  for(t = 0; t < nthreads; t++)
+    {
+      pthread_join(th[t], NULL);
+      *cost += sl[t].cost;
+    }
+  free(sl);
+  free(th);
+  return wall() - t0;
+}
+
+/* gravity_tree epilogue, gravtree.c:318-341: OldAcc from the pre-G acceleration, then the G scaling */
+void g2o_epilogue(g2o * o, int use_gravpm)
+{
+  int i, j;
+  for(i = 0; i < o->n; i++)
+    if(o->P[i].active)
+      {
+	particle *p = &o->P[i];
+	double a[3];
+	for(j = 0; j < 3; j++)
+	  a[j] = use_gravpm ? p->acc[j] + p->gravpm[j] / o->G : p->acc[j];
+	p->oldacc = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+	for(j = 0; j < 3; j++)
+	  p->acc[j] *= o->G;
+      }
+}
+
+/* gravity_tree (gravtree.c:27-460) for one rank: build, walk all active particles, epilogue */
+double g2o_gravity_tree(g2o * o, int nthreads)
+{
+  double cost, t;
+  g2o_treebuild(o);
+  t = g2o_walk_range(o, 0, o->n, nthreads, &cost);
+  o->t_walk = t;
+  g2o_epilogue(o, 0);
+  return cost;
+}
+
+/* ---- force_treeevaluate_direct, forcetree.c:3428-3548 (non-periodic form) ---- */
+void g2o_direct(g2o * o, int ntargets, const int *targets, double *acc)
+{
+  int t, i;
+  for(t = 0; t < ntargets; t++)
+    {
+      const particle *tp = &o->P[targets[t]];
+      const int pg = o->t2g[tp->type];
+      double ax = 0, ay = 0, az = 0;
+      for(i = 0; i < o->n; i++)
+	{
+	  const particle *sp = &o->P[i];
+	  double h = o->fsoft[sp->type] > o->fsoft[tp->type] ? o->fsoft[sp->type] : o->fsoft[tp->type];
+	  double dx = sp->pos[0] - (double) tp->pos[0], dy = sp->pos[1] - (double) tp->pos[1], dz = sp->pos[2] - (double) tp->pos[2];
+	  double r2 = dx * dx + dy * dy + dz * dz, r = sqrt(r2), fac;
+	  if(r * (1 / h) >= 1)
+	    fac = accel_fxn(o, pg, o->t2g[sp->type], tp->mass, sp->mass, r2, r, 1) / r;
+	  else
+	    fac = accel_spline(o, pg, o->t2g[sp->type], tp->mass, sp->mass, h, r, 1);
+	  ax += dx * fac;
+	  ay += dy * fac;
+	  az += dz * fac;
+	}
+      acc[3 * t] = ax;
+      acc[3 * t + 1] = ay;
+      acc[3 * t + 2] = az;
+    }
+}
+
+/* ---- short-range table: performConvolution (ngravs_core.c:72-159) + fill loop (forcetree.c:3274-3354) for the
+ *      Newtonian normalised Green's function normed_pgdelta = 1 (ngravs.c:400) or the normalised Yukawa one
+ *      (ngravs.c:880-885, ym in table units).  n = 12*NTAB*ol*len - 6*ol*len + 2 samples, Z = 0.5.
+ *      The backward DFT of the reference (FFTW-2, not vendored) is restated with a Bluestein transform. ---- */
+typedef struct { double re, im; } cpx;
+static void fft2(cpx * a, int n, int dir)
+{
+  int i, j, len;
+  for(i = 1, j = 0; i < n; i++)
+    {
+      int bit = n >> 1;
+      for(; j & bit; bit >>= 1)
+	j ^= bit;
+      j ^= bit;
+      if(i < j)
+	{
+	  cpx t = a[i];
+	  a[i] = a[j];
+	  a[j] = t;
+	}
+    }
+  for(len = 2; len <= n; len <<= 1)
+    {
+      int half = len / 2, k;
+      for(k = 0; k < half; k++)
+	{
+	  double ang = dir * 2.0 * M_PI * k / len, wr = cos(ang), wi = sin(ang);
+	  for(i = k; i < n; i += len)
+	    {
+	      cpx u = a[i], v = a[i + half], t;
+	      t.re = v.re * wr - v.im * wi;
+	      t.im = v.re * wi + v.im * wr;
+	      a[i].re = u.re + t.re;
+	      a[i].im = u.im + t.im;
+	      a[i + half].re = u.re - t.re;
+	      a[i + half].im = u.im - t.im;
+	    }
+	}
+    }
+}
+
+static void dft_any(const cpx * in, cpx * out, int n, int dir)
+{
+  int m = 1, k;
+  cpx *w, *a, *b;
+  while(m < 2 * n - 1)
+    m <<= 1;
+  w = malloc(sizeof(cpx) * n);
+  a = calloc(m, sizeof(cpx));
+  b = calloc(m, sizeof(cpx));
+  for(k = 0; k < n; k++)
+    {
+      long long k2 = ((long long) k * k) % (2LL * n);
+      double ang = dir * M_PI * (double) k2 / n;
+      w[k].re = cos(ang);
+      w[k].im = sin(ang);
+      a[k].re = in[k].re * w[k].re - in[k].im * w[k].im;
+      a[k].im = in[k].re * w[k].im + in[k].im * w[k].re;
+    }
+  b[0].re = w[0].re;
+  b[0].im = -w[0].im;
+  for(k = 1; k < n; k++)
+    {
+      b[k].re = b[m - k].re = w[k].re;
+      b[k].im = b[m - k].im = -w[k].im;
+    }
+  fft2(a, m, -1);
+  fft2(b, m, -1);
+  for(k = 0; k < m; k++)
+    {
+      cpx t;
+      t.re = a[k].re * b[k].re - a[k].im * b[k].im;
+      t.im = a[k].re * b[k].im + a[k].im * b[k].re;
+      a[k] = t;
+    }
+  fft2(a, m, +1);
+  for(k = 0; k < n; k++)
+    {
+      double re = a[k].re / m, im = a[k].im / m;
+      out[k].re = re * w[k].re - im * w[k].im;
+      out[k].im = re * w[k].im + im * w[k].re;
+    }
+  free(b);
+  free(a);
+  free(w);
+}
+
+/* kind 0: Newtonian (normed Green's function 1); kind 1: Yukawa with ym (already in table units) */
+int g2o_make_srtable(int ntab, int kind, double ym, double *force_tab)
+{
+  const int len = 3, ol = 8;
+  const int n = 12 * ntab * ol * len - 6 * ol * len + 2;	/* ngravs_core.c:179 */
+  const double Z = 0.5;
+  const double dk = 2.0 * M_PI * ntab * 6.0 * ol / (3.0 * n);	/* jTok, ngravs_core.c:45-48; also `norm` at :114 */
+  cpx *in = calloc(n, sizeof(cpx)), *out = calloc(n, sizeof(cpx));
+  double *cum = calloc(n / 3 + 2, sizeof(double));
+  double sum = 0;
+  int j, m, i;
+  if(!in || !out || !cum)
+    return 1;
+  for(j = 0; j < n / 2; j++)
+    {
+      double k = dk * j, k2 = k * k, gk = 1.0;
+      if(kind == 1)
+	gk = k2 / (k2 + ym * ym) * exp(-ym * ym * 0.25);
+      in[j].re = gk * exp(-k2 * Z * Z);		/* fourierIntegrand, ngravs_core.c:65-70 */
+      if(j > 0)
+	in[n - j].re = in[j].re;
+    }
+  dft_any(in, out, n, +1);
+  /* cumulative Newton-Cotes 3/8 integral of the transform (ngravs_core.c:131-141); x spacing = mTox(1) */
+  for(m = 0; m < n - 3; m += 3)
+    {
+      double dx = 3.0 * (m + 3) / (6.0 * ntab * ol) - 3.0 * m / (6.0 * ntab * ol);
+      sum += dx * 0.125 * dk * (out[m].re + 3.0 * out[m + 1].re + 3.0 * out[m + 2].re + out[m + 3].re);
+      cum[m / 3 + 1] = sum;
+    }
+  for(i = 0; i < ntab; i++)
+    {
+      int f = ol * (6 * i + 3);			/* gadgetToFourier, ngravs_core.c:55-58 */
+      double temp = out[f].re * dk, tempI = cum[f / 3];
+      double u = 3.0 / ntab * (i + 0.5);		/* forcetree.c:3335 */
+      force_tab[i] = tempI / (u * u) - temp / u;	/* forcetree.c:3345-3353 */
+    }
+  free(cum);
+  free(out);
+  free(in);
+  return 0;
+}
+
+/* ---- read-back ---- */
+void g2o_get_domain(g2o * o, double *out)
+{
+  int k;
+  for(k = 0; k < 3; k++)
+    {
+      out[k] = o->corner[k];
+      out[3 + k] = o->center[k];
+    }
+  out[6] = o->len;
+  out[7] = o->fac;
+}
+
+int g2o_counts(g2o * o, int *out)
+{
+  out[0] = o->n; out[1] = o->ntop; out[2] = o->ntopleaves; out[3] = o->numnodes;
+  return 0;
+}
+
+void g2o_get_particles(g2o * o, float *pos, float *mass, int *type, int *id, long long *key, float *acc, float *cost, float *oldacc, double *accd)
+{
+  int i, k;
+  for(i = 0; i < o->n; i++)
+    {
+      const particle *p = &o->P[i];
+      for(k = 0; k < 3; k++)
+	{
+	  if(pos) pos[3 * i + k] = p->pos[k];
+	  if(acc) acc[3 * i + k] = p->acc[k];
+	  if(accd) accd[3 * i + k] = p->accd[k];
+	}
+      if(mass) mass[i] = p->mass;
+      if(type) type[i] = p->type;
+      if(id) id[i] = p->id;
+      if(key) key[i] = p->key;
+      if(cost) cost[i] = p->cost;
+      if(oldacc) oldacc[i] = p->oldacc;
+    }
+}
+
+void g2o_get_topnodes(g2o * o, long long *tn /* 5 per node */, int *dni)
+{
+  int i;
+  for(i = 0; i < o->ntop; i++)
+    {
+      tn[5 * i] = o->top[i].daughter;
+      tn[5 * i + 1] = o->top[i].leaf;
+      tn[5 * i + 2] = o->top[i].size;
+      tn[5 * i + 3] = o->top[i].startkey;
+      tn[5 * i + 4] = o->top[i].count;
+    }
+  for(i = 0; i < o->ntopleaves; i++)
+    dni[i] = o->maxpart + o->dni[i];
+}
+
+void g2o_get_tree(g2o * o, float *len, float *center, float *s, float *mass, int *link, int *nextnode, int *father)
+{
+  int k, j, g, D = o->D;
+  for(k = 0; k < o->numnodes; k++)
+    {
+      const node *nd = &o->nodes[k];
+      len[k] = nd->len;
+      for(j = 0; j < 3; j++)
+	{
+	  center[3 * k + j] = nd->center[j];
+	  for(g = 0; g < D; g++)
+	    s[(3 * k + j) * D + g] = nd->s[j][g];
+	}
+      for(g = 0; g < D; g++)
+	mass[k * D + g] = nd->mass[g];
+      link[4 * k] = nd->bitflags;
+      link[4 * k + 1] = nd->sibling;
+      link[4 * k + 2] = nd->nextnode;
+      link[4 * k + 3] = nd->father;
+    }
+  for(k = 0; k < o->n; k++)
+    {
+      nextnode[k] = o->nextnode[k];
+      father[k] = o->father[k];
+    }
+}
+
+void g2o_timings(g2o * o, double *out)
+{
+  out[0] = o->t_domain;
+  out[1] = o->t_build;
+  out[2] = o->t_walk;
+}

@@ -1,0 +1,53 @@
+"""CPU tests (no GPU): the C-ABI library loads, exports every symbol include/g2gpu.h declares, and fails loudly
+(never falls back to a CPU path) when no device is present."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "g2gpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(g2gpu_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import g2gpu
+    lib = g2gpu.load_library()
+    names = declared_symbols()
+    assert len(names) >= 28
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/g2gpu.h but not exported by libg2gpu.so"
+    assert set(g2gpu.EXPORTED) == set(names)
+
+
+def test_struct_layouts_match_header():
+    import g2gpu
+    assert C.sizeof(g2gpu.Config) == 10 * 4
+    assert C.sizeof(g2gpu.WalkParams) == 8 * 8 + 8
+
+
+def test_no_cpu_fallback_without_device():
+    import g2gpu
+    lib = g2gpu.load_library()
+    if lib.g2gpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(g2gpu.G2Error) as e:
+        g2gpu.TreeGravity(max_part=1000)
+    assert e.value.code == -1
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product tree (package + include) must not import, link or mention oracle code paths."""
+    pkg = os.path.join(ROOT, "gadget-2.0.7-ngravs_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".c", ".h", ".py", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "g2_oracle" not in txt and "libg2oracle" not in txt and "g2ref" not in txt and "portrun" not in txt and "refrun" not in txt, f
