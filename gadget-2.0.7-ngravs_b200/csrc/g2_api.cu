@@ -72,6 +72,8 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   const int R = 2 + c->D;
   int rc = 0;
   rc |= dalloc(&c->in_pm, np); rc |= dalloc(&c->in_type, np); rc |= dalloc(&c->in_oldacc, np); rc |= dalloc(&c->in_active, np);
+  rc |= dalloc(&c->in_raw, 4 * np);
+  c->own_in_pm = c->in_pm; c->own_in_type = c->in_type; c->own_in_oldacc = c->in_oldacc; c->own_in_active = c->in_active;
   rc |= dalloc(&c->pm, np); rc |= dalloc(&c->ptype, np); rc |= dalloc(&c->oldacc, np); rc |= dalloc(&c->active, np);
   rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np);
   rc |= dalloc(&c->skey[0], np); rc |= dalloc(&c->skey[1], np); rc |= dalloc(&c->sval[0], np); rc |= dalloc(&c->sval[1], np);
@@ -120,7 +122,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
   cudaSetDevice(c->cfg.device);
   if(c->stream)
     cudaStreamSynchronize(c->stream);
-  void *ptrs[] = { c->in_pm, c->in_type, c->in_oldacc, c->in_active, c->in_vel, c->in_gravpm, c->pm, c->ptype, c->oldacc, c->active, c->vel, c->gravpm,
+  void *ptrs[] = { c->own_in_pm, c->own_in_type, c->own_in_oldacc, c->own_in_active, c->in_raw, c->in_vel, c->in_gravpm, c->pm, c->ptype, c->oldacc, c->active, c->vel, c->gravpm,
     c->phkey, c->perm, c->skey[0], c->skey[1], c->sval[0], c->sval[1], c->tilehist, c->scan_tmp, c->d_domain, c->d_minmax, c->d_top, c->d_topscratch,
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
@@ -257,6 +259,17 @@ static int ensure_opt(g2gpu_ctx *c, int want_vel, int want_gravpm)
   return 0;
 }
 
+// SoA arrays go to the device as they are (no host-side repacking); pack_inputs_kernel builds the float4 records.
+__global__ void __launch_bounds__(256) pack_inputs_kernel(int n, const float *__restrict__ pos3, const float *__restrict__ mass,
+							   const int *__restrict__ active_i, float4 *__restrict__ pm, unsigned char *__restrict__ active)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  pm[i] = make_float4(pos3[3 * (size_t) i], pos3[3 * (size_t) i + 1], pos3[3 * (size_t) i + 2], mass[i]);
+  active[i] = active_i ? (active_i[i] != 0) : 1;
+}
+
 extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
 			    const float *vel, const float *gravpm, const int *active)
 {
@@ -266,36 +279,34 @@ extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const flo
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
   G2_CUDA(cudaSetDevice(c->cfg.device));
   G2_TRY(ensure_opt(c, vel != nullptr, gravpm != nullptr));
-  const size_t n = (size_t) npart;
-  // pack into one pinned staging buffer: float4 pos+mass | int type | float oldacc | u8 active
-  size_t bytes = n * (16 + 4 + 4 + 1) + 64;
-  G2_TRY(ensure_stage(c, bytes));
-  float4 *s_pm = (float4 *) c->h_stage;
-  int *s_type = (int *) (s_pm + n);
-  float *s_old = (float *) (s_type + n);
-  unsigned char *s_act = (unsigned char *) (s_old + n);
-  for(size_t i = 0; i < n; i++)
-    {
-      s_pm[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], mass[i]);
-      int t = type[i];
-      if(t < 0 || t > 5)
-	return g2_fail(G2GPU_ERR_ARG, "particle %zu has type %d", i, t);
-      s_type[i] = t;
-      s_old[i] = oldacc ? oldacc[i] : 0.0f;
-      s_act[i] = active ? (active[i] != 0) : 1;
+  if(c->inputs_bound)
+    {				// back to the library's own input buffers
+      c->in_pm = c->own_in_pm; c->in_type = c->own_in_type; c->in_oldacc = c->own_in_oldacc; c->in_active = c->own_in_active;
+      c->inputs_bound = 0;
     }
+  const size_t n = (size_t) npart;
   cudaStream_t st = c->stream;
+  float *d_pos3 = c->in_raw, *d_mass = c->in_raw + 3 * n;
+  int *d_act = (int *) c->w_flags;
   G2_CUDA(cudaEventRecord(c->ev[9], st));
-  G2_CUDA(cudaMemcpyAsync(c->in_pm, s_pm, n * 16, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(c->in_type, s_type, n * 4, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(c->in_oldacc, s_old, n * 4, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(c->in_active, s_act, n, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(d_pos3, pos, n * 12, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(d_mass, mass, n * 4, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(c->in_type, type, n * 4, cudaMemcpyHostToDevice, st));
+  if(oldacc)
+    G2_CUDA(cudaMemcpyAsync(c->in_oldacc, oldacc, n * 4, cudaMemcpyHostToDevice, st));
+  else
+    G2_CUDA(cudaMemsetAsync(c->in_oldacc, 0, n * 4, st));
+  if(active)
+    G2_CUDA(cudaMemcpyAsync(d_act, active, n * 4, cudaMemcpyHostToDevice, st));
   if(vel)
     G2_CUDA(cudaMemcpyAsync(c->in_vel, vel, n * 12, cudaMemcpyHostToDevice, st));
   if(gravpm)
     G2_CUDA(cudaMemcpyAsync(c->in_gravpm, gravpm, n * 12, cudaMemcpyHostToDevice, st));
+  pack_inputs_kernel<<<g2_cdiv(npart, 256), 256, 0, st>>>(npart, d_pos3, d_mass, active ? d_act : nullptr, c->in_pm, c->in_active);
+  c->launches++;
   G2_CUDA(cudaEventRecord(c->ev[10], st));
-  G2_CUDA(cudaStreamSynchronize(st));	// the staging buffer is reused by the next call
+  G2_CUDA(cudaGetLastError());
+  c->h2d_bytes = n * (12 + 4 + 4 + (oldacc ? 4 : 0) + (active ? 4 : 0) + (vel ? 12 : 0) + (gravpm ? 12 : 0));
   c->have_vel = vel != nullptr;
   c->have_gravpm = gravpm != nullptr;
   c->npart = npart;
@@ -348,10 +359,28 @@ extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **ptrs)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(npart < 1 || npart > c->cfg.max_part)
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
-  ptrs[0] = c->in_pm;
-  ptrs[1] = c->in_type;
-  ptrs[2] = c->in_oldacc;
-  ptrs[3] = c->in_active;
+  ptrs[0] = c->own_in_pm;
+  ptrs[1] = c->own_in_type;
+  ptrs[2] = c->own_in_oldacc;
+  ptrs[3] = c->own_in_active;
+  return 0;
+}
+
+extern "C" int g2gpu_bind_inputs(g2gpu_ctx *c, int npart, void *posmass, void *type, void *oldacc, void *active)
+{
+  if(!c || !posmass || !type || !oldacc || !active)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(npart < 1 || npart > c->cfg.max_part)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  c->in_pm = (float4 *) posmass;
+  c->in_type = (int *) type;
+  c->in_oldacc = (float *) oldacc;
+  c->in_active = (unsigned char *) active;
+  c->inputs_bound = 1;
+  c->have_vel = 0;
+  c->have_gravpm = 0;
+  c->npart = npart;
+  c->stage = 1;
   return 0;
 }
 
@@ -361,6 +390,8 @@ extern "C" int g2gpu_inputs_ready(g2gpu_ctx *c, int npart)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(npart < 1 || npart > c->cfg.max_part)
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  c->in_pm = c->own_in_pm; c->in_type = c->own_in_type; c->in_oldacc = c->own_in_oldacc; c->in_active = c->own_in_active;
+  c->inputs_bound = 0;
   c->have_vel = 0;
   c->have_gravpm = 0;
   c->npart = npart;
@@ -529,6 +560,7 @@ extern "C" int g2gpu_download_acc(g2gpu_ctx *c, float *acc, float *cost, float *
     G2_CUDA(cudaMemcpyAsync(oldacc, c->oldacc_out, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaEventRecord(c->ev[12], st));
   G2_CUDA(cudaStreamSynchronize(st));
+  c->d2h_bytes = n * ((acc ? 12 : 0) + (cost ? 4 : 0) + (oldacc ? 4 : 0));
   return 0;
 }
 
@@ -581,9 +613,18 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[4])
 	  G2_CUDA(cudaMemcpy(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	  counters[1] = (long long) c->h_counters[0];
 	  counters[2] = (long long) c->h_counters[1];
-	  counters[3] = c->w_hi - c->w_lo;
+	  counters[3] = (long long) c->h_counters[2];
 	}
     }
+  return 0;
+}
+
+extern "C" int g2gpu_io_bytes(g2gpu_ctx *c, long long out[2])
+{
+  if(!c || !out)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  out[0] = (long long) c->h2d_bytes;
+  out[1] = (long long) c->d2h_bytes;
   return 0;
 }
 

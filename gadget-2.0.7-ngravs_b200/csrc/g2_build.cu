@@ -869,7 +869,6 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   const int maxcells = c->cfg.max_nodes;
   cudaStream_t st = c->stream;
   G2_CUDA(cudaEventRecord(c->ev[4], st));
-  G2_CUDA(cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), st));
 
   // 1. keys + sort (keys live in the sort ping-pong buffers)
   unsigned short *ptl = (unsigned short *) c->w_flags;	// per-particle top node, scratch reuse (n * 2 bytes)
@@ -894,6 +893,8 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   G2_CUDA(cudaMemcpyAsync(&c->h_err[5], &c->d_top->ntopnodes, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaMemcpyAsync(&c->h_err[0], c->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaStreamSynchronize(st));
+  if(c->h_err[2])
+    return g2_fail(G2GPU_ERR_ARG, "a particle has a type outside 0..5");
   if(c->h_err[7])
     return g2_fail(G2GPU_ERR_TOPNODES, "top-level tree exceeds %d nodes", G2_MAXTOP);
   if(c->h_err[0])

@@ -95,6 +95,13 @@ struct g2gpu_ctx
   float *in_vel;		// 3n, optional
   float *in_gravpm;		// 3n, optional
   unsigned char *in_active;
+  float *in_raw;		// H2D landing zone: pos[3n] | mass[n]
+  float4 *own_in_pm;		// the library's own input buffers (in_* may point at caller-bound device memory)
+  int *own_in_type;
+  float *own_in_oldacc;
+  unsigned char *own_in_active;
+  int inputs_bound;
+  size_t h2d_bytes, d2h_bytes;
   int have_vel, have_gravpm;
 
   // current-order (species-major PH) particle arrays

@@ -105,7 +105,7 @@ struct G2TypeMap { int t2g[6]; };
 // sort key = (block << 54) | PH key; block 0 = gas (type 0, peano.c:47-67), block 1+g = species g (peano.c:90-133)
 __global__ void __launch_bounds__(256) keys_kernel(const float4 *__restrict__ pm, const int *__restrict__ type, int n,
 						   const double *__restrict__ dom, G2TypeMap tm,
-						   unsigned long long *__restrict__ skey, unsigned int *__restrict__ sval)
+						   unsigned long long *__restrict__ skey, unsigned int *__restrict__ sval, int *__restrict__ err)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n)
@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4 *__restrict__ pm
   int z = __double2int_rz(__dmul_rn(__dsub_rn((double) p.z, dom[2]), fac));
   unsigned long long key = (unsigned long long) ph_key(x, y, z, G2_PH_BITS);
   int t = type[i];
+  if(t < 0 || t > 5)
+    {				// particle types are 0..5 (allvars.h:571)
+      atomicExch(&err[2], G2GPU_ERR_ARG);
+      t = t < 0 ? 0 : 5;
+    }
   unsigned long long block = (t == 0) ? 0ull : (unsigned long long) (1 + tm.t2g[t]);
   skey[i] = (block << (3 * G2_PH_BITS)) | key;
   sval[i] = (unsigned int) i;
@@ -136,7 +141,8 @@ __global__ void __launch_bounds__(256) gather_kernel(int n, const unsigned long 
     return;
   unsigned int src = sval[i];
   pm[i] = in_pm[src];
-  ptype[i] = (unsigned char) in_type[src];
+  int t = in_type[src];
+  ptype[i] = (unsigned char) (t < 0 ? 0 : (t > 5 ? 5 : t));
   oldacc[i] = in_oldacc[src];
   active[i] = in_active[src];
   if(in_vel)
@@ -471,6 +477,7 @@ int g2_stage_domain(g2gpu_ctx *c)
     return g2_fail(G2GPU_ERR_STATE, "domain: no particles uploaded");
   cudaStream_t st = c->stream;
   G2_CUDA(cudaEventRecord(c->ev[0], st));
+  G2_CUDA(cudaMemsetAsync(c->d_err, 0, 4 * sizeof(int), st));
 
   extent_init_kernel<<<1, 32, 0, st>>>((unsigned int *) c->d_minmax);
   int nb = c->nsm * 8;
@@ -481,7 +488,7 @@ int g2_stage_domain(g2gpu_ctx *c)
   G2TypeMap tm;
   for(int t = 0; t < 6; t++)
     tm.t2g[t] = c->type_to_grav[t];
-  keys_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->in_pm, c->in_type, n, c->d_domain, tm, c->skey[0], c->sval[0]);
+  keys_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->in_pm, c->in_type, n, c->d_domain, tm, c->skey[0], c->sval[0], c->d_err);
   c->launches += 4;
 
   // blocks 0 (gas) .. D (species D-1): 54 key bits + block bits

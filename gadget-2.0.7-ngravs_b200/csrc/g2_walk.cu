@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
   const int nchunks = (A.hi - A.lo + 31) >> 5;
-  unsigned long long tot_inter = 0, tot_visits = 0;
+  unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0;
 
   while(true)
     {
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
       const int tg = A.t2g[ptype];
       const float hself = A.fsoft[ptype];
       ACC ax = 0, ay = 0, az = 0;
-      int ninter = 0;
+      int ninter = 0, nterms = 0;
       unsigned int skip_until = valid ? 0u : 0xffffffffu;
       unsigned int cur = 0;
       const unsigned int end = (unsigned int) A.numnodes;
@@ -217,7 +217,11 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 #pragma unroll
 		      for(int g = 0; g < D; g++)
 			if(mass[g] != 0.0f)
-			  any |= pair_term<SR, STOCK, ACC>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, ax, ay, az);
+			  {
+			    bool cnt = pair_term<SR, STOCK, ACC>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, ax, ay, az);
+			    any |= cnt;
+			    nterms += cnt;
+			  }
 		      if(!SR || any)
 			ninter++;	// forcetree.c:1585 resp. 2031-2032
 		    }
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		      float ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxhalf);
 		      float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
 		      bool counted = pair_term<SR, STOCK, ACC>(A, s_tab, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, ax, ay, az);
+		      nterms += counted;
 		      if(!SR || counted)
 			ninter++;
 		    }
@@ -285,16 +290,21 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 	  A.acc[3 * (size_t) idx + 2] = fz;
 	  A.cost[idx] = (float) ninter;
 	  tot_inter += (unsigned long long) ninter;
+	  tot_terms += (unsigned long long) nterms;
 	}
     }
   // statistics: interactions (= sum of GravCost) and warp-level cell visits
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1)
-    tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
+    {
+      tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
+      tot_terms += __shfl_xor_sync(0xffffffffu, tot_terms, o);
+    }
   if(lane == 0)
     {
       atomicAdd(&A.counters[0], tot_inter);
       atomicAdd(&A.counters[1], tot_visits);
+      atomicAdd(&A.counters[2], tot_terms);
     }
 }
 

@@ -18,7 +18,7 @@ SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebamba
 
 EXPORTED = [
     "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
-    "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_domain",
+    "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree",
     "g2gpu_walk", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
     "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
@@ -207,14 +207,18 @@ class TreeGravity:
         self._chk(self.lib.g2gpu_download_acc(self.ctx, _p(acc), _p(cost), _p(old)))
         return acc, cost, old
 
-    def gravity_tree(self, pos, mass, ptype, wp, oldacc=None, active=None):
-        """Whole step from host buffers (upload, domain, build, walk, download): the e2e path."""
+    def gravity_tree(self, pos, mass, ptype, wp, oldacc=None, active=None, out=None):
+        """Whole step from host buffers (upload, domain, build, walk, download): the e2e path.
+        out = (acc[n,3] f32, cost[n] f32, oldacc[n] f32, perm[n] i32) lets the caller supply (pinned) result buffers."""
         pos, mass, ptype = _f32(pos), _f32(mass), _i32(ptype)
         n = len(mass)
-        acc = np.zeros((n, 3), dtype=np.float32)
-        cost = np.zeros(n, dtype=np.float32)
-        old = np.zeros(n, dtype=np.float32)
-        perm = np.zeros(n, dtype=np.int32)
+        if out is not None:
+            acc, cost, old, perm = out
+        else:
+            acc = np.zeros((n, 3), dtype=np.float32)
+            cost = np.zeros(n, dtype=np.float32)
+            old = np.zeros(n, dtype=np.float32)
+            perm = np.zeros(n, dtype=np.int32)
         self._chk(self.lib.g2gpu_gravity_tree(self.ctx, n, _p(pos), _p(mass), _p(ptype), _p(_f32(oldacc)), _p(_i32(active)),
                                               C.byref(wp), _p(acc), _p(cost), _p(old), _p(perm)))
         self.n = n
@@ -230,6 +234,17 @@ class TreeGravity:
         self._chk(self.lib.g2gpu_input_buffers(self.ctx, int(n), ptrs))
         return [int(p) for p in ptrs]
 
+    def bind_inputs(self, n, posmass_ptr, type_ptr, oldacc_ptr, active_ptr):
+        """Use caller-owned device arrays (raw pointers, e.g. torch tensors' data_ptr()) as the particle input."""
+        self._chk(self.lib.g2gpu_bind_inputs(self.ctx, int(n), C.c_void_p(posmass_ptr), C.c_void_p(type_ptr), C.c_void_p(oldacc_ptr),
+                                             C.c_void_p(active_ptr)))
+        self.n = int(n)
+
+    def io_bytes(self):
+        b = np.zeros(2, dtype=np.int64)
+        self._chk(self.lib.g2gpu_io_bytes(self.ctx, _p(b)))
+        return int(b[0]), int(b[1])
+
     def inputs_ready(self, n):
         self._chk(self.lib.g2gpu_inputs_ready(self.ctx, int(n)))
         self.n = int(n)
@@ -239,7 +254,7 @@ class TreeGravity:
         cnt = np.zeros(4, dtype=np.int64)
         self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
         return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6],
-                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), targets=int(cnt[3]))
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]))
 
     def reset_counters(self):
         self.lib.g2gpu_reset_counters(self.ctx)

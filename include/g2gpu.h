@@ -116,7 +116,11 @@ int g2gpu_upload_aos(g2gpu_ctx *ctx, int npart, const void *P, size_t stride, in
  * them, so that the caller's collective (NCCL all-gather over NVLink) can fill in the other ranks' slices.
  * ptrs[0..3] = device pointers of posmass (float4 n: x,y,z,mass), type (int n), oldacc (float n), active (u8 n). */
 int g2gpu_input_buffers(g2gpu_ctx *ctx, int npart, void **ptrs);
-int g2gpu_inputs_ready(g2gpu_ctx *ctx, int npart);	/* call after the all-gather: marks all active */
+int g2gpu_inputs_ready(g2gpu_ctx *ctx, int npart);	/* call after the all-gather filled the library's buffers */
+/* Zero-copy variant: use caller-owned DEVICE arrays (e.g. the output of an NCCL all-gather) as the particle input:
+ * posmass float4[n] (x,y,z,mass), type int[n], oldacc float[n], active unsigned char[n].  They must stay valid and
+ * unchanged until g2gpu_domain() has run.  The next g2gpu_upload()/g2gpu_inputs_ready() unbinds them. */
+int g2gpu_bind_inputs(g2gpu_ctx *ctx, int npart, void *posmass, void *type, void *oldacc, void *active);
 
 /* ---- stage 1: domain_findExtent + key loop + top tree + peano_hilbert_order
  *      (domain.c:882-924, 933-1138; peano.c:36-185, 356-398) ---- */
@@ -153,9 +157,11 @@ int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
 /* ---- instrumentation ---- */
 /* CUDA-event times (ms) of the last call of each stage: [0] domain [1] treebuild [2] walk
  * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H; counters[0] = kernel launches since
- * g2gpu_reset_counters, [1] = sum of GravCost of the last walk, [2] = node visits (if enabled). */
+ * g2gpu_reset_counters, [1] = sum of GravCost of the last walk (this rank's targets), [2] = cell visits summed
+ * over warps, [3] = species terms evaluated (one per particle interaction, <= D per node interaction). */
 int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[4]);
 void g2gpu_reset_counters(g2gpu_ctx *ctx);
+int g2gpu_io_bytes(g2gpu_ctx *ctx, long long out[2]);	/* host->device / device->host bytes of the last upload / download */
 void *g2gpu_stream(g2gpu_ctx *ctx);	/* cudaStream_t all kernels are launched on */
 int g2gpu_sync(g2gpu_ctx *ctx);
 

@@ -104,14 +104,15 @@ def test_nonperiodic_tree_and_forces(case, n, outdir):
 
 @pytest.mark.parametrize("n", [32768])
 def test_periodic_treepm_shortrange(n, outdir):
-    if not available("pm_d2_f32"):
+    """32^3 particles on a PMGRID=64 split: the particle-per-mesh-cell density of BASELINE config 3 (128^3 on 256^3)."""
+    if not available("pm64_d2_f32"):
         pytest.skip("oracle/_ref not built")
     box = 100000.0
     pos, mass, ptype = g2test.periodic_poisson(n, box)
     eps = box / round(n ** (1 / 3)) / 30.0
     soft = (eps,) * 6
     grav = g2test.GRAV_D2
-    ref = run_reference("pm_d2_f32", pos, mass, ptype, soft, grav, box=box)
+    ref = run_reference("pm64_d2_f32", pos, mass, ptype, soft, grav, box=box)
     rp = ref.particles()
     tg = gpu_for(ref, n, periodic=True, shortrange=True, unequal=False)
     tg.set_species(grav, g2test.force_softening(soft))
