@@ -170,12 +170,15 @@ def main():
     ap.add_argument("--workload", default="hernquist1m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--acc-float", action="store_true", help="FP32 accumulators in the walk (default FP64)")
+    ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up step, no e2e / cpu_baseline legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     W = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.profile:
+        W = 1
     K = args.steps
 
     w = make_workload(args.workload)
@@ -312,7 +315,7 @@ def main():
 
     # ---- e2e: host buffers -> g2gpu_gravity_tree -> host buffers (N == 1: whole set; N > 1: reported for rank 0's view)
     e2e = None
-    if world == 1:
+    if world == 1 and not args.profile:
         h_pos = torch.from_numpy(w["pos"]).pin_memory().numpy()
         h_mass = torch.from_numpy(w["mass"]).pin_memory().numpy()
         h_type = torch.from_numpy(w["ptype"].astype(np.int32)).pin_memory().numpy()
@@ -371,7 +374,7 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline, "roofline_sort": roofline_sort}
     if e2e is not None:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.profile:
         try:
             r = reference_run(w, oldacc_by_id, 1, 0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],

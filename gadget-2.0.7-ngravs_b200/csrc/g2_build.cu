@@ -310,9 +310,9 @@ __global__ void __launch_bounds__(128) top_children_kernel(const unsigned long l
 // Walk record of a cell, (2+D) float4, index U (depth-first order):
 //   [0]       len, center x, y, z                        (struct NODE len, center; allvars.h:620-621)
 //   [1+g]     s[0][g], s[1][g], s[2][g], mass[g]         (u.d.s, u.d.mass; allvars.h:642-643)
-//   [1+D]     as uint: sibling U | particle offset | pinfo | flags
-//             pinfo = count (4 bits) | type of direct particle j at bits 4+3j
-//             flags = maxsofttype<<2 | diffsoft<<5 (u.d.bitflags layout, forcetree.c:706) | 1<<8 if top-level
+//   [1+D]     as uint: sibling U | particle offset | pinfo | hmax
+//             pinfo = count (4 bits) | type of direct particle j at bits 4+3j | mixed-softening bit 28 | maxsofttype
+//             at bits 29-31 (u.d.bitflags content, forcetree.c:706); hmax = ForceSoftening[maxsofttype] as float bits
 template <int D>
 struct Moments
 {
@@ -399,8 +399,9 @@ __device__ __forceinline__ void mom_add_cell(Moments<D> &M, const float4 *__rest
   if(S.unequal)
     {
       uint4 w = __ldcg((const uint4 *) &rec[1 + D]);
-      int ctype = (w.w >> 2) & 7;
-      M.diffsoft |= (w.w >> 5) & 1;	// forcetree.c:571
+      int ctype = (w.z >> 29) & 7;
+      if(ctype != 7)		// (an empty child carries the bit only as the walk's always-open marker)
+	M.diffsoft |= (w.z >> 28) & 1;	// forcetree.c:571
       if(M.maxsofttype == 7)
 	M.maxsofttype = ctype;
       else if(ctype != 7)
@@ -443,8 +444,24 @@ __device__ __forceinline__ void mom_store(const Moments<D> &M, float4 *__restric
       q.w = (float) M.mass[g];
       rec[1 + g] = q;
     }
-  unsigned int flags = S.unequal ? (unsigned int) (4 * M.maxsofttype + 32 * M.diffsoft) : 0u;
-  uint4 w = make_uint4(sibU, poff, pinfo, flags | extra_flags);
+  // word 2: pinfo | mixed-softening bit (28) | maxsofttype (29-31); word 3: ForceSoftening[maxsofttype] as float.
+  // An empty node (maxsofttype 7) is always opened by the walk (forcetree.c:1478-1483): +inf and the mixed bit do that.
+  unsigned int tbits = 0u, hbits = 0u;
+  if(S.unequal)
+    {
+      if(M.maxsofttype == 7)
+	{
+	  tbits = (1u << 28) | (7u << 29);
+	  hbits = 0x7f800000u;
+	}
+      else
+	{
+	  tbits = ((unsigned int) M.diffsoft << 28) | ((unsigned int) M.maxsofttype << 29);
+	  hbits = __float_as_uint((float) S.fsoft[M.maxsofttype]);
+	}
+    }
+  (void) extra_flags;
+  uint4 w = make_uint4(sibU, poff, pinfo | tbits, hbits);
   *((uint4 *) &rec[1 + D]) = w;
 }
 
@@ -750,7 +767,7 @@ template <int D>
 __global__ void __launch_bounds__(128) export_kernel(BuildArrays A, const unsigned char *__restrict__ tm, const G2TopTree *__restrict__ tt,
 						     const unsigned int *__restrict__ c_refid, const int *__restrict__ p_parent,
 						     const int *__restrict__ top_sibling, const int *__restrict__ top_nextnode, int maxpart,
-						     ExportArrays E)
+						     int unequal, ExportArrays E)
 {
   int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncells = (int) A.tbase[A.n];
@@ -810,7 +827,11 @@ __global__ void __launch_bounds__(128) export_kernel(BuildArrays A, const unsign
 	}
       uint4 w = *((const uint4 *) &rec[1 + D]);
       if(E.bitflags)
-	E.bitflags[ref] = (int) ((w.w & 0xfcu) | extra);
+	{
+	  // an empty node carries the mixed bit only as a walk marker; the reference stores diffsoftflag = 0 for it
+	  unsigned int mt = (w.z >> 29) & 7u, df = (mt == 7u) ? 0u : ((w.z >> 28) & 1u);
+	  E.bitflags[ref] = unequal ? (int) (4u * mt + 32u * df + extra) : (int) extra;
+	}
       if(E.sibling)
 	E.sibling[ref] = sib;
       if(E.nextnode)
@@ -1007,12 +1028,12 @@ int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mas
   int grid = g2_cdiv(total, 128);
   switch (D)
     {
-    case 1: export_kernel<1><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
-    case 2: export_kernel<2><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
-    case 3: export_kernel<3><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
-    case 4: export_kernel<4><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
-    case 5: export_kernel<5><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
-    case 6: export_kernel<6><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, E); break;
+    case 1: export_kernel<1><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
+    case 2: export_kernel<2><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
+    case 3: export_kernel<3><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
+    case 4: export_kernel<4><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
+    case 5: export_kernel<5><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
+    case 6: export_kernel<6><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
     default: cudaFree(buf); return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
     }
   c->launches += 2;

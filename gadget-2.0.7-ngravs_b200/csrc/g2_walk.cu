@@ -38,7 +38,7 @@ struct WalkArgs
   int ntables;			// unique short-range tables held in shared memory
   float theta2;			// ErrTolTheta^2, 0 => relative criterion
   float errtol;			// ErrTolForceAcc
-  float boxsize, boxhalf;
+  float boxsize, boxinv;
   float rcut, rcut2, asmthfac, utor2wpi;
   double G, pos_fac_pre_g, pos_fac_post_g;
   int use_gravpm;
@@ -48,25 +48,30 @@ struct WalkArgs
   G2LawTable laws;
 };
 
+// NEAREST(x) (forcetree.c:43): x > L/2 -> x - L, x < -L/2 -> x + L.  For |x| < 1.5 L this equals x - L*rint(x/L)
+// (round-half-even leaves x = +-L/2 untouched, like the strict comparisons of the macro): 3 instructions.
 template <bool PERIODIC>
-__device__ __forceinline__ float nearest(float x, float boxsize, float boxhalf)
+__device__ __forceinline__ float nearest(float x, float boxsize, float boxinv)
 {
   if(PERIODIC)
-    {				// forcetree.c:43
-      if(x > boxhalf)
-	x -= boxsize;
-      else if(x < -boxhalf)
-	x += boxsize;
-    }
+    x = fmaf(-boxsize, rintf(x * boxinv), x);
   return x;
 }
 
-// one species term of an interaction: adds d*fac to the accumulators; returns whether it counted
-template <bool SR, bool STOCK, typename ACC>
-__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, int tg, int sg, int D, float pmass, float m, float dx,
-					  float dy, float dz, float r2, float h, ACC &ax, ACC &ay, ACC &az)
+__device__ __forceinline__ float fast_rsqrt(float x)
 {
-  float rinv = rsqrtf(fmaxf(r2, 1.0e-37f));
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// one species term of an interaction: adds d*fac to the FP32 partial sums of the current visit (the visit's sum
+// goes into the FP64/FP32 accumulators once); returns whether it counted
+template <bool SR, bool STOCK>
+__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, int tg, int sg, int D, float pmass, float m, float dx,
+					  float dy, float dz, float r2, float h, float &fx, float &fy, float &fz)
+{
+  float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   float r = r2 * rinv;
   float fac;
   if(SR)
@@ -77,7 +82,7 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
       if(r >= h)
 	{
 	  float a = STOCK ? m * rinv * rinv : accel_over_r(A.laws.accel[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, r2, r, rinv, 1.0f) * r;
-	  float t = s_tab[(int) A.tabmap[tg * D + sg] * A.ntab + tabindex];
+	  float t = STOCK ? s_tab[tabindex] : s_tab[(int) A.tabmap[tg * D + sg] * A.ntab + tabindex];
 	  fac = (a - m * A.utor2wpi * t) * rinv;	// forcetree.c:1972-1974
 	}
       else
@@ -90,9 +95,9 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
       else
 	fac = STOCK ? law_plummer(m, h, r) : accel_spline(A.laws.spline[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, h, r, 1.0f);
     }
-  ax += (ACC) (dx * fac);
-  ay += (ACC) (dy * fac);
-  az += (ACC) (dz * fac);
+  fx = fmaf(dx, fac, fx);
+  fy = fmaf(dy, fac, fy);
+  fz = fmaf(dz, fac, fz);
   return true;
 }
 
@@ -109,6 +114,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
     }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
+  unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
+#pragma unroll
+  for(int t = 0; t < 6; t++)
+    t2g_packed |= (unsigned int) A.t2g[t] << (4 * t);
   const int nchunks = (A.hi - A.lo + 31) >> 5;
   unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0;
 
@@ -159,9 +168,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		  const float4 q = __ldg(rec + 1 + g);
 		  mass[g] = q.w;
 		  summass += q.w;
-		  dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxhalf);
-		  dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxhalf);
-		  dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxhalf);
+		  dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
+		  dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
+		  dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
 		  r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
 		  r2min = fminf(r2min, r2[g]);
 		  r2max = fmaxf(r2max, r2[g]);
@@ -173,9 +182,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		  if(r2min > A.rcut2)
 		    {		// forcetree.c:1828-1862
 		      const float eff = A.rcut + 0.5f * len;
-		      float d0 = nearest<PERIODIC>(q0.y - px, A.boxsize, A.boxhalf);
-		      float d1 = nearest<PERIODIC>(q0.z - py, A.boxsize, A.boxhalf);
-		      float d2 = nearest<PERIODIC>(q0.w - pz, A.boxsize, A.boxhalf);
+		      float d0 = nearest<PERIODIC>(q0.y - px, A.boxsize, A.boxinv);
+		      float d1 = nearest<PERIODIC>(q0.z - py, A.boxsize, A.boxinv);
+		      float d2 = nearest<PERIODIC>(q0.w - pz, A.boxsize, A.boxinv);
 		      if(d0 < -eff || d0 > eff || d1 < -eff || d1 > eff || d2 < -eff || d2 > eff)
 			done = true;
 		    }
@@ -197,14 +206,13 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		}
 	      float h = hself;
 	      if(UNEQUAL && !done && !open)
-		{		// forcetree.c:1475-1501
-		  const int maxsofttype = (w.w >> 2) & 7;
-		  if(maxsofttype == 7)
-		    open = true;
-		  else if(h < A.fsoft[maxsofttype])
+		{		// forcetree.c:1475-1501; the record carries ForceSoftening[maxsofttype] (+inf and the
+				// mixed-softening bit for an empty node, maxsofttype == 7, which is always opened)
+		  const float hnode = __uint_as_float(w.w);
+		  if(h < hnode)
 		    {
-		      h = A.fsoft[maxsofttype];
-		      if(r2max < h * h && ((w.w >> 5) & 1))
+		      h = hnode;
+		      if(r2max < h * h && ((w.z >> 28) & 1))
 			open = true;
 		    }
 		}
@@ -214,14 +222,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		  if(!done)
 		    {
 		      bool any = false;
+		      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
 #pragma unroll
 		      for(int g = 0; g < D; g++)
 			if(mass[g] != 0.0f)
 			  {
-			    bool cnt = pair_term<SR, STOCK, ACC>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, ax, ay, az);
+			    bool cnt = pair_term<SR, STOCK>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, fx, fy, fz);
 			    any |= cnt;
 			    nterms += cnt;
 			  }
+		      ax += (ACC) fx;
+		      ay += (ACC) fy;
+		      az += (ACC) fz;
 		      if(!SR || any)
 			ninter++;	// forcetree.c:1585 resp. 2031-2032
 		    }
@@ -232,26 +244,30 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 	    {
 	      // direct particle children of the opened cell, for the lanes that opened it
 	      const unsigned int np = w.z & 15u;
+	      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
 	      for(unsigned int j = 0; j < np; j++)
 		{
 		  const float4 p = __ldg(A.wpart + w.y + j);
 		  if(open)
 		    {
 		      const int stype = (w.z >> (4 + 3 * j)) & 7;
-		      const int sg = A.t2g[stype];
+		      const int sg = (t2g_packed >> (4 * stype)) & 7;
 		      float h = hself;
 		      if(UNEQUAL)
 			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
-		      float ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxhalf);
-		      float ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxhalf);
-		      float ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxhalf);
+		      float ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
+		      float ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
+		      float ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
 		      float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
-		      bool counted = pair_term<SR, STOCK, ACC>(A, s_tab, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, ax, ay, az);
+		      bool counted = pair_term<SR, STOCK>(A, s_tab, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, fx, fy, fz);
 		      nterms += counted;
 		      if(!SR || counted)
 			ninter++;
 		    }
 		}
+	      ax += (ACC) fx;
+	      ay += (ACC) fy;
+	      az += (ACC) fz;
 	      cur = cur + 1;
 	    }
 	  else
@@ -400,7 +416,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.lo = c->w_lo; A.hi = c->w_hi; A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;
   A.theta2 = (float) (wp->theta * wp->theta);
   A.errtol = (float) wp->errtol_force_acc;
-  A.boxsize = (float) wp->boxsize; A.boxhalf = (float) (0.5 * wp->boxsize);
+  A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
   if(sr)
     {
       A.rcut = (float) wp->rcut; A.rcut2 = (float) (wp->rcut * wp->rcut);
