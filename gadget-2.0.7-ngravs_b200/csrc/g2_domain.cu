@@ -175,39 +175,29 @@ __global__ void block_starts_kernel(const unsigned long long *__restrict__ skey,
 }
 
 // ---------------------------------------------------------------- top-level tree ---------------------------
-// number of particles with PH key in [k0, k1): the reference counts them in KeySorted (all species together,
-// domain.c:1052-1066); here keys are sorted per block, so sum over blocks.
-__device__ int count_keys(const long long *__restrict__ phkey, const int *bstart, int nblocks, long long k0, long long k1)
+// first index in [lo,hi) whose key is >= target (keys ascending): warp-cooperative 32-ary search, all 32 lanes
+// must call; a handful of rounds instead of ~20 dependent loads.
+__device__ __forceinline__ int warp_lower_bound(const long long *__restrict__ phkey, int lo, int hi, long long target)
 {
-  int cnt = 0;
-  for(int b = 0; b < nblocks; b++)
+  const int lane = threadIdx.x & 31;
+  while(hi - lo > 32)
     {
-      int s = bstart[b], e = bstart[b + 1];
-      int lo = s, hi = e;
-      while(lo < hi)
-	{
-	  int mid = (lo + hi) >> 1;
-	  if(phkey[mid] < k0)
-	    lo = mid + 1;
-	  else
-	    hi = mid;
-	}
-      int first = lo;
-      hi = e;
-      while(lo < hi)
-	{
-	  int mid = (lo + hi) >> 1;
-	  if(phkey[mid] < k1)
-	    lo = mid + 1;
-	  else
-	    hi = mid;
-	}
-      cnt += lo - first;
+      int step = (hi - lo + 31) >> 5;
+      int idx = lo + (lane + 1) * step - 1;	// last element of this lane's chunk
+      bool below = idx < hi && phkey[idx] < target;
+      int t = __popc(__ballot_sync(0xffffffffu, below));	// chunks entirely below the target (a prefix of the lanes)
+      lo = lo + t * step;
+      int nh = lo + step;
+      hi = nh < hi ? nh : hi;
     }
-  return cnt;
+  int idx = lo + lane;
+  bool below = idx < hi && phkey[idx] < target;
+  return lo + __popc(__ballot_sync(0xffffffffu, below));
 }
 
 #define TT_THREADS 1024
+#define TT_CHUNK 32		// frontier nodes refined per round
+#define TT_MAXBLOCKS (G2GPU_MAX_GRAVS + 1)
 // scratch of the breadth-first refinement (temporary numbering)
 struct G2TopScratch
 {
@@ -222,7 +212,8 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
 							      const double *__restrict__ dom, G2TopTree *tt, G2TopScratch *ts)
 {
   __shared__ int s_nfront, s_nnext, s_ntmp, s_err;
-  const int tid = threadIdx.x;
+  __shared__ int s_lb[TT_CHUNK * 9 * TT_MAXBLOCKS];	// lower bounds of the 9 child boundaries per block
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double thr = __ddiv_rn((double) n, 20.0);	// All.TotNumPart / (TOPNODEFACTOR * NTask * NTask), domain.c:1071
 
   if(tid == 0)
@@ -240,10 +231,10 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
   int cur = 0;
   while(true)
     {
-      int nfront = s_nfront;
+      const int nfront = s_nfront;
       if(nfront == 0)
 	break;
-      int base = s_ntmp;
+      const int base = s_ntmp;
       if(base + 8 * nfront > G2_MAXTOP)
 	{
 	  if(tid == 0)
@@ -254,26 +245,47 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
       if(tid == 0)
 	s_nnext = 0;
       __syncthreads();
-      for(int it = tid; it < 8 * nfront; it += TT_THREADS)
+      for(int c0 = 0; c0 < nfront; c0 += TT_CHUNK)
 	{
-	  int f = ts->frontier[cur][it >> 3], ci = it & 7;
-	  int id = base + it;
-	  int sh = ts->shift[f] - 3;
-	  long long st = ts->start[f] + ((long long) ci << sh);
-	  int cnt = count_keys(phkey, bstart, nblocks, st, st + (1LL << sh));
-	  ts->start[id] = st;
-	  ts->shift[id] = sh;
-	  ts->count[id] = cnt;
-	  ts->child[id] = -1;
-	  if(ci == 0)
-	    ts->child[f] = id;
-	  if((double) cnt > thr && sh >= 3)
+	  const int nc = nfront - c0 < TT_CHUNK ? nfront - c0 : TT_CHUNK;
+	  // number of particles with PH key in a child's key range: the reference counts them in KeySorted (all
+	  // species together, domain.c:1052-1066); keys are sorted per block here, so search every block.
+	  const int ntask = nc * 9 * nblocks;
+	  for(int task = warp; task < ntask; task += TT_THREADS / 32)
 	    {
-	      int slot = atomicAdd(&s_nnext, 1);
-	      ts->frontier[cur ^ 1][slot] = id;
+	      int fi = task / (9 * nblocks), rem = task - fi * 9 * nblocks;
+	      int ci = rem / nblocks, b = rem - ci * nblocks;
+	      int f = ts->frontier[cur][c0 + fi];
+	      int sh = ts->shift[f] - 3;
+	      long long key = ts->start[f] + ((long long) ci << sh);
+	      int r = warp_lower_bound(phkey, bstart[b], bstart[b + 1], key);
+	      if(lane == 0)
+		s_lb[task] = r;
 	    }
+	  __syncthreads();
+	  for(int it = tid; it < 8 * nc; it += TT_THREADS)
+	    {
+	      int fi = it >> 3, ci = it & 7;
+	      int f = ts->frontier[cur][c0 + fi];
+	      int id = base + 8 * (c0 + fi) + ci;
+	      int sh = ts->shift[f] - 3;
+	      int cnt = 0;
+	      for(int b = 0; b < nblocks; b++)
+		cnt += s_lb[(fi * 9 + ci + 1) * nblocks + b] - s_lb[(fi * 9 + ci) * nblocks + b];
+	      ts->start[id] = ts->start[f] + ((long long) ci << sh);
+	      ts->shift[id] = sh;
+	      ts->count[id] = cnt;
+	      ts->child[id] = -1;
+	      if(ci == 0)
+		ts->child[f] = id;
+	      if((double) cnt > thr && sh >= 3)
+		{
+		  int slot = atomicAdd(&s_nnext, 1);
+		  ts->frontier[cur ^ 1][slot] = id;
+		}
+	    }
+	  __syncthreads();
 	}
-      __syncthreads();
       if(tid == 0)
 	{
 	  s_ntmp = base + 8 * nfront;

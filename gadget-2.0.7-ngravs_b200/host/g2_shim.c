@@ -1,0 +1,526 @@
+/* g2_shim.c — host-side drop-in for Gadget-2.0.7-ngravs: the reference's own C entry points, re-implemented on
+ * top of the C ABI of include/g2gpu.h (hand-written sm_100a kernels in libg2gpu.so).
+ *
+ * It is compiled WITH the reference's headers (allvars.h, proto.h, ngravs.h) and replaces, symbol for symbol,
+ *   gravtree.c : gravity_tree (27), set_softenings (468), grav_tree_compare_key (525)
+ *   forcetree.c: force_treeallocate (3176), force_treefree (3411), force_treebuild (61),
+ *                force_treeevaluate (1244), force_treeevaluate_shortrange (1623)
+ *   peano.c    : peano_hilbert_key (356), peano_hilbert_order (36), compare_key (190)
+ * so that accel.c, domain.c, init.c, run.c, ... call it unchanged.
+ * All state stays in the reference's globals (P[], All, NumPart, TreeReconstructFlag, ...).  Errors of the GPU
+ * library end the run through endrun() like the reference's own failures (endrun.c:24).  There is no CPU
+ * fallback: without a B200 the first call to force_treeallocate() ends the run.
+ */
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <mpi.h>
+
+#include "allvars.h"
+#include "proto.h"
+#include "ngravs.h"
+
+#include "g2gpu.h"
+#include "g2_ph_table.h"
+
+static g2gpu_ctx *G2 = NULL;
+static int g2_maxpart = 0, g2_maxnodes = 0;
+static int *g2_perm = NULL;		/* device particle index -> index in P[] */
+static int g2_perm_identity = 1;
+static float *g2_acc = NULL, *g2_cost = NULL, *g2_oldacc = NULL;
+static int g2_mirror = -1;		/* refresh the host mirror Nodes[]/Nextnode[]/Father[] after every build */
+
+#ifdef PMGRID
+static double g2_srtable[N_GRAVS][N_GRAVS][NTAB];
+static int g2_srtable_done = 0;
+#endif
+
+static void g2_check(int rc, const char *what)
+{
+  if(rc != 0)
+    {
+      printf("task %d: g2gpu %s failed (%d): %s\n", ThisTask, what, rc, g2gpu_last_error());
+      fflush(stdout);
+      endrun(7000 - rc);
+    }
+}
+
+/* ---------------------------------------------------------------- peano.c ---------------------------------- */
+static const unsigned char g2_ph[G2_PH_NSTATES * 8] = G2_PH_TABLE_INIT;
+
+/* peano.c:356.  Called by domain.c:940 for every particle and by forcetree code for top-level cells. */
+peanokey peano_hilbert_key(int x, int y, int z, int bits)
+{
+  unsigned st = 0;
+  peanokey key = 0;
+  int l;
+  for(l = bits - 1; l >= 0; l--)
+    {
+      unsigned o = (((x >> l) & 1) << 2) | (((y >> l) & 1) << 1) | ((z >> l) & 1);
+      unsigned e = g2_ph[st * 8 + o];
+      key = (key << 3) | (e & 7);
+      st = e >> 3;
+    }
+  return key;
+}
+
+struct g2_keyindex { peanokey key; int index; };
+int compare_key(const void *a, const void *b)	/* peano.c:190 */
+{
+  peanokey x = ((const struct g2_keyindex *) a)->key, y = ((const struct g2_keyindex *) b)->key;
+  return (x > y) - (x < y);
+}
+
+static void g2_upload(int npart)
+{
+  int off_gravpm = -1;
+#ifdef PMGRID
+  off_gravpm = (int) offsetof(struct particle_data, GravPM);
+#endif
+  g2_check(g2gpu_upload_aos(G2, npart, P, sizeof(struct particle_data), (int) sizeof(FLOAT),
+			    (int) offsetof(struct particle_data, Pos), (int) offsetof(struct particle_data, Mass),
+			    (int) offsetof(struct particle_data, Type), (int) offsetof(struct particle_data, OldAcc),
+			    -1, off_gravpm, (int) offsetof(struct particle_data, Ti_endstep), All.Ti_Current), "upload");
+}
+
+static void g2_fetch_order(int npart)
+{
+  int i;
+  g2_check(g2gpu_get_order(G2, g2_perm), "get_order");
+  g2_perm_identity = 1;
+  for(i = 0; i < npart; i++)
+    if(g2_perm[i] != i)
+      {
+	g2_perm_identity = 0;
+	break;
+      }
+}
+
+/* peano.c:36: gas block first, then species-major, Peano-Hilbert inside a block.  Keys and the sort run on the GPU;
+ * the host only applies the permutation to P[] (and SphP[] for the leading gas block). */
+void peano_hilbert_order(void)
+{
+  int i;
+  struct particle_data *tmp;
+
+  if(ThisTask == 0)
+    printf("begin Peano-Hilbert order (GPU)...\n");
+  if(NumPart == 0)
+    return;
+  g2_upload(NumPart);
+  g2_check(g2gpu_domain(G2), "domain");
+  g2_fetch_order(NumPart);
+  if(!g2_perm_identity)
+    {
+      if(!(tmp = malloc(sizeof(struct particle_data) * NumPart)))
+	endrun(7101);
+      memcpy(tmp, P, sizeof(struct particle_data) * NumPart);
+      for(i = 0; i < NumPart; i++)
+	P[i] = tmp[g2_perm[i]];
+      free(tmp);
+      if(N_gas > 0)
+	{
+	  struct sph_particle_data *stmp = malloc(sizeof(struct sph_particle_data) * N_gas);
+	  if(!stmp)
+	    endrun(7102);
+	  memcpy(stmp, SphP, sizeof(struct sph_particle_data) * N_gas);
+	  for(i = 0; i < N_gas; i++)
+	    SphP[i] = stmp[g2_perm[i]];
+	  free(stmp);
+	}
+    }
+  if(ThisTask == 0)
+    printf("Peano-Hilbert done.\n");
+}
+
+/* ---------------------------------------------------------------- forcetree.c ------------------------------- */
+static int g2_law_id(gravity f)
+{
+  if(f == none) return G2GPU_LAW_NONE;
+  if(f == newtonian) return G2GPU_LAW_NEWTONIAN;
+  if(f == neg_newtonian) return G2GPU_LAW_NEG_NEWTONIAN;
+  if(f == yukawa) return G2GPU_LAW_YUKAWA;
+  if(f == coloyuk) return G2GPU_LAW_COLOYUK;
+  if(f == bambam) return G2GPU_LAW_BAMBAM;
+  if(f == sourcebambaryon) return G2GPU_LAW_SOURCEBAMBARYON;
+  if(f == sourcebaryonbam) return G2GPU_LAW_SOURCEBARYONBAM;
+  return -1;
+}
+
+static int g2_spline_id(gravity f)
+{
+  if(f == none) return G2GPU_SPLINE_NONE;
+  if(f == plummer) return G2GPU_SPLINE_PLUMMER;
+  if(f == neg_plummer) return G2GPU_SPLINE_NEG_PLUMMER;
+  if(f == bambam_spline) return G2GPU_SPLINE_BAMBAM;
+  if(f == sourcebambaryon_spline) return G2GPU_SPLINE_SOURCEBAMBARYON;
+  if(f == sourcebaryonbam_spline) return G2GPU_SPLINE_SOURCEBARYONBAM;
+  return -1;
+}
+
+#ifndef YUKAWA_IMASS
+#define YUKAWA_IMASS 60.0	/* ngravs.c:41-43 */
+#endif
+#ifndef BAM_EPSILON
+#define BAM_EPSILON 1.31e-6	/* ngravs.c:45-47 */
+#endif
+
+/* hands TypeToGrav, All.ForceSoftening and the D x D law tables of wire_grav_maps() (ngravs.c:64) to the device */
+static void g2_push_tables(void)
+{
+  int accel[N_GRAVS * N_GRAVS], spline[N_GRAVS * N_GRAVS], i, j;
+  double par[N_GRAVS * N_GRAVS * 4];
+  for(i = 0; i < N_GRAVS; i++)
+    for(j = 0; j < N_GRAVS; j++)
+      {
+	int a = g2_law_id(AccelFxns[i][j]), s = g2_spline_id(AccelSplines[i][j]);
+	if(a < 0 || s < 0)
+	  {
+	    printf("ngravs/g2gpu: AccelFxns[%d][%d] or AccelSplines[%d][%d] has no device implementation.\n"
+		   "Register it in include/g2gpu.h (enum g2gpu_law) and csrc/g2_laws.cuh.\n", i, j, i, j);
+	    endrun(7201);
+	  }
+	accel[i * N_GRAVS + j] = a;
+	spline[i * N_GRAVS + j] = s;
+	par[4 * (i * N_GRAVS + j) + 0] = All.BoxSize > 0 ? YUKAWA_IMASS / All.BoxSize : 0.0;	/* ngravs.c:858 */
+	par[4 * (i * N_GRAVS + j) + 1] = BAM_EPSILON;
+	par[4 * (i * N_GRAVS + j) + 2] = par[4 * (i * N_GRAVS + j) + 3] = 0;
+      }
+  g2_check(g2gpu_set_species(G2, TypeToGrav, All.ForceSoftening), "set_species");
+  g2_check(g2gpu_set_laws(G2, accel, spline, par), "set_laws");
+}
+
+#ifdef PMGRID
+extern struct ngravsInterpolant *ngravsPeriodicTable;
+
+/* forcetree.c:3274-3354: the reference's own FFT integration (ngravs_core.c:72-159) stays on the host, in double */
+static void g2_build_srtable(void)
+{
+  int nA, nB, i;
+  double temp[NTAB], tempI[NTAB], u;
+  ngravsPeriodicTable = ngravsConvolutionInit(NTAB, 3, 8);
+  for(nA = 0; nA < N_GRAVS; nA++)
+    for(nB = 0; nB < N_GRAVS; nB++)
+      {
+	if(performConvolution(ngravsPeriodicTable, NormedGreensFxns[nB][nA], 0.5, temp, tempI))
+	  endrun(1047);
+	for(i = 0; i < NTAB; i++)
+	  {
+	    u = 3.0 / NTAB * (i + 0.5);
+	    g2_srtable[nB][nA][i] = tempI[i] / (u * u) - temp[i] / u;
+	  }
+      }
+  ngravsConvolutionFree(ngravsPeriodicTable);
+  g2_srtable_done = 1;
+}
+#endif
+
+/* forcetree.c:3176.  The host arrays stay (restart.c, predict.c, ngb.c read them); the device context is created
+ * once and survives force_treefree() because pm_periodic.c frees/reallocates the tree around every PM step. */
+void force_treeallocate(int maxnodes, int maxpart)
+{
+  MaxNodes = maxnodes;
+  if(!(Nodes_base = malloc((MaxNodes + 1) * sizeof(struct NODE))) || !(Extnodes_base = malloc((MaxNodes + 1) * sizeof(struct extNODE)))
+     || !(Nextnode = malloc((maxpart + MAXTOPNODES) * sizeof(int))) || !(Father = malloc(maxpart * sizeof(int))))
+    {
+      printf("failed to allocate memory for %d tree-nodes.\n", MaxNodes);
+      endrun(3);
+    }
+  Nodes = Nodes_base - All.MaxPart;
+  Extnodes = Extnodes_base - All.MaxPart;
+
+  if(G2 && (g2_maxpart != All.MaxPart || g2_maxnodes != maxnodes))
+    {
+      g2gpu_destroy(G2);
+      G2 = NULL;
+    }
+  if(!G2)
+    {
+      g2gpu_config cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.device = 0;
+      cfg.n_gravs = N_GRAVS;
+#ifdef PERIODIC
+      cfg.periodic = 1;
+#endif
+#ifdef PMGRID
+      cfg.shortrange = 1;
+      cfg.ntab = NTAB;
+#endif
+#ifdef UNEQUALSOFTENINGS
+      cfg.unequal_softenings = 1;
+#endif
+      cfg.max_part = All.MaxPart;
+      cfg.max_nodes = maxnodes;
+      cfg.rank = 0;
+      cfg.nranks = 1;
+      g2_check(g2gpu_create(&G2, &cfg), "create");
+      g2_maxpart = All.MaxPart;
+      g2_maxnodes = maxnodes;
+      g2_perm = realloc(g2_perm, sizeof(int) * All.MaxPart);
+      g2_acc = realloc(g2_acc, sizeof(float) * 3 * All.MaxPart);
+      g2_cost = realloc(g2_cost, sizeof(float) * All.MaxPart);
+      g2_oldacc = realloc(g2_oldacc, sizeof(float) * All.MaxPart);
+      if(ThisTask == 0)
+	printf("\ng2gpu: device context for %d particles / %d tree nodes created.\n\n", All.MaxPart, maxnodes);
+#ifdef PMGRID
+      if(!g2_srtable_done)
+	g2_build_srtable();
+      g2_check(g2gpu_set_srtable(G2, &g2_srtable[0][0][0]), "set_srtable");
+#endif
+    }
+  if(g2_mirror < 0)
+    g2_mirror = getenv("G2GPU_HOST_MIRROR") ? atoi(getenv("G2GPU_HOST_MIRROR")) : 0;
+}
+
+void force_treefree(void)	/* forcetree.c:3411 */
+{
+  free(Father);
+  free(Nextnode);
+  free(Extnodes_base);
+  free(Nodes_base);
+}
+
+/* copies the device tree into the reference's host layout (struct NODE after the moment pass, allvars.h:618-660) */
+static void g2_refresh_mirror(int npart)
+{
+  int nn = Numnodestree, k, j, g;
+  float *len = malloc(sizeof(float) * nn), *center = malloc(sizeof(float) * 3 * nn), *s = malloc(sizeof(float) * 3 * nn * N_GRAVS),
+    *mass = malloc(sizeof(float) * nn * N_GRAVS);
+  int *bf = malloc(sizeof(int) * nn * 4), *sib = bf + nn, *nxt = sib + nn, *fat = nxt + nn;
+  if(!len || !center || !s || !mass || !bf)
+    endrun(7301);
+  g2_check(g2gpu_download_tree(G2, len, center, s, mass, bf, sib, nxt, fat, Nextnode, Father), "download_tree");
+  for(k = 0; k < nn; k++)
+    {
+      struct NODE *nop = &Nodes[All.MaxPart + k];
+      nop->len = len[k];
+      for(j = 0; j < 3; j++)
+	{
+	  nop->center[j] = center[3 * k + j];
+	  for(g = 0; g < N_GRAVS; g++)
+	    nop->u.d.s[j][g] = s[(3 * k + j) * N_GRAVS + g];
+	}
+      for(g = 0; g < N_GRAVS; g++)
+	nop->u.d.mass[g] = mass[k * N_GRAVS + g];
+      nop->u.d.bitflags = bf[k];
+      nop->u.d.sibling = sib[k];
+      nop->u.d.nextnode = nxt[k];
+      nop->u.d.father = fat[k];
+    }
+  (void) npart;
+  free(bf);
+  free(mass);
+  free(s);
+  free(center);
+  free(len);
+}
+
+/* forcetree.c:61.  Uploads the first npart particles, runs the device domain stage (extent, keys, top-level tree)
+ * and the parallel build; the tree always reflects the current P[]. */
+int force_treebuild(int npart)
+{
+  int numnodes = 0;
+  g2_push_tables();
+  g2_upload(npart);
+  g2_check(g2gpu_domain(G2), "domain");
+  g2_fetch_order(npart);
+  g2_check(g2gpu_treebuild(G2, &numnodes), "treebuild");
+  Numnodestree = numnodes;
+  if(g2_mirror || N_gas > 0)
+    {
+      if(!g2_perm_identity)
+	{
+	  printf("g2gpu: host tree mirror requested but P[] is not in Peano-Hilbert order\n");
+	  endrun(7302);
+	}
+      g2_refresh_mirror(npart);
+    }
+  TimeOfLastTreeConstruction = All.Time;
+  return Numnodestree;
+}
+
+static void g2_fill_walk_params(g2gpu_walk_params * wp)
+{
+  memset(wp, 0, sizeof(*wp));
+  wp->theta = All.ErrTolTheta;
+  wp->errtol_force_acc = All.ErrTolForceAcc;
+  wp->boxsize = All.BoxSize;
+  wp->G = All.G;
+#ifdef PMGRID
+  wp->asmth = All.Asmth[0];
+  wp->rcut = All.Rcut[0];
+  wp->use_gravpm = 1;
+#endif
+#if !defined(PERIODIC) && !defined(PMGRID)
+  if(All.ComovingIntegrationOn)
+    wp->pos_fac_pre_g = 0.5 * All.Hubble * All.Hubble * All.Omega0 / All.G;	/* gravtree.c:304-316 */
+  else
+    wp->pos_fac_post_g = All.OmegaLambda * All.Hubble * All.Hubble;	/* gravtree.c:346-358 */
+#endif
+}
+
+/* forcetree.c:1244 / 1623 for ONE target: kept for callers outside gravity_tree().  Runs a device walk with only
+ * `target` active; returns its interaction count. */
+static int g2_evaluate_one(int target, int mode)
+{
+  g2gpu_walk_params wp;
+  int i, save, n = NumPart, cost;
+  int *ti;
+  if(mode != 0)
+    {
+      printf("g2gpu: force_treeevaluate(mode=1) (imported particles) does not exist without domain decomposition\n");
+      endrun(7401);
+    }
+  ti = malloc(sizeof(int) * n);
+  for(i = 0; i < n; i++)
+    {
+      ti[i] = P[i].Ti_endstep;
+      P[i].Ti_endstep = All.Ti_Current + 1;
+    }
+  P[target].Ti_endstep = All.Ti_Current;
+  save = TreeReconstructFlag;
+  force_treebuild(NumPart);
+  TreeReconstructFlag = save;
+  g2_fill_walk_params(&wp);
+  wp.G = 1.0;			/* the per-target functions return the pre-G acceleration (forcetree.c:1592) */
+  wp.pos_fac_pre_g = wp.pos_fac_post_g = 0;
+  g2_check(g2gpu_walk(G2, &wp), "walk");
+  g2_check(g2gpu_download_acc(G2, g2_acc, g2_cost, g2_oldacc), "download_acc");
+  for(i = 0; i < n; i++)
+    if(g2_perm[i] == target)
+      {
+	P[target].GravAccel[0] = g2_acc[3 * i];
+	P[target].GravAccel[1] = g2_acc[3 * i + 1];
+	P[target].GravAccel[2] = g2_acc[3 * i + 2];
+	P[target].GravCost = g2_cost[i];
+	break;
+      }
+  cost = (int) P[target].GravCost;
+  for(i = 0; i < n; i++)
+    P[i].Ti_endstep = ti[i];
+  free(ti);
+  return cost;
+}
+
+int force_treeevaluate(int target, int mode, double *ewaldcountsum)
+{
+  (void) ewaldcountsum;
+  return g2_evaluate_one(target, mode);
+}
+
+#ifdef PMGRID
+int force_treeevaluate_shortrange(int target, int mode)
+{
+  return g2_evaluate_one(target, mode);
+}
+#endif
+
+/* ---------------------------------------------------------------- gravtree.c -------------------------------- */
+void set_softenings(void)	/* gravtree.c:468 */
+{
+  const double soft[6] = { All.SofteningGas, All.SofteningHalo, All.SofteningDisk, All.SofteningBulge, All.SofteningStars, All.SofteningBndry };
+  const double maxphys[6] = { All.SofteningGasMaxPhys, All.SofteningHaloMaxPhys, All.SofteningDiskMaxPhys, All.SofteningBulgeMaxPhys,
+    All.SofteningStarsMaxPhys, All.SofteningBndryMaxPhys };
+  int i;
+  for(i = 0; i < 6; i++)
+    {
+      if(All.ComovingIntegrationOn && soft[i] * All.Time > maxphys[i])
+	All.SofteningTable[i] = maxphys[i] / All.Time;
+      else
+	All.SofteningTable[i] = soft[i];
+      All.ForceSoftening[i] = 2.8 * All.SofteningTable[i];
+    }
+  All.MinGasHsml = All.MinGasHsmlFractional * All.ForceSoftening[0];
+}
+
+int grav_tree_compare_key(const void *a, const void *b)	/* gravtree.c:525 */
+{
+  int x = ((const struct gravdata_index *) a)->Task, y = ((const struct gravdata_index *) b)->Task;
+  return (x > y) - (x < y);
+}
+
+/* gravtree.c:27.  Build if flagged (always from the current P[]), walk every particle with
+ * Ti_endstep == All.Ti_Current on the GPU, epilogue (OldAcc, G, cosmological terms) fused into the walk kernel,
+ * results written back into P[], the reference's counters and timings.txt lines kept. */
+void gravity_tree(void)
+{
+  double tstart, tend, timetree, costtotal = 0;
+  long long ntot = NumForceUpdate;
+  g2gpu_walk_params wp;
+  int i, j, k;
+
+  if(All.ComovingIntegrationOn)
+    set_softenings();
+
+  tstart = second();
+  if(ThisTask == 0 && TreeReconstructFlag)
+    printf("Tree construction.\n");
+  force_treebuild(NumPart);	/* the device tree is rebuilt for every force computation */
+  TreeReconstructFlag = 0;
+  tend = second();
+  All.CPU_TreeConstruction += timediff(tstart, tend);
+
+#ifndef NOGRAVITY
+  if(ThisTask == 0)
+    printf("Begin tree force.\n");
+#ifdef SELECTIVE_NO_GRAVITY
+  for(i = 0; i < NumPart; i++)
+    if(((1 << P[i].Type) & (SELECTIVE_NO_GRAVITY)))
+      P[i].Ti_endstep = -P[i].Ti_endstep - 1;
+  force_treebuild(NumPart);	/* re-upload the changed active flags */
+#endif
+  tstart = second();
+  g2_fill_walk_params(&wp);
+  g2_check(g2gpu_walk(G2, &wp), "walk");
+  g2_check(g2gpu_download_acc(G2, g2_acc, g2_cost, g2_oldacc), "download_acc");
+  for(i = 0; i < NumPart; i++)
+    {
+      j = g2_perm[i];
+      if(P[j].Ti_endstep == All.Ti_Current)
+	{
+	  for(k = 0; k < 3; k++)
+	    P[j].GravAccel[k] = g2_acc[3 * i + k];
+	  P[j].GravCost = g2_cost[i];
+	  P[j].OldAcc = g2_oldacc[i];
+	  costtotal += g2_cost[i];
+	}
+    }
+  tend = second();
+  timetree = timediff(tstart, tend);
+
+  if(All.TypeOfOpeningCriterion == 1)
+    All.ErrTolTheta = 0;	/* gravtree.c:334-335 */
+#ifdef SELECTIVE_NO_GRAVITY
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep < 0)
+      P[i].Ti_endstep = -P[i].Ti_endstep - 1;
+#endif
+  if(ThisTask == 0)
+    printf("tree is done.\n");
+#else
+  timetree = 0;
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep == All.Ti_Current)
+      for(j = 0; j < 3; j++)
+	P[i].GravAccel[j] = 0;
+#endif
+
+  if(ThisTask == 0)
+    {				/* timings.txt, gravtree.c:404-452 */
+      All.TotNumOfForces += ntot;
+      fprintf(FdTimings, "Step= %d  t= %g  dt= %g \n", All.NumCurrentTiStep, All.Time, All.TimeStep);
+      fprintf(FdTimings, "Nf= %d%09d  total-Nf= %d%09d  ex-frac= %g  iter= %d\n", (int) (ntot / 1000000000), (int) (ntot % 1000000000),
+	      (int) (All.TotNumOfForces / 1000000000), (int) (All.TotNumOfForces % 1000000000), 0.0, 1);
+      fprintf(FdTimings, "work-load balance: %g  max=%g avg=%g PE0=%g\n", 1.0, timetree, timetree, timetree);
+      fprintf(FdTimings, "particle-load balance: %g\n", 1.0);
+      fprintf(FdTimings, "max. nodes: %d, filled: %g\n", Numnodestree, Numnodestree / (All.TreeAllocFactor * All.MaxPart));
+      fprintf(FdTimings, "part/sec=%g | %g  ia/part=%g (%g)\n", ntot / (timetree + 1.0e-20), ntot / (timetree + 1.0e-20),
+	      ntot > 0 ? costtotal / ntot : 0.0, 0.0);
+      fprintf(FdTimings, "\n");
+      fflush(FdTimings);
+      All.CPU_TreeWalk += timetree;
+    }
+}

@@ -18,8 +18,8 @@ _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 
-def available(variant):
-    return os.path.exists(os.path.join(REF_DIR, f"libg2ref_{variant}.so"))
+def available(variant, prefix="g2ref"):
+    return os.path.exists(os.path.join(REF_DIR, f"lib{prefix}_{variant}.so"))
 
 
 class RefOracle:
@@ -27,8 +27,10 @@ class RefOracle:
 
     def __init__(self, variant, maxpart, boxsize=0.0, G=1.0, theta=0.5, errtol=0.005, criterion=1,
                  softening=(0.0, 1.0, 1.0, 1.0, 1.0, 1.0), gravity=(0, 0, 1, 0, 0, 0), tree_alloc=1.5,
-                 buffer_mb=32):
-        src = os.path.join(REF_DIR, f"libg2ref_{variant}.so")
+                 buffer_mb=32, prefix="g2ref"):
+        """prefix="g2ref": the unmodified reference; prefix="g2shim": the same reference linked with the product's host shim
+        (integration/Makefile), i.e. its gravity_tree()/peano_hilbert_order()/force_treebuild() run on the GPU."""
+        src = os.path.join(REF_DIR, f"lib{prefix}_{variant}.so")
         if not os.path.exists(src):
             raise FileNotFoundError(src)
         fd, self._tmp = tempfile.mkstemp(suffix=".so", prefix=f"g2ref_{variant}_")

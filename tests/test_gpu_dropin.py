@@ -1,0 +1,78 @@
+"""GPU parity of the DROP-IN: the unmodified reference's own call chain -- domain_Decomposition() (domain.c, CPU) ->
+peano_hilbert_order() -> gravity_tree() -> force_treebuild() -- linked with the product's host shim
+(gadget-2.0.7-ngravs_b200/host/g2_shim.c, built by integration/Makefile) instead of gravtree.c / peano.c / the replaced
+entry points of forcetree.c, against the same chain of the pure-CPU reference build."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import g2test
+from refrun import RefOracle, available
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _preload():
+    C.CDLL(os.path.join(ROOT, "gadget-2.0.7-ngravs_b200", "libg2gpu.so"), mode=C.RTLD_GLOBAL)
+
+
+@pytest.mark.parametrize("variant", ["np_d2_f32", "pm64_d2_f32"])
+def test_reference_call_chain_runs_on_the_gpu(variant, outdir, monkeypatch):
+    if not (available(variant) and available(variant, "g2shim")):
+        pytest.skip("oracle/_ref (reference and shim builds) not present")
+    monkeypatch.setenv("G2GPU_HOST_MIRROR", "1")
+    _preload()
+    n = 40000 if variant == "np_d2_f32" else 32768
+    if variant == "np_d2_f32":
+        pos, mass, ptype = g2test.hernquist(n, seed=77)
+        soft, box = g2test.SOFT_NP, 0.0
+    else:
+        box = 100000.0
+        pos, mass, ptype = g2test.periodic_poisson(n, box, seed=13)
+        soft = (box / 32 / 30.0,) * 6
+    kw = dict(boxsize=box, softening=soft, gravity=g2test.GRAV_D2)
+    ref = RefOracle(variant, int(1.1 * n) + 64, **kw)
+    shim = RefOracle(variant, int(1.1 * n) + 64, prefix="g2shim", **kw)
+    for o in (ref, shim):
+        o.load(pos, mass, ptype)
+        o.domain()                 # reference domain.c on the CPU; peano_hilbert_order() on the GPU for the shim build
+    rp, sp = ref.particles(), shim.particles()
+    # same particle order (ties between equal keys excepted: the reference's qsort leaves them unordered)
+    same = rp["id"] == sp["id"]
+    keys = ref.keys()
+    if not same.all():
+        tie = np.zeros(n, dtype=bool)
+        eq = keys[1:] == keys[:-1]
+        tie[1:] |= eq
+        tie[:-1] |= eq
+        assert tie[~same].all()
+    # first force computation of a run: Barnes-Hut, then the relative criterion (accel.c:46-49)
+    for o in (ref, shim):
+        o.gravity()
+    r1, s1 = ref.particles(), shim.particles()
+    assert shim.lib.g2ref_numnodes() == ref.lib.g2ref_numnodes()
+    if same.all():
+        mism = g2test.compare_tree(shim.tree(), ref.tree(), ref.D)     # host mirror Nodes[]/Nextnode[]/Father[] filled by the shim
+        assert all(v == 0 for v in mism.values()), mism
+    ra = np.zeros((n, 3)); ra[r1["id"]] = r1["acc"]
+    sa = np.zeros((n, 3)); sa[s1["id"]] = s1["acc"]
+    e1 = g2test.rel_err(sa, ra)
+    rc = np.zeros(n); rc[r1["id"]] = r1["cost"]
+    sc = np.zeros(n); sc[s1["id"]] = s1["cost"]
+    for o in (ref, shim):
+        o.set_opening(0.0, 0.005, 1)
+        o.force_rebuild()
+        o.gravity()
+    r2, s2 = ref.particles(), shim.particles()
+    ra2 = np.zeros((n, 3)); ra2[r2["id"]] = r2["acc"]
+    sa2 = np.zeros((n, 3)); sa2[s2["id"]] = s2["acc"]
+    e2 = g2test.rel_err(sa2, ra2)
+    with open(os.path.join(outdir, f"dropin_{variant}.txt"), "w") as f:
+        f.write(f"bh median {np.median(e1):.3e} p99.9 {np.percentile(e1, 99.9):.3e} cost_mismatch {int((rc != sc).sum())}\n")
+        f.write(f"rel median {np.median(e2):.3e} p99.9 {np.percentile(e2, 99.9):.3e}\n")
+    for e in (e1, e2):
+        assert np.median(e) <= 1e-5 and np.percentile(e, 99.9) <= 1e-3
+    assert (rc != sc).sum() <= 0.002 * n
