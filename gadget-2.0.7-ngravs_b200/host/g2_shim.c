@@ -73,6 +73,8 @@ int compare_key(const void *a, const void *b)	/* peano.c:190 */
   return (x > y) - (x < y);
 }
 
+static void g2_push_tables(void);
+
 static void g2_upload(int npart)
 {
   int off_gravpm = -1;
@@ -109,6 +111,7 @@ void peano_hilbert_order(void)
     printf("begin Peano-Hilbert order (GPU)...\n");
   if(NumPart == 0)
     return;
+  g2_push_tables();		/* the sort needs TypeToGrav */
   g2_upload(NumPart);
   g2_check(g2gpu_domain(G2), "domain");
   g2_fetch_order(NumPart);
