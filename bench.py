@@ -232,40 +232,23 @@ def main():
     tg.set_option("rank", rank)
 
     # ---- device-resident inputs.  N > 1: every rank owns the slice [lo,hi) and all-gathers the rest each step.
+    import multigpu
     pm_host = np.concatenate([w["pos"], w["mass"][:, None]], axis=1).astype(np.float32)
-    d_pm = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    d_type = torch.empty(n, dtype=torch.int32, device=dev)
-    d_old = torch.empty(n, dtype=torch.float32, device=dev)
     d_act = torch.ones(n, dtype=torch.uint8, device=dev)
-    per = (n + world - 1) // world
-    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
-    if world > 1:
-        npad = per * world
-        g_pm = torch.zeros((npad, 4), dtype=torch.float32, device=dev)
-        g_type = torch.zeros(npad, dtype=torch.int32, device=dev)
-        g_old = torch.zeros(npad, dtype=torch.float32, device=dev)
-        s_pm = torch.zeros((per, 4), dtype=torch.float32, device=dev)
-        s_type = torch.zeros(per, dtype=torch.int32, device=dev)
-        s_old = torch.zeros(per, dtype=torch.float32, device=dev)
-        s_pm[: hi - lo] = torch.from_numpy(pm_host[lo:hi]).to(dev)
-        s_type[: hi - lo] = torch.from_numpy(w["ptype"][lo:hi].astype(np.int32)).to(dev)
-        s_old[: hi - lo] = torch.from_numpy(oldacc_by_id[lo:hi]).to(dev)
-    else:
-        d_pm.copy_(torch.from_numpy(pm_host))
-        d_type.copy_(torch.from_numpy(w["ptype"].astype(np.int32)))
-        d_old.copy_(torch.from_numpy(oldacc_by_id))
+    lo, hi, per = multigpu.owner_slice(n, rank, world)
+    ex = multigpu.ParticleExchange(n, dev, world)
+    ex.set_local(torch.from_numpy(pm_host[lo:hi]).to(dev), torch.from_numpy(w["ptype"][lo:hi].astype(np.int32)).to(dev),
+                 torch.from_numpy(oldacc_by_id[lo:hi]).to(dev))
+    if world == 1:
+        ex.gather()                                     # single GPU: the records simply stay resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
     torch.cuda.synchronize()
 
     def step_resident():
         if world > 1:
-            dist.all_gather_into_tensor(g_pm, s_pm)
-            dist.all_gather_into_tensor(g_type, s_type)
-            dist.all_gather_into_tensor(g_old, s_old)
+            ex.gather()                                 # NCCL all-gather of (x,y,z,m), type, OldAcc over NVLink
             torch.cuda.current_stream().synchronize()
-            tg.bind_inputs(n, g_pm.data_ptr(), g_type.data_ptr(), g_old.data_ptr(), d_act.data_ptr())
-        else:
-            tg.bind_inputs(n, d_pm.data_ptr(), d_type.data_ptr(), d_old.data_ptr(), d_act.data_ptr())
+        tg.bind_inputs(n, ex.g_pm.data_ptr(), ex.g_type.data_ptr(), ex.g_old.data_ptr(), d_act.data_ptr())
         tg.domain()
         tg.treebuild()
         tg.walk(wp_rel)
@@ -371,6 +354,7 @@ def main():
             "stages_ms": {k: v / K for k, v in stage.items()}, "cell_visits_per_warp_step": visits,
             "first_pass_barnes_hut": {"ia_per_particle": bh_stats["interactions"] / n, "walk_kernel_ms": bh_stats["walk_kernel_ms"]},
             "wall_ms_per_step_incl_flush": 1e3 * wall / K,
+            "allgather_bytes_per_step": ex.bytes_per_step() if world > 1 else 0,
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline, "roofline_sort": roofline_sort}
     if e2e is not None:
         line["e2e"] = e2e
