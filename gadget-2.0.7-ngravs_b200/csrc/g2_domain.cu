@@ -197,6 +197,8 @@ __device__ __forceinline__ int warp_lower_bound(const long long *__restrict__ ph
 
 #define TT_THREADS 1024
 #define TT_CHUNK 32		// frontier nodes refined per round
+#define TT_FAST 4096		// refinement trees up to this size are numbered out of shared memory
+#define TT_DYN_SMEM (TT_FAST * (8 + 5 * 4))
 #define TT_MAXBLOCKS (G2GPU_MAX_GRAVS + 1)
 // scratch of the breadth-first refinement (temporary numbering)
 struct G2TopScratch
@@ -295,166 +297,226 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
       __syncthreads();
     }
 
-  if(tid != 0)
-    return;
-  tt->err = s_err;
+  // ---- the numbering passes are sequential (they ARE the reference's recursion order); run them on one thread, but
+  //      out of shared memory: the refinement tree is staged by all threads first (global loads on a single
+  //      thread cost ~0.5 us each and dominated this kernel).  Larger trees fall back to global memory.
+  extern __shared__ unsigned char tt_dyn[];
+  long long *m_start = (long long *) tt_dyn;	// TT_FAST
+  int *m_child = (int *) (m_start + TT_FAST);
+  int *m_count = m_child + TT_FAST;
+  int *m_shift = m_count + TT_FAST;
+  int *m_daughter = m_shift + TT_FAST;
+  int *m_leaf = m_daughter + TT_FAST;
+  const int ntmp = s_ntmp;
+  const bool fast = ntmp <= TT_FAST;
+  if(fast)
+    for(int i = tid; i < ntmp; i += TT_THREADS)
+      {
+	m_start[i] = ts->start[i];
+	m_child[i] = ts->child[i];
+	m_count[i] = ts->count[i];
+	m_shift[i] = ts->shift[i];
+      }
+  __syncthreads();
+#define TS_START(i) (fast ? m_start[i] : ts->start[i])
+#define TS_CHILD(i) (fast ? m_child[i] : ts->child[i])
+#define TS_COUNT(i) (fast ? m_count[i] : ts->count[i])
+#define TS_SHIFT(i) (fast ? m_shift[i] : ts->shift[i])
+#define TT_DAUGHTER(i) (fast ? m_daughter[i] : tt->daughter[i])
+#define TT_LEAF(i) (fast ? m_leaf[i] : tt->leaf[i])
+#define SET_DAUGHTER(i, v) do { const int v__ = (v); tt->daughter[i] = v__; if(fast) m_daughter[i] = v__; } while(0)
+#define SET_LEAF(i, v) do { const int v__ = (v); tt->leaf[i] = v__; if(fast) m_leaf[i] = v__; } while(0)
+
+  if(tid == 0)
+    {
+      tt->err = s_err;
+      if(!s_err)
+	{
+	  int sp = 0;
+	  // ---- depth-first numbering exactly as the recursion of domain_topsplit_local (domain.c:1019-1075): a node that
+	  //      is split allocates its 8 daughters when it is entered, then enters the daughters that exceed the threshold
+	  int stack_node[32], stack_tmp[32], stack_i[32];
+	  int ntop = 1;
+	  SET_DAUGHTER(0, -1);
+	  SET_LEAF(0, -1);
+	  tt->shift[0] = TS_SHIFT(0); tt->startkey[0] = 0; tt->count[0] = n;
+	  {
+	    int pend_node = 0, pend_tmp = 0;
+	    bool pending = true;
+	    while(pending || sp > 0)
+	      {
+		if(pending)
+		  {		// enter (pend_node, pend_tmp)
+		    pending = false;
+		    int c0 = TS_CHILD(pend_tmp);
+		    if(c0 >= 0)
+		      {
+			SET_DAUGHTER(pend_node, ntop);
+			for(int i = 0; i < 8; i++)
+			  {
+			    SET_DAUGHTER(ntop + i, -1);
+			    SET_LEAF(ntop + i, -1);
+			    tt->shift[ntop + i] = TS_SHIFT(c0 + i); tt->startkey[ntop + i] = TS_START(c0 + i); tt->count[ntop + i] = TS_COUNT(c0 + i);
+			  }
+			stack_node[sp] = ntop; stack_tmp[sp] = c0; stack_i[sp] = 0; sp++;	// daughters base, tmp children base
+			ntop += 8;
+		      }
+		    continue;
+		  }
+		int i = stack_i[sp - 1];
+		if(i == 8)
+		  {
+		    sp--;
+		    continue;
+		  }
+		stack_i[sp - 1] = i + 1;
+		if(TS_CHILD(stack_tmp[sp - 1] + i) >= 0)
+		  {
+		    pend_node = stack_node[sp - 1] + i;
+		    pend_tmp = stack_tmp[sp - 1] + i;
+		    pending = true;
+		  }
+	      }
+	  }
+	  tt->ntopnodes = ntop;
+
+	  // ---- leaves in Peano-Hilbert order: domain_walktoptree (domain.c:802-816)
+	  int nleaves = 0;
+	  {
+	    int st_node[32], st_i[32];
+	    sp = 0;
+	    if(TT_DAUGHTER(0) == -1)
+	      SET_LEAF(0, nleaves++);
+	    else
+	      {
+		st_node[0] = 0; st_i[0] = 0; sp = 1;
+	      }
+	    while(sp > 0)
+	      {
+		int node = st_node[sp - 1], i = st_i[sp - 1];
+		if(i == 8)
+		  {
+		    sp--;
+		    continue;
+		  }
+		st_i[sp - 1] = i + 1;
+		int sub = TT_DAUGHTER(node) + i;
+		if(TT_DAUGHTER(sub) == -1)
+		  SET_LEAF(sub, nleaves++);
+		else
+		  {
+		    st_node[sp] = sub; st_i[sp] = 0; sp++;
+		  }
+	      }
+	  }
+	  tt->ntopleaves = nleaves;
+
+	  // ---- force-tree nodes of the top-level tree: root (forcetree.c:103-110) + force_create_empty_nodes
+	  //      (forcetree.c:292-336): children created in loop order i(x) outer, k(z) inner, each followed at once by
+	  //      its own subtree; the TopNodes daughter of octant (i,j,k) is the last PH digit of the child's cell.
+	  //      The parent's geometry travels on the stack (no read-back from global memory).
+	  {
+	    int nf = 1;
+	    int st_k[32], st_top[32], st_state[32], st_c[32], st_depth[32];
+	    float st_len[32], st_cx[32], st_cy[32], st_cz[32];
+	    unsigned long long st_mort[32];
+	    tt->flen[0] = (float) dom[6];
+	    tt->fcx[0] = (float) dom[3]; tt->fcy[0] = (float) dom[4]; tt->fcz[0] = (float) dom[5];
+	    tt->fdepth[0] = 0; tt->fmorton[0] = 0; tt->ffather[0] = -1; tt->fnode[0] = 0;
+	    for(int s = 0; s < 8; s++)
+	      tt->fsuns[0][s] = -1;
+	    tt->fisleaf[0] = (TT_DAUGHTER(0) == -1);
+	    if(TT_DAUGHTER(0) == -1)
+	      tt->dni[TT_LEAF(0)] = 0;
+	    st_k[0] = 0; st_top[0] = 0; st_state[0] = 0; st_c[0] = 0; st_depth[0] = 0; st_mort[0] = 0;
+	    st_len[0] = (float) dom[6]; st_cx[0] = (float) dom[3]; st_cy[0] = (float) dom[4]; st_cz[0] = (float) dom[5];
+	    sp = 1;
+	    while(sp > 0)
+	      {
+		const int f = sp - 1;
+		const int k = st_k[f], top = st_top[f], cidx = st_c[f];
+		const int dbase = TT_DAUGHTER(top);
+		if(dbase < 0 || cidx == 8)
+		  {
+		    sp--;
+		    continue;
+		  }
+		st_c[f] = cidx + 1;
+		const int i = (cidx >> 2) & 1, j = (cidx >> 1) & 1, kk = cidx & 1;	// loop order i, j, k
+		const unsigned int e = c_ph_table[st_state[f] * 8 + (i << 2 | j << 1 | kk)];
+		const int sub = e & 7;
+		const int slot = i + 2 * j + 4 * kk;
+		const int nn = nf++;
+		tt->fsuns[k][slot] = nn;
+		const float plen = st_len[f];
+		const double q = __dmul_rn(0.25, (double) plen);
+		const float nlen = 0.5f * plen;
+		const float ncx = (float) __dadd_rn((double) st_cx[f], i ? q : -q);
+		const float ncy = (float) __dadd_rn((double) st_cy[f], j ? q : -q);
+		const float ncz = (float) __dadd_rn((double) st_cz[f], kk ? q : -q);
+		const unsigned long long nm = (st_mort[f] << 3) | (unsigned long long) slot;
+		tt->flen[nn] = nlen; tt->fcx[nn] = ncx; tt->fcy[nn] = ncy; tt->fcz[nn] = ncz;
+		tt->fdepth[nn] = st_depth[f] + 1;
+		tt->fmorton[nn] = nm;
+		tt->ffather[nn] = k;
+		for(int s = 0; s < 8; s++)
+		  tt->fsuns[nn][s] = -1;
+		const int tsub = dbase + sub;
+		tt->fnode[tsub] = nn;
+		const bool isleaf = TT_DAUGHTER(tsub) == -1;
+		tt->fisleaf[nn] = isleaf;
+		if(isleaf)
+		  tt->dni[TT_LEAF(tsub)] = nn;
+		st_k[sp] = nn; st_top[sp] = tsub; st_state[sp] = (int) (e >> 3); st_c[sp] = 0; st_depth[sp] = st_depth[f] + 1; st_mort[sp] = nm;
+		st_len[sp] = nlen; st_cx[sp] = ncx; st_cy[sp] = ncy; st_cz[sp] = ncz;
+		sp++;
+	      }
+	  }
+	}
+      __threadfence();
+    }
+  __syncthreads();
   if(s_err)
     return;
 
-  // ---- depth-first numbering exactly as the recursion of domain_topsplit_local (domain.c:1019-1075)
-  int stack_node[32], stack_tmp[32], stack_i[32];
-  int ntop = 1;
-  tt->daughter[0] = -1; tt->shift[0] = ts->shift[0]; tt->startkey[0] = 0; tt->count[0] = n; tt->leaf[0] = -1;
-  int sp = 0;
-  // "enter" a node: if split, allocate its 8 children
+  // ---- slot-order DFS rank (the order the walk visits top-level nodes: children 0..7, forcetree.c:526-540), in
+  //      parallel: node A precedes B iff padded path(A) < padded path(B), or the paths tie and A is shallower.
   {
-    int node = 0, tmp = 0;
-    if(ts->child[tmp] >= 0)
-      {
-	tt->daughter[node] = ntop;
-	for(int i = 0; i < 8; i++)
-	  {
-	    int ct = ts->child[tmp] + i;
-	    tt->daughter[ntop + i] = -1; tt->shift[ntop + i] = ts->shift[ct]; tt->startkey[ntop + i] = ts->start[ct];
-	    tt->count[ntop + i] = ts->count[ct]; tt->leaf[ntop + i] = -1;
-	  }
-	ntop += 8;
-	stack_node[0] = node; stack_tmp[0] = tmp; stack_i[0] = 0; sp = 1;
-      }
-  }
-  while(sp > 0)
-    {
-      int node = stack_node[sp - 1], tmp = stack_tmp[sp - 1], i = stack_i[sp - 1];
-      if(i == 8)
+    const int ntop = *((volatile int *) &tt->ntopnodes);
+    unsigned long long *m_key = (unsigned long long *) m_start;	// reuse the staging area
+    int *m_depth = m_child;
+    const bool fastd = ntop <= TT_FAST;
+    if(fastd)
+      for(int k = tid; k < ntop; k += TT_THREADS)
 	{
-	  sp--;
-	  continue;
+	  int d = __ldcg(&tt->fdepth[k]);
+	  m_depth[k] = d;
+	  m_key[k] = d == 0 ? 0ull : (__ldcg(&tt->fmorton[k]) << (3 * (G2_MAXDEPTH - d)));
 	}
-      stack_i[sp - 1] = i + 1;
-      int sub = tt->daughter[node] + i, ct = ts->child[tmp] + i;
-      if(ts->child[ct] >= 0)
-	{
-	  tt->daughter[sub] = ntop;
-	  for(int j = 0; j < 8; j++)
-	    {
-	      int c2 = ts->child[ct] + j;
-	      tt->daughter[ntop + j] = -1; tt->shift[ntop + j] = ts->shift[c2]; tt->startkey[ntop + j] = ts->start[c2];
-	      tt->count[ntop + j] = ts->count[c2]; tt->leaf[ntop + j] = -1;
-	    }
-	  ntop += 8;
-	  stack_node[sp] = sub; stack_tmp[sp] = ct; stack_i[sp] = 0; sp++;
-	}
-    }
-  tt->ntopnodes = ntop;
-
-  // ---- leaves in Peano-Hilbert order: domain_walktoptree (domain.c:802-816)
-  int nleaves = 0;
-  {
-    int st_node[32], st_i[32];
-    sp = 0;
-    if(tt->daughter[0] == -1)
-      tt->leaf[0] = nleaves++;
-    else
+    __syncthreads();
+    for(int k = tid; k < ntop; k += TT_THREADS)
       {
-	st_node[0] = 0; st_i[0] = 0; sp = 1;
-      }
-    while(sp > 0)
-      {
-	int node = st_node[sp - 1], i = st_i[sp - 1];
-	if(i == 8)
+	int dk = fastd ? m_depth[k] : __ldcg(&tt->fdepth[k]);
+	unsigned long long kk = fastd ? m_key[k] : (dk == 0 ? 0ull : (__ldcg(&tt->fmorton[k]) << (3 * (G2_MAXDEPTH - dk))));
+	int rank = 0;
+	for(int j = 0; j < ntop; j++)
 	  {
-	    sp--;
-	    continue;
+	    int dj = fastd ? m_depth[j] : __ldcg(&tt->fdepth[j]);
+	    unsigned long long kj = fastd ? m_key[j] : (dj == 0 ? 0ull : (__ldcg(&tt->fmorton[j]) << (3 * (G2_MAXDEPTH - dj))));
+	    rank += (kj < kk || (kj == kk && dj < dk)) ? 1 : 0;
 	  }
-	st_i[sp - 1] = i + 1;
-	int sub = tt->daughter[node] + i;
-	if(tt->daughter[sub] == -1)
-	  tt->leaf[sub] = nleaves++;
-	else
-	  {
-	    st_node[sp] = sub; st_i[sp] = 0; sp++;
-	  }
+	tt->fdfs[k] = rank;
+	tt->fdfs_inv[rank] = k;
       }
   }
-  tt->ntopleaves = nleaves;
-
-  // ---- force-tree nodes of the top-level tree: root (forcetree.c:103-110) + force_create_empty_nodes
-  //      (forcetree.c:292-336): children created in loop order i(x) outer, k(z) inner, each followed at once by
-  //      its own subtree; TopNodes daughter of octant (i,j,k) is the last PH digit of the child's cell.
-  {
-    int nf = 0;
-    tt->flen[0] = (float) dom[6];
-    tt->fcx[0] = (float) dom[3]; tt->fcy[0] = (float) dom[4]; tt->fcz[0] = (float) dom[5];
-    tt->fdepth[0] = 0; tt->fmorton[0] = 0; tt->ffather[0] = -1; tt->fnode[0] = 0;
-    for(int s = 0; s < 8; s++)
-      tt->fsuns[0][s] = -1;
-    tt->fisleaf[0] = (tt->daughter[0] == -1);
-    if(tt->fisleaf[0])
-      tt->dni[tt->leaf[0]] = 0;
-    nf = 1;
-    int st_k[32], st_top[32], st_state[32], st_c[32];
-    sp = 0;
-    st_k[0] = 0; st_top[0] = 0; st_state[0] = 0; st_c[0] = 0; sp = 1;
-    while(sp > 0)
-      {
-	int k = st_k[sp - 1], top = st_top[sp - 1], state = st_state[sp - 1], cidx = st_c[sp - 1];
-	if(tt->daughter[top] < 0 || cidx == 8)
-	  {
-	    sp--;
-	    continue;
-	  }
-	st_c[sp - 1] = cidx + 1;
-	int i = (cidx >> 2) & 1, j = (cidx >> 1) & 1, kk = cidx & 1;	// loop order i, j, k
-	unsigned int e = c_ph_table[state * 8 + (i << 2 | j << 1 | kk)];
-	int sub = e & 7;
-	int slot = i + 2 * j + 4 * kk;
-	int nn = nf++;
-	tt->fsuns[k][slot] = nn;
-	float plen = tt->flen[k];
-	tt->flen[nn] = 0.5f * plen;
-	double q = __dmul_rn(0.25, (double) plen);
-	tt->fcx[nn] = (float) __dadd_rn((double) tt->fcx[k], i ? q : -q);
-	tt->fcy[nn] = (float) __dadd_rn((double) tt->fcy[k], j ? q : -q);
-	tt->fcz[nn] = (float) __dadd_rn((double) tt->fcz[k], kk ? q : -q);
-	tt->fdepth[nn] = tt->fdepth[k] + 1;
-	tt->fmorton[nn] = (tt->fmorton[k] << 3) | (unsigned long long) slot;
-	tt->ffather[nn] = k;
-	for(int s = 0; s < 8; s++)
-	  tt->fsuns[nn][s] = -1;
-	int tsub = tt->daughter[top] + sub;
-	tt->fnode[tsub] = nn;
-	tt->fisleaf[nn] = (tt->daughter[tsub] == -1);
-	if(tt->fisleaf[nn])
-	  tt->dni[tt->leaf[tsub]] = nn;
-	st_k[sp] = nn; st_top[sp] = tsub; st_state[sp] = (int) (e >> 3); st_c[sp] = 0; sp++;
-      }
-    // nf == ntop by construction
-  }
-
-  // ---- slot-order DFS rank (the order the walk visits top-level nodes: children 0..7, forcetree.c:526-540)
-  {
-    int st_k[32], st_s[32];
-    int rank = 0;
-    sp = 0;
-    tt->fdfs[0] = rank; tt->fdfs_inv[rank] = 0; rank++;
-    st_k[0] = 0; st_s[0] = 0; sp = 1;
-    while(sp > 0)
-      {
-	int k = st_k[sp - 1], s = st_s[sp - 1];
-	if(s == 8)
-	  {
-	    sp--;
-	    continue;
-	  }
-	st_s[sp - 1] = s + 1;
-	int ch = tt->fsuns[k][s];
-	if(ch >= 0)
-	  {
-	    tt->fdfs[ch] = rank; tt->fdfs_inv[rank] = ch; rank++;
-	    st_k[sp] = ch; st_s[sp] = 0; sp++;
-	  }
-      }
-  }
+#undef TS_START
+#undef TS_CHILD
+#undef TS_COUNT
+#undef TS_SHIFT
+#undef TT_DAUGHTER
+#undef TT_LEAF
+#undef SET_DAUGHTER
+#undef SET_LEAF
 }
 
 // ---------------------------------------------------------------- stand-alone key kernel (tests) ---------------
@@ -520,7 +582,8 @@ int g2_stage_domain(g2gpu_ctx *c)
   block_starts_kernel<<<1, 32, 0, st>>>(k, n, nblocks, c->d_species_start);
   if(!c->d_topscratch)
     G2_CUDA(cudaMalloc(&c->d_topscratch, sizeof(G2TopScratch)));
-  toptree_kernel<<<1, TT_THREADS, 0, st>>>(c->phkey, c->d_species_start, nblocks, n, c->d_domain, c->d_top, (G2TopScratch *) c->d_topscratch);
+  G2_CUDA(cudaFuncSetAttribute(toptree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_DYN_SMEM));
+  toptree_kernel<<<1, TT_THREADS, TT_DYN_SMEM, st>>>(c->phkey, c->d_species_start, nblocks, n, c->d_domain, c->d_top, (G2TopScratch *) c->d_topscratch);
   c->launches += 3;
   G2_CUDA(cudaEventRecord(c->ev[3], st));
   G2_CUDA(cudaGetLastError());
