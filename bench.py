@@ -334,8 +334,12 @@ def main():
     walk_ms = stage["walk_kernel_ms"] / K
     flops_alg = terms * FLOP_PER_TERM[w["flop"]]
     achieved = flops_alg / (walk_ms * 1e-3) / 1e12 * (1.0 if world == 1 else 1.0 / world)
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(w["key"])
+    except Exception:
+        traffic = None
     roofline = {"kernel": "walk_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                "traffic": None, "share_of_step": walk_ms / ms_step,
+                "traffic": traffic, "share_of_step": walk_ms / ms_step,
                 "note": f"algorithmic flops = species terms x {FLOP_PER_TERM[w['flop']]:.0f} (SURVEY.md §8d), cell-opening arithmetic excluded; peak = "
                         f"{prop.multi_processor_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal CUDA-core FP32, of MEASURED_PEAKS sm_max_mhz)"}
     hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
