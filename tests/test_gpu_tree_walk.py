@@ -155,3 +155,113 @@ def test_periodic_treepm_shortrange(n, outdir):
         assert s["median"] <= MEDIAN_TOL, s
         assert s["p999"] <= P999_TOL, s
         assert s["cost_mismatch"] <= 0.002 * n, s
+
+
+def test_config1_galaxy_collision_fixture(outdir):
+    """BASELINE config 1 (GalaxyCollision.IC + Configuration.reference, 60 000 particles): GPU against the committed fixture
+    generated from the unmodified reference (tests/golden/make_golden.py)."""
+    import hashlib
+    from g2gpu import TreeGravity
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_galaxycollision.npz"))
+    o = g["order_id"]
+    pos, mass, ptype = g["in_pos"][o], g["in_mass"][o], g["in_type"][o]
+    n = len(mass)
+    tg = TreeGravity(max_part=int(g["maxpart"]), n_gravs=2)
+    tg.set_species(g["grav"], g2test.force_softening(g["soft"]))
+    tg.set_laws()
+    G = float(g["G"])
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+    assert hashlib.sha256(tg.keys().tobytes()).hexdigest() == str(g["keys_sha"])
+    assert tg.treebuild() == int(g["numnodes"])
+    t = tg.tree()
+    for k in ("len", "center", "s", "mass", "bitflags", "sibling", "nextnode", "father", "p_nextnode", "p_father"):
+        assert hashlib.sha256(np.ascontiguousarray(t[k]).tobytes()).hexdigest() == str(g["sha_" + k]), k
+    tg.walk(tg.walk_params(theta=0.5, errtol=0.005, G=G))
+    acc, cost, old = tg.download_acc()
+    s1 = summarize(g2test.rel_err(acc, g["bh_acc"]))
+    s1["cost_mismatch"] = int(np.sum(cost != g["bh_cost"]))
+    tg.upload(pos, mass, ptype, oldacc=g["bh_oldacc"])
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.0, errtol=0.005, G=G))
+    acc2, cost2, _ = tg.download_acc()
+    s2 = summarize(g2test.rel_err(acc2, g["rel_acc"]))
+    s2["cost_mismatch"] = int(np.sum(cost2 != g["rel_cost"]))
+    s2["ia_per_part"] = float(cost2.mean())
+    dump(outdir, "walk_config1.json", dict(bh=s1, relative=s2))
+    tg.close()
+    for s in (s1, s2):
+        assert s["median"] <= MEDIAN_TOL and s["p999"] <= P999_TOL, s
+        assert s["cost_mismatch"] <= 0.002 * n, s
+
+
+def test_four_species_with_gas_fixture(outdir):
+    """BASELINE config 4 in miniature: all 6 particle types mapped onto 4 gravitational species (gas = species 0, a separate
+    leading block), periodic TreePM; GPU against the reference fixture."""
+    from g2gpu import TreeGravity
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pm64_d4_poisson4096.npz"))
+    o = g["order_id"]
+    pos, mass, ptype = g["in_pos"][o], g["in_mass"][o], g["in_type"][o]
+    n = len(mass)
+    tg = TreeGravity(max_part=int(g["maxpart"]), n_gravs=4, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(g["grav"], g2test.force_softening(g["soft"]))
+    tg.set_laws()
+    tg.set_srtable(g["srtable"])
+    # from the ORIGINAL order: the device sort must reproduce the reference's gas-first, species-major PH order
+    tg.upload(g["in_pos"], g["in_mass"], g["in_type"])
+    tg.domain()
+    perm = tg.order()
+    assert np.array_equal(tg.keys(), g["keys"])
+    same = perm == o
+    assert same.mean() > 0.99                       # ties of equal keys only
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+    assert tg.treebuild() == len(g["tree_len"])
+    t = tg.tree()
+    for k in ("len", "center", "s", "mass", "bitflags", "sibling", "nextnode", "father", "p_nextnode", "p_father"):
+        assert np.array_equal(t[k], g["tree_" + k]), k
+    wp = tg.walk_params(theta=0.5, errtol=0.005, boxsize=float(g["box"]), G=1.0, asmth=float(g["asmth"]), rcut=float(g["rcut"]))
+    tg.walk(wp)
+    acc, cost, old = tg.download_acc()
+    s1 = summarize(g2test.rel_err(acc, g["bh_acc"]))
+    s1["cost_mismatch"] = int(np.sum(cost != g["bh_cost"]))
+    dump(outdir, "walk_d4.json", s1)
+    tg.close()
+    assert s1["median"] <= MEDIAN_TOL and s1["p999"] <= P999_TOL, s1
+    assert s1["cost_mismatch"] <= 0.002 * n, s1
+
+
+def test_accuracy_against_direct_summation(outdir):
+    """gravtree_forcetest-style check (gravtree_forcetest.c:28, forcetree.c:3428): the GPU tree force has the same error
+    distribution against the reference's direct summation as the reference's own tree force."""
+    if not available("np_d2_f32_ft"):
+        pytest.skip("oracle/_ref not built")
+    n = 30000
+    pos, mass, ptype = g2test.hernquist(n, seed=99)
+    soft, grav = g2test.SOFT_NP, g2test.GRAV_D2
+    ref = run_reference("np_d2_f32_ft", pos, mass, ptype, soft, grav)
+    rp = ref.particles()
+    ref.gravity()
+    r1 = ref.particles()
+    ref.set_opening(0.0, 0.005, 1)
+    ref.gravity()
+    r2 = ref.particles()
+    targets = np.arange(0, n, 37, dtype=np.int32)
+    direct = ref.direct(targets)                    # pre-G direct sum, G = 1
+    tg = gpu_for(ref, n)
+    tg.set_species(grav, g2test.force_softening(soft))
+    tg.set_laws()
+    tg.upload(rp["pos"], rp["mass"], rp["type"], oldacc=r1["oldacc"])
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.0, errtol=0.005, G=1.0))
+    acc, cost, old = tg.download_acc()
+    tg.close()
+    e_gpu = g2test.rel_err(acc[targets], direct)
+    e_ref = g2test.rel_err(r2["acc"][targets], direct)
+    dump(outdir, "forcetest.json", dict(gpu=summarize(e_gpu), ref=summarize(e_ref)))
+    assert abs(np.median(e_gpu) - np.median(e_ref)) <= 0.02 * np.median(e_ref)
+    assert np.percentile(e_gpu, 99) <= 1.05 * np.percentile(e_ref, 99)
