@@ -40,6 +40,7 @@ struct WalkArgs
   float errtol;			// ErrTolForceAcc
   float boxsize, boxinv;
   float rcut, rcut2, asmthfac, utor2wpi;
+  float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
   double G, pos_fac_pre_g, pos_fac_post_g;
   int use_gravpm;
   float fsoft[6];
@@ -50,11 +51,17 @@ struct WalkArgs
 
 // NEAREST(x) (forcetree.c:43): x > L/2 -> x - L, x < -L/2 -> x + L.  For |x| < 1.5 L this equals x - L*rint(x/L)
 // (round-half-even leaves x = +-L/2 untouched, like the strict comparisons of the macro): 3 instructions.
+// rint() for |t| < 2^22 on the FMA pipe (two adds with 1.5*2^23) instead of FRND, which runs on the quarter-rate XU pipe
+__device__ __forceinline__ float rint_small(float t)
+{
+  return __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+}
+
 template <bool PERIODIC>
 __device__ __forceinline__ float nearest(float x, float boxsize, float boxinv)
 {
   if(PERIODIC)
-    x = fmaf(-boxsize, rintf(x * boxinv), x);
+    x = fmaf(-boxsize, rint_small(x * boxinv), x);
   return x;
 }
 
@@ -65,40 +72,77 @@ __device__ __forceinline__ float fast_rsqrt(float x)
   return y;
 }
 
-// one species term of an interaction: adds d*fac to the FP32 partial sums of the current visit (the visit's sum
-// goes into the FP64/FP32 accumulators once); returns whether it counted
-template <bool SR, bool STOCK>
-__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, int tg, int sg, int D, float pmass, float m, float dx,
-					  float dy, float dz, float r2, float h, float &fx, float &fy, float &fz)
+__device__ __forceinline__ float lds_f32(unsigned int saddr)
 {
-  float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
-  float r = r2 * rinv;
-  float fac;
-  if(SR)
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
+// one species term of an interaction: adds d*fac to the lane's FP32 partial sums; returns whether it counted
+// (mass != 0 and, for TreePM, r inside the short-range table: forcetree.c:1553-1582, 1958-2026).
+// Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the rare r < h case.
+template <bool SR, bool STOCK>
+__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
+					  float pmass, float m, float dx, float dy, float dz, float r2, float h, float &fx, float &fy, float &fz)
+{
+  const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
+  const float r = r2 * rinv;
+  if(STOCK)
     {
-      int tabindex = (int) (A.asmthfac * r);	// forcetree.c:1962
-      if(tabindex >= A.ntab)
-	return false;
-      if(r >= h)
+      bool counted = m != 0.0f;
+      float fac;
+      if(SR)
 	{
-	  float a = STOCK ? m * rinv * rinv : accel_over_r(A.laws.accel[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, r2, r, rinv, 1.0f) * r;
-	  float t = STOCK ? s_tab[tabindex] : s_tab[(int) A.tabmap[tg * D + sg] * A.ntab + tabindex];
-	  fac = (a - m * A.utor2wpi * t) * rinv;	// forcetree.c:1972-1974
+	  int tabindex = (int) (A.asmthfac * r);	// forcetree.c:1962
+	  counted = counted && tabindex < A.ntab;
+	  tabindex = min(tabindex, A.ntab - 1);
+	  const float t = lds_f32(s_tab_addr + 4u * (unsigned int) tabindex);
+	  // (m/r^2 - m*utor2wpi*tab) / r   (forcetree.c:1972-1974)
+	  fac = m * rinv * fmaf(-A.utor2wpi, t, rinv * rinv);
 	}
       else
-	fac = STOCK ? law_plummer(m, h, r) : accel_spline(A.laws.spline[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, h, r, 1.0f);
+	fac = m * rinv * rinv * rinv;
+      if(r < h)			// inside the softening: spline (rare)
+	fac = law_plummer(m, h, r);
+      fac = counted ? fac : 0.0f;
+      fx = fmaf(dx, fac, fx);
+      fy = fmaf(dy, fac, fy);
+      fz = fmaf(dz, fac, fz);
+      return counted;
     }
   else
     {
-      if(r >= h)
-	fac = STOCK ? m * rinv * rinv * rinv : accel_over_r(A.laws.accel[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, r2, r, rinv, 1.0f);
+      if(m == 0.0f)
+	return false;
+      float fac;
+      const int ij = tg * D + sg;
+      if(SR)
+	{
+	  int tabindex = (int) (A.asmthfac * r);
+	  if(tabindex >= A.ntab)
+	    return false;
+	  if(r >= h)
+	    {
+	      float a = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, 1.0f) * r;
+	      float t = s_tab[(int) A.tabmap[ij] * A.ntab + tabindex];
+	      fac = (a - m * A.utor2wpi * t) * rinv;
+	    }
+	  else
+	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, 1.0f);
+	}
       else
-	fac = STOCK ? law_plummer(m, h, r) : accel_spline(A.laws.spline[tg * D + sg], A.laws.par[tg * D + sg], pmass, m, h, r, 1.0f);
+	{
+	  if(r >= h)
+	    fac = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, 1.0f);
+	  else
+	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, 1.0f);
+	}
+      fx = fmaf(dx, fac, fx);
+      fy = fmaf(dy, fac, fy);
+      fz = fmaf(dz, fac, fz);
+      return true;
     }
-  fx = fmaf(dx, fac, fx);
-  fy = fmaf(dy, fac, fy);
-  fz = fmaf(dz, fac, fz);
-  return true;
 }
 
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC>
@@ -114,6 +158,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
     }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
+  const unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
   unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
 #pragma unroll
   for(int t = 0; t < 6; t++)
@@ -147,6 +192,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
       const int tg = A.t2g[ptype];
       const float hself = A.fsoft[ptype];
       ACC ax = 0, ay = 0, az = 0;
+      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
       int ninter = 0, nterms = 0;
       unsigned int skip_until = valid ? 0u : 0xffffffffu;
       unsigned int cur = 0;
@@ -158,19 +204,40 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
 	  bool open = false;
+	  // TreePM: a cell that can interact with (or must be opened by) a target lies within rcut + len of it, so for
+	  // len < L/2 - rcut every point of the cell has the same periodic image as the cell centre; points of cells that
+	  // are culled anyway can only look farther away.  The image shift is then computed once per cell, not per point.
+	  const bool small_cell = SR && PERIODIC && q0.x < A.shift_len_max;	// warp-uniform (a property of the cell)
+	  float shx = 0.0f, shy = 0.0f, shz = 0.0f;
 	  if(cur >= skip_until)
 	    {
 	      float dx[D], dy[D], dz[D], r2[D], mass[D];
 	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
+	      const float cxr = q0.y - px, cyr = q0.z - py, czr = q0.w - pz;
+	      if(SR && PERIODIC)
+		{
+		  shx = A.boxsize * rint_small(cxr * A.boxinv);
+		  shy = A.boxsize * rint_small(cyr * A.boxinv);
+		  shz = A.boxsize * rint_small(czr * A.boxinv);
+		}
 #pragma unroll
 	      for(int g = 0; g < D; g++)
 		{
 		  const float4 q = __ldg(rec + 1 + g);
 		  mass[g] = q.w;
 		  summass += q.w;
-		  dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
-		  dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
-		  dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
+		  if(small_cell)
+		    {
+		      dx[g] = (q.x - px) - shx;
+		      dy[g] = (q.y - py) - shy;
+		      dz[g] = (q.z - pz) - shz;
+		    }
+		  else
+		    {
+		      dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
+		      dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
+		      dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
+		    }
 		  r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
 		  r2min = fminf(r2min, r2[g]);
 		  r2max = fmaxf(r2max, r2[g]);
@@ -182,9 +249,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		  if(r2min > A.rcut2)
 		    {		// forcetree.c:1828-1862
 		      const float eff = A.rcut + 0.5f * len;
-		      float d0 = nearest<PERIODIC>(q0.y - px, A.boxsize, A.boxinv);
-		      float d1 = nearest<PERIODIC>(q0.z - py, A.boxsize, A.boxinv);
-		      float d2 = nearest<PERIODIC>(q0.w - pz, A.boxsize, A.boxinv);
+		      const float d0 = PERIODIC ? cxr - shx : cxr, d1 = PERIODIC ? cyr - shy : cyr, d2 = PERIODIC ? czr - shz : czr;
 		      if(d0 < -eff || d0 > eff || d1 < -eff || d1 > eff || d2 < -eff || d2 > eff)
 			done = true;
 		    }
@@ -200,7 +265,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		    {		// relative criterion, forcetree.c:1446-1472
 		      if(summass * len * len > r2min * r2min * aold)
 			open = true;
-		      else if(fabsf(q0.y - px) < 0.60f * len && fabsf(q0.z - py) < 0.60f * len && fabsf(q0.w - pz) < 0.60f * len)
+		      else if(fabsf(cxr) < 0.60f * len && fabsf(cyr) < 0.60f * len && fabsf(czr) < 0.60f * len)
 			open = true;
 		    }
 		}
@@ -222,29 +287,28 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		  if(!done)
 		    {
 		      bool any = false;
-		      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
 #pragma unroll
 		      for(int g = 0; g < D; g++)
-			if(mass[g] != 0.0f)
-			  {
-			    bool cnt = pair_term<SR, STOCK>(A, s_tab, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, fx, fy, fz);
-			    any |= cnt;
-			    nterms += cnt;
-			  }
-		      ax += (ACC) fx;
-		      ay += (ACC) fy;
-		      az += (ACC) fz;
+			{
+			  bool cnt = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, fx, fy, fz);
+			  any |= cnt;
+			  nterms += cnt;
+			}
 		      if(!SR || any)
 			ninter++;	// forcetree.c:1585 resp. 2031-2032
 		    }
 		}
 	    }
 	  tot_visits++;
+	  if((tot_visits & 7u) == 0u)
+	    {			// FP32 partial sums of at most 8 visits go into the (FP64) accumulators: few conversions, bounded error
+	      ax += (ACC) fx; ay += (ACC) fy; az += (ACC) fz;
+	      fx = fy = fz = 0.0f;
+	    }
 	  if(__any_sync(0xffffffffu, open))
 	    {
 	      // direct particle children of the opened cell, for the lanes that opened it
 	      const unsigned int np = w.z & 15u;
-	      float fx = 0.0f, fy = 0.0f, fz = 0.0f;
 	      for(unsigned int j = 0; j < np; j++)
 		{
 		  const float4 p = __ldg(A.wpart + w.y + j);
@@ -255,29 +319,37 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		      float h = hself;
 		      if(UNEQUAL)
 			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
-		      float ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
-		      float ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
-		      float ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
+		      float ddx, ddy, ddz;
+		      if(small_cell)
+			{
+			  ddx = (p.x - px) - shx;
+			  ddy = (p.y - py) - shy;
+			  ddz = (p.z - pz) - shz;
+			}
+		      else
+			{
+			  ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
+			  ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
+			  ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
+			}
 		      float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
-		      bool counted = pair_term<SR, STOCK>(A, s_tab, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, fx, fy, fz);
+		      bool counted = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, fx, fy, fz);
 		      nterms += counted;
 		      if(!SR || counted)
 			ninter++;
 		    }
 		}
-	      ax += (ACC) fx;
-	      ay += (ACC) fy;
-	      az += (ACC) fz;
 	      cur = cur + 1;
 	    }
 	  else
 	    cur = w.x;
 	}
 
+      ax += (ACC) fx; ay += (ACC) fy; az += (ACC) fz;
       if(valid)
 	{
 	  // gravity_tree epilogue: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
-	  float fx = (float) ax, fy = (float) ay, fz = (float) az;
+	  fx = (float) ax; fy = (float) ay; fz = (float) az;
 	  if(A.pos_fac_pre_g != 0.0)
 	    {
 	      fx = (float) ((double) fx + A.pos_fac_pre_g * (double) px);
@@ -422,6 +494,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.rcut = (float) wp->rcut; A.rcut2 = (float) (wp->rcut * wp->rcut);
       A.asmthfac = (float) (0.5 / wp->asmth * (c->cfg.ntab / 3.0));	// forcetree.c:1708
       A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
+      A.shift_len_max = (float) (0.499 * wp->boxsize - 1.001 * wp->rcut);
     }
   A.G = wp->G; A.pos_fac_pre_g = wp->pos_fac_pre_g; A.pos_fac_post_g = wp->pos_fac_post_g;
   A.use_gravpm = wp->use_gravpm && c->have_gravpm;
