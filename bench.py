@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--workload", default="hernquist1m")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--acc-float", action="store_true", help="FP32 accumulators in the walk (default FP64)")
+    ap.add_argument("--walk-group", type=int, default=0, help="targets per walk cursor (4, 8, 16, 32); 0 = library default")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up step, no e2e / cpu_baseline legs")
     args = ap.parse_args()
 
@@ -213,6 +214,8 @@ def main():
     tg.set_laws()
     if args.acc_float:
         tg.set_option("acc_double", 0)
+    if args.walk_group:
+        tg.set_option("walk_group", args.walk_group)
     asmth, rcut = pm_split(w)
     if w["shortrange"]:
         tab = np.load(os.path.join(PKG, "data", "srtable_newton_ntab2048.npy"))

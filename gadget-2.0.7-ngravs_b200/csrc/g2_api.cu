@@ -61,6 +61,13 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->D = cfg->n_gravs;
   c->nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : G2_NSM_FALLBACK;
   c->acc_double = 1;
+  c->walk_group = 32;
+  if(getenv("G2GPU_WALK_GROUP"))
+    {
+      int g = atoi(getenv("G2GPU_WALK_GROUP"));
+      if(g == 8 || g == 32)
+	c->walk_group = g;
+    }
   for(int t = 0; t < 6; t++)
     c->force_softening[t] = 1.0;
   G2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -456,6 +463,12 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(strcmp(name, "acc_double") == 0)
     c->acc_double = value;
+  else if(strcmp(name, "walk_group") == 0)
+    {
+      if(value != 8 && value != 32)
+	return g2_fail(G2GPU_ERR_ARG, "walk_group must be 8 or 32");
+      c->walk_group = value;
+    }
   else if(strcmp(name, "rank") == 0)
     c->cfg.rank = value;
   else if(strcmp(name, "nranks") == 0)

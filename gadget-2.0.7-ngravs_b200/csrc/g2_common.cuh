@@ -87,6 +87,7 @@ struct g2gpu_ctx
   int sr_ntables;		// unique short-range tables (identical pair tables are stored once)
   unsigned char sr_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   int acc_double;		// accumulate accelerations in FP64 (default) or FP32
+  int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
 
   // upload-order inputs
   float4 *in_pm;

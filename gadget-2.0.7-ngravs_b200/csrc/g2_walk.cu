@@ -145,9 +145,17 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
     }
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, int G>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 {
+  // G = targets per cursor.  G == 32: the whole warp shares one cursor (every node record is one broadcast load).
+  // G < 32: the warp's 32 consecutive targets form 32/G sub-groups with their own cursors; a sub-group's union of
+  // interaction regions is tighter, so fewer lanes sleep through a visit, at the price of 32/G distinct record
+  // addresses per load instruction.  All sub-groups execute the same instruction stream (loads, decision, vote,
+  // particle loop), only on different nodes.  MEASURED (B200, round 1): G = 16/8/4 need 1.2-1.7x fewer iterations per
+  // cursor but run 10-30 % SLOWER than G = 32 on all three bench workloads (the divergent record loads cost more than
+  // the saved visits), and software prefetch of the next record did not help either -- the kernel is issue bound.
+  // Only G = 32 (and G = 8 with -DG2_WALK_SUBGROUPS, for experiments) is instantiated.
   extern __shared__ float s_tab[];
   __shared__ unsigned int s_chunk[WALK_WARPS];
   if(SR)
@@ -158,6 +166,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
     }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
+  const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
   const unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
   unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
 #pragma unroll
@@ -165,6 +174,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
     t2g_packed |= (unsigned int) A.t2g[t] << (4 * t);
   const int nchunks = (A.hi - A.lo + 31) >> 5;
   unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0;
+  unsigned int iter = 0;
 
   while(true)
     {
@@ -189,27 +199,36 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 	  ptype = A.ptype[idx];
 	  aold = A.errtol * A.oldacc[idx];	// forcetree.c:1289
 	}
-      const int tg = A.t2g[ptype];
+      const int tg = (t2g_packed >> (4 * ptype)) & 7;
       const float hself = A.fsoft[ptype];
       ACC ax = 0, ay = 0, az = 0;
       float fx = 0.0f, fy = 0.0f, fz = 0.0f;
       int ninter = 0, nterms = 0;
       unsigned int skip_until = valid ? 0u : 0xffffffffu;
-      unsigned int cur = 0;
       const unsigned int end = (unsigned int) A.numnodes;
+      // a sub-group without any valid target has nothing to walk
+      unsigned int cur = (__ballot_sync(0xffffffffu, valid) & gmask) ? 0u : end;
 
-      while(cur < end)
+      while(true)
 	{
-	  const float4 *rec = A.cells + (size_t) cur * R;
+	  const bool live = cur < end;
+	  if(G == 32)
+	    {
+	      if(!live)
+		break;
+	    }
+	  else if(!__any_sync(0xffffffffu, live))
+	    break;
+	  const float4 *rec = A.cells + (size_t) (live ? cur : 0u) * R;
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
 	  bool open = false;
 	  // TreePM: a cell that can interact with (or must be opened by) a target lies within rcut + len of it, so for
 	  // len < L/2 - rcut every point of the cell has the same periodic image as the cell centre; points of cells that
 	  // are culled anyway can only look farther away.  The image shift is then computed once per cell, not per point.
-	  const bool small_cell = SR && PERIODIC && q0.x < A.shift_len_max;	// warp-uniform (a property of the cell)
+	  const bool small_cell = SR && PERIODIC && q0.x < A.shift_len_max;	// uniform within a sub-group (a property of the cell)
 	  float shx = 0.0f, shy = 0.0f, shz = 0.0f;
-	  if(cur >= skip_until)
+	  if(live && cur >= skip_until)
 	    {
 	      float dx[D], dy[D], dz[D], r2[D], mass[D];
 	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
@@ -299,50 +318,57 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 		    }
 		}
 	    }
-	  tot_visits++;
-	  if((tot_visits & 7u) == 0u)
+	  iter++;
+	  if((iter & 7u) == 0u)
 	    {			// FP32 partial sums of at most 8 visits go into the (FP64) accumulators: few conversions, bounded error
 	      ax += (ACC) fx; ay += (ACC) fy; az += (ACC) fz;
 	      fx = fy = fz = 0.0f;
 	    }
-	  if(__any_sync(0xffffffffu, open))
+	  const unsigned int ball = __ballot_sync(0xffffffffu, open);
+	  const bool gopen = (ball & gmask) != 0u;	// some target of my sub-group opens the node
+	  if(live && (lane & (G - 1)) == 0)
+	    tot_visits++;
+	  if(ball != 0u)
 	    {
 	      // direct particle children of the opened cell, for the lanes that opened it
-	      const unsigned int np = w.z & 15u;
-	      for(unsigned int j = 0; j < np; j++)
+	      const unsigned int np = (live && gopen) ? (w.z & 15u) : 0u;
+	      const unsigned int npmax = (G == 32) ? np : __reduce_max_sync(0xffffffffu, np);
+	      for(unsigned int j = 0; j < npmax; j++)
 		{
-		  const float4 p = __ldg(A.wpart + w.y + j);
-		  if(open)
+		  if(j < np)
 		    {
-		      const int stype = (w.z >> (4 + 3 * j)) & 7;
-		      const int sg = (t2g_packed >> (4 * stype)) & 7;
-		      float h = hself;
-		      if(UNEQUAL)
-			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
-		      float ddx, ddy, ddz;
-		      if(small_cell)
+		      const float4 p = __ldg(A.wpart + w.y + j);
+		      if(open)
 			{
-			  ddx = (p.x - px) - shx;
-			  ddy = (p.y - py) - shy;
-			  ddz = (p.z - pz) - shz;
+			  const int stype = (w.z >> (4 + 3 * j)) & 7;
+			  const int sg = (t2g_packed >> (4 * stype)) & 7;
+			  float h = hself;
+			  if(UNEQUAL)
+			    h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
+			  float ddx, ddy, ddz;
+			  if(small_cell)
+			    {
+			      ddx = (p.x - px) - shx;
+			      ddy = (p.y - py) - shy;
+			      ddz = (p.z - pz) - shz;
+			    }
+			  else
+			    {
+			      ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
+			      ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
+			      ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
+			    }
+			  float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
+			  bool counted = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, fx, fy, fz);
+			  nterms += counted;
+			  if(!SR || counted)
+			    ninter++;
 			}
-		      else
-			{
-			  ddx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
-			  ddy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
-			  ddz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
-			}
-		      float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
-		      bool counted = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, sg, D, pmass, p.w, ddx, ddy, ddz, rr2, h, fx, fy, fz);
-		      nterms += counted;
-		      if(!SR || counted)
-			ninter++;
 		    }
 		}
-	      cur = cur + 1;
 	    }
-	  else
-	    cur = w.x;
+	  if(live)
+	    cur = gopen ? cur + 1u : w.x;
 	}
 
       ax += (ACC) fx; ay += (ACC) fy; az += (ACC) fz;
@@ -381,12 +407,13 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 	  tot_terms += (unsigned long long) nterms;
 	}
     }
-  // statistics: interactions (= sum of GravCost) and warp-level cell visits
+  // statistics: interactions (= sum of GravCost), cell visits (per cursor), species terms
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1)
     {
       tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
       tot_terms += __shfl_xor_sync(0xffffffffu, tot_terms, o);
+      tot_visits += __shfl_xor_sync(0xffffffffu, tot_visits, o);
     }
   if(lane == 0)
     {
@@ -413,28 +440,33 @@ __global__ void __launch_bounds__(256) target_compact_kernel(const unsigned char
     targets[scan[p]] = (unsigned int) p;
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
-static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, int acc_double)
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, int G>
+static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
 {
-  if(acc_double)
-    {
-      if(smem > 48 * 1024)
-	G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, double><<<grid, WALK_THREADS, smem, c->stream>>>(A);
-    }
-  else
-    {
-      if(smem > 48 * 1024)
-	G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, float><<<grid, WALK_THREADS, smem, c->stream>>>(A);
-    }
+  if(smem > 48 * 1024)
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, G><<<grid, WALK_THREADS, smem, c->stream>>>(A);
   return 0;
 }
 
-template <int D>
-static int dispatch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd)
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
+static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, int acc_double, int group)
 {
-#define G2_W(SRv, PERv, UNEv, STv) return launch_walk<D, SRv, PERv, UNEv, STv>(c, A, grid, smem, accd)
+  if(!acc_double)
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, 32>(c, A, grid, smem);
+  switch (group)
+    {
+#ifdef G2_WALK_SUBGROUPS
+    case 8: return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, 8>(c, A, grid, smem);
+#endif
+    default: return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, 32>(c, A, grid, smem);
+    }
+}
+
+template <int D>
+static int dispatch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int group)
+{
+#define G2_W(SRv, PERv, UNEv, STv) return launch_walk<D, SRv, PERv, UNEv, STv>(c, A, grid, smem, accd, group)
   if(sr)
     {				// TreePM implies PERIODIC and equal softenings are not required; keep both UNEQUAL variants
       if(unequal) { if(stock) G2_W(true, true, true, true); else G2_W(true, true, true, false); }
@@ -524,12 +556,18 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       int rc;
       switch (D)
 	{
-	case 1: rc = dispatch_walk<1>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
-	case 2: rc = dispatch_walk<2>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
-	case 3: rc = dispatch_walk<3>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
-	case 4: rc = dispatch_walk<4>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
-	case 5: rc = dispatch_walk<5>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
-	case 6: rc = dispatch_walk<6>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double); break;
+#ifndef G2_FAST_BUILD
+	case 1: rc = dispatch_walk<1>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+#endif
+	case 2: rc = dispatch_walk<2>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+#ifndef G2_FAST_BUILD
+	case 3: rc = dispatch_walk<3>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+#endif
+	case 4: rc = dispatch_walk<4>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+#ifndef G2_FAST_BUILD
+	case 5: rc = dispatch_walk<5>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+	case 6: rc = dispatch_walk<6>(c, A, grid, smem, sr, per, uneq, stock, c->acc_double, c->walk_group); break;
+#endif
 	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
 	}
       if(rc)

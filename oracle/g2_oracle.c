@@ -1136,3 +1136,161 @@ void g2o_timings(g2o * o, double *out)
   out[1] = o->t_build;
   out[2] = o->t_walk;
 }
+
+/* ---- design aid (not a reference restatement): statistics of a GROUP walk, in which `gsize` consecutive targets (in
+ *      depth-first tree order) share one cursor and a node is descended into if ANY member opens it -- the traversal the
+ *      GPU walk kernel performs with gsize = 32.  Returns per group: node visits and the sum over visits of members that
+ *      were awake (not skipping an accepted/culled ancestor).  Decisions are those of tree_evaluate(). ---- */
+static int node_decision(g2o * o, const particle * tp, const node * nop)	/* 0 cull, 1 accept, 2 open */
+{
+  const int D = o->D, SR = o->shortrange, PER = o->periodic;
+  const double boxsize = o->boxsize, boxhalf = 0.5 * o->boxsize;
+  double r2min = INFINITY, r2max = -INFINITY, summass = 0, h;
+  const double pp[3] = { tp->pos[0], tp->pos[1], tp->pos[2] };
+  const double aold = o->errtol * tp->oldacc;
+  int g, k;
+  for(g = 0; g < D; g++)
+    {
+      double d[3], r2 = 0;
+      for(k = 0; k < 3; k++)
+	{
+	  d[k] = nop->s[k][g] - pp[k];
+	  if(PER)
+	    d[k] = NEAREST(d[k]);
+	  r2 += d[k] * d[k];
+	}
+      summass += nop->mass[g];
+      if(r2 < r2min) r2min = r2;
+      if(r2 > r2max) r2max = r2;
+    }
+  if(SR && r2min > o->rcut * o->rcut)
+    {
+      double eff = o->rcut + 0.5 * nop->len;
+      for(k = 0; k < 3; k++)
+	{
+	  double dist = nop->center[k] - pp[k];
+	  if(PER)
+	    dist = NEAREST(dist);
+	  if(dist < -eff || dist > eff)
+	    return 0;
+	}
+    }
+  if(o->theta)
+    {
+      if(nop->len * nop->len > r2min * o->theta * o->theta)
+	return 2;
+    }
+  else
+    {
+      if(summass * nop->len * nop->len > r2min * r2min * aold)
+	return 2;
+      if(fabs(nop->center[0] - pp[0]) < 0.60 * nop->len && fabs(nop->center[1] - pp[1]) < 0.60 * nop->len && fabs(nop->center[2] - pp[2]) < 0.60 * nop->len)
+	return 2;
+    }
+  if(o->unequal)
+    {
+      int mt = (nop->bitflags >> 2) & 7;
+      h = o->fsoft[tp->type];
+      if(mt == 7)
+	return 2;
+      if(h < o->fsoft[mt])
+	{
+	  h = o->fsoft[mt];
+	  if(r2max < h * h && ((nop->bitflags >> 5) & 1))
+	    return 2;
+	}
+    }
+  return 1;
+}
+
+/* order[] = targets in depth-first tree order (filled by following nextnode from the root) */
+void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
+{
+  const int MP = o->maxpart, n = o->n;
+  int *order = malloc(sizeof(int) * n), *skip = malloc(sizeof(int) * gsize);
+  int no = MP, cnt = 0, gi, ngroups = 0;
+  double visits = 0, awake = 0, accepts = 0, pvis = 0, pawake = 0;
+  /* DFS order of particles: open everything */
+  while(no >= 0)
+    {
+      if(no < MP)
+	{
+	  order[cnt++] = no;
+	  no = o->nextnode[no];
+	}
+      else
+	no = NODE_OF(o, no)->nextnode;
+    }
+  /* pre-order rank of every node/particle to implement "sleep until the cursor leaves the subtree" */
+  {
+    int stride = n / (gsize * ngroups_max);
+    if(stride < 1)
+      stride = 1;
+    for(gi = 0; gi + gsize <= n && ngroups < ngroups_max; gi += gsize * stride, ngroups++)
+      {
+	int m, cur = MP;
+	/* skip[m] = node index at which member m wakes up again (-2 = awake) */
+	for(m = 0; m < gsize; m++)
+	  skip[m] = -2;
+	while(cur >= 0)
+	  {
+	    if(cur < MP)
+	      {			/* a particle: members that are awake interact */
+		int na = 0;
+		for(m = 0; m < gsize; m++)
+		  {
+		    if(skip[m] == cur)
+		      skip[m] = -2;
+		    if(skip[m] == -2)
+		      na++;
+		  }
+		pvis += 1;
+		pawake += na;
+		cur = o->nextnode[cur];
+		continue;
+	      }
+	    {
+	      node *nop = NODE_OF(o, cur);
+	      int anyopen = 0, na = 0;
+	      for(m = 0; m < gsize; m++)
+		{
+		  if(skip[m] == cur)
+		    skip[m] = -2;
+		  if(skip[m] == -2)
+		    {
+		      int dec = node_decision(o, &o->P[order[gi + m]], nop);
+		      na++;
+		      if(dec == 2)
+			anyopen = 1;
+		      else
+			{
+			  skip[m] = nop->sibling;	/* wake up at the sibling (-1: never) */
+			  if(dec == 1)
+			    accepts += 1;
+			}
+		    }
+		}
+	      visits += 1;
+	      awake += na;
+	      if(anyopen)
+		cur = nop->nextnode;
+	      else
+		cur = nop->sibling;
+	      /* members sleeping until a node that is skipped over by a sibling jump wake at that jump target:
+	         their wake node is an ancestor's sibling, which the cursor reaches later or equals cur */
+	      for(m = 0; m < gsize; m++)
+		if(skip[m] == -1 && cur == -1)
+		  skip[m] = -2;
+	    }
+	  }
+      }
+  }
+  out[0] = ngroups;
+  out[1] = visits / ngroups;
+  out[2] = awake / ngroups;
+  out[3] = accepts / ngroups;
+  out[4] = pvis / ngroups;
+  out[5] = pawake / ngroups;
+  free(skip);
+  free(order);
+}
