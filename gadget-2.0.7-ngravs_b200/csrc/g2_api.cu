@@ -78,10 +78,10 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   const size_t cap = (np > nn ? np : nn) + G2_MAXTOP + 8;
   const int R = 2 + c->D;
   int rc = 0;
-  rc |= dalloc(&c->in_pm, np); rc |= dalloc(&c->in_type, np); rc |= dalloc(&c->in_oldacc, np); rc |= dalloc(&c->in_active, np);
-  rc |= dalloc(&c->in_raw, 4 * np);
-  c->own_in_pm = c->in_pm; c->own_in_type = c->in_type; c->own_in_oldacc = c->in_oldacc; c->own_in_active = c->in_active;
-  rc |= dalloc(&c->pm, np); rc |= dalloc(&c->ptype, np); rc |= dalloc(&c->oldacc, np); rc |= dalloc(&c->active, np);
+  rc |= dalloc(&c->in_rec, np);
+  rc |= dalloc(&c->in_raw, 7 * np);
+  c->own_in_rec = c->in_rec;
+  rc |= dalloc(&c->prec, np);
   rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np);
   rc |= dalloc(&c->skey[0], np); rc |= dalloc(&c->skey[1], np); rc |= dalloc(&c->sval[0], np); rc |= dalloc(&c->sval[1], np);
   c->tilehist_elems = (size_t) ((np + 4095) / 4096) * 512 + 8;
@@ -101,6 +101,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->wcells, (nn + G2_MAXTOP) * R); rc |= dalloc(&c->wpart, np);
   rc |= dalloc(&c->hist2, np + 2); rc |= dalloc(&c->hist2_scan, np + 2); rc |= dalloc(&c->dmin, np + 2);
   rc |= dalloc(&c->d_err, (size_t) 8);
+  rc |= dalloc(&c->d_depth, (size_t) 64);
   rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
   rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
   rc |= dalloc(&c->d_counters, (size_t) 8);
@@ -109,7 +110,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
       g2gpu_destroy(c);
       return G2GPU_ERR_NOMEM;
     }
-  if(cudaMallocHost((void **) &c->h_err, 16 * sizeof(int)) != cudaSuccess || cudaMallocHost((void **) &c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess
+  if(cudaMallocHost((void **) &c->h_err, 64 * sizeof(int)) != cudaSuccess || cudaMallocHost((void **) &c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess
      || cudaMallocHost((void **) &c->h_top, sizeof(G2TopTree)) != cudaSuccess)
     {
       g2gpu_destroy(c);
@@ -129,11 +130,11 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
   cudaSetDevice(c->cfg.device);
   if(c->stream)
     cudaStreamSynchronize(c->stream);
-  void *ptrs[] = { c->own_in_pm, c->own_in_type, c->own_in_oldacc, c->own_in_active, c->in_raw, c->in_vel, c->in_gravpm, c->pm, c->ptype, c->oldacc, c->active, c->vel, c->gravpm,
+  void *ptrs[] = { c->own_in_rec, c->in_raw, c->in_vel, c->in_gravpm, c->prec, c->vel, c->gravpm,
     c->phkey, c->perm, c->skey[0], c->skey[1], c->sval[0], c->sval[1], c->tilehist, c->scan_tmp, c->d_domain, c->d_minmax, c->d_top, c->d_topscratch,
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
-    c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
+    c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
     c->d_srtable, c->d_srtable_f };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
@@ -266,15 +267,23 @@ static int ensure_opt(g2gpu_ctx *c, int want_vel, int want_gravpm)
   return 0;
 }
 
-// SoA arrays go to the device as they are (no host-side repacking); pack_inputs_kernel builds the float4 records.
-__global__ void __launch_bounds__(256) pack_inputs_kernel(int n, const float *__restrict__ pos3, const float *__restrict__ mass,
-							   const int *__restrict__ active_i, float4 *__restrict__ pm, unsigned char *__restrict__ active)
+// SoA arrays go to the device as they are (no host-side repacking); pack_inputs_kernel builds the 32-byte records.
+__global__ void __launch_bounds__(256) pack_inputs_kernel(int n, const float *__restrict__ pos3, const float *__restrict__ mass, const int *__restrict__ type,
+							   const float *__restrict__ oldacc, const int *__restrict__ active_i, G2PRec *__restrict__ rec)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n)
     return;
-  pm[i] = make_float4(pos3[3 * (size_t) i], pos3[3 * (size_t) i + 1], pos3[3 * (size_t) i + 2], mass[i]);
-  active[i] = active_i ? (active_i[i] != 0) : 1;
+  G2PRec r;
+  r.x = pos3[3 * (size_t) i];
+  r.y = pos3[3 * (size_t) i + 1];
+  r.z = pos3[3 * (size_t) i + 2];
+  r.m = mass[i];
+  r.type = type[i];
+  r.oldacc = oldacc ? oldacc[i] : 0.0f;
+  r.active = active_i ? (active_i[i] != 0) : 1;
+  r.pad = 0;
+  rec[i] = r;
 }
 
 extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
@@ -286,30 +295,25 @@ extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const flo
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
   G2_CUDA(cudaSetDevice(c->cfg.device));
   G2_TRY(ensure_opt(c, vel != nullptr, gravpm != nullptr));
-  if(c->inputs_bound)
-    {				// back to the library's own input buffers
-      c->in_pm = c->own_in_pm; c->in_type = c->own_in_type; c->in_oldacc = c->own_in_oldacc; c->in_active = c->own_in_active;
-      c->inputs_bound = 0;
-    }
+  c->in_rec = c->own_in_rec;	// back to the library's own input buffer
+  c->inputs_bound = 0;
   const size_t n = (size_t) npart;
   cudaStream_t st = c->stream;
-  float *d_pos3 = c->in_raw, *d_mass = c->in_raw + 3 * n;
-  int *d_act = (int *) c->w_flags;
+  float *d_pos3 = c->in_raw, *d_mass = c->in_raw + 3 * n, *d_old = c->in_raw + 5 * n;
+  int *d_type = (int *) (c->in_raw + 4 * n), *d_act = (int *) (c->in_raw + 6 * n);
   G2_CUDA(cudaEventRecord(c->ev[9], st));
   G2_CUDA(cudaMemcpyAsync(d_pos3, pos, n * 12, cudaMemcpyHostToDevice, st));
   G2_CUDA(cudaMemcpyAsync(d_mass, mass, n * 4, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(c->in_type, type, n * 4, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaMemcpyAsync(d_type, type, n * 4, cudaMemcpyHostToDevice, st));
   if(oldacc)
-    G2_CUDA(cudaMemcpyAsync(c->in_oldacc, oldacc, n * 4, cudaMemcpyHostToDevice, st));
-  else
-    G2_CUDA(cudaMemsetAsync(c->in_oldacc, 0, n * 4, st));
+    G2_CUDA(cudaMemcpyAsync(d_old, oldacc, n * 4, cudaMemcpyHostToDevice, st));
   if(active)
     G2_CUDA(cudaMemcpyAsync(d_act, active, n * 4, cudaMemcpyHostToDevice, st));
   if(vel)
     G2_CUDA(cudaMemcpyAsync(c->in_vel, vel, n * 12, cudaMemcpyHostToDevice, st));
   if(gravpm)
     G2_CUDA(cudaMemcpyAsync(c->in_gravpm, gravpm, n * 12, cudaMemcpyHostToDevice, st));
-  pack_inputs_kernel<<<g2_cdiv(npart, 256), 256, 0, st>>>(npart, d_pos3, d_mass, active ? d_act : nullptr, c->in_pm, c->in_active);
+  pack_inputs_kernel<<<g2_cdiv(npart, 256), 256, 0, st>>>(npart, d_pos3, d_mass, d_type, oldacc ? d_old : nullptr, active ? d_act : nullptr, c->in_rec);
   c->launches++;
   G2_CUDA(cudaEventRecord(c->ev[10], st));
   G2_CUDA(cudaGetLastError());
@@ -360,29 +364,25 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
   return rc;
 }
 
-extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **ptrs)
+extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **records)
 {
-  if(!c || !ptrs)
+  if(!c || !records)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(npart < 1 || npart > c->cfg.max_part)
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
-  ptrs[0] = c->own_in_pm;
-  ptrs[1] = c->own_in_type;
-  ptrs[2] = c->own_in_oldacc;
-  ptrs[3] = c->own_in_active;
+  *records = c->own_in_rec;
   return 0;
 }
 
-extern "C" int g2gpu_bind_inputs(g2gpu_ctx *c, int npart, void *posmass, void *type, void *oldacc, void *active)
+extern "C" int g2gpu_bind_inputs(g2gpu_ctx *c, int npart, void *records)
 {
-  if(!c || !posmass || !type || !oldacc || !active)
+  if(!c || !records)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(npart < 1 || npart > c->cfg.max_part)
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
-  c->in_pm = (float4 *) posmass;
-  c->in_type = (int *) type;
-  c->in_oldacc = (float *) oldacc;
-  c->in_active = (unsigned char *) active;
+  if(((size_t) records & 15) != 0)
+    return g2_fail(G2GPU_ERR_ARG, "particle records must be 16-byte aligned");
+  c->in_rec = (G2PRec *) records;
   c->inputs_bound = 1;
   c->have_vel = 0;
   c->have_gravpm = 0;
@@ -397,7 +397,7 @@ extern "C" int g2gpu_inputs_ready(g2gpu_ctx *c, int npart)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(npart < 1 || npart > c->cfg.max_part)
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
-  c->in_pm = c->own_in_pm; c->in_type = c->own_in_type; c->in_oldacc = c->own_in_oldacc; c->in_active = c->own_in_active;
+  c->in_rec = c->own_in_rec;
   c->inputs_bound = 0;
   c->have_vel = 0;
   c->have_gravpm = 0;

@@ -55,7 +55,7 @@ __device__ __forceinline__ void descend(float &cx, float &cy, float &cz, float &
 }
 
 // ---------------------------------------------------------------- 1. tree keys -------------------------------
-__global__ void __launch_bounds__(256) treekey_kernel(const float4 *__restrict__ pm, const long long *__restrict__ phkey, int n,
+__global__ void __launch_bounds__(256) treekey_kernel(const G2PRec *__restrict__ prec, const long long *__restrict__ phkey, int n,
 						      const G2TopTree *__restrict__ tt, unsigned long long *__restrict__ tkey,
 						      unsigned int *__restrict__ tval, unsigned short *__restrict__ ptl)
 {
@@ -67,13 +67,30 @@ __global__ void __launch_bounds__(256) treekey_kernel(const float4 *__restrict__
   float cx = tt->fcx[k], cy = tt->fcy[k], cz = tt->fcz[k], len = tt->flen[k];
   int t = tt->fdepth[k];
   unsigned long long path = tt->fmorton[k];
-  float4 p = pm[i];
-  for(int lvl = t + 1; lvl <= G2_MAXDEPTH; lvl++)
-    {
-      unsigned int sub = (p.x > cx ? 1u : 0u) | (p.y > cy ? 2u : 0u) | (p.z > cz ? 4u : 0u);
-      path = (path << 3) | sub;
-      descend(cx, cy, cz, len, sub);
-    }
+  const float4 p = *((const float4 *) &prec[i]);
+  // `(FLOAT) (center +- 0.25*len)` of forcetree.c:190-206 is a double sum rounded to float.  When the exponents of the
+  // centre and of len/4 at the deepest level differ by less than 29 bits the double sum is exact, so a plain float
+  // addition (one rounding of the same exact value) gives the identical result without FP64 conversions.
+  const float cmax = fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fabsf(cz)) + len;
+  const bool float_exact = cmax < len * (float) (1 << (t + 5 > 30 ? 30 : t + 5));	// |c| / (len_leaf / 2^(23-t)) < 2^28
+  if(float_exact)
+    for(int lvl = t + 1; lvl <= G2_MAXDEPTH; lvl++)
+      {
+	unsigned int sub = (p.x > cx ? 1u : 0u) | (p.y > cy ? 2u : 0u) | (p.z > cz ? 4u : 0u);
+	path = (path << 3) | sub;
+	const float q = 0.25f * len;
+	cx = __fadd_rn(cx, (sub & 1) ? q : -q);
+	cy = __fadd_rn(cy, (sub & 2) ? q : -q);
+	cz = __fadd_rn(cz, (sub & 4) ? q : -q);
+	len = 0.5f * len;
+      }
+  else
+    for(int lvl = t + 1; lvl <= G2_MAXDEPTH; lvl++)
+      {
+	unsigned int sub = (p.x > cx ? 1u : 0u) | (p.y > cy ? 2u : 0u) | (p.z > cz ? 4u : 0u);
+	path = (path << 3) | sub;
+	descend(cx, cy, cz, len, sub);
+      }
   tkey[i] = path;
   tval[i] = (unsigned int) i;
   ptl[i] = (unsigned short) k;
@@ -143,25 +160,59 @@ __global__ void __launch_bounds__(256) cell_count_kernel(const unsigned char *__
 __global__ void __launch_bounds__(256) cell_init_kernel(const unsigned char *__restrict__ tm, const unsigned short *__restrict__ tl,
 							const G2TopTree *__restrict__ tt, const unsigned int *__restrict__ tbase, int n,
 							int max_cells, unsigned int *__restrict__ c_a, unsigned char *__restrict__ c_d,
-							int *__restrict__ err)
+							int *__restrict__ err, unsigned int *__restrict__ depth_count)
 {
+  __shared__ unsigned int s_hist[32];
+  if(threadIdx.x < 32)
+    s_hist[threadIdx.x] = 0;
+  __syncthreads();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if(p >= n)
-    return;
-  unsigned int b0 = tbase[p], b1 = tbase[p + 1];
-  if(b1 == b0)
-    return;
-  if(b1 > (unsigned int) max_cells)
+  if(p < n)
     {
-      atomicExch(&err[1], G2GPU_ERR_MAXNODES);
-      return;
+      unsigned int b0 = tbase[p], b1 = tbase[p + 1];
+      if(b1 > b0)
+	{
+	  if(b1 > (unsigned int) max_cells)
+	    atomicExch(&err[1], G2GPU_ERR_MAXNODES);
+	  else
+	    {
+	      int fd = first_depth(tm, tl, tt, p);
+	      for(unsigned int c = b0; c < b1; c++)
+		{
+		  int d = fd + (int) (c - b0);
+		  c_a[c] = (unsigned int) p;
+		  c_d[c] = (unsigned char) d;
+		  atomicAdd(&s_hist[d & 31], 1u);
+		}
+	    }
+	}
     }
-  int fd = first_depth(tm, tl, tt, p);
-  for(unsigned int c = b0; c < b1; c++)
-    {
-      c_a[c] = (unsigned int) p;
-      c_d[c] = (unsigned char) (fd + (int) (c - b0));
-    }
+  __syncthreads();
+  if(threadIdx.x < 32 && s_hist[threadIdx.x])
+    atomicAdd(&depth_count[threadIdx.x], s_hist[threadIdx.x]);	// cells per depth: the moment pass runs level by level
+}
+
+struct DepthStarts { unsigned int start[32]; };
+
+// cell ids grouped by depth (order inside a depth is irrelevant): block-aggregated slot allocation
+__global__ void __launch_bounds__(256) depth_scatter_kernel(const unsigned char *__restrict__ c_d, int ncells, DepthStarts ds, unsigned int *__restrict__ cursor,
+							    unsigned int *__restrict__ depth_list)
+{
+  __shared__ unsigned int s_cnt[32], s_base[32];
+  if(threadIdx.x < 32)
+    s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int d = c < ncells ? (int) c_d[c] & 31 : -1;
+  unsigned int rank = 0;
+  if(d >= 0)
+    rank = atomicAdd(&s_cnt[d], 1u);
+  __syncthreads();
+  if(threadIdx.x < 32 && s_cnt[threadIdx.x])
+    s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  if(d >= 0)
+    depth_list[ds.start[d] + s_base[d] + rank] = (unsigned int) c;
 }
 
 // last position in [pos, hi] sharing the first `depth` digits with position pos (keys sorted ascending)
@@ -471,8 +522,7 @@ struct BuildArrays
   const unsigned int *tq;
   const unsigned short *tl;
   const unsigned int *tbase;
-  const float4 *pm;
-  const unsigned char *ptype;
+  const G2PRec *prec;
   const unsigned int *c_a, *c_b;
   const unsigned char *c_d;
   const int *c_suns, *c_father;
@@ -516,8 +566,8 @@ __device__ int process_cell(const BuildArrays &A, const G2TopTree *__restrict__ 
       if(v >= 0)
 	{
 	  unsigned int idx = A.tq[v];
-	  float4 p = A.pm[idx];
-	  int type = A.ptype[idx];
+	  const float4 p = *((const float4 *) &A.prec[idx]);
+	  const int type = A.prec[idx].type;
 	  mom_add_particle<D>(M, p, type, idx, S);
 	  A.wpart[poff + np] = p;
 	  pinfo |= (unsigned int) type << (4 + 3 * np);
@@ -557,8 +607,8 @@ __device__ int process_top(const BuildArrays &A, const G2TopTree *__restrict__ t
 	  if(v >= 0)
 	    {
 	      unsigned int idx = A.tq[v];
-	      float4 p = A.pm[idx];
-	      int type = A.ptype[idx];
+	      const float4 p = *((const float4 *) &A.prec[idx]);
+	      const int type = A.prec[idx].type;
 	      mom_add_particle<D>(M, p, type, idx, S);
 	      A.wpart[poff + np] = p;
 	      pinfo |= (unsigned int) type << (4 + 3 * np);
@@ -597,53 +647,20 @@ __device__ int process_top(const BuildArrays &A, const G2TopTree *__restrict__ t
   return tt->ffather[k] >= 0 ? -(tt->ffather[k] + 2) : -1;
 }
 
-// One thread per node; only nodes without child cells start, the last child to arrive continues with the father
-// (every cell is processed exactly once, after all its children).
+// Moment pass, one launch per depth (deepest first): every cell / top-level node of that depth is processed by one
+// thread; its children were completed by the previous launches, so no flags, fences or atomics are needed.
 template <int D>
-__global__ void __launch_bounds__(128) bottomup_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, G2Soft S)
+__global__ void __launch_bounds__(128) level_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, G2Soft S, int depth, unsigned int lstart, int lcount,
+						    const unsigned int *__restrict__ depth_list)
 {
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ncells = (int) A.tbase[A.n];
-  const int ntop = tt->ntopnodes;
-  int code;			// >= 0 regular cell, <= -2 top node
-  if(tid < ncells)
-    {
-      if(A.c_nchild[tid] != 0)
-	return;
-      code = tid;
-    }
-  else if(tid < ncells + ntop)
-    {
-      int k = tid - ncells;
-      if(!(tt->fisleaf[k] && A.t_nchild[k] == 0))
-	return;
-      code = -(k + 2);
-    }
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < lcount)
+    process_cell<D>(A, tt, S, (int) depth_list[lstart + i]);
   else
-    return;
-
-  while(true)
     {
-      int father = code >= 0 ? process_cell<D>(A, tt, S, code) : process_top<D>(A, tt, S, -(code + 2));
-      if(father == -1)
-	break;			// root done
-      __threadfence();
-      unsigned int need, old;
-      if(father >= 0)
-	{
-	  need = A.c_nchild[father];
-	  old = atomicAdd(&A.c_ready[father], 1u);
-	}
-      else
-	{
-	  int fk = -(father + 2);
-	  need = tt->fisleaf[fk] ? (unsigned int) A.t_nchild[fk] : 8u;
-	  old = atomicAdd(&A.t_ready[fk], 1u);
-	}
-      if(old + 1u < need)
-	break;
-      __threadfence();
-      code = father;
+      int k = i - lcount;
+      if(k < tt->ntopnodes && tt->fdepth[k] == depth)
+	process_top<D>(A, tt, S, k);
     }
 }
 
@@ -873,7 +890,7 @@ static G2Soft make_soft(const g2gpu_ctx *c)
 static BuildArrays make_arrays(g2gpu_ctx *c)
 {
   BuildArrays A;
-  A.tkey = c->tkey; A.tq = c->tq; A.tl = c->ttl; A.tbase = c->tbase; A.pm = c->pm; A.ptype = c->ptype;
+  A.tkey = c->tkey; A.tq = c->tq; A.tl = c->ttl; A.tbase = c->tbase; A.prec = c->prec;
   A.c_a = c->c_a; A.c_b = c->c_b; A.c_d = c->c_d; A.c_suns = c->c_suns; A.c_father = c->c_father;
   A.c_nchild = c->c_nchild; A.c_ready = c->c_ready; A.c_min1 = c->c_min1; A.c_min2 = c->c_min2;
   A.t_suns = c->t_suns; A.t_first = c->t_first; A.t_last = c->t_last; A.t_u = c->t_ubase; A.t_nchild = c->t_nchild;
@@ -893,7 +910,7 @@ int g2_stage_treebuild(g2gpu_ctx *c)
 
   // 1. keys + sort (keys live in the sort ping-pong buffers)
   unsigned short *ptl = (unsigned short *) c->w_flags;	// per-particle top node, scratch reuse (n * 2 bytes)
-  treekey_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->pm, c->phkey, n, c->d_top, c->skey[0], c->sval[0], ptl);
+  treekey_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->prec, c->phkey, n, c->d_top, c->skey[0], c->sval[0], ptl);
   c->launches++;
   unsigned long long *k = c->skey[0];
   unsigned int *v = c->sval[0];
@@ -906,13 +923,15 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   cell_count_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tm, c->ttl, c->d_top, n, c->tcnt);
   c->launches += 2;
   G2_TRY(g2_scan_exclusive_u32(c, c->tcnt, c->tbase, (size_t) n));
-  cell_init_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tm, c->ttl, c->d_top, c->tbase, n, maxcells, c->c_a, c->c_d, c->d_err);
+  G2_CUDA(cudaMemsetAsync(c->d_depth, 0, 64 * sizeof(unsigned int), st));
+  cell_init_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tm, c->ttl, c->d_top, c->tbase, n, maxcells, c->c_a, c->c_d, c->d_err, c->d_depth);
   c->launches++;
 
   // the cell count is needed on the host for grid sizes and the MaxNodes check (forcetree.c:249-255)
   G2_CUDA(cudaMemcpyAsync(&c->h_err[4], c->tbase + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-  G2_CUDA(cudaMemcpyAsync(&c->h_err[5], &c->d_top->ntopnodes, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[5], &c->d_top->ntopnodes, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaMemcpyAsync(&c->h_err[0], c->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  G2_CUDA(cudaMemcpyAsync(&c->h_err[16], c->d_depth, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaStreamSynchronize(st));
   if(c->h_err[2])
     return g2_fail(G2GPU_ERR_ARG, "a particle has a type outside 0..5");
@@ -929,8 +948,25 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   const int numnodes = c->numnodes;
 
   // 4. children, particle groups
-  G2_CUDA(cudaMemsetAsync(c->c_ready, 0, sizeof(unsigned int) * (size_t) (ncells + 1), st));
-  G2_CUDA(cudaMemsetAsync(c->t_ready, 0, sizeof(unsigned int) * G2_MAXTOP, st));
+  DepthStarts ds;
+  int maxdepth = 0;
+  {
+    unsigned int run = 0;
+    for(int d = 0; d < 32; d++)
+      {
+	ds.start[d] = run;
+	run += (unsigned int) c->h_err[16 + d];
+	if(c->h_err[16 + d])
+	  maxdepth = d;
+      }
+    if(c->h_err[8] > maxdepth)
+      maxdepth = c->h_err[8];	// deepest top-level node
+  }
+  if(ncells > 0)
+    {
+      depth_scatter_kernel<<<g2_cdiv(ncells, 256), 256, 0, st>>>(c->c_d, ncells, ds, c->d_depth + 32, c->c_ready);
+      c->launches++;
+    }
   if(ncells > 0)
     topdown_kernel<<<g2_cdiv(ncells, 128), 128, 0, st>>>(c->tkey, c->tm, c->ttl, c->d_top, c->tbase, n, maxcells, c->c_a, c->c_d, c->c_b,
 							  c->c_suns, c->c_father, c->p_parent, c->c_nchild, c->c_npart, c->tcnt);
@@ -942,19 +978,24 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   // 5. moments
   BuildArrays A = make_arrays(c);
   G2Soft S = make_soft(c);
-  const int nthreads = ncells + ntop;
-  const int grid = g2_cdiv(nthreads, 128);
-  switch (c->D)
+  for(int d = maxdepth; d >= 0; d--)
     {
-    case 1: bottomup_kernel<1><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    case 2: bottomup_kernel<2><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    case 3: bottomup_kernel<3><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    case 4: bottomup_kernel<4><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    case 5: bottomup_kernel<5><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    case 6: bottomup_kernel<6><<<grid, 128, 0, st>>>(A, c->d_top, S); break;
-    default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", c->D);
+      const int lcount = c->h_err[16 + d];
+      const int nthreads = lcount + ntop;
+      const int grid = g2_cdiv(nthreads, 128);
+      const unsigned int *dl = c->c_ready;	// depth-grouped cell list
+      switch (c->D)
+	{
+	case 1: level_kernel<1><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	case 2: level_kernel<2><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	case 3: level_kernel<3><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	case 4: level_kernel<4><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	case 5: level_kernel<5><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	case 6: level_kernel<6><<<grid, 128, 0, st>>>(A, c->d_top, S, d, ds.start[d], lcount, dl); break;
+	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", c->D);
+	}
+      c->launches++;
     }
-  c->launches++;
   G2_CUDA(cudaEventRecord(c->ev[5], st));
   G2_CUDA(cudaGetLastError());
   c->renumbered = 0;

@@ -30,6 +30,17 @@ int g2_fail(int code, const char *fmt, ...);
 
 static inline int g2_cdiv(long long a, long long b) { return (int) ((a + b - 1) / b); }
 
+// 32-byte particle record (= g2gpu_particle of include/g2gpu.h): one random access fetches everything the tree code
+// needs about a particle
+struct __align__(16) G2PRec
+{
+  float x, y, z, m;
+  int type;
+  float oldacc;
+  int active;
+  int pad;
+};
+
 // ---- device copy of the top-level tree (domain.c TopNodes + forcetree.c top-level nodes) ----
 struct G2TopTree
 {
@@ -90,28 +101,19 @@ struct g2gpu_ctx
   int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
 
   // upload-order inputs
-  float4 *in_pm;
-  int *in_type;
-  float *in_oldacc;
+  G2PRec *in_rec;		// may point at caller-bound device memory (g2gpu_bind_inputs)
+  G2PRec *own_in_rec;		// the library's own input buffer
   float *in_vel;		// 3n, optional
   float *in_gravpm;		// 3n, optional
-  unsigned char *in_active;
-  float *in_raw;		// H2D landing zone: pos[3n] | mass[n]
-  float4 *own_in_pm;		// the library's own input buffers (in_* may point at caller-bound device memory)
-  int *own_in_type;
-  float *own_in_oldacc;
-  unsigned char *own_in_active;
+  float *in_raw;		// H2D landing zone: pos[3n] | mass[n] | type[n] | oldacc[n] | active[n]
   int inputs_bound;
   size_t h2d_bytes, d2h_bytes;
   int have_vel, have_gravpm;
 
   // current-order (species-major PH) particle arrays
-  float4 *pm;
-  unsigned char *ptype;
-  float *oldacc;
+  G2PRec *prec;
   float *vel;
   float *gravpm;
-  unsigned char *active;
   long long *phkey;
   int *perm;
 
@@ -165,6 +167,7 @@ struct g2gpu_ctx
   unsigned int *hist2, *hist2_scan;	// reference renumbering scratch (size n+1)
   unsigned int *dmin;
   int renumbered;
+  unsigned int *d_depth;	// [0..31] cells per depth, [32..63] scatter cursors
   int *d_err;			// device error flags (4 ints)
   int *h_err;			// pinned
 

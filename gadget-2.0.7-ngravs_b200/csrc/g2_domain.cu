@@ -29,12 +29,12 @@ __global__ void extent_init_kernel(unsigned int *mm)
     mm[threadIdx.x] = 0u;		// max
 }
 
-__global__ void __launch_bounds__(256) extent_kernel(const float4 *__restrict__ pm, int n, unsigned int *mm)
+__global__ void __launch_bounds__(256) extent_kernel(const G2PRec *__restrict__ rec, int n, unsigned int *mm)
 {
   float mn[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, mx[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
   for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
-      float4 p = pm[i];
+      float4 p = *((const float4 *) &rec[i]);
       mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
       mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
       mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
@@ -86,38 +86,49 @@ __global__ void domain_params_kernel(const unsigned int *mm, double *dom)
 }
 
 // ---------------------------------------------------------------- keys -----------------------------------
-__device__ __forceinline__ long long ph_key(int x, int y, int z, int bits)
+// tab: the 24x8 state machine; threads of a warp index it divergently, so callers pass a SHARED-memory copy (the
+// constant cache would serialise the 32 different addresses of every level)
+__device__ __forceinline__ long long ph_key(const unsigned char *__restrict__ tab, int x, int y, int z, int bits)
 {
   unsigned int st = 0;
   long long key = 0;
   for(int l = bits - 1; l >= 0; l--)
     {
       unsigned int o = (((x >> l) & 1) << 2) | (((y >> l) & 1) << 1) | ((z >> l) & 1);
-      unsigned int e = c_ph_table[st * 8 + o];
+      unsigned int e = tab[st * 8 + o];
       key = (key << 3) | (e & 7);
       st = e >> 3;
     }
   return key;
 }
 
+__device__ __forceinline__ void ph_table_to_shared(unsigned char *s_tab)
+{
+  for(int i = threadIdx.x; i < G2_PH_NSTATES * 8; i += blockDim.x)
+    s_tab[i] = c_ph_table[i];
+  __syncthreads();
+}
+
 struct G2TypeMap { int t2g[6]; };
 
 // sort key = (block << 54) | PH key; block 0 = gas (type 0, peano.c:47-67), block 1+g = species g (peano.c:90-133)
-__global__ void __launch_bounds__(256) keys_kernel(const float4 *__restrict__ pm, const int *__restrict__ type, int n,
+__global__ void __launch_bounds__(256) keys_kernel(const G2PRec *__restrict__ rec, int n,
 						   const double *__restrict__ dom, G2TypeMap tm,
 						   unsigned long long *__restrict__ skey, unsigned int *__restrict__ sval, int *__restrict__ err)
 {
+  __shared__ unsigned char s_ph[G2_PH_NSTATES * 8];
+  ph_table_to_shared(s_ph);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n)
     return;
-  float4 p = pm[i];
+  const G2PRec p = rec[i];
   double fac = dom[7];
   // (P[i].Pos[k] - DomainCorner[k]) * DomainFac, converted to int by truncation (domain.c:940-943)
   int x = __double2int_rz(__dmul_rn(__dsub_rn((double) p.x, dom[0]), fac));
   int y = __double2int_rz(__dmul_rn(__dsub_rn((double) p.y, dom[1]), fac));
   int z = __double2int_rz(__dmul_rn(__dsub_rn((double) p.z, dom[2]), fac));
-  unsigned long long key = (unsigned long long) ph_key(x, y, z, G2_PH_BITS);
-  int t = type[i];
+  unsigned long long key = (unsigned long long) ph_key(s_ph, x, y, z, G2_PH_BITS);
+  int t = p.type;
   if(t < 0 || t > 5)
     {				// particle types are 0..5 (allvars.h:571)
       atomicExch(&err[2], G2GPU_ERR_ARG);
@@ -129,22 +140,18 @@ __global__ void __launch_bounds__(256) keys_kernel(const float4 *__restrict__ pm
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(int n, const unsigned long long *__restrict__ skey, const unsigned int *__restrict__ sval,
-						     const float4 *__restrict__ in_pm, const int *__restrict__ in_type,
-						     const float *__restrict__ in_oldacc, const unsigned char *__restrict__ in_active,
-						     const float *__restrict__ in_vel, const float *__restrict__ in_gravpm,
-						     float4 *__restrict__ pm, unsigned char *__restrict__ ptype, float *__restrict__ oldacc,
-						     unsigned char *__restrict__ active, float *__restrict__ vel, float *__restrict__ gravpm,
+						     const G2PRec *__restrict__ in_rec, const float *__restrict__ in_vel, const float *__restrict__ in_gravpm,
+						     G2PRec *__restrict__ prec, float *__restrict__ vel, float *__restrict__ gravpm,
 						     long long *__restrict__ phkey, int *__restrict__ perm)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= n)
     return;
   unsigned int src = sval[i];
-  pm[i] = in_pm[src];
-  int t = in_type[src];
-  ptype[i] = (unsigned char) (t < 0 ? 0 : (t > 5 ? 5 : t));
-  oldacc[i] = in_oldacc[src];
-  active[i] = in_active[src];
+  G2PRec r = in_rec[src];
+  r.type = r.type < 0 ? 0 : (r.type > 5 ? 5 : r.type);
+  r.active = r.active != 0;
+  prec[i] = r;
   if(in_vel)
     for(int k = 0; k < 3; k++)
       vel[3 * (size_t) i + k] = in_vel[3 * (size_t) src + k];
@@ -416,7 +423,7 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
 	  //      its own subtree; the TopNodes daughter of octant (i,j,k) is the last PH digit of the child's cell.
 	  //      The parent's geometry travels on the stack (no read-back from global memory).
 	  {
-	    int nf = 1;
+	    int nf = 1, topmaxdepth = 0;
 	    int st_k[32], st_top[32], st_state[32], st_c[32], st_depth[32];
 	    float st_len[32], st_cx[32], st_cy[32], st_cz[32];
 	    unsigned long long st_mort[32];
@@ -457,6 +464,8 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
 		const unsigned long long nm = (st_mort[f] << 3) | (unsigned long long) slot;
 		tt->flen[nn] = nlen; tt->fcx[nn] = ncx; tt->fcy[nn] = ncy; tt->fcz[nn] = ncz;
 		tt->fdepth[nn] = st_depth[f] + 1;
+		if(st_depth[f] + 1 > topmaxdepth)
+		  topmaxdepth = st_depth[f] + 1;
 		tt->fmorton[nn] = nm;
 		tt->ffather[nn] = k;
 		for(int s = 0; s < 8; s++)
@@ -471,6 +480,7 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
 		st_len[sp] = nlen; st_cx[sp] = ncx; st_cy[sp] = ncy; st_cz[sp] = ncz;
 		sp++;
 	      }
+	    tt->pad = topmaxdepth;	// depth of the deepest top-level node
 	  }
 	}
       __threadfence();
@@ -522,9 +532,11 @@ __global__ void __launch_bounds__(TT_THREADS) toptree_kernel(const long long *__
 // ---------------------------------------------------------------- stand-alone key kernel (tests) ---------------
 __global__ void peano_keys_kernel(const int *__restrict__ xyz, int n, int bits, long long *__restrict__ keys)
 {
+  __shared__ unsigned char s_ph[G2_PH_NSTATES * 8];
+  ph_table_to_shared(s_ph);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i < n)
-    keys[i] = ph_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bits);
+    keys[i] = ph_key(s_ph, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bits);
 }
 
 int g2_peano_keys_standalone(g2gpu_ctx *c, int n, const int *xyz, int bits, long long *keys)
@@ -557,12 +569,12 @@ int g2_stage_domain(g2gpu_ctx *c)
   int nb = c->nsm * 8;
   if(nb > g2_cdiv(n, 256))
     nb = g2_cdiv(n, 256);
-  extent_kernel<<<nb, 256, 0, st>>>(c->in_pm, n, (unsigned int *) c->d_minmax);
+  extent_kernel<<<nb, 256, 0, st>>>(c->in_rec, n, (unsigned int *) c->d_minmax);
   domain_params_kernel<<<1, 32, 0, st>>>((const unsigned int *) c->d_minmax, c->d_domain);
   G2TypeMap tm;
   for(int t = 0; t < 6; t++)
     tm.t2g[t] = c->type_to_grav[t];
-  keys_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->in_pm, c->in_type, n, c->d_domain, tm, c->skey[0], c->sval[0], c->d_err);
+  keys_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->in_rec, n, c->d_domain, tm, c->skey[0], c->sval[0], c->d_err);
   c->launches += 4;
 
   // blocks 0 (gas) .. D (species D-1): 54 key bits + block bits
@@ -576,9 +588,8 @@ int g2_stage_domain(g2gpu_ctx *c)
   G2_TRY(g2_radix_sort_pairs(c, n, &k, &v, c->skey[1], c->sval[1], 0, 3 * G2_PH_BITS + blockbits));
   G2_CUDA(cudaEventRecord(c->ev[2], st));
 
-  gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(n, k, v, c->in_pm, c->in_type, c->in_oldacc, c->in_active,
-						  c->have_vel ? c->in_vel : nullptr, c->have_gravpm ? c->in_gravpm : nullptr,
-						  c->pm, c->ptype, c->oldacc, c->active, c->vel, c->gravpm, c->phkey, c->perm);
+  gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(n, k, v, c->in_rec, c->have_vel ? c->in_vel : nullptr, c->have_gravpm ? c->in_gravpm : nullptr,
+						  c->prec, c->vel, c->gravpm, c->phkey, c->perm);
   block_starts_kernel<<<1, 32, 0, st>>>(k, n, nblocks, c->d_species_start);
   if(!c->d_topscratch)
     G2_CUDA(cudaMalloc(&c->d_topscratch, sizeof(G2TopScratch)));

@@ -22,9 +22,7 @@ struct WalkArgs
   const float4 *__restrict__ wpart;
   const unsigned int *__restrict__ targets;	// sorted positions of active targets
   const unsigned int *__restrict__ tq;		// particle index of a sorted position
-  const float4 *__restrict__ pm;
-  const unsigned char *__restrict__ ptype;
-  const float *__restrict__ oldacc;
+  const G2PRec *__restrict__ prec;
   const float *__restrict__ gravpm;
   const float *__restrict__ srtable;		// unique tables, NTAB floats each
   float *__restrict__ acc;
@@ -194,10 +192,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
       if(valid)
 	{
 	  idx = A.tq[A.targets[ti]];
-	  float4 p = A.pm[idx];
-	  px = p.x; py = p.y; pz = p.z; pmass = p.w;
-	  ptype = A.ptype[idx];
-	  aold = A.errtol * A.oldacc[idx];	// forcetree.c:1289
+	  const G2PRec p = A.prec[idx];
+	  px = p.x; py = p.y; pz = p.z; pmass = p.m;
+	  ptype = p.type;
+	  aold = A.errtol * p.oldacc;	// forcetree.c:1289
 	}
       const int tg = (t2g_packed >> (4 * ptype)) & 7;
       const float hself = A.fsoft[ptype];
@@ -424,19 +422,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
 }
 
 // ---------------------------------------------------------------- active target list ---------------------------
-__global__ void __launch_bounds__(256) target_flag_kernel(const unsigned int *__restrict__ tq, const unsigned char *__restrict__ active, int n,
+__global__ void __launch_bounds__(256) target_flag_kernel(const unsigned int *__restrict__ tq, const G2PRec *__restrict__ prec, int n,
 							  unsigned int *__restrict__ flags)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if(p < n)
-    flags[p] = active[tq[p]] ? 1u : 0u;
+    flags[p] = prec[tq[p]].active ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) target_compact_kernel(const unsigned char *__restrict__ active, const unsigned int *__restrict__ tq,
-							     const unsigned int *__restrict__ scan, int n, unsigned int *__restrict__ targets)
+__global__ void __launch_bounds__(256) target_compact_kernel(const unsigned int *__restrict__ scan, int n, unsigned int *__restrict__ targets)
 {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if(p < n && active[tq[p]])
+  if(p < n && scan[p + 1] != scan[p])	// exclusive scan of the 0/1 flags: a step marks an active target
     targets[scan[p]] = (unsigned int) p;
 }
 
@@ -499,10 +496,10 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   G2_CUDA(cudaEventRecord(c->ev[6], st));
 
   // active targets in tree order (gravtree.c:113: Ti_endstep == Ti_Current), split into nranks equal slices
-  target_flag_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tq, c->active, n, c->w_flags);
+  target_flag_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->tq, c->prec, n, c->w_flags);
   c->launches++;
   G2_TRY(g2_scan_exclusive_u32(c, c->w_flags, c->w_flags, (size_t) n));
-  target_compact_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->active, c->tq, c->w_flags, n, c->w_targets);
+  target_compact_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->w_flags, n, c->w_targets);
   c->launches++;
   G2_CUDA(cudaMemcpyAsync(&c->h_err[4], c->w_flags + n, sizeof(int), cudaMemcpyDeviceToHost, st));
   G2_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
@@ -514,8 +511,8 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
 
   WalkArgs A;
   memset(&A, 0, sizeof(A));
-  A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.tq = c->tq; A.pm = c->pm; A.ptype = c->ptype;
-  A.oldacc = c->oldacc; A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
+  A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.tq = c->tq; A.prec = c->prec;
+  A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
   A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
   A.lo = c->w_lo; A.hi = c->w_hi; A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;
   A.theta2 = (float) (wp->theta * wp->theta);

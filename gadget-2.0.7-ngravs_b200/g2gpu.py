@@ -230,14 +230,13 @@ class TreeGravity:
         return lo.value, hi.value
 
     def input_buffers(self, n):
-        ptrs = (C.c_void_p * 4)()
-        self._chk(self.lib.g2gpu_input_buffers(self.ctx, int(n), ptrs))
-        return [int(p) for p in ptrs]
+        ptr = C.c_void_p()
+        self._chk(self.lib.g2gpu_input_buffers(self.ctx, int(n), C.byref(ptr)))
+        return int(ptr.value)
 
-    def bind_inputs(self, n, posmass_ptr, type_ptr, oldacc_ptr, active_ptr):
-        """Use caller-owned device arrays (raw pointers, e.g. torch tensors' data_ptr()) as the particle input."""
-        self._chk(self.lib.g2gpu_bind_inputs(self.ctx, int(n), C.c_void_p(posmass_ptr), C.c_void_p(type_ptr), C.c_void_p(oldacc_ptr),
-                                             C.c_void_p(active_ptr)))
+    def bind_inputs(self, n, records_ptr):
+        """Use a caller-owned device array of n 32-byte g2gpu_particle records (raw pointer, e.g. a torch tensor's data_ptr())."""
+        self._chk(self.lib.g2gpu_bind_inputs(self.ctx, int(n), C.c_void_p(records_ptr)))
         self.n = int(n)
 
     def io_bytes(self):

@@ -17,37 +17,40 @@ def owner_slice(n, rank, nranks):
     return min(n, rank * per), min(n, (rank + 1) * per), per
 
 
+def pack_records(pos, mass, ptype, oldacc=None, active=None):
+    """(n, 8) float32 tensor of 32-byte g2gpu_particle records: x, y, z, m, type (int32 bits), OldAcc, active (int32 bits), pad."""
+    n = pos.shape[0]
+    rec = torch.zeros((n, 8), dtype=torch.float32, device=pos.device)
+    rec[:, 0:3] = pos
+    rec[:, 3] = mass
+    irec = rec.view(torch.int32)
+    irec[:, 4] = ptype.to(torch.int32)
+    if oldacc is not None:
+        rec[:, 5] = oldacc
+    irec[:, 6] = 1 if active is None else active.to(torch.int32)
+    return rec
+
+
 class ParticleExchange:
-    """Persistent buffers for the per-step all-gather of (x,y,z,m), type and OldAcc."""
+    """Persistent buffers for the per-step all-gather of the particle records (ONE collective per step)."""
 
     def __init__(self, n, device, world):
         self.n, self.world = n, world
         self.per = (n + world - 1) // world
         npad = self.per * world
-        self.g_pm = torch.zeros((npad, 4), dtype=torch.float32, device=device)
-        self.g_type = torch.zeros(npad, dtype=torch.int32, device=device)
-        self.g_old = torch.zeros(npad, dtype=torch.float32, device=device)
-        self.s_pm = torch.zeros((self.per, 4), dtype=torch.float32, device=device)
-        self.s_type = torch.zeros(self.per, dtype=torch.int32, device=device)
-        self.s_old = torch.zeros(self.per, dtype=torch.float32, device=device)
+        self.g_rec = torch.zeros((npad, 8), dtype=torch.float32, device=device)
+        self.s_rec = torch.zeros((self.per, 8), dtype=torch.float32, device=device)
 
-    def set_local(self, pm, ptype, oldacc):
-        k = pm.shape[0]
-        self.s_pm[:k].copy_(pm)
-        self.s_type[:k].copy_(ptype)
-        self.s_old[:k].copy_(oldacc)
+    def set_local(self, rec):
+        self.s_rec[: rec.shape[0]].copy_(rec)
 
     def gather(self):
-        """one collective per array; returns views of the first n gathered records"""
+        """returns a view of the first n gathered records"""
         if self.world > 1:
-            dist.all_gather_into_tensor(self.g_pm, self.s_pm)
-            dist.all_gather_into_tensor(self.g_type, self.s_type)
-            dist.all_gather_into_tensor(self.g_old, self.s_old)
+            dist.all_gather_into_tensor(self.g_rec, self.s_rec)
         else:
-            self.g_pm.copy_(self.s_pm)
-            self.g_type.copy_(self.s_type)
-            self.g_old.copy_(self.s_old)
-        return self.g_pm[: self.n], self.g_type[: self.n], self.g_old[: self.n]
+            self.g_rec.copy_(self.s_rec)
+        return self.g_rec[: self.n]
 
     def bytes_per_step(self):
-        return self.per * self.world * (16 + 4 + 4)
+        return self.per * self.world * 32

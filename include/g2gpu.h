@@ -112,15 +112,26 @@ int g2gpu_upload(g2gpu_ctx *ctx, int npart, const float *pos, const float *mass,
 int g2gpu_upload_aos(g2gpu_ctx *ctx, int npart, const void *P, size_t stride, int float_bytes, int off_pos,
 		     int off_mass, int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep,
 		     int ti_current);
-/* Multi-GPU: upload only this rank's slice [lo,hi) of the SoA input into the device input buffers and expose
- * them, so that the caller's collective (NCCL all-gather over NVLink) can fill in the other ranks' slices.
- * ptrs[0..3] = device pointers of posmass (float4 n: x,y,z,mass), type (int n), oldacc (float n), active (u8 n). */
-int g2gpu_input_buffers(g2gpu_ctx *ctx, int npart, void **ptrs);
-int g2gpu_inputs_ready(g2gpu_ctx *ctx, int npart);	/* call after the all-gather filled the library's buffers */
-/* Zero-copy variant: use caller-owned DEVICE arrays (e.g. the output of an NCCL all-gather) as the particle input:
- * posmass float4[n] (x,y,z,mass), type int[n], oldacc float[n], active unsigned char[n].  They must stay valid and
- * unchanged until g2gpu_domain() has run.  The next g2gpu_upload()/g2gpu_inputs_ready() unbinds them. */
-int g2gpu_bind_inputs(g2gpu_ctx *ctx, int npart, void *posmass, void *type, void *oldacc, void *active);
+/* The device-side particle record (32 bytes): what the library builds from the SoA/AoS uploads, and what a caller that
+ * fills device memory itself (multi-GPU all-gather) must provide. */
+typedef struct g2gpu_particle
+{
+  float pos[3];			/* P[].Pos  */
+  float mass;			/* P[].Mass */
+  int type;			/* P[].Type, 0..5 */
+  float oldacc;			/* P[].OldAcc */
+  int active;			/* != 0 <=> P[].Ti_endstep == All.Ti_Current */
+  int pad;
+} g2gpu_particle;
+
+/* Multi-GPU: *records = the library's own device input buffer (max_part records), to be filled by the caller (e.g. as the
+ * receive buffer of an NCCL all-gather); call g2gpu_inputs_ready(npart) afterwards. */
+int g2gpu_input_buffers(g2gpu_ctx *ctx, int npart, void **records);
+int g2gpu_inputs_ready(g2gpu_ctx *ctx, int npart);
+/* Zero-copy variant: use a caller-owned DEVICE array of npart g2gpu_particle records (16-byte aligned, e.g. the output of
+ * an NCCL all-gather) as the particle input.  It must stay valid and unchanged until g2gpu_domain() has run.  The next
+ * g2gpu_upload()/g2gpu_inputs_ready() unbinds it. */
+int g2gpu_bind_inputs(g2gpu_ctx *ctx, int npart, void *records);
 
 /* ---- stage 1: domain_findExtent + key loop + top tree + peano_hilbert_order
  *      (domain.c:882-924, 933-1138; peano.c:36-185, 356-398) ---- */

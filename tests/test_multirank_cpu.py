@@ -25,10 +25,11 @@ WORKER = textwrap.dedent('''
     pos, mass, ptype = g2test.hernquist(n, seed=3)
     lo, hi, per = multigpu.owner_slice(n, rank, world)
     ex = multigpu.ParticleExchange(n, torch.device("cpu"), world)
-    pm = torch.from_numpy(np.concatenate([pos, mass[:, None]], axis=1).astype(np.float32))
-    ex.set_local(pm[lo:hi], torch.from_numpy(ptype[lo:hi].astype(np.int32)), torch.zeros(hi - lo))
-    g_pm, g_type, g_old = ex.gather()
-    assert torch.equal(g_pm, pm) and torch.equal(g_type, torch.from_numpy(ptype.astype(np.int32)))
+    full = multigpu.pack_records(torch.from_numpy(pos), torch.from_numpy(mass), torch.from_numpy(ptype.astype(np.int32)))
+    ex.set_local(full[lo:hi])
+    g_rec = ex.gather()
+    assert torch.equal(g_rec, full)
+    g_pm, g_type = g_rec[:, :4], g_rec.view(torch.int32)[:, 4].contiguous()
     # every rank: same tree from the gathered set, walk only its slice of the targets
     o = PortOracle(int(1.1 * n) + 64, softening=g2test.SOFT_NP, gravity=g2test.GRAV_D2)
     o.load(g_pm[:, :3].numpy(), g_pm[:, 3].numpy(), g_type.numpy())
