@@ -166,6 +166,10 @@ def reference_run(w, oldacc_by_id, steps, warmup, sample_frac=None, nthreads=Non
 
 # ------------------------------------------------------------------------------------------------ GPU arm --------
 def main():
+    # stdout carries exactly ONE JSON line: everything else that native libraries print there (e.g. the NCCL version banner)
+    # is sent to stderr by pointing fd 1 at fd 2 and keeping a private copy of the real stdout for the result line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -199,7 +203,7 @@ def main():
                 "interactions_per_s": r["interactions_per_s"],
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
         return
 
     import torch
@@ -374,7 +378,7 @@ def main():
                                     "interactions_per_s": r["interactions_per_s"]}
         except Exception as e:                           # the baseline is a reported number, never a dependency of the GPU arm
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

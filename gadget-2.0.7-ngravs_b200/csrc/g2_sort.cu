@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const unsigned 
 // out in tile-sorted order: consecutive threads write consecutive addresses of one bin's run (coalesced), instead of
 // 4096 scattered 8-byte stores.
 #define SCATTER_SMEM (SORT_WARPS * RADIX_BINS * 4 + 2 * RADIX_BINS * 4 + 64 * 4 + SORT_TILE * 8 + SORT_TILE * 4)
-__global__ void __launch_bounds__(SORT_THREADS) sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
+__global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
 								     unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
 								     const unsigned int *__restrict__ tilescan, int n, int ntiles, int shift, unsigned int mask)
 {
