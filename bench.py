@@ -71,32 +71,45 @@ def pm_split(w):
 
 # ------------------------------------------------------------------------------------------------ clocks --------
 class ClockSampler(threading.Thread):
+    """Samples nvidia-smi continuously; result() keeps the samples whose query overlapped the timed region (a query takes
+    ~0.1 s, longer than a short timed region, so overlap rather than containment is the criterion)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.samples, self.reasons, self.maxmhz, self.stop_flag = gpu, [], set(), None, False
+        self.gpu, self.samples, self.maxmhz, self.stop_flag = gpu, [], None, False
+        self.t0 = self.t1 = None
 
     def run(self):
         while not self.stop_flag:
+            ts = time.time()
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip()
                 f = [x.strip() for x in out.split(",")]
-                self.samples.append(float(f[0]))
+                reasons = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6])
+                           if v.lower().startswith("active")]
+                self.samples.append((ts, time.time(), float(f[0]), reasons))
                 self.maxmhz = float(f[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+        time.sleep(0.25)                                 # let the query that overlaps the end of the region finish
+        self.stop_flag = True
 
     def result(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        sel = [s for s in self.samples if self.t0 is not None and s[0] <= self.t1 and s[1] >= self.t0] or self.samples[-1:]
+        if not sel:
+            return {"sm_mhz": None, "sm_max_mhz": self.maxmhz, "reasons": []}
+        reasons = sorted({r for s in sel for r in s[3]})
+        return {"sm_mhz": float(np.median([s[2] for s in sel])), "sm_max_mhz": self.maxmhz, "reasons": reasons, "samples": len(sel)}
 
 
 def measured_peaks():
@@ -267,13 +280,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(W):
         flush.zero_()
         step_resident()
     tg.sync()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.begin()
     tg.reset_counters()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     stage = dict(domain_ms=0.0, build_ms=0.0, walk_ms=0.0, walk_kernel_ms=0.0, sort_ms=0.0)
@@ -293,7 +307,7 @@ def main():
             last = t
     barrier()
     wall = time.time() - wall0
-    sampler.stop_flag = True
+    sampler.end()
     launches = tg.timings()["launches"]
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
     t_ms = torch.tensor([ms_dev], dtype=torch.float64, device=dev)

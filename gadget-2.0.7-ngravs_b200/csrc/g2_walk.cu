@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
     t2g_packed |= (unsigned int) A.t2g[t] << (4 * t);
   const int nchunks = (A.hi - A.lo + 31) >> 5;
   unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0;
-  unsigned int iter = 0;
 
   while(true)
     {
@@ -203,6 +202,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
       float fx = 0.0f, fy = 0.0f, fz = 0.0f;
       int ninter = 0, nterms = 0;
       unsigned int skip_until = valid ? 0u : 0xffffffffu;
+      unsigned int iter = 0;	// per chunk, so that the FP32 flush points (and hence the result bits) do not depend on scheduling
       const unsigned int end = (unsigned int) A.numnodes;
       // a sub-group without any valid target has nothing to walk
       unsigned int cur = (__ballot_sync(0xffffffffu, valid) & gmask) ? 0u : end;

@@ -1,0 +1,176 @@
+"""GPU: edge cases of the hot path (tiny and ragged inputs, sparse active sets, error paths) and size-independent properties
+at a BASELINE size (1 M particles, config 2)."""
+import numpy as np
+import pytest
+
+import g2test
+from refrun import RefOracle, available
+
+pytestmark = pytest.mark.gpu
+
+
+def make_tg(maxpart, **kw):
+    from g2gpu import TreeGravity
+    tg = TreeGravity(max_part=maxpart, n_gravs=2, **kw)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening(g2test.SOFT_NP))
+    tg.set_laws()
+    return tg
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 33, 257])
+def test_tiny_and_ragged_particle_counts(n):
+    """fewer targets than one warp / not a multiple of 32 / a handful of tree nodes: bit-exact tree, forces within tolerance"""
+    if not available("np_d2_f32"):
+        pytest.skip("oracle/_ref not built")
+    pos, mass, ptype = g2test.gaussian_blobs(n, seed=100 + n)
+    ref = RefOracle("np_d2_f32", 1024, softening=g2test.SOFT_NP, gravity=g2test.GRAV_D2)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    rp = ref.particles()
+    ref.gravity()
+    r1 = ref.particles()
+    tg = make_tg(1024)
+    tg.upload(rp["pos"], rp["mass"], rp["type"])
+    tg.domain()
+    assert tg.treebuild() == ref.tree()["numnodes"]
+    mism = g2test.compare_tree(tg.tree(), ref.tree(), 2)
+    assert all(v == 0 for v in mism.values()), mism
+    tg.walk(tg.walk_params(theta=0.5, G=1.0))
+    acc, cost, old = tg.download_acc()
+    tg.close()
+    assert np.array_equal(cost, r1["cost"])
+    err = g2test.rel_err(acc, r1["acc"])
+    assert np.median(err) <= 1e-5 and err.max() <= 1e-3
+
+
+def test_sparse_active_set_only_updates_active_particles():
+    """individual timesteps: only particles with Ti_endstep == Ti_Current are walked (gravtree.c:113)"""
+    if not available("np_d2_f32"):
+        pytest.skip("oracle/_ref not built")
+    n = 20000
+    pos, mass, ptype = g2test.hernquist(n, seed=8)
+    ref = RefOracle("np_d2_f32", int(1.1 * n) + 64, softening=g2test.SOFT_NP, gravity=g2test.GRAV_D2)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    rp = ref.particles()
+    rng = np.random.default_rng(4)
+    active = (rng.uniform(size=n) < 0.25).astype(np.int32)
+    ref.set_active(active)
+    ref.gravity()
+    r1 = ref.particles()
+    tg = make_tg(ref.maxpart)
+    tg.upload(rp["pos"], rp["mass"], rp["type"], active=active)
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.5, G=1.0))
+    acc, cost, old = tg.download_acc()
+    t = tg.timings()
+    tg.close()
+    a = active.astype(bool)
+    assert t["interactions"] == int(r1["cost"][a].sum())
+    assert np.array_equal(cost[a], r1["cost"][a])
+    assert np.all(acc[~a] == 0) and np.all(cost[~a] == 0)          # untouched
+    err = g2test.rel_err(acc[a], r1["acc"][a])
+    assert np.median(err) <= 1e-5 and np.percentile(err, 99.9) <= 1e-3
+
+
+def test_error_paths_are_reported_not_papered_over():
+    from g2gpu import G2Error, TreeGravity
+    n = 5000
+    pos, mass, ptype = g2test.gaussian_blobs(n, seed=2)
+    # coincident particles cannot be separated by the octree (the reference with NOTREERND runs out of nodes)
+    tg = make_tg(8192)
+    p2 = pos.copy()
+    p2[10] = p2[11]
+    tg.upload(p2, mass, ptype)
+    tg.domain()
+    with pytest.raises(G2Error) as e:
+        tg.treebuild()
+    assert e.value.code == -5
+    tg.close()
+    # MaxNodes too small: forcetree.c:249-255 -> endrun(1)
+    tg = TreeGravity(max_part=8192, n_gravs=2, tree_alloc_factor=0.02)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening(g2test.SOFT_NP))
+    tg.set_laws()
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    with pytest.raises(G2Error) as e:
+        tg.treebuild()
+    assert e.value.code == -4
+    tg.close()
+    # particle type outside 0..5
+    tg = make_tg(8192)
+    bad = ptype.copy()
+    bad[7] = 9
+    tg.upload(pos, mass, bad)
+    tg.domain()
+    with pytest.raises(G2Error) as e:
+        tg.treebuild()
+    assert e.value.code == -2
+    # calls out of order / unwired laws
+    with pytest.raises(G2Error):
+        tg.walk(tg.walk_params())
+    tg.close()
+    tg = TreeGravity(max_part=8192, n_gravs=2)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening(g2test.SOFT_NP))
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    tg.treebuild()
+    with pytest.raises(G2Error) as e:
+        tg.walk(tg.walk_params())
+    assert e.value.code == -7                                        # ngravs_core.c:326-365: every slot must be wired
+    with pytest.raises(G2Error):
+        tg.set_species((0, 0, 5, 0, 0, 0), g2test.force_softening(g2test.SOFT_NP))   # ngravs_core.c:270-279
+    tg.close()
+
+
+def test_full_size_properties_one_million_particles():
+    """BASELINE config 2 size (1 M two-species Hernquist): properties that need no oracle."""
+    n = 1_000_000
+    pos, mass, ptype = g2test.hernquist(n)
+    eps = 0.05
+    soft = (0.0, eps, eps, eps, eps, eps)
+    from g2gpu import TreeGravity
+    tg = TreeGravity(max_part=int(1.1 * n) + 64, n_gravs=2)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening(soft))
+    tg.set_laws()
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    keys, perm = tg.keys(), tg.order()
+    # a permutation, species-major, Peano-Hilbert sorted inside each species block
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    species = np.asarray(g2test.GRAV_D2)[ptype[perm]]
+    assert np.all(np.diff(species) >= 0)
+    for g in (0, 1):
+        assert np.all(np.diff(keys[species == g]) >= 0)
+    nn = tg.treebuild()
+    t = tg.tree()
+    # tree invariants: fathers precede children (insertion order), root holds all mass, per-species masses add up
+    assert np.all(t["father"][1:] < tg.max_part + np.arange(1, nn)) and t["father"][0] == -1
+    msum = np.array([mass[(np.asarray(g2test.GRAV_D2)[ptype] == g)].astype(np.float64).sum() for g in (0, 1)])
+    assert np.allclose(t["mass"][0], msum, rtol=1e-5)
+    assert np.all(t["len"] > 0) and np.isfinite(t["s"]).all()
+    # every particle is the leaf of exactly one node and is reachable: Nextnode is a permutation-like successor map
+    assert t["p_father"].min() >= tg.max_part and t["p_father"].max() < tg.max_part + nn
+    wp = tg.walk_params(theta=0.5, G=1.0)
+    tg.walk(wp)
+    acc1, cost1, old1 = tg.download_acc()
+    tm = tg.timings()
+    assert tm["interactions"] == int(cost1.astype(np.int64).sum())
+    assert np.isfinite(acc1).all() and cost1.min() >= 1
+    # momentum: sum m a vanishes up to the tree's force error
+    m = mass[perm].astype(np.float64)
+    resid = np.linalg.norm((m[:, None] * acc1).sum(0)) / (m * np.linalg.norm(acc1, axis=1)).sum()
+    assert resid < 5e-3
+    # idempotence / determinism: the same step again gives the same bits
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    assert tg.treebuild() == nn
+    tg.walk(wp)
+    acc2, cost2, old2 = tg.download_acc()
+    assert np.array_equal(cost1, cost2) and np.array_equal(acc1, acc2) and np.array_equal(old1, old2)
+    # feeding the sorted output back is a fixed point of peano_hilbert_order
+    tg.upload(pos[perm], mass[perm], ptype[perm])
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+    tg.close()
