@@ -15,6 +15,9 @@
 
 #define WALK_THREADS 128
 #define WALK_WARPS (WALK_THREADS / 32)
+#ifndef WALK_MINBLOCKS
+#define WALK_MINBLOCKS 9
+#endif
 
 struct WalkArgs
 {
@@ -144,7 +147,7 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
 }
 
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, int G>
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) walk_kernel(const WalkArgs A)
 {
   // G = targets per cursor.  G == 32: the whole warp shares one cursor (every node record is one broadcast load).
   // G < 32: the warp's 32 consecutive targets form 32/G sub-groups with their own cursors; a sub-group's union of
