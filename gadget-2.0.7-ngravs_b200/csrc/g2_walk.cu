@@ -41,6 +41,7 @@ struct WalkArgs
   float errtol;			// ErrTolForceAcc
   float boxsize, boxinv;
   float rcut, rcut2, asmthfac, utor2wpi;
+  float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions)
   float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
   double G, pos_fac_pre_g, pos_fac_post_g;
   int use_gravpm;
@@ -233,46 +234,54 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) walk_kernel(cons
 	    {
 	      float dx[D], dy[D], dz[D], r2[D], mass[D];
 	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
+	      const float len = q0.x;
 	      const float cxr = q0.y - px, cyr = q0.z - py, czr = q0.w - pz;
+	      bool done = false;	// culled: skip the subtree without interaction
+	      bool outside = false;
 	      if(SR && PERIODIC)
 		{
 		  shx = A.boxsize * rint_small(cxr * A.boxinv);
 		  shy = A.boxsize * rint_small(cyr * A.boxinv);
 		  shz = A.boxsize * rint_small(czr * A.boxinv);
 		}
-#pragma unroll
-	      for(int g = 0; g < D; g++)
-		{
-		  const float4 q = __ldg(rec + 1 + g);
-		  mass[g] = q.w;
-		  summass += q.w;
-		  if(small_cell)
-		    {
-		      dx[g] = (q.x - px) - shx;
-		      dy[g] = (q.y - py) - shy;
-		      dz[g] = (q.z - pz) - shz;
-		    }
-		  else
-		    {
-		      dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
-		      dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
-		      dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
-		    }
-		  r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
-		  r2min = fminf(r2min, r2[g]);
-		  r2max = fmaxf(r2max, r2[g]);
-		}
-	      const float len = q0.x;
-	      bool done = false;	// culled: skip the subtree without interaction
 	      if(SR)
 		{
-		  if(r2min > A.rcut2)
-		    {		// forcetree.c:1828-1862
-		      const float eff = A.rcut + 0.5f * len;
-		      const float d0 = PERIODIC ? cxr - shx : cxr, d1 = PERIODIC ? cyr - shy : cyr, d2 = PERIODIC ? czr - shz : czr;
-		      if(d0 < -eff || d0 > eff || d1 < -eff || d1 > eff || d2 < -eff || d2 > eff)
-			done = true;
+		  // forcetree.c:1828-1862 culls a node if r2min > rcut^2 AND the target is farther than rcut + len/2 from the
+		  // node centre on some axis.  All mass of a node lies inside its cube (up to float rounding of positions), so a
+		  // target that clears the cube by a small margin on one axis is farther than rcut from every centre of mass:
+		  // r2min > rcut^2 is then certain and the per-species distances need not be computed at all.
+		  const float eff = A.rcut + 0.5f * len;
+		  const float d0 = fabsf(PERIODIC ? cxr - shx : cxr), d1 = fabsf(PERIODIC ? cyr - shy : cyr), d2 = fabsf(PERIODIC ? czr - shz : czr);
+		  const float dmax = fmaxf(fmaxf(d0, d1), d2);
+		  outside = dmax > eff;
+		  done = dmax > eff + A.cull_margin + 1.0e-3f * len;
+		}
+	      if(!done)
+		{
+#pragma unroll
+		  for(int g = 0; g < D; g++)
+		    {
+		      const float4 q = __ldg(rec + 1 + g);
+		      mass[g] = q.w;
+		      summass += q.w;
+		      if(small_cell)
+			{
+			  dx[g] = (q.x - px) - shx;
+			  dy[g] = (q.y - py) - shy;
+			  dz[g] = (q.z - pz) - shz;
+			}
+		      else
+			{
+			  dx[g] = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
+			  dy[g] = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
+			  dz[g] = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
+			}
+		      r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
+		      r2min = fminf(r2min, r2[g]);
+		      r2max = fmaxf(r2max, r2[g]);
 		    }
+		  if(SR && outside && r2min > A.rcut2)
+		    done = true;
 		}
 	      if(!done)
 		{
@@ -527,6 +536,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.asmthfac = (float) (0.5 / wp->asmth * (c->cfg.ntab / 3.0));	// forcetree.c:1708
       A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
       A.shift_len_max = (float) (0.499 * wp->boxsize - 1.001 * wp->rcut);
+      A.cull_margin = (float) (1.0e-5 * wp->boxsize);
     }
   A.G = wp->G; A.pos_fac_pre_g = wp->pos_fac_pre_g; A.pos_fac_post_g = wp->pos_fac_post_g;
   A.use_gravpm = wp->use_gravpm && c->have_gravpm;

@@ -1210,6 +1210,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
   int *order = malloc(sizeof(int) * n), *skip = malloc(sizeof(int) * gsize);
   int no = MP, cnt = 0, gi, ngroups = 0;
   double visits = 0, awake = 0, accepts = 0, pvis = 0, pawake = 0;
+  double v_noaccept = 0, v_chain = 0, v_allcull = 0, v_allaccept = 0, opens = 0, culls = 0, v_leafonly = 0;
   /* DFS order of particles: open everything */
   while(no >= 0)
     {
@@ -1251,7 +1252,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 	      }
 	    {
 	      node *nop = NODE_OF(o, cur);
-	      int anyopen = 0, na = 0;
+	      int anyopen = 0, na = 0, nacc = 0, ncull = 0, nopen = 0;
 	      for(m = 0; m < gsize; m++)
 		{
 		  if(skip[m] == cur)
@@ -1261,17 +1262,39 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		      int dec = node_decision(o, &o->P[order[gi + m]], nop);
 		      na++;
 		      if(dec == 2)
-			anyopen = 1;
+			{
+			  anyopen = 1;
+			  nopen++;
+			}
 		      else
 			{
 			  skip[m] = nop->sibling;	/* wake up at the sibling (-1: never) */
 			  if(dec == 1)
-			    accepts += 1;
+			    {
+			      accepts += 1;
+			      nacc++;
+			    }
+			  else
+			    ncull++;
 			}
 		    }
 		}
 	      visits += 1;
 	      awake += na;
+	      opens += nopen;
+	      culls += ncull;
+	      if(nacc == 0)
+		v_noaccept += 1;
+	      if(ncull == na)
+		v_allcull += 1;
+	      if(nacc == na)
+		v_allaccept += 1;
+	      {
+		/* chain node: exactly one child, which is a node (the next in the walk is a node whose sibling equals ours) */
+		int nx = nop->nextnode;
+		if(nx >= MP && NODE_OF(o, nx)->sibling == nop->sibling)
+		  v_chain += 1;
+	      }
 	      if(anyopen)
 		cur = nop->nextnode;
 	      else
@@ -1291,6 +1314,12 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
   out[3] = accepts / ngroups;
   out[4] = pvis / ngroups;
   out[5] = pawake / ngroups;
+  out[6] = v_noaccept / ngroups;
+  out[7] = v_chain / ngroups;
+  out[8] = v_allcull / ngroups;
+  out[9] = v_allaccept / ngroups;
+  out[10] = opens / ngroups;
+  out[11] = culls / ngroups;
   free(skip);
   free(order);
 }
