@@ -25,20 +25,24 @@ __device__ __forceinline__ float law_plummer(float m, float h, float r)
   return m * h3 * f;
 }
 
-// BAM family, ngravs.c:495-670.  eta, rho depend on which side is the BAM halo.
-__device__ __forceinline__ float bam_core_over_r(float rho, float eta, float r)	// law(r)/r for r >= h
+// BAM family, ngravs.c:495-670.  eta, rho depend on which side is the BAM halo.  The closed form
+// atan(x)/x^2 - 1/(x(1+x^2)) cancels badly just above the reference's Taylor switch (x = 0.1), so this (rarely wired)
+// law is evaluated in FP64 and rounded once.
+__device__ __forceinline__ float bam_core_over_r(float rhof, float etaf, float rf)	// law(r)/r for r >= h
 {
-  float reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
-  if(reta < 0.1f)
-    return rho * eta3 * (2.0f / 3.0f - 4.0f * reta2 / 5.0f + 6.0f * reta2 * reta2 / 7.0f);
-  return rho * eta3 * (atanf(reta) / (reta2 * eta) - 1.0f / (reta * eta * (1.0f + reta2))) / r;
+  const double rho = rhof, eta = etaf, r = rf;
+  const double reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
+  if(reta < 0.1)
+    return (float) (rho * eta3 * (2.0 / 3.0 - 4.0 * reta2 / 5.0 + 6.0 * reta2 * reta2 / 7.0));
+  return (float) (rho * eta3 * (atan(reta) / (reta2 * eta) - 1.0 / (reta * eta * (1.0 + reta2))) / r);
 }
-__device__ __forceinline__ float bam_core_spline(float rho, float eta, float r)
+__device__ __forceinline__ float bam_core_spline(float rhof, float etaf, float rf)
 {
-  float reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
-  if(reta < 0.1f)
-    return rho * eta3 * (2.0f / 3.0f - 4.0f * reta2 / 5.0f + 6.0f * reta2 * reta2 / 7.0f);
-  return rho * eta3 * (atanf(reta) / (reta2 * reta) - 1.0f / (reta2 * (1.0f + reta2)));
+  const double rho = rhof, eta = etaf, r = rf;
+  const double reta = r * eta, reta2 = reta * reta, eta3 = eta * eta * eta;
+  if(reta < 0.1)
+    return (float) (rho * eta3 * (2.0 / 3.0 - 4.0 * reta2 / 5.0 + 6.0 * reta2 * reta2 / 7.0));
+  return (float) (rho * eta3 * (atan(reta) / (reta2 * reta) - 1.0 / (reta2 * (1.0 + reta2))));
 }
 
 // AccelFxns[..](pm, m, r2, r, N) / r      (par[0] = Yukawa inverse range ym, par[1] = BAM_EPSILON)
@@ -53,12 +57,12 @@ __device__ __forceinline__ float accel_over_r(int id, const float *par, float pm
     case G2GPU_LAW_YUKAWA:
       {				// ngravs.c:856-861: source*exp(-r*ym)*(ym/r + 1/r2)
 	float ym = par[0];
-	return m * __expf(-r * ym) * (ym * rinv + rinv * rinv) * rinv;
+	return m * expf(-r * ym) * (ym * rinv + rinv * rinv) * rinv;
       }
     case G2GPU_LAW_COLOYUK:
       {				// ngravs.c:826
 	float ym = par[0];
-	return (m * __expf(-r * ym) * (ym * rinv + rinv * rinv) + m * rinv * rinv) * rinv;
+	return (m * expf(-r * ym) * (ym * rinv + rinv * rinv) + m * rinv * rinv) * rinv;
       }
     case G2GPU_LAW_BAMBAM:
       {				// ngravs.c:495-529
