@@ -556,6 +556,14 @@ extern "C" int g2gpu_download_tree(g2gpu_ctx *c, float *len, float *center, floa
   return g2_export_tree(c, len, center, s, mass, bitflags, sibling, nextnode, father, p_nextnode, p_father);
 }
 
+extern "C" int g2gpu_download_extnodes(g2gpu_ctx *c, float *vs)
+{
+  if(!c || !vs)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_export_extnodes(c, vs);
+}
+
 extern "C" int g2gpu_download_acc(g2gpu_ctx *c, float *acc, float *cost, float *oldacc)
 {
   if(!c)

@@ -664,6 +664,157 @@ __global__ void __launch_bounds__(128) level_kernel(BuildArrays A, const G2TopTr
     }
 }
 
+// wvs (depth-first index U) -> reference numbering
+__global__ void __launch_bounds__(128) vs_permute_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, const unsigned int *__restrict__ c_refid,
+							 int ncells, int D, const float *__restrict__ wvs, float *__restrict__ out)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ntop = tt->ntopnodes;
+  unsigned int U;
+  int ref;
+  if(tid < ncells)
+    {
+      U = (unsigned int) tid + (unsigned int) tt->fdfs[A.tl[A.c_a[tid]]] + 1u;
+      ref = (int) c_refid[tid];
+    }
+  else if(tid < ncells + ntop)
+    {
+      int k = tid - ncells;
+      U = A.t_u[k];
+      ref = k;
+    }
+  else
+    return;
+  for(int q = 0; q < 3 * D; q++)
+    out[(size_t) ref * 3 * D + q] = wvs[(size_t) U * 3 * D + q];
+}
+
+// ---------------------------------------------------------------- velocity moments (Extnodes[].vs) -----------------
+// forcetree.c:563-567, 617-619, 667-677, 692-694: vs = sum(m v) / sum(m) per species, FLOAT*FLOAT products accumulated in
+// double, children in slot order.  Only needed for the host mirror (dynamic tree updates, SPH), so it is a separate
+// on-demand pass over the same depth lists; wvs[U][3][D].
+template <int D>
+__global__ void __launch_bounds__(128) vs_level_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, G2Soft S, const float *__restrict__ vel,
+						       float *__restrict__ wvs, int depth, unsigned int lstart, int lcount,
+						       const unsigned int *__restrict__ depth_list)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int *suns;
+  unsigned int U;
+  int leafk, istop = 0, k = -1;
+  if(i < lcount)
+    {
+      int c = (int) depth_list[lstart + i];
+      suns = A.c_suns + 8 * (size_t) c;
+      leafk = A.tl[A.c_a[c]];
+      U = (unsigned int) c + (unsigned int) tt->fdfs[leafk] + 1u;
+    }
+  else
+    {
+      k = i - lcount;
+      if(k >= tt->ntopnodes || tt->fdepth[k] != depth)
+	return;
+      istop = 1;
+      suns = A.t_suns + 8 * k;
+      leafk = k;
+      U = A.t_u[k];
+    }
+  double v[3][D], m[D];
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    v[0][g] = v[1][g] = v[2][g] = m[g] = 0.0;
+  for(int s = 0; s < 8; s++)
+    {
+      unsigned int Uc = 0xffffffffu;
+      if(istop && !tt->fisleaf[k])
+	{
+	  int ch = tt->fsuns[k][s];
+	  if(ch < 0)
+	    continue;
+	  Uc = A.t_u[ch];
+	}
+      else
+	{
+	  int sv = suns[s];
+	  if(sv == -1)
+	    continue;
+	  if(sv >= 0)
+	    {
+	      unsigned int idx = A.tq[sv];
+	      const G2PRec r = A.prec[idx];
+	      int g = S.t2g[r.type];
+#pragma unroll
+	      for(int gg = 0; gg < D; gg++)
+		if(gg == g)
+		  {
+		    m[gg] = __dadd_rn(m[gg], (double) r.m);
+		    for(int j = 0; j < 3; j++)
+		      v[j][gg] = __dadd_rn(v[j][gg], (double) __fmul_rn(r.m, vel[3 * (size_t) idx + j]));
+		  }
+	      continue;
+	    }
+	  Uc = (unsigned int) (-(sv + 2)) + (unsigned int) tt->fdfs[leafk] + 1u;
+	}
+      const float4 *rec = A.wcells + (size_t) Uc * (2 + D);
+#pragma unroll
+      for(int g = 0; g < D; g++)
+	{
+	  float mc = rec[1 + g].w;
+	  m[g] = __dadd_rn(m[g], (double) mc);
+	  for(int j = 0; j < 3; j++)
+	    v[j][g] = __dadd_rn(v[j][g], (double) __fmul_rn(mc, wvs[((size_t) Uc * 3 + j) * D + g]));
+	}
+    }
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    for(int j = 0; j < 3; j++)
+      wvs[((size_t) U * 3 + j) * D + g] = m[g] > 0 ? (float) __ddiv_rn(v[j][g], m[g]) : (float) v[j][g];
+}
+
+static G2Soft make_soft(const g2gpu_ctx *c);
+static BuildArrays make_arrays(g2gpu_ctx *c);
+
+int g2_export_extnodes(g2gpu_ctx *c, float *vs)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "tree has not been built");
+  if(!c->have_vel)
+    return g2_fail(G2GPU_ERR_STATE, "velocities were not uploaded (g2gpu_upload vel argument)");
+  G2_TRY(g2_stage_renumber(c));
+  const int nn = c->numnodes, D = c->D, ntop = nn - c->ncells;
+  cudaStream_t st = c->stream;
+  float *wvs, *out;
+  G2_CUDA(cudaMalloc(&wvs, sizeof(float) * 3 * (size_t) D * nn));
+  G2_CUDA(cudaMalloc(&out, sizeof(float) * 3 * (size_t) D * nn));
+  BuildArrays A = make_arrays(c);
+  G2Soft S = make_soft(c);
+  for(int d = c->maxdepth; d >= 0; d--)
+    {
+      const int lcount = c->depth_count[d];
+      const int grid = g2_cdiv(lcount + ntop, 128);
+      switch (D)
+	{
+	case 1: vs_level_kernel<1><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 2: vs_level_kernel<2><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 3: vs_level_kernel<3><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 4: vs_level_kernel<4><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 5: vs_level_kernel<5><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	default: vs_level_kernel<6><<<grid, 128, 0, st>>>(A, c->d_top, S, c->vel, wvs, d, c->depth_start[d], lcount, c->c_ready); break;
+	}
+      c->launches++;
+    }
+  vs_permute_kernel<<<g2_cdiv(nn, 128), 128, 0, st>>>(A, c->d_top, c->c_refid, c->ncells, D, wvs, out);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(vs, out, sizeof(float) * 3 * (size_t) D * nn, cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
+  cudaFree(wvs);
+  cudaFree(out);
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "extnodes export: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---------------------------------------------------------------- 5. reference numbering -----------------------
 // The reference creates the internal nodes of one insertion (particle i meeting particle j < i) as a chain of
 // consecutive depths; these are exactly the cells whose second-smallest particle index is i (forcetree.c:183-247).
@@ -955,12 +1106,15 @@ int g2_stage_treebuild(g2gpu_ctx *c)
     for(int d = 0; d < 32; d++)
       {
 	ds.start[d] = run;
+	c->depth_start[d] = run;
+	c->depth_count[d] = c->h_err[16 + d];
 	run += (unsigned int) c->h_err[16 + d];
 	if(c->h_err[16 + d])
 	  maxdepth = d;
       }
     if(c->h_err[8] > maxdepth)
       maxdepth = c->h_err[8];	// deepest top-level node
+    c->maxdepth = maxdepth;
   }
   if(ncells > 0)
     {

@@ -167,6 +167,9 @@ struct g2gpu_ctx
   unsigned int *hist2, *hist2_scan;	// reference renumbering scratch (size n+1)
   unsigned int *dmin;
   int renumbered;
+  unsigned int depth_start[32];	// cells grouped by depth (list in c_ready)
+  int depth_count[32];
+  int maxdepth;
   unsigned int *d_depth;	// [0..31] cells per depth, [32..63] scatter cursors
   int *d_err;			// device error flags (4 ints)
   int *h_err;			// pinned
@@ -196,6 +199,7 @@ int g2_stage_domain(g2gpu_ctx *c);
 int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_export_extnodes(g2gpu_ctx *c, float *vs);
 int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,
 		   int *nextnode, int *father, int *p_nextnode, int *p_father);
 int g2_peano_keys_standalone(g2gpu_ctx *c, int n, const int *xyz, int bits, long long *keys);

@@ -77,14 +77,16 @@ static void g2_push_tables(void);
 
 static void g2_upload(int npart)
 {
-  int off_gravpm = -1;
+  int off_gravpm = -1, off_vel = -1;
 #ifdef PMGRID
   off_gravpm = (int) offsetof(struct particle_data, GravPM);
 #endif
+  if(g2_mirror > 0 || N_gas > 0)
+    off_vel = (int) offsetof(struct particle_data, Vel);	/* Extnodes[].vs of the host mirror */
   g2_check(g2gpu_upload_aos(G2, npart, P, sizeof(struct particle_data), (int) sizeof(FLOAT),
 			    (int) offsetof(struct particle_data, Pos), (int) offsetof(struct particle_data, Mass),
 			    (int) offsetof(struct particle_data, Type), (int) offsetof(struct particle_data, OldAcc),
-			    -1, off_gravpm, (int) offsetof(struct particle_data, Ti_endstep), All.Ti_Current), "upload");
+			    off_vel, off_gravpm, (int) offsetof(struct particle_data, Ti_endstep), All.Ti_Current), "upload");
 }
 
 static void g2_fetch_order(int npart)
@@ -291,11 +293,12 @@ static void g2_refresh_mirror(int npart)
 {
   int nn = Numnodestree, k, j, g;
   float *len = malloc(sizeof(float) * nn), *center = malloc(sizeof(float) * 3 * nn), *s = malloc(sizeof(float) * 3 * nn * N_GRAVS),
-    *mass = malloc(sizeof(float) * nn * N_GRAVS);
+    *mass = malloc(sizeof(float) * nn * N_GRAVS), *vs = malloc(sizeof(float) * 3 * nn * N_GRAVS);
   int *bf = malloc(sizeof(int) * nn * 4), *sib = bf + nn, *nxt = sib + nn, *fat = nxt + nn;
-  if(!len || !center || !s || !mass || !bf)
+  if(!len || !center || !s || !mass || !bf || !vs)
     endrun(7301);
   g2_check(g2gpu_download_tree(G2, len, center, s, mass, bf, sib, nxt, fat, Nextnode, Father), "download_tree");
+  g2_check(g2gpu_download_extnodes(G2, vs), "download_extnodes");
   for(k = 0; k < nn; k++)
     {
       struct NODE *nop = &Nodes[All.MaxPart + k];
@@ -308,12 +311,17 @@ static void g2_refresh_mirror(int npart)
 	}
       for(g = 0; g < N_GRAVS; g++)
 	nop->u.d.mass[g] = mass[k * N_GRAVS + g];
+      for(j = 0; j < 3; j++)
+	for(g = 0; g < N_GRAVS; g++)
+	  Extnodes[All.MaxPart + k].vs[j][g] = vs[(3 * k + j) * N_GRAVS + g];
+      Extnodes[All.MaxPart + k].hmax = 0;	/* SPH smoothing lengths are outside the path */
       nop->u.d.bitflags = bf[k];
       nop->u.d.sibling = sib[k];
       nop->u.d.nextnode = nxt[k];
       nop->u.d.father = fat[k];
     }
   (void) npart;
+  free(vs);
   free(bf);
   free(mass);
   free(s);

@@ -151,6 +151,10 @@ int g2gpu_treebuild(g2gpu_ctx *ctx, int *numnodes);
 int g2gpu_download_tree(g2gpu_ctx *ctx, float *len, float *center, float *s, float *mass, int *bitflags,
 			int *sibling, int *nextnode, int *father, int *p_nextnode, int *p_father);
 
+/* struct extNODE (allvars.h:667-677): vs[(3k+j)*D+g] = Extnodes[MaxPart+k].vs[j][g], the centre-of-mass velocity per
+ * species (forcetree.c:563-567, 617-619, 667-694); needs the vel argument of g2gpu_upload.  hmax (SPH) is not computed. */
+int g2gpu_download_extnodes(g2gpu_ctx *ctx, float *vs);
+
 /* ---- stage 3: the walk + gravity_tree epilogue (gravtree.c:102-358; forcetree.c:1244-2052) ---- */
 int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
 /* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT

@@ -350,6 +350,14 @@ void g2ref_get_particles(double *pos, double *mass, int *type, unsigned int *id,
     }
 }
 
+void g2ref_set_vel(const double *vel)	/* velocities of the particles in their CURRENT order */
+{
+  int i, k;
+  for(i = 0; i < NumPart; i++)
+    for(k = 0; k < 3; k++)
+      P[i].Vel[k] = vel[3 * i + k];
+}
+
 void g2ref_set_oldacc(const double *oldacc)
 {
   int i;

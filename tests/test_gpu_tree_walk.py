@@ -53,7 +53,10 @@ def test_nonperiodic_tree_and_forces(case, n, outdir):
     tg = gpu_for(ref, n)
     tg.set_species(grav, g2test.force_softening(soft))
     tg.set_laws()
-    tg.upload(rp["pos"], rp["mass"], rp["type"])
+    rng = np.random.default_rng(12)
+    vel = rng.normal(size=(n, 3)).astype(np.float32)
+    ref.lib.g2ref_set_vel(np.ascontiguousarray(vel, dtype=np.float64).ctypes.data_as(__import__("ctypes").c_void_p))
+    tg.upload(rp["pos"], rp["mass"], rp["type"], vel=vel)
     tg.domain()
     assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
 
@@ -68,6 +71,7 @@ def test_nonperiodic_tree_and_forces(case, n, outdir):
     assert nn == rt["numnodes"]
     dni = tg.topnodes()["domain_node_index"]
     assert np.array_equal(dni, ref.topnodes()["domain_node_index"])
+    mism["vs"] = int(np.sum(tg.extnodes_vs() != rt["vs"].astype(np.float32)))      # Extnodes[].vs, bit-exact
 
     wp = tg.walk_params(theta=0.5, errtol=0.005, G=1.0)
     tg.walk(wp)
