@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — tree-force throughput of the B200 path (and of the reference's CPU path beside it).
 
-    python bench.py --gpus N --steps K --warmup W [--workload hernquist1m|periodic128|periodic256] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload hernquist1m|periodic128|periodic256|periodic256x4] [--active-frac F]
+                    [--impl reference]
 
 A "step" is one pass of the hot path over the particle set: domain_findExtent + Peano-Hilbert keys + radix sort +
 top-level tree + species-major order, force_treebuild (tree + per-species moments) and the tree walk of every active
@@ -50,17 +51,20 @@ def make_workload(name):
                     key=name, n=n, pos=pos, mass=mass, ptype=ptype, soft=(0.0, eps, eps, eps, eps, eps), grav=(0, 0, 1, 0, 0, 0),
                     D=2, periodic=False, shortrange=False, unequal=True, box=0.0, pmgrid=0, ref_variant="np_d2_f32", flop="np")
     if name.startswith("periodic"):
-        side = int(name[len("periodic"):])
+        four = name.endswith("x4")                      # BASELINE config 4: all 6 particle types mapped onto 4 species
+        side = int(name[len("periodic"):-2] if four else name[len("periodic"):])
         n = side ** 3
         box = 100000.0
-        pos, mass, ptype = g2test.periodic_poisson(n, box)
+        pos, mass, ptype = g2test.periodic_poisson(n, box, ntypes=6 if four else 2)
         pmgrid = 256 if side >= 128 else 64
         eps = box / side / 30.0
-        return dict(name=f"periodic {side}^3 two-species Poisson box, TreePM short-range walk, PMGRID={pmgrid}, ASMTH=1.25, RCUT=4.5, "
-                         "relative criterion alpha=0.005",
-                    key=name, n=n, pos=pos, mass=mass, ptype=ptype, soft=(eps,) * 6, grav=(0, 0, 1, 0, 0, 0), D=2, periodic=True,
-                    shortrange=True, unequal=False, box=box, pmgrid=pmgrid, ref_variant="pm_d2_f32" if pmgrid == 256 else "pm64_d2_f32",
-                    flop="sr")
+        D = 4 if four else 2
+        return dict(name=f"periodic {side}^3 Poisson box, " + ("6 particle types (i mod 6, gas first) on 4 gravitational species (Gravity* = 0,1,2,3,1,2)"
+                                                               if four else "two species") +
+                         f", TreePM short-range walk, PMGRID={pmgrid}, ASMTH=1.25, RCUT=4.5, relative criterion alpha=0.005",
+                    key=name, n=n, pos=pos, mass=mass, ptype=ptype, soft=(eps,) * 6, grav=(0, 1, 2, 3, 1, 2) if four else (0, 0, 1, 0, 0, 0), D=D,
+                    periodic=True, shortrange=True, unequal=False, box=box, pmgrid=pmgrid,
+                    ref_variant=("pm_d%d_f32" if pmgrid == 256 else "pm64_d%d_f32") % D, flop="sr")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -190,6 +194,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="periodic256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--active-frac", type=float, default=1.0, help="fraction of particles with Ti_endstep == Ti_Current (random, seed 7); "
+                    "the metric then counts the ACTIVE particles only (SURVEY.md §8d 'sparse active' case)")
     ap.add_argument("--acc-float", action="store_true", help="FP32 accumulators in the walk (default FP64)")
     ap.add_argument("--walk-group", type=int, default=0, help="targets per walk cursor (4, 8, 16, 32); 0 = library default")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up step, no e2e / cpu_baseline legs")
@@ -259,8 +265,14 @@ def main():
     import multigpu
     lo, hi, per = multigpu.owner_slice(n, rank, world)
     ex = multigpu.ParticleExchange(n, dev, world)
+    active = None
+    n_active = n
+    if args.active_frac < 1.0:
+        active = (np.random.default_rng(7).random(n) < args.active_frac).astype(np.int32)
+        n_active = int(active.sum())
     ex.set_local(multigpu.pack_records(torch.from_numpy(w["pos"][lo:hi]).to(dev), torch.from_numpy(w["mass"][lo:hi]).to(dev),
-                                       torch.from_numpy(w["ptype"][lo:hi].astype(np.int32)).to(dev), torch.from_numpy(oldacc_by_id[lo:hi]).to(dev)))
+                                       torch.from_numpy(w["ptype"][lo:hi].astype(np.int32)).to(dev), torch.from_numpy(oldacc_by_id[lo:hi]).to(dev),
+                                       None if active is None else torch.from_numpy(active[lo:hi]).to(dev)))
     if world == 1:
         ex.gather()                                     # single GPU: the records simply stay resident in HBM
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
@@ -317,11 +329,11 @@ def main():
         dist.all_reduce(inter, op=dist.ReduceOp.SUM)
     ms_step = float(t_ms.item()) / K
     interactions, terms, visits = (float(x) for x in inter.tolist())
-    value = n / (ms_step * 1e-3)
+    value = n_active / (ms_step * 1e-3)
 
     # ---- e2e: host buffers -> g2gpu_gravity_tree -> host buffers (N == 1: whole set; N > 1: reported for rank 0's view)
     e2e = None
-    if world == 1 and not args.profile:
+    if world == 1 and not args.profile and active is None:
         h_pos = torch.from_numpy(w["pos"]).pin_memory().numpy()
         h_mass = torch.from_numpy(w["mass"]).pin_memory().numpy()
         h_type = torch.from_numpy(w["ptype"].astype(np.int32)).pin_memory().numpy()
@@ -375,9 +387,10 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "particles": n, "l2": "flushed between timed iterations (256 MiB write)",
+            "config": {"workload": w["name"] + ("" if active is None else f", {n_active} of {n} particles active (random {args.active_frac:g})"),
+                       "particles": n, "active": n_active, "l2": "flushed between timed iterations (256 MiB write)",
                        "parallelism": f"replicated tree, {world} equal tree-order target slices" + (", NCCL all-gather of particle records per step" if world > 1 else "")},
-            "interactions_per_s": interactions / (ms_step * 1e-3), "ia_per_particle": interactions / n,
+            "interactions_per_s": interactions / (ms_step * 1e-3), "ia_per_particle": interactions / n_active,
             "stages_ms": {k: v / K for k, v in stage.items()}, "cell_visits_per_warp_step": visits,
             "first_pass_barnes_hut": {"ia_per_particle": bh_stats["interactions"] / n, "walk_kernel_ms": bh_stats["walk_kernel_ms"]},
             "wall_ms_per_step_incl_flush": 1e3 * wall / K,
@@ -385,7 +398,7 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline, "roofline_sort": roofline_sort}
     if e2e is not None:
         line["e2e"] = e2e
-    if world == 1 and not args.no_cpu_baseline and not args.profile:
+    if world == 1 and not args.no_cpu_baseline and not args.profile and active is None:
         try:
             r = reference_run(w, oldacc_by_id, 1, 0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
