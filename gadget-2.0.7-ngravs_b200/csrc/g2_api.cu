@@ -1,5 +1,8 @@
 // g2_api.cu — the C ABI (include/g2gpu.h): context life cycle, uploads, downloads, stage entry points.
 #include "g2_common.cuh"
+#include <algorithm>
+#include <thread>
+#include <vector>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -147,6 +150,16 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     cudaFreeHost(c->h_top);
   if(c->h_stage)
     cudaFreeHost(c->h_stage);
+  if(c->h_rec)
+    cudaFreeHost(c->h_rec);
+  if(c->h_vel)
+    cudaFreeHost(c->h_vel);
+  if(c->h_gravpm)
+    cudaFreeHost(c->h_gravpm);
+  if(c->h_export)
+    cudaFreeHost(c->h_export);
+  if(c->d_export)
+    cudaFree(c->d_export);
   for(int i = 0; i < 16; i++)
     if(c->ev[i])
       cudaEventDestroy(c->ev[i]);
@@ -237,20 +250,6 @@ extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
 }
 
 // ---- uploads --------------------------------------------------------------------------------------------------
-static int ensure_stage(g2gpu_ctx *c, size_t bytes)
-{
-  if(c->h_stage_bytes >= bytes)
-    return 0;
-  if(c->h_stage)
-    cudaFreeHost(c->h_stage);
-  c->h_stage = nullptr;
-  c->h_stage_bytes = 0;
-  if(cudaMallocHost(&c->h_stage, bytes) != cudaSuccess)
-    return g2_fail(G2GPU_ERR_NOMEM, "pinned staging allocation of %zu bytes failed", bytes);
-  c->h_stage_bytes = bytes;
-  return 0;
-}
-
 static int ensure_opt(g2gpu_ctx *c, int want_vel, int want_gravpm)
 {
   const size_t np = (size_t) c->cfg.max_part;
@@ -325,6 +324,8 @@ extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const flo
   return 0;
 }
 
+// The reference's AoS goes through ONE pass on the host (several threads) into a pinned staging area that already has the
+// device layout -- 32-byte particle records (+ optional velocity / GravPM triples) -- and then to the device with one copy each.
 extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
 				int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current)
 {
@@ -334,34 +335,71 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
   if(float_bytes != 4 && float_bytes != 8)
     return g2_fail(G2GPU_ERR_ARG, "float_bytes must be 4 or 8");
-  const size_t n = (size_t) npart;
-  float *buf = (float *) malloc(sizeof(float) * n * 11 + sizeof(int) * n * 2);
-  if(!buf)
-    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
-  float *pos = buf, *mass = pos + 3 * n, *old = mass + n, *vel = old + n, *gpm = vel + 3 * n;
-  int *type = (int *) (gpm + 3 * n), *act = type + n;
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  G2_TRY(ensure_opt(c, off_vel >= 0, off_gravpm >= 0));
+  const size_t n = (size_t) npart, np = (size_t) c->cfg.max_part;
+  if(!c->h_rec)
+    G2_CUDA(cudaMallocHost((void **) &c->h_rec, sizeof(G2PRec) * np));
+  if(off_vel >= 0 && !c->h_vel)
+    G2_CUDA(cudaMallocHost((void **) &c->h_vel, sizeof(float) * 3 * np));
+  if(off_gravpm >= 0 && !c->h_gravpm)
+    G2_CUDA(cudaMallocHost((void **) &c->h_gravpm, sizeof(float) * 3 * np));
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaStreamSynchronize(st));	// the staging area may still be the source of the previous upload
   const char *base = (const char *) P;
+  G2PRec *hrec = c->h_rec;
+  float *hvel = c->h_vel, *hgpm = c->h_gravpm;
+  auto convert = [=](size_t lo, size_t hi) {
 #define G2_RD(off, k) (float_bytes == 4 ? ((const float *) (q + (off)))[k] : (float) ((const double *) (q + (off)))[k])
-  for(size_t i = 0; i < n; i++)
-    {
-      const char *q = base + i * stride;
-      for(int k = 0; k < 3; k++)
-	{
-	  pos[3 * i + k] = G2_RD(off_pos, k);
-	  if(off_vel >= 0)
-	    vel[3 * i + k] = G2_RD(off_vel, k);
-	  if(off_gravpm >= 0)
-	    gpm[3 * i + k] = G2_RD(off_gravpm, k);
-	}
-      mass[i] = G2_RD(off_mass, 0);
-      old[i] = off_oldacc >= 0 ? G2_RD(off_oldacc, 0) : 0.0f;
-      type[i] = *(const int *) (q + off_type);
-      act[i] = off_ti_endstep >= 0 ? (*(const int *) (q + off_ti_endstep) == ti_current) : 1;
-    }
+    for(size_t i = lo; i < hi; i++)
+      {
+	const char *q = base + i * stride;
+	G2PRec r;
+	r.x = G2_RD(off_pos, 0);
+	r.y = G2_RD(off_pos, 1);
+	r.z = G2_RD(off_pos, 2);
+	r.m = G2_RD(off_mass, 0);
+	r.type = *(const int *) (q + off_type);
+	r.oldacc = off_oldacc >= 0 ? G2_RD(off_oldacc, 0) : 0.0f;
+	r.active = off_ti_endstep >= 0 ? (*(const int *) (q + off_ti_endstep) == ti_current) : 1;
+	r.pad = 0;
+	hrec[i] = r;
+	if(off_vel >= 0)
+	  for(int k = 0; k < 3; k++)
+	    hvel[3 * i + k] = G2_RD(off_vel, k);
+	if(off_gravpm >= 0)
+	  for(int k = 0; k < 3; k++)
+	    hgpm[3 * i + k] = G2_RD(off_gravpm, k);
+      }
 #undef G2_RD
-  int rc = g2gpu_upload(c, npart, pos, mass, type, old, off_vel >= 0 ? vel : nullptr, off_gravpm >= 0 ? gpm : nullptr, act);
-  free(buf);
-  return rc;
+  };
+  unsigned int nthr = std::thread::hardware_concurrency();
+  nthr = std::max(1u, std::min(std::min(nthr, 16u), (unsigned int) (n / 262144 + 1)));
+  if(nthr == 1)
+    convert(0, n);
+  else
+    {
+      std::vector<std::thread> pool;
+      for(unsigned int t = 0; t < nthr; t++)
+	pool.emplace_back(convert, n * t / nthr, n * (t + 1) / nthr);
+      for(auto &t : pool)
+	t.join();
+    }
+  c->in_rec = c->own_in_rec;
+  c->inputs_bound = 0;
+  G2_CUDA(cudaEventRecord(c->ev[9], st));
+  G2_CUDA(cudaMemcpyAsync(c->own_in_rec, hrec, sizeof(G2PRec) * n, cudaMemcpyHostToDevice, st));
+  if(off_vel >= 0)
+    G2_CUDA(cudaMemcpyAsync(c->in_vel, hvel, n * 12, cudaMemcpyHostToDevice, st));
+  if(off_gravpm >= 0)
+    G2_CUDA(cudaMemcpyAsync(c->in_gravpm, hgpm, n * 12, cudaMemcpyHostToDevice, st));
+  G2_CUDA(cudaEventRecord(c->ev[10], st));
+  c->h2d_bytes = n * (sizeof(G2PRec) + (off_vel >= 0 ? 12 : 0) + (off_gravpm >= 0 ? 12 : 0));
+  c->have_vel = off_vel >= 0;
+  c->have_gravpm = off_gravpm >= 0;
+  c->npart = npart;
+  c->stage = 1;
+  return 0;
 }
 
 extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **records)

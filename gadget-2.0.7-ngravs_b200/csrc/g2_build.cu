@@ -774,6 +774,24 @@ __global__ void __launch_bounds__(128) vs_level_kernel(BuildArrays A, const G2To
 static G2Soft make_soft(const g2gpu_ctx *c);
 static BuildArrays make_arrays(g2gpu_ctx *c);
 
+// Persistent staging of the on-demand exports (device buffer + pinned host mirror of it): one allocation, one D2H copy per call.
+static int export_reserve(g2gpu_ctx *c, size_t bytes)
+{
+  if(c->export_bytes >= bytes)
+    return 0;
+  if(c->d_export)
+    cudaFree(c->d_export);
+  if(c->h_export)
+    cudaFreeHost(c->h_export);
+  c->d_export = c->h_export = nullptr;
+  c->export_bytes = 0;
+  bytes += bytes / 4;
+  G2_CUDA(cudaMalloc((void **) &c->d_export, bytes));
+  G2_CUDA(cudaMallocHost((void **) &c->h_export, bytes));
+  c->export_bytes = bytes;
+  return 0;
+}
+
 int g2_export_extnodes(g2gpu_ctx *c, float *vs)
 {
   if(c->stage < 3)
@@ -783,9 +801,9 @@ int g2_export_extnodes(g2gpu_ctx *c, float *vs)
   G2_TRY(g2_stage_renumber(c));
   const int nn = c->numnodes, D = c->D, ntop = nn - c->ncells;
   cudaStream_t st = c->stream;
-  float *wvs, *out;
-  G2_CUDA(cudaMalloc(&wvs, sizeof(float) * 3 * (size_t) D * nn));
-  G2_CUDA(cudaMalloc(&out, sizeof(float) * 3 * (size_t) D * nn));
+  const size_t vbytes = sizeof(float) * 3 * (size_t) D * nn;
+  G2_TRY(export_reserve(c, 2 * vbytes));
+  float *wvs = (float *) (c->d_export + vbytes), *out = (float *) c->d_export;
   BuildArrays A = make_arrays(c);
   G2Soft S = make_soft(c);
   for(int d = c->maxdepth; d >= 0; d--)
@@ -805,13 +823,12 @@ int g2_export_extnodes(g2gpu_ctx *c, float *vs)
     }
   vs_permute_kernel<<<g2_cdiv(nn, 128), 128, 0, st>>>(A, c->d_top, c->c_refid, c->ncells, D, wvs, out);
   c->launches++;
-  cudaError_t e = cudaMemcpyAsync(vs, out, sizeof(float) * 3 * (size_t) D * nn, cudaMemcpyDeviceToHost, st);
+  cudaError_t e = cudaMemcpyAsync(c->h_export, out, vbytes, cudaMemcpyDeviceToHost, st);
   if(e == cudaSuccess)
     e = cudaStreamSynchronize(st);
-  cudaFree(wvs);
-  cudaFree(out);
   if(e != cudaSuccess)
     return g2_fail(G2GPU_ERR_CUDA, "extnodes export: %s", cudaGetErrorString(e));
+  memcpy(vs, c->h_export, vbytes);
   return 0;
 }
 
@@ -1185,14 +1202,6 @@ int g2_stage_renumber(g2gpu_ctx *c)
   return 0;
 }
 
-template <typename T>
-static int dl(g2gpu_ctx *c, T *host, const T *dev, size_t count)
-{
-  if(host)
-    G2_CUDA(cudaMemcpyAsync(host, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, c->stream));
-  return 0;
-}
-
 int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling, int *nextnode,
 		   int *father, int *p_nextnode, int *p_father)
 {
@@ -1202,8 +1211,8 @@ int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mas
   // device staging
   size_t fbytes = sizeof(float) * (size_t) nn * (4 + 4 * (size_t) D);
   size_t ibytes = sizeof(int) * ((size_t) nn * 4 + (size_t) n * 2 + 2 * G2_MAXTOP);
-  char *buf;
-  G2_CUDA(cudaMalloc(&buf, fbytes + ibytes));
+  G2_TRY(export_reserve(c, fbytes + ibytes));
+  char *buf = c->d_export;
   ExportArrays E;
   E.len = (float *) buf;
   E.center = E.len + nn;
@@ -1229,26 +1238,29 @@ int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mas
     case 4: export_kernel<4><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
     case 5: export_kernel<5><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
     case 6: export_kernel<6><<<grid, 128, 0, st>>>(A, c->tm, c->d_top, c->c_refid, c->p_parent, top_sibling, top_nextnode, c->cfg.max_part, c->cfg.unequal_softenings, E); break;
-    default: cudaFree(buf); return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
+    default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
     }
   c->launches += 2;
   (void) ntop;
-  int rc = 0;
-  rc |= dl(c, len, E.len, (size_t) nn);
-  rc |= dl(c, center, E.center, 3 * (size_t) nn);
-  rc |= dl(c, s, E.s, 3 * (size_t) nn * D);
-  rc |= dl(c, mass, E.mass, (size_t) nn * D);
-  rc |= dl(c, bitflags, E.bitflags, (size_t) nn);
-  rc |= dl(c, sibling, E.sibling, (size_t) nn);
-  rc |= dl(c, nextnode, E.nextnode, (size_t) nn);
-  rc |= dl(c, father, E.father, (size_t) nn);
-  rc |= dl(c, p_nextnode, E.p_nextnode, (size_t) n);
-  rc |= dl(c, p_father, E.p_father, (size_t) n);
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(buf);
-  if(rc)
-    return rc;
+  // one copy into the pinned mirror of the staging buffer, then plain memcpy into the caller's (pageable) arrays
+  const size_t used = fbytes + sizeof(int) * ((size_t) nn * 4 + (size_t) n * 2);
+  cudaError_t e = cudaMemcpyAsync(c->h_export, buf, used, cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
   if(e != cudaSuccess)
     return g2_fail(G2GPU_ERR_CUDA, "export: %s", cudaGetErrorString(e));
+  const char *h = c->h_export;
+#define G2_OUT(dst, src, count) if(dst) memcpy(dst, h + ((const char *) (src) - buf), sizeof(*(dst)) * (count))
+  G2_OUT(len, E.len, (size_t) nn);
+  G2_OUT(center, E.center, 3 * (size_t) nn);
+  G2_OUT(s, E.s, 3 * (size_t) nn * D);
+  G2_OUT(mass, E.mass, (size_t) nn * D);
+  G2_OUT(bitflags, E.bitflags, (size_t) nn);
+  G2_OUT(sibling, E.sibling, (size_t) nn);
+  G2_OUT(nextnode, E.nextnode, (size_t) nn);
+  G2_OUT(father, E.father, (size_t) nn);
+  G2_OUT(p_nextnode, E.p_nextnode, (size_t) n);
+  G2_OUT(p_father, E.p_father, (size_t) n);
+#undef G2_OUT
   return 0;
 }

@@ -105,6 +105,10 @@ struct g2gpu_ctx
   G2PRec *own_in_rec;		// the library's own input buffer
   float *in_vel;		// 3n, optional
   float *in_gravpm;		// 3n, optional
+  G2PRec *h_rec;		// pinned host staging of g2gpu_upload_aos (records | velocities | GravPM), allocated on first use
+  float *h_vel, *h_gravpm;
+  char *d_export, *h_export;	// staging of g2gpu_download_tree / g2gpu_download_extnodes (device, pinned host), grown on demand
+  size_t export_bytes;
   float *in_raw;		// H2D landing zone: pos[3n] | mass[n] | type[n] | oldacc[n] | active[n]
   int inputs_bound;
   size_t h2d_bytes, d2h_bytes;

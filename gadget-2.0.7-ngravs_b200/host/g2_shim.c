@@ -81,7 +81,7 @@ static void g2_upload(int npart)
 #ifdef PMGRID
   off_gravpm = (int) offsetof(struct particle_data, GravPM);
 #endif
-  if(g2_mirror > 0 || N_gas > 0)
+  if(g2_mirror > 0 || N_gas > 0 || (All.TreeDomainUpdateFrequency > 0.0 && TreeReconstructFlag))
     off_vel = (int) offsetof(struct particle_data, Vel);	/* Extnodes[].vs of the host mirror */
   g2_check(g2gpu_upload_aos(G2, npart, P, sizeof(struct particle_data), (int) sizeof(FLOAT),
 			    (int) offsetof(struct particle_data, Pos), (int) offsetof(struct particle_data, Mass),
@@ -329,26 +329,62 @@ static void g2_refresh_mirror(int npart)
   free(len);
 }
 
+/* P[] is not in the device's order (a construction was requested without a preceding peano_hilbert_order): the host-side
+ * dynamic updates get a one-node tree to act on, so that every Father[] chain is valid memory. */
+static void g2_neutral_mirror(int npart)
+{
+  struct NODE *root = &Nodes[All.MaxPart];
+  int i, j;
+  memset(root, 0, sizeof(*root));
+  memset(&Extnodes[All.MaxPart], 0, sizeof(struct extNODE));
+  root->len = DomainLen;
+  for(j = 0; j < 3; j++)
+    root->center[j] = DomainCenter[j];
+  root->u.d.sibling = root->u.d.nextnode = root->u.d.father = -1;
+  for(i = 0; i < npart; i++)
+    {
+      Father[i] = All.MaxPart;
+      Nextnode[i] = -1;
+    }
+}
+
 /* forcetree.c:61.  Uploads the first npart particles, runs the device domain stage (extent, keys, top-level tree)
  * and the parallel build; the tree always reflects the current P[]. */
 int force_treebuild(int npart)
 {
   int numnodes = 0;
+  if(npart <= 0)
+    {				/* ngb_treebuild() of a run without gas (init.c:151, ngb.c:408): nothing to build */
+      g2_neutral_mirror(0);
+      Numnodestree = 1;
+      return Numnodestree;
+    }
   g2_push_tables();
   g2_upload(npart);
   g2_check(g2gpu_domain(G2), "domain");
   g2_fetch_order(npart);
   g2_check(g2gpu_treebuild(G2, &numnodes), "treebuild");
   Numnodestree = numnodes;
-  if(g2_mirror || N_gas > 0)
-    {
-      if(!g2_perm_identity)
-	{
-	  printf("g2gpu: host tree mirror requested but P[] is not in Peano-Hilbert order\n");
-	  endrun(7302);
-	}
-      g2_refresh_mirror(npart);
-    }
+  {
+    /* Who reads the host arrays: ngb.c / density.c (gas), and -- when the run does not rebuild at every step
+     * (TreeDomainUpdateFrequency > 0) -- predict.c:79-91, timestep.c:329-344 and force_update_len(), which drift / kick /
+     * enlarge Nodes[], Extnodes[] through Father[] between two constructions.  They get the tree of the construction the
+     * reference itself asked for (TreeReconstructFlag); the device tree is rebuilt from the current P[] regardless. */
+    const int forced = g2_mirror > 0 || N_gas > 0;
+    const int dynamic = All.TreeDomainUpdateFrequency > 0.0 && TreeReconstructFlag;
+    if(forced || dynamic)
+      {
+	if(g2_perm_identity)
+	  g2_refresh_mirror(npart);
+	else if(forced)
+	  {
+	    printf("g2gpu: host tree mirror requested but P[] is not in Peano-Hilbert order\n");
+	    endrun(7302);
+	  }
+	else
+	  g2_neutral_mirror(npart);
+      }
+  }
   TimeOfLastTreeConstruction = All.Time;
   return Numnodestree;
 }

@@ -1210,7 +1210,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
   int *order = malloc(sizeof(int) * n), *skip = malloc(sizeof(int) * gsize);
   int no = MP, cnt = 0, gi, ngroups = 0;
   double visits = 0, awake = 0, accepts = 0, pvis = 0, pawake = 0;
-  double v_noaccept = 0, v_chain = 0, v_allcull = 0, v_allaccept = 0, opens = 0, culls = 0, v_leafonly = 0;
+  double v_noaccept = 0, v_chain = 0, v_allcull = 0, v_allaccept = 0, opens = 0, culls = 0, v_leafonly = 0, passes = 0, ppasses = 0;
   /* DFS order of particles: open everything */
   while(no >= 0)
     {
@@ -1247,6 +1247,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		  }
 		pvis += 1;
 		pawake += na;
+		ppasses += (na + 31) / 32;
 		cur = o->nextnode[cur];
 		continue;
 	      }
@@ -1281,6 +1282,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		}
 	      visits += 1;
 	      awake += na;
+	      passes += (na + 31) / 32;
 	      opens += nopen;
 	      culls += ncull;
 	      if(nacc == 0)
@@ -1320,6 +1322,8 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
   out[9] = v_allaccept / ngroups;
   out[10] = opens / ngroups;
   out[11] = culls / ngroups;
+  out[12] = passes / ngroups;	/* 32-lane passes if awake members are packed onto lanes */
+  out[13] = ppasses / ngroups;
   free(skip);
   free(order);
 }
