@@ -71,3 +71,28 @@ def compare_tree(gt, rt, D):
     out["p_nextnode"] = int(np.sum(gt["p_nextnode"] != rt["p_nextnode"]))
     out["p_father"] = int(np.sum(gt["p_father"] != rt["p_father"]))
     return out
+
+
+def direct_sum(pos, mass, h, targets, chunk=None):
+    """FP64 direct summation with the GADGET-2 spline softening (the stock pair law of every BASELINE config: Newtonian for
+    r >= h, ngravs.c:420-434 below; h = max of the two particles' 2.8 eps as in forcetree.c:3428-3548); G = 1, pre-G."""
+    pos = np.asarray(pos, dtype=np.float64)
+    mass = np.asarray(mass, dtype=np.float64)
+    h = np.asarray(h, dtype=np.float64)
+    out = np.zeros((len(targets), 3))
+    chunk = chunk or max(1, int(1.6e7 // len(mass)))       # ~0.4 GB of temporaries per chunk
+    for c0 in range(0, len(targets), chunk):
+        t = np.asarray(targets[c0:c0 + chunk])
+        d = pos[None, :, :] - pos[t][:, None, :]
+        r2 = np.einsum("tnk,tnk->tn", d, d)
+        r = np.sqrt(r2)
+        hh = np.maximum(h[None, :], h[t][:, None])
+        u = r / hh
+        with np.errstate(divide="ignore", invalid="ignore"):
+            newton = 1.0 / (r2 * r)
+            inner = (10.666666666667 + u * u * (32.0 * u - 38.4)) / hh ** 3
+            outer = (21.333333333333 - 48.0 * u + 38.4 * u * u - 10.666666666667 * u ** 3 - 0.066666666667 / u ** 3) / hh ** 3
+        fac = np.where(r >= hh, newton, np.where(u < 0.5, inner, outer))
+        fac[r2 == 0.0] = 0.0
+        out[c0:c0 + len(t)] = np.einsum("tn,tnk->tk", fac * mass[None, :], d)
+    return out
