@@ -114,8 +114,15 @@ __global__ void __launch_bounds__(256) pair_depth_kernel(const unsigned long lon
       unsigned long long x = tkey[p] ^ tkey[p + 1];
       if(x == 0)
 	{
+	  // Particles that share all G2_MAXDEPTH levels end up together in one cell of that depth (a bucket of up to 8 direct
+	  // particles, see find_children).  The reference would go on subdividing -- or, at this scale, pick random subnodes
+	  // (forcetree.c:208-232: len < 1e-3 ForceSoftening) -- so its tree is not defined by geometry there either.
 	  m = G2_MAXDEPTH;
-	  atomicExch(&err[0], G2GPU_ERR_TREE_DEPTH);
+	  int k = 1;
+	  while(k < 8 && p - k >= 0 && tkey[p - k] == tkey[p])
+	    k++;
+	  if(k >= 8)
+	    atomicExch(&err[0], G2GPU_ERR_TREE_DEPTH);	// 9 or more: does not fit the 8 child slots of a node
 	}
       else
 	m = (unsigned char) ((__clzll((long long) x) - (64 - KEYBITS)) / 3);
@@ -253,6 +260,16 @@ __device__ __forceinline__ void find_children(const unsigned long long *__restri
   for(int s = 0; s < 8; s++)
     suns[s] = -1;
   unsigned int pos = a;
+  if(d >= G2_MAXDEPTH)
+    {				// bucket at the deepest level: its (at most 8, pair_depth_kernel) particles are direct children
+      for(; pos <= b && pos - a < 8u; pos++)
+	{
+	  suns[pos - a] = (int) pos;
+	  p_parent[pos] = self_code;
+	  npart++;
+	}
+      return;
+    }
   while(pos <= b)
     {
       unsigned int slot = digit_at(tkey[pos], d + 1);
@@ -1106,7 +1123,7 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   if(c->h_err[7])
     return g2_fail(G2GPU_ERR_TOPNODES, "top-level tree exceeds %d nodes", G2_MAXTOP);
   if(c->h_err[0])
-    return g2_fail(G2GPU_ERR_TREE_DEPTH, "two particles share all %d octree levels (coincident particles?)", G2_MAXDEPTH);
+    return g2_fail(G2GPU_ERR_TREE_DEPTH, "more than 8 particles share all %d octree levels (coincident particles?)", G2_MAXDEPTH);
   c->ncells = c->h_err[4];
   const int ntop = c->h_err[5];
   c->numnodes = ntop + c->ncells;

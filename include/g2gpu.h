@@ -30,7 +30,7 @@ enum g2gpu_error
   G2GPU_ERR_ARG = -2,		/* invalid argument / call order */
   G2GPU_ERR_NOMEM = -3,		/* device or host allocation failed */
   G2GPU_ERR_MAXNODES = -4,	/* more tree nodes than MaxNodes (forcetree.c:249-255 -> endrun(1)) */
-  G2GPU_ERR_TREE_DEPTH = -5,	/* two particles not separable within the supported tree depth */
+  G2GPU_ERR_TREE_DEPTH = -5,	/* more than 8 particles not separable within the supported tree depth (21 levels) */
   G2GPU_ERR_TOPNODES = -6,	/* top-level tree larger than MAXTOPNODES (domain.c:1049 -> endrun(13213)) */
   G2GPU_ERR_LAW = -7,		/* unknown / unwired pair force law (ngravs_core.c:326-365) */
   G2GPU_ERR_STATE = -8		/* call made before its prerequisite stage */

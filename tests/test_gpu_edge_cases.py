@@ -78,10 +78,10 @@ def test_error_paths_are_reported_not_papered_over():
     from g2gpu import G2Error, TreeGravity
     n = 5000
     pos, mass, ptype = g2test.gaussian_blobs(n, seed=2)
-    # coincident particles cannot be separated by the octree (the reference with NOTREERND runs out of nodes)
+    # nine coincident particles do not fit the 8 child slots of the deepest node (the reference with NOTREERND runs out of nodes)
     tg = make_tg(8192)
     p2 = pos.copy()
-    p2[10] = p2[11]
+    p2[10:19] = p2[10]
     tg.upload(p2, mass, ptype)
     tg.domain()
     with pytest.raises(G2Error) as e:
@@ -195,3 +195,38 @@ def test_full_size_properties_one_million_particles():
     tg.domain()
     assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
     tg.close()
+
+
+def test_particles_closer_than_the_deepest_level_share_a_bucket_node():
+    """Two/three particles that cannot be separated within 21 octree levels (and exact duplicates) must not stop a run: they become
+    direct children of one node of the deepest level.  The reference's own tree is not geometric at that scale either
+    (forcetree.c:208-232 picks random subnodes below 1e-3 ForceSoftening), so the check is physical: forces against FP64 direct sums."""
+    n = 4000
+    pos, mass, ptype = g2test.gaussian_blobs(n, seed=4)
+    pos = pos.copy()
+    pos[101] = pos[100] + np.float32(1e-6)             # closer than L / 2^21
+    pos[201] = pos[200]                                  # exact duplicates (a triple)
+    pos[202] = pos[200]
+    pos[301] = pos[300] * np.float32(1.0000002)
+    tg = make_tg(8192)
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    perm = tg.order()
+    nn = tg.treebuild()
+    t = tg.tree()
+    assert t["father"][0] == -1 and np.all(t["father"][1:] < tg.max_part + np.arange(1, nn))
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)
+    # the duplicates hang under the same node
+    pf = t["p_father"]
+    assert pf[inv[200]] == pf[inv[201]] == pf[inv[202]] and pf[inv[100]] == pf[inv[101]]
+    tg.walk(tg.walk_params(theta=0.3, G=1.0))
+    acc, cost, _ = tg.download_acc()
+    tg.close()
+    targets = np.array([100, 101, 200, 201, 202, 300, 301, 5, 1777, 3999])
+    hsoft = g2test.force_softening(g2test.SOFT_NP)[ptype]
+    direct = g2test.direct_sum(pos, mass, hsoft, targets)
+    err = g2test.rel_err(acc[inv[targets]], direct)
+    assert err.max() < 2e-2, err
+    assert np.isfinite(acc).all()
+    assert int(cost.sum()) == int(cost.astype(np.int64).sum()) and cost.min() >= 1
