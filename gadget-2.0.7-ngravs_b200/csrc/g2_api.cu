@@ -138,7 +138,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f };
+    c->d_srtable, c->d_srtable_f, c->wcnt };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -501,6 +501,8 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(strcmp(name, "acc_double") == 0)
     c->acc_double = value;
+  else if(strcmp(name, "accumulator") == 0)
+    c->accumulator = value != 0;	// takes effect at the next g2gpu_treebuild
   else if(strcmp(name, "walk_group") == 0)
     {
       if(value != 8 && value != 32)
@@ -600,6 +602,14 @@ extern "C" int g2gpu_download_extnodes(g2gpu_ctx *c, float *vs)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   G2_CUDA(cudaSetDevice(c->cfg.device));
   return g2_export_extnodes(c, vs);
+}
+
+extern "C" int g2gpu_download_nparticles(g2gpu_ctx *c, long long *nparticles)
+{
+  if(!c || !nparticles)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_export_nparticles(c, nparticles);
 }
 
 extern "C" int g2gpu_download_acc(g2gpu_ctx *c, float *acc, float *cost, float *oldacc)

@@ -809,6 +809,150 @@ static int export_reserve(g2gpu_ctx *c, size_t bytes)
   return 0;
 }
 
+// ---------------------------------------------------------------- particle counts per species (NGRAVS_ACCUMULATOR) ----
+// forcetree.c:557-559, 621-623: Nparticles[g] of a node = number of particles of species g below it; handed to the pair laws as
+// N for particle-node interactions (forcetree.c:1563-1577).  A separate bottom-up pass over the same depth lists; wcnt[U][D].
+template <int D>
+__global__ void __launch_bounds__(128) cnt_level_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, G2Soft S, unsigned int *__restrict__ wcnt,
+							int depth, unsigned int lstart, int lcount, const unsigned int *__restrict__ depth_list)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int *suns;
+  unsigned int U;
+  int leafk, istop = 0, k = -1;
+  if(i < lcount)
+    {
+      int c = (int) depth_list[lstart + i];
+      suns = A.c_suns + 8 * (size_t) c;
+      leafk = A.tl[A.c_a[c]];
+      U = (unsigned int) c + (unsigned int) tt->fdfs[leafk] + 1u;
+    }
+  else
+    {
+      k = i - lcount;
+      if(k >= tt->ntopnodes || tt->fdepth[k] != depth)
+	return;
+      istop = 1;
+      suns = A.t_suns + 8 * k;
+      leafk = k;
+      U = A.t_u[k];
+    }
+  unsigned int cnt[D];
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    cnt[g] = 0;
+  for(int s = 0; s < 8; s++)
+    {
+      unsigned int Uc;
+      if(istop && !tt->fisleaf[k])
+	{
+	  int ch = tt->fsuns[k][s];
+	  if(ch < 0)
+	    continue;
+	  Uc = A.t_u[ch];
+	}
+      else
+	{
+	  int sv = suns[s];
+	  if(sv == -1)
+	    continue;
+	  if(sv >= 0)
+	    {
+	      int g = S.t2g[A.prec[A.tq[sv]].type];
+#pragma unroll
+	      for(int gg = 0; gg < D; gg++)
+		cnt[gg] += (gg == g) ? 1u : 0u;
+	      continue;
+	    }
+	  Uc = (unsigned int) (-(sv + 2)) + (unsigned int) tt->fdfs[leafk] + 1u;
+	}
+#pragma unroll
+      for(int g = 0; g < D; g++)
+	cnt[g] += wcnt[(size_t) Uc * D + g];
+    }
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    wcnt[(size_t) U * D + g] = cnt[g];
+}
+
+// wcnt (depth-first index U) -> reference numbering, widened to the reference's `long`
+__global__ void __launch_bounds__(128) cnt_permute_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, const unsigned int *__restrict__ c_refid,
+							  int ncells, int D, const unsigned int *__restrict__ wcnt, long long *__restrict__ out)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ntop = tt->ntopnodes;
+  unsigned int U;
+  int ref;
+  if(tid < ncells)
+    {
+      U = (unsigned int) tid + (unsigned int) tt->fdfs[A.tl[A.c_a[tid]]] + 1u;
+      ref = (int) c_refid[tid];
+    }
+  else if(tid < ncells + ntop)
+    {
+      int k = tid - ncells;
+      U = A.t_u[k];
+      ref = k;
+    }
+  else
+    return;
+  for(int g = 0; g < D; g++)
+    out[(size_t) ref * D + g] = (long long) wcnt[(size_t) U * D + g];
+}
+
+int g2_stage_counts(g2gpu_ctx *c)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "tree has not been built");
+  const int D = c->D, ntop = c->numnodes - c->ncells;
+  cudaStream_t st = c->stream;
+  if(!c->wcnt)
+    G2_CUDA(cudaMalloc((void **) &c->wcnt, sizeof(unsigned int) * (size_t) D * (size_t) c->cfg.max_nodes));
+  BuildArrays A = make_arrays(c);
+  G2Soft S = make_soft(c);
+  for(int d = c->maxdepth; d >= 0; d--)
+    {
+      const int lcount = c->depth_count[d];
+      const int grid = g2_cdiv(lcount + ntop, 128);
+      switch (D)
+	{
+	case 1: cnt_level_kernel<1><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 2: cnt_level_kernel<2><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 3: cnt_level_kernel<3><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 4: cnt_level_kernel<4><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	case 5: cnt_level_kernel<5><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	default: cnt_level_kernel<6><<<grid, 128, 0, st>>>(A, c->d_top, S, c->wcnt, d, c->depth_start[d], lcount, c->c_ready); break;
+	}
+      c->launches++;
+    }
+  G2_CUDA(cudaGetLastError());
+  c->counts_valid = 1;
+  return 0;
+}
+
+int g2_export_nparticles(g2gpu_ctx *c, long long *out)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "tree has not been built");
+  if(!c->counts_valid)
+    G2_TRY(g2_stage_counts(c));
+  G2_TRY(g2_stage_renumber(c));
+  const int nn = c->numnodes, D = c->D;
+  const size_t bytes = sizeof(long long) * (size_t) D * nn;
+  G2_TRY(export_reserve(c, bytes));
+  cudaStream_t st = c->stream;
+  BuildArrays A = make_arrays(c);
+  cnt_permute_kernel<<<g2_cdiv(nn, 128), 128, 0, st>>>(A, c->d_top, c->c_refid, c->ncells, D, c->wcnt, (long long *) c->d_export);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(c->h_export, c->d_export, bytes, cudaMemcpyDeviceToHost, st);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(st);
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "nparticles export: %s", cudaGetErrorString(e));
+  memcpy(out, c->h_export, bytes);
+  return 0;
+}
+
 int g2_export_extnodes(g2gpu_ctx *c, float *vs)
 {
   if(c->stage < 3)
@@ -1187,7 +1331,10 @@ int g2_stage_treebuild(g2gpu_ctx *c)
   G2_CUDA(cudaEventRecord(c->ev[5], st));
   G2_CUDA(cudaGetLastError());
   c->renumbered = 0;
+  c->counts_valid = 0;
   c->stage = 3;
+  if(c->accumulator)
+    G2_TRY(g2_stage_counts(c));
   return 0;
 }
 

@@ -98,6 +98,9 @@ struct g2gpu_ctx
   int sr_ntables;		// unique short-range tables (identical pair tables are stored once)
   unsigned char sr_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   int acc_double;		// accumulate accelerations in FP64 (default) or FP32
+  int accumulator;		// NGRAVS_ACCUMULATOR: nodes carry the particle count per species (wcnt), laws receive it as N
+  int counts_valid;		// wcnt belongs to the current tree
+  unsigned int *wcnt;		// [U][D], filled by g2_stage_counts after the build when accumulator != 0
   int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
 
   // upload-order inputs
@@ -203,6 +206,8 @@ int g2_stage_domain(g2gpu_ctx *c);
 int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_stage_counts(g2gpu_ctx *c);
+int g2_export_nparticles(g2gpu_ctx *c, long long *out);
 int g2_export_extnodes(g2gpu_ctx *c, float *vs);
 int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,
 		   int *nextnode, int *father, int *p_nextnode, int *p_father);

@@ -18,6 +18,10 @@
 #ifndef WALK_MINBLOCKS
 #define WALK_MINBLOCKS 9
 #endif
+#ifndef WALK_WIDE_D
+#define WALK_WIDE_D 3		// from this many species on the per-species registers no longer fit 56 registers without spills
+#define WALK_MINBLOCKS_WIDE 8
+#endif
 
 struct WalkArgs
 {
@@ -27,6 +31,7 @@ struct WalkArgs
   const unsigned int *__restrict__ tq;		// particle index of a sorted position
   const G2PRec *__restrict__ prec;
   const float *__restrict__ gravpm;
+  const unsigned int *__restrict__ cnt;	// particle counts per species of every cell [U][D] (NGRAVS_ACCUMULATOR), or null
   const float *__restrict__ srtable;		// unique tables, NTAB floats each
   float *__restrict__ acc;
   float *__restrict__ cost;
@@ -86,7 +91,8 @@ __device__ __forceinline__ float lds_f32(unsigned int saddr)
 // Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the rare r < h case.
 template <bool SR, bool STOCK>
 __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
-					  float pmass, float m, float dx, float dy, float dz, float r2, float h, float &fx, float &fy, float &fz)
+					  float pmass, float m, float dx, float dy, float dz, float r2, float h, float &fx, float &fy, float &fz,
+					  float nn = 1.0f)	// N of forcetree.c:1563-1577 (only the non-stock laws read it)
 {
   const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   const float r = r2 * rinv;
@@ -126,19 +132,19 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
 	    return false;
 	  if(r >= h)
 	    {
-	      float a = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, 1.0f) * r;
+	      float a = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, nn) * r;
 	      float t = s_tab[(int) A.tabmap[ij] * A.ntab + tabindex];
 	      fac = (a - m * A.utor2wpi * t) * rinv;
 	    }
 	  else
-	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, 1.0f);
+	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, nn);
 	}
       else
 	{
 	  if(r >= h)
-	    fac = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, 1.0f);
+	    fac = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, nn);
 	  else
-	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, 1.0f);
+	    fac = accel_spline(A.laws.spline[ij], A.laws.par[ij], pmass, m, h, r, nn);
 	}
       fx = fmaf(dx, fac, fx);
       fy = fmaf(dy, fac, fy);
@@ -148,7 +154,7 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
 }
 
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, int G>
-__global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) walk_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
 {
   // G = targets per cursor.  G == 32: the whole warp shares one cursor (every node record is one broadcast load).
   // G < 32: the warp's 32 consecutive targets form 32/G sub-groups with their own cursors; a sub-group's union of
@@ -319,7 +325,8 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_MINBLOCKS) walk_kernel(cons
 #pragma unroll
 		      for(int g = 0; g < D; g++)
 			{
-			  bool cnt = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, fx, fy, fz);
+			  const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
+			  bool cnt = pair_term<SR, STOCK>(A, s_tab, s_tab_addr, tg, g, D, pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, fx, fy, fz, nn);
 			  any |= cnt;
 			  nterms += cnt;
 			}
@@ -525,6 +532,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   WalkArgs A;
   memset(&A, 0, sizeof(A));
   A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.tq = c->tq; A.prec = c->prec;
+  A.cnt = (c->accumulator && c->counts_valid) ? c->wcnt : nullptr;
   A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
   A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
   A.lo = c->w_lo; A.hi = c->w_hi; A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;

@@ -19,7 +19,7 @@ SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebamba
 EXPORTED = [
     "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
-    "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes",
+    "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
     "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
 ]
@@ -196,6 +196,12 @@ class TreeGravity:
         vs = np.zeros((self.numnodes, 3, self.D), dtype=np.float32)
         self._chk(self.lib.g2gpu_download_extnodes(self.ctx, _p(vs)))
         return vs
+
+    def nparticles(self):
+        """Nodes[].u.d.Nparticles[g] of a -DNGRAVS_ACCUMULATOR build (allvars.h:645-648)."""
+        cnt = np.zeros((self.numnodes, self.D), dtype=np.int64)
+        self._chk(self.lib.g2gpu_download_nparticles(self.ctx, _p(cnt)))
+        return cnt
 
     # ---- gravity_tree -------------------------------------------------------------------------------------------
     @staticmethod

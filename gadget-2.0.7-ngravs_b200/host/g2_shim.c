@@ -262,6 +262,9 @@ void force_treeallocate(int maxnodes, int maxpart)
       cfg.rank = 0;
       cfg.nranks = 1;
       g2_check(g2gpu_create(&G2, &cfg), "create");
+#ifdef NGRAVS_ACCUMULATOR
+      g2_check(g2gpu_set_option(G2, "accumulator", 1), "set_option");	/* laws receive Nodes[].u.d.Nparticles as N */
+#endif
       g2_maxpart = All.MaxPart;
       g2_maxnodes = maxnodes;
       g2_perm = realloc(g2_perm, sizeof(int) * All.MaxPart);
@@ -320,6 +323,18 @@ static void g2_refresh_mirror(int npart)
       nop->u.d.nextnode = nxt[k];
       nop->u.d.father = fat[k];
     }
+#ifdef NGRAVS_ACCUMULATOR
+  {
+    long long *cnt = malloc(sizeof(long long) * nn * N_GRAVS);
+    if(!cnt)
+      endrun(7301);
+    g2_check(g2gpu_download_nparticles(G2, cnt), "download_nparticles");
+    for(k = 0; k < nn; k++)
+      for(g = 0; g < N_GRAVS; g++)
+	Nodes[All.MaxPart + k].u.d.Nparticles[g] = (long) cnt[k * N_GRAVS + g];
+    free(cnt);
+  }
+#endif
   (void) npart;
   free(vs);
   free(bf);

@@ -155,6 +155,11 @@ int g2gpu_download_tree(g2gpu_ctx *ctx, float *len, float *center, float *s, flo
  * species (forcetree.c:563-567, 617-619, 667-694); needs the vel argument of g2gpu_upload.  hmax (SPH) is not computed. */
 int g2gpu_download_extnodes(g2gpu_ctx *ctx, float *vs);
 
+/* -DNGRAVS_ACCUMULATOR (allvars.h:645-648; forcetree.c:557-559, 621-623): nparticles[k*D+g] = Nodes[MaxPart+k].u.d.Nparticles[g],
+ * the number of particles of species g below node k.  With the option "accumulator" the walk hands it to the pair laws as N for
+ * particle-node interactions (forcetree.c:1563-1577); particle-particle interactions always pass 1. */
+int g2gpu_download_nparticles(g2gpu_ctx *ctx, long long *nparticles);
+
 /* ---- stage 3: the walk + gravity_tree epilogue (gravtree.c:102-358; forcetree.c:1244-2052) ---- */
 int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
 /* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT
@@ -166,7 +171,8 @@ int g2gpu_gravity_tree(g2gpu_ctx *ctx, int npart, const float *pos, const float 
 		       const float *oldacc, const int *active, const g2gpu_walk_params *wp, float *acc, float *cost,
 		       float *oldacc_out, int *perm);
 
-/* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks". */
+/* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks", "walk_group",
+ * "accumulator" (1 = the reference built with -DNGRAVS_ACCUMULATOR; takes effect at the next g2gpu_treebuild). */
 int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
 
 /* ---- instrumentation ---- */

@@ -416,6 +416,21 @@ void g2ref_get_tree(double *geom, double *s, double *mass, double *vs, int *link
     }
 }
 
+/* Nodes[].u.d.Nparticles[g] (allvars.h:645-648); returns 0 when the variant was built without -DNGRAVS_ACCUMULATOR */
+int g2ref_get_nparticles(long long *out)
+{
+#ifdef NGRAVS_ACCUMULATOR
+  int k, g;
+  for(k = 0; k < Numnodestree; k++)
+    for(g = 0; g < N_GRAVS; g++)
+      out[k * N_GRAVS + g] = Nodes[All.MaxPart + k].u.d.Nparticles[g];
+  return 1;
+#else
+  (void) out;
+  return 0;
+#endif
+}
+
 /* short-range table shortrange_fourier_force[tgt][src][NTAB] (forcetree.c:33, filled 3274-3354) */
 int g2ref_get_srtable(double *out)
 {

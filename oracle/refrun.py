@@ -183,6 +183,11 @@ class RefOracle:
                     vs=vs, bitflags=link[:, 0].copy(), sibling=link[:, 1].copy(), nextnode=link[:, 2].copy(),
                     father=link[:, 3].copy(), p_nextnode=nextnode, p_father=father)
 
+    def nparticles(self):
+        """Nodes[].u.d.Nparticles (variants built with -DNGRAVS_ACCUMULATOR), else None."""
+        cnt = np.zeros((self.lib.g2ref_numnodes(), self.D), dtype=np.int64)
+        return cnt if self.lib.g2ref_get_nparticles(cnt.ctypes.data_as(C.c_void_p)) else None
+
     def srtable(self):
         if not self.pmgrid:
             return None

@@ -49,7 +49,7 @@ def test_pair_laws_pointwise(variant, wiring, box):
     tg.close()
 
 
-@pytest.mark.parametrize("variant,wiring", [("np_yuk_f32", YUK), ("np_bam_f32", BAM)])
+@pytest.mark.parametrize("variant,wiring", [("np_yuk_f32", YUK), ("np_bam_f32", BAM), ("np_bamacc_f32", BAM)])
 def test_walk_with_non_newtonian_wiring(variant, wiring, outdir):
     if not available(variant):
         pytest.skip("oracle/_ref not built")
@@ -57,7 +57,7 @@ def test_walk_with_non_newtonian_wiring(variant, wiring, outdir):
     n = 20000
     box = 1000.0 if variant == "np_yuk_f32" else 0.0
     pos, mass, ptype = g2test.gaussian_blobs(n, seed=21)
-    if variant == "np_bam_f32":
+    if variant.startswith("np_bam"):
         mass = (mass * 1e-3).astype(np.float32)        # BAM scale radii 4 pi eps / m comparable to the separations
     soft, grav = g2test.SOFT_NP, g2test.GRAV_D2
     ref = RefOracle(variant, int(1.1 * n) + 64, boxsize=box, softening=soft, gravity=grav)
@@ -69,9 +69,13 @@ def test_walk_with_non_newtonian_wiring(variant, wiring, outdir):
     tg = TreeGravity(max_part=ref.maxpart, n_gravs=2)
     tg.set_species(grav, g2test.force_softening(soft))
     tg.set_laws(wiring["accel"], wiring["spline"], law_params(box))
+    if variant == "np_bamacc_f32":
+        tg.set_option("accumulator", 1)                # the reference built with -DNGRAVS_ACCUMULATOR: laws get N of the node
     tg.upload(rp["pos"], rp["mass"], rp["type"])
     tg.domain()
     assert tg.treebuild() == ref.tree()["numnodes"]
+    if variant == "np_bamacc_f32":
+        assert np.array_equal(tg.nparticles(), ref.nparticles())       # Nodes[].u.d.Nparticles, bit-exact
     tg.walk(tg.walk_params(theta=0.5, boxsize=box, G=1.0))
     acc, cost, old = tg.download_acc()
     tg.close()
