@@ -323,12 +323,13 @@ def main():
     launches = tg.timings()["launches"]
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
     t_ms = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-    inter = torch.tensor([float(last["interactions"]), float(last["species_terms"]), float(last["cell_visits"])], dtype=torch.float64, device=dev)
+    inter = torch.tensor([float(last["interactions"]), float(last["species_terms"]), float(last["cell_visits"]), float(last["decisions"])],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(inter, op=dist.ReduceOp.SUM)
     ms_step = float(t_ms.item()) / K
-    interactions, terms, visits = (float(x) for x in inter.tolist())
+    interactions, terms, visits, decisions = (float(x) for x in inter.tolist())
     value = n_active / (ms_step * 1e-3)
 
     # ---- e2e: host buffers -> g2gpu_gravity_tree -> host buffers (N == 1: whole set; N > 1: reported for rank 0's view)
@@ -373,10 +374,27 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(w["key"])
     except Exception:
         traffic = None
+    # visit-inclusive figure of SURVEY.md §8d: every opening decision of a target (accepted or not) costs 16 D + 6 flop (+ 12 TreePM cull)
+    flops_dec = decisions * (16.0 * w["D"] + 6.0 + (12.0 if w["shortrange"] else 0.0))
+    achieved_incl = (flops_alg + flops_dec) / (walk_ms * 1e-3) / 1e12 * (1.0 if world == 1 else 1.0 / world)
     roofline = {"kernel": "walk_kernel", "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "traffic": traffic, "share_of_step": walk_ms / ms_step,
+                "visit_inclusive": {"achieved": achieved_incl, "frac": achieved_incl / fp32_peak, "decisions_per_particle": decisions / max(n_active, 1),
+                                    "flop_per_decision": 16.0 * w["D"] + 6.0 + (12.0 if w["shortrange"] else 0.0)},
                 "note": f"algorithmic flops = species terms x {FLOP_PER_TERM[w['flop']]:.0f} (SURVEY.md §8d), cell-opening arithmetic excluded; peak = "
                         f"{prop.multi_processor_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal CUDA-core FP32, of MEASURED_PEAKS sm_max_mhz)"}
+    # ncu's own utilisation figures of the same kernel on the same workload, from the committed capture (never measured under this run)
+    for suffix in ("r1b", "final", "v1"):
+        prof = os.path.join(ROOT, "profiles", f"r1_walk_{w['key']}_{suffix}.txt")
+        if os.path.exists(prof):
+            ncu = {"source": os.path.relpath(prof, ROOT)}
+            for ln in open(prof):
+                f = ln.split()
+                if len(f) >= 2 and f[0] in ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                                            "smsp__thread_inst_executed_per_inst_executed.ratio"):
+                    ncu[f[0]] = float(f[1])
+            roofline["ncu"] = ncu
+            break
     hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
     # radix sorts of stage 1: 7 passes x (8 B hist read + 12 B scatter read + 12 B write) per pair
     sort_bytes = n * 7 * 32.0

@@ -657,7 +657,7 @@ extern "C" int g2gpu_gravity_tree(g2gpu_ctx *c, int npart, const float *pos, con
   return 0;
 }
 
-extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[4])
+extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[8])
 {
   if(!c)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
@@ -676,13 +676,15 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[4])
   if(counters)
     {
       counters[0] = c->launches;
-      counters[1] = counters[2] = counters[3] = 0;
+      for(int i = 1; i < 8; i++)
+	counters[i] = 0;
       if(c->stage >= 4)
 	{
-	  G2_CUDA(cudaMemcpy(c->h_counters, c->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	  G2_CUDA(cudaMemcpy(c->h_counters, c->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	  counters[1] = (long long) c->h_counters[0];
 	  counters[2] = (long long) c->h_counters[1];
 	  counters[3] = (long long) c->h_counters[2];
+	  counters[4] = (long long) c->h_counters[4];
 	}
     }
   return 0;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   for(int t = 0; t < 6; t++)
     t2g_packed |= (unsigned int) A.t2g[t] << (4 * t);
   const int nchunks = (A.hi - A.lo + 31) >> 5;
-  unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0;
+  unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0, tot_dec = 0;
 
   while(true)
     {
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       const float hself = A.fsoft[ptype];
       ACC ax = 0, ay = 0, az = 0;
       float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-      int ninter = 0, nterms = 0;
+      int ninter = 0, nterms = 0, ndec = 0;
       unsigned int skip_until = valid ? 0u : 0xffffffffu;
       unsigned int iter = 0;	// per chunk, so that the FP32 flush points (and hence the result bits) do not depend on scheduling
       const unsigned int end = (unsigned int) A.numnodes;
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	  float shx = 0.0f, shy = 0.0f, shz = 0.0f;
 	  if(live && cur >= skip_until)
 	    {
+	      ndec++;
 	      float dx[D], dy[D], dz[D], r2[D], mass[D];
 	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
 	      const float len = q0.x;
@@ -423,6 +424,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	  A.cost[idx] = (float) ninter;
 	  tot_inter += (unsigned long long) ninter;
 	  tot_terms += (unsigned long long) nterms;
+	  tot_dec += (unsigned long long) ndec;
 	}
     }
   // statistics: interactions (= sum of GravCost), cell visits (per cursor), species terms
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
     {
       tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
       tot_terms += __shfl_xor_sync(0xffffffffu, tot_terms, o);
+      tot_dec += __shfl_xor_sync(0xffffffffu, tot_dec, o);
       tot_visits += __shfl_xor_sync(0xffffffffu, tot_visits, o);
     }
   if(lane == 0)
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       atomicAdd(&A.counters[0], tot_inter);
       atomicAdd(&A.counters[1], tot_visits);
       atomicAdd(&A.counters[2], tot_terms);
+      atomicAdd(&A.counters[4], tot_dec);
     }
 }
 
@@ -522,7 +526,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   target_compact_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(c->w_flags, n, c->w_targets);
   c->launches++;
   G2_CUDA(cudaMemcpyAsync(&c->h_err[4], c->w_flags + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-  G2_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  G2_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned long long), st));
   G2_CUDA(cudaStreamSynchronize(st));
   c->w_ntargets = c->h_err[4];
   const int nr = c->cfg.nranks > 0 ? c->cfg.nranks : 1, rk = c->cfg.rank;

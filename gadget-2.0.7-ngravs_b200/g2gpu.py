@@ -261,10 +261,10 @@ class TreeGravity:
 
     def timings(self):
         ms = np.zeros(8)
-        cnt = np.zeros(4, dtype=np.int64)
+        cnt = np.zeros(8, dtype=np.int64)
         self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
         return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6],
-                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]))
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]))
 
     def reset_counters(self):
         self.lib.g2gpu_reset_counters(self.ctx)

@@ -179,8 +179,9 @@ int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
 /* CUDA-event times (ms) of the last call of each stage: [0] domain [1] treebuild [2] walk
  * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H; counters[0] = kernel launches since
  * g2gpu_reset_counters, [1] = sum of GravCost of the last walk (this rank's targets), [2] = cell visits summed
- * over warps, [3] = species terms evaluated (one per particle interaction, <= D per node interaction). */
-int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[4]);
+ * over warps, [3] = species terms evaluated (one per particle interaction, <= D per node interaction), [4] = opening decisions
+ * (node visits summed over the targets that were awake at the visit), [5..7] reserved (0). */
+int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[8]);
 void g2gpu_reset_counters(g2gpu_ctx *ctx);
 int g2gpu_io_bytes(g2gpu_ctx *ctx, long long out[2]);	/* host->device / device->host bytes of the last upload / download */
 void *g2gpu_stream(g2gpu_ctx *ctx);	/* cudaStream_t all kernels are launched on */
