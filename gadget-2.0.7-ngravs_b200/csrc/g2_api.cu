@@ -485,6 +485,14 @@ extern "C" int g2gpu_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   return g2_stage_walk(c, wp);
 }
 
+extern "C" int g2gpu_direct(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc)
+{
+  if(!c || !wp || !targets || !acc || ntargets < 1)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_direct_sum(c, wp, ntargets, targets, acc);
+}
+
 extern "C" int g2gpu_sync(g2gpu_ctx *c)
 {
   if(!c)

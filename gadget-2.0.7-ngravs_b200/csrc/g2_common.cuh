@@ -207,6 +207,7 @@ int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_counts(g2gpu_ctx *c);
+int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 int g2_export_nparticles(g2gpu_ctx *c, long long *out);
 int g2_export_extnodes(g2gpu_ctx *c, float *vs);
 int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,

@@ -603,6 +603,147 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   return 0;
 }
 
+// ---------------------------------------------------------------- direct summation (accuracy oracle) -------------
+// force_treeevaluate_direct (forcetree.c:3428-3548; gravity_forcetest, gravtree_forcetest.c:28-356): O(N) sum over all particles for a
+// few targets, h = max of the two softenings, same pair laws, FP64 displacements and sums.  One CTA per target.  With the TreePM
+// split (shortrange != 0) the sum is the SHORT-RANGE force the tree walk approximates (same table, cut at tabindex >= NTAB); periodic
+// boxes use the nearest image (the reference's lattice-correction tables are outside the path).
+struct DirectArgs
+{
+  const G2PRec *__restrict__ prec;
+  const float *__restrict__ srtable;
+  const int *__restrict__ targets;
+  double *__restrict__ out;
+  int n, D, ntab, sr, periodic, unequal, stock;
+  double boxsize, asmthfac, utor2wpi;
+  float fsoft[6];
+  int t2g[6];
+  unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  G2LawTable laws;
+};
+
+__global__ void __launch_bounds__(256) direct_kernel(const DirectArgs A)
+{
+  __shared__ double s_red[3][256];
+  const G2PRec p = A.prec[A.targets[blockIdx.x]];
+  const int tg = A.t2g[p.type];
+  const double hp = (double) A.fsoft[p.type];
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  for(int i = threadIdx.x; i < A.n; i += blockDim.x)
+    {
+      const G2PRec q = A.prec[i];
+      double dx = (double) q.x - (double) p.x, dy = (double) q.y - (double) p.y, dz = (double) q.z - (double) p.z;
+      if(A.periodic)
+	{
+	  dx -= A.boxsize * rint(dx / A.boxsize);
+	  dy -= A.boxsize * rint(dy / A.boxsize);
+	  dz -= A.boxsize * rint(dz / A.boxsize);
+	}
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      if(r2 == 0.0 || q.m == 0.0f)
+	continue;
+      const double r = sqrt(r2);
+      double h = hp;
+      if(A.unequal)
+	h = fmax(h, (double) A.fsoft[q.type]);
+      const int sg = A.t2g[q.type], ij = tg * A.D + sg;
+      int tabindex = 0;
+      if(A.sr)
+	{
+	  tabindex = (int) (A.asmthfac * r);
+	  if(tabindex >= A.ntab)
+	    continue;
+	}
+      double fac;
+      if(r >= h)
+	{
+	  double a;		// |a| of the pair law
+	  if(A.stock)
+	    a = (double) q.m / r2;
+	  else
+	    a = (double) accel_over_r(A.laws.accel[ij], A.laws.par[ij], p.m, q.m, (float) r2, (float) r, (float) (1.0 / r), 1.0f) * r;
+	  if(A.sr)
+	    a -= (double) q.m * A.utor2wpi * (double) A.srtable[(int) A.tabmap[ij] * A.ntab + tabindex];
+	  fac = a / r;
+	}
+      else if(A.stock)
+	{			// ngravs.c:420-434 in FP64
+	  const double hinv = 1.0 / h, u = r * hinv, h3 = hinv * hinv * hinv;
+	  fac = (double) q.m * h3 * (u < 0.5 ? 10.666666666667 + u * u * (32.0 * u - 38.4)
+				     : 21.333333333333 - 48.0 * u + 38.4 * u * u - 10.666666666667 * u * u * u - 0.066666666667 / (u * u * u));
+	}
+      else
+	fac = (double) accel_spline(A.laws.spline[ij], A.laws.par[ij], p.m, q.m, (float) h, (float) r, 1.0f);
+      ax += dx * fac;
+      ay += dy * fac;
+      az += dz * fac;
+    }
+  s_red[0][threadIdx.x] = ax;
+  s_red[1][threadIdx.x] = ay;
+  s_red[2][threadIdx.x] = az;
+  __syncthreads();
+  for(int o = 128; o > 0; o >>= 1)
+    {
+      if(threadIdx.x < o)
+	for(int k = 0; k < 3; k++)
+	  s_red[k][threadIdx.x] += s_red[k][threadIdx.x + o];
+      __syncthreads();
+    }
+  if(threadIdx.x < 3)
+    A.out[3 * (size_t) blockIdx.x + threadIdx.x] = s_red[threadIdx.x][0];
+}
+
+int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc)
+{
+  if(c->stage < 2)
+    return g2_fail(G2GPU_ERR_STATE, "direct summation needs g2gpu_domain (particles in current order)");
+  if(!c->laws_set)
+    return g2_fail(G2GPU_ERR_LAW, "pair force laws not set (g2gpu_set_laws)");
+  const int sr = c->cfg.shortrange && wp->asmth > 0;
+  if(sr && !c->srtable_set)
+    return g2_fail(G2GPU_ERR_STATE, "direct: short-range table not set (g2gpu_set_srtable)");
+  for(int i = 0; i < ntargets; i++)
+    if(targets[i] < 0 || targets[i] >= c->npart)
+      return g2_fail(G2GPU_ERR_ARG, "direct: target %d outside [0, %d)", targets[i], c->npart);
+  DirectArgs A;
+  memset(&A, 0, sizeof(A));
+  int *d_t;
+  double *d_out;
+  G2_CUDA(cudaMalloc(&d_t, sizeof(int) * (size_t) ntargets));
+  G2_CUDA(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t) ntargets));
+  G2_CUDA(cudaMemcpyAsync(d_t, targets, sizeof(int) * (size_t) ntargets, cudaMemcpyHostToDevice, c->stream));
+  A.prec = c->prec; A.srtable = c->d_srtable_f; A.targets = d_t; A.out = d_out;
+  A.n = c->npart; A.D = c->D; A.ntab = c->cfg.ntab; A.sr = sr; A.periodic = c->cfg.periodic != 0 && wp->boxsize > 0;
+  A.unequal = c->cfg.unequal_softenings != 0;
+  A.boxsize = wp->boxsize;
+  if(sr)
+    {
+      A.asmthfac = 0.5 / wp->asmth * (c->cfg.ntab / 3.0);
+      A.utor2wpi = 1.0 / (M_PI * 4 * wp->asmth * wp->asmth);
+    }
+  A.stock = 1;
+  for(int i = 0; i < c->D * c->D; i++)
+    if(c->laws.accel[i] != G2GPU_LAW_NEWTONIAN || c->laws.spline[i] != G2GPU_SPLINE_PLUMMER)
+      A.stock = 0;
+  for(int t = 0; t < 6; t++)
+    {
+      A.fsoft[t] = (float) c->force_softening[t];
+      A.t2g[t] = c->type_to_grav[t];
+    }
+  A.laws = c->laws;
+  memcpy(A.tabmap, c->sr_tabmap, sizeof(A.tabmap));
+  direct_kernel<<<ntargets, 256, 0, c->stream>>>(A);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(acc, d_out, sizeof(double) * 3 * (size_t) ntargets, cudaMemcpyDeviceToHost, c->stream);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_t);
+  cudaFree(d_out);
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "direct: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ---------------------------------------------------------------- stand-alone pair evaluation (tests) -----------
 __global__ void eval_pairs_kernel(int n, int accel_id, int spline_id, float p0, float p1, const float *__restrict__ pm, const float *__restrict__ m,
 				  const float *__restrict__ r, const float *__restrict__ h, const int *__restrict__ nn, float *__restrict__ fac)

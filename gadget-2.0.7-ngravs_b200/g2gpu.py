@@ -20,7 +20,7 @@ EXPORTED = [
     "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
-    "g2gpu_walk", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
+    "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
     "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
 ]
 
@@ -210,6 +210,13 @@ class TreeGravity:
 
     def walk(self, wp):
         self._chk(self.lib.g2gpu_walk(self.ctx, C.byref(wp)))
+
+    def direct(self, wp, targets):
+        """force_treeevaluate_direct for the given current-order indices: (len(targets), 3) float64, pre-G."""
+        t = _i32(targets)
+        out = np.zeros((len(t), 3))
+        self._chk(self.lib.g2gpu_direct(self.ctx, C.byref(wp), len(t), _p(t), _p(out)))
+        return out
 
     def download_acc(self):
         acc = np.zeros((self.n, 3), dtype=np.float32)

@@ -162,6 +162,12 @@ int g2gpu_download_nparticles(g2gpu_ctx *ctx, long long *nparticles);
 
 /* ---- stage 3: the walk + gravity_tree epilogue (gravtree.c:102-358; forcetree.c:1244-2052) ---- */
 int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
+/* force_treeevaluate_direct (forcetree.c:3428-3548), the accuracy oracle of gravity_forcetest (gravtree_forcetest.c:28-356): FP64
+ * direct summation over all particles for ntargets particles given by their index in CURRENT order (after g2gpu_domain);
+ * acc[3*i+k] is the pre-G acceleration (G = 1).  Under the TreePM split (config.shortrange and wp->asmth > 0) it is the short-range
+ * force the tree walk approximates; periodic boxes take the nearest image (no lattice correction). */
+int g2gpu_direct(g2gpu_ctx *ctx, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
+
 /* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT
  * particle order; only entries of active particles of this rank's slice are written. */
 int g2gpu_download_acc(g2gpu_ctx *ctx, float *acc, float *cost, float *oldacc);

@@ -1,5 +1,7 @@
 """GPU: edge cases of the hot path (tiny and ragged inputs, sparse active sets, error paths) and size-independent properties
 at a BASELINE size (1 M particles, config 2)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -230,3 +232,39 @@ def test_particles_closer_than_the_deepest_level_share_a_bucket_node():
     assert err.max() < 2e-2, err
     assert np.isfinite(acc).all()
     assert int(cost.sum()) == int(cost.astype(np.int64).sum()) and cost.min() >= 1
+
+
+@pytest.mark.parametrize("side", [128, 256])
+def test_full_size_treepm_against_direct_shortrange_sum(side, outdir):
+    """BASELINE configs 3 and 5 at full size (2.1 M and 16.8 M particles, periodic TreePM): the short-range tree force of random
+    targets against the FP64 direct short-range sum over ALL particles (g2gpu_direct, same table and cut-off) -- what is left is
+    the tree approximation, bounded by the relative opening criterion (alpha = 0.005)."""
+    import json
+    from g2gpu import TreeGravity
+    n = side ** 3
+    box = 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box)
+    eps = box / side / 30.0
+    tg = TreeGravity(max_part=int(1.1 * n) + 64, n_gravs=2, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening((eps,) * 6))
+    tg.set_laws()
+    tab = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gadget-2.0.7-ngravs_b200", "data", "srtable_newton_ntab2048.npy"))
+    tg.set_srtable(np.broadcast_to(tab, (2, 2, len(tab))).copy())
+    asmth = 1.25 * box / 256
+    rcut = 4.5 * asmth
+    wp_bh = tg.walk_params(theta=0.5, errtol=0.005, boxsize=box, G=1.0, asmth=asmth, rcut=rcut)
+    wp_rel = tg.walk_params(theta=0.0, errtol=0.005, boxsize=box, G=1.0, asmth=asmth, rcut=rcut)
+    acc0, cost0, old0, perm = tg.gravity_tree(pos, mass, ptype, wp_bh)
+    oldacc_by_id = np.zeros(n, dtype=np.float32)
+    oldacc_by_id[perm] = old0
+    acc, cost, old, perm2 = tg.gravity_tree(pos, mass, ptype, wp_rel, oldacc=oldacc_by_id)
+    assert np.array_equal(perm, perm2)
+    targets = np.sort(np.random.default_rng(11).choice(n, 512, replace=False)).astype(np.int32)
+    direct = tg.direct(wp_rel, targets)
+    tm = tg.timings()
+    tg.close()
+    err = g2test.rel_err(acc[targets], direct)
+    json.dump(dict(n=n, median=float(np.median(err)), p99=float(np.percentile(err, 99)), max=float(err.max()),
+                   ia_per_particle=tm["interactions"] / n), open(os.path.join(outdir, f"fullsize_treepm_{side}.json"), "w"))
+    assert np.isfinite(acc).all() and cost.min() >= 1
+    assert np.median(err) < 5e-3 and np.percentile(err, 99) < 5e-2, (float(np.median(err)), float(np.percentile(err, 99)))

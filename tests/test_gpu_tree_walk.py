@@ -263,7 +263,10 @@ def test_accuracy_against_direct_summation(outdir):
     tg.treebuild()
     tg.walk(tg.walk_params(theta=0.0, errtol=0.005, G=1.0))
     acc, cost, old = tg.download_acc()
+    # the device's own FP64 direct summation (g2gpu_direct = force_treeevaluate_direct) against the reference's
+    direct_gpu = tg.direct(tg.walk_params(theta=0.0, errtol=0.005, G=1.0), targets)
     tg.close()
+    assert np.median(g2test.rel_err(direct_gpu, direct)) < 1e-6 and g2test.rel_err(direct_gpu, direct).max() < 1e-4
     e_gpu = g2test.rel_err(acc[targets], direct)
     e_ref = g2test.rel_err(r2["acc"][targets], direct)
     dump(outdir, "forcetest.json", dict(gpu=summarize(e_gpu), ref=summarize(e_ref)))
