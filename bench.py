@@ -396,11 +396,15 @@ def main():
             roofline["ncu"] = ncu
             break
     hbm_peak = (peaks or {}).get("hbm_gbs", 6650.0)
+    try:
+        sort_traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get("sort_stage1_" + w["key"])
+    except Exception:
+        sort_traffic = None
     # radix sorts of stage 1: 7 passes x (8 B hist read + 12 B scatter read + 12 B write) per pair
     sort_bytes = n * 7 * 32.0
     roofline_sort = {"kernel": "sort_hist_kernel+sort_scatter_kernel (stage 1, 7 passes)", "bound": "hbm",
                      "achieved": sort_bytes / (stage["sort_ms"] / K * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": sort_bytes / (stage["sort_ms"] / K * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                     "frac": sort_bytes / (stage["sort_ms"] / K * 1e-3) / 1e9 / hbm_peak, "traffic": sort_traffic,
                      "note": "of measured" if peaks else "of fallback"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
