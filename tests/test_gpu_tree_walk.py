@@ -272,3 +272,54 @@ def test_accuracy_against_direct_summation(outdir):
     dump(outdir, "forcetest.json", dict(gpu=summarize(e_gpu), ref=summarize(e_ref)))
     assert abs(np.median(e_gpu) - np.median(e_ref)) <= 0.02 * np.median(e_ref)
     assert np.percentile(e_gpu, 99) <= 1.05 * np.percentile(e_ref, 99)
+
+
+@pytest.mark.parametrize("variant,grav,periodic", [("np_d1_f32", (0, 0, 0, 0, 0, 0), False), ("np_d3_f32", (0, 0, 1, 2, 1, 2), False),
+                                                   ("np_d5_f32", (0, 0, 1, 2, 3, 4), False), ("np_d6_f32", (0, 1, 2, 3, 4, 5), False),
+                                                   ("pm64_d3_f32", (0, 1, 2, 1, 2, 1), True)])
+def test_every_species_count_against_the_reference(variant, grav, periodic, outdir):
+    """N_GRAVS = 1, 3, 5, 6 (and 3 under TreePM with a gas block): every template instance of the moment pass and the walk against the
+    reference built with the same N_GRAVS -- tree bit-exact, accelerations within tolerance, GravCost compared exactly."""
+    if not available(variant):
+        pytest.skip("oracle/_ref not built")
+    n = 12000
+    box = 100000.0 if periodic else 0.0
+    if periodic:
+        pos, mass, ptype = g2test.periodic_poisson(n, box, seed=5, ntypes=6)
+        soft = (box / 23 / 30.0,) * 6
+    else:
+        pos, mass, ptype = g2test.gaussian_blobs(n, seed=31, types=(1, 2, 3, 4, 5))
+        soft = (0.0, 0.05, 0.02, 0.03, 0.05, 0.01)
+    ref = run_reference(variant, pos, mass, ptype, soft, grav, box=box)
+    rp = ref.particles()
+    tg = gpu_for(ref, n, periodic=periodic, shortrange=periodic, unequal=not periodic)
+    tg.set_species(grav, g2test.force_softening(soft))
+    tg.set_laws()
+    kw = {}
+    if periodic:
+        tg.set_srtable(ref.srtable())
+        asmth, rcut = ref.pm_split()
+        kw = dict(boxsize=box, asmth=asmth, rcut=rcut)
+    tg.upload(rp["pos"], rp["mass"], rp["type"])
+    tg.domain()
+    assert np.array_equal(tg.order(), np.arange(n, dtype=np.int32))
+    ref.gravity()
+    rt, r1 = ref.tree(), ref.particles()
+    assert tg.treebuild() == rt["numnodes"]
+    mism = g2test.compare_tree(tg.tree(), rt, ref.D)
+    assert all(v == 0 for v in mism.values()), mism
+    tg.walk(tg.walk_params(theta=0.5, errtol=0.005, G=1.0, **kw))
+    acc, cost, old = tg.download_acc()
+    ref.set_opening(0.0, 0.005, 1)
+    ref.gravity()
+    r2 = ref.particles()
+    tg.upload(rp["pos"], rp["mass"], rp["type"], oldacc=r1["oldacc"])
+    tg.domain()
+    tg.treebuild()
+    tg.walk(tg.walk_params(theta=0.0, errtol=0.005, G=1.0, **kw))
+    acc2, cost2, old2 = tg.download_acc()
+    tg.close()
+    for a, c, r in ((acc, cost, r1), (acc2, cost2, r2)):
+        s = summarize(g2test.rel_err(a, r["acc"]))
+        assert s["median"] <= MEDIAN_TOL and s["p999"] <= P999_TOL, (variant, s)
+        assert int(np.sum(c != r["cost"])) <= 0.002 * n
