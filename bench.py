@@ -198,6 +198,7 @@ def main():
                     "the metric then counts the ACTIVE particles only (SURVEY.md §8d 'sparse active' case)")
     ap.add_argument("--acc-float", action="store_true", help="FP32 accumulators in the walk (default FP64)")
     ap.add_argument("--walk-group", type=int, default=0, help="targets per walk cursor (4, 8, 16, 32); 0 = library default")
+    ap.add_argument("--walk-mode", type=int, default=-1, help="0: one cursor per 32 targets; 1: one warp per target; -1 = library default")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up step, no e2e / cpu_baseline legs")
     args = ap.parse_args()
 
@@ -243,6 +244,8 @@ def main():
         tg.set_option("acc_double", 0)
     if args.walk_group:
         tg.set_option("walk_group", args.walk_group)
+    if args.walk_mode >= 0:
+        tg.set_option("walk_mode", args.walk_mode)
     asmth, rcut = pm_split(w)
     if w["shortrange"]:
         tab = np.load(os.path.join(PKG, "data", "srtable_newton_ntab2048.npy"))

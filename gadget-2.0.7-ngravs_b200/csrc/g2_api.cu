@@ -65,6 +65,9 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : G2_NSM_FALLBACK;
   c->acc_double = 1;
   c->walk_group = 32;
+  c->walk_mode = G2_DEFAULT_WALK_MODE;
+  if(getenv("G2GPU_WALK_MODE"))
+    c->walk_mode = atoi(getenv("G2GPU_WALK_MODE")) == 1 ? 1 : 0;
   if(getenv("G2GPU_WALK_GROUP"))
     {
       int g = atoi(getenv("G2GPU_WALK_GROUP"));
@@ -138,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->wcnt };
+    c->d_srtable, c->d_srtable_f, c->wcnt, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -511,6 +514,13 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     c->acc_double = value;
   else if(strcmp(name, "accumulator") == 0)
     c->accumulator = value != 0;	// takes effect at the next g2gpu_treebuild
+  else if(strcmp(name, "walk_mode") == 0)
+    {
+      if(value != 0 && value != 1)
+	return g2_fail(G2GPU_ERR_ARG, "walk_mode must be 0 (cursor per 32 targets) or 1 (warp per target)");
+      c->walk_mode = value;
+      c->bfs_valid = 0;
+    }
   else if(strcmp(name, "walk_group") == 0)
     {
       if(value != 8 && value != 32)

@@ -10,6 +10,9 @@
 #define G2_MAXDEPTH 21		// 3*21 = 63 key bits: deepest supported octree level below the root
 #define G2_PH_BITS 18		// BITS_PER_DIMENSION (allvars.h:34)
 #define G2_NSM_FALLBACK 148
+#ifndef G2_DEFAULT_WALK_MODE
+#define G2_DEFAULT_WALK_MODE 0
+#endif
 
 extern char g2_errbuf[512];
 int g2_fail(int code, const char *fmt, ...);
@@ -102,6 +105,13 @@ struct g2gpu_ctx
   int counts_valid;		// wcnt belongs to the current tree
   unsigned int *wcnt;		// [U][D], filled by g2_stage_counts after the build when accumulator != 0
   int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
+  int walk_mode;		// 0: one cursor per 32 targets (g2_walk.cu); 1: one warp per target over level-order records (g2_walkb.cu)
+  int bfs_valid;		// the level-order records belong to the current tree
+  float4 *b_q0, *b_s;		// level-order SoA walk records (allocated on first use)
+  uint4 *b_w;
+  unsigned char *b_ptype;
+  unsigned long long *b_key[2];
+  unsigned int *b_val[2], *b_vofu;
 
   // upload-order inputs
   G2PRec *in_rec;		// may point at caller-bound device memory (g2gpu_bind_inputs)
@@ -207,6 +217,7 @@ int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_counts(g2gpu_ctx *c);
+int g2_stage_bfs(g2gpu_ctx *c);
 int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 int g2_export_nparticles(g2gpu_ctx *c, long long *out);
 int g2_export_extnodes(g2gpu_ctx *c, float *vs);
