@@ -145,6 +145,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
+  g2_pm_destroy(c);
   if(c->h_err)
     cudaFreeHost(c->h_err);
   if(c->h_counters)
@@ -322,6 +323,7 @@ extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const flo
   c->h2d_bytes = n * (12 + 4 + 4 + (oldacc ? 4 : 0) + (active ? 4 : 0) + (vel ? 12 : 0) + (gravpm ? 12 : 0));
   c->have_vel = vel != nullptr;
   c->have_gravpm = gravpm != nullptr;
+  c->pm_done = 0;
   c->npart = npart;
   c->stage = 1;
   return 0;
@@ -400,6 +402,7 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
   c->h2d_bytes = n * (sizeof(G2PRec) + (off_vel >= 0 ? 12 : 0) + (off_gravpm >= 0 ? 12 : 0));
   c->have_vel = off_vel >= 0;
   c->have_gravpm = off_gravpm >= 0;
+  c->pm_done = 0;
   c->npart = npart;
   c->stage = 1;
   return 0;
@@ -427,6 +430,7 @@ extern "C" int g2gpu_bind_inputs(g2gpu_ctx *c, int npart, void *records)
   c->inputs_bound = 1;
   c->have_vel = 0;
   c->have_gravpm = 0;
+  c->pm_done = 0;
   c->npart = npart;
   c->stage = 1;
   return 0;
@@ -442,6 +446,7 @@ extern "C" int g2gpu_inputs_ready(g2gpu_ctx *c, int npart)
   c->inputs_bound = 0;
   c->have_vel = 0;
   c->have_gravpm = 0;
+  c->pm_done = 0;
   c->npart = npart;
   c->stage = 1;
   return 0;
@@ -505,6 +510,22 @@ extern "C" int g2gpu_sync(g2gpu_ctx *c)
 }
 
 extern "C" void *g2gpu_stream(g2gpu_ctx *c) { return c ? (void *) c->stream : nullptr; }
+
+extern "C" int g2gpu_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
+{
+  if(!c || !pp)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_pm_periodic(c, pp);
+}
+
+extern "C" int g2gpu_download_gravpm(g2gpu_ctx *c, float *gravpm)
+{
+  if(!c || !gravpm)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_pm_download(c, gravpm);
+}
 
 extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
 {
@@ -689,7 +710,7 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[8])
       ms[4] = c->stage >= 2 ? ev_ms(c, 1, 2) : 0;
       ms[5] = c->stage >= 1 ? ev_ms(c, 9, 10) : 0;
       ms[6] = c->stage >= 4 ? ev_ms(c, 11, 12) : 0;
-      ms[7] = 0;
+      ms[7] = c->pm_done ? ev_ms(c, 13, 14) : 0;
     }
   if(counters)
     {

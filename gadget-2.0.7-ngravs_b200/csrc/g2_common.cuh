@@ -202,6 +202,10 @@ struct g2gpu_ctx
   unsigned long long *d_counters;	// [0] sum cost, [1] node visits, [2] particle visits
   unsigned long long *h_counters;
 
+  // periodic PM long-range force (g2_pm.cu)
+  int pm_grid, pm_fwd, pm_inv, pm_plans_valid, pm_done;	// mesh size the buffers/plans were made for; cuFFT handles
+  void *pm_rho, *pm_rk, *pm_potk;	// real mesh (density, then potential), D spectra, filtered spectrum of one target species
+
   void *h_stage;		// pinned upload staging
   size_t h_stage_bytes;
   double ms[8];
@@ -218,6 +222,9 @@ int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_stage_bfs(g2gpu_ctx *c);
+int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp);
+int g2_pm_download(g2gpu_ctx *c, float *gravpm);
+void g2_pm_destroy(g2gpu_ctx *c);
 int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 int g2_export_nparticles(g2gpu_ctx *c, long long *out);
 int g2_export_extnodes(g2gpu_ctx *c, float *vs);

@@ -21,7 +21,7 @@ EXPORTED = [
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
-    "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+    "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
 ]
 
 
@@ -35,6 +35,15 @@ class WalkParams(C.Structure):
     _fields_ = [("theta", C.c_double), ("errtol_force_acc", C.c_double), ("boxsize", C.c_double), ("G", C.c_double),
                 ("asmth", C.c_double), ("rcut", C.c_double), ("pos_fac_pre_g", C.c_double),
                 ("pos_fac_post_g", C.c_double), ("use_gravpm", C.c_int)]
+
+
+GREENS = dict(none=0, pgdelta=1, neg_pgdelta=2, pgyukawa=3, pgcoloyuk=4)
+MAX_GRAVS = 6
+
+
+class PMParams(C.Structure):
+    _fields_ = [("pmgrid", C.c_int), ("boxsize", C.c_double), ("asmth", C.c_double), ("G", C.c_double),
+                ("greens_id", C.c_int * (MAX_GRAVS * MAX_GRAVS)), ("greens_par", C.c_double * (MAX_GRAVS * MAX_GRAVS))]
 
 
 class G2Error(RuntimeError):
@@ -266,11 +275,29 @@ class TreeGravity:
         self._chk(self.lib.g2gpu_inputs_ready(self.ctx, int(n)))
         self.n = int(n)
 
+    # ---- long_range_force -> pmforce_periodic (longrange.c:56, pm_periodic.c:204) --------------------------------------
+    def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None):
+        """Periodic PM long-range force of the particles uploaded last; returns GravPM[n,3] in upload order.
+        greens: a name for all pairs or a D x D nested list indexed [source][target] like GreensFxns[nA][nB]."""
+        D = self.D
+        pp = PMParams()
+        pp.pmgrid, pp.boxsize, pp.G = int(pmgrid), float(boxsize), float(G)
+        pp.asmth = float(1.25 * boxsize / pmgrid if asmth is None else asmth)      # ASMTH = 1.25 (allvars.h:82)
+        for a in range(D):
+            for b in range(D):
+                name = greens if isinstance(greens, str) else greens[a][b]
+                pp.greens_id[a * D + b] = GREENS[name]
+                pp.greens_par[a * D + b] = 0.0 if greens_par is None else float(np.asarray(greens_par).reshape(D, D)[a, b])
+        self._chk(self.lib.g2gpu_pm_periodic(self.ctx, C.byref(pp)))
+        out = np.zeros((self.n, 3), dtype=np.float32)
+        self._chk(self.lib.g2gpu_download_gravpm(self.ctx, _p(out)))
+        return out
+
     def timings(self):
         ms = np.zeros(8)
         cnt = np.zeros(8, dtype=np.int64)
         self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
-        return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6],
+        return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6], pm_ms=ms[7],
                     launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]))
 
     def reset_counters(self):

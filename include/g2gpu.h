@@ -56,6 +56,16 @@ enum g2gpu_law
   G2GPU_SPLINE_SOURCEBARYONBAM = 21	/* sourcebaryonbam_spline() ngravs.c:616 */
 };
 
+/* k-space Green's functions of the periodic PM force shipped in ngravs.c (GreensFxns[source][target], allvars.h:140; mesh units). */
+enum g2gpu_greens
+{
+  G2GPU_GREENS_NONE = 0,	/* none()      ngravs.c:344 */
+  G2GPU_GREENS_NEWTON = 1,	/* pgdelta()   ngravs.c:390: 1/k^2 */
+  G2GPU_GREENS_NEG_NEWTON = 2,	/* neg_pgdelta() ngravs.c:407 */
+  G2GPU_GREENS_YUKAWA = 3,	/* pgyukawa()  ngravs.c:869, param = YUKAWA_IMASS/(2 pi) */
+  G2GPU_GREENS_COLOYUK = 4	/* pgcoloyuk() ngravs.c:831 */
+};
+
 /* Compile-time switches of the reference (Makefile.reference:49-135) become run-time configuration. */
 typedef struct g2gpu_config
 {
@@ -85,6 +95,18 @@ typedef struct g2gpu_walk_params
   double pos_fac_post_g;	/* added as fac*Pos after the G scaling  (gravtree.c:346-358), normally 0 */
   int use_gravpm;		/* OldAcc includes GravPM/G (gravtree.c:321-325) */
 } g2gpu_walk_params;
+
+/* Parameters of the periodic PM long-range force: PMGRID, the fields of `All` pmforce_periodic() reads (pm_periodic.c:204-237) and
+ * the k-space Green's function of every ORDERED species pair, indexed [source * D + target] like GreensFxns[nA][nB] (:512). */
+typedef struct g2gpu_pm_params
+{
+  int pmgrid;			/* PMGRID (mesh cells per dimension) */
+  double boxsize;		/* All.BoxSize */
+  double asmth;			/* All.Asmth[0] = ASMTH * BoxSize / PMGRID (pm_periodic.c:59) */
+  double G;			/* All.G */
+  int greens_id[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	/* enum g2gpu_greens */
+  double greens_par[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+} g2gpu_pm_params;
 
 typedef struct g2gpu_ctx g2gpu_ctx;
 
@@ -168,6 +190,14 @@ int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
  * force the tree walk approximates; periodic boxes take the nearest image (no lattice correction). */
 int g2gpu_direct(g2gpu_ctx *ctx, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 
+/* ---- periodic PM long-range force: pmforce_periodic (pm_periodic.c:204-790), the caller of which is long_range_force
+ *      (longrange.c:56-141; accel.c:36 runs it BEFORE gravity_tree).  Works on the particle records uploaded last, in UPLOAD
+ *      order (no g2gpu_domain needed): CIC assignment per species, FFT, per-pair Green's function x Gaussian filter x CIC
+ *      deconvolution, inverse FFT, 4-point differences, CIC interpolation; FP64 meshes.  The result also becomes the GravPM input
+ *      of the next g2gpu_domain/g2gpu_walk (walk_params.use_gravpm), as if it had been passed to g2gpu_upload. ---- */
+int g2gpu_pm_periodic(g2gpu_ctx *ctx, const g2gpu_pm_params *pp);
+int g2gpu_download_gravpm(g2gpu_ctx *ctx, float *gravpm);	/* P[].GravPM, n x 3, upload order */
+
 /* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT
  * particle order; only entries of active particles of this rank's slice are written. */
 int g2gpu_download_acc(g2gpu_ctx *ctx, float *acc, float *cost, float *oldacc);
@@ -183,7 +213,7 @@ int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
 
 /* ---- instrumentation ---- */
 /* CUDA-event times (ms) of the last call of each stage: [0] domain [1] treebuild [2] walk
- * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H; counters[0] = kernel launches since
+ * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H [7] g2gpu_pm_periodic; counters[0] = kernel launches since
  * g2gpu_reset_counters, [1] = sum of GravCost of the last walk (this rank's targets), [2] = cell visits summed
  * over warps, [3] = species terms evaluated (one per particle interaction, <= D per node interaction), [4] = opening decisions
  * (node visits summed over the targets that were awake at the visit), [5..7] reserved (0). */

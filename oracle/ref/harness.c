@@ -499,3 +499,28 @@ void do_box_wrapping(void)	/* predict.c:106 is outside the closure; the oracle i
 #endif
 size_t my_fread(void *ptr, size_t size, size_t nmemb, FILE * stream) { return fread(ptr, size, nmemb, stream); }
 size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE * stream) { return fwrite(ptr, size, nmemb, stream); }
+
+/* ---- periodic PM long-range force (pm_periodic.c:204-790), single rank through the rfftwnd_mpi stand-in ----
+ * P[] must be in the order domain_Decomposition() left it (species blocks, NgravLocal[] set: pm_periodic.c:251-254).
+ * out: GravPM of every particle (n x 3, as double), in the current order of P[]. */
+int g2ref_pmforce(double *out)
+{
+#if defined(PMGRID) && defined(PERIODIC)
+  static int pm_ready = 0;
+  int i, k;
+  if(!pm_ready)
+    {
+      pm_init_periodic();	/* pm_periodic.c:53 */
+      pm_ready = 1;
+    }
+  pmforce_periodic();		/* frees and re-allocates the tree storage like the reference does */
+  TreeReconstructFlag = 1;
+  for(i = 0; i < NumPart; i++)
+    for(k = 0; k < 3; k++)
+      out[3 * i + k] = P[i].GravPM[k];
+  return 0;
+#else
+  (void) out;
+  return -1;
+#endif
+}

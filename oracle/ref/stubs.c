@@ -133,3 +133,104 @@ void fftw_one(fftw_plan p, fftw_complex *in, fftw_complex *out)
   free(a);
   free(w);
 }
+
+/* ---- FFTW-2 MPI real 3-D transforms, single rank (pm_periodic.c:65-73, 465, 531) ---- */
+#include "rfftw_mpi_stub.h"
+rfftwnd_mpi_plan rfftw3d_mpi_create_plan(MPI_Comm comm, int nx, int ny, int nz, int dir, int flags)
+{
+  rfftwnd_mpi_plan p = malloc(sizeof(*p));
+  (void) comm; (void) flags;
+  if((nx & (nx - 1)) || (ny & (ny - 1)) || (nz & (nz - 1)))
+    { fprintf(stderr, "g2ref: the rfftwnd_mpi stand-in needs power-of-two mesh sizes\n"); abort(); }
+  p->nx = nx; p->ny = ny; p->nz = nz; p->dir = dir;
+  return p;
+}
+void rfftwnd_mpi_destroy_plan(rfftwnd_mpi_plan p) { free(p); }
+void rfftwnd_mpi_local_sizes(rfftwnd_mpi_plan p, int *local_nx, int *local_x_start, int *local_ny_after_transpose,
+			     int *local_y_start_after_transpose, int *total_local_size)
+{
+  *local_nx = p->nx; *local_x_start = 0; *local_ny_after_transpose = p->ny; *local_y_start_after_transpose = 0;
+  *total_local_size = p->nx * p->ny * 2 * (p->nz / 2 + 1);
+}
+
+/* in-place 3-D complex DFT of c[x][y][z], unnormalised */
+static void fft3(cpx *c, int nx, int ny, int nz, int dir)
+{
+  int x, y, z, nmax = nx > ny ? nx : ny;
+  cpx *line = malloc(sizeof(cpx) * nmax);
+  for(x = 0; x < nx; x++)
+    for(y = 0; y < ny; y++)
+      fft_pow2(c + ((size_t) x * ny + y) * nz, nz, dir);
+  for(x = 0; x < nx; x++)
+    for(z = 0; z < nz; z++)
+      {
+	for(y = 0; y < ny; y++) line[y] = c[((size_t) x * ny + y) * nz + z];
+	fft_pow2(line, ny, dir);
+	for(y = 0; y < ny; y++) c[((size_t) x * ny + y) * nz + z] = line[y];
+      }
+  for(y = 0; y < ny; y++)
+    for(z = 0; z < nz; z++)
+      {
+	for(x = 0; x < nx; x++) line[x] = c[((size_t) x * ny + y) * nz + z];
+	fft_pow2(line, nx, dir);
+	for(x = 0; x < nx; x++) c[((size_t) x * ny + y) * nz + z] = line[x];
+      }
+  free(line);
+}
+
+void rfftwnd_mpi(rfftwnd_mpi_plan p, int n_fields, fftw_real *data, fftw_real *work, fftwnd_mpi_output_order order)
+{
+  const int nx = p->nx, ny = p->ny, nz = p->nz, nzh = nz / 2 + 1, nz2 = 2 * nzh;
+  int x, y, z;
+  cpx *c = malloc(sizeof(cpx) * (size_t) nx * ny * nz);
+  fftw_complex *cd = (fftw_complex *) data;
+  (void) work;
+  if(n_fields != 1 || order != FFTW_TRANSPOSED_ORDER)
+    { fprintf(stderr, "g2ref: rfftwnd_mpi stand-in: unsupported call\n"); abort(); }
+  if(p->dir == FFTW_REAL_TO_COMPLEX)
+    {
+      for(x = 0; x < nx; x++)
+	for(y = 0; y < ny; y++)
+	  for(z = 0; z < nz; z++)
+	    {
+	      c[((size_t) x * ny + y) * nz + z].re = data[((size_t) x * ny + y) * nz2 + z];
+	      c[((size_t) x * ny + y) * nz + z].im = 0.0;
+	    }
+      fft3(c, nx, ny, nz, -1);
+      for(y = 0; y < ny; y++)
+	for(x = 0; x < nx; x++)
+	  for(z = 0; z < nzh; z++)
+	    {
+	      cd[((size_t) y * nx + x) * nzh + z].re = c[((size_t) x * ny + y) * nz + z].re;
+	      cd[((size_t) y * nx + x) * nzh + z].im = c[((size_t) x * ny + y) * nz + z].im;
+	    }
+    }
+  else
+    {
+      /* rebuild the full spectrum from the stored half (Hermitian symmetry of a real field) */
+      for(x = 0; x < nx; x++)
+	for(y = 0; y < ny; y++)
+	  for(z = 0; z < nz; z++)
+	    {
+	      cpx v;
+	      if(z < nzh)
+		{
+		  v.re = cd[((size_t) y * nx + x) * nzh + z].re;
+		  v.im = cd[((size_t) y * nx + x) * nzh + z].im;
+		}
+	      else
+		{
+		  int xm = (nx - x) % nx, ym = (ny - y) % ny, zm = nz - z;
+		  v.re = cd[((size_t) ym * nx + xm) * nzh + zm].re;
+		  v.im = -cd[((size_t) ym * nx + xm) * nzh + zm].im;
+		}
+	      c[((size_t) x * ny + y) * nz + z] = v;
+	    }
+      fft3(c, nx, ny, nz, +1);
+      for(x = 0; x < nx; x++)
+	for(y = 0; y < ny; y++)
+	  for(z = 0; z < nz; z++)
+	    data[((size_t) x * ny + y) * nz2 + z] = c[((size_t) x * ny + y) * nz + z].re;
+    }
+  free(c);
+}

@@ -1,0 +1,1 @@
+#include "rfftw_mpi_stub.h"

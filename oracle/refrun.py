@@ -159,6 +159,14 @@ class RefOracle:
         self.lib.g2ref_get_particles(*(a.ctypes.data_as(C.c_void_p) for a in (pos, mass, ptype, pid, acc, cost, oldacc)))
         return dict(pos=pos, mass=mass, type=ptype, id=pid, acc=acc, cost=cost, oldacc=oldacc)
 
+    def pmforce(self):
+        """GravPM of every particle in the current order of P[] (pmforce_periodic, pm_periodic.c:204); PM variants only."""
+        out = np.zeros((self.n, 3))
+        rc = self.lib.g2ref_pmforce(out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("this oracle variant was compiled without PMGRID/PERIODIC")
+        return out
+
     def topnodes(self):
         nt = self.lib.g2ref_ntopnodes()
         nl = self.lib.g2ref_ntopleaves()

@@ -30,6 +30,7 @@ def test_struct_layouts_match_header():
     import g2gpu
     assert C.sizeof(g2gpu.Config) == 10 * 4
     assert C.sizeof(g2gpu.WalkParams) == 8 * 8 + 8
+    assert C.sizeof(g2gpu.PMParams) == 8 + 3 * 8 + 36 * 4 + 36 * 8
 
 
 def test_no_cpu_fallback_without_device():

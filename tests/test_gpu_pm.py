@@ -1,0 +1,105 @@
+"""GPU: periodic PM long-range force (g2gpu_pm_periodic, csrc/g2_pm.cu) against the unmodified reference's pmforce_periodic
+(pm_periodic.c:204-790; committed fixtures tests/golden/pm_*.npz and, where oracle/_ref travelled, a fresh run of it) and
+against the pinned numpy restatement oracle/pm_port.py at the full 256^3 mesh.
+
+Tolerance (floating point; the mesh arithmetic is FP64 on both sides, the result a FLOAT): every component within 1e-5 of the
+largest |GravPM| component, median relative error per particle <= 1e-5.  The GPU sums the species-pair contributions in k-space
+and rounds to FLOAT once, the reference rounds P[].GravPM after every pair (pm_periodic.c:780)."""
+import os
+
+import numpy as np
+import pytest
+
+import g2test
+import pm_port
+from refrun import RefOracle, available
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ABS_TOL = 1.0e-5       # of max |GravPM| component
+MEDIAN_TOL = 1.0e-5
+
+
+def gpu_pm(pos, mass, ptype, grav, D, pmgrid, box, G=1.0, **kw):
+    from g2gpu import TreeGravity
+    n = len(mass)
+    tg = TreeGravity(max_part=n + 64, n_gravs=D, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(grav, g2test.force_softening((1.0,) * 6))
+    tg.upload(pos, mass, ptype)
+    pm = tg.pm_periodic(pmgrid, box, G=G, **kw)
+    t = tg.timings()
+    tg.close()
+    return pm, t
+
+
+def check(pm, ref):
+    scale = np.abs(ref).max()
+    assert np.isfinite(pm).all()
+    assert np.abs(pm - ref).max() <= ABS_TOL * scale, np.abs(pm - ref).max() / scale
+    assert np.median(g2test.rel_err(pm, ref)) <= MEDIAN_TOL
+
+
+@pytest.mark.parametrize("case,D", [("pm_pm64_d2_poisson4096", 2), ("pm_pm64_d4_poisson4096", 4)])
+def test_pm_matches_reference_fixture(case, D):
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    pm, _ = gpu_pm(g["pos"], g["mass"], g["type"], g["grav"], D, int(g["pmgrid"]), float(g["box"]), float(g["G"]))
+    check(pm, g["gravpm"])
+    # upload order must not matter (the reference needs species blocks, the device version does not)
+    perm = np.random.default_rng(3).permutation(len(g["mass"]))
+    pm2, _ = gpu_pm(g["pos"][perm], g["mass"][perm], g["type"][perm], g["grav"], D, int(g["pmgrid"]), float(g["box"]), float(g["G"]))
+    check(pm2, g["gravpm"][perm])
+
+
+def test_pm_matches_reference_run_d3():
+    if not available("pm64_d3_f32"):
+        pytest.skip("oracle/_ref not built")
+    n, box = 20000, 80000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=11, ntypes=6)
+    grav = (0, 1, 2, 1, 2, 1)
+    ref = RefOracle("pm64_d3_f32", int(1.1 * n) + 64, boxsize=box, softening=(50.0,) * 6, gravity=grav, G=43007.1)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    rpm = ref.pmforce().astype(np.float32)
+    rp = ref.particles()
+    pm, _ = gpu_pm(rp["pos"].astype(np.float32), rp["mass"].astype(np.float32), rp["type"], grav, 3, 64, box, G=43007.1)
+    check(pm, rpm)
+
+
+def test_pm_full_mesh_256_against_port(outdir):
+    """BASELINE config 3 mesh (PMGRID = 256) with 2^18 particles on two species; the numpy port is the checker."""
+    n, box, N = 262144, 100000.0, 256
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=21)
+    species = np.asarray(g2test.GRAV_D2)[ptype]
+    port = pm_port.pm_force(pos, mass, species, 2, N, box, 1.0, 1.25 * box / N)
+    pm, t = gpu_pm(pos, mass, ptype, g2test.GRAV_D2, 2, N, box)
+    check(pm, port)
+    tot = (mass[:, None].astype(np.float64) * pm).sum(axis=0)
+    assert np.abs(tot).max() <= 1e-4 * np.abs(mass[:, None] * pm).sum()       # momentum conservation
+    print(f"PM 256^3, {n} particles: {t['pm_ms']:.3f} ms")
+
+
+def test_pm_yukawa_greens_and_none():
+    """Per-pair Green's functions: Yukawa between the species, nothing within species 1 (GreensFxns wiring of ngravs.c:260-275)."""
+    n, box, N = 5000, 1000.0, 64
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=4)
+    species = np.asarray(g2test.GRAV_D2)[ptype]
+    ym = 60.0 / (2 * np.pi)                     # YUKAWA_IMASS / (2 pi), ngravs.c:41-43, 871
+    asmth = 1.25 * box / N
+    asmth2 = ((2 * np.pi) * asmth / box) ** 2
+    names = [["pgdelta", "pgyukawa"], ["pgyukawa", "none"]]
+
+    def greens(a, b, k2):
+        with np.errstate(divide="ignore"):
+            return {"pgdelta": 1.0 / k2, "pgyukawa": 1.0 / (k2 + ym * ym) * np.exp(-ym * ym * asmth2), "none": np.zeros_like(k2)}[names[a][b]]
+    port = pm_port.pm_force(pos, mass, species, 2, N, box, 1.0, asmth, greens=greens)
+    pm, _ = gpu_pm(pos, mass, ptype, g2test.GRAV_D2, 2, N, box, greens=names, greens_par=[[0, ym], [ym, 0]])
+    check(pm, port)
+
+
+def test_pm_requires_upload():
+    from g2gpu import TreeGravity, G2Error
+    tg = TreeGravity(max_part=100, n_gravs=2, periodic=True, shortrange=True)
+    with pytest.raises(G2Error):
+        tg.pm_periodic(64, 100.0)
+    tg.close()
