@@ -361,6 +361,31 @@ def main():
         e2e = {"value": n / (e_ms / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / K,
                "checksum": float(np.abs(acc_e).sum())}
 
+    # ---- the long-range complement of the TreePM split (pmforce_periodic on the device); reported beside the tree numbers, not part
+    # of the step.  Device time from the library's own events around the PM stage, inputs resident (uploaded once).
+    pm = None
+    if world == 1 and w["shortrange"] and not args.profile and active is None:
+        # P[] is in Peano-Hilbert order when the reference runs its PM step (domain_Decomposition precedes it, domain.c:65-72)
+        tg.upload(w["pos"][perm0], w["mass"][perm0], w["ptype"][perm0])
+        for _ in range(2):
+            tg.pm_device(w["pmgrid"], w["box"])
+        pm_ms = 0.0
+        for _ in range(K):
+            flush.zero_()
+            torch.cuda.synchronize()
+            tg.pm_device(w["pmgrid"], w["box"])
+            pm_ms += tg.timings()["pm_ms"]
+        pm_ms /= K
+        N3, D = float(w["pmgrid"]) ** 3, w["D"]
+        # algorithmic bytes of one call: per species a mesh clear + 8 FP64 read-modify-writes per particle + one real
+        # and one half-complex mesh pass per transform; per target species the D+1 spectra of the filter; 32 B read per particle in
+        # deposit and gather, 12 B written, 56 distinct FP64 potential values gathered
+        pm_bytes = D * 8 * N3 + n * (32 + 8 * 16) + 2 * D * (8 * N3 + 8 * N3) + D * (D + 1) * 8 * N3 + n * (32 + 12 + 56 * 8)
+        hbm = (measured_peaks() or {}).get("hbm_gbs", 6650.0)
+        pm = {"kernel": "pm_deposit/cuFFT D2Z/pm_filter/cuFFT Z2D/pm_gather", "pmgrid": w["pmgrid"], "ms_per_call": pm_ms, "particle_order": "species-major Peano-Hilbert (as after domain_Decomposition)",
+              "particles_per_s": n / (pm_ms * 1e-3), "bound": "hbm", "algorithmic_bytes": pm_bytes,
+              "achieved": pm_bytes / (pm_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": pm_bytes / (pm_ms * 1e-3) / 1e9 / hbm}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -423,6 +448,8 @@ def main():
             "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline, "roofline_sort": roofline_sort}
     if e2e is not None:
         line["e2e"] = e2e
+    if pm is not None:
+        line["pm_long_range"] = pm
     if world == 1 and not args.no_cpu_baseline and not args.profile and active is None:
         try:
             r = reference_run(w, oldacc_by_id, 1, 0)

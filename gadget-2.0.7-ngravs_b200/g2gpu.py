@@ -276,7 +276,7 @@ class TreeGravity:
         self.n = int(n)
 
     # ---- long_range_force -> pmforce_periodic (longrange.c:56, pm_periodic.c:204) --------------------------------------
-    def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None):
+    def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None, download=True):
         """Periodic PM long-range force of the particles uploaded last; returns GravPM[n,3] in upload order.
         greens: a name for all pairs or a D x D nested list indexed [source][target] like GreensFxns[nA][nB]."""
         D = self.D
@@ -289,9 +289,15 @@ class TreeGravity:
                 pp.greens_id[a * D + b] = GREENS[name]
                 pp.greens_par[a * D + b] = 0.0 if greens_par is None else float(np.asarray(greens_par).reshape(D, D)[a, b])
         self._chk(self.lib.g2gpu_pm_periodic(self.ctx, C.byref(pp)))
+        if not download:
+            return None
         out = np.zeros((self.n, 3), dtype=np.float32)
         self._chk(self.lib.g2gpu_download_gravpm(self.ctx, _p(out)))
         return out
+
+    def pm_device(self, pmgrid, boxsize, **kw):
+        """pm_periodic without the device->host copy: GravPM stays on the device as the input of the next domain()/walk()."""
+        return self.pm_periodic(pmgrid, boxsize, download=False, **kw)
 
     def timings(self):
         ms = np.zeros(8)

@@ -6,6 +6,8 @@
  *   forcetree.c: force_treeallocate (3176), force_treefree (3411), force_treebuild (61),
  *                force_treeevaluate (1244), force_treeevaluate_shortrange (1623)
  *   peano.c    : peano_hilbert_key (356), peano_hilbert_order (36), compare_key (190)
+ *   pm_periodic.c (PMGRID && PERIODIC, unless -DG2_SHIM_KEEP_REFERENCE_PM): pm_init_periodic (53), pm_init_periodic_allocate (139),
+ *                pm_init_periodic_free (187), pmforce_periodic (204); pmpotential_periodic (800) is not provided and ends the run
  * so that accel.c, domain.c, init.c, run.c, ... call it unchanged.
  * All state stays in the reference's globals (P[], All, NumPart, TreeReconstructFlag, ...).  Errors of the GPU
  * library end the run through endrun() like the reference's own failures (endrun.c:24).  There is no CPU
@@ -290,6 +292,94 @@ void force_treefree(void)	/* forcetree.c:3411 */
   free(Extnodes_base);
   free(Nodes_base);
 }
+
+/* ---------------------------------------------------------------- pm_periodic.c ----------------------------- */
+#if defined(PMGRID) && defined(PERIODIC) && !defined(G2_SHIM_KEEP_REFERENCE_PM)
+static int g2_greens_id(gravity f)
+{
+  if(f == none) return G2GPU_GREENS_NONE;
+  if(f == pgdelta) return G2GPU_GREENS_NEWTON;
+  if(f == neg_pgdelta) return G2GPU_GREENS_NEG_NEWTON;
+  if(f == pgyukawa) return G2GPU_GREENS_YUKAWA;
+  if(f == pgcoloyuk) return G2GPU_GREENS_COLOYUK;
+  return -1;
+}
+
+void pm_init_periodic(void)	/* pm_periodic.c:53: no FFTW plans or slab tables to set up, cuFFT plans are made on first use */
+{
+  All.Asmth[0] = ASMTH * All.BoxSize / PMGRID;
+  All.Rcut[0] = RCUT * All.Asmth[0];
+}
+
+void pm_init_periodic_allocate(int dimprod) { (void) dimprod; }	/* the meshes live on the device */
+void pm_init_periodic_free(void) { }
+
+/* pm_periodic.c:204.  long_range_force() (longrange.c:56) calls it before gravity_tree() (accel.c:36-46) with P[] in whatever
+ * order the last domain decomposition left; the device version does not need species blocks, so P[] is uploaded as it is and
+ * P[].GravPM is read back in the same order. */
+void pmforce_periodic(void)
+{
+  g2gpu_pm_params pp;
+  float *gpm;
+  int i, nA, nB;
+
+  if(ThisTask == 0)
+    {
+      printf("Starting periodic PM calculation.\n");
+      fflush(stdout);
+    }
+  if(!G2)
+    {
+      printf("g2gpu: pmforce_periodic() before force_treeallocate()\n");
+      endrun(7311);
+    }
+  memset(&pp, 0, sizeof(pp));
+  pp.pmgrid = PMGRID;
+  pp.boxsize = All.BoxSize;
+  pp.asmth = All.Asmth[0];
+  pp.G = All.G;
+  for(nA = 0; nA < N_GRAVS; nA++)
+    for(nB = 0; nB < N_GRAVS; nB++)
+      {
+	int id = g2_greens_id(GreensFxns[nA][nB]);
+	if(id < 0)
+	  {
+	    printf("ngravs/g2gpu: GreensFxns[%d][%d] has no device implementation.\n"
+		   "Register it in include/g2gpu.h (enum g2gpu_greens) and csrc/g2_pm.cu.\n", nA, nB);
+	    endrun(7312);
+	  }
+	pp.greens_id[nA * N_GRAVS + nB] = id;
+	pp.greens_par[nA * N_GRAVS + nB] = YUKAWA_IMASS / (2 * M_PI);	/* ngravs.c:871 */
+      }
+  g2_push_tables();
+  g2_upload(NumPart);
+  g2_check(g2gpu_pm_periodic(G2, &pp), "pm_periodic");
+  gpm = malloc(sizeof(float) * 3 * (size_t) NumPart);
+  g2_check(g2gpu_download_gravpm(G2, gpm), "download_gravpm");
+  for(i = 0; i < NumPart; i++)
+    {
+      P[i].GravPM[0] = gpm[3 * i + 0];
+      P[i].GravPM[1] = gpm[3 * i + 1];
+      P[i].GravPM[2] = gpm[3 * i + 2];
+    }
+  free(gpm);
+  /* the reference frees and re-allocates the tree storage around the PM step and therefore asks for a new domain decomposition
+   * (pm_periodic.c:232, 781-783); the request is kept so that the sequence of decompositions and tree builds of a run is unchanged */
+  All.NumForcesSinceLastDomainDecomp = 1 + All.TotNumPart * All.TreeDomainUpdateFrequency;
+  TreeReconstructFlag = 1;
+  if(ThisTask == 0)
+    {
+      printf("done PM.\n");
+      fflush(stdout);
+    }
+}
+
+void pmpotential_periodic(void)	/* pm_periodic.c:800, outside the replaced path */
+{
+  printf("g2gpu: pmpotential_periodic() is not provided by the shim; build with -DG2_SHIM_KEEP_REFERENCE_PM and FFTW-2 to use it.\n");
+  endrun(7313);
+}
+#endif
 
 /* copies the device tree into the reference's host layout (struct NODE after the moment pass, allvars.h:618-660) */
 static void g2_refresh_mirror(int npart)

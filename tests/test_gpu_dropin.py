@@ -79,3 +79,32 @@ def test_reference_call_chain_runs_on_the_gpu(variant, outdir, monkeypatch):
     for e in (e1, e2):
         assert np.median(e) <= 1e-5 and np.percentile(e, 99.9) <= 1e-3
     assert (rc != sc).sum() <= 0.002 * n
+
+
+def test_reference_pm_call_runs_on_the_gpu(outdir):
+    """pm_init_periodic() + pmforce_periodic() of the shim (device PM) against the unmodified pm_periodic.c, then the reference's own
+    gravity_tree() on top of it: OldAcc contains GravPM/G (gravtree.c:318-331) on both sides."""
+    variant = "pm64_d2_f32"
+    if not (available(variant) and available(variant, "g2shim")):
+        pytest.skip("oracle/_ref (reference and shim builds) not present")
+    _preload()
+    n, box = 32768, 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=17)
+    kw = dict(boxsize=box, softening=(box / 32 / 30.0,) * 6, gravity=g2test.GRAV_D2, G=43007.1)
+    ref = RefOracle(variant, int(1.1 * n) + 64, **kw)
+    shim = RefOracle(variant, int(1.1 * n) + 64, prefix="g2shim", **kw)
+    out = {}
+    for name, o in (("ref", ref), ("shim", shim)):
+        o.load(pos, mass, ptype)
+        o.domain()
+        pm = o.pmforce()
+        o.gravity()
+        p = o.particles()
+        gp = np.zeros((n, 3)); gp[p["id"]] = pm
+        old = np.zeros(n); old[p["id"]] = p["oldacc"]
+        out[name] = (gp, old)
+    scale = np.abs(out["ref"][0]).max()
+    assert np.abs(out["shim"][0] - out["ref"][0]).max() <= 1e-5 * scale
+    assert np.median(g2test.rel_err(out["shim"][0], out["ref"][0])) <= 1e-5
+    rel = np.abs(out["shim"][1] - out["ref"][1]) / np.maximum(out["ref"][1], 1e-30)
+    assert np.median(rel) <= 1e-5 and np.percentile(rel, 99.9) <= 1e-3

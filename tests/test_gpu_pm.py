@@ -103,3 +103,36 @@ def test_pm_requires_upload():
     with pytest.raises(G2Error):
         tg.pm_periodic(64, 100.0)
     tg.close()
+
+
+def test_treepm_total_force_against_ewald(outdir):
+    """Tree short-range walk + PM long-range force = the complete TreePM force (what gravity_forcetest writes as GravAccel + GravPM,
+    gravtree_forcetest.c:304-310), against exact Ewald sums for 32 targets.  32^3 particles on a 64^3 mesh: the particles-per-mesh-
+    cell density of BASELINE config 3.  The TreePM scheme itself (ASMTH 1.25, RCUT 4.5, CIC mesh) is accurate to about a per cent."""
+    from g2gpu import TreeGravity
+    PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gadget-2.0.7-ngravs_b200")
+    n, box, N = 32768, 100000.0, 64
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=31)
+    eps = box / 32 / 30.0
+    tg = TreeGravity(max_part=n + 64, n_gravs=2, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening((eps,) * 6))
+    tg.set_laws()
+    tab = np.load(os.path.join(PKG, "data", "srtable_newton_ntab2048.npy"))
+    tg.set_srtable(np.broadcast_to(tab, (2, 2, len(tab))).copy())
+    asmth = 1.25 * box / N
+    tg.upload(pos, mass, ptype)
+    pm = tg.pm_periodic(N, box, G=1.0)
+    acc, cost, old, perm = tg.gravity_tree(pos, mass, ptype, tg.walk_params(theta=0.3, errtol=0.005, boxsize=box, G=1.0, asmth=asmth, rcut=4.5 * asmth))
+    tree = np.zeros_like(acc)
+    tree[perm] = acc
+    tg.close()
+    targets = np.random.default_rng(2).choice(n, 32, replace=False)
+    exact = g2test.ewald_direct(pos, mass, targets, box)
+    total = tree[targets].astype(np.float64) + pm[targets]
+    err = np.linalg.norm(total - exact, axis=1) / np.linalg.norm(exact, axis=1)
+    err_tree_only = np.linalg.norm(tree[targets] - exact, axis=1) / np.linalg.norm(exact, axis=1)
+    with open(os.path.join(outdir, "treepm_vs_ewald.txt"), "w") as f:
+        f.write(f"TreePM (tree + PM) vs Ewald: median {np.median(err):.3e} max {err.max():.3e}; tree alone: median {np.median(err_tree_only):.3e}\n")
+    print(f"TreePM vs Ewald: median {np.median(err):.3e} max {err.max():.3e}; tree alone median {np.median(err_tree_only):.3e}")
+    assert np.median(err) <= 1e-2 and err.max() <= 8e-2
+    assert np.median(err_tree_only) > 5 * np.median(err)          # the long-range part matters

@@ -17,7 +17,7 @@ PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 def _run(mode, pos, mass, ptype, D, grav, soft, periodic, sr, unequal, box, pmgrid, theta, oldacc=None, acc_double=1):
     from g2gpu import TreeGravity
     n = len(mass)
-    tg = TreeGravity(max_part=int(1.1 * n) + 64, n_gravs=D, periodic=periodic, shortrange=sr, unequal_softenings=unequal)
+    tg = TreeGravity(max_part=max(int(1.1 * n) + 64, 2000), n_gravs=D, periodic=periodic, shortrange=sr, unequal_softenings=unequal)
     tg.set_option("walk_mode", mode)
     tg.set_option("acc_double", acc_double)
     tg.set_species(grav, g2test.force_softening(soft))
