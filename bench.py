@@ -377,10 +377,11 @@ def main():
             pm_ms += tg.timings()["pm_ms"]
         pm_ms /= K
         N3, D = float(w["pmgrid"]) ** 3, w["D"]
-        # algorithmic bytes of one call: per species a mesh clear + 8 FP64 read-modify-writes per particle + one real
-        # and one half-complex mesh pass per transform; per target species the D+1 spectra of the filter; 32 B read per particle in
-        # deposit and gather, 12 B written, 56 distinct FP64 potential values gathered
-        pm_bytes = D * 8 * N3 + n * (32 + 8 * 16) + 2 * D * (8 * N3 + 8 * N3) + D * (D + 1) * 8 * N3 + n * (32 + 12 + 56 * 8)
+        # algorithmic DRAM bytes of one call, every mesh touched the minimum number of times: clear (8 N^3 per species),
+        # deposit (32 B per particle + one read-modify-write of the mesh), forward transform (8 N^3 in, 8 N^3 out per species), filter
+        # (D + 1 spectra of 8 N^3 per target species), inverse transform (8 N^3 + 8 N^3), gather (32 B read + 12 B written per particle +
+        # the potential mesh once).  The 56 potential values a particle gathers are served by L1/L2 and not counted.
+        pm_bytes = D * 8 * N3 + n * 32 + D * 16 * N3 + D * 16 * N3 + D * (D + 1) * 8 * N3 + D * 16 * N3 + n * 44 + D * 8 * N3
         hbm = (measured_peaks() or {}).get("hbm_gbs", 6650.0)
         pm = {"kernel": "pm_deposit/cuFFT D2Z/pm_filter/cuFFT Z2D/pm_gather", "pmgrid": w["pmgrid"], "ms_per_call": pm_ms, "particle_order": "species-major Peano-Hilbert (as after domain_Decomposition)",
               "particles_per_s": n / (pm_ms * 1e-3), "bound": "hbm", "algorithmic_bytes": pm_bytes,

@@ -204,7 +204,9 @@ struct g2gpu_ctx
 
   // periodic PM long-range force (g2_pm.cu)
   int pm_grid, pm_fwd, pm_inv, pm_plans_valid, pm_done;	// mesh size the buffers/plans were made for; cuFFT handles
-  void *pm_rho, *pm_rk, *pm_potk;	// real mesh (density, then potential), D spectra, filtered spectrum of one target species
+  void *pm_rho, *pm_rk, *pm_potk, *pm_tab;
+  double pm_tab_asmth2;
+  int pm_tab_n;	// real mesh (density, then potential), D spectra, filtered spectrum of one target species
 
   void *h_stage;		// pinned upload staging
   size_t h_stage_bytes;

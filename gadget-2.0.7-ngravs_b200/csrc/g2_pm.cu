@@ -36,21 +36,21 @@ __device__ __forceinline__ void pm_cell(const PMArgs &A, float pos, int &slab, d
   d = (double) __fsub_rn(u, (float) slab);
 }
 
-__global__ void __launch_bounds__(256) pm_deposit_kernel(PMArgs A, int nA, double *__restrict__ rho)
+// one pass over the particles: every particle adds its mass to the mesh of its own species (mesh g at rho + g * N^3)
+__global__ void __launch_bounds__(256) pm_deposit_kernel(PMArgs A, double *__restrict__ rho_all)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= A.n)
     return;
   const G2PRec p = A.rec[i];
-  if((int) ((A.t2g_packed >> (4 * p.type)) & 7u) != nA)
-    return;
+  double *__restrict__ rho = rho_all + (size_t) ((A.t2g_packed >> (4 * p.type)) & 7u) * A.N * A.N * A.N;
   int sx, sy, sz;
   double dx, dy, dz;
   pm_cell(A, p.x, sx, dx);
   pm_cell(A, p.y, sy, dy);
   pm_cell(A, p.z, sz, dz);
   const int N = A.N;
-  const int sxx = (sx + 1) % N, syy = (sy + 1) % N, szz = (sz + 1) % N;
+  const int sxx = sx + 1 == N ? 0 : sx + 1, syy = sy + 1 == N ? 0 : sy + 1, szz = sz + 1 == N ? 0 : sz + 1;
   const double m = (double) p.m;
 #define G2_RHO(X, Y, Z) (rho + ((size_t) (X) * N + (Y)) * N + (Z))
   // products left to right as in pm_periodic.c:312-319
@@ -84,9 +84,11 @@ __device__ __forceinline__ double pm_greens(int id, double par, double k2, doubl
     }
 }
 
+// tab[i] = exp(-k_i^2 asmth2) / sinc(pi k_i / N)^4 for mesh index i (k_i = i > N/2 ? i - N : i): the Gaussian long-range filter and the
+// twofold CIC deconvolution of pm_periodic.c:487-513 factorise over the three dimensions; the table is filled on the host in double.
 template <int D>
-__global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PMGreens Gf, const double2 *__restrict__ rk, size_t kstride,
-							 double2 *__restrict__ potk)
+__global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PMGreens Gf, const double *__restrict__ tab, const double2 *__restrict__ rk,
+							 size_t kstride, double2 *__restrict__ potk)
 {
   const int nzh = N / 2 + 1;
   const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,24 +100,7 @@ __global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PM
   double2 out = make_double2(0.0, 0.0);
   if(k2 > 0)
     {
-      double fx = 1, fy = 1, fz = 1;	// deconvolution, :491-509
-      if(kx != 0)
-	{
-	  fx = (M_PI * kx) / N;
-	  fx = sin(fx) / fx;
-	}
-      if(ky != 0)
-	{
-	  fy = (M_PI * ky) / N;
-	  fy = sin(fy) / fy;
-	}
-      if(kz != 0)
-	{
-	  fz = (M_PI * kz) / N;
-	  fz = sin(fz) / fz;
-	}
-      const double ff = 1 / (fx * fy * fz);
-      const double filt = -exp(-k2 * asmth2) * ff * ff * ff * ff;	// :513
+      const double filt = -(__ldg(tab + x) * __ldg(tab + y) * __ldg(tab + z));	// :513
 #pragma unroll
       for(int nA = 0; nA < D; nA++)
 	{
@@ -128,44 +113,58 @@ __global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PM
   potk[idx] = out;		// k = 0: zero (:525-526)
 }
 
-// finite differences (:726-737) of the potential at mesh point (x,y,z) along `dim`, without the factor `fac`
-__device__ __forceinline__ double pm_fd(const double *__restrict__ phi, int N, int x, int y, int z, int dim)
-{
-  int c = dim == 0 ? x : (dim == 1 ? y : z);
-  const int l = (c + N - 1) % N, r = (c + 1) % N, ll = (c + N - 2) % N, rr = (c + 2) % N;
-  const size_t sx = (size_t) N * N, sy = (size_t) N;
-  const size_t base = dim == 0 ? (size_t) y * sy + z : (dim == 1 ? (size_t) x * sx + z : (size_t) x * sx + (size_t) y * sy);
-  const size_t st = dim == 0 ? sx : (dim == 1 ? sy : 1);
-  return (4.0 / 3) * (__ldg(phi + base + l * st) - __ldg(phi + base + r * st)) - (1.0 / 6) * (__ldg(phi + base + ll * st) - __ldg(phi + base + rr * st));
-}
-
-__global__ void __launch_bounds__(256) pm_gather_kernel(PMArgs A, int nB, const double *__restrict__ phi, double fac, float *__restrict__ gravpm)
+// Finite differences (:726-737) + trilinear interpolation (:739-781) fused: the 4-point difference along one dimension at the 8 corners of
+// the particle's cell needs the potential at 6 mesh planes of that dimension (cell index - 2 .. + 3, periodic) and 2 x 2 of the others.
+// One pass over the particles: every particle reads the potential mesh of its own species (mesh g at phi + g * N^3).
+__global__ void __launch_bounds__(256) pm_gather_kernel(PMArgs A, const double *__restrict__ phi_all, double fac, float *__restrict__ gravpm)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= A.n)
     return;
   const G2PRec p = A.rec[i];
-  if((int) ((A.t2g_packed >> (4 * p.type)) & 7u) != nB)
-    return;
-  int sx, sy, sz;
-  double dx, dy, dz;
-  pm_cell(A, p.x, sx, dx);
-  pm_cell(A, p.y, sy, dy);
-  pm_cell(A, p.z, sz, dz);
   const int N = A.N;
-  const int sxx = (sx + 1) % N, syy = (sy + 1) % N, szz = (sz + 1) % N;
+  const double *__restrict__ phi = phi_all + (size_t) ((A.t2g_packed >> (4 * p.type)) & 7u) * N * N * N;
+  int s[3];
+  double d[3];
+  pm_cell(A, p.x, s[0], d[0]);
+  pm_cell(A, p.y, s[1], d[1]);
+  pm_cell(A, p.z, s[2], d[2]);
+  // element offsets of the 6 planes s-2 .. s+3 of every dimension (periodic wrap without integer division)
+  unsigned int off[3][6];
+  const unsigned int stride[3] = { (unsigned int) N * (unsigned int) N, (unsigned int) N, 1u };
+#pragma unroll
+  for(int dim = 0; dim < 3; dim++)
+#pragma unroll
+    for(int k = 0; k < 6; k++)
+      {
+	int c = s[dim] - 2 + k;
+	c = c < 0 ? c + N : (c >= N ? c - N : c);
+	off[dim][k] = (unsigned int) c * stride[dim];
+      }
+  const double wx[2] = { 1.0 - d[0], d[0] }, wy[2] = { 1.0 - d[1], d[1] }, wz[2] = { 1.0 - d[2], d[2] };
 #pragma unroll
   for(int dim = 0; dim < 3; dim++)
     {
-      // corner order and products as in pm_periodic.c:769-778
-      double acc = fac * pm_fd(phi, N, sx, sy, sz, dim) * (1.0 - dx) * (1.0 - dy) * (1.0 - dz);
-      acc += fac * pm_fd(phi, N, sx, syy, sz, dim) * (1.0 - dx) * dy * (1.0 - dz);
-      acc += fac * pm_fd(phi, N, sx, sy, szz, dim) * (1.0 - dx) * (1.0 - dy) * dz;
-      acc += fac * pm_fd(phi, N, sx, syy, szz, dim) * (1.0 - dx) * dy * dz;
-      acc += fac * pm_fd(phi, N, sxx, sy, sz, dim) * dx * (1.0 - dy) * (1.0 - dz);
-      acc += fac * pm_fd(phi, N, sxx, syy, sz, dim) * dx * dy * (1.0 - dz);
-      acc += fac * pm_fd(phi, N, sxx, sy, szz, dim) * dx * (1.0 - dy) * dz;
-      acc += fac * pm_fd(phi, N, sxx, syy, szz, dim) * dx * dy * dz;
+      double acc = 0.0;
+      // corner order and products as in pm_periodic.c:769-778: (x,y,z), (x,yy,z), (x,y,zz), (x,yy,zz), (xx,y,z), ...
+      const int order[8][3] = { {0, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 1, 1}, {1, 0, 0}, {1, 1, 0}, {1, 0, 1}, {1, 1, 1} };
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+	{
+	  const int a = order[q][0], b = order[q][1], cz = order[q][2];
+	  const int cc[3] = { a, b, cz };
+	  // offsets of the two other dimensions at this corner, and the four planes along `dim`
+	  unsigned int base = 0;
+#pragma unroll
+	  for(int e = 0; e < 3; e++)
+	    if(e != dim)
+	      base += off[e][2 + cc[e]];
+	  const int k0 = cc[dim];	// corner plane index is 2 + k0: l = 1 + k0, r = 3 + k0, ll = k0, rr = 4 + k0
+	  const double f = (4.0 / 3) * (__ldg(phi + base + off[dim][1 + k0]) - __ldg(phi + base + off[dim][3 + k0]))
+	    - (1.0 / 6) * (__ldg(phi + base + off[dim][k0]) - __ldg(phi + base + off[dim][4 + k0]));
+	  const double term = fac * f * wx[a] * wy[b] * wz[cz];
+	  acc = q == 0 ? term : acc + term;
+	}
       gravpm[3 * (size_t) i + dim] = (float) acc;	// P[i].GravPM is a FLOAT
     }
 }
@@ -184,6 +183,9 @@ static void pm_release(g2gpu_ctx *c)
     cudaFree(c->pm_rk);
   if(c->pm_potk)
     cudaFree(c->pm_potk);
+  if(c->pm_tab)
+    cudaFree(c->pm_tab);
+  c->pm_tab = nullptr;
   c->pm_rho = nullptr;
   c->pm_rk = nullptr;
   c->pm_potk = nullptr;
@@ -198,7 +200,7 @@ static int pm_reserve(g2gpu_ctx *c, int N)
     return 0;
   pm_release(c);
   const size_t nreal = (size_t) N * N * N, ncpx = (size_t) N * N * (N / 2 + 1);
-  if(cudaMalloc(&c->pm_rho, sizeof(double) * nreal) != cudaSuccess || cudaMalloc(&c->pm_rk, sizeof(double2) * ncpx * c->D) != cudaSuccess
+  if(cudaMalloc(&c->pm_rho, sizeof(double) * nreal * c->D) != cudaSuccess || cudaMalloc(&c->pm_tab, sizeof(double) * N) != cudaSuccess || cudaMalloc(&c->pm_rk, sizeof(double2) * ncpx * c->D) != cudaSuccess
      || cudaMalloc(&c->pm_potk, sizeof(double2) * ncpx) != cudaSuccess)
     {
       pm_release(c);
@@ -229,7 +231,8 @@ template <int D>
 static void launch_filter(g2gpu_ctx *c, int N, double asmth2, const PMGreens &Gf)
 {
   const size_t ncpx = (size_t) N * N * (N / 2 + 1);
-  pm_filter_kernel<D><<<g2_cdiv((long long) ncpx, 256), 256, 0, c->stream>>>(N, asmth2, Gf, (const double2 *) c->pm_rk, ncpx, (double2 *) c->pm_potk);
+  pm_filter_kernel<D><<<g2_cdiv((long long) ncpx, 256), 256, 0, c->stream>>>(N, asmth2, Gf, (const double *) c->pm_tab, (const double2 *) c->pm_rk, ncpx,
+										 (double2 *) c->pm_potk);
 }
 
 int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
@@ -237,7 +240,7 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
   if(c->stage < 1)
     return g2_fail(G2GPU_ERR_STATE, "PM: no particles uploaded");
   const int N = pp->pmgrid, n = c->npart, D = c->D;
-  if(N < 4 || N > 2048 || pp->boxsize <= 0 || pp->asmth <= 0)
+  if(N < 4 || N > 1024 || pp->boxsize <= 0 || pp->asmth <= 0)
     return g2_fail(G2GPU_ERR_ARG, "PM: bad parameters (PMGRID=%d BoxSize=%g Asmth=%g)", N, pp->boxsize, pp->asmth);
   for(int i = 0; i < D * D; i++)
     if(pp->greens_id[i] < G2GPU_GREENS_NONE || pp->greens_id[i] > G2GPU_GREENS_COLOYUK)
@@ -260,15 +263,39 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
   fac *= 1 / (2 * pp->boxsize / N);
   const size_t nreal = (size_t) N * N * N, ncpx = (size_t) N * N * (N / 2 + 1);
 
-  for(int nA = 0; nA < D; nA++)
+  // filter table (host, double, libm like the reference): exp(-k^2 asmth2) / sinc^4 per mesh index
+  if(c->pm_tab_asmth2 != asmth2 || c->pm_tab_n != N)
     {
-      G2_CUDA(cudaMemsetAsync(c->pm_rho, 0, sizeof(double) * nreal, st));
-      pm_deposit_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, nA, (double *) c->pm_rho);
-      c->launches++;
-      if(cufftExecD2Z((cufftHandle) c->pm_fwd, (cufftDoubleReal *) c->pm_rho, (cufftDoubleComplex *) c->pm_rk + (size_t) nA * ncpx) != CUFFT_SUCCESS)
-	return g2_fail(G2GPU_ERR_CUDA, "PM: forward FFT failed");
+      double *tab = (double *) malloc(sizeof(double) * N);
+      for(int i = 0; i < N; i++)
+	{
+	  const double k = i > N / 2 ? i - N : i;
+	  double f = 1;
+	  if(k != 0)
+	    {
+	      f = (M_PI * k) / N;
+	      f = sin(f) / f;
+	    }
+	  const double ff = 1 / f;
+	  tab[i] = exp(-k * k * asmth2) * ff * ff * ff * ff;
+	}
+      cudaError_t e = cudaMemcpyAsync(c->pm_tab, tab, sizeof(double) * N, cudaMemcpyHostToDevice, st);
+      if(e == cudaSuccess)
+	e = cudaStreamSynchronize(st);
+      free(tab);
+      if(e != cudaSuccess)
+	return g2_fail(G2GPU_ERR_CUDA, "PM: %s", cudaGetErrorString(e));
+      c->pm_tab_asmth2 = asmth2;
+      c->pm_tab_n = N;
     }
-  G2_CUDA(cudaMemsetAsync(c->in_gravpm, 0, sizeof(float) * 3 * (size_t) n, st));	// longrange.c:67
+
+  G2_CUDA(cudaMemsetAsync(c->pm_rho, 0, sizeof(double) * nreal * D, st));
+  pm_deposit_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, (double *) c->pm_rho);
+  c->launches++;
+  for(int nA = 0; nA < D; nA++)
+    if(cufftExecD2Z((cufftHandle) c->pm_fwd, (cufftDoubleReal *) c->pm_rho + (size_t) nA * nreal, (cufftDoubleComplex *) c->pm_rk + (size_t) nA * ncpx) != CUFFT_SUCCESS)
+      return g2_fail(G2GPU_ERR_CUDA, "PM: forward FFT failed");
+  // the density meshes are free now: mesh nB becomes the potential acting on species nB
   for(int nB = 0; nB < D; nB++)
     {
       PMGreens Gf;
@@ -280,7 +307,10 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
 	  any = any || Gf.id[nA] != G2GPU_GREENS_NONE;
 	}
       if(!any)
-	continue;
+	{
+	  G2_CUDA(cudaMemsetAsync((double *) c->pm_rho + (size_t) nB * nreal, 0, sizeof(double) * nreal, st));
+	  continue;
+	}
       switch (D)
 	{
 	case 1: launch_filter<1>(c, N, asmth2, Gf); break;
@@ -292,11 +322,11 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
 	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
 	}
       c->launches++;
-      if(cufftExecZ2D((cufftHandle) c->pm_inv, (cufftDoubleComplex *) c->pm_potk, (cufftDoubleReal *) c->pm_rho) != CUFFT_SUCCESS)
+      if(cufftExecZ2D((cufftHandle) c->pm_inv, (cufftDoubleComplex *) c->pm_potk, (cufftDoubleReal *) c->pm_rho + (size_t) nB * nreal) != CUFFT_SUCCESS)
 	return g2_fail(G2GPU_ERR_CUDA, "PM: inverse FFT failed");
-      pm_gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, nB, (const double *) c->pm_rho, fac, c->in_gravpm);
-      c->launches++;
     }
+  pm_gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, (const double *) c->pm_rho, fac, c->in_gravpm);	// writes every particle (longrange.c:67)
+  c->launches++;
   G2_CUDA(cudaEventRecord(c->ev[14], st));
   G2_CUDA(cudaGetLastError());
   c->have_gravpm = 1;		// the next g2gpu_domain carries GravPM along for the OldAcc term of the walk (gravtree.c:318-331)
