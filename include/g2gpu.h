@@ -208,6 +208,7 @@ int g2gpu_gravity_tree(g2gpu_ctx *ctx, int npart, const float *pos, const float 
 		       float *oldacc_out, int *perm);
 
 /* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks", "walk_group",
+ * "walk_mode" (0: one walk cursor per 32 targets, default; 1: one warp per target over level-order records, experimental),
  * "accumulator" (1 = the reference built with -DNGRAVS_ACCUMULATOR; takes effect at the next g2gpu_treebuild). */
 int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
 
