@@ -34,7 +34,10 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
   const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(G - 1)));
-  const unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
+  unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
+#ifndef G2_WALK_NO_TABREG
+  asm volatile("" : "+r"(s_tab_addr));	// keep the table base in a register: re-deriving it costs 4 uniform instructions per pair term
+#endif
   unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
 #pragma unroll
   for(int t = 0; t < 6; t++)
@@ -75,6 +78,22 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       const unsigned int end = (unsigned int) A.numnodes;
       // a sub-group without any valid target has nothing to walk
       unsigned int cur = (__ballot_sync(0xffffffffu, valid) & gmask) ? 0u : end;
+      // TreePM: a target farther than rcut + len/2 (+ margins) from every face of the box needs no periodic image of a cell of size len:
+      // cells across a face are culled with the raw distance as well (raw >= nearest-image distance >= distance to the face).  Cells
+      // smaller than nowrap_len (warp minimum over the 32 targets, so uniform) skip the image-shift arithmetic; results are unchanged.
+      float nowrap_len = 0.0f;
+#ifndef G2_WALK_NO_NOWRAP
+      if(SR && PERIODIC && G == 32)
+#else
+      if(false)
+#endif
+	{
+	  float m = valid ? fminf(fminf(fminf(px, A.boxsize - px), fminf(py, A.boxsize - py)), fminf(pz, A.boxsize - pz)) : 3.0e38f;
+#pragma unroll
+	  for(int o = 16; o > 0; o >>= 1)
+	    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	  nowrap_len = fminf(A.shift_len_max, 1.99f * (m - A.rcut - 2.0f * A.cull_margin));
+	}
 
       while(true)
 	{
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	      const float cxr = q0.y - px, cyr = q0.z - py, czr = q0.w - pz;
 	      bool done = false;	// culled: skip the subtree without interaction
 	      bool outside = false;
-	      if(SR && PERIODIC)
+	      if(SR && PERIODIC && !(len < nowrap_len))
 		{
 		  shx = A.boxsize * rint_small(cxr * A.boxinv);
 		  shy = A.boxsize * rint_small(cyr * A.boxinv);

@@ -1,0 +1,19 @@
+# walk micro-optimisation variants (round 1): rebuilds the library on the GPU box with different -D flags and times two workloads
+run() { tag=$1; shift
+  make -C gadget-2.0.7-ngravs_b200 -j16 EXTRA="-DG2_FAST_BUILD $*" > gpurun_out/make_$tag.log 2>&1
+  for wl in periodic128 periodic256; do
+    timeout 400 python bench.py --workload $wl --steps 3 --no-cpu-baseline > gpurun_out/bench_${wl}_$tag.json 2> gpurun_out/bench_${wl}_$tag.err
+  done; }
+mkdir -p gpurun_out
+run base -DG2_WALK_NO_NOWRAP
+run nowrap
+run nowrap_tabreg -DG2_WALK_TABREG
+run nowrap_tabreg_mb8 -DG2_WALK_TABREG -DWALK_MINBLOCKS=8
+run nowrap_mb8 -DWALK_MINBLOCKS=8
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("gpurun_out/bench_periodic*_*.json")):
+    try:
+        d=json.load(open(f)); print(f, round(d["ms_per_step"],3), round(d["stages_ms"]["walk_kernel_ms"],3), round(d["ia_per_particle"],3), d["e2e"]["checksum"])
+    except Exception as e: print(f, "ERR", e)
+PY
