@@ -361,6 +361,39 @@ def main():
         e2e = {"value": n / (e_ms / K * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / K,
                "checksum": float(np.abs(acc_e).sum())}
 
+    if world > 1 and not args.profile and active is None:
+        # N > 1: every rank copies ITS OWN 1/N of the particle records from pinned host memory, the all-gather replicates them, and every
+        # rank reads the result arrays back (its own targets are the entries that changed); max over ranks
+        cnt = hi - lo
+        h_rec = multigpu.pack_records(torch.from_numpy(w["pos"][lo:hi]), torch.from_numpy(w["mass"][lo:hi]), torch.from_numpy(w["ptype"][lo:hi].astype(np.int32)),
+                                      torch.from_numpy(oldacc_by_id[lo:hi])).pin_memory()
+        outbuf = (torch.zeros((n, 3), dtype=torch.float32).pin_memory().numpy(), torch.zeros(n, dtype=torch.float32).pin_memory().numpy(),
+                  torch.zeros(n, dtype=torch.float32).pin_memory().numpy())
+
+        def step_e2e():
+            ex.s_rec[:cnt].copy_(h_rec, non_blocking=True)
+            step_resident()
+            return tg.download_acc(out=outbuf)
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        e_ms = 0.0
+        for k in range(K):
+            flush.zero_()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(torch.cuda.current_stream())
+            acc_e, cost_e, old_e = step_e2e()
+            b.record(lib_stream)
+            tg.sync()
+            e_ms += a.elapsed_time(b)
+        t_e = torch.tensor([e_ms / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e_ms = float(t_e.item())
+        e2e = {"value": n / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": cnt * 32, "d2h_bytes_per_step": 20 * n, "ms_per_step": e_ms,
+               "note": "per rank: H2D of its 1/N of the 32-byte records, D2H of the whole result arrays; max over ranks",
+               "checksum": float(np.abs(acc_e).sum())}
+
     # ---- the long-range complement of the TreePM split (pmforce_periodic on the device); reported beside the tree numbers, not part
     # of the step.  Device time from the library's own events around the PM stage, inputs resident (uploaded once).
     pm = None

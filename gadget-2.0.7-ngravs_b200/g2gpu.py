@@ -227,10 +227,14 @@ class TreeGravity:
         self._chk(self.lib.g2gpu_direct(self.ctx, C.byref(wp), len(t), _p(t), _p(out)))
         return out
 
-    def download_acc(self):
-        acc = np.zeros((self.n, 3), dtype=np.float32)
-        cost = np.zeros(self.n, dtype=np.float32)
-        old = np.zeros(self.n, dtype=np.float32)
+    def download_acc(self, out=None):
+        """out = (acc[n,3], cost[n], oldacc[n]) float32 arrays (e.g. pinned) to receive the results; allocated when None."""
+        if out is not None:
+            acc, cost, old = out
+        else:
+            acc = np.zeros((self.n, 3), dtype=np.float32)
+            cost = np.zeros(self.n, dtype=np.float32)
+            old = np.zeros(self.n, dtype=np.float32)
         self._chk(self.lib.g2gpu_download_acc(self.ctx, _p(acc), _p(cost), _p(old)))
         return acc, cost, old
 
