@@ -446,7 +446,7 @@ def main():
                 "note": f"algorithmic flops = species terms x {FLOP_PER_TERM[w['flop']]:.0f} (SURVEY.md §8d), cell-opening arithmetic excluded; peak = "
                         f"{prop.multi_processor_count} SMs x 128 lanes x 2 x {sm_max:.0f} MHz (nominal CUDA-core FP32, of MEASURED_PEAKS sm_max_mhz)"}
     # ncu's own utilisation figures of the same kernel on the same workload, from the committed capture (never measured under this run)
-    for suffix in ("r1b", "final", "v1"):
+    for suffix in ("r1e", "r1b", "final", "v1"):
         prof = os.path.join(ROOT, "profiles", f"r1_walk_{w['key']}_{suffix}.txt")
         if os.path.exists(prof):
             ncu = {"source": os.path.relpath(prof, ROOT)}

@@ -535,6 +535,8 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     c->acc_double = value;
   else if(strcmp(name, "accumulator") == 0)
     c->accumulator = value != 0;	// takes effect at the next g2gpu_treebuild
+  else if(strcmp(name, "direct_ewald") == 0)
+    c->direct_ewald = value != 0;
   else if(strcmp(name, "walk_mode") == 0)
     {
       if(value != 0 && value != 1)

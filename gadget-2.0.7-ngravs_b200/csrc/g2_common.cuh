@@ -105,6 +105,7 @@ struct g2gpu_ctx
   int counts_valid;		// wcnt belongs to the current tree
   unsigned int *wcnt;		// [U][D], filled by g2_stage_counts after the build when accumulator != 0
   int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
+  int direct_ewald;		// g2gpu_direct adds the exact lattice correction of a periodic box (option "direct_ewald")
   int walk_mode;		// 0: one cursor per 32 targets (g2_walk.cu); 1: one warp per target over level-order records (g2_walkb.cu)
   int bfs_valid;		// the level-order records belong to the current tree
   float4 *b_q0, *b_s;		// level-order SoA walk records (allocated on first use)

@@ -503,13 +503,50 @@ struct DirectArgs
   const float *__restrict__ srtable;
   const int *__restrict__ targets;
   double *__restrict__ out;
-  int n, D, ntab, sr, periodic, unequal, stock;
+  int n, D, ntab, sr, periodic, unequal, stock, ewald;
   double boxsize, asmthfac, utor2wpi;
   float fsoft[6];
   int t2g[6];
   unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   G2LawTable laws;
 };
+
+// Exact lattice (Ewald) correction of a periodic box: the acceleration due to all periodic images of a unit source minus the nearest-image
+// Newtonian term, for a nearest-image displacement (dx,dy,dz) = source - target in units of the box size; multiply by m / L^2.  This is
+// what the reference tabulates on a 65^3 grid (ewald_force, ngravs.c:1170; lattice_init, forcetree.c:3611) and interpolates tri-linearly in
+// lattice_corr (forcetree.c:3803) for gravity_forcetest; here the sums are evaluated directly in FP64 (alpha = 2, |n| <= 3, |h|^2 < 10,
+// truncation error < 1e-11), so it is exact ground truth for Newtonian pairs, at ~2e4 flop per pair (accuracy tests only).
+__device__ void ewald_correction(double x, double y, double z, double *out)
+{
+  const double alpha = 2.0, r2 = x * x + y * y + z * z, r = sqrt(r2);
+  double fx = -x / (r2 * r), fy = -y / (r2 * r), fz = -z / (r2 * r);
+  for(int i = -3; i <= 3; i++)
+    for(int j = -3; j <= 3; j++)
+      for(int k = -3; k <= 3; k++)
+	{
+	  const double dx = x - i, dy = y - j, dz = z - k;
+	  const double d2 = dx * dx + dy * dy + dz * dz, d = sqrt(d2);
+	  const double g = (erfc(alpha * d) + 2.0 * alpha * d / sqrt(M_PI) * exp(-alpha * alpha * d2)) / (d2 * d);
+	  fx += dx * g;
+	  fy += dy * g;
+	  fz += dz * g;
+	}
+  for(int i = -3; i <= 3; i++)
+    for(int j = -3; j <= 3; j++)
+      for(int k = -3; k <= 3; k++)
+	{
+	  const int h2 = i * i + j * j + k * k;
+	  if(h2 == 0 || h2 >= 10)
+	    continue;
+	  const double v = 2.0 / h2 * exp(-M_PI * M_PI * h2 / (alpha * alpha)) * sin(2.0 * M_PI * (i * x + j * y + k * z));
+	  fx += i * v;
+	  fy += j * v;
+	  fz += k * v;
+	}
+  out[0] = fx;
+  out[1] = fy;
+  out[2] = fz;
+}
 
 __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs A)
 {
@@ -566,6 +603,15 @@ __global__ void __launch_bounds__(256) direct_kernel(const DirectArgs A)
       ax += dx * fac;
       ay += dy * fac;
       az += dz * fac;
+      if(A.ewald)
+	{			// forcetree.c:3513-3522: the images matter even inside the softening
+	  double c[3];
+	  const double linv = 1.0 / A.boxsize, mf = (double) q.m * linv * linv;
+	  ewald_correction(dx * linv, dy * linv, dz * linv, c);
+	  ax += mf * c[0];
+	  ay += mf * c[1];
+	  az += mf * c[2];
+	}
     }
   s_red[0][threadIdx.x] = ax;
   s_red[1][threadIdx.x] = ay;
@@ -605,6 +651,7 @@ int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const
   A.n = c->npart; A.D = c->D; A.ntab = c->cfg.ntab; A.sr = sr; A.periodic = c->cfg.periodic != 0 && wp->boxsize > 0;
   A.unequal = c->cfg.unequal_softenings != 0;
   A.boxsize = wp->boxsize;
+  A.ewald = c->direct_ewald && A.periodic && !sr;
   if(sr)
     {
       A.asmthfac = 0.5 / wp->asmth * (c->cfg.ntab / 3.0);

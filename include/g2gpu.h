@@ -187,7 +187,9 @@ int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
 /* force_treeevaluate_direct (forcetree.c:3428-3548), the accuracy oracle of gravity_forcetest (gravtree_forcetest.c:28-356): FP64
  * direct summation over all particles for ntargets particles given by their index in CURRENT order (after g2gpu_domain);
  * acc[3*i+k] is the pre-G acceleration (G = 1).  Under the TreePM split (config.shortrange and wp->asmth > 0) it is the short-range
- * force the tree walk approximates; periodic boxes take the nearest image (no lattice correction). */
+ * force the tree walk approximates; periodic boxes take the nearest image.  With the option "direct_ewald" and wp->asmth == 0 a periodic
+ * box gets the exact lattice (Ewald) correction of all images added (what the reference tabulates and interpolates in lattice_corr,
+ * forcetree.c:3803, for gravity_forcetest), i.e. the complete periodic Newtonian force the TreePM sum (tree + PM) approximates. */
 int g2gpu_direct(g2gpu_ctx *ctx, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 
 /* ---- periodic PM long-range force: pmforce_periodic (pm_periodic.c:204-790), the caller of which is long_range_force
@@ -208,6 +210,7 @@ int g2gpu_gravity_tree(g2gpu_ctx *ctx, int npart, const float *pos, const float 
 		       float *oldacc_out, int *perm);
 
 /* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks", "walk_group",
+ * "direct_ewald" (1: g2gpu_direct adds the exact periodic lattice correction),
  * "walk_mode" (0: one walk cursor per 32 targets, default; 1: one warp per target over level-order records, experimental),
  * "accumulator" (1 = the reference built with -DNGRAVS_ACCUMULATOR; takes effect at the next g2gpu_treebuild). */
 int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);

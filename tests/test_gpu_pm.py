@@ -136,3 +136,61 @@ def test_treepm_total_force_against_ewald(outdir):
     print(f"TreePM vs Ewald: median {np.median(err):.3e} max {err.max():.3e}; tree alone median {np.median(err_tree_only):.3e}")
     assert np.median(err) <= 1e-2 and err.max() <= 8e-2
     assert np.median(err_tree_only) > 5 * np.median(err)          # the long-range part matters
+
+
+def test_device_ewald_direct_sum_against_numpy():
+    """g2gpu_direct with the option "direct_ewald": the complete periodic Newtonian force (nearest image + exact lattice correction of all
+    images, the quantity gravity_forcetest compares the TreePM force with) against the independent numpy Ewald sum of g2test."""
+    from g2gpu import TreeGravity
+    n, box = 4096, 1000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=8)
+    mass = (mass * np.random.default_rng(1).uniform(0.5, 2.0, n)).astype(np.float32)
+    tg = TreeGravity(max_part=n + 2000, n_gravs=2, periodic=True, shortrange=False, unequal_softenings=False)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening((1.0e-6,) * 6))
+    tg.set_laws()
+    tg.set_option("direct_ewald", 1)
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    order = tg.order()
+    targets = np.arange(0, n, n // 16, dtype=np.int32)[:16]
+    d = tg.direct(tg.walk_params(theta=0.5, errtol=0.005, boxsize=box, G=1.0), targets)
+    tg.close()
+    exact = g2test.ewald_direct(pos, mass, order[targets], box)
+    err = np.linalg.norm(d - exact, axis=1) / np.linalg.norm(exact, axis=1)
+    assert err.max() < 1e-8, err
+
+
+@pytest.mark.parametrize("side,ntargets", [(128, 128), (256, 32)])
+def test_full_size_treepm_total_force_against_ewald(side, ntargets, outdir):
+    """BASELINE configs 3 and 5 at full size (2.1 M / 16.8 M particles, PMGRID 256): tree short-range walk (relative criterion) + device PM
+    = the complete TreePM force, against the exact periodic force of random targets (device FP64 direct sum over ALL particles with the
+    Ewald lattice correction).  What is left is the accuracy of the TreePM scheme itself (about a per cent, Springel 2005 fig. 3)."""
+    import json
+    from g2gpu import TreeGravity
+    PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gadget-2.0.7-ngravs_b200")
+    n, box, N = side ** 3, 100000.0, 256
+    pos, mass, ptype = g2test.periodic_poisson(n, box)
+    eps = box / side / 30.0
+    tg = TreeGravity(max_part=int(1.1 * n) + 64, n_gravs=2, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening((eps,) * 6))
+    tg.set_laws()
+    tg.set_option("direct_ewald", 1)
+    tab = np.load(os.path.join(PKG, "data", "srtable_newton_ntab2048.npy"))
+    tg.set_srtable(np.broadcast_to(tab, (2, 2, len(tab))).copy())
+    asmth = 1.25 * box / N
+    wp = dict(boxsize=box, G=1.0, asmth=asmth, rcut=4.5 * asmth)
+    tg.upload(pos, mass, ptype)
+    pm = tg.pm_periodic(N, box, G=1.0)                                  # upload order
+    acc0, cost0, old0, perm = tg.gravity_tree(pos, mass, ptype, tg.walk_params(theta=0.5, errtol=0.005, **wp))
+    oldacc_by_id = np.zeros(n, dtype=np.float32)
+    oldacc_by_id[perm] = old0
+    acc, cost, old, perm = tg.gravity_tree(pos, mass, ptype, tg.walk_params(theta=0.0, errtol=0.005, **wp), oldacc=oldacc_by_id)
+    targets = np.sort(np.random.default_rng(11).choice(n, ntargets, replace=False)).astype(np.int32)      # current-order indices
+    exact = tg.direct(tg.walk_params(theta=0.0, errtol=0.005, boxsize=box, G=1.0, asmth=0.0, rcut=0.0), targets)
+    tg.close()
+    total = acc[targets].astype(np.float64) + pm[perm[targets]]
+    err = np.linalg.norm(total - exact, axis=1) / np.linalg.norm(exact, axis=1)
+    json.dump(dict(n=n, ntargets=ntargets, median=float(np.median(err)), p90=float(np.percentile(err, 90)), max=float(err.max())),
+              open(os.path.join(outdir, f"fullsize_treepm_total_vs_ewald_{side}.json"), "w"))
+    print(f"TreePM total vs Ewald at {side}^3: median {np.median(err):.3e} p90 {np.percentile(err, 90):.3e} max {err.max():.3e}")
+    assert np.median(err) < 1.5e-2 and err.max() < 0.15
