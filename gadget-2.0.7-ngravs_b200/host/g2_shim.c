@@ -8,6 +8,8 @@
  *   peano.c    : peano_hilbert_key (356), peano_hilbert_order (36), compare_key (190)
  *   pm_periodic.c (PMGRID && PERIODIC, unless -DG2_SHIM_KEEP_REFERENCE_PM): pm_init_periodic (53), pm_init_periodic_allocate (139),
  *                pm_init_periodic_free (187), pmforce_periodic (204); pmpotential_periodic (800) is not provided and ends the run
+ *   gravtree_forcetest.c (-DFORCETEST, unless -DG2_SHIM_KEEP_REFERENCE_FORCETEST): gravity_forcetest (28), the direct-summation accuracy
+ *                check; force_treeevaluate_direct (forcetree.c:3428) itself stays available on the host
  * so that accel.c, domain.c, init.c, run.c, ... call it unchanged.
  * All state stays in the reference's globals (P[], All, NumPart, TreeReconstructFlag, ...).  Errors of the GPU
  * library end the run through endrun() like the reference's own failures (endrun.c:24).  There is no CPU
@@ -76,6 +78,7 @@ int compare_key(const void *a, const void *b)	/* peano.c:190 */
 }
 
 static void g2_push_tables(void);
+static void g2_fill_walk_params(g2gpu_walk_params * wp);
 
 static void g2_upload(int npart)
 {
@@ -378,6 +381,127 @@ void pmpotential_periodic(void)	/* pm_periodic.c:800, outside the replaced path 
 {
   printf("g2gpu: pmpotential_periodic() is not provided by the shim; build with -DG2_SHIM_KEEP_REFERENCE_PM and FFTW-2 to use it.\n");
   endrun(7313);
+}
+#endif
+
+/* ---------------------------------------------------------------- gravtree_forcetest.c ---------------------- */
+#if defined(FORCETEST) && !defined(G2_SHIM_KEEP_REFERENCE_FORCETEST)
+/* gravtree_forcetest.c:28.  accel.c:52-54 calls it right after gravity_tree(), so the device still holds the particles of this force
+ * computation (current order, g2_perm).  The random fraction FORCETEST of the active particles is selected exactly like the reference does
+ * (get_random_number(P[i].ID)); their direct sums run as ONE device call (one CTA per target, FP64).  In a periodic box the lattice
+ * correction of all images is evaluated exactly (Ewald sums) where the reference interpolates its 65^3 table (lattice_corr, forcetree.c:3803):
+ * Newtonian pairs only.  forcetest.txt lines and the DIRECT line of timings.txt keep the reference's formats. */
+void gravity_forcetest(void)
+{
+  int i, j, k, nt = 0, *targets, *pidx, *inv;
+  double *acc, tstart, tend, timetree, fac1;
+  g2gpu_walk_params wp;
+  char buf[200];
+
+#ifdef PMGRID
+  if(All.PM_Ti_endstep != All.Ti_Current)
+    return;
+#endif
+  if(All.ComovingIntegrationOn)
+    set_softenings();
+  for(i = 0, NumForceUpdate = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep == All.Ti_Current && get_random_number(P[i].ID) < FORCETEST)
+      {
+	P[i].Ti_endstep = -P[i].Ti_endstep - 1;
+	NumForceUpdate++;
+      }
+  nt = NumForceUpdate;
+  targets = malloc(sizeof(int) * (nt + 1));
+  pidx = malloc(sizeof(int) * (nt + 1));
+  acc = malloc(sizeof(double) * 3 * (nt + 1));
+  inv = malloc(sizeof(int) * (NumPart + 1));
+  for(i = 0; i < NumPart; i++)
+    inv[g2_perm[i]] = i;	/* index in P[] -> index on the device */
+  for(i = 0, nt = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep < 0)
+      {
+	targets[nt] = inv[i];
+	pidx[nt] = i;
+	nt++;
+      }
+  tstart = second();
+  g2_fill_walk_params(&wp);
+  wp.asmth = wp.rcut = 0;	/* the complete force, not its short-range part */
+#ifdef PERIODIC
+  for(i = 0; i < N_GRAVS; i++)
+    for(j = 0; j < N_GRAVS; j++)
+      if(AccelFxns[i][j] != newtonian)
+	{
+	  printf("g2gpu: gravity_forcetest() in a periodic box knows the lattice sum of Newtonian pairs only (pair %d,%d)\n", i, j);
+	  endrun(7321);
+	}
+  g2_check(g2gpu_set_option(G2, "direct_ewald", 1), "set_option");
+#endif
+  if(nt > 0)
+    g2_check(g2gpu_direct(G2, &wp, nt, targets, acc), "direct");
+  tend = second();
+  timetree = timediff(tstart, tend);
+  for(i = 0; i < nt; i++)
+    for(k = 0; k < 3; k++)
+      P[pidx[i]].GravAccelDirect[k] = acc[3 * i + k];
+  /* gravtree_forcetest.c:241-268 */
+  if(All.ComovingIntegrationOn)
+    {
+#ifndef PERIODIC
+      fac1 = 0.5 * All.Hubble * All.Hubble * All.Omega0 / All.G;
+      for(i = 0; i < NumPart; i++)
+	if(P[i].Ti_endstep < 0)
+	  for(j = 0; j < 3; j++)
+	    P[i].GravAccelDirect[j] += fac1 * P[i].Pos[j];
+#endif
+    }
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep < 0)
+      for(j = 0; j < 3; j++)
+	P[i].GravAccelDirect[j] *= All.G;
+  if(All.ComovingIntegrationOn == 0)
+    {
+      fac1 = All.OmegaLambda * All.Hubble * All.Hubble;
+      for(i = 0; i < NumPart; i++)
+	if(P[i].Ti_endstep < 0)
+	  for(j = 0; j < 3; j++)
+	    P[i].GravAccelDirect[j] += fac1 * P[i].Pos[j];
+    }
+  sprintf(buf, "%s%s", All.OutputDir, "forcetest.txt");
+  if(!(FdForceTest = fopen(buf, "a")))
+    {
+      printf("error in opening file '%s'\n", buf);
+      endrun(17);
+    }
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep < 0)
+      {
+#ifndef PMGRID
+	fprintf(FdForceTest, "%d %g %g %g %g %g %g %g %g %g %g %g %d\n", P[i].Type, All.Time, All.Time - TimeOfLastTreeConstruction,
+		P[i].Pos[0], P[i].Pos[1], P[i].Pos[2], P[i].GravAccelDirect[0], P[i].GravAccelDirect[1], P[i].GravAccelDirect[2],
+		P[i].GravAccel[0], P[i].GravAccel[1], P[i].GravAccel[2], P[i].ID);
+#else
+	fprintf(FdForceTest, "%d %f %f %f %f %f %.15e %.15e %.15e %.15e %.15e %.15e %.15e %.15e %.15e %d\n", P[i].Type, All.Time,
+		All.Time - TimeOfLastTreeConstruction, P[i].Pos[0], P[i].Pos[1], P[i].Pos[2], P[i].GravAccelDirect[0], P[i].GravAccelDirect[1],
+		P[i].GravAccelDirect[2], P[i].GravAccel[0], P[i].GravAccel[1], P[i].GravAccel[2], P[i].GravPM[0] + P[i].GravAccel[0],
+		P[i].GravPM[1] + P[i].GravAccel[1], P[i].GravPM[2] + P[i].GravAccel[2], P[i].ID);
+#endif
+      }
+  fclose(FdForceTest);
+  for(i = 0; i < NumPart; i++)
+    if(P[i].Ti_endstep < 0)
+      P[i].Ti_endstep = -P[i].Ti_endstep - 1;
+  if(ThisTask == 0)
+    {
+      fprintf(FdTimings, "DIRECT Nf= %d    part/sec=%g | %g  ia/part=%g \n", nt, nt / (timetree + 1.0e-20), nt / (timetree + 1.0e-20),
+	      (double) NumPart);
+      fprintf(FdTimings, "\n");
+      fflush(FdTimings);
+    }
+  free(inv);
+  free(acc);
+  free(pidx);
+  free(targets);
 }
 #endif
 

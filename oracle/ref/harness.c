@@ -524,3 +524,20 @@ int g2ref_pmforce(double *out)
   return -1;
 #endif
 }
+
+/* gravity_forcetest() (gravtree_forcetest.c:28) after a gravity_tree(): direct sums of the selected particles (all active ones with
+ * FORCETEST = 1.0, RndTable = 0.5).  out: P[].GravAccelDirect (n x 3, post-G), current order.  forcetest.txt goes to the working directory. */
+int g2ref_forcetest(double *out)
+{
+#if defined(FORCETEST) && !defined(PERIODIC)
+  int i, k;
+  gravity_forcetest();
+  for(i = 0; i < NumPart; i++)
+    for(k = 0; k < 3; k++)
+      out[3 * i + k] = P[i].GravAccelDirect[k];
+  return 0;
+#else
+  (void) out;
+  return -1;
+#endif
+}

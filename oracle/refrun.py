@@ -159,6 +159,13 @@ class RefOracle:
         self.lib.g2ref_get_particles(*(a.ctypes.data_as(C.c_void_p) for a in (pos, mass, ptype, pid, acc, cost, oldacc)))
         return dict(pos=pos, mass=mass, type=ptype, id=pid, acc=acc, cost=cost, oldacc=oldacc)
 
+    def run_forcetest(self):
+        """gravity_forcetest() (gravtree_forcetest.c:28): P[].GravAccelDirect of every particle, current order; FORCETEST variants only."""
+        out = np.zeros((self.n, 3))
+        if self.lib.g2ref_forcetest(out.ctypes.data_as(C.c_void_p)) != 0:
+            raise RuntimeError("this oracle variant was compiled without FORCETEST (or with PERIODIC)")
+        return out
+
     def pmforce(self):
         """GravPM of every particle in the current order of P[] (pmforce_periodic, pm_periodic.c:204); PM variants only."""
         out = np.zeros((self.n, 3))

@@ -108,3 +108,37 @@ def test_reference_pm_call_runs_on_the_gpu(outdir):
     assert np.median(g2test.rel_err(out["shim"][0], out["ref"][0])) <= 1e-5
     rel = np.abs(out["shim"][1] - out["ref"][1]) / np.maximum(out["ref"][1], 1e-30)
     assert np.median(rel) <= 1e-5 and np.percentile(rel, 99.9) <= 1e-3
+
+
+def test_reference_forcetest_call_runs_on_the_gpu(outdir, tmp_path, monkeypatch):
+    """gravity_forcetest() (gravtree_forcetest.c:28, the -DFORCETEST accuracy check accel.c:52 runs after gravity_tree()): the shim's
+    version (one device call, FP64 direct sums) against the unmodified file, and the forcetest.txt lines both write."""
+    variant = "np_d2_f32_ft"
+    if not (available(variant) and available(variant, "g2shim")):
+        pytest.skip("oracle/_ref (reference and shim builds) not present")
+    _preload()
+    monkeypatch.chdir(tmp_path)
+    n = 3000
+    pos, mass, ptype = g2test.gaussian_blobs(n, seed=5)
+    kw = dict(softening=g2test.SOFT_NP, gravity=g2test.GRAV_D2, G=43007.1)
+    res = {}
+    for name, prefix in (("ref", "g2ref"), ("shim", "g2shim")):
+        d = tmp_path / name
+        d.mkdir()
+        monkeypatch.chdir(d)
+        o = RefOracle(variant, int(1.1 * n) + 64, prefix=prefix, **kw)
+        o.load(pos, mass, ptype)
+        o.domain()
+        o.gravity()
+        direct = o.run_forcetest()
+        p = o.particles()
+        full = np.zeros((n, 3)); full[p["id"]] = direct
+        tree = np.zeros((n, 3)); tree[p["id"]] = p["acc"]
+        lines = open(d / "forcetest.txt").read().splitlines()
+        res[name] = (full, tree, lines)
+    err = g2test.rel_err(res["shim"][0], res["ref"][0])
+    assert err.max() < 1e-5, err.max()                       # FP32 pair arithmetic inputs, FP64 sums on both sides
+    assert len(res["shim"][2]) == len(res["ref"][2]) == n
+    assert len(res["shim"][2][0].split()) == len(res["ref"][2][0].split()) == 13
+    # and the point of the exercise: the tree force of either build agrees with the direct sums
+    assert np.median(g2test.rel_err(res["shim"][1], res["shim"][0])) < 5e-3
