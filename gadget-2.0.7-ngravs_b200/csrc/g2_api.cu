@@ -104,7 +104,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->t_suns, (size_t) G2_MAXTOP * 8); rc |= dalloc(&c->t_first, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_last, (size_t) G2_MAXTOP);
   rc |= dalloc(&c->t_min1, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_min2, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_ready, (size_t) G2_MAXTOP);
   rc |= dalloc(&c->t_npart, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_nchild, (size_t) G2_MAXTOP); rc |= dalloc(&c->t_ubase, (size_t) G2_MAXTOP);
-  rc |= dalloc(&c->wcells, (nn + G2_MAXTOP) * R); rc |= dalloc(&c->wpart, np);
+  rc |= dalloc(&c->wcells, (nn + G2_MAXTOP) * R); rc |= dalloc(&c->wpart, np); rc |= dalloc(&c->wsrc, np);
   rc |= dalloc(&c->hist2, np + 2); rc |= dalloc(&c->hist2_scan, np + 2); rc |= dalloc(&c->dmin, np + 2);
   rc |= dalloc(&c->d_err, (size_t) 8);
   rc |= dalloc(&c->d_depth, (size_t) 64);
@@ -141,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->wcnt, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
+    c->d_srtable, c->d_srtable_f, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -510,6 +510,14 @@ extern "C" int g2gpu_sync(g2gpu_ctx *c)
 }
 
 extern "C" void *g2gpu_stream(g2gpu_ctx *c) { return c ? (void *) c->stream : nullptr; }
+
+extern "C" int g2gpu_update_tree(g2gpu_ctx *c, const float *len, const float *s)
+{
+  if(!c || !len || !s)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_update_tree(c, len, s);
+}
 
 extern "C" int g2gpu_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
 {

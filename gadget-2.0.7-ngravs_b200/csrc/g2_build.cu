@@ -554,6 +554,7 @@ struct BuildArrays
   const unsigned int *u_poff;	// exclusive scan of u_npart
   float4 *wcells;
   float4 *wpart;
+  unsigned int *wsrc;		// particle index (current order) behind every record of wpart
   int n;
   int numnodes_cap;
 };
@@ -587,6 +588,7 @@ __device__ int process_cell(const BuildArrays &A, const G2TopTree *__restrict__ 
 	  const int type = A.prec[idx].type;
 	  mom_add_particle<D>(M, p, type, idx, S);
 	  A.wpart[poff + np] = p;
+	  A.wsrc[poff + np] = idx;
 	  pinfo |= (unsigned int) type << (4 + 3 * np);
 	  np++;
 	}
@@ -628,6 +630,7 @@ __device__ int process_top(const BuildArrays &A, const G2TopTree *__restrict__ t
 	      const int type = A.prec[idx].type;
 	      mom_add_particle<D>(M, p, type, idx, S);
 	      A.wpart[poff + np] = p;
+	      A.wsrc[poff + np] = idx;
 	      pinfo |= (unsigned int) type << (4 + 3 * np);
 	      np++;
 	    }
@@ -1224,7 +1227,7 @@ static BuildArrays make_arrays(g2gpu_ctx *c)
   A.c_nchild = c->c_nchild; A.c_ready = c->c_ready; A.c_min1 = c->c_min1; A.c_min2 = c->c_min2;
   A.t_suns = c->t_suns; A.t_first = c->t_first; A.t_last = c->t_last; A.t_u = c->t_ubase; A.t_nchild = c->t_nchild;
   A.t_ready = c->t_ready; A.t_min1 = c->t_min1; A.t_min2 = c->t_min2; A.u_poff = c->c_poff;
-  A.wcells = c->wcells; A.wpart = c->wpart; A.n = c->npart; A.numnodes_cap = c->cfg.max_nodes;
+  A.wcells = c->wcells; A.wpart = c->wpart; A.wsrc = c->wsrc; A.n = c->npart; A.numnodes_cap = c->cfg.max_nodes;
   return A;
 }
 
@@ -1330,6 +1333,7 @@ int g2_stage_treebuild(g2gpu_ctx *c)
     }
   c->bfs_valid = 0;
   c->stage = 3;
+  c->tree_npart = n;
   if(c->walk_mode == 1 && !c->accumulator && c->walk_group == 32)
     G2_TRY(g2_stage_bfs(c));	// part of the build time
   G2_CUDA(cudaEventRecord(c->ev[5], st));
@@ -1459,6 +1463,101 @@ int g2_stage_bfs(g2gpu_ctx *c)
   c->launches += 2;
   G2_CUDA(cudaGetLastError());
   c->bfs_valid = 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- dynamic tree update ----------------------------
+// Between two tree constructions the reference keeps its tree and lets it follow the particles: node centres of mass drift with the
+// node velocities (predict.c:79-91), kicks are passed up the Father chain (timestep.c:329-344) and force_update_len (forcetree.c:1005-1122)
+// enlarges nodes whose particles left them.  All of that runs on the host mirror; here the device tree of the LAST construction takes
+// (a) the freshly uploaded particle records (same particles, same upload order) and (b) the host's len and s of every node.
+__global__ void __launch_bounds__(256) dyn_particles_kernel(int n, const int *__restrict__ perm, const G2PRec *__restrict__ in_rec,
+							     const float *__restrict__ in_gravpm, G2PRec *__restrict__ prec, float *__restrict__ gravpm)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  const int src = perm[i];
+  G2PRec r = in_rec[src];
+  r.type = r.type < 0 ? 0 : (r.type > 5 ? 5 : r.type);
+  r.active = r.active != 0;
+  prec[i] = r;
+  if(in_gravpm)
+    for(int k = 0; k < 3; k++)
+      gravpm[3 * (size_t) i + k] = in_gravpm[3 * (size_t) src + k];
+}
+
+__global__ void __launch_bounds__(256) dyn_wpart_kernel(int n, const unsigned int *__restrict__ wsrc, const G2PRec *__restrict__ prec,
+							 float4 *__restrict__ wpart)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+    wpart[i] = *((const float4 *) &prec[wsrc[i]]);
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) dyn_nodes_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, const unsigned int *__restrict__ c_refid,
+							 int ncells, const float *__restrict__ len, const float *__restrict__ s)
+{
+  int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int U;
+  int ref;
+  if(tid < ncells)
+    {
+      U = (unsigned int) tid + (unsigned int) tt->fdfs[A.tl[A.c_a[tid]]] + 1u;
+      ref = (int) c_refid[tid];
+    }
+  else if(tid - ncells < tt->ntopnodes)
+    {
+      ref = tid - ncells;
+      U = A.t_u[ref];
+    }
+  else
+    return;
+  float4 *rec = A.wcells + (size_t) U * (2 + D);
+  rec[0].x = len[ref];
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    {
+      rec[1 + g].x = s[(3 * (size_t) ref + 0) * D + g];
+      rec[1 + g].y = s[(3 * (size_t) ref + 1) * D + g];
+      rec[1 + g].z = s[(3 * (size_t) ref + 2) * D + g];
+    }
+}
+
+int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s)
+{
+  if(!c->tree_npart)
+    return g2_fail(G2GPU_ERR_STATE, "update_tree: no tree has been built");
+  if(c->stage != 1 || c->npart != c->tree_npart)
+    return g2_fail(G2GPU_ERR_STATE, "update_tree: upload the same %d particles first (stage %d, %d uploaded)", c->tree_npart, c->stage, c->npart);
+  c->stage = 3;			// the arrays of the last construction are intact: an upload touches none of them
+  G2_TRY(g2_stage_renumber(c));
+  const int n = c->npart, nn = c->numnodes, D = c->D, ncells = c->ncells;
+  cudaStream_t st = c->stream;
+  const size_t lbytes = sizeof(float) * (size_t) nn, sbytes = sizeof(float) * 3 * (size_t) nn * D;
+  G2_TRY(export_reserve(c, lbytes + sbytes));
+  memcpy(c->h_export, len, lbytes);
+  memcpy(c->h_export + lbytes, s, sbytes);
+  G2_CUDA(cudaMemcpyAsync(c->d_export, c->h_export, lbytes + sbytes, cudaMemcpyHostToDevice, st));
+  c->h2d_bytes += lbytes + sbytes;
+  dyn_particles_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(n, c->perm, c->in_rec, c->have_gravpm ? c->in_gravpm : nullptr, c->prec, c->gravpm);
+  dyn_wpart_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(n, c->wsrc, c->prec, c->wpart);
+  BuildArrays A = make_arrays(c);
+  const int total = nn;
+  const float *dl = (const float *) c->d_export, *ds = (const float *) (c->d_export + lbytes);
+  switch (D)
+    {
+#define G2_B(Dv) case Dv: dyn_nodes_kernel<Dv><<<g2_cdiv(total, 256), 256, 0, st>>>(A, c->d_top, c->c_refid, ncells, dl, ds); break
+      G2_B(1); G2_B(2); G2_B(3); G2_B(4); G2_B(5); G2_B(6);
+#undef G2_B
+    default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
+    }
+  c->launches += 3;
+  G2_CUDA(cudaGetLastError());
+  G2_CUDA(cudaStreamSynchronize(st));	// h_export may be reused by the caller's next export
+  c->bfs_valid = 0;
+  c->counts_valid = c->accumulator ? c->counts_valid : 0;
   return 0;
 }
 

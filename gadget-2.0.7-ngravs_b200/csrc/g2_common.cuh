@@ -182,6 +182,8 @@ struct g2gpu_ctx
   // moments in provisional indexing (U order): the walk records
   float4 *wcells;		// (2+D) float4 per cell, U order
   float4 *wpart;		// leaf-grouped particle records
+  unsigned int *wsrc;		// particle index (current order) behind every record of wpart (dynamic tree update)
+  int tree_npart;		// particles of the last tree construction (0: none)
   unsigned int *hist2, *hist2_scan;	// reference renumbering scratch (size n+1)
   unsigned int *dmin;
   int renumbered;
@@ -225,6 +227,7 @@ int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_stage_bfs(g2gpu_ctx *c);
+int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);
 int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp);
 int g2_pm_download(g2gpu_ctx *c, float *gravpm);
 void g2_pm_destroy(g2gpu_ctx *c);

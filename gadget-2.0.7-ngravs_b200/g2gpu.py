@@ -21,7 +21,7 @@ EXPORTED = [
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
-    "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+    "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
 ]
 
 
@@ -278,6 +278,13 @@ class TreeGravity:
     def inputs_ready(self, n):
         self._chk(self.lib.g2gpu_inputs_ready(self.ctx, int(n)))
         self.n = int(n)
+
+    def update_tree(self, length, s):
+        """Dynamic tree update: re-attach the last tree to freshly uploaded particles with the host's node len / s (reference numbering)."""
+        l = _f32(length)
+        ss = _f32(s)
+        assert len(l) == self.numnodes and ss.size == 3 * self.numnodes * self.D
+        self._chk(self.lib.g2gpu_update_tree(self.ctx, _p(l), _p(ss)))
 
     # ---- long_range_force -> pmforce_periodic (longrange.c:56, pm_periodic.c:204) --------------------------------------
     def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None, download=True):

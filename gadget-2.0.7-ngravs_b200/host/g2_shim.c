@@ -35,6 +35,8 @@ static int *g2_perm = NULL;		/* device particle index -> index in P[] */
 static int g2_perm_identity = 1;
 static float *g2_acc = NULL, *g2_cost = NULL, *g2_oldacc = NULL;
 static int g2_mirror = -1;		/* refresh the host mirror Nodes[]/Nextnode[]/Father[] after every build */
+static int g2_tree_mirrored = 0;	/* Nodes[] holds the tree the device built last and P[] has not been reordered since */
+static int g2_dynamic = -1;		/* follow the reference's dynamic tree updates instead of building a new tree (G2GPU_DYNAMIC_TREE) */
 
 #ifdef PMGRID
 static double g2_srtable[N_GRAVS][N_GRAVS][NTAB];
@@ -113,6 +115,7 @@ void peano_hilbert_order(void)
 {
   int i;
   struct particle_data *tmp;
+  g2_tree_mirrored = 0;
 
   if(ThisTask == 0)
     printf("begin Peano-Hilbert order (GPU)...\n");
@@ -588,6 +591,7 @@ int force_treebuild(int npart)
       Numnodestree = 1;
       return Numnodestree;
     }
+  g2_tree_mirrored = 0;
   g2_push_tables();
   g2_upload(npart);
   g2_check(g2gpu_domain(G2), "domain");
@@ -604,7 +608,10 @@ int force_treebuild(int npart)
     if(forced || dynamic)
       {
 	if(g2_perm_identity)
-	  g2_refresh_mirror(npart);
+	  {
+	    g2_refresh_mirror(npart);
+	    g2_tree_mirrored = npart;
+	  }
 	else if(forced)
 	  {
 	    printf("g2gpu: host tree mirror requested but P[] is not in Peano-Hilbert order\n");
@@ -718,6 +725,31 @@ int grav_tree_compare_key(const void *a, const void *b)	/* gravtree.c:525 */
   return (x > y) - (x < y);
 }
 
+/* The reference does not build a new tree for every force computation: while NumForcesSinceLastDomainDecomp stays below
+ * TotNumPart * TreeDomainUpdateFrequency it drifts the node centres of mass (predict.c:79-91), kicks the node velocities
+ * (timestep.c:329-344) and enlarges nodes (force_update_len, forcetree.c:1005) -- all on the host arrays, which the shim filled from the
+ * device tree at the last construction.  Here the device tree of that construction takes the current P[] and the host's len / s, so the
+ * walk sees the tree the reference's walk would see. */
+static void g2_dynamic_update(int npart)
+{
+  const int nn = Numnodestree;
+  float *len = malloc(sizeof(float) * (size_t) nn), *s = malloc(sizeof(float) * 3 * (size_t) nn * N_GRAVS);
+  int k, j, g;
+  for(k = 0; k < nn; k++)
+    {
+      const struct NODE *nop = &Nodes[All.MaxPart + k];
+      len[k] = nop->len;
+      for(j = 0; j < 3; j++)
+	for(g = 0; g < N_GRAVS; g++)
+	  s[(3 * (size_t) k + j) * N_GRAVS + g] = nop->u.d.s[j][g];
+    }
+  g2_push_tables();
+  g2_upload(npart);
+  g2_check(g2gpu_update_tree(G2, len, s), "update_tree");
+  free(s);
+  free(len);
+}
+
 /* gravtree.c:27.  Build if flagged (always from the current P[]), walk every particle with
  * Ti_endstep == All.Ti_Current on the GPU, epilogue (OldAcc, G, cosmological terms) fused into the walk kernel,
  * results written back into P[], the reference's counters and timings.txt lines kept. */
@@ -732,9 +764,14 @@ void gravity_tree(void)
     set_softenings();
 
   tstart = second();
+  if(g2_dynamic < 0)
+    g2_dynamic = getenv("G2GPU_DYNAMIC_TREE") ? atoi(getenv("G2GPU_DYNAMIC_TREE")) : 1;
   if(ThisTask == 0 && TreeReconstructFlag)
     printf("Tree construction.\n");
-  force_treebuild(NumPart);	/* the device tree is rebuilt for every force computation */
+  if(!TreeReconstructFlag && g2_dynamic && g2_tree_mirrored == NumPart && All.TreeDomainUpdateFrequency > 0.0)
+    g2_dynamic_update(NumPart);	/* the reference keeps its (drifted) tree: so does the device */
+  else
+    force_treebuild(NumPart);	/* a new device tree from the current P[] */
   TreeReconstructFlag = 0;
   tend = second();
   All.CPU_TreeConstruction += timediff(tstart, tend);

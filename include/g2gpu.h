@@ -173,6 +173,14 @@ int g2gpu_treebuild(g2gpu_ctx *ctx, int *numnodes);
 int g2gpu_download_tree(g2gpu_ctx *ctx, float *len, float *center, float *s, float *mass, int *bitflags,
 			int *sibling, int *nextnode, int *father, int *p_nextnode, int *p_father);
 
+/* Dynamic tree update: between two constructions the reference lets its tree follow the particles on the host (node drift
+ * predict.c:79-91, node kicks timestep.c:329-344, force_update_len forcetree.c:1005-1122).  After a fresh g2gpu_upload*() of the SAME
+ * particles in the SAME order as at the last g2gpu_treebuild, this call re-attaches the tree of that construction (instead of
+ * g2gpu_domain + g2gpu_treebuild): particle records are refreshed from the upload, and every node takes the host's values
+ * len[k] = Nodes[MaxPart+k].len and s[(3k+j)*D+g] = Nodes[MaxPart+k].u.d.s[j][g] (reference numbering, as g2gpu_download_tree
+ * delivers them).  g2gpu_walk then sees what the reference's walk sees. */
+int g2gpu_update_tree(g2gpu_ctx *ctx, const float *len, const float *s);
+
 /* struct extNODE (allvars.h:667-677): vs[(3k+j)*D+g] = Extnodes[MaxPart+k].vs[j][g], the centre-of-mass velocity per
  * species (forcetree.c:563-567, 617-619, 667-694); needs the vel argument of g2gpu_upload.  hmax (SPH) is not computed. */
 int g2gpu_download_extnodes(g2gpu_ctx *ctx, float *vs);

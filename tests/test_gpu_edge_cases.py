@@ -268,3 +268,38 @@ def test_full_size_treepm_against_direct_shortrange_sum(side, outdir):
                    ia_per_particle=tm["interactions"] / n), open(os.path.join(outdir, f"fullsize_treepm_{side}.json"), "w"))
     assert np.isfinite(acc).all() and cost.min() >= 1
     assert np.median(err) < 5e-3 and np.percentile(err, 99) < 5e-2, (float(np.median(err)), float(np.percentile(err, 99)))
+
+
+def test_update_tree_reattaches_the_last_tree():
+    """g2gpu_update_tree (dynamic tree update): with unchanged inputs the walk repeats bit for bit; with every particle and
+    every node centre of mass shifted by the same vector (what a uniform drift does to the reference's tree) the Barnes-Hut walk, which
+    only looks at distances and node sizes, gives the same interaction lists and forces."""
+    from g2gpu import TreeGravity, G2Error
+    n = 30000
+    pos, mass, ptype = g2test.gaussian_blobs(n, seed=9)
+    tg = TreeGravity(max_part=int(1.1 * n) + 64, n_gravs=2)
+    tg.set_species(g2test.GRAV_D2, g2test.force_softening(g2test.SOFT_NP))
+    tg.set_laws()
+    wp = tg.walk_params(theta=0.5, errtol=0.005, G=1.0)
+    with pytest.raises(G2Error):
+        tg.update_tree(np.zeros(0), np.zeros(0))            # no tree yet
+    tg.upload(pos, mass, ptype)
+    tg.domain()
+    tg.treebuild()
+    tg.walk(wp)
+    acc0, cost0, _ = tg.download_acc()
+    t = tg.tree()
+    tg.upload(pos, mass, ptype)
+    tg.update_tree(t["len"], t["s"])
+    tg.walk(wp)
+    acc1, cost1, _ = tg.download_acc()
+    assert np.array_equal(acc0.view(np.uint32), acc1.view(np.uint32)) and np.array_equal(cost0, cost1)
+    shift = np.array([4.0, -2.0, 1.0], dtype=np.float32)
+    tg.upload(pos + shift, mass, ptype)
+    tg.update_tree(t["len"], t["s"] + shift[None, :, None])
+    tg.walk(wp)
+    acc2, cost2, _ = tg.download_acc()
+    tg.close()
+    assert np.sum(cost2 != cost0) <= 0.002 * n
+    err = g2test.rel_err(acc2, acc0)
+    assert np.median(err) < 1e-5 and np.percentile(err, 99.9) < 1e-3

@@ -65,3 +65,24 @@ def test_new_tree_every_step_matches_cpu_program(tmp_path, outdir):
     assert np.median(d) < 2e-6 * np.median(move) + 1e-6
     assert d.max() < 1e-3 * np.median(move)
     assert np.median(dv) < 1e-5
+
+
+@pytest.mark.skipif(not (have("g2gpu") and have("ref")), reason="integration/Makefile has not been run")
+def test_dynamic_tree_updates_match_cpu_program(tmp_path, outdir):
+    """TreeDomainUpdateFrequency = 0.1 (shipped): between two constructions the reference drifts and kicks its tree nodes on the host
+    (predict.c:79-91, timestep.c:329-344, force_update_len) and the shim hands that drifted tree to the device (g2gpu_update_tree) instead
+    of building a new one, so both programs walk the same tree at every step: agreement as tight as with a new tree per step."""
+    a = fullrun.run("ref", "f32", str(tmp_path / "cpu"), time_max=0.02, TreeDomainUpdateFrequency=0.1)
+    b = fullrun.run("g2gpu", "f32", str(tmp_path / "gpu"), time_max=0.02, TreeDomainUpdateFrequency=0.1)
+    c = fullrun.run("g2gpu", "f32", str(tmp_path / "gpu_rebuild"), time_max=0.02, TreeDomainUpdateFrequency=0.1, env={"G2GPU_DYNAMIC_TREE": "0"})
+    assert a["steps"] == b["steps"] and a["force_computations"] == b["force_computations"]
+    move = np.linalg.norm(a["snap"]["pos"] - fullrun.example_ic()[0], axis=1)
+    d = np.linalg.norm(a["snap"]["pos"] - b["snap"]["pos"], axis=1)
+    d_rebuild = np.linalg.norm(a["snap"]["pos"] - c["snap"]["pos"], axis=1)
+    json.dump(dict(cpu=summary(a), gpu=summary(b), gpu_rebuild=summary(c), pos_diff_median=float(np.median(d)), pos_diff_max=float(d.max()),
+                   pos_diff_max_rebuild_every_step=float(d_rebuild.max()), displacement_median=float(np.median(move))),
+              open(os.path.join(outdir, "fullrun_dynamic_tree.json"), "w"))
+    assert abs(a["ia_per_part_mean"] - b["ia_per_part_mean"]) < 1e-3 * a["ia_per_part_mean"]
+    assert np.median(d) < 2e-6 * np.median(move) + 1e-6
+    assert d.max() < 1e-3 * np.median(move)
+    assert d.max() < d_rebuild.max()            # following the reference's tree is closer to it than a fresh tree at every step
