@@ -108,6 +108,13 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	  const float4 *rec = A.cells + (size_t) (live ? cur : 0u) * R;
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+#ifdef G2_WALK_PREFETCH
+	  // EXPERIMENT (off): the next record is either the first child (cur + 1, adjacent) or the sibling; asking L1 for the sibling's line
+	  // now (prefetch.global.L1, no destination register) would hide its L2 latency behind this visit.  MEASURED (B200, round 1): 208.3 ->
+	  // 215.3 ms at 256^3, 3.69 -> 4.16 ms Hernquist 1 M: the kernel is issue bound, the extra instructions cost more than the latency.
+	  if(G == 32 && live && w.x < end)
+	    asm volatile("prefetch.global.L1 [%0];" :: "l"(A.cells + (size_t) w.x * R));
+#endif
 	  bool open = false;
 	  // TreePM: a cell that can interact with (or must be opened by) a target lies within rcut + len of it, so for
 	  // len < L/2 - rcut every point of the cell has the same periodic image as the cell centre; points of cells that
