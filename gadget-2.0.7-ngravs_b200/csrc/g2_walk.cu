@@ -455,7 +455,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
 
   size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
   const int ntgt = c->w_hi - c->w_lo;
-  int grid = c->nsm * 8;
+  int grid = c->nsm * (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS);	// every CTA resident: the chunk counter balances the load
   int need = g2_cdiv(g2_cdiv(ntgt, 32), WALK_WARPS);
   if(grid > need)
     grid = need;

@@ -11,7 +11,9 @@
 #define WALK_MINBLOCKS 8	// 64 registers: measured 4 % faster than 9 blocks / 56 registers once the table base and the no-wrap bound stay in registers
 #endif
 #ifndef WALK_WIDE_D
-#define WALK_WIDE_D 3		// from this many species on the per-species registers no longer fit 56 registers without spills
+#define WALK_WIDE_D 3		// from this many species on the per-species registers no longer fit 64 registers without spills
+#endif
+#ifndef WALK_MINBLOCKS_WIDE
 #define WALK_MINBLOCKS_WIDE 8
 #endif
 
