@@ -77,7 +77,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   for(int t = 0; t < 6; t++)
     c->force_softening[t] = 1.0;
   G2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for(int i = 0; i < 16; i++)
+  for(int i = 0; i < 20; i++)
     G2_CUDA(cudaEventCreate(&c->ev[i]));
 
   const size_t np = (size_t) cfg->max_part, nn = (size_t) cfg->max_nodes;
@@ -141,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -164,7 +164,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     cudaFreeHost(c->h_export);
   if(c->d_export)
     cudaFree(c->d_export);
-  for(int i = 0; i < 16; i++)
+  for(int i = 0; i < 20; i++)
     if(c->ev[i])
       cudaEventDestroy(c->ev[i]);
   if(c->stream)
@@ -679,6 +679,91 @@ extern "C" int g2gpu_download_acc(g2gpu_ctx *c, float *acc, float *cost, float *
   G2_CUDA(cudaEventRecord(c->ev[12], st));
   G2_CUDA(cudaStreamSynchronize(st));
   c->d2h_bytes = n * ((acc ? 12 : 0) + (cost ? 4 : 0) + (oldacc ? 4 : 0));
+  return 0;
+}
+
+// ---- potential walk (g2_pot.cu) ---------------------------------------------------------------------------------
+extern "C" int g2gpu_set_potential_laws(g2gpu_ctx *c, const int *pot_id, const int *potspline_id)
+{
+  if(!c || !pot_id || !potspline_id)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  const int D = c->D;
+  for(int i = 0; i < D * D; i++)
+    {
+      if(pot_id[i] < G2GPU_POT_NONE || pot_id[i] > G2GPU_POT_NEG_NEWTONIAN)	// ngravs_core.c:348-358: every slot must be wired
+	return g2_fail(G2GPU_ERR_LAW, "PotentialFxns[%d][%d] is not a registered potential (%d)", i / D, i % D, pot_id[i]);
+      if(potspline_id[i] < G2GPU_POTSPLINE_NONE || potspline_id[i] > G2GPU_POTSPLINE_NEG_PLUMMER)
+	return g2_fail(G2GPU_ERR_LAW, "PotentialSplines[%d][%d] is not a registered potential spline (%d)", i / D, i % D, potspline_id[i]);
+      c->potfxn[i] = pot_id[i];
+      c->potspline[i] = potspline_id[i];
+    }
+  c->potlaws_set = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_set_srpot_table(g2gpu_ctx *c, const double *table)
+{
+  if(!c || !table)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  const int D = c->D, ntab = c->cfg.ntab;
+  if(ntab <= 0)
+    return g2_fail(G2GPU_ERR_ARG, "ntab not configured");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  int nu = 0;
+  int first[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  for(int i = 0; i < D * D; i++)
+    {				// identical pair tables are stored once
+      int found = -1;
+      for(int u = 0; u < nu && found < 0; u++)
+	if(memcmp(table + (size_t) first[u] * ntab, table + (size_t) i * ntab, sizeof(double) * ntab) == 0)
+	  found = u;
+      if(found < 0)
+	{
+	  first[nu] = i;
+	  found = nu++;
+	}
+      c->pot_tabmap[i] = (unsigned char) found;
+    }
+  if((size_t) nu * ntab * sizeof(float) > 200 * 1024)
+    return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range potential tables do not fit in shared memory", nu);
+  float *hf = (float *) malloc(sizeof(float) * (size_t) nu * ntab);
+  if(!hf)
+    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
+  for(int u = 0; u < nu; u++)
+    for(int k = 0; k < ntab; k++)
+      hf[(size_t) u * ntab + k] = (float) table[(size_t) first[u] * ntab + k];
+  if(c->d_pottable_f)
+    cudaFree(c->d_pottable_f);
+  c->d_pottable_f = nullptr;
+  int rc = dalloc(&c->d_pottable_f, (size_t) nu * ntab);
+  if(rc == 0 && cudaMemcpy(c->d_pottable_f, hf, sizeof(float) * (size_t) nu * ntab, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = g2_fail(G2GPU_ERR_CUDA, "table upload failed");
+  free(hf);
+  if(rc)
+    return rc;
+  c->pot_ntables = nu;
+  c->pottable_set = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
+{
+  if(!c || !wp)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_stage_potential(c, wp);
+}
+
+extern "C" int g2gpu_download_potential(g2gpu_ctx *c, float *pot, double *kernel_ms)
+{
+  if(!c || !pot)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(!c->pot_valid)
+    return g2_fail(G2GPU_ERR_STATE, "g2gpu_potential has not run");
+  G2_CUDA(cudaMemcpyAsync(pot, c->pot, sizeof(float) * (size_t) c->npart, cudaMemcpyDeviceToHost, c->stream));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  if(kernel_ms)
+    *kernel_ms = c->pot_ms;
   return 0;
 }
 

@@ -86,7 +86,7 @@ struct g2gpu_ctx
   int D;			// n_gravs
   int nsm;
   cudaStream_t stream;
-  cudaEvent_t ev[16];
+  cudaEvent_t ev[20];
 
   int npart;			// current particle count
   int nactive;			// active particles (all ranks)
@@ -100,6 +100,14 @@ struct g2gpu_ctx
   int srtable_set;
   int sr_ntables;		// unique short-range tables (identical pair tables are stored once)
   unsigned char sr_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  // potential walk (g2_pot.cu)
+  int potfxn[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS], potspline[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// PotentialFxns / PotentialSplines [tgt*D+src]
+  int potlaws_set, pottable_set, pot_valid;
+  float *d_pottable_f;		// unique shortrange_fourier_pot tables, NTAB floats each
+  int pot_ntables;
+  unsigned char pot_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  float *pot;			// n, current particle order (allocated on first use)
+  double pot_ms;
   int acc_double;		// accumulate accelerations in FP64 (default) or FP32
   int accumulator;		// NGRAVS_ACCUMULATOR: nodes carry the particle count per species (wcnt), laws receive it as N
   int counts_valid;		// wcnt belongs to the current tree
@@ -225,6 +233,7 @@ int g2_stage_domain(g2gpu_ctx *c);
 int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_stage_bfs(g2gpu_ctx *c);
 int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);

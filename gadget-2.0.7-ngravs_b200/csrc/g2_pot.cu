@@ -1,0 +1,336 @@
+// g2_pot.cu — the tree potential walks of compute_potential (potential.c:22-354): force_treeevaluate_potential_shortrange
+// (forcetree.c:2789-3163, TreePM) and force_treeevaluate_potential (forcetree.c:2467-2776, no PM, non-periodic).  SURVEY.md 8f-3.
+//
+// Same traversal as g2_walk.cu (one cursor per 32 tree-adjacent targets over the depth-first cell records, per-lane decisions, warp
+// vote to descend), with the potential walk's own rules, reproduced as the reference has them:
+//   * every particle is a target (potential.c:86), the target itself included: its self term PotentialSplines(m, h, 0) is removed by
+//     the caller afterwards (potential.c:250-254);
+//   * TreePM cull: the box test ALONE (|NEAREST(center - pos)| > rcut + len/2 on some axis, forcetree.c:2988-3015), not preceded by
+//     the r2min > rcut^2 test of the force walk;
+//   * a term counts if tabindex = (int)(r * asmthfac) < NTAB (forcetree.c:3108-3112, 3128-3132);
+//   * particle term, r >= h:  pot -= PotentialFxns(m, r) - utorwpi * shortrange_fourier_pot[tgt][src][tabindex]   (forcetree.c:3115: the
+//     table term carries NO mass factor in the reference); r < h: pot += PotentialSplines(m, h, r);
+//   * node term: the table term is present only in a -DNGRAVS_ACCUMULATOR build (forcetree.c:3134-3140) -- option "accumulator";
+//     species with zero mass in the node are skipped (forcetree.c:3123).
+// Terms are evaluated in FP32 and summed into an FP64 accumulator whenever the warp descends (like the force walk); the result is
+// stored as FLOAT like P[].Potential.  Decisions that fall within float rounding of the cull boundary are re-taken in FP64, which is
+// what the reference computes in.
+#include "g2_walk_common.cuh"
+
+struct PotArgs
+{
+  const float4 *__restrict__ cells;
+  const float4 *__restrict__ wpart;
+  const unsigned int *__restrict__ tq;
+  const G2PRec *__restrict__ prec;
+  const float *__restrict__ pottable;	// unique tables, NTAB floats each
+  float *__restrict__ pot;
+  unsigned int *__restrict__ work_counter;
+  int lo, hi, numnodes, ntab, ntables, node_table_term;
+  float theta2, errtol, boxsize, boxinv, rcut, asmthfac, utorwpi;
+  double rcut_d, boxsize_d;
+  float fsoft[6];
+  int t2g[6];
+  unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  int potfxn[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS], potspline[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+};
+
+// plummer_pot, ngravs.c:459-471 (u = r/h)
+__device__ __forceinline__ float pot_plummer(float m, float h, float r)
+{
+  const float hinv = __frcp_rn(h), u = r * hinv;
+  if(u < 0.5f)
+    return m * hinv * (-2.8f + u * u * (5.333333333333f + u * u * (6.4f * u - 9.6f)));
+  return m * hinv * (-3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u))));
+}
+
+// one species term; returns the amount to ADD to pot
+template <bool SR>
+__device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restrict__ s_tab, int ij, float m, float r2, float h, bool table_term)
+{
+  const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
+  const float r = r2 * rinv;
+  int tabindex = 0;
+  if(SR)
+    {
+      tabindex = (int) (r * A.asmthfac);
+      if(tabindex >= A.ntab)
+	return 0.0f;
+    }
+  if(r >= h)
+    {
+      float p;
+      switch (A.potfxn[ij])
+	{
+	case G2GPU_POT_NEWTONIAN: p = m * rinv; break;	// ngravs.c:368
+	case G2GPU_POT_NEG_NEWTONIAN: p = -m * rinv; break;	// ngravs.c:375
+	default: p = 0.0f; break;	// none, ngravs.c:344
+	}
+      if(SR && table_term)
+	p -= A.utorwpi * s_tab[(int) A.tabmap[ij] * A.ntab + tabindex];
+      return -p;
+    }
+  switch (A.potspline[ij])
+    {
+    case G2GPU_POTSPLINE_PLUMMER: return pot_plummer(m, h, r);	// ngravs.c:459
+    case G2GPU_POTSPLINE_NEG_PLUMMER: return -pot_plummer(m, h, r);	// ngravs.c:476
+    default: return 0.0f;
+    }
+}
+
+__device__ __forceinline__ double nearest_d(double x, double box)
+{
+  if(x > 0.5 * box)
+    x -= box;
+  if(x < -0.5 * box)
+    x += box;
+  return x;
+}
+
+template <int D, bool SR, bool UNEQUAL>
+__global__ void __launch_bounds__(WALK_THREADS, 6) pot_kernel(const PotArgs A)
+{
+  constexpr bool PERIODIC = SR;	// the reference's TreePM potential walk is the periodic one
+  extern __shared__ float s_tab[];
+  __shared__ unsigned int s_chunk[WALK_WARPS];
+  if(SR)
+    {
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
+	s_tab[i] = A.pottable[i];
+      __syncthreads();
+    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = 2 + D;
+  const int nchunks = (A.hi - A.lo + 31) >> 5;
+  const unsigned int end = (unsigned int) A.numnodes;
+
+  while(true)
+    {
+      if(lane == 0)
+	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+      __syncwarp();
+      const unsigned int chunk = s_chunk[warp];
+      __syncwarp();
+      if(chunk >= (unsigned int) nchunks)
+	break;
+      const int ti = A.lo + (int) chunk * 32 + lane;
+      const bool valid = ti < A.hi;
+      unsigned int idx = 0;
+      float px = 0, py = 0, pz = 0, aold = 0;
+      int ptype = 1;
+      if(valid)
+	{
+	  idx = A.tq[ti];
+	  const G2PRec p = A.prec[idx];
+	  px = p.x; py = p.y; pz = p.z;
+	  ptype = p.type;
+	  aold = A.errtol * p.oldacc;	// forcetree.c:2830
+	}
+      const int tg = A.t2g[ptype];
+      const float hself = A.fsoft[ptype];
+      double pot = 0.0;
+      float fpot = 0.0f;
+      unsigned int skip_until = valid ? 0u : 0xffffffffu;
+      unsigned int cur = 0u;
+
+      while(cur < end)
+	{
+	  const float4 *rec = A.cells + (size_t) cur * R;
+	  const float4 q0 = __ldg(rec);
+	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+	  bool open = false;
+	  if(cur >= skip_until)
+	    {
+	      float r2[D], mass[D];
+	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
+	      const float len = q0.x;
+	      const float cxr = q0.y - px, cyr = q0.z - py, czr = q0.w - pz;
+	      bool done = false;
+	      if(SR)
+		{		// forcetree.c:2988-3015
+		  const float eff = A.rcut + 0.5f * len;
+		  const float d0 = fabsf(nearest<PERIODIC>(cxr, A.boxsize, A.boxinv)), d1 = fabsf(nearest<PERIODIC>(cyr, A.boxsize, A.boxinv)),
+		    d2 = fabsf(nearest<PERIODIC>(czr, A.boxsize, A.boxinv));
+		  const float dmax = fmaxf(fmaxf(d0, d1), d2);
+		  done = dmax > eff;
+		  if(fabsf(dmax - eff) < 4.0e-6f * A.boxsize)
+		    {		// within float rounding of the boundary: decide as the reference does, in double
+		      const double effd = A.rcut_d + 0.5 * (double) len;
+		      const double e0 = fabs(nearest_d((double) q0.y - (double) px, A.boxsize_d)), e1 = fabs(nearest_d((double) q0.z - (double) py, A.boxsize_d)),
+			e2 = fabs(nearest_d((double) q0.w - (double) pz, A.boxsize_d));
+		      done = e0 > effd || e1 > effd || e2 > effd;
+		    }
+		}
+	      if(!done)
+		{
+#pragma unroll
+		  for(int g = 0; g < D; g++)
+		    {
+		      const float4 q = __ldg(rec + 1 + g);
+		      mass[g] = q.w;
+		      summass += q.w;
+		      const float dx = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
+		      const float dy = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
+		      const float dz = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
+		      r2[g] = dx * dx + dy * dy + dz * dz;
+		      r2min = fminf(r2min, r2[g]);
+		      r2max = fmaxf(r2max, r2[g]);
+		    }
+		  if(A.theta2 > 0.0f)
+		    {		// forcetree.c:3017-3025
+		      if(len * len > r2min * A.theta2)
+			open = true;
+		    }
+		  else
+		    {		// forcetree.c:3026-3047
+		      if(summass * len * len > r2min * r2min * aold)
+			open = true;
+		      else if(fabsf(cxr) < 0.60f * len && fabsf(cyr) < 0.60f * len && fabsf(czr) < 0.60f * len)
+			open = true;
+		    }
+		}
+	      float h = hself;
+	      if(UNEQUAL && !done && !open)
+		{		// forcetree.c:3049-3077 (the record carries ForceSoftening[maxsofttype]; +inf and the mixed bit for an empty node)
+		  const float hnode = __uint_as_float(w.w);
+		  if(h < hnode)
+		    {
+		      h = hnode;
+		      if(r2max < h * h && ((w.z >> 28) & 1))
+			open = true;
+		    }
+		}
+	      if(!open)
+		{
+		  skip_until = w.x;
+		  if(!done)
+		    {
+#pragma unroll
+		      for(int g = 0; g < D; g++)
+			if(mass[g] != 0.0f)	// forcetree.c:3123
+			  fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0);
+		    }
+		}
+	    }
+	  const unsigned int ball = __ballot_sync(0xffffffffu, open);
+	  if(ball != 0u)
+	    {
+	      pot += (double) fpot;
+	      fpot = 0.0f;
+	      const unsigned int np = w.z & 15u;
+	      for(unsigned int j = 0; j < np; j++)
+		{
+		  const float4 p = __ldg(A.wpart + w.y + j);
+		  if(open)
+		    {
+		      const int stype = (w.z >> (4 + 3 * j)) & 7;
+		      const int sg = A.t2g[stype];
+		      float h = hself;
+		      if(UNEQUAL)
+			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:2958-2961
+		      const float dx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
+		      const float dy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
+		      const float dz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
+		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true);
+		    }
+		}
+	      cur = cur + 1u;
+	    }
+	  else
+	    cur = w.x;
+	}
+      pot += (double) fpot;
+      if(valid)
+	A.pot[idx] = (float) pot;	// forcetree.c:3158
+    }
+}
+
+template <int D>
+static void launch_pot(g2gpu_ctx *c, const PotArgs &A, int grid, size_t smem, bool sr, bool unequal)
+{
+#define G2_P(SRv, UNEv) do { \
+    if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+    pot_kernel<D, SRv, UNEv><<<grid, WALK_THREADS, smem, c->stream>>>(A); } while(0)
+  if(sr) { if(unequal) G2_P(true, true); else G2_P(true, false); }
+  else   { if(unequal) G2_P(false, true); else G2_P(false, false); }
+#undef G2_P
+}
+
+int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
+{
+  if(c->stage < 3)
+    return g2_fail(G2GPU_ERR_STATE, "potential: tree has not been built");
+  if(!c->potlaws_set)
+    return g2_fail(G2GPU_ERR_LAW, "potential: pair potential laws not set (g2gpu_set_potential_laws)");
+  const int n = c->npart, D = c->D;
+  const bool sr = c->cfg.shortrange != 0;
+  if(sr && !c->pottable_set)
+    return g2_fail(G2GPU_ERR_STATE, "potential: short-range potential table not set (g2gpu_set_srpot_table)");
+  if(!sr && c->cfg.periodic)
+    return g2_fail(G2GPU_ERR_ARG, "potential: a periodic box without PM needs the lattice-sum potential tables (lattice_pot_corr, forcetree.c:3895), which are not built");
+  cudaStream_t st = c->stream;
+  if(!c->pot)
+    {
+      G2_CUDA(cudaMalloc((void **) &c->pot, sizeof(float) * (size_t) c->cfg.max_part));
+      G2_CUDA(cudaMemsetAsync(c->pot, 0, sizeof(float) * (size_t) c->cfg.max_part, st));
+    }
+  PotArgs A;
+  memset(&A, 0, sizeof(A));
+  const int nr = c->cfg.nranks > 0 ? c->cfg.nranks : 1, rk = c->cfg.rank;
+  A.cells = c->wcells; A.wpart = c->wpart; A.tq = c->tq; A.prec = c->prec; A.pottable = c->d_pottable_f; A.pot = c->pot;
+  A.work_counter = (unsigned int *) (c->d_counters + 5);
+  A.lo = (int) ((long long) n * rk / nr); A.hi = (int) ((long long) n * (rk + 1) / nr);
+  A.numnodes = c->numnodes; A.ntab = c->cfg.ntab; A.ntables = c->pot_ntables;
+  A.node_table_term = (c->accumulator != 0);
+  A.theta2 = (float) (wp->theta * wp->theta);
+  A.errtol = (float) wp->errtol_force_acc;
+  A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
+  A.boxsize_d = wp->boxsize;
+  if(sr)
+    {
+      if(!(wp->asmth > 0) || !(wp->boxsize > 0))
+	return g2_fail(G2GPU_ERR_ARG, "potential: asmth and boxsize must be positive under the TreePM split");
+      A.rcut = (float) wp->rcut; A.rcut_d = wp->rcut;
+      A.asmthfac = (float) (0.5 / wp->asmth * (c->cfg.ntab / 3.0));	// forcetree.c:2862
+      A.utorwpi = (float) (1.0 / (2 * M_PI * wp->asmth));	// forcetree.c:2865
+    }
+  for(int t = 0; t < 6; t++)
+    {
+      A.fsoft[t] = (float) c->force_softening[t];
+      A.t2g[t] = c->type_to_grav[t];
+    }
+  memcpy(A.tabmap, c->pot_tabmap, sizeof(A.tabmap));
+  memcpy(A.potfxn, c->potfxn, sizeof(A.potfxn));
+  memcpy(A.potspline, c->potspline, sizeof(A.potspline));
+  const size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
+  int grid = c->nsm * 6, need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
+  if(grid > need)
+    grid = need;
+  G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));
+  G2_CUDA(cudaEventRecord(c->ev[16], st));
+  if(grid > 0)
+    {
+      const bool uneq = c->cfg.unequal_softenings != 0;
+      switch (D)
+	{
+#ifndef G2_FAST_BUILD
+	case 1: launch_pot<1>(c, A, grid, smem, sr, uneq); break;
+	case 3: launch_pot<3>(c, A, grid, smem, sr, uneq); break;
+	case 5: launch_pot<5>(c, A, grid, smem, sr, uneq); break;
+	case 6: launch_pot<6>(c, A, grid, smem, sr, uneq); break;
+#endif
+	case 2: launch_pot<2>(c, A, grid, smem, sr, uneq); break;
+	case 4: launch_pot<4>(c, A, grid, smem, sr, uneq); break;
+	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
+	}
+      c->launches++;
+    }
+  G2_CUDA(cudaEventRecord(c->ev[17], st));
+  G2_CUDA(cudaGetLastError());
+  G2_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[16], c->ev[17]);
+  c->pot_ms = ms;
+  c->pot_valid = 1;
+  return 0;
+}

@@ -56,6 +56,18 @@ enum g2gpu_law
   G2GPU_SPLINE_SOURCEBARYONBAM = 21	/* sourcebaryonbam_spline() ngravs.c:616 */
 };
 
+/* Pair potentials shipped in ngravs.c for the tree potential walks: PotentialFxns[tgt][src](pm, m, h, r, N) for r >= h,
+ * PotentialSplines[tgt][src](pm, m, h, r, N) for r < h (allvars.h:147-148).  The BAM potentials (ngravs.c:672-760) are not registered. */
+enum g2gpu_potlaw
+{
+  G2GPU_POT_NONE = 32,		/* none()              ngravs.c:344 */
+  G2GPU_POT_NEWTONIAN = 33,	/* newtonian_pot()     ngravs.c:368 */
+  G2GPU_POT_NEG_NEWTONIAN = 34,	/* neg_newtonian_pot() ngravs.c:375 */
+  G2GPU_POTSPLINE_NONE = 48,	/* none()              as a spline */
+  G2GPU_POTSPLINE_PLUMMER = 49,	/* plummer_pot()       ngravs.c:459 */
+  G2GPU_POTSPLINE_NEG_PLUMMER = 50	/* neg_plummer_pot()   ngravs.c:476 */
+};
+
 /* k-space Green's functions of the periodic PM force shipped in ngravs.c (GreensFxns[source][target], allvars.h:140; mesh units). */
 enum g2gpu_greens
 {
@@ -199,6 +211,22 @@ int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
  * box gets the exact lattice (Ewald) correction of all images added (what the reference tabulates and interpolates in lattice_corr,
  * forcetree.c:3803, for gravity_forcetest), i.e. the complete periodic Newtonian force the TreePM sum (tree + PM) approximates. */
 int g2gpu_direct(g2gpu_ctx *ctx, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
+
+/* ---- tree potential of compute_potential (potential.c:22-354): force_treeevaluate_potential_shortrange
+ *      (forcetree.c:2789-3163) when config.shortrange is set, else force_treeevaluate_potential (forcetree.c:2467-2776; non-periodic
+ *      only -- the periodic variant needs the lattice-sum tables of lattice_pot_corr, which are not built: G2GPU_ERR_ARG).
+ *      g2gpu_potential walks the current tree (after g2gpu_treebuild or g2gpu_update_tree) for EVERY particle (potential.c:86) with the
+ *      opening criterion of wp (theta, errtol_force_acc with the uploaded OldAcc) and stores what the reference's walk stores in
+ *      P[].Potential (forcetree.c:3158): the pre-G sum, self term included; the caller applies potential.c:250-270 (self term, G).
+ *      The node terms carry the short-range table term only with the option "accumulator" (forcetree.c:3134-3140).  With nranks > 1
+ *      a rank walks its 1/nranks slice of the tree-ordered particles. ---- */
+/* pot_id / potspline_id: D*D ids of enum g2gpu_potlaw indexed [target][source]. */
+int g2gpu_set_potential_laws(g2gpu_ctx *ctx, const int *pot_id, const int *potspline_id);
+/* shortrange_fourier_pot[target][source][NTAB] (forcetree.c:34, filled at 3346), as double. */
+int g2gpu_set_srpot_table(g2gpu_ctx *ctx, const double *table);
+int g2gpu_potential(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
+/* pot[n] = P[].Potential as left by the walk, in CURRENT particle order; *kernel_ms (optional) = CUDA-event time of the walk kernel. */
+int g2gpu_download_potential(g2gpu_ctx *ctx, float *pot, double *kernel_ms);
 
 /* ---- periodic PM long-range force: pmforce_periodic (pm_periodic.c:204-790), the caller of which is long_range_force
  *      (longrange.c:56-141; accel.c:36 runs it BEFORE gravity_tree).  Works on the particle records uploaded last, in UPLOAD

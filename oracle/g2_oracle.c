@@ -60,6 +60,10 @@ typedef struct g2o
   int accel_id[MAXG][MAXG], spline_id[MAXG][MAXG];
   double lawpar[MAXG][MAXG][4];
   double *srtab;			/* [D][D][ntab] */
+  double *srpot;			/* shortrange_fourier_pot [D][D][ntab] */
+  int pot_id[MAXG][MAXG], potspline_id[MAXG][MAXG];	/* PotentialFxns / PotentialSplines, ids of include/g2gpu.h */
+  int node_table_term;			/* -DNGRAVS_ACCUMULATOR build: node terms of the short-range potential carry the table term */
+  float *pot;				/* P[].Potential after the potential walk */
   double boxsize, G, theta, errtol, asmth, rcut;
   int n;
   particle *P;
@@ -187,7 +191,7 @@ void g2o_destroy(g2o * o)
 {
   if(!o)
     return;
-  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o);
+  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o->srpot); free(o->pot); free(o);
 }
 
 void g2o_set_species(g2o * o, const int *t2g, const double *fsoft)
@@ -819,6 +823,251 @@ static int tree_evaluate(g2o * o, int target)
   return ninteractions;
 }
 
+/* ---- potential walks ----
+ * PotentialFxns[tg][sg](pm, m, h, r, N) / PotentialSplines[tg][sg](pm, m, h, r, N): ngravs.c:368, 375, 459-490 */
+static double plummer_pot_law(double m, double h, double r)	/* ngravs.c:459-471 */
+{
+  double hinv = 1 / h;
+  r *= hinv;
+  if(r < 0.5)
+    return m * hinv * (-2.8 + r * r * (5.333333333333 + r * r * (6.4 * r - 9.6)));
+  return m * hinv * (-3.2 + 0.066666666667 / r + r * r * (10.666666666667 + r * (-16.0 + r * (9.6 - 2.133333333333 * r))));
+}
+
+static double pot_fxn(const g2o * o, int tg, int sg, double m, double r)
+{
+  switch (o->pot_id[tg][sg])
+    {
+    case 33: return m / r;
+    case 34: return -m / r;
+    default: return 0.0;
+    }
+}
+
+static double pot_spline(const g2o * o, int tg, int sg, double m, double h, double r)
+{
+  switch (o->potspline_id[tg][sg])
+    {
+    case 49: return plummer_pot_law(m, h, r);
+    case 50: return -plummer_pot_law(m, h, r);
+    default: return 0.0;
+    }
+}
+
+double g2o_potfxn(g2o * o, int tg, int sg, double m, double h, double r) { (void) h; return pot_fxn(o, tg, sg, m, r); }
+double g2o_potspline(g2o * o, int tg, int sg, double m, double h, double r) { return pot_spline(o, tg, sg, m, h, r); }
+
+void g2o_set_potlaws(g2o * o, const int *pot_id, const int *potspline_id, int node_table_term)
+{
+  int i, j;
+  for(i = 0; i < o->D; i++)
+    for(j = 0; j < o->D; j++)
+      {
+	o->pot_id[i][j] = pot_id[i * o->D + j];
+	o->potspline_id[i][j] = potspline_id[i * o->D + j];
+      }
+  o->node_table_term = node_table_term;
+}
+
+void g2o_set_srpot(g2o * o, const double *tab)
+{
+  size_t n = (size_t) o->D * o->D * o->ntab;
+  free(o->srpot);
+  o->srpot = malloc(sizeof(double) * n);
+  memcpy(o->srpot, tab, sizeof(double) * n);
+}
+
+/* force_treeevaluate_potential_shortrange (forcetree.c:2789-3163) when o->shortrange, else force_treeevaluate_potential
+ * (forcetree.c:2467-2776; the latter does not compile in the reference -- this branch restates what its text says, minus the
+ * lattice correction of PERIODIC builds -- so it is NOT pinned against a reference run). */
+static void tree_potential(g2o * o, int target)
+{
+  const int D = o->D, MP = o->maxpart, SR = o->shortrange, PER = o->periodic;
+  const particle *tp = &o->P[target];
+  double r2[MAXG], mass[MAXG], r, h, d[3];
+  double pot = 0;
+  const double pos[3] = { tp->pos[0], tp->pos[1], tp->pos[2] };
+  const int ptype = tp->type, pg = o->t2g[ptype];
+  const double aold = o->errtol * tp->oldacc;
+  const double boxsize = o->boxsize, boxhalf = 0.5 * o->boxsize;
+  const double rcut = o->rcut, asmth = o->asmth;
+  const double asmthfac = SR ? 0.5 / asmth * (o->ntab / 3.0) : 0, utorwpi = SR ? 1.0 / (2 * M_PI * asmth) : 0;
+  int no = MP, sG, g, k;
+  node *nop = 0;
+
+  h = o->fsoft[ptype];
+  while(no >= 0)
+    {
+      if(no < MP)
+	{
+	  const particle *sp = &o->P[no];
+	  sG = o->t2g[sp->type];
+	  mass[sG] = sp->mass;
+	  for(k = 0; k < 3; k++)
+	    {
+	      d[k] = sp->pos[k] - pos[k];
+	      if(PER)
+		d[k] = NEAREST(d[k]);
+	    }
+	  r2[sG] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+	  if(o->unequal)
+	    {
+	      h = o->fsoft[ptype];
+	      if(h < o->fsoft[sp->type])
+		h = o->fsoft[sp->type];
+	    }
+	  no = o->nextnode[no];
+	}
+      else
+	{
+	  double r2min = INFINITY, r2max = -INFINITY, summass = 0;
+	  nop = NODE_OF(o, no);
+	  for(g = 0; g < D; g++)
+	    {
+	      mass[g] = nop->mass[g];
+	      summass += nop->mass[g];
+	      for(k = 0; k < 3; k++)
+		{
+		  d[k] = nop->s[k][g] - pos[k];
+		  if(PER)
+		    d[k] = NEAREST(d[k]);
+		}
+	      r2[g] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+	      if(r2[g] < r2min)
+		r2min = r2[g];
+	      if(r2[g] > r2max)
+		r2max = r2[g];
+	    }
+	  sG = -1;
+	  if(SR)
+	    {			/* forcetree.c:2988-3015: the box test alone */
+	      double eff_dist = rcut + 0.5 * nop->len, dist;
+	      int cull = 0;
+	      for(k = 0; k < 3 && !cull; k++)
+		{
+		  dist = nop->center[k] - pos[k];
+		  if(PER)
+		    dist = NEAREST(dist);
+		  if(dist < -eff_dist || dist > eff_dist)
+		    cull = 1;
+		}
+	      if(cull)
+		{
+		  no = nop->sibling;
+		  continue;
+		}
+	    }
+	  if(o->theta)
+	    {
+	      if(nop->len * nop->len > r2min * o->theta * o->theta)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  else
+	    {
+	      if(summass * nop->len * nop->len > r2min * r2min * aold)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	      if(fabs(nop->center[0] - pos[0]) < 0.60 * nop->len && fabs(nop->center[1] - pos[1]) < 0.60 * nop->len
+		 && fabs(nop->center[2] - pos[2]) < 0.60 * nop->len)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  if(o->unequal)
+	    {			/* forcetree.c:3049-3077 */
+	      int maxsofttype = (nop->bitflags >> 2) & 7;
+	      h = o->fsoft[ptype];
+	      if(maxsofttype == 7)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	      if(h < o->fsoft[maxsofttype])
+		{
+		  h = o->fsoft[maxsofttype];
+		  if(r2max < h * h && ((nop->bitflags >> 5) & 1))
+		    {
+		      no = nop->nextnode;
+		      continue;
+		    }
+		}
+	    }
+	  no = nop->sibling;
+	}
+
+      for(g = (sG > -1 ? sG : 0); g < (sG > -1 ? sG + 1 : D); g++)
+	{			/* forcetree.c:3104-3155 (2724-2768 without PM) */
+	  int tabindex = 0;
+	  if(sG < 0 && mass[g] == 0.0)
+	    continue;
+	  r = sqrt(r2[g]);
+	  if(SR)
+	    {
+	      tabindex = (int) (r * asmthfac);
+	      if(tabindex >= o->ntab)
+		continue;
+	    }
+	  if(r >= h)
+	    {
+	      double p = pot_fxn(o, pg, g, mass[g], r);
+	      if(SR && (sG > -1 || o->node_table_term))	/* forcetree.c:3115-3116 (no mass factor) vs 3139 */
+		p -= utorwpi * o->srpot[((size_t) pg * D + g) * o->ntab + tabindex];
+	      pot -= p;
+	    }
+	  else
+	    pot += pot_spline(o, pg, g, mass[g], h, r);
+	}
+    }
+  o->pot[target] = pot;		/* FLOAT store, forcetree.c:3158 */
+}
+
+struct pslice { g2o *o; int lo, hi; };
+static void *pot_slice(void *arg)
+{
+  struct pslice *s = arg;
+  int i;
+  for(i = s->lo; i < s->hi; i++)
+    tree_potential(s->o, i);
+  return NULL;
+}
+
+/* the per-particle loop of compute_potential (potential.c:86-97) over ALL particles; out[i] = P[i].Potential after the walk */
+int g2o_potential(g2o * o, int nthreads, float *out)
+{
+  pthread_t *th;
+  struct pslice *sl;
+  int t;
+  if(o->shortrange && !o->srpot)
+    return -1;
+  if(!o->shortrange && o->periodic)
+    return -2;			/* lattice_pot_corr (forcetree.c:3895) is not restated */
+  if(nthreads < 1)
+    nthreads = 1;
+  free(o->pot);
+  o->pot = malloc(sizeof(float) * (o->n > 0 ? o->n : 1));
+  th = malloc(sizeof(pthread_t) * nthreads);
+  sl = malloc(sizeof(struct pslice) * nthreads);
+  for(t = 0; t < nthreads; t++)
+    {
+      sl[t].o = o;
+      sl[t].lo = (int) ((long long) o->n * t / nthreads);
+      sl[t].hi = (int) ((long long) o->n * (t + 1) / nthreads);
+      pthread_create(&th[t], NULL, pot_slice, &sl[t]);
+    }
+  for(t = 0; t < nthreads; t++)
+    pthread_join(th[t], NULL);
+  free(sl);
+  free(th);
+  memcpy(out, o->pot, sizeof(float) * o->n);
+  return 0;
+}
+
 struct slice { g2o *o; int lo, hi; double cost; };
 static void *walk_slice(void *arg)
 {
@@ -1006,7 +1255,14 @@ static void dft_any(const cpx * in, cpx * out, int n, int dir)
 }
 
 /* kind 0: Newtonian (normed Green's function 1); kind 1: Yukawa with ym (already in table units) */
+int g2o_make_srtables(int ntab, int kind, double ym, double *force_tab, double *pot_tab);
 int g2o_make_srtable(int ntab, int kind, double ym, double *force_tab)
+{
+  return g2o_make_srtables(ntab, kind, ym, force_tab, NULL);
+}
+
+/* both tables of one pair law: shortrange_fourier_force and shortrange_fourier_pot (forcetree.c:3335-3353) */
+int g2o_make_srtables(int ntab, int kind, double ym, double *force_tab, double *pot_tab)
 {
   const int len = 3, ol = 8;
   const int n = 12 * ntab * ol * len - 6 * ol * len + 2;	/* ngravs_core.c:179 */
@@ -1040,7 +1296,10 @@ int g2o_make_srtable(int ntab, int kind, double ym, double *force_tab)
       int f = ol * (6 * i + 3);			/* gadgetToFourier, ngravs_core.c:55-58 */
       double temp = out[f].re * dk, tempI = cum[f / 3];
       double u = 3.0 / ntab * (i + 0.5);		/* forcetree.c:3335 */
-      force_tab[i] = tempI / (u * u) - temp / u;	/* forcetree.c:3345-3353 */
+      if(force_tab)
+	force_tab[i] = tempI / (u * u) - temp / u;	/* forcetree.c:3345-3353 */
+      if(pot_tab)
+	pot_tab[i] = temp / u;			/* forcetree.c:3342-3346 */
     }
   free(cum);
   free(out);

@@ -11,6 +11,9 @@ LIB = os.path.join(HERE, "libg2oracle.so")
 LAW = dict(none=0, newtonian=1, neg_newtonian=2, yukawa=3, coloyuk=4, bambam=5, sourcebambaryon=6, sourcebaryonbam=7)
 SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebambaryon_spline=20, sourcebaryonbam_spline=21)
 
+POT = dict(none=32, newtonian=33, neg_newtonian=34)
+POTSPLINE = dict(none=48, plummer=49, neg_plummer=50)
+
 _lib = None
 
 
@@ -30,6 +33,11 @@ def lib():
         L.g2o_spline.argtypes = L.g2o_accel.argtypes
         L.g2o_set_params.argtypes = [C.c_void_p] + [C.c_double] * 6
         L.g2o_make_srtable.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.g2o_make_srtables.argtypes = [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.g2o_potfxn.restype = C.c_double
+        L.g2o_potspline.restype = C.c_double
+        L.g2o_potfxn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.g2o_potspline.argtypes = L.g2o_potfxn.argtypes
         _lib = L
     return _lib
 
@@ -44,6 +52,14 @@ def make_srtable(ntab=2048, kind=0, ym=0.0):
     rc = lib().g2o_make_srtable(ntab, kind, ym, _p(t))
     assert rc == 0
     return t
+
+
+def make_srtables(ntab=2048, kind=0, ym=0.0):
+    """(shortrange_fourier_force, shortrange_fourier_pot) of one pair law (forcetree.c:3335-3353)."""
+    f, p = np.zeros(ntab), np.zeros(ntab)
+    rc = lib().g2o_make_srtables(ntab, kind, ym, _p(f), _p(p))
+    assert rc == 0
+    return f, p
 
 
 class PortOracle:
@@ -93,6 +109,36 @@ class PortOracle:
         t = np.ascontiguousarray(table, dtype=np.float64)
         assert t.shape == (self.D, self.D, self.ntab)
         self.L.g2o_set_srtable(self.h, _p(t))
+
+    def set_potential_laws(self, pot="newtonian", spline="plummer", node_table_term=False):
+        """PotentialFxns / PotentialSplines [target][source]; node_table_term = a -DNGRAVS_ACCUMULATOR build (forcetree.c:3134-3140)."""
+        D = self.D
+
+        def grid(x, table):
+            if isinstance(x, str):
+                return np.full((D, D), table[x], dtype=np.int32)
+            return np.array([[table[v] for v in row] for row in x], dtype=np.int32)
+        a, s = grid(pot, POT), grid(spline, POTSPLINE)
+        self.L.g2o_set_potlaws(self.h, _p(a), _p(s), int(node_table_term))
+
+    def set_srpot_table(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (self.D, self.D, self.ntab)
+        self.L.g2o_set_srpot(self.h, _p(t))
+
+    def potential(self, nthreads=8):
+        """P[].Potential of every particle (current order) as the potential walk leaves it (pre-G, self term included)."""
+        out = np.zeros(self.n, dtype=np.float32)
+        rc = self.L.g2o_potential(self.h, int(nthreads), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"g2o_potential failed ({rc})")
+        return out
+
+    def potfxn(self, tgt, src, m, h, r):
+        return self.L.g2o_potfxn(self.h, tgt, src, m, h, r)
+
+    def potspline(self, tgt, src, m, h, r):
+        return self.L.g2o_potspline(self.h, tgt, src, m, h, r)
 
     def set_opening(self, theta, errtol, criterion=1):
         self.theta, self.errtol = theta, errtol

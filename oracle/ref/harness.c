@@ -23,6 +23,7 @@
 
 /* accessor defined in ref_forcetree_unit.c (needs file-scope statics of forcetree.c) */
 int g2ref_srtable_copy(double *out);
+int g2ref_srpot_copy(double *out);
 
 static double wall(void)
 {
@@ -435,6 +436,82 @@ int g2ref_get_nparticles(long long *out)
 int g2ref_get_srtable(double *out)
 {
   return g2ref_srtable_copy(out);
+}
+
+int g2ref_get_srpot_table(double *out)
+{
+  return g2ref_srpot_copy(out);
+}
+
+/* ---- tree potential of EVERY particle with the reference's own per-target walk, as the loop of compute_potential()
+ * does (potential.c:86-97): force_treeevaluate_potential_shortrange (forcetree.c:2789) under PMGRID, else
+ * force_treeevaluate_potential (forcetree.c:2467; its body exists only with -DOUTPUTPOTENTIAL).  The tree must be
+ * current (g2ref_gravity / g2ref_treebuild).  out[i] = P[i].Potential straight after the walk: the pre-G sum that still
+ * contains the self term (potential.c:250-268 removes it and applies G afterwards).  Returns -1 where the variant
+ * has no potential walk. */
+struct pslice { int lo, hi; };
+static void *pot_slice(void *arg)
+{
+  struct pslice *s = (struct pslice *) arg;
+  int i;
+  for(i = s->lo; i < s->hi; i++)
+    {
+#ifdef PMGRID
+      force_treeevaluate_potential_shortrange(i, 0);
+#else
+      force_treeevaluate_potential(i, 0);
+#endif
+    }
+  return NULL;
+}
+
+int g2ref_potential(double *out, int nthreads)
+{
+#if defined(PMGRID) || defined(OUTPUTPOTENTIAL)
+  pthread_t *th;
+  struct pslice *sl;
+  int t, i;
+  if(nthreads < 1)
+    nthreads = 1;
+  th = malloc(sizeof(pthread_t) * nthreads);
+  sl = malloc(sizeof(struct pslice) * nthreads);
+  for(t = 0; t < nthreads; t++)
+    {
+      sl[t].lo = (int) ((long long) NumPart * t / nthreads);
+      sl[t].hi = (int) ((long long) NumPart * (t + 1) / nthreads);
+      pthread_create(&th[t], NULL, pot_slice, &sl[t]);
+    }
+  for(t = 0; t < nthreads; t++)
+    pthread_join(th[t], NULL);
+  free(sl);
+  free(th);
+  for(i = 0; i < NumPart; i++)
+    out[i] = P[i].Potential;
+  return 0;
+#else
+  (void) out;
+  (void) nthreads;
+  return -1;
+#endif
+}
+
+/* potential pair-law probes (allvars.h:147-148) */
+double g2ref_potfxn(int tgt, int src, double pm, double m, double h, double r, long n)
+{
+#if defined(PMGRID) || defined(OUTPUTPOTENTIAL)
+  return (*PotentialFxns[tgt][src]) (pm, m, h, r, n);
+#else
+  return 0.0 / 0.0;
+#endif
+}
+
+double g2ref_potspline(int tgt, int src, double pm, double m, double h, double r, long n)
+{
+#if defined(PMGRID) || defined(OUTPUTPOTENTIAL)
+  return (*PotentialSplines[tgt][src]) (pm, m, h, r, n);
+#else
+  return 0.0 / 0.0;
+#endif
 }
 
 void g2ref_get_pm_split(double *out)

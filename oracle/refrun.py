@@ -210,6 +210,32 @@ class RefOracle:
         self.lib.g2ref_get_srtable(t.ctypes.data_as(C.c_void_p))
         return t
 
+    def srpot_table(self):
+        """shortrange_fourier_pot[tgt][src][NTAB] (forcetree.c:34, filled at 3346); PM variants only."""
+        if not self.pmgrid:
+            return None
+        t = np.zeros((self.D, self.D, self.ntab))
+        self.lib.g2ref_get_srpot_table(t.ctypes.data_as(C.c_void_p))
+        return t
+
+    def potential(self, nthreads=8):
+        """P[].Potential of every particle (current order) straight after the reference's own per-target potential walk
+        (force_treeevaluate_potential_shortrange, forcetree.c:2789): pre-G, self term included.  PM variants only."""
+        out = np.zeros(self.n)
+        if self.lib.g2ref_potential(out.ctypes.data_as(C.c_void_p), int(nthreads)) != 0:
+            raise RuntimeError("this oracle variant has no potential walk (needs PMGRID)")
+        return out
+
+    def potfxn(self, tgt, src, pm, m, h, r, n=1):
+        self.lib.g2ref_potfxn.restype = C.c_double
+        self.lib.g2ref_potfxn.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
+        return self.lib.g2ref_potfxn(tgt, src, pm, m, h, r, n)
+
+    def potspline(self, tgt, src, pm, m, h, r, n=1):
+        self.lib.g2ref_potspline.restype = C.c_double
+        self.lib.g2ref_potspline.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
+        return self.lib.g2ref_potspline(tgt, src, pm, m, h, r, n)
+
     def pm_split(self):
         d = np.zeros(2)
         self.lib.g2ref_get_pm_split(d.ctypes.data_as(C.c_void_p))

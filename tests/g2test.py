@@ -98,6 +98,26 @@ def direct_sum(pos, mass, h, targets, chunk=None):
     return out
 
 
+def direct_potential(pos, mass, h, targets):
+    """FP64 direct-sum potential with the GADGET-2 spline (newtonian_pot / plummer_pot, ngravs.c:368, 459-471; h = max of the two
+    particles' 2.8 eps), self term INCLUDED, pre-G: what the tree potential walks approximate (forcetree.c:2724-2768)."""
+    pos = np.asarray(pos, dtype=np.float64)
+    mass = np.asarray(mass, dtype=np.float64)
+    h = np.asarray(h, dtype=np.float64)
+    out = np.zeros(len(targets))
+    for k, t in enumerate(targets):
+        d = pos - pos[t]
+        r = np.sqrt(np.einsum("nk,nk->n", d, d))
+        hh = np.maximum(h, h[t])
+        u = r / hh
+        with np.errstate(divide="ignore", invalid="ignore"):
+            newton = -1.0 / r
+            inner = (-2.8 + u * u * (5.333333333333 + u * u * (6.4 * u - 9.6))) / hh
+            outer = (-3.2 + 0.066666666667 / u + u * u * (10.666666666667 + u * (-16.0 + u * (9.6 - 2.133333333333 * u)))) / hh
+        out[k] = np.sum(mass * np.where(r >= hh, newton, np.where(u < 0.5, inner, outer)))
+    return out
+
+
 def ewald_direct(pos, mass, targets, box, alpha_l=2.0, nmax=3, hmax2=10):
     """Exact periodic Newtonian acceleration (G = 1, point masses) of the particles `targets` by Ewald summation, FP64: the ground
     truth the reference's FORCETEST uses for periodic boxes (direct sum + lattice correction, forcetree.c:3428-3548 with
