@@ -394,6 +394,23 @@ def main():
                "note": "per rank: H2D of its 1/N of the 32-byte records, D2H of the whole result arrays; max over ranks",
                "checksum": float(np.abs(acc_e).sum())}
 
+    # ---- the tree potential of every particle (compute_potential -> force_treeevaluate_potential[_shortrange]) on the tree
+    # of the last step, timed by the library's own CUDA events around the kernel; not part of `value`
+    potw = None
+    if world == 1 and not args.profile and active is None:
+        tg.set_potential_laws()
+        if w["shortrange"]:
+            ptab = np.load(os.path.join(PKG, "data", "srpot_newton_ntab2048.npy"))
+            tg.set_srpot_table(np.broadcast_to(ptab, (w["D"], w["D"], len(ptab))).copy())
+        pot_ms = []
+        for _ in range(3):
+            flush.zero_()
+            torch.cuda.synchronize()
+            _, ms1 = tg.potential(wp_rel, with_time=True)
+            pot_ms.append(ms1)
+        potw = {"kernel": "pot_kernel", "ms_per_call": float(np.median(pot_ms)), "particles_per_s": n / (float(np.median(pot_ms)) * 1e-3),
+                "criterion": "relative (OldAcc of the first pass)", "note": "all particles are targets (potential.c:86)"}
+
     # ---- the long-range complement of the TreePM split (pmforce_periodic on the device); reported beside the tree numbers, not part
     # of the step.  Device time from the library's own events around the PM stage, inputs resident (uploaded once).
     pm = None
@@ -484,6 +501,8 @@ def main():
         line["e2e"] = e2e
     if pm is not None:
         line["pm_long_range"] = pm
+    if potw is not None:
+        line["potential_walk"] = potw
     if world == 1 and not args.no_cpu_baseline and not args.profile and active is None:
         try:
             r = reference_run(w, oldacc_by_id, 1, 0)

@@ -16,12 +16,16 @@ LAW = dict(none=0, newtonian=1, neg_newtonian=2, yukawa=3, coloyuk=4, bambam=5, 
 SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebambaryon_spline=20,
               sourcebaryonbam_spline=21)
 
+POT = dict(none=32, newtonian=33, neg_newtonian=34)
+POTSPLINE = dict(none=48, plummer=49, neg_plummer=50)
+
 EXPORTED = [
     "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
     "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+    "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential",
 ]
 
 
@@ -226,6 +230,32 @@ class TreeGravity:
         out = np.zeros((len(t), 3))
         self._chk(self.lib.g2gpu_direct(self.ctx, C.byref(wp), len(t), _p(t), _p(out)))
         return out
+
+    # ---- compute_potential (potential.c:22): the tree potential of every particle -----------------------------------------
+    def set_potential_laws(self, pot="newtonian", spline="plummer"):
+        """PotentialFxns / PotentialSplines: a name for all pairs, or a D x D nested list of names indexed [target][source]."""
+        D = self.D
+
+        def grid(x, table):
+            if isinstance(x, str):
+                return np.full((D, D), table[x], dtype=np.int32)
+            return np.array([[table[v] for v in row] for row in x], dtype=np.int32)
+        a, s = grid(pot, POT), grid(spline, POTSPLINE)
+        self._chk(self.lib.g2gpu_set_potential_laws(self.ctx, _p(a), _p(s)))
+
+    def set_srpot_table(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (self.D, self.D, self.cfg.ntab)
+        self._chk(self.lib.g2gpu_set_srpot_table(self.ctx, _p(t)))
+
+    def potential(self, wp, with_time=False):
+        """force_treeevaluate_potential[_shortrange] for every particle: P[].Potential as the walk leaves it (pre-G, self term included),
+        float32, current particle order."""
+        self._chk(self.lib.g2gpu_potential(self.ctx, C.byref(wp)))
+        out = np.zeros(self.n, dtype=np.float32)
+        ms = C.c_double(0)
+        self._chk(self.lib.g2gpu_download_potential(self.ctx, _p(out), C.byref(ms)))
+        return (out, ms.value) if with_time else out
 
     def download_acc(self, out=None):
         """out = (acc[n,3], cost[n], oldacc[n]) float32 arrays (e.g. pinned) to receive the results; allocated when None."""

@@ -4,7 +4,9 @@
  * It is compiled WITH the reference's headers (allvars.h, proto.h, ngravs.h) and replaces, symbol for symbol,
  *   gravtree.c : gravity_tree (27), set_softenings (468), grav_tree_compare_key (525)
  *   forcetree.c: force_treeallocate (3176), force_treefree (3411), force_treebuild (61),
- *                force_treeevaluate (1244), force_treeevaluate_shortrange (1623)
+ *                force_treeevaluate (1244), force_treeevaluate_shortrange (1623),
+ *                force_treeevaluate_potential_shortrange (2789; PMGRID, unless -DG2_SHIM_KEEP_REFERENCE_POTENTIAL): the per-target
+ *                function compute_potential() loops over (potential.c:86-97) is served from ONE device walk of all particles
  *   peano.c    : peano_hilbert_key (356), peano_hilbert_order (36), compare_key (190)
  *   pm_periodic.c (PMGRID && PERIODIC, unless -DG2_SHIM_KEEP_REFERENCE_PM): pm_init_periodic (53), pm_init_periodic_allocate (139),
  *                pm_init_periodic_free (187), pmforce_periodic (204); pmpotential_periodic (800) is not provided and ends the run
@@ -40,8 +42,10 @@ static int g2_dynamic = -1;		/* follow the reference's dynamic tree updates inst
 
 #ifdef PMGRID
 static double g2_srtable[N_GRAVS][N_GRAVS][NTAB];
+static double g2_srpot[N_GRAVS][N_GRAVS][NTAB];	/* shortrange_fourier_pot, forcetree.c:34 */
 static int g2_srtable_done = 0;
 #endif
+static int g2_pot_valid = 0;	/* g2_pot_byP[] holds the tree potential of the particles as uploaded last */
 
 static void g2_check(int rc, const char *what)
 {
@@ -85,6 +89,7 @@ static void g2_fill_walk_params(g2gpu_walk_params * wp);
 static void g2_upload(int npart)
 {
   int off_gravpm = -1, off_vel = -1;
+  g2_pot_valid = 0;
 #ifdef PMGRID
   off_gravpm = (int) offsetof(struct particle_data, GravPM);
 #endif
@@ -203,6 +208,23 @@ static void g2_push_tables(void)
       }
   g2_check(g2gpu_set_species(G2, TypeToGrav, All.ForceSoftening), "set_species");
   g2_check(g2gpu_set_laws(G2, accel, spline, par), "set_laws");
+#ifdef PMGRID
+  {				/* PotentialFxns / PotentialSplines (allvars.h:147-148).  A wiring without a device implementation (the BAM potentials)
+				 * is left unset: the force path does not need it, and a potential request then ends the run (G2GPU_ERR_LAW). */
+    int pot[N_GRAVS * N_GRAVS], pots[N_GRAVS * N_GRAVS], ok = 1;
+    for(i = 0; i < N_GRAVS; i++)
+      for(j = 0; j < N_GRAVS; j++)
+	{
+	  gravity f = PotentialFxns[i][j], g = PotentialSplines[i][j];
+	  pot[i * N_GRAVS + j] = f == none ? G2GPU_POT_NONE : f == newtonian_pot ? G2GPU_POT_NEWTONIAN : f == neg_newtonian_pot ? G2GPU_POT_NEG_NEWTONIAN : -1;
+	  pots[i * N_GRAVS + j] = g == none ? G2GPU_POTSPLINE_NONE : g == plummer_pot ? G2GPU_POTSPLINE_PLUMMER : g == neg_plummer_pot ? G2GPU_POTSPLINE_NEG_PLUMMER : -1;
+	  if(pot[i * N_GRAVS + j] < 0 || pots[i * N_GRAVS + j] < 0)
+	    ok = 0;
+	}
+    if(ok)
+      g2_check(g2gpu_set_potential_laws(G2, pot, pots), "set_potential_laws");
+  }
+#endif
 }
 
 #ifdef PMGRID
@@ -223,6 +245,7 @@ static void g2_build_srtable(void)
 	  {
 	    u = 3.0 / NTAB * (i + 0.5);
 	    g2_srtable[nB][nA][i] = tempI[i] / (u * u) - temp[i] / u;
+	    g2_srpot[nB][nA][i] = temp[i] / u;	/* forcetree.c:3342-3346 */
 	  }
       }
   ngravsConvolutionFree(ngravsPeriodicTable);
@@ -285,6 +308,7 @@ void force_treeallocate(int maxnodes, int maxpart)
       if(!g2_srtable_done)
 	g2_build_srtable();
       g2_check(g2gpu_set_srtable(G2, &g2_srtable[0][0][0]), "set_srtable");
+      g2_check(g2gpu_set_srpot_table(G2, &g2_srpot[0][0][0]), "set_srpot_table");
 #endif
     }
   if(g2_mirror < 0)
@@ -698,6 +722,46 @@ int force_treeevaluate(int target, int mode, double *ewaldcountsum)
 int force_treeevaluate_shortrange(int target, int mode)
 {
   return g2_evaluate_one(target, mode);
+}
+#endif
+
+#if defined(PMGRID) && !defined(G2_SHIM_KEEP_REFERENCE_POTENTIAL)
+/* forcetree.c:2789.  compute_potential() (potential.c:86-97) calls this once per particle.  The first call after the particles or
+ * the opening parameters changed builds a tree from the current P[] and walks it for ALL particles in one device call
+ * (g2gpu_potential); every call then stores its particle's value in P[target].Potential exactly as the reference's function does
+ * (pre-G, self term included: potential.c:250-270 goes on from there unchanged). */
+static float *g2_pot_byP = NULL;
+static int g2_pot_n = 0;
+static double g2_pot_theta = -1, g2_pot_errtol = -1;
+
+void force_treeevaluate_potential_shortrange(int target, int mode)
+{
+  if(mode != 0)
+    {
+      printf("g2gpu: force_treeevaluate_potential_shortrange(mode=1) (imported particles) does not exist without domain decomposition\n");
+      endrun(7402);
+    }
+  if(!g2_pot_valid || g2_pot_n != NumPart || g2_pot_theta != All.ErrTolTheta || g2_pot_errtol != All.ErrTolForceAcc)
+    {
+      g2gpu_walk_params wp;
+      float *pot = malloc(sizeof(float) * (size_t) NumPart);
+      int i, save = TreeReconstructFlag;
+      if(!pot || !(g2_pot_byP = realloc(g2_pot_byP, sizeof(float) * (size_t) All.MaxPart)))
+	endrun(7403);
+      force_treebuild(NumPart);
+      TreeReconstructFlag = save;
+      g2_fill_walk_params(&wp);
+      g2_check(g2gpu_potential(G2, &wp), "potential");
+      g2_check(g2gpu_download_potential(G2, pot, NULL), "download_potential");
+      for(i = 0; i < NumPart; i++)
+	g2_pot_byP[g2_perm[i]] = pot[i];
+      free(pot);
+      g2_pot_n = NumPart;
+      g2_pot_theta = All.ErrTolTheta;
+      g2_pot_errtol = All.ErrTolForceAcc;
+      g2_pot_valid = 1;
+    }
+  P[target].Potential = g2_pot_byP[target];
 }
 #endif
 

@@ -1068,6 +1068,26 @@ int g2o_potential(g2o * o, int nthreads, float *out)
   return 0;
 }
 
+/* the same walk for a list of targets only (full-size spot checks) */
+int g2o_potential_targets(g2o * o, int ntargets, const int *targets, float *out)
+{
+  int t;
+  if(o->shortrange && !o->srpot)
+    return -1;
+  if(!o->shortrange && o->periodic)
+    return -2;
+  free(o->pot);
+  o->pot = malloc(sizeof(float) * (o->n > 0 ? o->n : 1));
+  for(t = 0; t < ntargets; t++)
+    {
+      if(targets[t] < 0 || targets[t] >= o->n)
+	return -3;
+      tree_potential(o, targets[t]);
+      out[t] = o->pot[targets[t]];
+    }
+  return 0;
+}
+
 struct slice { g2o *o; int lo, hi; double cost; };
 static void *walk_slice(void *arg)
 {

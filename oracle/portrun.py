@@ -134,6 +134,14 @@ class PortOracle:
             raise RuntimeError(f"g2o_potential failed ({rc})")
         return out
 
+    def potential_targets(self, targets):
+        t = np.ascontiguousarray(targets, dtype=np.int32)
+        out = np.zeros(len(t), dtype=np.float32)
+        rc = self.L.g2o_potential_targets(self.h, len(t), _p(t), _p(out))
+        if rc != 0:
+            raise RuntimeError(f"g2o_potential_targets failed ({rc})")
+        return out
+
     def potfxn(self, tgt, src, m, h, r):
         return self.L.g2o_potfxn(self.h, tgt, src, m, h, r)
 

@@ -473,6 +473,9 @@ int g2ref_potential(double *out, int nthreads)
   int t, i;
   if(nthreads < 1)
     nthreads = 1;
+#ifdef G2_SHIM_HARNESS
+  nthreads = 1;			/* the shim's entry points drive one device context: single caller, like the reference's own loop */
+#endif
   th = malloc(sizeof(pthread_t) * nthreads);
   sl = malloc(sizeof(struct pslice) * nthreads);
   for(t = 0; t < nthreads; t++)

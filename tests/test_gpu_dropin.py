@@ -110,6 +110,38 @@ def test_reference_pm_call_runs_on_the_gpu(outdir):
     assert np.median(rel) <= 1e-5 and np.percentile(rel, 99.9) <= 1e-3
 
 
+def test_reference_potential_loop_runs_on_the_gpu(outdir):
+    """The loop of compute_potential() (potential.c:86-97: force_treeevaluate_potential_shortrange(i, 0) for every particle) through the
+    shim's entry point -- one device walk of all particles behind the reference's per-target function -- against the unmodified
+    forcetree.c:2789, Barnes-Hut and relative criterion (OldAcc from the reference's own gravity_tree() on both sides)."""
+    variant = "pm64_d2_f32"
+    if not (available(variant) and available(variant, "g2shim")):
+        pytest.skip("oracle/_ref (reference and shim builds) not present")
+    _preload()
+    n, box = 32768, 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=19)
+    mass = (mass * np.random.default_rng(2).uniform(0.5, 2.0, n)).astype(np.float32)
+    kw = dict(boxsize=box, softening=(box / 32 / 30.0,) * 6, gravity=g2test.GRAV_D2)
+    ref = RefOracle(variant, int(1.1 * n) + 64, **kw)
+    shim = RefOracle(variant, int(1.1 * n) + 64, prefix="g2shim", **kw)
+    res = {}
+    for name, o in (("ref", ref), ("shim", shim)):
+        o.load(pos, mass, ptype)
+        o.domain()
+        o.gravity()
+        ids = o.particles()["id"]
+        for theta in (0.5, 0.0):
+            o.set_opening(theta, 0.005, 1)
+            pot = np.zeros(n)
+            pot[ids] = o.potential()
+            res[name, theta] = pot
+    with open(os.path.join(outdir, "dropin_potential.txt"), "w") as f:
+        for theta in (0.5, 0.0):
+            e = np.abs(res["shim", theta] - res["ref", theta]) / np.abs(res["ref", theta])
+            f.write(f"theta {theta}: median {np.median(e):.3e} p99.9 {np.percentile(e, 99.9):.3e} max {e.max():.3e}\n")
+            assert np.median(e) <= 1e-5 and np.percentile(e, 99.9) <= 1e-3
+
+
 def test_reference_forcetest_call_runs_on_the_gpu(outdir, tmp_path, monkeypatch):
     """gravity_forcetest() (gravtree_forcetest.c:28, the -DFORCETEST accuracy check accel.c:52 runs after gravity_tree()): the shim's
     version (one device call, FP64 direct sums) against the unmodified file, and the forcetest.txt lines both write."""

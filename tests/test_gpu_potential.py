@@ -1,0 +1,233 @@
+"""GPU parity of the tree potential walks: g2gpu_potential against
+  * the committed fixtures tests/golden/pot_*.npz = P[].Potential of the UNMODIFIED reference's force_treeevaluate_potential_shortrange
+    (forcetree.c:2789-3163) for every particle (potential.c:86-97), Barnes-Hut and relative criterion;
+  * a fresh run of the reference where oracle/_ref travelled (D = 3, clustered, unequal masses);
+  * the pinned oracle port at a larger size, with and without the table term on node terms (the NGRAVS_ACCUMULATOR variant);
+  * FP64 direct sums for the non-PM potential walk (force_treeevaluate_potential, forcetree.c:2467), which the reference itself cannot
+    compile, and a size-independent property at full size (the self term, and agreement between 1 rank and 2 rank slices).
+Tolerance: FP32 terms on float inputs against the reference's double arithmetic: median relative error <= 1e-5, 99.9th percentile <= 1e-3
+(the tolerances of the force walk, BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import g2test
+from portrun import PortOracle
+from refrun import RefOracle, available
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MEDIAN_TOL = 1.0e-5
+P999_TOL = 1.0e-3
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.abs(b)
+
+
+def check(pot, ref, what):
+    e = relerr(pot, ref)
+    assert np.median(e) <= MEDIAN_TOL, (what, np.median(e))
+    assert np.percentile(e, 99.9) <= P999_TOL, (what, np.percentile(e, 99.9), e.max())
+    return e
+
+
+def gpu_treepm(maxpart, D, grav, soft, srtable, srpot, box, accumulator=False):
+    from g2gpu import TreeGravity
+    t = TreeGravity(max_part=maxpart, n_gravs=D, periodic=True, shortrange=True, unequal_softenings=False)
+    t.set_species(grav, g2test.force_softening(soft))
+    t.set_laws()
+    t.set_srtable(srtable)
+    if accumulator:
+        t.set_option("accumulator", 1)
+    return t
+
+
+@pytest.mark.parametrize("case", ["pot_pm64_d2_poisson4096", "pot_pm64_d4_poisson4096"])
+def test_shortrange_potential_matches_reference_fixture(case):
+    g = np.load(os.path.join(GOLD, case + ".npz"))
+    box, n = float(g["box"]), len(g["mass"])
+    t = gpu_treepm(int(g["maxpart"]), int(g["D"]), g["grav"], g["soft"], g["srtable"], g["srpot"], box)
+    wp = t.walk_params(theta=0.5, errtol=0.005, boxsize=box, asmth=float(g["asmth"]), rcut=float(g["rcut"]))
+    t.upload(g["pos"], g["mass"], g["type"], oldacc=g["oldacc"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    # call order is checked: laws and table must be set first
+    from g2gpu import G2Error
+    with pytest.raises(G2Error):
+        t.potential(wp)
+    t.set_potential_laws("newtonian", "plummer")
+    with pytest.raises(G2Error):
+        t.potential(wp)
+    t.set_srpot_table(g["srpot"])
+    check(t.potential(wp), g["pot_bh"], "barnes-hut")
+    wp.theta = 0.0
+    check(t.potential(wp), g["pot_rel"], "relative")
+
+
+@pytest.mark.skipif(not available("pm64_d3_f32"), reason="oracle/_ref not built")
+def test_shortrange_potential_matches_fresh_reference_run():
+    n, box = 20000, 100000.0
+    rng = np.random.default_rng(23)
+    pos = (rng.normal(size=(n, 3)) * box / 12 + box / 2).astype(np.float32) % np.float32(box)
+    pos = np.minimum(pos, np.float32(np.nextafter(np.float32(box), np.float32(0))))
+    mass = rng.uniform(0.2, 3.0, n).astype(np.float32)
+    ptype = rng.integers(1, 6, n).astype(np.int32)
+    eps = box / 27 / 30.0
+    soft, grav = (eps,) * 6, (0, 0, 1, 2, 1, 0)
+    ref = RefOracle("pm64_d3_f32", int(1.1 * n) + 64, boxsize=box, softening=soft, gravity=grav)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    ref.gravity()
+    rp = ref.particles()
+    asmth, rcut = ref.pm_split()
+    t = gpu_treepm(ref.maxpart, 3, grav, soft, ref.srtable(), ref.srpot_table(), box)
+    t.set_potential_laws()
+    t.set_srpot_table(ref.srpot_table())
+    t.upload(rp["pos"], rp["mass"], rp["type"], oldacc=rp["oldacc"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    for theta in (0.5, 0.0):
+        ref.set_opening(theta, 0.005, 1)
+        wp = t.walk_params(theta=theta, errtol=0.005, boxsize=box, asmth=asmth, rcut=rcut)
+        check(t.potential(wp), ref.potential(), f"theta={theta}")
+
+
+@pytest.mark.parametrize("accumulator", [False, True])
+def test_shortrange_potential_against_pinned_port(accumulator):
+    """200 k particles, D = 2, PMGRID 64 geometry; node terms with the table term (an NGRAVS_ACCUMULATOR build, forcetree.c:3134) and without."""
+    n, box = 200000, 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=3)
+    mass = (mass * np.random.default_rng(9).uniform(0.5, 2.0, n)).astype(np.float32)
+    g = np.load(os.path.join(GOLD, "pot_pm64_d2_poisson4096.npz"))
+    eps = box / 58 / 30.0
+    soft, grav = (eps,) * 6, g2test.GRAV_D2
+    o = PortOracle(int(1.1 * n) + 64, D=2, periodic=True, shortrange=True, unequal=False, boxsize=box, pmgrid=64, softening=soft, gravity=grav)
+    o.set_srtable(g["srtable"])
+    o.set_srpot_table(g["srpot"])
+    o.set_potential_laws("newtonian", "plummer", accumulator)
+    o.load(pos, mass, ptype)
+    o.domain()
+    o.gravity(nthreads=8)                    # Barnes-Hut pass: OldAcc for the relative criterion
+    p = o.particles()
+    o.load(p["pos"], p["mass"], p["type"], oldacc=p["oldacc"])
+    o.domain()
+    o.treebuild()
+    o.set_opening(0.0, 0.005)
+    ref = o.potential(nthreads=8)
+    t = gpu_treepm(o.maxpart, 2, grav, soft, g["srtable"], g["srpot"], box, accumulator=accumulator)
+    t.set_potential_laws()
+    t.set_srpot_table(g["srpot"])
+    t.upload(p["pos"], p["mass"], p["type"], oldacc=p["oldacc"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    wp = t.walk_params(theta=0.0, errtol=0.005, boxsize=box, asmth=o.asmth, rcut=o.rcut)
+    check(t.potential(wp), ref, f"accumulator={accumulator}")
+
+
+def test_nonperiodic_potential_against_direct_sum_and_port():
+    """force_treeevaluate_potential (no PM): against the port's restatement of the reference text (not compilable there, so unpinned)
+    and against what it approximates, the FP64 softened direct-sum potential."""
+    from g2gpu import TreeGravity
+    n = 100000
+    pos, mass, ptype = g2test.hernquist(n)
+    soft, grav = g2test.SOFT_NP, g2test.GRAV_D2
+    o = PortOracle(int(1.1 * n) + 64, softening=soft, gravity=grav)
+    o.set_potential_laws("newtonian", "plummer")
+    o.load(pos, mass, ptype)
+    o.domain()
+    o.treebuild()
+    o.set_opening(0.5, 0.005)
+    p = o.particles()
+    ref = o.potential(nthreads=8)
+    t = TreeGravity(max_part=o.maxpart, n_gravs=2)
+    t.set_species(grav, g2test.force_softening(soft))
+    t.set_laws()
+    t.set_potential_laws()
+    t.upload(p["pos"], p["mass"], p["type"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    pot = t.potential(t.walk_params(theta=0.5, errtol=0.005))
+    check(pot, ref, "port")
+    tg = np.arange(0, n, 997)
+    d = g2test.direct_potential(p["pos"], p["mass"], g2test.force_softening(soft)[p["type"]], tg)
+    e = relerr(pot[tg], d)
+    assert np.median(e) < 2e-3 and e.max() < 3e-2, (np.median(e), e.max())
+
+
+def test_periodic_box_without_pm_is_refused():
+    """PERIODIC without PMGRID needs lattice_pot_corr (forcetree.c:3895), which is not built: the call must fail, not approximate."""
+    from g2gpu import G2Error, TreeGravity
+    n, box = 5000, 1000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=5)
+    t = TreeGravity(max_part=n + 64, n_gravs=2, periodic=True, shortrange=False, unequal_softenings=False)
+    t.set_species(g2test.GRAV_D2, g2test.force_softening((1.0,) * 6))
+    t.set_laws()
+    t.set_potential_laws()
+    t.upload(pos, mass, ptype)
+    t.domain()
+    t.treebuild()
+    with pytest.raises(G2Error):
+        t.potential(t.walk_params(theta=0.5, boxsize=box))
+
+
+def test_full_size_potential_properties(outdir):
+    """Config 3 size (128^3 = 2.1 M particles, PMGRID 256): (1) two rank slices together give exactly the single-rank result; (2) the
+    walk result is below the self term -m/eps for every particle (all pair terms of the Newtonian potential are attractive given the
+    reference's tables) and finite; (3) 4096 targets agree with the pinned oracle port run on the same 2.1 M particles."""
+    import json
+    from g2gpu import TreeGravity
+    n, box, pmgrid = 128 ** 3, 100000.0, 256
+    pos, mass, ptype = g2test.periodic_poisson(n, box)
+    g = np.load(os.path.join(GOLD, "pot_pm64_d2_poisson4096.npz"))
+    eps = box / 128 / 30.0
+    soft, grav = (eps,) * 6, g2test.GRAV_D2
+    asmth = 1.25 * box / pmgrid
+    rcut = 4.5 * asmth
+    res = []
+    for nranks in (1, 2):
+        parts = []
+        for rank in range(nranks):
+            t = TreeGravity(max_part=n + 64, n_gravs=2, periodic=True, shortrange=True, unequal_softenings=False, rank=rank, nranks=nranks)
+            t.set_species(grav, g2test.force_softening(soft))
+            t.set_laws()
+            t.set_srtable(g["srtable"])
+            t.set_potential_laws()
+            t.set_srpot_table(g["srpot"])
+            t.upload(pos, mass, ptype)
+            t.domain()
+            t.treebuild()
+            wp = t.walk_params(theta=0.5, errtol=0.005, boxsize=box, asmth=asmth, rcut=rcut)
+            pot, ms = t.potential(wp, with_time=True)
+            order = t.order()
+            parts.append(pot)
+            t.close()
+        res.append((parts, ms))
+    single = res[0][0][0]
+    a, b = res[1][0]
+    assert np.all((a == 0) | (b == 0))                        # disjoint slices
+    assert np.array_equal(a + b, single)
+    assert np.isfinite(single).all()
+    self_term = -mass[order].astype(np.float64) / eps
+    assert np.all(single < self_term * (1 - 1e-6))
+    # (3) 4096 targets with the pinned oracle port on the same 2.1 M particles (the port's tree is the reference's tree, bit for bit)
+    o = PortOracle(n + 64, D=2, periodic=True, shortrange=True, unequal=False, boxsize=box, pmgrid=pmgrid, softening=soft, gravity=grav)
+    o.set_srtable(g["srtable"])
+    o.set_srpot_table(g["srpot"])
+    o.set_potential_laws("newtonian", "plummer")
+    o.load(pos[order], mass[order], ptype[order])
+    o.domain()
+    assert np.array_equal(o.particles()["id"], np.arange(n))
+    o.treebuild()
+    o.set_opening(0.5, 0.005)
+    tg = np.arange(0, n, n // 4096)[:4096].astype(np.int32)
+    e = check(single[tg], o.potential_targets(tg), "full size")
+    with open(os.path.join(outdir, "potential_p128.json"), "w") as f:
+        json.dump(dict(n=n, kernel_ms=res[0][1], kernel_ms_2ranks=res[1][1], err_vs_port=dict(median=float(np.median(e)), p999=float(np.percentile(e, 99.9)), max=float(e.max()))), f)
