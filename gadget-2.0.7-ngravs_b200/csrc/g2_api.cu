@@ -141,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -765,6 +765,76 @@ extern "C" int g2gpu_download_potential(g2gpu_ctx *c, float *pot, double *kernel
   if(kernel_ms)
     *kernel_ms = c->pot_ms;
   return 0;
+}
+
+// ---- lattice-sum correction (g2_lattice.cu) ----------------------------------------------------------------------
+extern "C" int g2gpu_set_lattice_tables(g2gpu_ctx *c, int en, const double *fcorr)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  if(!fcorr)
+    {				// back to the nearest-image force
+      c->lattice_set = 0;
+      return 0;
+    }
+  if(!c->cfg.periodic || c->cfg.shortrange)
+    return g2_fail(G2GPU_ERR_ARG, "lattice tables belong to a periodic box without PM (PERIODIC && !PMGRID)");
+  if(en < 1 || en > 256)
+    return g2_fail(G2GPU_ERR_ARG, "EN must be in [1, 256]");
+  const int D = c->D;
+  const size_t n3 = (size_t) (en + 1) * (en + 1) * (en + 1);
+  // fcorr[comp][tgt][src][n3]; identical pair tables (all three components) are stored once
+  int nu = 0, first[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  for(int i = 0; i < D * D; i++)
+    {
+      int found = -1;
+      for(int u = 0; u < nu && found < 0; u++)
+	{
+	  bool same = true;
+	  for(int cc = 0; cc < 3 && same; cc++)
+	    same = memcmp(fcorr + ((size_t) cc * D * D + first[u]) * n3, fcorr + ((size_t) cc * D * D + i) * n3, sizeof(double) * n3) == 0;
+	  if(same)
+	    found = u;
+	}
+      if(found < 0)
+	{
+	  first[nu] = i;
+	  found = nu++;
+	}
+      c->lattice_tabmap[i] = (unsigned char) found;
+    }
+  float *hf = (float *) malloc(sizeof(float) * 4 * n3 * (size_t) nu);
+  if(!hf)
+    return g2_fail(G2GPU_ERR_NOMEM, "host allocation failed");
+  for(int u = 0; u < nu; u++)
+    for(size_t q = 0; q < n3; q++)
+      {
+	for(int cc = 0; cc < 3; cc++)
+	  hf[4 * ((size_t) u * n3 + q) + cc] = (float) fcorr[((size_t) cc * D * D + first[u]) * n3 + q];
+	hf[4 * ((size_t) u * n3 + q) + 3] = 0.0f;
+      }
+  if(c->d_lattice)
+    cudaFree(c->d_lattice);
+  c->d_lattice = nullptr;
+  int rc = dalloc(&c->d_lattice, 4 * n3 * (size_t) nu);
+  if(rc == 0 && cudaMemcpy(c->d_lattice, hf, sizeof(float) * 4 * n3 * (size_t) nu, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = g2_fail(G2GPU_ERR_CUDA, "table upload failed");
+  free(hf);
+  if(rc)
+    return rc;
+  c->lattice_en = en;
+  c->lattice_ntables = nu;
+  c->lattice_set = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_make_ewald_table(g2gpu_ctx *c, int en, double *out)
+{
+  if(!c || !out)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_make_ewald_table(c, en, out);
 }
 
 extern "C" int g2gpu_slice(g2gpu_ctx *c, int *lo, int *hi)

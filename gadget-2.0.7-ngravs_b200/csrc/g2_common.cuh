@@ -108,6 +108,11 @@ struct g2gpu_ctx
   unsigned char pot_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   float *pot;			// n, current particle order (allocated on first use)
   double pot_ms;
+  // lattice-sum correction of a periodic box without PM (g2_lattice.cu)
+  float *d_lattice;		// unique tables, (EN+1)^3 float4 (fx, fy, fz, 0) each
+  int lattice_en, lattice_set, lattice_ntables;
+  unsigned char lattice_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  float *latt, *lattcost;	// 3n / n, current particle order (allocated on first use)
   int acc_double;		// accumulate accelerations in FP64 (default) or FP32
   int accumulator;		// NGRAVS_ACCUMULATOR: nodes carry the particle count per species (wcnt), laws receive it as N
   int counts_valid;		// wcnt belongs to the current tree
@@ -234,6 +239,8 @@ int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
 int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_make_ewald_table(g2gpu_ctx *c, int en, double *out);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_stage_bfs(g2gpu_ctx *c);
 int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);

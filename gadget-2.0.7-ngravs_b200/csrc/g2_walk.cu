@@ -280,6 +280,12 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	{
 	  // gravity_tree epilogue: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
 	  fx = (float) ax; fy = (float) ay; fz = (float) az;
+	  if(PERIODIC && !SR && A.latt)
+	    {			// force_treeevaluate_lattice_correction adds to the FLOAT result and to GravCost (forcetree.c:2435-2438)
+	      fx = (float) ((double) fx + (double) A.latt[3 * (size_t) idx + 0]);
+	      fy = (float) ((double) fy + (double) A.latt[3 * (size_t) idx + 1]);
+	      fz = (float) ((double) fz + (double) A.latt[3 * (size_t) idx + 2]);
+	    }
 	  if(A.pos_fac_pre_g != 0.0)
 	    {
 	      fx = (float) ((double) fx + A.pos_fac_pre_g * (double) px);
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	  A.acc[3 * (size_t) idx + 0] = fx;
 	  A.acc[3 * (size_t) idx + 1] = fy;
 	  A.acc[3 * (size_t) idx + 2] = fz;
-	  A.cost[idx] = (float) ninter;
+	  A.cost[idx] = (PERIODIC && !SR && A.lattcost) ? (float) ninter + A.lattcost[idx] : (float) ninter;
 	  tot_inter += (unsigned long long) ninter;
 	  tot_terms += (unsigned long long) nterms;
 	  tot_dec += (unsigned long long) ndec;
@@ -461,7 +467,16 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
     grid = need;
   // walk mode 1 (one warp per target) needs the level-order records; pair laws that take the per-cell particle counts
   // (NGRAVS_ACCUMULATOR) and the sub-group experiments stay on the cursor walk
-  const bool mode_b = c->walk_mode == 1 && c->bfs_valid && A.cnt == nullptr && c->walk_group == 32;
+  // periodic box without PM: the lattice-sum correction walk first (its result enters the epilogue of the walk kernel)
+  const bool lattice = c->cfg.periodic && !sr && c->lattice_set && ntgt > 0;
+  if(lattice)
+    {
+      if(!(wp->boxsize > 0))
+	return g2_fail(G2GPU_ERR_ARG, "walk: boxsize must be positive for the lattice-sum correction");
+      G2_TRY(g2_stage_lattice(c, wp));
+      A.latt = c->latt; A.lattcost = c->lattcost;
+    }
+  const bool mode_b = c->walk_mode == 1 && c->bfs_valid && A.cnt == nullptr && c->walk_group == 32 && !lattice;
   G2_CUDA(cudaEventRecord(c->ev[7], st));
   if(ntgt > 0 && mode_b)
     {

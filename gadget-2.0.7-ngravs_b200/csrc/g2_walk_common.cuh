@@ -27,6 +27,8 @@ struct WalkArgs
   const float *__restrict__ gravpm;
   const unsigned int *__restrict__ cnt;	// particle counts per species of every cell [U][D] (NGRAVS_ACCUMULATOR), or null
   const float *__restrict__ srtable;		// unique tables, NTAB floats each
+  const float *__restrict__ latt;		// lattice-sum correction of every target (periodic box without PM, g2_lattice.cu), or null
+  const float *__restrict__ lattcost;
   float *__restrict__ acc;
   float *__restrict__ cost;
   float *__restrict__ oldacc_out;

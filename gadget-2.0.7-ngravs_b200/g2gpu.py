@@ -25,6 +25,7 @@ EXPORTED = [
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
     "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+    "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table",
     "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential",
 ]
 
@@ -230,6 +231,29 @@ class TreeGravity:
         out = np.zeros((len(t), 3))
         self._chk(self.lib.g2gpu_direct(self.ctx, C.byref(wp), len(t), _p(t), _p(out)))
         return out
+
+    # ---- lattice_init / force_treeevaluate_lattice_correction (forcetree.c:3611, 2077): periodic box without PM -------------
+    def make_ewald_table(self, en=64):
+        """ewald_force (ngravs.c:1170) at x = 0.5 (i,j,k)/en, computed on the device in FP64: (3, en+1, en+1, en+1), dimensionless."""
+        out = np.zeros((3, en + 1, en + 1, en + 1))
+        self._chk(self.lib.g2gpu_make_ewald_table(self.ctx, int(en), _p(out)))
+        return out
+
+    def set_lattice_tables(self, fcorr, en=64):
+        """fcorr: (3, D, D, en+1, en+1, en+1) = fcorrx/y/z[target][source] after lattice_init (divided by BoxSize^2), or None to go
+        back to the nearest-image force.  walk()/gravity_tree() then include the lattice-sum correction walk."""
+        if fcorr is None:
+            self._chk(self.lib.g2gpu_set_lattice_tables(self.ctx, int(en), None))
+            return
+        t = np.ascontiguousarray(fcorr, dtype=np.float64)
+        assert t.shape == (3, self.D, self.D, en + 1, en + 1, en + 1)
+        self._chk(self.lib.g2gpu_set_lattice_tables(self.ctx, int(en), _p(t)))
+
+    def set_ewald_lattice(self, boxsize, en=64):
+        """The stock wiring (LatticeForce = ewald_force for every pair, ngravs.c:131): device-made table / BoxSize^2 for all pairs."""
+        t = self.make_ewald_table(en) / (boxsize * boxsize)
+        self.set_lattice_tables(np.broadcast_to(t[:, None, None], (3, self.D, self.D) + t.shape[1:]).copy(), en)
+        return t
 
     # ---- compute_potential (potential.c:22): the tree potential of every particle -----------------------------------------
     def set_potential_laws(self, pot="newtonian", spline="plummer"):

@@ -212,6 +212,18 @@ int g2gpu_walk(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
  * forcetree.c:3803, for gravity_forcetest), i.e. the complete periodic Newtonian force the TreePM sum (tree + PM) approximates. */
 int g2gpu_direct(g2gpu_ctx *ctx, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);
 
+/* ---- lattice-sum correction of a periodic box WITHOUT PM (config.periodic && !config.shortrange):
+ *      force_treeevaluate_lattice_correction (forcetree.c:2077-2455), the second walk force_treeevaluate runs for every target
+ *      (forcetree.c:1606-1608).  Once tables are set, g2gpu_walk runs that walk as well: the correction is added to GravAccel before the
+ *      gravity_tree epilogue and its interaction count to GravCost (forcetree.c:2435-2438; counters[1] stays the tree walk's own sum,
+ *      like costtotal in gravtree.c:120).  Without tables the force is the nearest-image tree force.
+ *      fcorr[((c * D + target) * D + source) * (en+1)^3 + (i * (en+1) + j) * (en+1) + k], c = 0,1,2: the reference's fcorrx/y/z AFTER
+ *      lattice_init (forcetree.c:3611-3790), i.e. divided by BoxSize^2; en = NGRAVS_EN (64).  NULL removes the tables. ---- */
+int g2gpu_set_lattice_tables(g2gpu_ctx *ctx, int en, const double *fcorr);
+/* The table lattice_init computes for the stock wiring: ewald_force (ngravs.c:1170-1236) at x = 0.5 (i,j,k)/en, FP64 on the device,
+ * DIMENSIONLESS (divide by BoxSize^2 for g2gpu_set_lattice_tables); out[c * (en+1)^3 + ...], c = 0,1,2. */
+int g2gpu_make_ewald_table(g2gpu_ctx *ctx, int en, double *out);
+
 /* ---- tree potential of compute_potential (potential.c:22-354): force_treeevaluate_potential_shortrange
  *      (forcetree.c:2789-3163) when config.shortrange is set, else force_treeevaluate_potential (forcetree.c:2467-2776; non-periodic
  *      only -- the periodic variant needs the lattice-sum tables of lattice_pot_corr, which are not built: G2GPU_ERR_ARG).

@@ -61,6 +61,9 @@ typedef struct g2o
   double lawpar[MAXG][MAXG][4];
   double *srtab;			/* [D][D][ntab] */
   double *srpot;			/* shortrange_fourier_pot [D][D][ntab] */
+  double *fcorr;			/* fcorrx/y/z after lattice_init: [3][D][D][(en+1)^3] (PERIODIC without PMGRID), or NULL */
+  int lattice_en;
+  double lattice_cost;			/* sum of the lattice walk's return values (ewaldcount, gravtree.c:120) */
   int pot_id[MAXG][MAXG], potspline_id[MAXG][MAXG];	/* PotentialFxns / PotentialSplines, ids of include/g2gpu.h */
   int node_table_term;			/* -DNGRAVS_ACCUMULATOR build: node terms of the short-range potential carry the table term */
   float *pot;				/* P[].Potential after the potential walk */
@@ -191,7 +194,7 @@ void g2o_destroy(g2o * o)
 {
   if(!o)
     return;
-  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o->srpot); free(o->pot); free(o);
+  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o->srpot); free(o->pot); free(o->fcorr); free(o);
 }
 
 void g2o_set_species(g2o * o, const int *t2g, const double *fsoft)
@@ -1088,6 +1091,151 @@ int g2o_potential_targets(g2o * o, int ntargets, const int *targets, float *out)
   return 0;
 }
 
+/* ---- lattice-sum correction walk: force_treeevaluate_lattice_correction, forcetree.c:2077-2455 ---- */
+void g2o_set_lattice_tables(g2o * o, int en, const double *fcorr)
+{
+  size_t n = (size_t) 3 * o->D * o->D * (en + 1) * (en + 1) * (en + 1);
+  free(o->fcorr);
+  o->fcorr = NULL;
+  if(!fcorr)
+    return;
+  o->fcorr = malloc(sizeof(double) * n);
+  memcpy(o->fcorr, fcorr, sizeof(double) * n);
+  o->lattice_en = en;
+}
+
+static int lattice_correction(g2o * o, int target, double pos_x, double pos_y, double pos_z, double aold)
+{
+  const int D = o->D, MP = o->maxpart, EN = o->lattice_en, n1 = EN + 1;
+  const size_t n3 = (size_t) n1 * n1 * n1;
+  const double boxsize = o->boxsize, boxhalf = 0.5 * o->boxsize, fac_intp = 2 * EN / o->boxsize;	/* forcetree.c:3749 */
+  const int pg = o->t2g[o->P[target].type];
+  double dx[MAXG], dy[MAXG], dz[MAXG], mass[MAXG], r2[MAXG];
+  double acc[3] = { 0, 0, 0 };
+  int no = MP, cost = 0, sG, g, n;
+  node *nop = 0;
+
+  while(no >= 0)
+    {
+      if(no < MP)
+	{
+	  const particle *sp = &o->P[no];
+	  sG = o->t2g[sp->type];
+	  mass[sG] = sp->mass;
+	  dx[sG] = NEAREST(sp->pos[0] - pos_x);
+	  dy[sG] = NEAREST(sp->pos[1] - pos_y);
+	  dz[sG] = NEAREST(sp->pos[2] - pos_z);
+	  no = o->nextnode[no];
+	}
+      else
+	{
+	  double r2min = INFINITY, summass = 0, u;
+	  int openflag = 0, k;
+	  const double pp[3] = { pos_x, pos_y, pos_z };
+	  nop = NODE_OF(o, no);
+	  for(g = 0; g < D; g++)
+	    {
+	      mass[g] = nop->mass[g];
+	      summass += nop->mass[g];
+	      dx[g] = NEAREST(nop->s[0][g] - pos_x);
+	      dy[g] = NEAREST(nop->s[1][g] - pos_y);
+	      dz[g] = NEAREST(nop->s[2][g] - pos_z);
+	      r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
+	      if(r2[g] < r2min)
+		r2min = r2[g];
+	    }
+	  sG = -1;
+	  if(o->theta)
+	    {
+	      if(nop->len * nop->len > r2min * o->theta * o->theta)
+		openflag = 1;
+	    }
+	  else
+	    {
+	      if(summass * nop->len * nop->len > r2min * r2min * aold)
+		openflag = 1;
+	      else if(fabs(nop->center[0] - pos_x) < 0.60 * nop->len && fabs(nop->center[1] - pos_y) < 0.60 * nop->len
+		      && fabs(nop->center[2] - pos_z) < 0.60 * nop->len)
+		openflag = 1;
+	    }
+	  if(openflag)
+	    {			/* forcetree.c:2211-2256 */
+	      int must = 0;
+	      for(k = 0; k < 3 && !must; k++)
+		{
+		  u = nop->center[k] - pp[k];
+		  if(u > boxhalf)
+		    u -= boxsize;
+		  if(u < -boxhalf)
+		    u += boxsize;
+		  if(fabs(u) > 0.5 * (boxsize - nop->len))
+		    must = 1;
+		}
+	      if(must || nop->len > 0.20 * boxsize)
+		{
+		  no = nop->nextnode;
+		  continue;
+		}
+	    }
+	  no = nop->sibling;
+	}
+
+      for(n = (sG > -1 ? sG : 0); n < (sG > -1 ? sG + 1 : D); n++)
+	{			/* forcetree.c:2262-2428 */
+	  double sg[3], d[3] = { dx[n], dy[n], dz[n] }, f[3], w[8];
+	  int ix[3], c, k;
+	  const double *tab;
+	  if(sG < 0 && mass[n] == 0.0)
+	    continue;
+	  for(k = 0; k < 3; k++)
+	    {
+	      if(d[k] < 0)
+		{
+		  d[k] = -d[k];
+		  sg[k] = +1;
+		}
+	      else
+		sg[k] = -1;
+	      f[k] = d[k] * fac_intp;
+	      ix[k] = (int) f[k];
+	      if(ix[k] >= EN)
+		ix[k] = EN - 1;
+	      f[k] -= ix[k];
+	    }
+	  w[0] = (1 - f[0]) * (1 - f[1]) * (1 - f[2]);
+	  w[1] = (1 - f[0]) * (1 - f[1]) * (f[2]);
+	  w[2] = (1 - f[0]) * (f[1]) * (1 - f[2]);
+	  w[3] = (1 - f[0]) * (f[1]) * (f[2]);
+	  w[4] = (f[0]) * (1 - f[1]) * (1 - f[2]);
+	  w[5] = (f[0]) * (1 - f[1]) * (f[2]);
+	  w[6] = (f[0]) * (f[1]) * (1 - f[2]);
+	  w[7] = (f[0]) * (f[1]) * (f[2]);
+	  for(c = 0; c < 3; c++)
+	    {
+	      tab = o->fcorr + ((size_t) (c * D + pg) * D + n) * n3 + ((size_t) ix[0] * n1 + ix[1]) * n1 + ix[2];
+	      acc[c] += mass[n] * sg[c] * (tab[0] * w[0] + tab[1] * w[1] + tab[n1] * w[2] + tab[n1 + 1] * w[3] +
+					   tab[(size_t) n1 * n1] * w[4] + tab[(size_t) n1 * n1 + 1] * w[5] +
+					   tab[(size_t) n1 * n1 + n1] * w[6] + tab[(size_t) n1 * n1 + n1 + 1] * w[7]);
+	    }
+	}
+      cost++;
+    }
+  /* forcetree.c:2435-2438: added to the FLOAT results of the tree walk */
+  o->P[target].acc[0] += acc[0];
+  o->P[target].acc[1] += acc[1];
+  o->P[target].acc[2] += acc[2];
+  o->P[target].cost += cost;
+  return cost;
+}
+
+static int tree_evaluate_with_lattice(g2o * o, int target)
+{
+  int n = tree_evaluate(o, target);
+  if(o->periodic && !o->shortrange && o->fcorr)
+    lattice_correction(o, target, o->P[target].pos[0], o->P[target].pos[1], o->P[target].pos[2], o->errtol * o->P[target].oldacc);
+  return n;
+}
+
 struct slice { g2o *o; int lo, hi; double cost; };
 static void *walk_slice(void *arg)
 {
@@ -1096,7 +1244,7 @@ static void *walk_slice(void *arg)
   s->cost = 0;
   for(i = s->lo; i < s->hi; i++)
     if(s->o->P[i].active)
-      s->cost += tree_evaluate(s->o, i);
+      s->cost += tree_evaluate_with_lattice(s->o, i);
   return NULL;
 }
 

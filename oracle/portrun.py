@@ -110,6 +110,13 @@ class PortOracle:
         assert t.shape == (self.D, self.D, self.ntab)
         self.L.g2o_set_srtable(self.h, _p(t))
 
+    def set_lattice_tables(self, fcorr, en=64):
+        """fcorrx/y/z after lattice_init, shape (3, D, D, en+1, en+1, en+1) (PERIODIC without PMGRID): gravity() then runs the
+        lattice-correction walk after the tree walk of every target (forcetree.c:1606-1608)."""
+        t = np.ascontiguousarray(fcorr, dtype=np.float64)
+        assert t.shape == (3, self.D, self.D, en + 1, en + 1, en + 1)
+        self.L.g2o_set_lattice_tables(self.h, int(en), _p(t))
+
     def set_potential_laws(self, pot="newtonian", spline="plummer", node_table_term=False):
         """PotentialFxns / PotentialSplines [target][source]; node_table_term = a -DNGRAVS_ACCUMULATOR build (forcetree.c:3134-3140)."""
         D = self.D

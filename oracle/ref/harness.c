@@ -16,6 +16,7 @@
 #include <math.h>
 #include <pthread.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include "allvars.h"
 #include "proto.h"
@@ -133,6 +134,18 @@ int g2ref_setup(const double *par)
   allocate_memory();		/* allocate.c:98  */
   set_softenings();		/* gravtree.c:468 */
   force_treeallocate((int) (All.TreeAllocFactor * All.MaxPart), All.MaxPart);	/* init.c:151 */
+#if defined(PERIODIC) && !defined(PMGRID)
+  {
+    /* begrun.c:47-49.  lattice_init() (forcetree.c:3611) reads its tables from / writes them to lattice_spc_table_*.dat in the working
+     * directory (forcetree.c:3637-3745); G2REF_CACHE_DIR (set by refrun.py to oracle/_ref) keeps that cache next to the libraries. */
+    char cwd[4096];
+    const char *dir = getenv("G2REF_CACHE_DIR");
+    int moved = dir && getcwd(cwd, sizeof(cwd)) && chdir(dir) == 0;
+    lattice_init();
+    if(moved && chdir(cwd) != 0)
+      return -2;
+  }
+#endif
 
   g2ref_ready = 1;
   return 0;
@@ -436,6 +449,14 @@ int g2ref_get_nparticles(long long *out)
 int g2ref_get_srtable(double *out)
 {
   return g2ref_srtable_copy(out);
+}
+
+int g2ref_lattice_copy(double *out);
+/* fcorrx/y/z[tgt][src][EN+1][EN+1][EN+1] after lattice_init (already divided by BoxSize^2, forcetree.c:3757-3761) as double:
+ * out[((c * D + tgt) * D + src) * (EN+1)^3 + ...], c = 0, 1, 2.  Returns EN + 1, or 0 where the variant has no such tables. */
+int g2ref_get_lattice_tables(double *out)
+{
+  return g2ref_lattice_copy(out);
 }
 
 int g2ref_get_srpot_table(double *out)

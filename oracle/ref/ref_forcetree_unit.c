@@ -26,3 +26,25 @@ int g2ref_srpot_copy(double *out)
   return 0;
 #endif
 }
+
+/* the lattice-sum force tables fcorrx/y/z (forcetree.c:49-53), file-scope statics like the tables above */
+int g2ref_lattice_copy(double *out)
+{
+#if defined(PERIODIC) && !defined(PMGRID)
+  const size_t n3 = (size_t) (NGRAVS_EN + 1) * (NGRAVS_EN + 1) * (NGRAVS_EN + 1);
+  int l, m;
+  size_t q;
+  for(l = 0; l < N_GRAVS; l++)
+    for(m = 0; m < N_GRAVS; m++)
+      for(q = 0; q < n3; q++)
+	{
+	  out[((size_t) (0 * N_GRAVS + l) * N_GRAVS + m) * n3 + q] = (&fcorrx[l][m][0][0][0])[q];
+	  out[((size_t) (1 * N_GRAVS + l) * N_GRAVS + m) * n3 + q] = (&fcorry[l][m][0][0][0])[q];
+	  out[((size_t) (2 * N_GRAVS + l) * N_GRAVS + m) * n3 + q] = (&fcorrz[l][m][0][0][0])[q];
+	}
+  return NGRAVS_EN + 1;
+#else
+  (void) out;
+  return 0;
+#endif
+}

@@ -61,8 +61,15 @@ class RefOracle:
         lib.g2ref_spline.restype = C.c_double
         lib.g2ref_accel.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
         lib.g2ref_spline.argtypes = lib.g2ref_accel.argtypes
+        # lattice_init() (PERIODIC without PMGRID) caches its tables as files in the working directory (forcetree.c:3637-3745).  In a
+        # FLOAT = float build that cache is unusable: the tables are `static double` (forcetree.c:49-52) but are written and read with
+        # sizeof(FLOAT) per entry, so a run that FINDS the file gets only the first half of every table (the rest stays zero).  The
+        # oracle therefore always runs in a fresh scratch directory: tables are computed (~1 min), the file is discarded.
+        self._scratch = tempfile.mkdtemp(prefix="g2ref_lattice_")
+        os.environ["G2REF_CACHE_DIR"] = self._scratch
         # the reference prints progress with printf; silence fd 1 during calls
         rc = self._quiet(lib.g2ref_setup, par.ctypes.data_as(C.c_void_p))
+        shutil.rmtree(self._scratch, ignore_errors=True)
         if rc != 0:
             raise RuntimeError("g2ref_setup failed")
         self.maxpart = maxpart
@@ -209,6 +216,16 @@ class RefOracle:
         t = np.zeros((self.D, self.D, self.ntab))
         self.lib.g2ref_get_srtable(t.ctypes.data_as(C.c_void_p))
         return t
+
+    def lattice_tables(self):
+        """fcorrx/y/z[tgt][src][EN+1]^3 after lattice_init (PERIODIC without PMGRID), shape (3, D, D, EN+1, EN+1, EN+1); else None."""
+        en1 = 65
+        out = np.zeros((3, self.D, self.D, en1, en1, en1))
+        got = self.lib.g2ref_get_lattice_tables(out.ctypes.data_as(C.c_void_p))
+        if got == 0:
+            return None
+        assert got == en1
+        return out
 
     def srpot_table(self):
         """shortrange_fourier_pot[tgt][src][NTAB] (forcetree.c:34, filled at 3346); PM variants only."""
