@@ -4,7 +4,8 @@
  * It is compiled WITH the reference's headers (allvars.h, proto.h, ngravs.h) and replaces, symbol for symbol,
  *   gravtree.c : gravity_tree (27), set_softenings (468), grav_tree_compare_key (525)
  *   forcetree.c: force_treeallocate (3176), force_treefree (3411), force_treebuild (61),
- *                force_treeevaluate (1244), force_treeevaluate_shortrange (1623),
+ *                force_treeevaluate (1244; in a PERIODIC build without PMGRID together with force_treeevaluate_lattice_correction, 2077,
+ *                from tables the shim tabulates like lattice_init, 3611), force_treeevaluate_shortrange (1623),
  *                force_treeevaluate_potential_shortrange (2789; PMGRID, unless -DG2_SHIM_KEEP_REFERENCE_POTENTIAL): the per-target
  *                function compute_potential() loops over (potential.c:86-97) is served from ONE device walk of all particles
  *   peano.c    : peano_hilbert_key (356), peano_hilbert_order (36), compare_key (190)
@@ -253,6 +254,54 @@ static void g2_build_srtable(void)
 }
 #endif
 
+#if defined(PERIODIC) && !defined(PMGRID)
+/* lattice_init (forcetree.c:3611-3790) for the device: fcorrx/y/z[target][source] on the (NGRAVS_EN+1)^3 grid x = 0.5 (i,j,k)/NGRAVS_EN,
+ * divided by BoxSize^2.  The reference's own tables are file-scope statics of forcetree.c, so they are tabulated again here: pairs wired
+ * to ewald_force (the stock wiring, ngravs.c:131) on the device in FP64 (g2gpu_make_ewald_table, the same sums), any other LatticeForce
+ * through the reference's function pointer on the host; every distinct function once. */
+static void g2_push_lattice(void)
+{
+  const size_t n1 = NGRAVS_EN + 1, n3 = n1 * n1 * n1;
+  double *tab = malloc(sizeof(double) * 3 * N_GRAVS * N_GRAVS * n3), *one = malloc(sizeof(double) * 3 * n3);
+  int l, m, l2, m2, c, i, j, k;
+  if(!tab || !one)
+    endrun(7501);
+  for(l = 0; l < N_GRAVS; l++)
+    for(m = 0; m < N_GRAVS; m++)
+      {
+	int done = 0;
+	for(l2 = 0; l2 <= l && !done; l2++)
+	  for(m2 = 0; m2 < (l2 < l ? N_GRAVS : m) && !done; m2++)
+	    if(LatticeForce[l2][m2] == LatticeForce[l][m])
+	      {
+		for(c = 0; c < 3; c++)
+		  memcpy(tab + ((size_t) (c * N_GRAVS + l) * N_GRAVS + m) * n3, tab + ((size_t) (c * N_GRAVS + l2) * N_GRAVS + m2) * n3, sizeof(double) * n3);
+		done = 1;
+	      }
+	if(done)
+	  continue;
+	if(LatticeForce[l][m] == ewald_force)
+	  g2_check(g2gpu_make_ewald_table(G2, NGRAVS_EN, one), "make_ewald_table");
+	else
+	  for(i = 0; i <= NGRAVS_EN; i++)
+	    for(j = 0; j <= NGRAVS_EN; j++)
+	      for(k = 0; k <= NGRAVS_EN; k++)
+		{
+		  double x[3] = { 0.5 * i / NGRAVS_EN, 0.5 * j / NGRAVS_EN, 0.5 * k / NGRAVS_EN }, force[3];
+		  (*LatticeForce[l][m]) (i, j, k, x, force);	/* forcetree.c:3700-3710 */
+		  for(c = 0; c < 3; c++)
+		    one[c * n3 + (i * n1 + j) * n1 + k] = force[c];
+		}
+	for(c = 0; c < 3; c++)
+	  for(i = 0; i < (int) n3; i++)
+	    tab[((size_t) (c * N_GRAVS + l) * N_GRAVS + m) * n3 + i] = one[c * n3 + i] / (All.BoxSize * All.BoxSize);	/* forcetree.c:3757-3761 */
+      }
+  g2_check(g2gpu_set_lattice_tables(G2, NGRAVS_EN, tab), "set_lattice_tables");
+  free(one);
+  free(tab);
+}
+#endif
+
 /* forcetree.c:3176.  The host arrays stay (restart.c, predict.c, ngb.c read them); the device context is created
  * once and survives force_treefree() because pm_periodic.c frees/reallocates the tree around every PM step. */
 void force_treeallocate(int maxnodes, int maxpart)
@@ -309,6 +358,9 @@ void force_treeallocate(int maxnodes, int maxpart)
 	g2_build_srtable();
       g2_check(g2gpu_set_srtable(G2, &g2_srtable[0][0][0]), "set_srtable");
       g2_check(g2gpu_set_srpot_table(G2, &g2_srpot[0][0][0]), "set_srpot_table");
+#endif
+#if defined(PERIODIC) && !defined(PMGRID)
+      g2_push_lattice();	/* gravity_tree() then includes the lattice-sum correction walk (forcetree.c:1606-1608) */
 #endif
     }
   if(g2_mirror < 0)
