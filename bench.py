@@ -50,6 +50,16 @@ def make_workload(name):
                          "non-periodic, UNEQUALSOFTENINGS, relative criterion alpha=0.005",
                     key=name, n=n, pos=pos, mass=mass, ptype=ptype, soft=(0.0, eps, eps, eps, eps, eps), grav=(0, 0, 1, 0, 0, 0),
                     D=2, periodic=False, shortrange=False, unequal=True, box=0.0, pmgrid=0, ref_variant="np_d2_f32", flop="np")
+    if name.startswith("periodic") and name.endswith("nopm"):
+        # PERIODIC without PMGRID: tree walk with nearest images + lattice-sum correction walk (forcetree.c:1606-1608)
+        side = int(name[len("periodic"):-4])
+        n, box = side ** 3, 100000.0
+        pos, mass, ptype = g2test.periodic_poisson(n, box, ntypes=2)
+        eps = box / side / 30.0
+        return dict(name=f"periodic {side}^3 Poisson box, two species, no PM: tree walk (nearest image) + lattice-sum correction walk "
+                         "(Ewald table 65^3, made on the device), relative criterion alpha=0.005",
+                    key=name, n=n, pos=pos, mass=mass, ptype=ptype, soft=(eps,) * 6, grav=(0, 0, 1, 0, 0, 0), D=2, periodic=True,
+                    shortrange=False, unequal=False, box=box, pmgrid=0, ref_variant="per_d2_f32", flop="per")
     if name.startswith("periodic"):
         four = name.endswith("x4")                      # BASELINE config 4: all 6 particle types mapped onto 4 species
         side = int(name[len("periodic"):-2] if four else name[len("periodic"):])
@@ -240,6 +250,8 @@ def main():
     import g2test
     tg.set_species(w["grav"], g2test.force_softening(w["soft"]))
     tg.set_laws()
+    if w["periodic"] and not w["shortrange"]:
+        tg.set_ewald_lattice(w["box"])
     if args.acc_float:
         tg.set_option("acc_double", 0)
     if args.walk_group:
@@ -397,7 +409,7 @@ def main():
     # ---- the tree potential of every particle (compute_potential -> force_treeevaluate_potential[_shortrange]) on the tree
     # of the last step, timed by the library's own CUDA events around the kernel; not part of `value`
     potw = None
-    if world == 1 and not args.profile and active is None:
+    if world == 1 and not args.profile and active is None and (w["shortrange"] or not w["periodic"]):
         tg.set_potential_laws()
         if w["shortrange"]:
             ptab = np.load(os.path.join(PKG, "data", "srpot_newton_ntab2048.npy"))
@@ -503,6 +515,9 @@ def main():
         line["pm_long_range"] = pm
     if potw is not None:
         line["potential_walk"] = potw
+    if w["periodic"] and not w["shortrange"]:
+        line["lattice_correction"] = {"kernel": "lattice_kernel", "ms_per_step": (stage["walk_ms"] - stage["walk_kernel_ms"]) / K,
+                                      "note": "walk stage minus walk kernel: target compaction + lattice-sum correction walk of all targets"}
     if world == 1 and not args.no_cpu_baseline and not args.profile and active is None:
         try:
             r = reference_run(w, oldacc_by_id, 1, 0)

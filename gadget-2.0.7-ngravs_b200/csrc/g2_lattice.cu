@@ -11,6 +11,12 @@
 // the gravity_tree epilogue exactly where the reference does (forcetree.c:2435-2437).
 #include "g2_walk_common.cuh"
 
+// resident CTAs of 128 threads per SM.  MEASURED (B200, periodic 128^3 without PM, profiles/experiments/r1_pot_lattice_occupancy.sh):
+// 6 (80 registers) -> 78.6 ms, 7 (72) -> 79.0 ms, 8 (64, 44 bytes spilled) -> 85.8 ms
+#ifndef LATTICE_MINBLOCKS
+#define LATTICE_MINBLOCKS 6
+#endif
+
 struct LatticeArgs
 {
   const float4 *__restrict__ cells;
@@ -51,7 +57,7 @@ __device__ __forceinline__ void lattice_term(const LatticeArgs &A, int ij, float
 }
 
 template <int D>
-__global__ void __launch_bounds__(WALK_THREADS, 6) lattice_kernel(const LatticeArgs A)
+__global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kernel(const LatticeArgs A)
 {
   __shared__ unsigned int s_chunk[WALK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -188,7 +194,7 @@ int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   for(int t = 0; t < 6; t++)
     A.t2g[t] = c->type_to_grav[t];
   memcpy(A.tabmap, c->lattice_tabmap, sizeof(A.tabmap));
-  int grid = c->nsm * 6, need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
+  int grid = c->nsm * LATTICE_MINBLOCKS, need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));

@@ -17,6 +17,16 @@
 // what the reference computes in.
 #include "g2_walk_common.cuh"
 
+// resident CTAs of 128 threads per SM.  MEASURED (B200, periodic 128^3 TreePM, D = 2, profiles/experiments/r1_pot_lattice_occupancy.sh):
+// 6 -> 14.5 ms, 8 -> 12.0 ms, 9 -> 11.3 ms (54 registers as written, no spills at the 56-register cap); D >= 3 needs up to 64 registers
+#ifndef POT_MINBLOCKS
+#define POT_MINBLOCKS 9
+#endif
+#ifndef POT_MINBLOCKS_WIDE
+#define POT_MINBLOCKS_WIDE 8
+#endif
+#define POT_BLOCKS(D) ((D) >= WALK_WIDE_D ? POT_MINBLOCKS_WIDE : POT_MINBLOCKS)
+
 struct PotArgs
 {
   const float4 *__restrict__ cells;
@@ -88,7 +98,7 @@ __device__ __forceinline__ double nearest_d(double x, double box)
 }
 
 template <int D, bool SR, bool UNEQUAL>
-__global__ void __launch_bounds__(WALK_THREADS, 6) pot_kernel(const PotArgs A)
+__global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const PotArgs A)
 {
   constexpr bool PERIODIC = SR;	// the reference's TreePM potential walk is the periodic one
   extern __shared__ float s_tab[];
@@ -303,7 +313,7 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   memcpy(A.potfxn, c->potfxn, sizeof(A.potfxn));
   memcpy(A.potspline, c->potspline, sizeof(A.potspline));
   const size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
-  int grid = c->nsm * 6, need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
+  int grid = c->nsm * POT_BLOCKS(D), need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));
