@@ -64,7 +64,6 @@ __global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kerne
   const int R = 2 + D;
   const int nchunks = (A.hi - A.lo + 31) >> 5;
   const unsigned int end = (unsigned int) A.numnodes;
-  const float boxhalf = 0.5f * A.boxsize;
 
   while(true)
     {
@@ -160,7 +159,6 @@ __global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kerne
 	  else
 	    cur = w.x;
 	}
-      (void) boxhalf;
       if(valid)
 	{
 	  A.latt[3 * (size_t) idx + 0] = (float) ax;

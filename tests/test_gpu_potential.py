@@ -231,3 +231,29 @@ def test_full_size_potential_properties(outdir):
     e = check(single[tg], o.potential_targets(tg), "full size")
     with open(os.path.join(outdir, "potential_p128.json"), "w") as f:
         json.dump(dict(n=n, kernel_ms=res[0][1], kernel_ms_2ranks=res[1][1], err_vs_port=dict(median=float(np.median(e)), p999=float(np.percentile(e, 99.9)), max=float(e.max()))), f)
+
+
+@pytest.mark.parametrize("n", [2, 33, 1000])
+def test_potential_known_answers_small_and_ragged_sets(n):
+    """Sets smaller than a warp and not a multiple of 32: with theta -> 0 every cell is opened, so the tree potential
+    IS the softened direct sum (self term -2.8 m/h = -m/eps included), to FP32 term accuracy."""
+    from g2gpu import TreeGravity
+    rng = np.random.default_rng(100 + n)
+    pos = rng.uniform(-10, 10, size=(n, 3)).astype(np.float32)
+    mass = rng.uniform(0.5, 2.0, n).astype(np.float32)
+    ptype = np.where(np.arange(n) % 3 == 0, 2, 1).astype(np.int32)
+    soft, grav = g2test.SOFT_NP, g2test.GRAV_D2
+    t = TreeGravity(max_part=max(n + 64, 1024), n_gravs=2)      # MaxNodes = 1.5 MaxPart must hold the top-level tree as well
+    t.set_species(grav, g2test.force_softening(soft))
+    t.set_laws()
+    t.set_potential_laws()
+    t.upload(pos, mass, ptype)
+    t.domain()
+    order = t.order()
+    t.treebuild()
+    pot = t.potential(t.walk_params(theta=1.0e-3, errtol=0.005)).astype(np.float64)
+    p, m, ty = pos[order], mass[order], ptype[order]
+    ref = g2test.direct_potential(p, m, g2test.force_softening(soft)[ty], np.arange(n))
+    self_term = -m / np.asarray(soft)[ty]                       # -2.8 m / h, what potential.c:250-254 removes afterwards
+    assert np.all(np.abs(pot - ref) <= 2e-6 * np.abs(ref)), (pot, ref, self_term)
+    assert np.all(pot < self_term), (pot, ref, self_term)
