@@ -1104,6 +1104,82 @@ void g2o_set_lattice_tables(g2o * o, int en, const double *fcorr)
   o->lattice_en = en;
 }
 
+/* ewald_force (ngravs.c:1170-1236) on the grid of lattice_init (forcetree.c:3700-3710): out[c * (en+1)^3 + (i*(en+1)+j)*(en+1)+k],
+ * x = 0.5 (i,j,k)/en, dimensionless (lattice_init divides by BoxSize^2 afterwards, forcetree.c:3757-3761).  Same sums in the same order. */
+struct ewslice { int en, lo, hi; double *out; };
+static void *ewald_slice(void *arg)
+{
+  struct ewslice *s = arg;
+  const int en = s->en, n1 = en + 1;
+  const size_t n3 = (size_t) n1 * n1 * n1;
+  const double alpha = 2.0;
+  int q, a, n[3], h[3];
+  for(q = s->lo; q < s->hi; q++)
+    {
+      const int i = q / (n1 * n1), j = (q / n1) % n1, k = q % n1;
+      double x[3] = { 0.5 * ((double) i) / en, 0.5 * ((double) j) / en, 0.5 * ((double) k) / en };
+      double force[3] = { 0, 0, 0 }, r2, r, val, hdotx, dx[3];
+      if(q != 0)
+	{
+	  r2 = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+	  for(a = 0; a < 3; a++)
+	    force[a] += x[a] / (r2 * sqrt(r2));
+	  for(n[0] = -4; n[0] <= 4; n[0]++)
+	    for(n[1] = -4; n[1] <= 4; n[1]++)
+	      for(n[2] = -4; n[2] <= 4; n[2]++)
+		{
+		  for(a = 0; a < 3; a++)
+		    dx[a] = x[a] - n[a];
+		  r = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+		  val = erfc(alpha * r) + 2 * alpha * r / sqrt(M_PI) * exp(-alpha * alpha * r * r);
+		  for(a = 0; a < 3; a++)
+		    force[a] -= dx[a] / (r * r * r) * val;
+		}
+	  for(h[0] = -4; h[0] <= 4; h[0]++)
+	    for(h[1] = -4; h[1] <= 4; h[1]++)
+	      for(h[2] = -4; h[2] <= 4; h[2]++)
+		{
+		  int h2 = h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+		  hdotx = x[0] * h[0] + x[1] * h[1] + x[2] * h[2];
+		  if(h2 > 0)
+		    {
+		      val = 2.0 / ((double) h2) * exp(-M_PI * M_PI * h2 / (alpha * alpha)) * sin(2 * M_PI * hdotx);
+		      for(a = 0; a < 3; a++)
+			force[a] -= h[a] * val;
+		    }
+		}
+	}
+      for(a = 0; a < 3; a++)
+	s->out[a * n3 + q] = force[a];
+    }
+  return NULL;
+}
+
+int g2o_make_ewald_table(int en, int nthreads, double *out)
+{
+  const int n3 = (en + 1) * (en + 1) * (en + 1);
+  pthread_t *th;
+  struct ewslice *sl;
+  int t;
+  if(nthreads < 1)
+    nthreads = 1;
+  th = malloc(sizeof(pthread_t) * nthreads);
+  sl = malloc(sizeof(struct ewslice) * nthreads);
+  for(t = 0; t < nthreads; t++)
+    {
+      sl[t].en = en;
+      sl[t].out = out;
+      sl[t].lo = (int) ((long long) n3 * t / nthreads);
+      sl[t].hi = (int) ((long long) n3 * (t + 1) / nthreads);
+      pthread_create(&th[t], NULL, ewald_slice, &sl[t]);
+    }
+  for(t = 0; t < nthreads; t++)
+    pthread_join(th[t], NULL);
+  free(sl);
+  free(th);
+  return 0;
+}
+
 static int lattice_correction(g2o * o, int target, double pos_x, double pos_y, double pos_z, double aold)
 {
   const int D = o->D, MP = o->maxpart, EN = o->lattice_en, n1 = EN + 1;

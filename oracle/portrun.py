@@ -62,6 +62,14 @@ def make_srtables(ntab=2048, kind=0, ym=0.0):
     return f, p
 
 
+def make_ewald_table(en=64, nthreads=8):
+    """ewald_force (ngravs.c:1170) on the (en+1)^3 grid of lattice_init, dimensionless: (3, en+1, en+1, en+1); ~5 s on 8 threads."""
+    out = np.zeros((3, en + 1, en + 1, en + 1))
+    rc = lib().g2o_make_ewald_table(int(en), int(nthreads), _p(out))
+    assert rc == 0
+    return out
+
+
 class PortOracle:
     def __init__(self, maxpart, D=2, periodic=False, shortrange=False, unequal=True, ntab=2048, boxsize=0.0, G=1.0, theta=0.5,
                  errtol=0.005, softening=(0.0, 1.0, 1.0, 1.0, 1.0, 1.0), gravity=(0, 0, 1, 0, 0, 0), tree_alloc=1.5, pmgrid=0,

@@ -153,3 +153,32 @@ def test_lattice_correction_with_sparse_active_targets():
     t2.treebuild()
     t2.walk(wp)
     assert t2.timings()["interactions"] == 0
+
+
+def test_lattice_correction_matches_golden_fixture():
+    """The committed fixture of the unmodified PERIODIC-without-PMGRID reference (tests/golden/make_golden_lattice.py; single species, so
+    only its complete [0][0] table is involved) against the device walk with the device-made Ewald table: needs no reference build."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lattice_per_d2_poisson3000.npz"))
+    box, n = float(g["box"]), len(g["mass"])
+    t = gpu_periodic(int(g["maxpart"]), g["grav"], g["soft"])
+    ew = t.set_ewald_lattice(box)
+    idx = g["table_index"]
+    assert np.abs(ew[:, idx[:, 0], idx[:, 1], idx[:, 2]] - g["table_sample"]).max() <= 1e-9 * np.abs(g["table_sample"]).max()
+    t.upload(g["pos"], g["mass"], g["type"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    t.walk(t.walk_params(theta=0.5, errtol=0.005, boxsize=box))
+    acc, cost, old = t.download_acc()
+    e = g2test.rel_err(acc, g["bh_acc"])
+    assert np.median(e) <= 1e-5 and np.percentile(e, 99.9) <= 1e-3, (np.median(e), e.max())
+    assert (cost != g["bh_cost"]).sum() <= max(1, 0.002 * n)
+    t.upload(g["pos"], g["mass"], g["type"], oldacc=g["bh_oldacc"])
+    t.domain()
+    t.treebuild()
+    t.walk(t.walk_params(theta=0.0, errtol=0.005, boxsize=box))
+    acc2, cost2, _ = t.download_acc()
+    e2 = g2test.rel_err(acc2, g["rel_acc"])
+    assert np.median(e2) <= 1e-5 and np.percentile(e2, 99.9) <= 1e-3, (np.median(e2), e2.max())
+    assert (cost2 != g["rel_cost"]).sum() <= max(1, 0.002 * n)

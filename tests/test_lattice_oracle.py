@@ -56,3 +56,33 @@ def test_port_lattice_correction_matches_reference_build():
     r2, p2 = ref.particles(), o.particles()
     assert np.array_equal(p2["cost"], r2["cost"])
     assert np.array_equal(p2["acc"], r2["acc"].astype(np.float32))
+
+
+def test_port_lattice_correction_matches_golden_fixture():
+    """Needs no reference build: the port tabulates ewald_force itself (g2o_make_ewald_table, the sums of ngravs.c:1170-1236 in the same
+    order) and must reproduce the reference's sampled table entries and its results for the committed single-species fixture
+    (tests/golden/make_golden_lattice.py).  Tolerances instead of bit patterns only because erfc/exp/sin may differ by an ulp between
+    C libraries; on the machine that made the fixture the table is bit-identical."""
+    from portrun import make_ewald_table
+    g = np.load(os.path.join(GOLD, "lattice_per_d2_poisson3000.npz"))
+    box, n = float(g["box"]), len(g["mass"])
+    ew = make_ewald_table(64) / (box * box)
+    idx = g["table_index"]
+    sample = ew[:, idx[:, 0], idx[:, 1], idx[:, 2]]
+    assert np.abs(sample - g["table_sample"]).max() <= 1e-12 * np.abs(g["table_sample"]).max()
+    o = PortOracle(int(g["maxpart"]), D=2, periodic=True, shortrange=False, unequal=False, boxsize=box, softening=g["soft"], gravity=g["grav"])
+    o.set_lattice_tables(np.broadcast_to(ew[:, None, None], (3, 2, 2, 65, 65, 65)).copy())
+    o.load(g["pos"], g["mass"], g["type"])
+    o.domain()
+    assert np.array_equal(o.particles()["id"], np.arange(n))
+    o.gravity()
+    p1 = o.particles()
+    assert np.array_equal(p1["cost"], g["bh_cost"])
+    assert g2test.rel_err(p1["acc"], g["bh_acc"]).max() <= 1e-6
+    o.set_opening(0.0, 0.005)
+    o.load(g["pos"], g["mass"], g["type"], oldacc=g["bh_oldacc"])
+    o.domain()
+    o.gravity()
+    p2 = o.particles()
+    assert np.array_equal(p2["cost"], g["rel_cost"])
+    assert g2test.rel_err(p2["acc"], g["rel_acc"]).max() <= 1e-6
