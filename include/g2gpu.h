@@ -237,7 +237,8 @@ int g2gpu_set_potential_laws(g2gpu_ctx *ctx, const int *pot_id, const int *potsp
 /* shortrange_fourier_pot[target][source][NTAB] (forcetree.c:34, filled at 3346), as double. */
 int g2gpu_set_srpot_table(g2gpu_ctx *ctx, const double *table);
 int g2gpu_potential(g2gpu_ctx *ctx, const g2gpu_walk_params *wp);
-/* pot[n] = P[].Potential as left by the walk, in CURRENT particle order; *kernel_ms (optional) = CUDA-event time of the walk kernel. */
+/* pot[n] = P[].Potential as left by the walk, in CURRENT particle order; with nranks > 1 only the entries of this rank's slice are written
+ * by a call (the others keep what an earlier call left, zero initially).  *kernel_ms (optional) = CUDA-event time of the walk kernel. */
 int g2gpu_download_potential(g2gpu_ctx *ctx, float *pot, double *kernel_ms);
 
 /* ---- periodic PM long-range force: pmforce_periodic (pm_periodic.c:204-790), the caller of which is long_range_force

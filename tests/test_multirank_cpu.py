@@ -42,13 +42,19 @@ WORKER = textwrap.dedent('''
     acc[tlo:thi] = torch.from_numpy(p["accd"][tlo:thi])
     cnt = torch.zeros(n, dtype=torch.float64)
     cnt[tlo:thi] = torch.from_numpy(p["cost"][tlo:thi].astype(np.float64))
+    # the tree potential shards the same way (every particle is a target, potential.c:86): a rank walks its slice only
+    o.set_potential_laws("newtonian", "plummer")
+    o.set_opening(0.5, 0.005)
+    pot = torch.zeros(n, dtype=torch.float64)
+    pot[tlo:thi] = torch.from_numpy(o.potential_targets(np.arange(tlo, thi, dtype=np.int32)).astype(np.float64))
     dist.all_reduce(acc)       # slices are disjoint: the sum is a concatenation
     dist.all_reduce(cnt)
+    dist.all_reduce(pot)
     nodes = torch.tensor([nn]); allnodes = [torch.zeros_like(nodes) for _ in range(world)]
     dist.all_gather(allnodes, nodes)
     assert all(int(x) == nn for x in allnodes)
     if rank == 0:
-        np.save(sys.argv[2], np.concatenate([acc.numpy(), cnt.numpy()[:, None]], axis=1))
+        np.save(sys.argv[2], np.concatenate([acc.numpy(), cnt.numpy()[:, None], pot.numpy()[:, None]], axis=1))
     dist.destroy_process_group()
 ''')
 
@@ -84,3 +90,5 @@ def test_two_ranks_reproduce_single_rank(tmp_path):
     p = o.particles()
     assert np.array_equal(got[:, :3], p["accd"])
     assert np.array_equal(got[:, 3], p["cost"].astype(np.float64))
+    o.set_potential_laws("newtonian", "plummer")
+    assert np.array_equal(got[:, 4], o.potential(nthreads=2).astype(np.float64))
