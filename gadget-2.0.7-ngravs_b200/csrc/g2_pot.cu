@@ -38,6 +38,7 @@ struct PotArgs
   unsigned int *__restrict__ work_counter;
   int lo, hi, numnodes, ntab, ntables, node_table_term;
   float theta2, errtol, boxsize, boxinv, rcut, asmthfac, utorwpi;
+  float shift_len_max;		// -DG2_POT_CELLSHIFT: cells smaller than this take the periodic image of their centre for all their points
   double rcut_d, boxsize_d;
   float fsoft[6];
   int t2g[6];
@@ -149,6 +150,16 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
 	  bool open = false;
+#ifdef G2_POT_CELLSHIFT
+	  // EXPERIMENT (off; not yet measured): the per-cell image shift of the force walk (g2_walk.cu).  A cell that is not culled lies within
+	  // rcut + len/2 of the target on every axis, so for len < L/2 - rcut all its points share the periodic image of its centre: 3 rint
+	  // per cell instead of 3 per point.  Same results bit for bit (box * k is exact for k = -1, 0, 1).
+	  const bool small_cell = SR && q0.x < A.shift_len_max;
+	  float shx = 0.0f, shy = 0.0f, shz = 0.0f;
+#define POT_WRAP(v, sh) (small_cell ? (v) - (sh) : nearest<PERIODIC>((v), A.boxsize, A.boxinv))
+#else
+#define POT_WRAP(v, sh) nearest<PERIODIC>((v), A.boxsize, A.boxinv)
+#endif
 	  if(cur >= skip_until)
 	    {
 	      float r2[D], mass[D];
@@ -159,8 +170,15 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 	      if(SR)
 		{		// forcetree.c:2988-3015
 		  const float eff = A.rcut + 0.5f * len;
+#ifdef G2_POT_CELLSHIFT
+		  shx = A.boxsize * rint_small(cxr * A.boxinv);
+		  shy = A.boxsize * rint_small(cyr * A.boxinv);
+		  shz = A.boxsize * rint_small(czr * A.boxinv);
+		  const float d0 = fabsf(cxr - shx), d1 = fabsf(cyr - shy), d2 = fabsf(czr - shz);
+#else
 		  const float d0 = fabsf(nearest<PERIODIC>(cxr, A.boxsize, A.boxinv)), d1 = fabsf(nearest<PERIODIC>(cyr, A.boxsize, A.boxinv)),
 		    d2 = fabsf(nearest<PERIODIC>(czr, A.boxsize, A.boxinv));
+#endif
 		  const float dmax = fmaxf(fmaxf(d0, d1), d2);
 		  done = dmax > eff;
 		  if(fabsf(dmax - eff) < 4.0e-6f * A.boxsize)
@@ -179,9 +197,9 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 		      const float4 q = __ldg(rec + 1 + g);
 		      mass[g] = q.w;
 		      summass += q.w;
-		      const float dx = nearest<PERIODIC>(q.x - px, A.boxsize, A.boxinv);
-		      const float dy = nearest<PERIODIC>(q.y - py, A.boxsize, A.boxinv);
-		      const float dz = nearest<PERIODIC>(q.z - pz, A.boxsize, A.boxinv);
+		      const float dx = POT_WRAP(q.x - px, shx);
+		      const float dy = POT_WRAP(q.y - py, shy);
+		      const float dz = POT_WRAP(q.z - pz, shz);
 		      r2[g] = dx * dx + dy * dy + dz * dz;
 		      r2min = fminf(r2min, r2[g]);
 		      r2max = fmaxf(r2max, r2[g]);
@@ -238,9 +256,9 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 		      float h = hself;
 		      if(UNEQUAL)
 			h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:2958-2961
-		      const float dx = nearest<PERIODIC>(p.x - px, A.boxsize, A.boxinv);
-		      const float dy = nearest<PERIODIC>(p.y - py, A.boxsize, A.boxinv);
-		      const float dz = nearest<PERIODIC>(p.z - pz, A.boxsize, A.boxinv);
+		      const float dx = POT_WRAP(p.x - px, shx);
+		      const float dy = POT_WRAP(p.y - py, shy);
+		      const float dz = POT_WRAP(p.z - pz, shz);
 		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true);
 		    }
 		}
@@ -254,6 +272,8 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 	A.pot[idx] = (float) pot;	// forcetree.c:3158
     }
 }
+
+#undef POT_WRAP
 
 template <int D>
 static void launch_pot(g2gpu_ctx *c, const PotArgs &A, int grid, size_t smem, bool sr, bool unequal)
@@ -303,6 +323,7 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.rcut = (float) wp->rcut; A.rcut_d = wp->rcut;
       A.asmthfac = (float) (0.5 / wp->asmth * (c->cfg.ntab / 3.0));	// forcetree.c:2862
       A.utorwpi = (float) (1.0 / (2 * M_PI * wp->asmth));	// forcetree.c:2865
+      A.shift_len_max = (float) (0.499 * wp->boxsize - 1.001 * wp->rcut);
     }
   for(int t = 0; t < 6; t++)
     {
