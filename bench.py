@@ -207,8 +207,7 @@ def main():
     ap.add_argument("--active-frac", type=float, default=1.0, help="fraction of particles with Ti_endstep == Ti_Current (random, seed 7); "
                     "the metric then counts the ACTIVE particles only (SURVEY.md §8d 'sparse active' case)")
     ap.add_argument("--acc-float", action="store_true", help="FP32 accumulators in the walk (default FP64)")
-    ap.add_argument("--walk-group", type=int, default=0, help="targets per walk cursor (4, 8, 16, 32); 0 = library default")
-    ap.add_argument("--walk-mode", type=int, default=-1, help="0: one cursor per 32 targets; 1: one warp per target; -1 = library default")
+    ap.add_argument("--walk-exact", type=int, default=1, help="1 (default): borderline decisions re-walked in FP64 (exact GravCost); 0: FP32 decisions only")
     ap.add_argument("--profile", action="store_true", help="short run for ncu: 1 warm-up step, no e2e / cpu_baseline legs")
     args = ap.parse_args()
 
@@ -254,10 +253,7 @@ def main():
         tg.set_ewald_lattice(w["box"])
     if args.acc_float:
         tg.set_option("acc_double", 0)
-    if args.walk_group:
-        tg.set_option("walk_group", args.walk_group)
-    if args.walk_mode >= 0:
-        tg.set_option("walk_mode", args.walk_mode)
+    tg.set_option("walk_exact", args.walk_exact)
     asmth, rcut = pm_split(w)
     if w["shortrange"]:
         tab = np.load(os.path.join(PKG, "data", "srtable_newton_ntab2048.npy"))
@@ -336,6 +332,12 @@ def main():
     wall = time.time() - wall0
     sampler.end()
     launches = tg.timings()["launches"]
+    # one more, untimed step with the instrumented walk kernel: species terms, cell visits and decisions for the roofline figures
+    tg.set_option("walk_stats", 1)
+    step_resident()
+    tg.sync()
+    last = tg.timings()
+    tg.set_option("walk_stats", 0)
     ms_dev = sum(a.elapsed_time(b) for a, b in ev)
     t_ms = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
     inter = torch.tensor([float(last["interactions"]), float(last["species_terms"]), float(last["cell_visits"]), float(last["decisions"])],

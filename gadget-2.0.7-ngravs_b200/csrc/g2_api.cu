@@ -6,7 +6,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
-char g2_errbuf[512] = "";
+__thread char g2_errbuf[512] = "";
 
 int g2_fail(int code, const char *fmt, ...)
 {
@@ -64,31 +64,27 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->D = cfg->n_gravs;
   c->nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : G2_NSM_FALLBACK;
   c->acc_double = 1;
-  c->walk_group = 32;
-  c->walk_mode = G2_DEFAULT_WALK_MODE;
-  if(getenv("G2GPU_WALK_MODE"))
-    c->walk_mode = atoi(getenv("G2GPU_WALK_MODE")) == 1 ? 1 : 0;
-  if(getenv("G2GPU_WALK_GROUP"))
-    {
-      int g = atoi(getenv("G2GPU_WALK_GROUP"));
-      if(g == 8 || g == 32)
-	c->walk_group = g;
-    }
+  c->walk_exact = getenv("G2GPU_WALK_EXACT") ? atoi(getenv("G2GPU_WALK_EXACT")) != 0 : 1;
   for(int t = 0; t < 6; t++)
     c->force_softening[t] = 1.0;
-  G2_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  for(int i = 0; i < 20; i++)
-    G2_CUDA(cudaEventCreate(&c->ev[i]));
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for(int i = 0; i < 20 && ok; i++)
+    ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  if(!ok)
+    {
+      g2gpu_destroy(c);
+      return g2_fail(G2GPU_ERR_CUDA, "stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
 
   const size_t np = (size_t) cfg->max_part, nn = (size_t) cfg->max_nodes;
   const size_t cap = (np > nn ? np : nn) + G2_MAXTOP + 8;
   const int R = 2 + c->D;
   int rc = 0;
-  rc |= dalloc(&c->in_rec, np);
+  rc |= dalloc(&c->in_rec, np + 64);	// + slack: the padded all-gather of the multi-GPU group may write up to 7 records past MaxPart
   rc |= dalloc(&c->in_raw, 7 * np);
   c->own_in_rec = c->in_rec;
   rc |= dalloc(&c->prec, np);
-  rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np);
+  rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np); rc |= dalloc(&c->phorder, np);
   rc |= dalloc(&c->skey[0], np); rc |= dalloc(&c->skey[1], np); rc |= dalloc(&c->sval[0], np); rc |= dalloc(&c->sval[1], np);
   c->tilehist_elems = (size_t) ((np + 4095) / 4096) * 512 + 8;
   rc |= dalloc(&c->tilehist, c->tilehist_elems);
@@ -110,21 +106,25 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->d_depth, (size_t) 64);
   rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
   rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
-  rc |= dalloc(&c->d_counters, (size_t) 8);
+  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256);
   if(rc)
     {
       g2gpu_destroy(c);
       return G2GPU_ERR_NOMEM;
     }
   if(cudaMallocHost((void **) &c->h_err, 64 * sizeof(int)) != cudaSuccess || cudaMallocHost((void **) &c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess
-     || cudaMallocHost((void **) &c->h_top, sizeof(G2TopTree)) != cudaSuccess)
+     || cudaMallocHost((void **) &c->h_top, sizeof(G2TopTree)) != cudaSuccess || cudaMallocHost((void **) &c->h_slice, 4 * sizeof(int)) != cudaSuccess
+     || cudaMallocHost((void **) &c->h_domain, 8 * sizeof(double)) != cudaSuccess)
     {
       g2gpu_destroy(c);
       return g2_fail(G2GPU_ERR_NOMEM, "pinned host allocation failed");
     }
-  G2_CUDA(cudaMemset(c->acc, 0, sizeof(float) * 3 * np));
-  G2_CUDA(cudaMemset(c->cost, 0, sizeof(float) * np));
-  G2_CUDA(cudaMemset(c->oldacc_out, 0, sizeof(float) * np));
+  if(cudaMemset(c->acc, 0, sizeof(float) * 3 * np) != cudaSuccess || cudaMemset(c->cost, 0, sizeof(float) * np) != cudaSuccess
+     || cudaMemset(c->oldacc_out, 0, sizeof(float) * np) != cudaSuccess || cudaMemset(c->d_slice, 0, 4 * sizeof(int)) != cudaSuccess)
+    {
+      g2gpu_destroy(c);
+      return g2_fail(G2GPU_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
   *out = c;
   return 0;
 }
@@ -141,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->b_q0, c->b_s, c->b_w, c->b_ptype, c->b_key[0], c->b_key[1], c->b_val[0], c->b_val[1], c->b_vofu };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -152,6 +152,10 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     cudaFreeHost(c->h_counters);
   if(c->h_top)
     cudaFreeHost(c->h_top);
+  if(c->h_slice)
+    cudaFreeHost(c->h_slice);
+  if(c->h_domain)
+    cudaFreeHost(c->h_domain);
   if(c->h_stage)
     cudaFreeHost(c->h_stage);
   if(c->h_rec)
@@ -231,6 +235,12 @@ extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
 	}
       c->sr_tabmap[i] = (unsigned char) found;
     }
+  if((size_t) nu * ntab * sizeof(float) > 200 * 1024)
+    {
+      c->srtable_set = 0;
+      return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range tables do not fit in shared memory", nu);
+    }
+  c->srtable_set = 0;
   c->sr_ntables = nu;
   float *hf = (float *) malloc(sizeof(float) * (size_t) nu * ntab);
   if(!hf)
@@ -247,8 +257,6 @@ extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
   free(hf);
   if(rc)
     return rc;
-  if((size_t) nu * ntab * sizeof(float) > 200 * 1024)
-    return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range tables do not fit in shared memory", nu);
   c->srtable_set = 1;
   return 0;
 }
@@ -258,17 +266,17 @@ static int ensure_opt(g2gpu_ctx *c, int want_vel, int want_gravpm)
 {
   const size_t np = (size_t) c->cfg.max_part;
   if(want_vel && !c->in_vel)
-    {
-      G2_TRY(dalloc(&c->in_vel, 3 * np));
-      G2_TRY(dalloc(&c->vel, 3 * np));
-    }
+    G2_TRY(dalloc(&c->in_vel, 3 * np));
+  if(want_vel && !c->vel)
+    G2_TRY(dalloc(&c->vel, 3 * np));
   if(want_gravpm && !c->in_gravpm)
-    {
-      G2_TRY(dalloc(&c->in_gravpm, 3 * np));
-      G2_TRY(dalloc(&c->gravpm, 3 * np));
-    }
+    G2_TRY(dalloc(&c->in_gravpm, 3 * (np + 64)));
+  if(want_gravpm && !c->gravpm)
+    G2_TRY(dalloc(&c->gravpm, 3 * np));
   return 0;
 }
+
+int g2_ensure_optional_inputs(g2gpu_ctx *c, int want_vel, int want_gravpm) { return ensure_opt(c, want_vel, want_gravpm); }
 
 // SoA arrays go to the device as they are (no host-side repacking); pack_inputs_kernel builds the 32-byte records.
 __global__ void __launch_bounds__(256) pack_inputs_kernel(int n, const float *__restrict__ pos3, const float *__restrict__ mass, const int *__restrict__ type,
@@ -289,6 +297,43 @@ __global__ void __launch_bounds__(256) pack_inputs_kernel(int n, const float *__
   rec[i] = r;
 }
 
+// records [lo, lo + cnt) of an n_total-particle set: H2D of the SoA pieces + pack into own_in_rec[lo ...] (the multi-GPU group uploads
+// one shard per device and all-gathers the rest over NVLink, g2_group.cu)
+int g2_upload_soa_shard(g2gpu_ctx *c, int n_total, int lo, int cnt, const float *pos, const float *mass, const int *type, const float *oldacc,
+			const int *active)
+{
+  if(n_total < 1 || n_total > c->cfg.max_part || lo < 0 || cnt < 0 || lo + cnt > n_total)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d] (shard %d+%d)", n_total, c->cfg.max_part, lo, cnt);
+  c->in_rec = c->own_in_rec;	// back to the library's own input buffer
+  c->inputs_bound = 0;
+  const size_t n = (size_t) cnt;
+  cudaStream_t st = c->stream;
+  float *d_pos3 = c->in_raw, *d_mass = c->in_raw + 3 * n, *d_old = c->in_raw + 5 * n;
+  int *d_type = (int *) (c->in_raw + 4 * n), *d_act = (int *) (c->in_raw + 6 * n);
+  G2_CUDA(cudaEventRecord(c->ev[9], st));
+  if(cnt > 0)
+    {
+      G2_CUDA(cudaMemcpyAsync(d_pos3, pos + 3 * (size_t) lo, n * 12, cudaMemcpyHostToDevice, st));
+      G2_CUDA(cudaMemcpyAsync(d_mass, mass + lo, n * 4, cudaMemcpyHostToDevice, st));
+      G2_CUDA(cudaMemcpyAsync(d_type, type + lo, n * 4, cudaMemcpyHostToDevice, st));
+      if(oldacc)
+	G2_CUDA(cudaMemcpyAsync(d_old, oldacc + lo, n * 4, cudaMemcpyHostToDevice, st));
+      if(active)
+	G2_CUDA(cudaMemcpyAsync(d_act, active + lo, n * 4, cudaMemcpyHostToDevice, st));
+      pack_inputs_kernel<<<g2_cdiv(cnt, 256), 256, 0, st>>>(cnt, d_pos3, d_mass, d_type, oldacc ? d_old : nullptr, active ? d_act : nullptr, c->own_in_rec + lo);
+      c->launches++;
+    }
+  G2_CUDA(cudaEventRecord(c->ev[10], st));
+  G2_CUDA(cudaGetLastError());
+  c->h2d_bytes = n * (12 + 4 + 4 + (oldacc ? 4 : 0) + (active ? 4 : 0));
+  c->have_vel = 0;
+  c->have_gravpm = 0;
+  c->pm_done = 0;
+  c->npart = n_total;
+  c->stage = 1;
+  return 0;
+}
+
 extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
 			    const float *vel, const float *gravpm, const int *active)
 {
@@ -298,51 +343,32 @@ extern "C" int g2gpu_upload(g2gpu_ctx *c, int npart, const float *pos, const flo
     return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
   G2_CUDA(cudaSetDevice(c->cfg.device));
   G2_TRY(ensure_opt(c, vel != nullptr, gravpm != nullptr));
-  c->in_rec = c->own_in_rec;	// back to the library's own input buffer
-  c->inputs_bound = 0;
+  G2_TRY(g2_upload_soa_shard(c, npart, 0, npart, pos, mass, type, oldacc, active));
   const size_t n = (size_t) npart;
   cudaStream_t st = c->stream;
-  float *d_pos3 = c->in_raw, *d_mass = c->in_raw + 3 * n, *d_old = c->in_raw + 5 * n;
-  int *d_type = (int *) (c->in_raw + 4 * n), *d_act = (int *) (c->in_raw + 6 * n);
-  G2_CUDA(cudaEventRecord(c->ev[9], st));
-  G2_CUDA(cudaMemcpyAsync(d_pos3, pos, n * 12, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(d_mass, mass, n * 4, cudaMemcpyHostToDevice, st));
-  G2_CUDA(cudaMemcpyAsync(d_type, type, n * 4, cudaMemcpyHostToDevice, st));
-  if(oldacc)
-    G2_CUDA(cudaMemcpyAsync(d_old, oldacc, n * 4, cudaMemcpyHostToDevice, st));
-  if(active)
-    G2_CUDA(cudaMemcpyAsync(d_act, active, n * 4, cudaMemcpyHostToDevice, st));
   if(vel)
     G2_CUDA(cudaMemcpyAsync(c->in_vel, vel, n * 12, cudaMemcpyHostToDevice, st));
   if(gravpm)
     G2_CUDA(cudaMemcpyAsync(c->in_gravpm, gravpm, n * 12, cudaMemcpyHostToDevice, st));
-  pack_inputs_kernel<<<g2_cdiv(npart, 256), 256, 0, st>>>(npart, d_pos3, d_mass, d_type, oldacc ? d_old : nullptr, active ? d_act : nullptr, c->in_rec);
-  c->launches++;
   G2_CUDA(cudaEventRecord(c->ev[10], st));
-  G2_CUDA(cudaGetLastError());
-  c->h2d_bytes = n * (12 + 4 + 4 + (oldacc ? 4 : 0) + (active ? 4 : 0) + (vel ? 12 : 0) + (gravpm ? 12 : 0));
+  c->h2d_bytes += n * ((vel ? 12 : 0) + (gravpm ? 12 : 0));
   c->have_vel = vel != nullptr;
   c->have_gravpm = gravpm != nullptr;
-  c->pm_done = 0;
-  c->npart = npart;
-  c->stage = 1;
   return 0;
 }
 
 // The reference's AoS goes through ONE pass on the host (several threads) into a pinned staging area that already has the
 // device layout -- 32-byte particle records (+ optional velocity / GravPM triples) -- and then to the device with one copy each.
-extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
-				int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current)
+// Records [lo, lo + cnt) of an n_total-particle set (a shard per device in the multi-GPU group; the whole set otherwise).
+int g2_upload_aos_shard(g2gpu_ctx *c, int n_total, int lo, int cnt, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
+			int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current, unsigned int max_threads)
 {
-  if(!c || !P)
-    return g2_fail(G2GPU_ERR_ARG, "null argument");
-  if(npart < 1 || npart > c->cfg.max_part)
-    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d]", npart, c->cfg.max_part);
+  if(n_total < 1 || n_total > c->cfg.max_part || lo < 0 || cnt < 0 || lo + cnt > n_total)
+    return g2_fail(G2GPU_ERR_ARG, "npart %d outside [1, MaxPart=%d] (shard %d+%d)", n_total, c->cfg.max_part, lo, cnt);
   if(float_bytes != 4 && float_bytes != 8)
     return g2_fail(G2GPU_ERR_ARG, "float_bytes must be 4 or 8");
-  G2_CUDA(cudaSetDevice(c->cfg.device));
   G2_TRY(ensure_opt(c, off_vel >= 0, off_gravpm >= 0));
-  const size_t n = (size_t) npart, np = (size_t) c->cfg.max_part;
+  const size_t n = (size_t) cnt, np = (size_t) c->cfg.max_part;
   if(!c->h_rec)
     G2_CUDA(cudaMallocHost((void **) &c->h_rec, sizeof(G2PRec) * np));
   if(off_vel >= 0 && !c->h_vel)
@@ -351,12 +377,12 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
     G2_CUDA(cudaMallocHost((void **) &c->h_gravpm, sizeof(float) * 3 * np));
   cudaStream_t st = c->stream;
   G2_CUDA(cudaStreamSynchronize(st));	// the staging area may still be the source of the previous upload
-  const char *base = (const char *) P;
+  const char *base = (const char *) P + (size_t) lo * stride;
   G2PRec *hrec = c->h_rec;
   float *hvel = c->h_vel, *hgpm = c->h_gravpm;
-  auto convert = [=](size_t lo, size_t hi) {
+  auto convert = [=](size_t a, size_t b) {
 #define G2_RD(off, k) (float_bytes == 4 ? ((const float *) (q + (off)))[k] : (float) ((const double *) (q + (off)))[k])
-    for(size_t i = lo; i < hi; i++)
+    for(size_t i = a; i < b; i++)
       {
 	const char *q = base + i * stride;
 	G2PRec r;
@@ -379,7 +405,7 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
 #undef G2_RD
   };
   unsigned int nthr = std::thread::hardware_concurrency();
-  nthr = std::max(1u, std::min(std::min(nthr, 16u), (unsigned int) (n / 262144 + 1)));
+  nthr = std::max(1u, std::min(std::min(nthr, max_threads), (unsigned int) (n / 262144 + 1)));
   if(nthr == 1)
     convert(0, n);
   else
@@ -393,19 +419,32 @@ extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t s
   c->in_rec = c->own_in_rec;
   c->inputs_bound = 0;
   G2_CUDA(cudaEventRecord(c->ev[9], st));
-  G2_CUDA(cudaMemcpyAsync(c->own_in_rec, hrec, sizeof(G2PRec) * n, cudaMemcpyHostToDevice, st));
-  if(off_vel >= 0)
-    G2_CUDA(cudaMemcpyAsync(c->in_vel, hvel, n * 12, cudaMemcpyHostToDevice, st));
-  if(off_gravpm >= 0)
-    G2_CUDA(cudaMemcpyAsync(c->in_gravpm, hgpm, n * 12, cudaMemcpyHostToDevice, st));
+  if(cnt > 0)
+    {
+      G2_CUDA(cudaMemcpyAsync(c->own_in_rec + lo, hrec, sizeof(G2PRec) * n, cudaMemcpyHostToDevice, st));
+      if(off_vel >= 0)
+	G2_CUDA(cudaMemcpyAsync(c->in_vel + 3 * (size_t) lo, hvel, n * 12, cudaMemcpyHostToDevice, st));
+      if(off_gravpm >= 0)
+	G2_CUDA(cudaMemcpyAsync(c->in_gravpm + 3 * (size_t) lo, hgpm, n * 12, cudaMemcpyHostToDevice, st));
+    }
   G2_CUDA(cudaEventRecord(c->ev[10], st));
   c->h2d_bytes = n * (sizeof(G2PRec) + (off_vel >= 0 ? 12 : 0) + (off_gravpm >= 0 ? 12 : 0));
   c->have_vel = off_vel >= 0;
   c->have_gravpm = off_gravpm >= 0;
   c->pm_done = 0;
-  c->npart = npart;
+  c->npart = n_total;
   c->stage = 1;
   return 0;
+}
+
+extern "C" int g2gpu_upload_aos(g2gpu_ctx *c, int npart, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
+				int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current)
+{
+  if(!c || !P)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_upload_aos_shard(c, npart, 0, npart, P, stride, float_bytes, off_pos, off_mass, off_type, off_oldacc, off_vel, off_gravpm, off_ti_endstep,
+			     ti_current, 16u);
 }
 
 extern "C" int g2gpu_input_buffers(g2gpu_ctx *c, int npart, void **records)
@@ -545,23 +584,29 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     c->accumulator = value != 0;	// takes effect at the next g2gpu_treebuild
   else if(strcmp(name, "direct_ewald") == 0)
     c->direct_ewald = value != 0;
-  else if(strcmp(name, "walk_mode") == 0)
+  else if(strcmp(name, "walk_stats") == 0)
+    c->walk_stats = value != 0;
+  else if(strcmp(name, "walk_exact") == 0)
+    c->walk_exact = value != 0;
+  else if(strcmp(name, "compact") == 0)
     {
-      if(value != 0 && value != 1)
-	return g2_fail(G2GPU_ERR_ARG, "walk_mode must be 0 (cursor per 32 targets) or 1 (warp per target)");
-      c->walk_mode = value;
-      c->bfs_valid = 0;
-    }
-  else if(strcmp(name, "walk_group") == 0)
-    {
-      if(value != 8 && value != 32)
-	return g2_fail(G2GPU_ERR_ARG, "walk_group must be 8 or 32");
-      c->walk_group = value;
+      if(value && !c->cres)
+	{
+	  G2_CUDA(cudaSetDevice(c->cfg.device));
+	  G2_TRY(dalloc(&c->cres, 5 * (size_t) c->cfg.max_part));
+	}
+      c->compact = value != 0;
     }
   else if(strcmp(name, "rank") == 0)
-    c->cfg.rank = value;
+    {
+      c->cfg.rank = value;
+      c->slice_explicit = 0;
+    }
   else if(strcmp(name, "nranks") == 0)
-    c->cfg.nranks = value < 1 ? 1 : value;
+    {
+      c->cfg.nranks = value < 1 ? 1 : value;
+      c->slice_explicit = 0;
+    }
   else
     return g2_fail(G2GPU_ERR_ARG, "unknown option %s", name);
   return 0;
@@ -841,6 +886,7 @@ extern "C" int g2gpu_slice(g2gpu_ctx *c, int *lo, int *hi)
 {
   if(!c)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_TRY(g2_fetch_slice(c));
   if(lo)
     *lo = c->w_lo;
   if(hi)
@@ -889,6 +935,7 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[8])
 	  counters[2] = (long long) c->h_counters[1];
 	  counters[3] = (long long) c->h_counters[2];
 	  counters[4] = (long long) c->h_counters[4];
+	  counters[5] = (long long) c->h_counters[5];	// targets re-walked in FP64 (borderline decisions)
 	}
     }
   return 0;

@@ -1271,6 +1271,15 @@ int g2_stage_treebuild(g2gpu_ctx *c)
     return g2_fail(G2GPU_ERR_TOPNODES, "top-level tree exceeds %d nodes", G2_MAXTOP);
   if(c->h_err[0])
     return g2_fail(G2GPU_ERR_TREE_DEPTH, "more than 8 particles share all %d octree levels (coincident particles?)", G2_MAXDEPTH);
+  {				// largest |coordinate| of the domain cube (guard bands of the walk's FP32 decisions)
+    double m = 0;
+    for(int j = 0; j < 3; j++)
+      {
+	m = fmax(m, fabs(c->h_domain[j]));
+	m = fmax(m, fabs(c->h_domain[j] + c->h_domain[6]));
+      }
+    c->coord_max = m;
+  }
   c->ncells = c->h_err[4];
   const int ntop = c->h_err[5];
   c->numnodes = ntop + c->ncells;
@@ -1331,138 +1340,15 @@ int g2_stage_treebuild(g2gpu_ctx *c)
 	}
       c->launches++;
     }
-  c->bfs_valid = 0;
   c->stage = 3;
   c->tree_npart = n;
-  if(c->walk_mode == 1 && !c->accumulator && c->walk_group == 32)
-    G2_TRY(g2_stage_bfs(c));	// part of the build time
+  c->tree_dynamic = 0;
   G2_CUDA(cudaEventRecord(c->ev[5], st));
   G2_CUDA(cudaGetLastError());
   c->renumbered = 0;
   c->counts_valid = 0;
   if(c->accumulator)
     G2_TRY(g2_stage_counts(c));
-  return 0;
-}
-
-// ---------------------------------------------------------------- level-order walk records (g2_walkb.cu) ----------
-// The warp-per-target walk wants the child cells of a cell next to each other.  Cells of one depth, taken in depth-first
-// order (index U), have exactly that property (a subtree is a contiguous U range), so the level-order index V is the rank
-// of (depth, U): one stable radix pass on the depth.  Records are split into arrays (structure of arrays) so that 32
-// lanes reading 32 consecutive cells touch 512 contiguous bytes per load.
-__global__ void __launch_bounds__(256) bfs_key_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, int ncells, unsigned long long *__restrict__ key,
-						       unsigned int *__restrict__ val)
-{
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int U, d;
-  if(tid < ncells)
-    {
-      U = (unsigned int) tid + (unsigned int) tt->fdfs[A.tl[A.c_a[tid]]] + 1u;
-      d = A.c_d[tid];
-    }
-  else if(tid - ncells < tt->ntopnodes)
-    {
-      const int k = tid - ncells;
-      U = A.t_u[k];
-      d = (unsigned int) tt->fdepth[k];
-    }
-  else
-    return;
-  key[U] = d;
-  val[U] = U;
-}
-
-__global__ void __launch_bounds__(256) bfs_inverse_kernel(const unsigned int *__restrict__ order, int nn, unsigned int *__restrict__ vofu)
-{
-  int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if(v < nn)
-    vofu[order[v]] = (unsigned int) v;
-}
-
-template <int D>
-__global__ void __launch_bounds__(256) bfs_export_kernel(BuildArrays A, const G2TopTree *__restrict__ tt, int ncells, unsigned int nn,
-							  const unsigned int *__restrict__ vofu, float4 *__restrict__ bq0, float4 *__restrict__ bs,
-							  uint4 *__restrict__ bw, unsigned char *__restrict__ bptype)
-{
-  int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned int U, nchild;
-  if(tid < ncells)
-    {
-      U = (unsigned int) tid + (unsigned int) tt->fdfs[A.tl[A.c_a[tid]]] + 1u;
-      nchild = A.c_nchild[tid];
-    }
-  else if(tid - ncells < tt->ntopnodes)
-    {
-      const int k = tid - ncells;
-      U = A.t_u[k];
-      if(tt->fisleaf[k])
-	nchild = A.t_nchild[k];
-      else
-	{
-	  nchild = 0;
-	  for(int s = 0; s < 8; s++)
-	    nchild += tt->fsuns[k][s] >= 0;
-	}
-    }
-  else
-    return;
-  const unsigned int V = vofu[U];
-  const float4 *rec = A.wcells + (size_t) U * (2 + D);
-  bq0[V] = rec[0];
-#pragma unroll
-  for(int g = 0; g < D; g++)
-    bs[(size_t) g * nn + V] = rec[1 + g];
-  const uint4 w = *((const uint4 *) &rec[1 + D]);
-  const unsigned int np = w.z & 15u;
-  for(unsigned int j = 0; j < np; j++)
-    bptype[w.y + j] = (unsigned char) ((w.z >> (4 + 3 * j)) & 7u);
-  // the first child cell follows its parent in depth-first order
-  const unsigned int first = nchild ? vofu[U + 1] : 0u;
-  bw[V] = make_uint4(first | (nchild << 28), w.y | (np << 28), w.z, w.w);
-}
-
-int g2_stage_bfs(g2gpu_ctx *c)
-{
-  if(c->stage < 3)
-    return g2_fail(G2GPU_ERR_STATE, "level-order records: tree has not been built");
-  const size_t np = (size_t) c->cfg.max_part, cap = (size_t) c->cfg.max_nodes + G2_MAXTOP + 8;
-  const int nn = c->numnodes, ncells = c->ncells, ntop = nn - ncells;
-  if((size_t) nn > np || cap >= (1u << 28) || np >= (1u << 28))
-    return 0;			// outside the packed index range or the sort scratch: the walk stays on the cursor kernel
-  cudaStream_t st = c->stream;
-  if(!c->b_q0)
-    {
-      int rc = 0;
-      rc |= cudaMalloc((void **) &c->b_q0, sizeof(float4) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_s, sizeof(float4) * cap * c->D) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_w, sizeof(uint4) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_ptype, np + 16) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_key[0], sizeof(unsigned long long) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_key[1], sizeof(unsigned long long) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_val[0], sizeof(unsigned int) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_val[1], sizeof(unsigned int) * cap) != cudaSuccess;
-      rc |= cudaMalloc((void **) &c->b_vofu, sizeof(unsigned int) * cap) != cudaSuccess;
-      if(rc)
-	return g2_fail(G2GPU_ERR_NOMEM, "device allocation of the level-order walk records failed");
-    }
-  BuildArrays A = make_arrays(c);
-  const int total = ncells + ntop;
-  bfs_key_kernel<<<g2_cdiv(total, 256), 256, 0, st>>>(A, c->d_top, ncells, c->b_key[0], c->b_val[0]);
-  c->launches++;
-  unsigned long long *k = c->b_key[0];
-  unsigned int *v = c->b_val[0];
-  G2_TRY(g2_radix_sort_pairs(c, nn, &k, &v, c->b_key[1], c->b_val[1], 0, 5));
-  bfs_inverse_kernel<<<g2_cdiv(nn, 256), 256, 0, st>>>(v, nn, c->b_vofu);
-  switch (c->D)
-    {
-#define G2_B(Dv) case Dv: bfs_export_kernel<Dv><<<g2_cdiv(total, 256), 256, 0, st>>>(A, c->d_top, ncells, (unsigned int) nn, c->b_vofu, c->b_q0, c->b_s, c->b_w, c->b_ptype); break
-      G2_B(1); G2_B(2); G2_B(3); G2_B(4); G2_B(5); G2_B(6);
-#undef G2_B
-    default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", c->D);
-    }
-  c->launches += 2;
-  G2_CUDA(cudaGetLastError());
-  c->bfs_valid = 1;
   return 0;
 }
 
@@ -1556,7 +1442,7 @@ int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s)
   c->launches += 3;
   G2_CUDA(cudaGetLastError());
   G2_CUDA(cudaStreamSynchronize(st));	// h_export may be reused by the caller's next export
-  c->bfs_valid = 0;
+  c->tree_dynamic = 1;
   c->counts_valid = c->accumulator ? c->counts_valid : 0;
   return 0;
 }

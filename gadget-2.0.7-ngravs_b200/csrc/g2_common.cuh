@@ -14,7 +14,7 @@
 #define G2_DEFAULT_WALK_MODE 0
 #endif
 
-extern char g2_errbuf[512];
+extern __thread char g2_errbuf[512];	// per host thread: the group path (g2_group.cu) drives one context per thread
 int g2_fail(int code, const char *fmt, ...);
 
 #define G2_CUDA(call)                                                                                   \
@@ -117,15 +117,14 @@ struct g2gpu_ctx
   int accumulator;		// NGRAVS_ACCUMULATOR: nodes carry the particle count per species (wcnt), laws receive it as N
   int counts_valid;		// wcnt belongs to the current tree
   unsigned int *wcnt;		// [U][D], filled by g2_stage_counts after the build when accumulator != 0
-  int walk_group;		// targets per walk cursor: 32 (whole warp), 16, 8 or 4
   int direct_ewald;		// g2gpu_direct adds the exact lattice correction of a periodic box (option "direct_ewald")
-  int walk_mode;		// 0: one cursor per 32 targets (g2_walk.cu); 1: one warp per target over level-order records (g2_walkb.cu)
-  int bfs_valid;		// the level-order records belong to the current tree
-  float4 *b_q0, *b_s;		// level-order SoA walk records (allocated on first use)
-  uint4 *b_w;
-  unsigned char *b_ptype;
-  unsigned long long *b_key[2];
-  unsigned int *b_val[2], *b_vofu;
+  int walk_stats;		// option "walk_stats": the instrumented walk kernel (visits, species terms, decisions in counters[2..4])
+  int walk_exact;		// option "walk_exact" (default 1): borderline decisions are re-taken in FP64 (exact GravCost)
+  int compact;			// option "compact": the walk writes its slice's results in target order (cres) instead of by particle index
+  float *cres;			// 5 floats per target of the slice (acc[3], cost, oldacc), allocated with the option
+  int slice_explicit;		// slice_frac[] instead of rank/nranks (cost-weighted slices of the group path)
+  double slice_frac[2];
+  int tree_dynamic;		// the current tree came from g2gpu_update_tree (host-drifted nodes)
 
   // upload-order inputs
   G2PRec *in_rec;		// may point at caller-bound device memory (g2gpu_bind_inputs)
@@ -147,6 +146,9 @@ struct g2gpu_ctx
   float *gravpm;
   long long *phkey;
   int *perm;
+  unsigned int *phorder;	// particle index (current order) by rank along the Peano-Hilbert curve of ALL species
+  double *h_domain;		// pinned copy of d_domain (valid after the build's host synchronisation)
+  double coord_max;		// largest |coordinate| of the domain cube
 
   // sort scratch (ping-pong)
   unsigned long long *skey[2];
@@ -211,7 +213,10 @@ struct g2gpu_ctx
   unsigned int *w_targets;	// sorted positions of active targets (compacted)
   unsigned int *w_flags;	// scratch for compaction
   int w_ntargets;		// total active (all ranks)
-  int w_lo, w_hi;		// this rank's slice of w_targets
+  int w_lo, w_hi;		// this rank's slice of w_targets (host copies, valid after g2_fetch_slice)
+  int *d_slice, *h_slice;	// [G2_SLICE_*] on the device / pinned
+  void *d_exact;		// WalkExactParams of the current walk
+  int slice_pending;
   float *acc;			// 3n, current particle order
   float *cost;			// n
   float *oldacc_out;		// n
@@ -233,7 +238,15 @@ struct g2gpu_ctx
 // ---- cross-file entry points ----
 int g2_scan_exclusive_u32(g2gpu_ctx *c, const unsigned int *in, unsigned int *out, size_t n);
 int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io,
-			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit);
+			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit,
+			int capture_shift = -1, unsigned int *capture_dest = nullptr);
+int g2_ensure_optional_inputs(g2gpu_ctx *c, int want_vel, int want_gravpm);
+int g2_upload_soa_shard(g2gpu_ctx *c, int n_total, int lo, int cnt, const float *pos, const float *mass, const int *type, const float *oldacc,
+			const int *active);
+int g2_upload_aos_shard(g2gpu_ctx *c, int n_total, int lo, int cnt, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass,
+			int off_type, int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current, unsigned int max_threads);
+int g2_stage_targets(g2gpu_ctx *c, const g2gpu_walk_params *wp);
+int g2_fetch_slice(g2gpu_ctx *c);
 int g2_stage_domain(g2gpu_ctx *c);
 int g2_stage_treebuild(g2gpu_ctx *c);
 int g2_stage_renumber(g2gpu_ctx *c);
@@ -242,7 +255,6 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_make_ewald_table(g2gpu_ctx *c, int en, double *out);
 int g2_stage_counts(g2gpu_ctx *c);
-int g2_stage_bfs(g2gpu_ctx *c);
 int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);
 int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp);
 int g2_pm_download(g2gpu_ctx *c, float *gravpm);

@@ -585,7 +585,12 @@ int g2_stage_domain(g2gpu_ctx *c)
   unsigned long long *k = c->skey[0];
   unsigned int *v = c->sval[0];
   G2_CUDA(cudaEventRecord(c->ev[1], st));
-  G2_TRY(g2_radix_sort_pairs(c, n, &k, &v, c->skey[1], c->sval[1], 0, 3 * G2_PH_BITS + blockbits));
+  // the last pass (the block bits, starting at bit 54 = 6 x 9) finds the pairs in Peano-Hilbert order of ALL species and records where
+  // each goes: phorder[j] = index in the final (species-major) order of the particle with PH rank j -- the walk's target order
+  if(n > 1)
+    G2_TRY(g2_radix_sort_pairs(c, n, &k, &v, c->skey[1], c->sval[1], 0, 3 * G2_PH_BITS + blockbits, 3 * G2_PH_BITS, c->phorder));
+  else
+    G2_CUDA(cudaMemsetAsync(c->phorder, 0, sizeof(unsigned int), st));
   G2_CUDA(cudaEventRecord(c->ev[2], st));
 
   gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(n, k, v, c->in_rec, c->have_vel ? c->in_vel : nullptr, c->have_gravpm ? c->in_gravpm : nullptr,
@@ -596,6 +601,7 @@ int g2_stage_domain(g2gpu_ctx *c)
   G2_CUDA(cudaFuncSetAttribute(toptree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_DYN_SMEM));
   toptree_kernel<<<1, TT_THREADS, TT_DYN_SMEM, st>>>(c->phkey, c->d_species_start, nblocks, n, c->d_domain, c->d_top, (G2TopScratch *) c->d_topscratch);
   c->launches += 3;
+  G2_CUDA(cudaMemcpyAsync(c->h_domain, c->d_domain, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));	// read after the build's host synchronisation
   G2_CUDA(cudaEventRecord(c->ev[3], st));
   G2_CUDA(cudaGetLastError());
   c->stage = 2;

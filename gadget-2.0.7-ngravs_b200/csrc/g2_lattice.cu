@@ -21,14 +21,14 @@ struct LatticeArgs
 {
   const float4 *__restrict__ cells;
   const float4 *__restrict__ wpart;
-  const unsigned int *__restrict__ targets;
-  const unsigned int *__restrict__ tq;
+  const unsigned int *__restrict__ targets;	// particle index of every active target, merged Peano-Hilbert order
+  const int *__restrict__ slice;
   const G2PRec *__restrict__ prec;
   const float4 *__restrict__ tables;	// unique tables, (EN+1)^3 float4 (fx, fy, fz, 0) each, already divided by BoxSize^2
   float *__restrict__ latt;		// 3n, current particle order
   float *__restrict__ lattcost;	// n
   unsigned int *__restrict__ work_counter;
-  int lo, hi, numnodes, en;
+  int numnodes, en;
   float theta2, errtol, boxsize, boxinv, fac_intp;
   int t2g[6];
   unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kerne
   __shared__ unsigned int s_chunk[WALK_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int R = 2 + D;
-  const int nchunks = (A.hi - A.lo + 31) >> 5;
+  const int lo = A.slice[G2_SLICE_LO], hi = A.slice[G2_SLICE_HI];
+  const int nchunks = (hi - lo + 31) >> 5;
   const unsigned int end = (unsigned int) A.numnodes;
 
   while(true)
@@ -74,14 +75,14 @@ __global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kerne
       __syncwarp();
       if(chunk >= (unsigned int) nchunks)
 	break;
-      const int ti = A.lo + (int) chunk * 32 + lane;
-      const bool valid = ti < A.hi;
+      const int ti = lo + (int) chunk * 32 + lane;
+      const bool valid = ti < hi;
       unsigned int idx = 0;
       float px = 0, py = 0, pz = 0, aold = 0;
       int ptype = 1;
       if(valid)
 	{
-	  idx = A.tq[A.targets[ti]];
+	  idx = A.targets[ti];
 	  const G2PRec p = A.prec[idx];
 	  px = p.x; py = p.y; pz = p.z;
 	  ptype = p.type;
@@ -181,10 +182,10 @@ int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp)
     }
   LatticeArgs A;
   memset(&A, 0, sizeof(A));
-  A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.tq = c->tq; A.prec = c->prec;
+  A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.slice = c->d_slice; A.prec = c->prec;
   A.tables = (const float4 *) c->d_lattice; A.latt = c->latt; A.lattcost = c->lattcost;
   A.work_counter = (unsigned int *) (c->d_counters + 5);
-  A.lo = c->w_lo; A.hi = c->w_hi; A.numnodes = c->numnodes; A.en = c->lattice_en;
+  A.numnodes = c->numnodes; A.en = c->lattice_en;
   A.theta2 = (float) (wp->theta * wp->theta);
   A.errtol = (float) wp->errtol_force_acc;
   A.boxsize = (float) wp->boxsize; A.boxinv = (float) (1.0 / wp->boxsize);
@@ -192,7 +193,7 @@ int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   for(int t = 0; t < 6; t++)
     A.t2g[t] = c->type_to_grav[t];
   memcpy(A.tabmap, c->lattice_tabmap, sizeof(A.tabmap));
-  int grid = c->nsm * LATTICE_MINBLOCKS, need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
+  int grid = c->nsm * LATTICE_MINBLOCKS, need = g2_cdiv(g2_cdiv(c->npart, 32), WALK_WARPS);	// the target count stays on the device
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));

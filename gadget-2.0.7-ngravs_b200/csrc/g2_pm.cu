@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) pm_deposit_kernel(PMArgs A, double *__res
   if(i >= A.n)
     return;
   const G2PRec p = A.rec[i];
-  double *__restrict__ rho = rho_all + (size_t) ((A.t2g_packed >> (4 * p.type)) & 7u) * A.N * A.N * A.N;
+  double *__restrict__ rho = rho_all + (size_t) ((A.t2g_packed >> (4 * min(max(p.type, 0), 5))) & 7u) * A.N * A.N * A.N;
   int sx, sy, sz;
   double dx, dy, dz;
   pm_cell(A, p.x, sx, dx);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) pm_gather_kernel(PMArgs A, const double *
     return;
   const G2PRec p = A.rec[i];
   const int N = A.N;
-  const double *__restrict__ phi = phi_all + (size_t) ((A.t2g_packed >> (4 * p.type)) & 7u) * N * N * N;
+  const double *__restrict__ phi = phi_all + (size_t) ((A.t2g_packed >> (4 * min(max(p.type, 0), 5))) & 7u) * N * N * N;
   int s[3];
   double d[3];
   pm_cell(A, p.x, s[0], d[0]);
@@ -246,8 +246,9 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
     if(pp->greens_id[i] < G2GPU_GREENS_NONE || pp->greens_id[i] > G2GPU_GREENS_COLOYUK)
       return g2_fail(G2GPU_ERR_LAW, "PM: unknown k-space Green's function id %d for pair %d", pp->greens_id[i], i);
   G2_TRY(pm_reserve(c, N));
-  if(!c->in_gravpm)
-    G2_CUDA(cudaMalloc((void **) &c->in_gravpm, sizeof(float) * 3 * (size_t) c->cfg.max_part));
+  // the result becomes the GravPM input of the next domain stage / dynamic update: both the upload-order and the current-order array
+  // must exist (gather_kernel and dyn_particles_kernel write the latter)
+  G2_TRY(g2_ensure_optional_inputs(c, 0, 1));
   cudaStream_t st = c->stream;
   G2_CUDA(cudaEventRecord(c->ev[13], st));
 

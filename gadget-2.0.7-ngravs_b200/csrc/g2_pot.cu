@@ -31,7 +31,7 @@ struct PotArgs
 {
   const float4 *__restrict__ cells;
   const float4 *__restrict__ wpart;
-  const unsigned int *__restrict__ tq;
+  const unsigned int *__restrict__ order;	// particle index by rank along the Peano-Hilbert curve of all species (the walk's target order)
   const G2PRec *__restrict__ prec;
   const float *__restrict__ pottable;	// unique tables, NTAB floats each
   float *__restrict__ pot;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
       int ptype = 1;
       if(valid)
 	{
-	  idx = A.tq[ti];
+	  idx = A.order[ti];
 	  const G2PRec p = A.prec[idx];
 	  px = p.x; py = p.y; pz = p.z;
 	  ptype = p.type;
@@ -307,9 +307,13 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   PotArgs A;
   memset(&A, 0, sizeof(A));
   const int nr = c->cfg.nranks > 0 ? c->cfg.nranks : 1, rk = c->cfg.rank;
-  A.cells = c->wcells; A.wpart = c->wpart; A.tq = c->tq; A.prec = c->prec; A.pottable = c->d_pottable_f; A.pot = c->pot;
+  A.cells = c->wcells; A.wpart = c->wpart; A.order = c->phorder; A.prec = c->prec; A.pottable = c->d_pottable_f; A.pot = c->pot;
   A.work_counter = (unsigned int *) (c->d_counters + 5);
-  A.lo = (int) ((long long) n * rk / nr); A.hi = (int) ((long long) n * (rk + 1) / nr);
+  // slice boundaries at multiples of 32: the 32-target groups, and with them the result bits, do not depend on the number of ranks
+  A.lo = (int) (((long long) n * rk / nr + 16) / 32 * 32); A.hi = rk == nr - 1 ? n : (int) (((long long) n * (rk + 1) / nr + 16) / 32 * 32);
+  if(A.lo > n) A.lo = n;
+  if(A.hi > n) A.hi = n;
+  if(A.hi < A.lo) A.hi = A.lo;
   A.numnodes = c->numnodes; A.ntab = c->cfg.ntab; A.ntables = c->pot_ntables;
   A.node_table_term = (c->accumulator != 0);
   A.theta2 = (float) (wp->theta * wp->theta);

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_hist_kernel(const unsigned 
 #define SCATTER_SMEM (SORT_WARPS * RADIX_BINS * 4 + 2 * RADIX_BINS * 4 + 64 * 4 + SORT_TILE * 8 + SORT_TILE * 4)
 __global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
 								     unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
-								     const unsigned int *__restrict__ tilescan, int n, int ntiles, int shift, unsigned int mask)
+								     const unsigned int *__restrict__ tilescan, int n, int ntiles, int shift, unsigned int mask,
+									     unsigned int *__restrict__ capture_dest)
 {
   extern __shared__ unsigned long long sort_dyn[];
   unsigned long long *stage_k = sort_dyn;				// SORT_TILE keys
@@ -267,6 +268,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const uns
 	  unsigned int pos = binstart[d] + wcnt[warp][d] + r[i];
 	  stage_k[pos] = k[i];
 	  stage_v[pos] = vals_in[idx];
+	  if(capture_dest)		// where the element at input position idx of THIS pass ends up (coalesced: consecutive lanes, consecutive idx)
+	    capture_dest[idx] = gdelta[d] + pos;
 	}
     }
   __syncthreads();
@@ -282,8 +285,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const uns
 
 // Sorts n pairs by key bits [begin_bit, end_bit), stable.  *keys_io/*vals_io hold the input and are
 // updated to point at the buffers holding the result (ping-pong with keys_alt/vals_alt).
+// capture_shift >= 0: the pass that starts at that bit also writes capture_dest[i] = output position of its i-th input element.  An LSD
+// sort is sorted by the bits below `shift` when that pass starts, so with the pass being the last one capture_dest lists, in the order
+// of the low bits alone, where every element finally went (g2_domain.cu: Peano-Hilbert order of all species -> species-major order).
 int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io,
-			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit)
+			unsigned long long *keys_alt, unsigned int *vals_alt, int begin_bit, int end_bit, int capture_shift, unsigned int *capture_dest)
 {
   if(n <= 1 || end_bit <= begin_bit)
     return 0;
@@ -303,7 +309,8 @@ int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsig
       sort_hist_kernel<<<ntiles, SORT_THREADS, 0, c->stream>>>(kin, c->tilehist, n, ntiles, shift, mask);
       c->launches++;
       G2_TRY(g2_scan_exclusive_u32(c, c->tilehist, c->tilehist, (size_t) ntiles * RADIX_BINS));
-      sort_scatter_kernel<<<ntiles, SORT_THREADS, SCATTER_SMEM, c->stream>>>(kin, vin, kout, vout, c->tilehist, n, ntiles, shift, mask);
+      sort_scatter_kernel<<<ntiles, SORT_THREADS, SCATTER_SMEM, c->stream>>>(kin, vin, kout, vout, c->tilehist, n, ntiles, shift, mask,
+									      shift == capture_shift ? capture_dest : nullptr);
       c->launches++;
       unsigned long long *tk = kin; kin = kout; kout = tk;
       unsigned int *tv = vin; vin = vout; vout = tv;

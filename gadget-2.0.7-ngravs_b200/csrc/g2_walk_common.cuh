@@ -1,5 +1,5 @@
-// g2_walk_common.cuh — what the two walk kernels (g2_walk.cu: one cursor per 32 targets; g2_walkb.cu: one warp per target)
-// share: kernel arguments, the periodic wrap, and one species term of an interaction.
+// g2_walk_common.cuh — what the walk kernel (g2_walk_kernel.cuh) and its driver (g2_walk.cu) share: kernel arguments, the periodic
+// wrap, and one species term of an interaction.
 #pragma once
 #include "g2_common.cuh"
 #include "g2_laws.cuh"
@@ -17,24 +17,38 @@
 #define WALK_MINBLOCKS_WIDE 8
 #endif
 
+// slice[] (device memory, written by slice_kernel before the walk): the walk never needs a host round trip for the target count
+#define G2_SLICE_NTARGETS 0
+#define G2_SLICE_LO 1
+#define G2_SLICE_HI 2
+
+// what the FP64 re-evaluation of a borderline decision needs (walk_decide_exact): kept in device memory, so that the rarely called
+// non-inlined functions take one pointer instead of a copy of the kernel arguments
+struct WalkExactParams
+{
+  double boxsize, rcut, rcut2, theta, errtol, asmthfac;
+  double fsoft[6];
+  int ntab;
+};
+
 struct WalkArgs
 {
   const float4 *__restrict__ cells;
   const float4 *__restrict__ wpart;
-  const unsigned int *__restrict__ targets;	// sorted positions of active targets
-  const unsigned int *__restrict__ tq;		// particle index of a sorted position
+  const unsigned int *__restrict__ targets;	// particle index (current order) of every active target, in merged Peano-Hilbert order
+  const int *__restrict__ slice;		// [G2_SLICE_*]: number of targets, this rank's [lo, hi)
   const G2PRec *__restrict__ prec;
   const float *__restrict__ gravpm;
   const unsigned int *__restrict__ cnt;	// particle counts per species of every cell [U][D] (NGRAVS_ACCUMULATOR), or null
   const float *__restrict__ srtable;		// unique tables, NTAB floats each
   const float *__restrict__ latt;		// lattice-sum correction of every target (periodic box without PM, g2_lattice.cu), or null
   const float *__restrict__ lattcost;
-  float *__restrict__ acc;
+  float *__restrict__ acc;			// results by particle index (current order) ...
   float *__restrict__ cost;
   float *__restrict__ oldacc_out;
+  float *__restrict__ cres;			// ... or, when not null, compact: 5 floats (acc[3], cost, oldacc) per target of the slice, target order
   unsigned long long *__restrict__ counters;
   unsigned int *__restrict__ work_counter;
-  int lo, hi;			// slice of targets
   int numnodes;
   int ntab;
   int ntables;			// unique short-range tables held in shared memory
@@ -42,20 +56,23 @@ struct WalkArgs
   float errtol;			// ErrTolForceAcc
   float boxsize, boxinv;
   float rcut, rcut2, asmthfac, utor2wpi;
-  float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions)
+  float rmax2;			// (NTAB / asmthfac)^2: a term counts while r^2 is below it (tabindex < NTAB, forcetree.c:1962-1967)
+  float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions); +inf disables the shortcut
   float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
+  // guard bands: a comparison whose two sides are closer than this is re-taken in FP64, the arithmetic the reference decides in
+  float pos_border;		// absolute, for differences of coordinates (box cull, 0.6 len test)
+  float rcut2_border, rmax2_border;	// absolute, around rcut^2 and rmax2
+  float rel_tol, pos_ulp8;	// relative tolerance of r^2-based criteria: rel_tol + pos_ulp8 / r
   double G, pos_fac_pre_g, pos_fac_post_g;
+  const WalkExactParams *__restrict__ ex;
+  unsigned int *__restrict__ redo_list;	// slice ordinals of the targets that met a borderline comparison (one slot per target of the slice)
+  unsigned int *__restrict__ redo_count;
   int use_gravpm;
+  int exact;			// 0: no FP64 re-evaluation (FP32 decisions only)
   float fsoft[6];
   int t2g[6];
   unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// [tgt*D+src] -> unique table
   G2LawTable laws;
-  // level-order (children of a cell are contiguous) structure-of-arrays copy of the walk records, for g2_walkb.cu
-  const float4 *__restrict__ bq0;	// [V] len, centre
-  const float4 *__restrict__ bs;	// [g * bstride + V] centre of mass and mass of species g
-  const uint4 *__restrict__ bw;		// [V] first child V | #child cells << 28,  particle offset | #particles << 28,  pinfo,  hmax
-  const unsigned char *__restrict__ bptype;	// particle type of every record of wpart
-  unsigned int bstride;
 };
 
 // NEAREST(x) (forcetree.c:43): x > L/2 -> x - L, x < -L/2 -> x + L.  For |x| < 1.5 L this equals x - L*rint(x/L)
@@ -74,6 +91,13 @@ __device__ __forceinline__ float nearest(float x, float boxsize, float boxinv)
   return x;
 }
 
+// NEAREST() as the reference evaluates it, in double
+__device__ __forceinline__ double nearest_dd(double x, double box)
+{
+  const double half = 0.5 * box;
+  return x > half ? x - box : (x < -half ? x + box : x);
+}
+
 __device__ __forceinline__ float fast_rsqrt(float x)
 {
   float y;
@@ -88,25 +112,25 @@ __device__ __forceinline__ float lds_f32(unsigned int saddr)
   return v;
 }
 
-// one species term of an interaction: adds d*fac to the lane's FP32 partial sums; returns whether it counted
-// (mass != 0 and, for TreePM, r inside the short-range table: forcetree.c:1553-1582, 1958-2026).
-// Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the rare r < h case.
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// one species term of an interaction: adds d*fac to the lane's FP32 partial sums.  `inrange` = the term lies inside the short-range
+// table (tabindex < NTAB, forcetree.c:1962-1967), decided by the caller; `m != 0` is checked by the caller for node terms
+// (forcetree.c:1553, 1992).  Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the
+// rare r < h case.
 template <bool SR, bool STOCK>
-__device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
-					  float pmass, float m, float dx, float dy, float dz, float r2, float h, float &fx, float &fy, float &fz,
+__device__ __forceinline__ void pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
+					  float pmass, float m, float dx, float dy, float dz, float r2, float h, bool counted, float &fx, float &fy, float &fz,
 					  float nn = 1.0f)	// N of forcetree.c:1563-1577 (only the non-stock laws read it)
 {
   const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   const float r = r2 * rinv;
   if(STOCK)
     {
-      bool counted = m != 0.0f;
       float fac;
       if(SR)
 	{
-	  int tabindex = (int) (A.asmthfac * r);	// forcetree.c:1962
-	  counted = counted && tabindex < A.ntab;
-	  tabindex = min(tabindex, A.ntab - 1);
+	  const int tabindex = min((int) (A.asmthfac * r), A.ntab - 1);	// forcetree.c:1962
 	  const float t = lds_f32(s_tab_addr + 4u * (unsigned int) tabindex);
 	  // (m/r^2 - m*utor2wpi*tab) / r   (forcetree.c:1972-1974)
 	  fac = m * rinv * fmaf(-A.utor2wpi, t, rinv * rinv);
@@ -119,19 +143,16 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
       fx = fmaf(dx, fac, fx);
       fy = fmaf(dy, fac, fy);
       fz = fmaf(dz, fac, fz);
-      return counted;
     }
   else
     {
-      if(m == 0.0f)
-	return false;
+      if(!counted)
+	return;
       float fac;
       const int ij = tg * D + sg;
       if(SR)
 	{
-	  int tabindex = (int) (A.asmthfac * r);
-	  if(tabindex >= A.ntab)
-	    return false;
+	  const int tabindex = min((int) (A.asmthfac * r), A.ntab - 1);
 	  if(r >= h)
 	    {
 	      float a = accel_over_r(A.laws.accel[ij], A.laws.par[ij], pmass, m, r2, r, rinv, nn) * r;
@@ -151,9 +172,14 @@ __device__ __forceinline__ bool pair_term(const WalkArgs &A, const float *__rest
       fx = fmaf(dx, fac, fx);
       fy = fmaf(dy, fac, fy);
       fz = fmaf(dz, fac, fz);
-      return true;
     }
 }
 
-// g2_walkb.cu
-int g2_launch_walkb(g2gpu_ctx *c, const WalkArgs &A, bool sr, bool periodic, bool unequal, bool stock);
+// per-D launchers (g2_walk_dN.cu, one translation unit per N_GRAVS so that they compile in parallel)
+int g2_launch_walk_d1(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+int g2_launch_walk_d2(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+int g2_launch_walk_d3(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+int g2_launch_walk_d4(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+int g2_launch_walk_d5(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+int g2_launch_walk_d6(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats);
+

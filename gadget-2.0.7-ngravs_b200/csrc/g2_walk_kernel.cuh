@@ -1,0 +1,709 @@
+// g2_walk_kernel.cuh — the tree walk of force_treeevaluate (forcetree.c:1244-1610) and force_treeevaluate_shortrange
+// (forcetree.c:1623-2052), with the gravity_tree epilogue (gravtree.c:304-358).  Included by g2_walk_dN.cu (one per N_GRAVS).
+//
+// One warp takes 32 targets that are adjacent along the Peano-Hilbert curve of ALL species (hence compact in space: 10 % fewer
+// cell visits than 32 neighbours in depth-first tree order) and walks the depth-first
+// cell array once for all of them: at every cell each lane takes ITS OWN decision (cull / accept / open) with the reference's
+// criteria; the warp descends if any lane opens (ballot), otherwise jumps to the cell's sibling.  A lane that accepted or culled a
+// cell sleeps until the warp's cursor has left that cell's subtree (cells are in depth-first order, so this is one integer
+// compare).  Direct particle children of an opened cell sit in a contiguous group and are applied by the opening lanes only.
+// Per-lane interaction lists are therefore those of the reference walk; only the summation order differs.
+//
+// Decisions are taken in FP32.  The reference decides in double (forcetree.c:1628-1631), so a target that meets a comparison whose
+// two sides are closer than the FP32 rounding of their inputs allows (guard bands in WalkArgs) is flagged, and walk_redo_kernel walks
+// the tree again for the flagged targets (a fraction of a per cent) in the reference's own double arithmetic, operation by
+// operation: every target's interaction list, and with it GravCost, is then the reference's exactly.  Keeping the FP64 path out of
+// this kernel keeps its 64 registers free of spills.
+//
+// Node records are (2+D) x 16 B, fetched with 128-bit loads (all lanes read the same address: one L1 broadcast).
+#pragma once
+#include "g2_walk_common.cuh"
+
+#define G2_DEC_CULL 0
+#define G2_DEC_ACCEPT 1
+#define G2_DEC_OPEN 2
+
+// ---- the reference's decision on one node for one target, in its own arithmetic (double locals, FLOAT node fields):
+//      forcetree.c:1790-1926 (TreePM) and 1355-1501 (tree only).  Rare path: called for borderline comparisons only. ----
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL>
+__device__ __forceinline__ int walk_decide_exact(const WalkExactParams *__restrict__ E, const float4 *__restrict__ rec, const G2PRec *__restrict__ target)
+{
+  const G2PRec tp = *target;
+  const float oldacc = tp.oldacc;
+  const int ptype = tp.type;
+  const double px = (double) tp.x, py = (double) tp.y, pz = (double) tp.z, box = E->boxsize;
+  const float4 q0 = __ldg(rec);
+  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+  const double len = (double) q0.x;
+  double r2min = 1.0e300, r2max = -1.0e300, summass = 0.0;
+#pragma unroll
+  for(int g = 0; g < D; g++)
+    {
+      const float4 q = __ldg(rec + 1 + g);
+      double dx = (double) q.x - px, dy = (double) q.y - py, dz = (double) q.z - pz;
+      if(PERIODIC)
+	{
+	  dx = nearest_dd(dx, box);
+	  dy = nearest_dd(dy, box);
+	  dz = nearest_dd(dz, box);
+	}
+      const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+      summass = __dadd_rn(summass, (double) q.w);
+      if(r2 < r2min)
+	r2min = r2;
+      if(r2 > r2max)
+	r2max = r2;
+    }
+  if(SR && r2min > E->rcut2)
+    {				// forcetree.c:1828-1862
+      const double eff = __dadd_rn(E->rcut, __dmul_rn(0.5, len));
+      double d0 = (double) q0.y - px, d1 = (double) q0.z - py, d2 = (double) q0.w - pz;
+      if(PERIODIC)
+	{
+	  d0 = nearest_dd(d0, box);
+	  d1 = nearest_dd(d1, box);
+	  d2 = nearest_dd(d2, box);
+	}
+      if(d0 < -eff || d0 > eff || d1 < -eff || d1 > eff || d2 < -eff || d2 > eff)
+	return G2_DEC_CULL;
+    }
+  const double theta = E->theta;
+  if(theta != 0.0)
+    {				// forcetree.c:1865-1873
+      if(__dmul_rn(len, len) > __dmul_rn(__dmul_rn(r2min, theta), theta))
+	return G2_DEC_OPEN;
+    }
+  else
+    {				// forcetree.c:1874-1897
+      const double aold = __dmul_rn(E->errtol, (double) oldacc);
+      if(__dmul_rn(__dmul_rn(summass, len), len) > __dmul_rn(__dmul_rn(r2min, r2min), aold))
+	return G2_DEC_OPEN;
+      const double lim = __dmul_rn(0.60, len);
+      if(fabs((double) q0.y - px) < lim && fabs((double) q0.z - py) < lim && fabs((double) q0.w - pz) < lim)
+	return G2_DEC_OPEN;
+    }
+  if(UNEQUAL)
+    {				// forcetree.c:1899-1926
+      const int maxsofttype = (int) (w.z >> 29);
+      if(maxsofttype == 7)
+	return G2_DEC_OPEN;
+      double h = E->fsoft[ptype];
+      if(h < E->fsoft[maxsofttype])
+	{
+	  h = E->fsoft[maxsofttype];
+	  if(r2max < __dmul_rn(h, h) && ((w.z >> 28) & 1))
+	    return G2_DEC_OPEN;
+	}
+    }
+  return G2_DEC_ACCEPT;
+}
+
+// tabindex = (int) (asmthfac * sqrt(r2)) < NTAB in the reference's arithmetic (forcetree.c:1958-1967, 1996-2000)
+template <bool PERIODIC>
+__device__ __forceinline__ bool term_in_range_exact(const WalkExactParams *__restrict__ E, float sx, float sy, float sz, float pxf, float pyf, float pzf)
+{
+  double dx = (double) sx - (double) pxf, dy = (double) sy - (double) pyf, dz = (double) sz - (double) pzf;
+  if(PERIODIC)
+    {
+      dx = nearest_dd(dx, E->boxsize);
+      dy = nearest_dd(dy, E->boxsize);
+      dz = nearest_dd(dz, E->boxsize);
+    }
+  const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+  return (int) __dmul_rn(E->asmthfac, __dsqrt_rn(r2)) < E->ntab;
+}
+
+// periodic image shift of one cell for one target, split so that both partial differences are exact (walk_visit_cell)
+struct WalkShift
+{
+  float sx, sy, sz;		// subtracted from the source coordinate: max(shift, 0)
+  float tx, ty, tz;		// target coordinate + min(shift, 0)
+};
+
+// per-lane state of a walk
+struct WalkLane
+{
+  float px, py, pz, pmass, aold, hself;
+  int tg;
+  float fx, fy, fz;		// FP32 partial sums, flushed into the accumulators whenever the warp descends
+  int ninter, nterms, ndec;
+  int border;			// a comparison fell inside its guard band: the target goes to walk_redo_kernel
+  unsigned int skip_until;
+};
+
+// One visit, first half: this lane's decision on the cell at the cursor and, if it accepts the cell, the D species terms.
+// WRAP = false: no periodic image can matter for this cell and this warp's targets (non-periodic run, or a TreePM cell smaller
+// than the warp's no-wrap bound): plain differences.  WRAP = true: per-cell image shift for small TreePM cells, NEAREST per point
+// otherwise.  Returns whether the lane opens the cell; shx/shy/shz/small_cell are handed on to the particle half.
+// EXACT: comparisons inside their guard band flag the target for walk_redo_kernel (L.border).
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT>
+__device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, const float4 *__restrict__ rec,
+						const float4 q0, const uint4 w, unsigned int cur, WalkLane &L, WalkShift &S, bool &small_cell)
+{
+  bool open = false, done = false, outside = false, border = false;
+  if(STATS)
+    L.ndec++;
+  float dx[D], dy[D], dz[D], r2[D], mass[D];
+  float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
+  const float len = q0.x;
+  const float cxr = q0.y - L.px, cyr = q0.z - L.py, czr = q0.w - L.pz;
+  // TreePM: a cell that can interact with (or must be opened by) a target lies within rcut + len of it, so for
+  // len < L/2 - rcut every point of the cell has the same periodic image as the cell centre; points of cells that
+  // are culled anyway can only look farther away.  The image shift is then computed once per cell, not per point.
+  small_cell = WRAP && SR && len < A.shift_len_max;	// uniform (a property of the cell)
+  if(WRAP && SR)
+    {
+      // nearest image = source - target - shift, shift in {-L, 0, +L}.  Applied as (source - max(shift, 0)) - (target + min(shift, 0)):
+      // a shift of +L belongs to a source near the upper face, one of -L to a target near it, so both partial results are small
+      // and EXACT in FP32, and the final difference is rounded once to half an ulp of ITSELF -- like every unwrapped difference.
+      const float shx = A.boxsize * rint_small(cxr * A.boxinv), shy = A.boxsize * rint_small(cyr * A.boxinv), shz = A.boxsize * rint_small(czr * A.boxinv);
+      S.sx = fmaxf(shx, 0.0f); S.sy = fmaxf(shy, 0.0f); S.sz = fmaxf(shz, 0.0f);
+      S.tx = L.px + fminf(shx, 0.0f); S.ty = L.py + fminf(shy, 0.0f); S.tz = L.pz + fminf(shz, 0.0f);
+    }
+  if(SR)
+    {
+      // forcetree.c:1828-1862 culls a node if r2min > rcut^2 AND the target is farther than rcut + len/2 from the
+      // node centre on some axis.  All mass of a node lies inside its cube (up to float rounding of positions), so a
+      // target that clears the cube by a small margin on one axis is farther than rcut from every centre of mass:
+      // r2min > rcut^2 is then certain and the per-species distances need not be computed at all.
+      const float d0 = fabsf(WRAP ? (q0.y - S.sx) - S.tx : cxr), d1 = fabsf(WRAP ? (q0.z - S.sy) - S.ty : cyr), d2 = fabsf(WRAP ? (q0.w - S.sz) - S.tz : czr);
+      const float t = fmax3(d0, d1, d2) - fmaf(0.5f, len, A.rcut);
+      outside = t > 0.0f;
+      done = t > fmaf(1.0e-3f, len, A.cull_margin);
+      if(EXACT)
+	border = fabsf(t) < A.pos_border;
+    }
+  if(!done)
+    {
+#pragma unroll
+      for(int g = 0; g < D; g++)
+	{
+	  const float4 q = __ldg(rec + 1 + g);
+	  mass[g] = q.w;
+	  summass += q.w;
+	  if(!WRAP)
+	    {
+	      dx[g] = q.x - L.px;
+	      dy[g] = q.y - L.py;
+	      dz[g] = q.z - L.pz;
+	    }
+	  else if(small_cell)
+	    {
+	      dx[g] = (q.x - S.sx) - S.tx;
+	      dy[g] = (q.y - S.sy) - S.ty;
+	      dz[g] = (q.z - S.sz) - S.tz;
+	    }
+	  else
+	    {
+	      dx[g] = nearest<PERIODIC>(q.x - L.px, A.boxsize, A.boxinv);
+	      dy[g] = nearest<PERIODIC>(q.y - L.py, A.boxsize, A.boxinv);
+	      dz[g] = nearest<PERIODIC>(q.z - L.pz, A.boxsize, A.boxinv);
+	    }
+	  r2[g] = dx[g] * dx[g] + dy[g] * dy[g] + dz[g] * dz[g];
+	  r2min = fminf(r2min, r2[g]);
+	  r2max = fmaxf(r2max, r2[g]);
+	}
+      if(SR)
+	{
+	  const float u = r2min - A.rcut2;
+	  if(outside)
+	    {
+	      done = u > 0.0f;
+	      if(EXACT)
+		border = border || fabsf(u) < A.rcut2_border;
+	    }
+	  else if(EXACT)
+	    border = border && u > -A.rcut2_border;	// the box test is only taken when r2min > rcut^2
+	}
+    }
+  if(!done)
+    {
+      // The difference of two FP32 coordinates is rounded once, to half an ulp OF THE DIFFERENCE (it is exact when the operands share a
+      // binade), so an r^2 built from such differences, and the products compared below, carry a few 1e-7 of relative error whatever
+      // the magnitude of the coordinates: rel_tol covers it with a margin.
+      const float tol = (WRAP && !small_cell) ? fmaf(A.pos_ulp8, fast_rsqrt(r2min), A.rel_tol) : A.rel_tol;	// (per-point NEAREST rounds the raw difference at box scale)
+      if(A.theta2 > 0.0f)
+	{			// Barnes-Hut, forcetree.c:1437-1445
+	  const float lhs = len * len, v = fmaf(-r2min, A.theta2, lhs);
+	  open = v > 0.0f;
+	  if(EXACT)
+	    border = border || fabsf(v) < tol * lhs;
+	}
+      else
+	{			// relative criterion, forcetree.c:1446-1472
+	  const float lhs = summass * len * len, v = fmaf(-(r2min * r2min), L.aold, lhs);
+	  const float wv = fmaf(-0.60f, len, fmax3(fabsf(cxr), fabsf(cyr), fabsf(czr)));	// < 0: the target lies inside 0.6 len of the centre on every axis
+	  open = v > 0.0f || wv < 0.0f;
+	  if(EXACT)
+	    border = border || fabsf(v) < 2.0f * tol * lhs || fabsf(wv) < tol * len;
+	}
+    }
+  float h = L.hself;
+  if(UNEQUAL && !done && !open)
+    {				// forcetree.c:1475-1501; the record carries ForceSoftening[maxsofttype] (+inf and the
+				// mixed-softening bit for an empty node, maxsofttype == 7, which is always opened)
+      const float hnode = __uint_as_float(w.w);
+      if(h < hnode)
+	{
+	  h = hnode;
+	  if((w.z >> 28) & 1)
+	    {
+	      const float hv = fmaf(-h, h, r2max);
+	      open = hv < 0.0f;
+	      if(EXACT)
+		border = border || fabsf(hv) < 2.0f * A.rel_tol * r2max;
+	    }
+	}
+    }
+  if(EXACT && border)
+    L.border = 1;
+  if(!open)
+    {
+      L.skip_until = w.x;	// sleep until the cursor leaves this subtree
+      if(!done)
+	{
+	  bool any = false;
+#pragma unroll
+	  for(int g = 0; g < D; g++)
+	    {
+	      bool counted = mass[g] != 0.0f;	// forcetree.c:1553 / 1992
+	      if(SR)
+		{
+		  const float tv = r2[g] - A.rmax2;
+		  if(EXACT && fabsf(tv) < A.rmax2_border)
+		    L.border = 1;
+		  counted = counted && tv < 0.0f;
+		}
+	      const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
+	      pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
+	      any |= counted;
+	      if(STATS)
+		L.nterms += counted;
+	    }
+	  if(!SR || any)
+	    L.ninter++;		// forcetree.c:1585 resp. 2031-2032
+	}
+    }
+  return open;
+}
+
+// One visit, second half: the direct particle children of a cell, for the lanes that opened it.
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT>
+__device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, const uint4 w, bool open,
+						     unsigned int t2g_packed, WalkLane &L, const WalkShift &S, bool small_cell)
+{
+  const unsigned int np = w.z & 15u;
+  for(unsigned int j = 0; j < np; j++)
+    {
+      const float4 p = __ldg(A.wpart + w.y + j);
+      if(open)
+	{
+	  int sg = 0;
+	  float h = L.hself;
+	  if(UNEQUAL || !STOCK)
+	    {
+	      const int stype = (w.z >> (4 + 3 * j)) & 7;
+	      sg = (t2g_packed >> (4 * stype)) & 7;
+	      if(UNEQUAL)
+		h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
+	    }
+	  float ddx, ddy, ddz;
+	  if(!WRAP)
+	    {
+	      ddx = p.x - L.px;
+	      ddy = p.y - L.py;
+	      ddz = p.z - L.pz;
+	    }
+	  else if(small_cell)
+	    {
+	      ddx = (p.x - S.sx) - S.tx;
+	      ddy = (p.y - S.sy) - S.ty;
+	      ddz = (p.z - S.sz) - S.tz;
+	    }
+	  else
+	    {
+	      ddx = nearest<PERIODIC>(p.x - L.px, A.boxsize, A.boxinv);
+	      ddy = nearest<PERIODIC>(p.y - L.py, A.boxsize, A.boxinv);
+	      ddz = nearest<PERIODIC>(p.z - L.pz, A.boxsize, A.boxinv);
+	    }
+	  const float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
+	  bool counted = true;	// a particle term counts whatever its mass (forcetree.c:1958-1987)
+	  if(SR)
+	    {
+	      const float tv = rr2 - A.rmax2;
+	      counted = tv < 0.0f;
+	      if(EXACT && fabsf(tv) < A.rmax2_border)
+		L.border = 1;
+	    }
+	  pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz);
+	  L.ninter += counted;
+	  if(STATS)
+	    L.nterms += counted;
+	}
+    }
+}
+
+// gravity_tree epilogue for one target: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
+template <bool SR, bool PERIODIC>
+__device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned int idx, int tloc, float px, float py, float pz, float fx, float fy, float fz, float ninter)
+{
+  if(PERIODIC && !SR && A.latt)
+    {				// force_treeevaluate_lattice_correction adds to the FLOAT result and to GravCost (forcetree.c:2435-2438)
+      fx = (float) ((double) fx + (double) A.latt[3 * (size_t) idx + 0]);
+      fy = (float) ((double) fy + (double) A.latt[3 * (size_t) idx + 1]);
+      fz = (float) ((double) fz + (double) A.latt[3 * (size_t) idx + 2]);
+      if(A.lattcost)
+	ninter += A.lattcost[idx];
+    }
+  if(A.pos_fac_pre_g != 0.0)
+    {
+      fx = (float) ((double) fx + A.pos_fac_pre_g * (double) px);
+      fy = (float) ((double) fy + A.pos_fac_pre_g * (double) py);
+      fz = (float) ((double) fz + A.pos_fac_pre_g * (double) pz);
+    }
+  double sx = (double) fx, sy = (double) fy, sz = (double) fz;
+  if(A.use_gravpm)
+    {
+      sx += (double) A.gravpm[3 * (size_t) idx + 0] / A.G;
+      sy += (double) A.gravpm[3 * (size_t) idx + 1] / A.G;
+      sz += (double) A.gravpm[3 * (size_t) idx + 2] / A.G;
+    }
+  const float oldacc_new = (float) sqrt(sx * sx + sy * sy + sz * sz);
+  fx = (float) ((double) fx * A.G);
+  fy = (float) ((double) fy * A.G);
+  fz = (float) ((double) fz * A.G);
+  if(A.pos_fac_post_g != 0.0)
+    {
+      fx = (float) ((double) fx + A.pos_fac_post_g * (double) px);
+      fy = (float) ((double) fy + A.pos_fac_post_g * (double) py);
+      fz = (float) ((double) fz + A.pos_fac_post_g * (double) pz);
+    }
+  if(A.cres)
+    {				// compact results of the slice in target order (multi-GPU: only the slice travels to the host)
+      float *o = A.cres + 5 * (size_t) tloc;
+      o[0] = fx; o[1] = fy; o[2] = fz; o[3] = ninter; o[4] = oldacc_new;
+    }
+  else
+    {
+      A.oldacc_out[idx] = oldacc_new;
+      A.acc[3 * (size_t) idx + 0] = fx;
+      A.acc[3 * (size_t) idx + 1] = fy;
+      A.acc[3 * (size_t) idx + 2] = fz;
+      A.cost[idx] = ninter;
+    }
+}
+
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT>
+__global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
+{
+  extern __shared__ float s_tab[];
+  __shared__ unsigned int s_chunk[WALK_WARPS];
+  if(SR)
+    {
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
+	s_tab[i] = A.srtable[i];
+      __syncthreads();
+    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = 2 + D;
+  unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
+  asm volatile("" : "+r"(s_tab_addr));	// keep the table base in a register: re-deriving it costs 4 uniform instructions per pair term
+  unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
+#pragma unroll
+  for(int t = 0; t < 6; t++)
+    t2g_packed |= (unsigned int) A.t2g[t] << (4 * t);
+  const int lo = A.slice[G2_SLICE_LO], hi = A.slice[G2_SLICE_HI];
+  const int nchunks = (hi - lo + 31) >> 5;
+  const unsigned int end = (unsigned int) A.numnodes;
+  unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0, tot_dec = 0;
+
+  while(true)
+    {
+      // dynamic work distribution: one chunk of 32 consecutive targets per warp
+      if(lane == 0)
+	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+      __syncwarp();
+      const unsigned int chunk = s_chunk[warp];
+      __syncwarp();
+      if(chunk >= (unsigned int) nchunks)
+	break;
+      const int tloc = (int) chunk * 32 + lane;	// target ordinal inside the slice
+      const bool valid = lo + tloc < hi;
+      unsigned int idx = 0;
+      WalkLane L;
+      L.px = L.py = L.pz = L.pmass = L.aold = 0.0f;
+      int ptype = 1;
+      if(valid)
+	{
+	  idx = A.targets[lo + tloc];
+	  const G2PRec p = A.prec[idx];
+	  L.px = p.x; L.py = p.y; L.pz = p.z; L.pmass = p.m;
+	  ptype = p.type;
+	  L.aold = A.errtol * p.oldacc;	// forcetree.c:1289
+	}
+      L.tg = (t2g_packed >> (4 * ptype)) & 7;
+      L.hself = A.fsoft[ptype];
+      L.fx = L.fy = L.fz = 0.0f;
+      L.ninter = L.nterms = L.ndec = 0;
+      L.border = 0;
+      L.skip_until = valid ? 0u : 0xffffffffu;
+      ACC ax = 0, ay = 0, az = 0;
+      unsigned int iter = 0;
+      unsigned int cur = __any_sync(0xffffffffu, valid) ? 0u : end;
+      // TreePM: a target farther than rcut + len/2 (+ margins) from every face of the box needs no periodic image of a cell of size len:
+      // cells across a face are culled with the raw distance as well (raw >= nearest-image distance >= distance to the face).  Cells
+      // smaller than nowrap_len (warp minimum over the 32 targets, so uniform) take the no-wrap code path; results are unchanged.
+      float nowrap_len = 0.0f;
+      if(SR && PERIODIC)
+	{
+	  float m = valid ? fminf(fminf(fminf(L.px, A.boxsize - L.px), fminf(L.py, A.boxsize - L.py)), fminf(L.pz, A.boxsize - L.pz)) : 3.0e38f;
+#pragma unroll
+	  for(int o = 16; o > 0; o >>= 1)
+	    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+	  nowrap_len = fminf(A.shift_len_max, 1.99f * (m - A.rcut - 2.0f * A.cull_margin));
+	}
+
+      while(cur < end)
+	{
+	  const float4 *rec = A.cells + (size_t) cur * R;
+	  const float4 q0 = __ldg(rec);
+	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+	  const bool wrapv = PERIODIC && !(SR && q0.x < nowrap_len);	// uniform
+	  bool open = false, small_cell = false;
+	  WalkShift S;
+	  S.sx = S.sy = S.sz = S.tx = S.ty = S.tz = 0.0f;
+	  if(cur >= L.skip_until)
+	    {
+	      if(PERIODIC && wrapv)
+		open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
+	      else
+		open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
+	    }
+	  if(STATS)
+	    iter++;
+	  const unsigned int ball = __ballot_sync(0xffffffffu, open);
+	  if(ball != 0u)
+	    {
+	      // FP32 partial sums go into the (FP64) accumulators whenever the warp descends (about every third visit): few
+	      // conversions, bounded error, and flush points that depend on the traversal only (=> reproducible bits)
+	      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+	      L.fx = L.fy = L.fz = 0.0f;
+	      if(PERIODIC && wrapv)
+		walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
+	      else
+		walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
+	      cur = cur + 1u;
+	    }
+	  else
+	    cur = w.x;
+	}
+
+      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+      if(STATS && lane == 0)
+	tot_visits += iter;	// one cursor per warp: visits = loop trips
+      if(valid)
+	{
+	  if(EXACT && L.border)
+	    {			// walk_redo_kernel writes this target's result (the list has one slot per target of the slice)
+	      const unsigned int slot = atomicAdd(A.redo_count, 1u);
+	      A.redo_list[slot] = (unsigned int) tloc;
+	    }
+	  else
+	    {
+	      walk_store_result<SR, PERIODIC>(A, idx, tloc, L.px, L.py, L.pz, (float) ax, (float) ay, (float) az, (float) L.ninter);
+	      tot_inter += (unsigned long long) L.ninter;
+	    }
+	  if(STATS)
+	    {
+	      tot_terms += (unsigned long long) L.nterms;
+	      tot_dec += (unsigned long long) L.ndec;
+	    }
+	}
+    }
+  // statistics: interactions (= sum of GravCost), and with STATS cell visits (per cursor), species terms, decisions
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1)
+    {
+      tot_inter += __shfl_xor_sync(0xffffffffu, tot_inter, o);
+      if(STATS)
+	{
+	  tot_terms += __shfl_xor_sync(0xffffffffu, tot_terms, o);
+	  tot_dec += __shfl_xor_sync(0xffffffffu, tot_dec, o);
+	  tot_visits += __shfl_xor_sync(0xffffffffu, tot_visits, o);
+	}
+    }
+  if(lane == 0)
+    {
+      atomicAdd(&A.counters[0], tot_inter);
+      if(STATS)
+	{
+	  atomicAdd(&A.counters[1], tot_visits);
+	  atomicAdd(&A.counters[2], tot_terms);
+	  atomicAdd(&A.counters[4], tot_dec);
+	}
+    }
+}
+
+// ---- the walk of the targets the FP32 kernel flagged, one thread per target, in the reference's own arithmetic: double locals,
+//      FLOAT node and particle fields, decisions by walk_decide_exact, tabindex = (int) (asmthfac * r) (forcetree.c:1244-1610 and
+//      1623-2052 restated over the depth-first records).  The pair laws keep their FP32 device forms; sums are FP64. ----
+#define WALK_REDO_THREADS 64
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
+__global__ void __launch_bounds__(WALK_REDO_THREADS) walk_redo_kernel(const WalkArgs A)
+{
+  extern __shared__ float s_tab[];
+  if(SR)
+    {
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_REDO_THREADS)
+	s_tab[i] = A.srtable[i];
+      __syncthreads();
+    }
+  const WalkExactParams *__restrict__ E = A.ex;
+  const int R = 2 + D;
+  const int lo = A.slice[G2_SLICE_LO];
+  const unsigned int nredo = *A.redo_count, end = (unsigned int) A.numnodes;
+  unsigned long long tot_inter = 0;
+  for(unsigned int i = blockIdx.x * WALK_REDO_THREADS + threadIdx.x; i < nredo; i += gridDim.x * WALK_REDO_THREADS)
+    {
+      const int tloc = (int) A.redo_list[i];
+      const unsigned int idx = A.targets[lo + tloc];
+      const G2PRec tp = A.prec[idx];
+      const double px = (double) tp.x, py = (double) tp.y, pz = (double) tp.z, box = E->boxsize;
+      const int tg = A.t2g[tp.type];
+      const double hself = E->fsoft[tp.type];
+      double ax = 0.0, ay = 0.0, az = 0.0;
+      int ninter = 0;
+      unsigned int cur = 0u;
+      while(cur < end)
+	{
+	  const float4 *rec = A.cells + (size_t) cur * R;
+	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+	  const int dec = walk_decide_exact<D, SR, PERIODIC, UNEQUAL>(E, rec, A.prec + idx);
+	  if(dec == G2_DEC_CULL)
+	    {
+	      cur = w.x;
+	      continue;
+	    }
+	  const bool isnode = dec == G2_DEC_ACCEPT;
+	  const int nsrc = isnode ? D : (int) (w.z & 15u);
+	  double h = hself;
+	  if(UNEQUAL && isnode)
+	    {			// forcetree.c:1475-1501: the node's largest softening if it exceeds the target's
+	      const int mst = (int) (w.z >> 29);
+	      if(mst < 6 && h < E->fsoft[mst])
+		h = E->fsoft[mst];
+	    }
+	  bool any = false;
+	  for(int j = 0; j < nsrc; j++)
+	    {
+	      const float4 q = isnode ? __ldg(rec + 1 + j) : __ldg(A.wpart + w.y + j);
+	      int sg = j;
+	      double hh = h;
+	      if(!isnode)
+		{
+		  const int stype = (w.z >> (4 + 3 * j)) & 7;
+		  sg = A.t2g[stype];
+		  if(UNEQUAL && hh < E->fsoft[stype])
+		    hh = E->fsoft[stype];	// forcetree.c:1412-1415
+		}
+	      else if(q.w == 0.0f)
+		continue;	// forcetree.c:1553 / 1992
+	      double dx = (double) q.x - px, dy = (double) q.y - py, dz = (double) q.z - pz;
+	      if(PERIODIC)
+		{
+		  dx = nearest_dd(dx, box);
+		  dy = nearest_dd(dy, box);
+		  dz = nearest_dd(dz, box);
+		}
+	      const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+	      const double r = __dsqrt_rn(r2);
+	      int tabindex = 0;
+	      if(SR)
+		{
+		  tabindex = (int) __dmul_rn(E->asmthfac, r);	// forcetree.c:1962
+		  if(tabindex >= E->ntab)
+		    continue;
+		}
+	      else if(!isnode)
+		ninter++;	// without PM every particle of an opened node counts (forcetree.c:1585)
+	      const int ij = tg * D + sg;
+	      const double m = (double) q.w;
+	      const float nn = (isnode && !STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + j) : 1.0f;
+	      double fac = 0.0;
+	      if(r >= hh)
+		{
+		  double a = STOCK ? m / r2 : (double) accel_over_r(A.laws.accel[ij], A.laws.par[ij], tp.m, q.w, (float) r2, (float) r, (float) (1.0 / r), nn) * r;
+		  if(SR)
+		    a -= m * (double) A.utor2wpi * (double) s_tab[(int) A.tabmap[ij] * A.ntab + tabindex];
+		  fac = a / r;
+		}
+	      else
+		fac = STOCK ? (double) law_plummer(q.w, (float) hh, (float) r) : (double) accel_spline(A.laws.spline[ij], A.laws.par[ij], tp.m, q.w, (float) hh, (float) r, nn);
+	      ax += dx * fac;
+	      ay += dy * fac;
+	      az += dz * fac;
+	      any = true;
+	      if(SR && !isnode)
+		ninter++;	// a particle inside the table counts (forcetree.c:2031)
+	    }
+	  if(isnode && (!SR || any))
+	    ninter++;		// forcetree.c:1585 resp. 2031-2032
+	  cur = isnode ? w.x : cur + 1u;
+	}
+      walk_store_result<SR, PERIODIC>(A, idx, tloc, tp.x, tp.y, tp.z, (float) ax, (float) ay, (float) az, (float) ninter);
+      tot_inter += (unsigned long long) ninter;
+    }
+  if(tot_inter)
+    atomicAdd(&A.counters[0], tot_inter);
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+    A.counters[5] = (unsigned long long) nredo;
+}
+
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT>
+static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
+{
+  if(smem > 48 * 1024)
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT><<<grid, WALK_THREADS, smem, c->stream>>>(A);
+  if(EXACT)
+    {
+      if(smem > 48 * 1024)
+	G2_CUDA(cudaFuncSetAttribute(walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+      walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK><<<c->nsm * 8, WALK_REDO_THREADS, smem, c->stream>>>(A);
+      c->launches++;
+    }
+  return 0;
+}
+
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
+static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, int acc_double, int stats)
+{
+  // exact (default): FP64 accumulators + guard bands + redo pass; otherwise the plain FP32-decision kernel with FP32 accumulators
+  if(stats)			// instrumented instantiation (visits, species terms, decisions)
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, true, true>(c, A, grid, smem);
+  if(!acc_double || !A.exact)
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false>(c, A, grid, smem);
+  return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true>(c, A, grid, smem);
+}
+
+template <int D>
+static int dispatch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, bool sr, bool periodic, bool unequal, bool stock, int accd, int stats)
+{
+#define G2_W(SRv, PERv, UNEv, STv) return launch_walk<D, SRv, PERv, UNEv, STv>(c, A, grid, smem, accd, stats)
+  if(sr)
+    {				// TreePM implies PERIODIC and equal softenings are not required; keep both UNEQUAL variants
+      if(unequal) { if(stock) G2_W(true, true, true, true); else G2_W(true, true, true, false); }
+      else        { if(stock) G2_W(true, true, false, true); else G2_W(true, true, false, false); }
+    }
+  else if(periodic)
+    {
+      if(unequal) { if(stock) G2_W(false, true, true, true); else G2_W(false, true, true, false); }
+      else        { if(stock) G2_W(false, true, false, true); else G2_W(false, true, false, false); }
+    }
+  else
+    {
+      if(unequal) { if(stock) G2_W(false, false, true, true); else G2_W(false, false, true, false); }
+      else        { if(stock) G2_W(false, false, false, true); else G2_W(false, false, false, false); }
+    }
+#undef G2_W
+}

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libg2gpu.so")
+LIB_PATH = os.environ.get("G2GPU_LIB") or os.path.join(HERE, "libg2gpu.so")   # G2GPU_LIB: a variant build (profiles/experiments)
 
 LAW = dict(none=0, newtonian=1, neg_newtonian=2, yukawa=3, coloyuk=4, bambam=5, sourcebambaryon=6, sourcebaryonbam=7)
 SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebambaryon_spline=20,
@@ -27,6 +27,11 @@ EXPORTED = [
     "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
     "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table",
     "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential",
+    "g2gpu_group_create", "g2gpu_group_destroy", "g2gpu_group_size", "g2gpu_group_ctx", "g2gpu_group_set_species", "g2gpu_group_set_laws",
+    "g2gpu_group_set_srtable", "g2gpu_group_set_lattice_tables", "g2gpu_group_set_option", "g2gpu_group_upload", "g2gpu_group_upload_aos",
+    "g2gpu_group_gather_resident", "g2gpu_group_shard", "g2gpu_group_domain", "g2gpu_group_treebuild", "g2gpu_group_update_tree",
+    "g2gpu_group_walk", "g2gpu_group_download_acc", "g2gpu_group_download_aos", "g2gpu_group_get_order", "g2gpu_group_gravity_tree",
+    "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices",
 ]
 
 
@@ -69,6 +74,7 @@ def load_library():
         lib = C.CDLL(LIB_PATH)
         lib.g2gpu_last_error.restype = C.c_char_p
         lib.g2gpu_stream.restype = C.c_void_p
+        lib.g2gpu_group_ctx.restype = C.c_void_p
         _lib = lib
     return _lib
 
@@ -369,7 +375,7 @@ class TreeGravity:
         cnt = np.zeros(8, dtype=np.int64)
         self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
         return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6], pm_ms=ms[7],
-                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]))
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]), rewalked=int(cnt[5]))
 
     def reset_counters(self):
         self.lib.g2gpu_reset_counters(self.ctx)
@@ -399,3 +405,151 @@ class TreeGravity:
         fac = np.zeros(len(r), dtype=np.float32)
         self._chk(self.lib.g2gpu_eval_pairs(self.ctx, len(r), tgt, src, _p(pm), _p(m), _p(r), _p(h), _p(_i32(nn)), _p(fac)))
         return fac
+
+
+class TreeGravityGroup:
+    """Several GPUs of one node behind the same stage calls (g2gpu_group_*, csrc/g2_group.cu): ONE process, one context + stream +
+    host thread per device, sharded upload + NCCL all-gather of the particle records, replicated tree, one target slice per device.
+    It is the device twin of the parallel driver inside the reference's gravity_tree() (gravtree.c:102-285)."""
+
+    def __init__(self, max_part, n_gravs=2, periodic=False, shortrange=False, ntab=2048, unequal_softenings=True, tree_alloc_factor=1.5,
+                 ndev=0, devices=None):
+        self.lib = load_library()
+        self.cfg = Config(0, n_gravs, int(periodic), int(shortrange), ntab, int(unequal_softenings), int(max_part),
+                          int(tree_alloc_factor * max_part), 0, 1)
+        self.grp = C.c_void_p()
+        dv = None if devices is None else _i32(devices)
+        self._chk(self.lib.g2gpu_group_create(C.byref(self.grp), C.byref(self.cfg), int(ndev if devices is None else len(devices)), _p(dv)))
+        self.ndev = int(self.lib.g2gpu_group_size(self.grp))
+        self.D = n_gravs
+        self.max_part = int(max_part)
+        self.n = 0
+        self.numnodes = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise G2Error(rc, self.lib.g2gpu_last_error().decode())
+
+    def close(self):
+        if self.grp:
+            self.lib.g2gpu_group_destroy(self.grp)
+            self.grp = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def ctx(self, i=0):
+        """Device i's context as a (non-owning) TreeGravity: tree mirror, potential, PM, direct sums are served by device 0."""
+        t = TreeGravity.__new__(TreeGravity)
+        t.lib, t.cfg, t.D, t.max_part, t.n, t.numnodes = self.lib, self.cfg, self.D, self.max_part, self.n, self.numnodes
+        t.ctx = C.c_void_p(self.lib.g2gpu_group_ctx(self.grp, int(i)))
+        t.close = lambda: None
+        return t
+
+    def set_species(self, type_to_grav, force_softening):
+        t2g = _i32(type_to_grav)
+        fs = np.ascontiguousarray(force_softening, dtype=np.float64)
+        self._chk(self.lib.g2gpu_group_set_species(self.grp, _p(t2g), _p(fs)))
+
+    def set_laws(self, accel="newtonian", spline="plummer", params=None):
+        D = self.D
+
+        def grid(x, table):
+            if isinstance(x, str):
+                return np.full((D, D), table[x], dtype=np.int32)
+            return np.array([[table[v] for v in row] for row in x], dtype=np.int32)
+        a, s = grid(accel, LAW), grid(spline, SPLINE)
+        par = np.zeros((D, D, 4)) if params is None else np.ascontiguousarray(params, dtype=np.float64)
+        self._chk(self.lib.g2gpu_group_set_laws(self.grp, _p(a), _p(s), _p(par)))
+
+    def set_srtable(self, table):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        assert t.shape == (self.D, self.D, self.cfg.ntab)
+        self._chk(self.lib.g2gpu_group_set_srtable(self.grp, _p(t)))
+
+    def set_option(self, name, value):
+        self._chk(self.lib.g2gpu_group_set_option(self.grp, name.encode(), int(value)))
+
+    walk_params = staticmethod(lambda **kw: TreeGravity.walk_params(**kw))
+
+    def upload(self, pos, mass, ptype, oldacc=None, active=None):
+        pos, mass, ptype = _f32(pos), _f32(mass), _i32(ptype)
+        self.n = len(mass)
+        self._chk(self.lib.g2gpu_group_upload(self.grp, self.n, _p(pos), _p(mass), _p(ptype), _p(_f32(oldacc)), _p(_i32(active))))
+
+    def shard(self, n, i):
+        lo, cnt = C.c_int(), C.c_int()
+        self._chk(self.lib.g2gpu_group_shard(self.grp, int(n), int(i), C.byref(lo), C.byref(cnt)))
+        return lo.value, cnt.value
+
+    def gather_resident(self, n):
+        self._chk(self.lib.g2gpu_group_gather_resident(self.grp, int(n)))
+        self.n = int(n)
+
+    def domain(self):
+        self._chk(self.lib.g2gpu_group_domain(self.grp))
+
+    def treebuild(self):
+        nn = C.c_int()
+        self._chk(self.lib.g2gpu_group_treebuild(self.grp, C.byref(nn)))
+        self.numnodes = nn.value
+        return nn.value
+
+    def walk(self, wp):
+        self._chk(self.lib.g2gpu_group_walk(self.grp, C.byref(wp)))
+
+    def download_acc(self, out=None):
+        if out is not None:
+            acc, cost, old = out
+        else:
+            acc = np.zeros((self.n, 3), dtype=np.float32)
+            cost = np.zeros(self.n, dtype=np.float32)
+            old = np.zeros(self.n, dtype=np.float32)
+        self._chk(self.lib.g2gpu_group_download_acc(self.grp, _p(acc), _p(cost), _p(old)))
+        return acc, cost, old
+
+    def get_order(self):
+        perm = np.zeros(self.n, dtype=np.int32)
+        self._chk(self.lib.g2gpu_group_get_order(self.grp, _p(perm)))
+        return perm
+
+    def gravity_tree(self, pos, mass, ptype, wp, oldacc=None, active=None, out=None):
+        """Whole step from host buffers on all devices (the e2e path); results in CURRENT (device) order + perm, like TreeGravity.gravity_tree."""
+        pos, mass, ptype = _f32(pos), _f32(mass), _i32(ptype)
+        n = len(mass)
+        if out is not None:
+            acc, cost, old, perm = out
+        else:
+            acc = np.zeros((n, 3), dtype=np.float32)
+            cost = np.zeros(n, dtype=np.float32)
+            old = np.zeros(n, dtype=np.float32)
+            perm = np.zeros(n, dtype=np.int32)
+        self._chk(self.lib.g2gpu_group_gravity_tree(self.grp, n, _p(pos), _p(mass), _p(ptype), _p(_f32(oldacc)), _p(_i32(active)),
+                                                    C.byref(wp), _p(acc), _p(cost), _p(old), _p(perm)))
+        self.n = n
+        return acc, cost, old, perm
+
+    def sync(self):
+        self._chk(self.lib.g2gpu_group_sync(self.grp))
+
+    def timings(self):
+        ms = np.zeros(8)
+        cnt = np.zeros(8, dtype=np.int64)
+        self._chk(self.lib.g2gpu_group_timings(self.grp, _p(ms), _p(cnt)))
+        return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6], pm_ms=ms[7],
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]),
+                    rewalked=int(cnt[5]))
+
+    def io_bytes(self):
+        b = np.zeros(3, dtype=np.int64)
+        self._chk(self.lib.g2gpu_group_io_bytes(self.grp, _p(b)))
+        return int(b[0]), int(b[1]), int(b[2])
+
+    def slices(self):
+        lo, hi = np.zeros(self.ndev, dtype=np.int32), np.zeros(self.ndev, dtype=np.int32)
+        fr = np.zeros(self.ndev + 1)
+        self._chk(self.lib.g2gpu_group_slices(self.grp, _p(lo), _p(hi), _p(fr)))
+        return lo, hi, fr

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <pthread.h>
+#include <unistd.h>
 #include <mpi.h>
 
 #include "allvars.h"
@@ -32,11 +34,57 @@
 #include "g2gpu.h"
 #include "g2_ph_table.h"
 
-static g2gpu_ctx *G2 = NULL;
+static g2gpu_group *G2G = NULL;	/* all GPUs of the node (or G2GPU_NGPU of them): one context + host thread per device */
+static g2gpu_ctx *G2 = NULL;	/* device 0's context: tree mirror, potential, PM, direct sums */
+static int g2_ndev = 1;
 static int g2_maxpart = 0, g2_maxnodes = 0;
 static int *g2_perm = NULL;		/* device particle index -> index in P[] */
 static int g2_perm_identity = 1;
-static float *g2_acc = NULL, *g2_cost = NULL, *g2_oldacc = NULL;
+static float *g2_acc = NULL, *g2_cost = NULL, *g2_oldacc = NULL;	/* per-target results of g2_evaluate_one (allocated on first use) */
+
+/* ---- host loops over NumPart run on several threads (the reference's are single-threaded; at 16.8 M particles they would
+ *      otherwise cost more than the device step) ---- */
+struct g2_par_job { void (*fn) (long lo, long hi, void *arg); void *arg; long lo, hi; };
+static void *g2_par_thread(void *v)
+{
+  struct g2_par_job *j = v;
+  j->fn(j->lo, j->hi, j->arg);
+  return NULL;
+}
+static void g2_parallel_for(long n, void (*fn) (long lo, long hi, void *arg), void *arg)
+{
+  long nt = sysconf(_SC_NPROCESSORS_ONLN), t;
+  pthread_t th[16];
+  int started[16];
+  struct g2_par_job job[16];
+  if(nt > 16)
+    nt = 16;
+  if(nt > n / 65536 + 1)
+    nt = n / 65536 + 1;
+  if(nt <= 1)
+    {
+      fn(0, n, arg);
+      return;
+    }
+  for(t = 0; t < nt; t++)
+    {
+      job[t].fn = fn;
+      job[t].arg = arg;
+      job[t].lo = n * t / nt;
+      job[t].hi = n * (t + 1) / nt;
+      started[t] = 0;
+    }
+  for(t = 1; t < nt; t++)
+    started[t] = pthread_create(&th[t], NULL, g2_par_thread, &job[t]) == 0;
+  fn(job[0].lo, job[0].hi, arg);
+  for(t = 1; t < nt; t++)
+    {
+      if(started[t])
+	pthread_join(th[t], NULL);
+      else
+	fn(job[t].lo, job[t].hi, arg);	/* could not start a thread: do the slice here */
+    }
+}
 static int g2_mirror = -1;		/* refresh the host mirror Nodes[]/Nextnode[]/Father[] after every build */
 static int g2_tree_mirrored = 0;	/* Nodes[] holds the tree the device built last and P[] has not been reordered since */
 static int g2_dynamic = -1;		/* follow the reference's dynamic tree updates instead of building a new tree (G2GPU_DYNAMIC_TREE) */
@@ -96,16 +144,23 @@ static void g2_upload(int npart)
 #endif
   if(g2_mirror > 0 || N_gas > 0 || (All.TreeDomainUpdateFrequency > 0.0 && TreeReconstructFlag))
     off_vel = (int) offsetof(struct particle_data, Vel);	/* Extnodes[].vs of the host mirror */
-  g2_check(g2gpu_upload_aos(G2, npart, P, sizeof(struct particle_data), (int) sizeof(FLOAT),
-			    (int) offsetof(struct particle_data, Pos), (int) offsetof(struct particle_data, Mass),
-			    (int) offsetof(struct particle_data, Type), (int) offsetof(struct particle_data, OldAcc),
-			    off_vel, off_gravpm, (int) offsetof(struct particle_data, Ti_endstep), All.Ti_Current), "upload");
+  if(off_vel >= 0 && g2_ndev > 1)
+    {
+      printf("g2gpu: the host tree mirror (gas particles, TreeDomainUpdateFrequency > 0 or G2GPU_HOST_MIRROR) needs node velocities, which a\n"
+	     "multi-GPU group does not keep; run with G2GPU_NGPU=1.\n");
+      endrun(7103);
+    }
+  /* every device copies its 1/N of P[] (packed by host threads into pinned 32-byte records), one NCCL all-gather replicates them */
+  g2_check(g2gpu_group_upload_aos(G2G, npart, P, sizeof(struct particle_data), (int) sizeof(FLOAT),
+				  (int) offsetof(struct particle_data, Pos), (int) offsetof(struct particle_data, Mass),
+				  (int) offsetof(struct particle_data, Type), (int) offsetof(struct particle_data, OldAcc),
+				  off_vel, off_gravpm, (int) offsetof(struct particle_data, Ti_endstep), All.Ti_Current), "upload");
 }
 
 static void g2_fetch_order(int npart)
 {
   int i;
-  g2_check(g2gpu_get_order(G2, g2_perm), "get_order");
+  g2_check(g2gpu_group_get_order(G2G, g2_perm), "get_order");
   g2_perm_identity = 1;
   for(i = 0; i < npart; i++)
     if(g2_perm[i] != i)
@@ -113,6 +168,19 @@ static void g2_fetch_order(int npart)
 	g2_perm_identity = 0;
 	break;
       }
+}
+
+static void g2_copy_P(long lo, long hi, void *arg)
+{
+  memcpy((struct particle_data *) arg + lo, P + lo, sizeof(struct particle_data) * (size_t) (hi - lo));
+}
+
+static void g2_permute_P(long lo, long hi, void *arg)
+{
+  const struct particle_data *tmp = arg;
+  long i;
+  for(i = lo; i < hi; i++)
+    P[i] = tmp[g2_perm[i]];
 }
 
 /* peano.c:36: gas block first, then species-major, Peano-Hilbert inside a block.  Keys and the sort run on the GPU;
@@ -129,15 +197,14 @@ void peano_hilbert_order(void)
     return;
   g2_push_tables();		/* the sort needs TypeToGrav */
   g2_upload(NumPart);
-  g2_check(g2gpu_domain(G2), "domain");
+  g2_check(g2gpu_group_domain(G2G), "domain");
   g2_fetch_order(NumPart);
   if(!g2_perm_identity)
     {
       if(!(tmp = malloc(sizeof(struct particle_data) * NumPart)))
 	endrun(7101);
-      memcpy(tmp, P, sizeof(struct particle_data) * NumPart);
-      for(i = 0; i < NumPart; i++)
-	P[i] = tmp[g2_perm[i]];
+      g2_parallel_for(NumPart, g2_copy_P, tmp);
+      g2_parallel_for(NumPart, g2_permute_P, tmp);
       free(tmp);
       if(N_gas > 0)
 	{
@@ -207,8 +274,8 @@ static void g2_push_tables(void)
 	par[4 * (i * N_GRAVS + j) + 1] = BAM_EPSILON;
 	par[4 * (i * N_GRAVS + j) + 2] = par[4 * (i * N_GRAVS + j) + 3] = 0;
       }
-  g2_check(g2gpu_set_species(G2, TypeToGrav, All.ForceSoftening), "set_species");
-  g2_check(g2gpu_set_laws(G2, accel, spline, par), "set_laws");
+  g2_check(g2gpu_group_set_species(G2G, TypeToGrav, All.ForceSoftening), "set_species");
+  g2_check(g2gpu_group_set_laws(G2G, accel, spline, par), "set_laws");
 #ifdef PMGRID
   {				/* PotentialFxns / PotentialSplines (allvars.h:147-148).  A wiring without a device implementation (the BAM potentials)
 				 * is left unset: the force path does not need it, and a potential request then ends the run (G2GPU_ERR_LAW). */
@@ -296,7 +363,7 @@ static void g2_push_lattice(void)
 	  for(i = 0; i < (int) n3; i++)
 	    tab[((size_t) (c * N_GRAVS + l) * N_GRAVS + m) * n3 + i] = one[c * n3 + i] / (All.BoxSize * All.BoxSize);	/* forcetree.c:3757-3761 */
       }
-  g2_check(g2gpu_set_lattice_tables(G2, NGRAVS_EN, tab), "set_lattice_tables");
+  g2_check(g2gpu_group_set_lattice_tables(G2G, NGRAVS_EN, tab), "set_lattice_tables");
   free(one);
   free(tab);
 }
@@ -316,12 +383,20 @@ void force_treeallocate(int maxnodes, int maxpart)
   Nodes = Nodes_base - All.MaxPart;
   Extnodes = Extnodes_base - All.MaxPart;
 
-  if(G2 && (g2_maxpart != All.MaxPart || g2_maxnodes != maxnodes))
+  if(NTask > 1)
+    {				/* the shim replaces gravity_tree() without its particle export/import between MPI tasks */
+      if(ThisTask == 0)
+	printf("g2gpu: this drop-in serves ONE MPI task that owns all particles (it spreads the work over the GPUs of the node itself);\n"
+	       "run with a single task.\n");
+      endrun(7001);
+    }
+  if(G2G && (g2_maxpart != All.MaxPart || g2_maxnodes != maxnodes))
     {
-      g2gpu_destroy(G2);
+      g2gpu_group_destroy(G2G);
+      G2G = NULL;
       G2 = NULL;
     }
-  if(!G2)
+  if(!G2G)
     {
       g2gpu_config cfg;
       memset(&cfg, 0, sizeof(cfg));
@@ -339,24 +414,22 @@ void force_treeallocate(int maxnodes, int maxpart)
 #endif
       cfg.max_part = All.MaxPart;
       cfg.max_nodes = maxnodes;
-      cfg.rank = 0;
-      cfg.nranks = 1;
-      g2_check(g2gpu_create(&G2, &cfg), "create");
+      /* all visible GPUs share the work (ndev = 0); G2GPU_NGPU limits them */
+      g2_check(g2gpu_group_create(&G2G, &cfg, getenv("G2GPU_NGPU") ? atoi(getenv("G2GPU_NGPU")) : 0, NULL), "group_create");
+      g2_ndev = g2gpu_group_size(G2G);
+      G2 = g2gpu_group_ctx(G2G, 0);
 #ifdef NGRAVS_ACCUMULATOR
-      g2_check(g2gpu_set_option(G2, "accumulator", 1), "set_option");	/* laws receive Nodes[].u.d.Nparticles as N */
+      g2_check(g2gpu_group_set_option(G2G, "accumulator", 1), "set_option");	/* laws receive Nodes[].u.d.Nparticles as N */
 #endif
       g2_maxpart = All.MaxPart;
       g2_maxnodes = maxnodes;
       g2_perm = realloc(g2_perm, sizeof(int) * All.MaxPart);
-      g2_acc = realloc(g2_acc, sizeof(float) * 3 * All.MaxPart);
-      g2_cost = realloc(g2_cost, sizeof(float) * All.MaxPart);
-      g2_oldacc = realloc(g2_oldacc, sizeof(float) * All.MaxPart);
       if(ThisTask == 0)
-	printf("\ng2gpu: device context for %d particles / %d tree nodes created.\n\n", All.MaxPart, maxnodes);
+	printf("\ng2gpu: %d device context%s for %d particles / %d tree nodes created.\n\n", g2_ndev, g2_ndev > 1 ? "s" : "", All.MaxPart, maxnodes);
 #ifdef PMGRID
       if(!g2_srtable_done)
 	g2_build_srtable();
-      g2_check(g2gpu_set_srtable(G2, &g2_srtable[0][0][0]), "set_srtable");
+      g2_check(g2gpu_group_set_srtable(G2G, &g2_srtable[0][0][0]), "set_srtable");
       g2_check(g2gpu_set_srpot_table(G2, &g2_srpot[0][0][0]), "set_srpot_table");
 #endif
 #if defined(PERIODIC) && !defined(PMGRID)
@@ -670,9 +743,9 @@ int force_treebuild(int npart)
   g2_tree_mirrored = 0;
   g2_push_tables();
   g2_upload(npart);
-  g2_check(g2gpu_domain(G2), "domain");
+  g2_check(g2gpu_group_domain(G2G), "domain");
   g2_fetch_order(npart);
-  g2_check(g2gpu_treebuild(G2, &numnodes), "treebuild");
+  g2_check(g2gpu_group_treebuild(G2G, &numnodes), "treebuild");
   Numnodestree = numnodes;
   {
     /* Who reads the host arrays: ngb.c / density.c (gas), and -- when the run does not rebuild at every step
@@ -746,8 +819,16 @@ static int g2_evaluate_one(int target, int mode)
   g2_fill_walk_params(&wp);
   wp.G = 1.0;			/* the per-target functions return the pre-G acceleration (forcetree.c:1592) */
   wp.pos_fac_pre_g = wp.pos_fac_post_g = 0;
-  g2_check(g2gpu_walk(G2, &wp), "walk");
-  g2_check(g2gpu_download_acc(G2, g2_acc, g2_cost, g2_oldacc), "download_acc");
+  if(!g2_acc)
+    {
+      g2_acc = malloc(sizeof(float) * 3 * (size_t) All.MaxPart);
+      g2_cost = malloc(sizeof(float) * (size_t) All.MaxPart);
+      g2_oldacc = malloc(sizeof(float) * (size_t) All.MaxPart);
+      if(!g2_acc || !g2_cost || !g2_oldacc)
+	endrun(7404);
+    }
+  g2_check(g2gpu_group_walk(G2G, &wp), "walk");
+  g2_check(g2gpu_group_download_acc(G2G, g2_acc, g2_cost, g2_oldacc), "download_acc");
   for(i = 0; i < n; i++)
     if(g2_perm[i] == target)
       {
@@ -803,6 +884,7 @@ void force_treeevaluate_potential_shortrange(int target, int mode)
       force_treebuild(NumPart);
       TreeReconstructFlag = save;
       g2_fill_walk_params(&wp);
+      g2_check(g2gpu_set_option(G2, "nranks", 1), "set_option");	/* device 0 walks all particles (compute_potential is not on the benchmarked path) */
       g2_check(g2gpu_potential(G2, &wp), "potential");
       g2_check(g2gpu_download_potential(G2, pot, NULL), "download_potential");
       for(i = 0; i < NumPart; i++)
@@ -861,7 +943,7 @@ static void g2_dynamic_update(int npart)
     }
   g2_push_tables();
   g2_upload(npart);
-  g2_check(g2gpu_update_tree(G2, len, s), "update_tree");
+  g2_check(g2gpu_group_update_tree(G2G, len, s), "update_tree");
   free(s);
   free(len);
 }
@@ -874,7 +956,9 @@ void gravity_tree(void)
   double tstart, tend, timetree, costtotal = 0;
   long long ntot = NumForceUpdate;
   g2gpu_walk_params wp;
-  int i, j, k;
+  int i, j;
+  (void) i;
+  (void) j;	/* used by the NOGRAVITY / SELECTIVE_NO_GRAVITY branches only */
 
   if(All.ComovingIntegrationOn)
     set_softenings();
@@ -903,20 +987,11 @@ void gravity_tree(void)
 #endif
   tstart = second();
   g2_fill_walk_params(&wp);
-  g2_check(g2gpu_walk(G2, &wp), "walk");
-  g2_check(g2gpu_download_acc(G2, g2_acc, g2_cost, g2_oldacc), "download_acc");
-  for(i = 0; i < NumPart; i++)
-    {
-      j = g2_perm[i];
-      if(P[j].Ti_endstep == All.Ti_Current)
-	{
-	  for(k = 0; k < 3; k++)
-	    P[j].GravAccel[k] = g2_acc[3 * i + k];
-	  P[j].GravCost = g2_cost[i];
-	  P[j].OldAcc = g2_oldacc[i];
-	  costtotal += g2_cost[i];
-	}
-    }
+  g2_check(g2gpu_group_walk(G2G, &wp), "walk");
+  /* every device returns its slice of the active targets; host threads write GravAccel, GravCost and OldAcc straight into P[] */
+  g2_check(g2gpu_group_download_aos(G2G, P, sizeof(struct particle_data), (int) sizeof(FLOAT), (int) offsetof(struct particle_data, GravAccel),
+				    (int) offsetof(struct particle_data, GravCost), (int) offsetof(struct particle_data, OldAcc),
+				    g2_perm_identity ? NULL : g2_perm, &costtotal), "download_aos");
   tend = second();
   timetree = timediff(tstart, tend);
 

@@ -258,18 +258,68 @@ int g2gpu_gravity_tree(g2gpu_ctx *ctx, int npart, const float *pos, const float 
 		       const float *oldacc, const int *active, const g2gpu_walk_params *wp, float *acc, float *cost,
 		       float *oldacc_out, int *perm);
 
-/* Run-time options: "acc_double" (1: FP64 acceleration accumulators, default; 0: FP32), "rank", "nranks", "walk_group",
+/* Run-time options: "rank", "nranks" (equal target slices, boundaries at multiples of 32),
+ * "walk_exact" (1, default: targets that meet a decision within FP32 rounding of its threshold are walked again in the reference's
+ * double arithmetic, so GravCost is the reference's exactly; 0: FP32 decisions only), "acc_double" (1: FP64 acceleration accumulators,
+ * default; 0: FP32 accumulators, implies walk_exact 0), "walk_stats" (1: instrumented walk kernel, fills counters[2..4] of g2gpu_timings),
+ * "compact" (1: the walk stores the results of this rank's slice in target order for g2gpu_download_slice instead of by particle index),
  * "direct_ewald" (1: g2gpu_direct adds the exact periodic lattice correction),
- * "walk_mode" (0: one walk cursor per 32 targets, default; 1: one warp per target over level-order records, experimental),
  * "accumulator" (1 = the reference built with -DNGRAVS_ACCUMULATOR; takes effect at the next g2gpu_treebuild). */
 int g2gpu_set_option(g2gpu_ctx *ctx, const char *name, int value);
+
+/* ---- several GPUs of one node behind the same entry points: the parallel driver inside gravity_tree() (gravtree.c:102-285: export,
+ *      walk, import), as ONE host process with one context, stream and host thread per device (csrc/g2_group.cu).  Every device
+ *      uploads its 1/N of the particle records, one ncclAllGather over NVLink replicates them, every device builds the same tree and
+ *      walks one slice of the Peano-Hilbert-ordered active targets (slices of equal GravCost of the previous call, domain.c:859-862;
+ *      boundaries at multiples of 32 targets, so results are bit-identical for any device count), and returns only its slice.
+ *      ndev <= 0: all visible devices; devices == NULL: 0..ndev-1; cfg->device/rank/nranks are set per device.  With one device no
+ *      NCCL is needed (it is resolved at run time).  Stage calls mirror the single-context ones; tables and options go to every
+ *      device; anything not listed (tree mirror, potential, PM, direct sums) is served by g2gpu_group_ctx(grp, 0). ---- */
+typedef struct g2gpu_group g2gpu_group;
+int g2gpu_group_create(g2gpu_group **grp, const g2gpu_config *cfg, int ndev, const int *devices);
+void g2gpu_group_destroy(g2gpu_group *grp);
+int g2gpu_group_size(g2gpu_group *grp);
+g2gpu_ctx *g2gpu_group_ctx(g2gpu_group *grp, int i);
+int g2gpu_group_set_species(g2gpu_group *grp, const int type_to_grav[G2GPU_NTYPES], const double force_softening[G2GPU_NTYPES]);
+int g2gpu_group_set_laws(g2gpu_group *grp, const int *accel_id, const int *spline_id, const double *params);
+int g2gpu_group_set_srtable(g2gpu_group *grp, const double *table);
+int g2gpu_group_set_lattice_tables(g2gpu_group *grp, int en, const double *fcorr);
+/* the options of g2gpu_set_option on every device, plus "cost_weighted" (1, default: slices of equal GravCost; 0: equal counts) */
+int g2gpu_group_set_option(g2gpu_group *grp, const char *name, int value);
+/* sharded H2D (device i copies records [i*per, (i+1)*per), per = ceil(npart / N)) + ncclAllGather; arguments as g2gpu_upload[_aos] */
+int g2gpu_group_upload(g2gpu_group *grp, int npart, const float *pos, const float *mass, const int *type, const float *oldacc, const int *active);
+int g2gpu_group_upload_aos(g2gpu_group *grp, int npart, const void *P, size_t stride, int float_bytes, int off_pos, int off_mass, int off_type,
+			   int off_oldacc, int off_vel, int off_gravpm, int off_ti_endstep, int ti_current);
+/* device-resident inputs: every device already holds ITS shard (g2gpu_group_shard) inside its input buffer (g2gpu_input_buffers of
+ * g2gpu_group_ctx(grp, i), record offset lo); only the all-gather runs */
+int g2gpu_group_gather_resident(g2gpu_group *grp, int npart);
+int g2gpu_group_shard(g2gpu_group *grp, int npart, int i, int *lo, int *cnt);
+int g2gpu_group_domain(g2gpu_group *grp);
+int g2gpu_group_treebuild(g2gpu_group *grp, int *numnodes);
+int g2gpu_group_update_tree(g2gpu_group *grp, const float *len, const float *s);
+int g2gpu_group_walk(g2gpu_group *grp, const g2gpu_walk_params *wp);
+/* slice downloads + host scatter: SoA in CURRENT (device) order like g2gpu_download_acc, or into the reference's P[]: P[perm[p]] for device
+ * index p (perm == NULL: P[] is in device order); float_bytes = sizeof(FLOAT) of GravAccel and OldAcc, GravCost is a float (allvars.h:572);
+ * off_gravcost / off_oldacc may be -1; *cost_sum = sum of GravCost over the targets */
+int g2gpu_group_download_acc(g2gpu_group *grp, float *acc, float *cost, float *oldacc);
+int g2gpu_group_download_aos(g2gpu_group *grp, void *P, size_t stride, int float_bytes, int off_gravaccel, int off_gravcost, int off_oldacc,
+			     const int *perm, double *cost_sum);
+int g2gpu_group_get_order(g2gpu_group *grp, int *perm);
+/* whole step with host buffers (the e2e path), arguments as g2gpu_gravity_tree; one host thread per device runs its whole pipeline */
+int g2gpu_group_gravity_tree(g2gpu_group *grp, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
+			     const int *active, const g2gpu_walk_params *wp, float *acc, float *cost, float *oldacc_out, int *perm);
+int g2gpu_group_sync(g2gpu_group *grp);
+int g2gpu_group_timings(g2gpu_group *grp, double ms[8], long long counters[8]);	/* times: max over devices; counters: sums */
+int g2gpu_group_io_bytes(g2gpu_group *grp, long long out[3]);	/* H2D, D2H (all devices), bytes received per device by the all-gather */
+int g2gpu_group_slices(g2gpu_group *grp, int *lo, int *hi, double *next_frac);	/* last walk's slices [N]; next walk's boundaries [N+1] */
 
 /* ---- instrumentation ---- */
 /* CUDA-event times (ms) of the last call of each stage: [0] domain [1] treebuild [2] walk
  * [3] walk kernel only [4] sort kernels of stage 1 [5] H2D [6] D2H [7] g2gpu_pm_periodic; counters[0] = kernel launches since
  * g2gpu_reset_counters, [1] = sum of GravCost of the last walk (this rank's targets), [2] = cell visits summed
  * over warps, [3] = species terms evaluated (one per particle interaction, <= D per node interaction), [4] = opening decisions
- * (node visits summed over the targets that were awake at the visit), [5..7] reserved (0). */
+ * (node visits summed over the targets that were awake at the visit) -- [2..4] only with the option "walk_stats" --, [5] = targets
+ * whose walk was repeated in FP64 because a decision was borderline in FP32 (option "walk_exact"), [6..7] reserved (0). */
 int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[8]);
 void g2gpu_reset_counters(g2gpu_ctx *ctx);
 int g2gpu_io_bytes(g2gpu_ctx *ctx, long long out[2]);	/* host->device / device->host bytes of the last upload / download */

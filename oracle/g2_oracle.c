@@ -1707,8 +1707,19 @@ static int node_decision(g2o * o, const particle * tp, const node * nop)	/* 0 cu
 }
 
 /* order[] = targets in depth-first tree order (filled by following nextnode from the root) */
+/* design aid: deferred dense evaluation of the accepted terms.  Every accepted species term / particle term is staged in a ring of
+ * g2o_sim_ring term sources shared by the group and appended to the accepting member's list; when the ring is full all lists are
+ * evaluated (one term per member per pass).  out[14] = passes per group, out[15] = member terms per group. */
+int g2o_sim_ring = 128;
+int g2o_sim_order = 0; int *g2o_sim_custom_order = 0;	/* 0 = depth-first tree order, 1 = Peano-Hilbert key order of all species */
+double g2o_group_visits[4096];
+static g2o *cmp_o_;
+static int cmp_phkey_(const void *a, const void *b) { peanokey ka = cmp_o_->P[*(const int *) a].key, kb = cmp_o_->P[*(const int *) b].key; return ka < kb ? -1 : ka > kb; }
+double g2o_hist_awake[65], g2o_hist_open[65], g2o_hist_awake_w[65];
 void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 {
+  double sim_passes = 0, sim_terms = 0; int sim_staged = 0; int *sim_n = calloc(gsize, sizeof(int));
+#define SIM_FLUSH() do { int mx_ = 0, m_; for(m_ = 0; m_ < gsize; m_++) { if(sim_n[m_] > mx_) mx_ = sim_n[m_]; sim_terms += sim_n[m_]; sim_n[m_] = 0; } sim_passes += mx_; sim_staged = 0; } while(0)
   const int MP = o->maxpart, n = o->n;
   int *order = malloc(sizeof(int) * n), *skip = malloc(sizeof(int) * gsize);
   int no = MP, cnt = 0, gi, ngroups = 0;
@@ -1725,6 +1736,8 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
       else
 	no = NODE_OF(o, no)->nextnode;
     }
+  if(g2o_sim_order == 1) { cmp_o_ = o; qsort(order, n, sizeof(int), cmp_phkey_); }
+  if(g2o_sim_order == 2 && g2o_sim_custom_order) memcpy(order, g2o_sim_custom_order, sizeof(int) * n);
   /* pre-order rank of every node/particle to implement "sleep until the cursor leaves the subtree" */
   {
     int stride = n / (gsize * ngroups_max);
@@ -1732,10 +1745,11 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
       stride = 1;
     for(gi = 0; gi + gsize <= n && ngroups < ngroups_max; gi += gsize * stride, ngroups++)
       {
-	int m, cur = MP;
+	int m, cur = MP; double v0_ = visits;
 	/* skip[m] = node index at which member m wakes up again (-2 = awake) */
 	for(m = 0; m < gsize; m++)
 	  skip[m] = -2;
+	    SIM_FLUSH();
 	while(cur >= 0)
 	  {
 	    if(cur < MP)
@@ -1750,6 +1764,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		  }
 		pvis += 1;
 		pawake += na;
+		    if(na) { for(m = 0; m < gsize; m++) if(skip[m] == -2) sim_n[m]++; if(++sim_staged >= g2o_sim_ring) SIM_FLUSH(); }
 		ppasses += (na + 31) / 32;
 		cur = o->nextnode[cur];
 		continue;
@@ -1777,6 +1792,7 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 			    {
 			      accepts += 1;
 			      nacc++;
+				  sim_n[m] += o->D;
 			    }
 			  else
 			    ncull++;
@@ -1785,6 +1801,8 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		}
 	      visits += 1;
 	      awake += na;
+		  if(gsize <= 64) { g2o_hist_awake[na] += 1; g2o_hist_open[nopen] += 1; }
+		  if(nacc) { sim_staged += o->D; if(sim_staged >= g2o_sim_ring) SIM_FLUSH(); }
 	      passes += (na + 31) / 32;
 	      opens += nopen;
 	      culls += ncull;
@@ -1811,6 +1829,8 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
 		  skip[m] = -2;
 	    }
 	  }
+	if(ngroups < 4096)
+	  g2o_group_visits[ngroups] = visits - v0_;
       }
   }
   out[0] = ngroups;
@@ -1827,6 +1847,10 @@ void g2o_groupwalk_stats(g2o * o, int gsize, int ngroups_max, double *out)
   out[11] = culls / ngroups;
   out[12] = passes / ngroups;	/* 32-lane passes if awake members are packed onto lanes */
   out[13] = ppasses / ngroups;
+  SIM_FLUSH();
+  out[14] = sim_passes / ngroups;
+  out[15] = sim_terms / ngroups;
+  free(sim_n);
   free(skip);
   free(order);
 }
