@@ -106,7 +106,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->d_depth, (size_t) 64);
   rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
   rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
-  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256);
+  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256); rc |= dalloc(&c->redo_list, (size_t) G2_REDO_CAP);
   if(rc)
     {
       g2gpu_destroy(c);
@@ -141,7 +141,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->redo_list, c->cres };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -735,9 +735,9 @@ extern "C" int g2gpu_set_potential_laws(g2gpu_ctx *c, const int *pot_id, const i
   const int D = c->D;
   for(int i = 0; i < D * D; i++)
     {
-      if(pot_id[i] < G2GPU_POT_NONE || pot_id[i] > G2GPU_POT_NEG_NEWTONIAN)	// ngravs_core.c:348-358: every slot must be wired
+      if(pot_id[i] < G2GPU_POT_NONE || pot_id[i] > G2GPU_POT_SOURCEBAMBARYON)	// ngravs_core.c:348-358: every slot must be wired
 	return g2_fail(G2GPU_ERR_LAW, "PotentialFxns[%d][%d] is not a registered potential (%d)", i / D, i % D, pot_id[i]);
-      if(potspline_id[i] < G2GPU_POTSPLINE_NONE || potspline_id[i] > G2GPU_POTSPLINE_NEG_PLUMMER)
+      if(potspline_id[i] < G2GPU_POTSPLINE_NONE || potspline_id[i] > G2GPU_POTSPLINE_SOURCEBAMBARYON)
 	return g2_fail(G2GPU_ERR_LAW, "PotentialSplines[%d][%d] is not a registered potential spline (%d)", i / D, i % D, potspline_id[i]);
       c->potfxn[i] = pot_id[i];
       c->potspline[i] = potspline_id[i];
@@ -935,8 +935,25 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[8])
 	  counters[2] = (long long) c->h_counters[1];
 	  counters[3] = (long long) c->h_counters[2];
 	  counters[4] = (long long) c->h_counters[4];
-	  counters[5] = (long long) c->h_counters[5];	// targets re-walked in FP64 (borderline decisions)
+	  counters[5] = (long long) c->h_counters[5];	// targets walked again in FP64 (an FP32 decision differed from the reference's)
+	  counters[6] = (long long) c->h_counters[7];	// borderline comparisons that were checked in FP64
 	}
+    }
+  return 0;
+}
+
+extern "C" int g2gpu_get_counts(g2gpu_ctx *c, int out[4])
+{
+  if(!c || !out)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  out[0] = c->npart;
+  out[1] = c->stage >= 3 ? c->numnodes : 0;
+  out[2] = 0;
+  out[3] = c->stage;
+  if(c->stage >= 4)
+    {
+      G2_TRY(g2_fetch_slice(c));
+      out[2] = c->w_ntargets;
     }
   return 0;
 }
@@ -992,4 +1009,13 @@ extern "C" int g2gpu_eval_pairs(g2gpu_ctx *c, int n, int tgt, int src, const flo
     return g2_fail(G2GPU_ERR_ARG, "bad argument");
   G2_CUDA(cudaSetDevice(c->cfg.device));
   return g2_eval_pairs_standalone(c, n, tgt, src, pm, m, r, h, npart_in_node, fac);
+}
+
+extern "C" int g2gpu_eval_potentials(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+				     const int *npart_in_node, float *out)
+{
+  if(!c || !pm || !m || !r || !h || !out || n < 1 || tgt < 0 || src < 0 || tgt >= c->D || src >= c->D)
+    return g2_fail(G2GPU_ERR_ARG, "bad argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_eval_potentials_standalone(c, n, tgt, src, pm, m, r, h, npart_in_node, out);
 }

@@ -10,6 +10,7 @@
 #define G2_MAXDEPTH 21		// 3*21 = 63 key bits: deepest supported octree level below the root
 #define G2_PH_BITS 18		// BITS_PER_DIMENSION (allvars.h:34)
 #define G2_NSM_FALLBACK 148
+#define G2_REDO_CAP 65536		// targets per walk that may be walked again in the reference's double arithmetic
 #ifndef G2_DEFAULT_WALK_MODE
 #define G2_DEFAULT_WALK_MODE 0
 #endif
@@ -216,6 +217,7 @@ struct g2gpu_ctx
   int w_lo, w_hi;		// this rank's slice of w_targets (host copies, valid after g2_fetch_slice)
   int *d_slice, *h_slice;	// [G2_SLICE_*] on the device / pinned
   void *d_exact;		// WalkExactParams of the current walk
+  unsigned int *redo_list;	// targets walked again in FP64 (G2_REDO_CAP slots)
   int slice_pending;
   float *acc;			// 3n, current particle order
   float *cost;			// n
@@ -265,6 +267,8 @@ int g2_export_extnodes(g2gpu_ctx *c, float *vs);
 int g2_export_tree(g2gpu_ctx *c, float *len, float *center, float *s, float *mass, int *bitflags, int *sibling,
 		   int *nextnode, int *father, int *p_nextnode, int *p_father);
 int g2_peano_keys_standalone(g2gpu_ctx *c, int n, const int *xyz, int bits, long long *keys);
+int g2_eval_potentials_standalone(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+				  const int *nn, float *out);
 int g2_eval_pairs_standalone(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r,
 			     const float *h, const int *nn, float *fac);
 

@@ -652,7 +652,29 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
   return 0;
 }
 
-// ms[8] / counters[8] like g2gpu_timings: times are the MAXIMUM over the devices, counters the SUM (launches: device 0)
+// One step with device-resident inputs (benchmarks: `value` of bench.py): all-gather of the resident shards -> domain -> treebuild ->
+// walk, one host thread per device running its whole pipeline; results stay on the devices.
+extern "C" int g2gpu_group_step_resident(g2gpu_group *g, int npart, const g2gpu_walk_params *wp)
+{
+  if(!g || !wp)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_TRY(group_begin_upload(g, npart));
+  G2_TRY(run_all(g, [&](int i) {
+    g2gpu_ctx *c = g->ctx[i];
+    G2_TRY(g2gpu_inputs_ready(c, npart));
+    G2_TRY(group_allgather(g, i, 0));
+    G2_TRY(g2_stage_domain(c));
+    G2_TRY(g2_stage_treebuild(c));
+    c->slice_explicit = 1;
+    c->slice_frac[0] = g->frac[i];
+    c->slice_frac[1] = g->frac[i + 1];
+    return g2_stage_walk(c, wp);
+  }));
+  g->gather_bytes = g->n > 1 ? (long long) g->per * g->n * (long long) sizeof(G2PRec) : 0;
+  return 0;
+}
+
+// ms[8] / counters[8] like g2gpu_timings: times are the MAXIMUM over the devices, counters the SUM
 extern "C" int g2gpu_group_timings(g2gpu_group *g, double ms[8], long long counters[8])
 {
   if(!g)
@@ -672,7 +694,7 @@ extern "C" int g2gpu_group_timings(g2gpu_group *g, double ms[8], long long count
 	{
 	  counters[k] = 0;
 	  for(int i = 0; i < g->n; i++)
-	    counters[k] += (k == 0 && i > 0) ? 0 : cn[i][k];
+	    counters[k] += cn[i][k];
 	}
     }
   return 0;

@@ -44,6 +44,8 @@ struct PotArgs
   int t2g[6];
   unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   int potfxn[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS], potspline[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  float bam_eps[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// BAM_EPSILON (ngravs.c:45), from the parameters of g2gpu_set_laws
+  const unsigned int *__restrict__ cnt;	// particle counts per species of every cell (NGRAVS_ACCUMULATOR), or null
 };
 
 // plummer_pot, ngravs.c:459-471 (u = r/h)
@@ -55,9 +57,29 @@ __device__ __forceinline__ float pot_plummer(float m, float h, float r)
   return m * hinv * (-3.2f + 0.066666666667f / u + u * u * (10.666666666667f + u * (-16.0f + u * (9.6f - 2.133333333333f * u))));
 }
 
+// BAM family, ngravs.c:672-760 (bambam_pot, sourcebaryonbam_pot, sourcebambaryon_pot): rho * atan(r eta) / r with a 7th-order Taylor
+// form for r eta < 0.1; eta depends on which side is the BAM halo.  Wired as PotentialFxns AND PotentialSplines (ngravs.c:198-200).
+// Evaluated in FP64 like the BAM force laws (g2_laws.cuh) and rounded once.
+__device__ __forceinline__ float pot_bam(int id, float eps, float pm, float m, float r, float nn)
+{
+  const double rho = 2.0 * (double) pm * (double) m / 3.14159265358979323846;
+  double eta;
+  if(id == G2GPU_POT_BAMBAM)
+    eta = 4.0 * 3.14159265358979323846 * (double) eps / ((double) pm + (double) m / (double) nn);	// ngravs.c:685
+  else if(id == G2GPU_POT_SOURCEBARYONBAM)
+    eta = 4.0 * (double) eps * 3.14159265358979323846 * (double) nn / (double) pm;	// ngravs.c:715
+  else
+    eta = 4.0 * (double) eps * 3.14159265358979323846 * (double) nn / (double) m;	// ngravs.c:741
+  const double reta = (double) r * eta, reta2 = reta * reta, reta4 = reta2 * reta2;
+  if(reta < 0.1)
+    return (float) (rho * eta * (1.0 - reta2 / 3.0 + reta4 / 5.0 - reta2 * reta4 / 7.0));
+  return (float) (rho * atan(reta) / (double) r);
+}
+
 // one species term; returns the amount to ADD to pot
 template <bool SR>
-__device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restrict__ s_tab, int ij, float m, float r2, float h, bool table_term)
+__device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restrict__ s_tab, int ij, float m, float r2, float h, bool table_term,
+					  float pm = 0.0f, float nn = 1.0f)
 {
   const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   const float r = r2 * rinv;
@@ -75,6 +97,9 @@ __device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restr
 	{
 	case G2GPU_POT_NEWTONIAN: p = m * rinv; break;	// ngravs.c:368
 	case G2GPU_POT_NEG_NEWTONIAN: p = -m * rinv; break;	// ngravs.c:375
+	case G2GPU_POT_BAMBAM:
+	case G2GPU_POT_SOURCEBARYONBAM:
+	case G2GPU_POT_SOURCEBAMBARYON: p = pot_bam(A.potfxn[ij], A.bam_eps[ij], pm, m, r, nn); break;
 	default: p = 0.0f; break;	// none, ngravs.c:344
 	}
       if(SR && table_term)
@@ -85,6 +110,10 @@ __device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restr
     {
     case G2GPU_POTSPLINE_PLUMMER: return pot_plummer(m, h, r);	// ngravs.c:459
     case G2GPU_POTSPLINE_NEG_PLUMMER: return -pot_plummer(m, h, r);	// ngravs.c:476
+    case G2GPU_POTSPLINE_BAMBAM:
+    case G2GPU_POTSPLINE_SOURCEBARYONBAM:
+    case G2GPU_POTSPLINE_SOURCEBAMBARYON:	// the reference ADDS the "spline" (forcetree.c:2734, 3118), also when it is wired to a *_pot function
+      return pot_bam(A.potspline[ij] - G2GPU_POTSPLINE_BAMBAM + G2GPU_POT_BAMBAM, A.bam_eps[ij], pm, m, r, nn);
     default: return 0.0f;
     }
 }
@@ -127,13 +156,13 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
       const int ti = A.lo + (int) chunk * 32 + lane;
       const bool valid = ti < A.hi;
       unsigned int idx = 0;
-      float px = 0, py = 0, pz = 0, aold = 0;
+      float px = 0, py = 0, pz = 0, aold = 0, pmass = 0;
       int ptype = 1;
       if(valid)
 	{
 	  idx = A.order[ti];
 	  const G2PRec p = A.prec[idx];
-	  px = p.x; py = p.y; pz = p.z;
+	  px = p.x; py = p.y; pz = p.z; pmass = p.m;
 	  ptype = p.type;
 	  aold = A.errtol * p.oldacc;	// forcetree.c:2830
 	}
@@ -236,7 +265,8 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 #pragma unroll
 		      for(int g = 0; g < D; g++)
 			if(mass[g] != 0.0f)	// forcetree.c:3123
-			  fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0);
+			  fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0, pmass,
+					       A.cnt ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f);
 		    }
 		}
 	    }
@@ -259,7 +289,7 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 		      const float dx = POT_WRAP(p.x - px, shx);
 		      const float dy = POT_WRAP(p.y - py, shy);
 		      const float dz = POT_WRAP(p.z - pz, shz);
-		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true);
+		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true, pmass, 1.0f);
 		    }
 		}
 	      cur = cur + 1u;
@@ -337,6 +367,9 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   memcpy(A.tabmap, c->pot_tabmap, sizeof(A.tabmap));
   memcpy(A.potfxn, c->potfxn, sizeof(A.potfxn));
   memcpy(A.potspline, c->potspline, sizeof(A.potspline));
+  for(int i = 0; i < D * D; i++)
+    A.bam_eps[i] = c->laws_set ? c->laws.par[i][1] : 1.31e-6f;
+  A.cnt = (c->accumulator && c->counts_valid) ? c->wcnt : nullptr;
   const size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
   int grid = c->nsm * POT_BLOCKS(D), need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
   if(grid > need)
@@ -367,5 +400,50 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   cudaEventElapsedTime(&ms, c->ev[16], c->ev[17]);
   c->pot_ms = ms;
   c->pot_valid = 1;
+  return 0;
+}
+
+// ---------------------------------------------------------------- stand-alone pair potentials (tests) -----------
+// out[i] = what the potential walk ADDS to pot for one pair without the TreePM table term: -PotentialFxns[tgt][src](pm, m, h, r, N) for
+// r >= h, +PotentialSplines[tgt][src](pm, m, h, r, N) for r < h (forcetree.c:2732-2734, 3115-3118), in the kernel's own arithmetic.
+__global__ void eval_pot_kernel(const PotArgs A, int n, int ij, const float *__restrict__ pm, const float *__restrict__ m, const float *__restrict__ r,
+				const float *__restrict__ h, const int *__restrict__ nn, float *__restrict__ out)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+    out[i] = pot_term<false>(A, nullptr, ij, m[i], r[i] * r[i], h[i], false, pm[i], nn ? (float) nn[i] : 1.0f);
+}
+
+int g2_eval_potentials_standalone(g2gpu_ctx *c, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+				  const int *nn, float *out)
+{
+  if(!c->potlaws_set)
+    return g2_fail(G2GPU_ERR_LAW, "pair potential laws not set (g2gpu_set_potential_laws)");
+  PotArgs A;
+  memset(&A, 0, sizeof(A));
+  memcpy(A.potfxn, c->potfxn, sizeof(A.potfxn));
+  memcpy(A.potspline, c->potspline, sizeof(A.potspline));
+  for(int i = 0; i < c->D * c->D; i++)
+    A.bam_eps[i] = c->laws_set ? c->laws.par[i][1] : 1.31e-6f;
+  float *d;
+  int *dn = nullptr;
+  const size_t fb = sizeof(float) * (size_t) n;
+  G2_CUDA(cudaMalloc(&d, 5 * fb));
+  G2_CUDA(cudaMemcpy(d, pm, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + n, m, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + 2 * (size_t) n, r, fb, cudaMemcpyHostToDevice));
+  G2_CUDA(cudaMemcpy(d + 3 * (size_t) n, h, fb, cudaMemcpyHostToDevice));
+  if(nn)
+    {
+      G2_CUDA(cudaMalloc(&dn, sizeof(int) * (size_t) n));
+      G2_CUDA(cudaMemcpy(dn, nn, sizeof(int) * (size_t) n, cudaMemcpyHostToDevice));
+    }
+  eval_pot_kernel<<<g2_cdiv(n, 256), 256, 0, c->stream>>>(A, n, tgt * c->D + src, d, d + n, d + 2 * (size_t) n, d + 3 * (size_t) n, dn, d + 4 * (size_t) n);
+  c->launches++;
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  G2_CUDA(cudaMemcpy(out, d + 4 * (size_t) n, fb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  if(dn)
+    cudaFree(dn);
   return 0;
 }

@@ -124,14 +124,16 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
   A.cres = c->compact ? c->cres : nullptr;
   // the scan scratch is free once the slice is known: one slot per target for the FP64 re-walk list
-  A.redo_list = c->w_flags; A.redo_count = (unsigned int *) (c->d_counters + 6);
+  A.border_list = (uint4 *) c->w_flags; A.border_count = (unsigned int *) (c->d_counters + 6); A.border_cap = (unsigned int) (c->cfg.max_part / 4);
+  A.redo_list = c->redo_list; A.redo_count = (unsigned int *) (c->d_counters + 6) + 1; A.redo_cap = G2_REDO_CAP;
   A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;
   A.theta2 = (float) (wp->theta * wp->theta);
   A.errtol = (float) wp->errtol_force_acc;
   A.ex = (const WalkExactParams *) c->d_exact;
   A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
-  // guard bands of the FP32 decisions (g2_walk_kernel.cuh): relative 2e-6, an order of magnitude above the accumulated FP32 rounding
-  A.rel_tol = 2.0e-6f;
+  // guard bands of the FP32 decisions (g2_walk_kernel.cuh): relative 1e-6 per compared quantity (2e-6 for the fourth-power criterion), several
+  // times the accumulated FP32 rounding of a comparison (a few 1e-7)
+  A.rel_tol = 1.0e-6f;
   A.pos_ulp8 = (per || sr) ? (float) (8.0 * wp->boxsize * 1.1920929e-7) : 0.0f;	// per-point NEAREST: raw differences of box-scale magnitude
   A.pos_border = 0.0f;
   A.exact = c->walk_exact;
@@ -143,15 +145,12 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
       const double rmax = c->cfg.ntab / asmthfac_d;
       A.rmax2 = (float) (rmax * rmax);
-      A.rmax2_border = (float) (rmax * rmax * 2.0e-6);
-      A.rcut2_border = (float) (wp->rcut * wp->rcut * 2.0e-6);
-      A.pos_border = (float) (4.0e-6 * wp->rcut);	// box cull: |max |d| - (rcut + len/2)|, both sides of order rcut
+      A.rmax2_border = (float) (rmax * rmax * 1.0e-6);
+      A.rcut2_border = (float) (wp->rcut * wp->rcut * 1.0e-6);
       // a tree that follows the host's drifted nodes (g2gpu_update_tree) may hold centres of mass outside their cubes: neither the
       // geometric cull shortcut nor the per-cell image shift may then be used
       A.shift_len_max = c->tree_dynamic ? 0.0f : (float) (0.499 * wp->boxsize - 1.001 * wp->rcut);
       A.cull_margin = c->tree_dynamic ? 3.0e38f : (float) (1.0e-5 * wp->boxsize);
-      if(A.pos_border > 0.5f * A.cull_margin)
-	A.pos_border = 0.5f * A.cull_margin;
     }
   A.G = wp->G; A.pos_fac_pre_g = wp->pos_fac_pre_g; A.pos_fac_post_g = wp->pos_fac_post_g;
   A.use_gravpm = wp->use_gravpm && c->have_gravpm;

@@ -65,8 +65,12 @@ struct WalkArgs
   float rel_tol, pos_ulp8;	// relative tolerance of r^2-based criteria: rel_tol + pos_ulp8 / r
   double G, pos_fac_pre_g, pos_fac_post_g;
   const WalkExactParams *__restrict__ ex;
-  unsigned int *__restrict__ redo_list;	// slice ordinals of the targets that met a borderline comparison (one slot per target of the slice)
+  uint4 *__restrict__ border_list;	// noted borderline comparisons: slice ordinal of the target, cell / particle index, FP32 outcome
+  unsigned int *__restrict__ border_count;
+  unsigned int border_cap;
+  unsigned int *__restrict__ redo_list;	// slice ordinals of the targets whose FP32 walk deviated from the reference's decisions
   unsigned int *__restrict__ redo_count;
+  unsigned int redo_cap;
   int use_gravpm;
   int exact;			// 0: no FP64 re-evaluation (FP32 decisions only)
   float fsoft[6];

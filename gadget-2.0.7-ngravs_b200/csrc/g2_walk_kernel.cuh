@@ -70,7 +70,7 @@ __device__ __forceinline__ int walk_decide_exact(const WalkExactParams *__restri
   const double theta = E->theta;
   if(theta != 0.0)
     {				// forcetree.c:1865-1873
-      if(__dmul_rn(len, len) > __dmul_rn(__dmul_rn(r2min, theta), theta))
+      if((double) __fmul_rn(q0.x, q0.x) > __dmul_rn(__dmul_rn(r2min, theta), theta))	// nop->len * nop->len is a FLOAT product (forcetree.c:1867)
 	return G2_DEC_OPEN;
     }
   else
@@ -120,6 +120,14 @@ struct WalkShift
   float tx, ty, tz;		// target coordinate + min(shift, 0)
 };
 
+// A comparison fell inside its guard band: the FP32 decision is applied and noted in the lane state (one event per walk, a second one
+// turns it into G2_EVT_SEVERAL); the walk's epilogue hands it to walk_verify_kernel.  kind: the FP32 decision of a cell visit, or a
+// term event with the FP32 in-range bit.  Rare: a few per thousand targets.
+#define G2_EVT_NODE_TERM 0x10000
+#define G2_EVT_PART_TERM 0x20000
+#define G2_EVT_SEVERAL 0x40000	// more than one borderline comparison in one walk: the target is walked again without further ado
+#define G2_EVT_DECISION 0x80000	// | FP32 decision
+
 // per-lane state of a walk
 struct WalkLane
 {
@@ -127,7 +135,8 @@ struct WalkLane
   int tg;
   float fx, fy, fz;		// FP32 partial sums, flushed into the accumulators whenever the warp descends
   int ninter, nterms, ndec;
-  int border;			// a comparison fell inside its guard band: the target goes to walk_redo_kernel
+  int evt_kind;			// borderline comparison met during this walk (0: none), and where (cell or particle record)
+  unsigned int evt_where;
   unsigned int skip_until;
 };
 
@@ -167,11 +176,11 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
       // target that clears the cube by a small margin on one axis is farther than rcut from every centre of mass:
       // r2min > rcut^2 is then certain and the per-species distances need not be computed at all.
       const float d0 = fabsf(WRAP ? (q0.y - S.sx) - S.tx : cxr), d1 = fabsf(WRAP ? (q0.z - S.sy) - S.ty : cyr), d2 = fabsf(WRAP ? (q0.w - S.sz) - S.tz : czr);
-      const float t = fmax3(d0, d1, d2) - fmaf(0.5f, len, A.rcut);
+      const float eff = fmaf(0.5f, len, A.rcut), t = fmax3(d0, d1, d2) - eff;
       outside = t > 0.0f;
       done = t > fmaf(1.0e-3f, len, A.cull_margin);
       if(EXACT)
-	border = fabsf(t) < A.pos_border;
+	border = fabsf(t) < A.rel_tol * eff;
     }
   if(!done)
     {
@@ -256,7 +265,10 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	}
     }
   if(EXACT && border)
-    L.border = 1;
+    {
+      L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_DECISION | (done ? G2_DEC_CULL : (open ? G2_DEC_OPEN : G2_DEC_ACCEPT)));
+      L.evt_where = cur;
+    }
   if(!open)
     {
       L.skip_until = w.x;	// sleep until the cursor leaves this subtree
@@ -271,7 +283,10 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 		{
 		  const float tv = r2[g] - A.rmax2;
 		  if(EXACT && fabsf(tv) < A.rmax2_border)
-		    L.border = 1;
+		    {
+		      L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_NODE_TERM | (g << 8) | (tv < 0.0f ? 1 : 0));
+		      L.evt_where = cur;
+		    }
 		  counted = counted && tv < 0.0f;
 		}
 	      const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
@@ -333,7 +348,10 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 	      const float tv = rr2 - A.rmax2;
 	      counted = tv < 0.0f;
 	      if(EXACT && fabsf(tv) < A.rmax2_border)
-		L.border = 1;
+		{
+		  L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_PART_TERM | (counted ? 1 : 0));
+		  L.evt_where = w.y + j;
+		}
 	    }
 	  pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz);
 	  L.ninter += counted;
@@ -398,6 +416,9 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 {
   extern __shared__ float s_tab[];
   __shared__ unsigned int s_chunk[WALK_WARPS];
+  // the FP64 accumulators of a lane live in shared memory (touched only when the warp descends, about every third visit): six
+  // registers less keeps the kernel at 64 registers without spills
+  __shared__ ACC s_acc[3][WALK_THREADS];
   if(SR)
     {
       for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
@@ -445,9 +466,10 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       L.hself = A.fsoft[ptype];
       L.fx = L.fy = L.fz = 0.0f;
       L.ninter = L.nterms = L.ndec = 0;
-      L.border = 0;
+      L.evt_kind = 0;
+      L.evt_where = 0u;
       L.skip_until = valid ? 0u : 0xffffffffu;
-      ACC ax = 0, ay = 0, az = 0;
+      s_acc[0][threadIdx.x] = 0; s_acc[1][threadIdx.x] = 0; s_acc[2][threadIdx.x] = 0;
       unsigned int iter = 0;
       unsigned int cur = __any_sync(0xffffffffu, valid) ? 0u : end;
       // TreePM: a target farther than rcut + len/2 (+ margins) from every face of the box needs no periodic image of a cell of size len:
@@ -486,7 +508,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	    {
 	      // FP32 partial sums go into the (FP64) accumulators whenever the warp descends (about every third visit): few
 	      // conversions, bounded error, and flush points that depend on the traversal only (=> reproducible bits)
-	      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+	      s_acc[0][threadIdx.x] += (ACC) L.fx; s_acc[1][threadIdx.x] += (ACC) L.fy; s_acc[2][threadIdx.x] += (ACC) L.fz;
 	      L.fx = L.fy = L.fz = 0.0f;
 	      if(PERIODIC && wrapv)
 		walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
@@ -498,20 +520,18 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	    cur = w.x;
 	}
 
-      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+      const ACC ax = s_acc[0][threadIdx.x] + (ACC) L.fx, ay = s_acc[1][threadIdx.x] + (ACC) L.fy, az = s_acc[2][threadIdx.x] + (ACC) L.fz;
       if(STATS && lane == 0)
 	tot_visits += iter;	// one cursor per warp: visits = loop trips
       if(valid)
 	{
-	  if(EXACT && L.border)
-	    {			// walk_redo_kernel writes this target's result (the list has one slot per target of the slice)
-	      const unsigned int slot = atomicAdd(A.redo_count, 1u);
-	      A.redo_list[slot] = (unsigned int) tloc;
-	    }
-	  else
-	    {
-	      walk_store_result<SR, PERIODIC>(A, idx, tloc, L.px, L.py, L.pz, (float) ax, (float) ay, (float) az, (float) L.ninter);
-	      tot_inter += (unsigned long long) L.ninter;
+	  walk_store_result<SR, PERIODIC>(A, idx, tloc, L.px, L.py, L.pz, (float) ax, (float) ay, (float) az, (float) L.ninter);
+	  tot_inter += (unsigned long long) L.ninter;
+	  if(EXACT && L.evt_kind)
+	    {			// to walk_verify_kernel
+	      const unsigned int slot = atomicAdd(A.border_count, 1u);
+	      if(slot < A.border_cap)
+		A.border_list[slot] = make_uint4((unsigned int) tloc, L.evt_where, (unsigned int) L.evt_kind, 0u);
 	    }
 	  if(STATS)
 	    {
@@ -544,28 +564,67 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
     }
 }
 
-// ---- the walk of the targets the FP32 kernel flagged, one thread per target, in the reference's own arithmetic: double locals,
-//      FLOAT node and particle fields, decisions by walk_decide_exact, tabindex = (int) (asmthfac * r) (forcetree.c:1244-1610 and
-//      1623-2052 restated over the depth-first records).  The pair laws keep their FP32 device forms; sums are FP64. ----
-#define WALK_REDO_THREADS 64
+// ---- every noted borderline comparison again in the reference's own double arithmetic: where the answer differs from the FP32 one
+//      that was applied, the target goes on the re-walk list (a handful per million targets) ----
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL>
+__global__ void __launch_bounds__(128) walk_verify_kernel(const WalkArgs A)
+{
+  const unsigned int n = min(*A.border_count, A.border_cap);
+  const int lo = A.slice[G2_SLICE_LO];
+  for(unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint4 e = A.border_list[i];
+      const unsigned int idx = A.targets[lo + (int) e.x];
+      bool differs;
+      if(e.z & G2_EVT_SEVERAL)
+	differs = true;
+      else if(e.z & (G2_EVT_NODE_TERM | G2_EVT_PART_TERM))
+	{
+	  const G2PRec tp = A.prec[idx];
+	  const float4 q = (e.z & G2_EVT_NODE_TERM) ? __ldg(A.cells + (size_t) e.y * (2 + D) + 1 + ((e.z >> 8) & 15)) : __ldg(A.wpart + e.y);
+	  differs = term_in_range_exact<PERIODIC>(A.ex, q.x, q.y, q.z, tp.x, tp.y, tp.z) != ((e.z & 1u) != 0u);
+	}
+      else
+	differs = walk_decide_exact<D, SR, PERIODIC, UNEQUAL>(A.ex, A.cells + (size_t) e.y * (2 + D), A.prec + idx) != (int) (e.z & 3u);
+      if(differs)
+	{
+	  const unsigned int slot = atomicAdd(A.redo_count, 1u);
+	  if(slot < A.redo_cap)
+	    A.redo_list[slot] = e.x;
+	}
+    }
+}
+
+// ---- the walk of a target whose FP32 walk took a decision the reference would not have taken: ONE WARP per target, in the
+//      reference's own arithmetic (double locals, FLOAT node and particle fields, decisions by walk_decide_exact, tabindex =
+//      (int) (asmthfac * r): forcetree.c:1244-1610 and 1623-2052 restated over the depth-first records).  The depth-first array is
+//      walked in disjoint index ranges, one per lane: lane 0 starts with the whole tree, and whenever a lane is idle a busy lane hands
+//      it the part of its range that lies behind the sibling of its current cell.  Partial sums are FP64 and reduced at the end. ----
+#define WALK_REDO_WARPS 4
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
-__global__ void __launch_bounds__(WALK_REDO_THREADS) walk_redo_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const WalkArgs A)
 {
   extern __shared__ float s_tab[];
   if(SR)
     {
-      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_REDO_THREADS)
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += 32 * WALK_REDO_WARPS)
 	s_tab[i] = A.srtable[i];
       __syncthreads();
     }
   const WalkExactParams *__restrict__ E = A.ex;
-  const int R = 2 + D;
+  const int R = 2 + D, lane = threadIdx.x & 31;
   const int lo = A.slice[G2_SLICE_LO];
-  const unsigned int nredo = *A.redo_count, end = (unsigned int) A.numnodes;
-  unsigned long long tot_inter = 0;
-  for(unsigned int i = blockIdx.x * WALK_REDO_THREADS + threadIdx.x; i < nredo; i += gridDim.x * WALK_REDO_THREADS)
+  const unsigned int nredo = min(*A.redo_count, A.redo_cap), nodes = (unsigned int) A.numnodes;
+  const unsigned int nwarps = gridDim.x * WALK_REDO_WARPS;
+  for(unsigned int i = blockIdx.x * WALK_REDO_WARPS + (threadIdx.x >> 5); i < nredo; i += nwarps)
     {
       const int tloc = (int) A.redo_list[i];
+      // a target that was noted twice is walked by the first of its entries only
+      bool dup = false;
+      for(unsigned int k = lane; k < i; k += 32)
+	dup = dup || A.redo_list[k] == (unsigned int) tloc;
+      if(__any_sync(0xffffffffu, dup))
+	continue;
       const unsigned int idx = A.targets[lo + tloc];
       const G2PRec tp = A.prec[idx];
       const double px = (double) tp.x, py = (double) tp.y, pz = (double) tp.z, box = E->boxsize;
@@ -573,11 +632,45 @@ __global__ void __launch_bounds__(WALK_REDO_THREADS) walk_redo_kernel(const Walk
       const double hself = E->fsoft[tp.type];
       double ax = 0.0, ay = 0.0, az = 0.0;
       int ninter = 0;
-      unsigned int cur = 0u;
-      while(cur < end)
+      unsigned int cur = lane == 0 ? 0u : nodes, end = nodes;	// this lane's range of the depth-first array
+      while(true)
 	{
-	  const float4 *rec = A.cells + (size_t) cur * R;
-	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
+	  const unsigned int busy = __ballot_sync(0xffffffffu, cur < end);
+	  if(busy == 0u)
+	    break;
+	  uint4 w = make_uint4(end, 0u, 0u, 0u);
+	  const float4 *rec = A.cells + (size_t) (cur < end ? cur : 0u) * R;
+	  if(cur < end)
+	    w = __ldg((const uint4 *) (rec + 1 + D));
+	  // work hand-over: the k-th idle lane takes [sibling, end) from the k-th busy lane that has cells behind the sibling of its
+	  // current cell; that lane keeps [cur, sibling)
+	  const bool isbusy = cur < end, can_give = isbusy && w.x < end;
+	  const unsigned int givers = __ballot_sync(0xffffffffu, can_give), idle = ~busy;
+	  const int npairs = min(__popc(givers), __popc(idle));
+	  if(npairs > 0)
+	    {
+	      const unsigned int below = (1u << lane) - 1u;
+	      const int grank = __popc(givers & below), irank = __popc(idle & below);
+	      const bool takes = !isbusy && irank < npairs;
+	      unsigned int src_lane = 0;
+	      if(takes)
+		{
+		  unsigned int m = givers;
+		  for(int r = 0; r < irank; r++)
+		    m &= m - 1u;
+		  src_lane = (unsigned int) (__ffs(m) - 1);
+		}
+	      const unsigned int give_lo = __shfl_sync(0xffffffffu, w.x, src_lane), give_hi = __shfl_sync(0xffffffffu, end, src_lane);
+	      if(takes)
+		{
+		  cur = give_lo;
+		  end = give_hi;
+		}
+	      else if(can_give && grank < npairs)
+		end = w.x;
+	    }
+	  if(!isbusy)
+	    continue;		// idle lanes, also those that just took work: they load their record in the next round
 	  const int dec = walk_decide_exact<D, SR, PERIODIC, UNEQUAL>(E, rec, A.prec + idx);
 	  if(dec == G2_DEC_CULL)
 	    {
@@ -650,13 +743,31 @@ __global__ void __launch_bounds__(WALK_REDO_THREADS) walk_redo_kernel(const Walk
 	    ninter++;		// forcetree.c:1585 resp. 2031-2032
 	  cur = isnode ? w.x : cur + 1u;
 	}
-      walk_store_result<SR, PERIODIC>(A, idx, tloc, tp.x, tp.y, tp.z, (float) ax, (float) ay, (float) az, (float) ninter);
-      tot_inter += (unsigned long long) ninter;
+#pragma unroll
+      for(int o = 16; o > 0; o >>= 1)
+	{
+	  ax += __shfl_xor_sync(0xffffffffu, ax, o);
+	  ay += __shfl_xor_sync(0xffffffffu, ay, o);
+	  az += __shfl_xor_sync(0xffffffffu, az, o);
+	  ninter += __shfl_xor_sync(0xffffffffu, ninter, o);
+	}
+      if(lane == 0)
+	{
+	  // replace the FP32 walk's result (and its share of the interaction total)
+	  const float old_inter = A.cres ? A.cres[5 * (size_t) tloc + 3] : A.cost[idx];
+	  float lattc = 0.0f;
+	  if(PERIODIC && !SR && A.latt && A.lattcost)
+	    lattc = A.lattcost[idx];
+	  walk_store_result<SR, PERIODIC>(A, idx, tloc, tp.x, tp.y, tp.z, (float) ax, (float) ay, (float) az, (float) ninter);
+	  const long long delta = (long long) ninter - (long long) (old_inter - lattc);
+	  atomicAdd(&A.counters[0], (unsigned long long) delta);
+	}
     }
-  if(tot_inter)
-    atomicAdd(&A.counters[0], tot_inter);
   if(blockIdx.x == 0 && threadIdx.x == 0)
-    A.counters[5] = (unsigned long long) nredo;
+    {
+      A.counters[5] = (unsigned long long) nredo;
+      A.counters[7] = (unsigned long long) *A.border_count;
+    }
 }
 
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT>
@@ -667,10 +778,11 @@ static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
   walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT><<<grid, WALK_THREADS, smem, c->stream>>>(A);
   if(EXACT)
     {
+      walk_verify_kernel<D, SR, PERIODIC, UNEQUAL><<<c->nsm * 4, 128, 0, c->stream>>>(A);
       if(smem > 48 * 1024)
 	G2_CUDA(cudaFuncSetAttribute(walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK><<<c->nsm * 8, WALK_REDO_THREADS, smem, c->stream>>>(A);
-      c->launches++;
+      walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK><<<c->nsm * 2, 32 * WALK_REDO_WARPS, smem, c->stream>>>(A);
+      c->launches += 2;
     }
   return 0;
 }

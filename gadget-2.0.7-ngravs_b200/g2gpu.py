@@ -16,22 +16,22 @@ LAW = dict(none=0, newtonian=1, neg_newtonian=2, yukawa=3, coloyuk=4, bambam=5, 
 SPLINE = dict(none=16, plummer=17, neg_plummer=18, bambam_spline=19, sourcebambaryon_spline=20,
               sourcebaryonbam_spline=21)
 
-POT = dict(none=32, newtonian=33, neg_newtonian=34)
-POTSPLINE = dict(none=48, plummer=49, neg_plummer=50)
+POT = dict(none=32, newtonian=33, neg_newtonian=34, bambam=35, sourcebaryonbam=36, sourcebambaryon=37)
+POTSPLINE = dict(none=48, plummer=49, neg_plummer=50, bambam=51, sourcebaryonbam=52, sourcebambaryon=53)
 
 EXPORTED = [
     "g2gpu_create", "g2gpu_destroy", "g2gpu_last_error", "g2gpu_device_count", "g2gpu_set_species", "g2gpu_set_laws",
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
-    "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings",
+    "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings", "g2gpu_get_counts",
     "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
     "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table",
-    "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential",
+    "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential", "g2gpu_eval_potentials",
     "g2gpu_group_create", "g2gpu_group_destroy", "g2gpu_group_size", "g2gpu_group_ctx", "g2gpu_group_set_species", "g2gpu_group_set_laws",
     "g2gpu_group_set_srtable", "g2gpu_group_set_lattice_tables", "g2gpu_group_set_option", "g2gpu_group_upload", "g2gpu_group_upload_aos",
     "g2gpu_group_gather_resident", "g2gpu_group_shard", "g2gpu_group_domain", "g2gpu_group_treebuild", "g2gpu_group_update_tree",
     "g2gpu_group_walk", "g2gpu_group_download_acc", "g2gpu_group_download_aos", "g2gpu_group_get_order", "g2gpu_group_gravity_tree",
-    "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices",
+    "g2gpu_group_step_resident", "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices",
 ]
 
 
@@ -200,7 +200,14 @@ class TreeGravity:
 
     force_treebuild = treebuild
 
+    def counts(self):
+        c = np.zeros(4, dtype=np.int32)
+        self._chk(self.lib.g2gpu_get_counts(self.ctx, _p(c)))
+        return dict(n=int(c[0]), numnodes=int(c[1]), ntargets=int(c[2]), stage=int(c[3]))
+
     def tree(self):
+        cn = self.counts()
+        self.numnodes, self.n = cn["numnodes"], cn["n"]
         nn, D, n = self.numnodes, self.D, self.n
         ln = np.zeros(nn, dtype=np.float32)
         ce = np.zeros((nn, 3), dtype=np.float32)
@@ -375,7 +382,7 @@ class TreeGravity:
         cnt = np.zeros(8, dtype=np.int64)
         self._chk(self.lib.g2gpu_timings(self.ctx, _p(ms), _p(cnt)))
         return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6], pm_ms=ms[7],
-                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]), rewalked=int(cnt[5]))
+                    launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]), rewalked=int(cnt[5]), border_checked=int(cnt[6]))
 
     def reset_counters(self):
         self.lib.g2gpu_reset_counters(self.ctx)
@@ -405,6 +412,13 @@ class TreeGravity:
         fac = np.zeros(len(r), dtype=np.float32)
         self._chk(self.lib.g2gpu_eval_pairs(self.ctx, len(r), tgt, src, _p(pm), _p(m), _p(r), _p(h), _p(_i32(nn)), _p(fac)))
         return fac
+
+    def eval_potentials(self, tgt, src, pm, m, r, h, nn=None):
+        """What the potential walk adds to pot for each pair (no TreePM table term): -PotentialFxns for r >= h, +PotentialSplines for r < h."""
+        pm, m, r, h = _f32(pm), _f32(m), _f32(r), _f32(h)
+        out = np.zeros(len(r), dtype=np.float32)
+        self._chk(self.lib.g2gpu_eval_potentials(self.ctx, len(r), tgt, src, _p(pm), _p(m), _p(r), _p(h), _p(_i32(nn)), _p(out)))
+        return out
 
 
 class TreeGravityGroup:
@@ -532,6 +546,14 @@ class TreeGravityGroup:
         self.n = n
         return acc, cost, old, perm
 
+    def step_resident(self, n, wp):
+        """all-gather of the resident shards -> domain -> treebuild -> walk on every device (results stay there)."""
+        self._chk(self.lib.g2gpu_group_step_resident(self.grp, int(n), C.byref(wp)))
+        self.n = int(n)
+
+    def stream(self, i=0):
+        return self.lib.g2gpu_stream(C.c_void_p(self.lib.g2gpu_group_ctx(self.grp, int(i))))
+
     def sync(self):
         self._chk(self.lib.g2gpu_group_sync(self.grp))
 
@@ -541,7 +563,7 @@ class TreeGravityGroup:
         self._chk(self.lib.g2gpu_group_timings(self.grp, _p(ms), _p(cnt)))
         return dict(domain_ms=ms[0], build_ms=ms[1], walk_ms=ms[2], walk_kernel_ms=ms[3], sort_ms=ms[4], h2d_ms=ms[5], d2h_ms=ms[6], pm_ms=ms[7],
                     launches=int(cnt[0]), interactions=int(cnt[1]), cell_visits=int(cnt[2]), species_terms=int(cnt[3]), decisions=int(cnt[4]),
-                    rewalked=int(cnt[5]))
+                    rewalked=int(cnt[5]), border_checked=int(cnt[6]))
 
     def io_bytes(self):
         b = np.zeros(3, dtype=np.int64)

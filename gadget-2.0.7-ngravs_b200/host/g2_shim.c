@@ -284,8 +284,11 @@ static void g2_push_tables(void)
       for(j = 0; j < N_GRAVS; j++)
 	{
 	  gravity f = PotentialFxns[i][j], g = PotentialSplines[i][j];
-	  pot[i * N_GRAVS + j] = f == none ? G2GPU_POT_NONE : f == newtonian_pot ? G2GPU_POT_NEWTONIAN : f == neg_newtonian_pot ? G2GPU_POT_NEG_NEWTONIAN : -1;
-	  pots[i * N_GRAVS + j] = g == none ? G2GPU_POTSPLINE_NONE : g == plummer_pot ? G2GPU_POTSPLINE_PLUMMER : g == neg_plummer_pot ? G2GPU_POTSPLINE_NEG_PLUMMER : -1;
+	  pot[i * N_GRAVS + j] = f == none ? G2GPU_POT_NONE : f == newtonian_pot ? G2GPU_POT_NEWTONIAN : f == neg_newtonian_pot ? G2GPU_POT_NEG_NEWTONIAN :
+	    f == bambam_pot ? G2GPU_POT_BAMBAM : f == sourcebaryonbam_pot ? G2GPU_POT_SOURCEBARYONBAM : f == sourcebambaryon_pot ? G2GPU_POT_SOURCEBAMBARYON : -1;
+	  pots[i * N_GRAVS + j] = g == none ? G2GPU_POTSPLINE_NONE : g == plummer_pot ? G2GPU_POTSPLINE_PLUMMER : g == neg_plummer_pot ? G2GPU_POTSPLINE_NEG_PLUMMER :
+	    g == bambam_pot ? G2GPU_POTSPLINE_BAMBAM : g == sourcebaryonbam_pot ? G2GPU_POTSPLINE_SOURCEBARYONBAM :
+	    g == sourcebambaryon_pot ? G2GPU_POTSPLINE_SOURCEBAMBARYON : -1;
 	  if(pot[i * N_GRAVS + j] < 0 || pots[i * N_GRAVS + j] < 0)
 	    ok = 0;
 	}

@@ -57,15 +57,22 @@ enum g2gpu_law
 };
 
 /* Pair potentials shipped in ngravs.c for the tree potential walks: PotentialFxns[tgt][src](pm, m, h, r, N) for r >= h,
- * PotentialSplines[tgt][src](pm, m, h, r, N) for r < h (allvars.h:147-148).  The BAM potentials (ngravs.c:672-760) are not registered. */
+ * PotentialSplines[tgt][src](pm, m, h, r, N) for r < h (allvars.h:147-148).  The BAM potentials take BAM_EPSILON from params[1] of
+ * g2gpu_set_laws; the reference wires them as function AND as "spline" (ngravs.c:198-200). */
 enum g2gpu_potlaw
 {
   G2GPU_POT_NONE = 32,		/* none()              ngravs.c:344 */
   G2GPU_POT_NEWTONIAN = 33,	/* newtonian_pot()     ngravs.c:368 */
   G2GPU_POT_NEG_NEWTONIAN = 34,	/* neg_newtonian_pot() ngravs.c:375 */
+  G2GPU_POT_BAMBAM = 35,	/* bambam_pot()        ngravs.c:672 */
+  G2GPU_POT_SOURCEBARYONBAM = 36,	/* sourcebaryonbam_pot() ngravs.c:708 */
+  G2GPU_POT_SOURCEBAMBARYON = 37,	/* sourcebambaryon_pot() ngravs.c:734 */
   G2GPU_POTSPLINE_NONE = 48,	/* none()              as a spline */
   G2GPU_POTSPLINE_PLUMMER = 49,	/* plummer_pot()       ngravs.c:459 */
-  G2GPU_POTSPLINE_NEG_PLUMMER = 50	/* neg_plummer_pot()   ngravs.c:476 */
+  G2GPU_POTSPLINE_NEG_PLUMMER = 50,	/* neg_plummer_pot()   ngravs.c:476 */
+  G2GPU_POTSPLINE_BAMBAM = 51,	/* the three BAM potentials in the spline slot */
+  G2GPU_POTSPLINE_SOURCEBARYONBAM = 52,
+  G2GPU_POTSPLINE_SOURCEBAMBARYON = 53
 };
 
 /* k-space Green's functions of the periodic PM force shipped in ngravs.c (GreensFxns[source][target], allvars.h:140; mesh units). */
@@ -308,6 +315,8 @@ int g2gpu_group_get_order(g2gpu_group *grp, int *perm);
 /* whole step with host buffers (the e2e path), arguments as g2gpu_gravity_tree; one host thread per device runs its whole pipeline */
 int g2gpu_group_gravity_tree(g2gpu_group *grp, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
 			     const int *active, const g2gpu_walk_params *wp, float *acc, float *cost, float *oldacc_out, int *perm);
+/* one step from device-resident shards (see g2gpu_group_gather_resident): all-gather -> domain -> treebuild -> walk; results stay on the devices */
+int g2gpu_group_step_resident(g2gpu_group *grp, int npart, const g2gpu_walk_params *wp);
 int g2gpu_group_sync(g2gpu_group *grp);
 int g2gpu_group_timings(g2gpu_group *grp, double ms[8], long long counters[8]);	/* times: max over devices; counters: sums */
 int g2gpu_group_io_bytes(g2gpu_group *grp, long long out[3]);	/* H2D, D2H (all devices), bytes received per device by the all-gather */
@@ -322,6 +331,7 @@ int g2gpu_group_slices(g2gpu_group *grp, int *lo, int *hi, double *next_frac);	/
  * whose walk was repeated in FP64 because a decision was borderline in FP32 (option "walk_exact"), [6..7] reserved (0). */
 int g2gpu_timings(g2gpu_ctx *ctx, double ms[8], long long counters[8]);
 void g2gpu_reset_counters(g2gpu_ctx *ctx);
+int g2gpu_get_counts(g2gpu_ctx *ctx, int out[4]);	/* particles, tree nodes (Numnodestree), active targets of the last walk, stage reached */
 int g2gpu_io_bytes(g2gpu_ctx *ctx, long long out[2]);	/* host->device / device->host bytes of the last upload / download */
 void *g2gpu_stream(g2gpu_ctx *ctx);	/* cudaStream_t all kernels are launched on */
 int g2gpu_sync(g2gpu_ctx *ctx);
@@ -333,6 +343,11 @@ int g2gpu_sort_pairs(g2gpu_ctx *ctx, int n, unsigned long long *keys, unsigned i
  * kernel's own arithmetic: out[i] = fac such that acc += d*fac (forcetree.c:1542-1544). */
 int g2gpu_eval_pairs(g2gpu_ctx *ctx, int n, int tgt, int src, const float *pm, const float *m, const float *r,
 		     const float *h, const int *npart_in_node, float *fac);
+
+/* what the potential walk adds to pot for one pair without the TreePM table term: -PotentialFxns[tgt][src](pm, m, h, r, N) for r >= h,
+ * +PotentialSplines[tgt][src](pm, m, h, r, N) for r < h (forcetree.c:2732-2734, 3115-3118), in the kernel's own arithmetic */
+int g2gpu_eval_potentials(g2gpu_ctx *ctx, int n, int tgt, int src, const float *pm, const float *m, const float *r, const float *h,
+			  const int *npart_in_node, float *out);
 
 #ifdef __cplusplus
 }

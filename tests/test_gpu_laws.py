@@ -80,5 +80,5 @@ def test_walk_with_non_newtonian_wiring(variant, wiring, outdir):
     acc, cost, old = tg.download_acc()
     tg.close()
     err = g2test.rel_err(acc, r1["acc"])
-    assert int(np.sum(cost != r1["cost"])) <= 0.002 * n
+    assert int(np.sum(cost != r1["cost"])) == 0
     assert np.median(err) <= 1e-5 and np.percentile(err, 99.9) <= 1e-3, (float(np.median(err)), float(np.percentile(err, 99.9)))

@@ -12,8 +12,10 @@ from refrun import RefOracle, available
 
 pytestmark = pytest.mark.gpu
 
-MEDIAN_TOL = 1.0e-5      # BASELINE.json north_star
-P999_TOL = 1.0e-3
+# BASELINE.json north_star asks for 1e-5 / 1e-3; the asserts sit within 10x of what is measured (median 3e-8 .. 2e-7, p99.9 <= 1.5e-4), so that a
+# regression cannot hide inside the tolerance.  GravCost is integer work: every particle's count must equal the reference's.
+MEDIAN_TOL = 1.0e-6
+P999_TOL = 3.0e-4
 
 
 def run_reference(variant, pos, mass, ptype, soft, grav, box=0.0, theta=0.5, errtol=0.005, criterion=1):
@@ -103,7 +105,7 @@ def test_nonperiodic_tree_and_forces(case, n, outdir):
     for s in (s1, s2):
         assert s["median"] <= MEDIAN_TOL, s
         assert s["p999"] <= P999_TOL, s
-        assert s["cost_mismatch"] <= 0.002 * n, s
+        assert s["cost_mismatch"] == 0, s
 
 
 @pytest.mark.parametrize("n", [32768])
@@ -158,7 +160,7 @@ def test_periodic_treepm_shortrange(n, outdir):
     for s in (s1, s2):
         assert s["median"] <= MEDIAN_TOL, s
         assert s["p999"] <= P999_TOL, s
-        assert s["cost_mismatch"] <= 0.002 * n, s
+        assert s["cost_mismatch"] == 0, s
 
 
 def test_config1_galaxy_collision_fixture(outdir):
@@ -198,7 +200,7 @@ def test_config1_galaxy_collision_fixture(outdir):
     tg.close()
     for s in (s1, s2):
         assert s["median"] <= MEDIAN_TOL and s["p999"] <= P999_TOL, s
-        assert s["cost_mismatch"] <= 0.002 * n, s
+        assert s["cost_mismatch"] == 0, s
 
 
 def test_four_species_with_gas_fixture(outdir):
@@ -235,7 +237,7 @@ def test_four_species_with_gas_fixture(outdir):
     dump(outdir, "walk_d4.json", s1)
     tg.close()
     assert s1["median"] <= MEDIAN_TOL and s1["p999"] <= P999_TOL, s1
-    assert s1["cost_mismatch"] <= 0.002 * n, s1
+    assert s1["cost_mismatch"] == 0, s1
 
 
 def test_accuracy_against_direct_summation(outdir):
