@@ -86,7 +86,9 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->prec, np);
   rc |= dalloc(&c->phkey, np); rc |= dalloc(&c->perm, np); rc |= dalloc(&c->phorder, np);
   rc |= dalloc(&c->skey[0], np); rc |= dalloc(&c->skey[1], np); rc |= dalloc(&c->sval[0], np); rc |= dalloc(&c->sval[1], np);
-  c->tilehist_elems = (size_t) ((np + 4095) / 4096) * 512 + 8;
+  // radix-sort scratch: the one-sweep sort keeps a status word per (pass, tile, bin): 7 passes x tiles x 512 bins
+  c->tilehist_elems = (size_t) 8 * 512 + 16 + (size_t) 7 * ((np + 4095) / 4096) * 512;
+  c->sort_onesweep = getenv("G2GPU_SORT_ONESWEEP") ? atoi(getenv("G2GPU_SORT_ONESWEEP")) != 0 : 1;
   rc |= dalloc(&c->tilehist, c->tilehist_elems);
   c->scan_tmp_elems = cap / 2048 + 16 + c->tilehist_elems / 2048;
   rc |= dalloc(&c->scan_tmp, c->scan_tmp_elems);
@@ -106,7 +108,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->d_depth, (size_t) 64);
   rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
   rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
-  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256); rc |= dalloc(&c->redo_list, (size_t) G2_REDO_CAP);
+  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256);
   if(rc)
     {
       g2gpu_destroy(c);
@@ -141,7 +143,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->redo_list, c->cres };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -586,6 +588,8 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     c->direct_ewald = value != 0;
   else if(strcmp(name, "walk_stats") == 0)
     c->walk_stats = value != 0;
+  else if(strcmp(name, "sort_onesweep") == 0)
+    c->sort_onesweep = value != 0;
   else if(strcmp(name, "walk_exact") == 0)
     c->walk_exact = value != 0;
   else if(strcmp(name, "compact") == 0)
@@ -936,7 +940,7 @@ extern "C" int g2gpu_timings(g2gpu_ctx *c, double ms[8], long long counters[8])
 	  counters[3] = (long long) c->h_counters[2];
 	  counters[4] = (long long) c->h_counters[4];
 	  counters[5] = (long long) c->h_counters[5];	// targets walked again in FP64 (an FP32 decision differed from the reference's)
-	  counters[6] = (long long) c->h_counters[7];	// borderline comparisons that were checked in FP64
+	  counters[6] = (long long) c->h_counters[7];	// targets flagged (equals [5] unless the list overflowed)
 	}
     }
   return 0;

@@ -10,7 +10,6 @@
 #define G2_MAXDEPTH 21		// 3*21 = 63 key bits: deepest supported octree level below the root
 #define G2_PH_BITS 18		// BITS_PER_DIMENSION (allvars.h:34)
 #define G2_NSM_FALLBACK 148
-#define G2_REDO_CAP 65536		// targets per walk that may be walked again in the reference's double arithmetic
 #ifndef G2_DEFAULT_WALK_MODE
 #define G2_DEFAULT_WALK_MODE 0
 #endif
@@ -154,6 +153,7 @@ struct g2gpu_ctx
   // sort scratch (ping-pong)
   unsigned long long *skey[2];
   unsigned int *sval[2];
+  int sort_onesweep;		// option "sort_onesweep" (default 1): one kernel per radix digit with decoupled look-back
   unsigned int *tilehist;	// NBINS * ntiles
   size_t tilehist_elems;
   unsigned int *scan_tmp;	// block sums for the device-wide scan
@@ -217,7 +217,6 @@ struct g2gpu_ctx
   int w_lo, w_hi;		// this rank's slice of w_targets (host copies, valid after g2_fetch_slice)
   int *d_slice, *h_slice;	// [G2_SLICE_*] on the device / pinned
   void *d_exact;		// WalkExactParams of the current walk
-  unsigned int *redo_list;	// targets walked again in FP64 (G2_REDO_CAP slots)
   int slice_pending;
   float *acc;			// 3n, current particle order
   float *cost;			// n

@@ -283,6 +283,236 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const uns
     }
 }
 
+// ------------------------------------------------------------------ one-sweep radix sort ------------------
+// One kernel per digit (9 bits): a tile loads its 4096 pairs ONCE, ranks them, learns where its run of every bin starts from the tiles
+// before it by a decoupled look-back over per-(tile, bin) status words, and scatters -- 12 B read + 12 B written per pair and pass,
+// instead of histogram + three scan kernels + scatter (32 B per pair and pass, five launches).  The digit histograms of ALL passes are
+// counted by one kernel up front (they do not depend on the order of the pairs).  Tiles take their number from an atomic ticket, so
+// every tile a look-back waits for is already running.
+#define OS_BITS RADIX_BITS		// 9 bits: 7 passes for the 56-bit (block, Peano-Hilbert) keys and for the 63-bit tree keys
+#define OS_BINS (1 << OS_BITS)
+#define OS_MAXPASS 8
+#define OS_FLAG_AGG 0x40000000u		// status word: count of this tile alone
+#define OS_FLAG_INC 0x80000000u		// status word: count of this tile and all tiles before it
+#define OS_VALUE_MASK 0x3fffffffu
+
+// hist[p * OS_BINS + d] += number of keys whose p-th digit is d (all passes at once)
+__global__ void __launch_bounds__(256) os_hist_kernel(const unsigned long long *__restrict__ keys, int n, int begin_bit, int nbits, int npass,
+						      unsigned int *__restrict__ hist)
+{
+  __shared__ unsigned int h[OS_MAXPASS * OS_BINS];
+  for(int i = threadIdx.x; i < npass * OS_BINS; i += 256)
+    h[i] = 0;
+  __syncthreads();
+  const size_t stride = (size_t) gridDim.x * 256;
+  for(size_t i = (size_t) blockIdx.x * 256 + threadIdx.x; i < (size_t) n; i += stride)
+    {
+      const unsigned long long k = keys[i] >> begin_bit;
+      for(int p = 0; p < npass; p++)
+	{
+	  const int bits = nbits - p * OS_BITS < OS_BITS ? nbits - p * OS_BITS : OS_BITS;	// the last pass may be narrower
+	  atomicAdd(&h[p * OS_BINS + (unsigned int) ((k >> (p * OS_BITS)) & ((1u << bits) - 1u))], 1u);
+	}
+    }
+  __syncthreads();
+  for(int i = threadIdx.x; i < npass * OS_BINS; i += 256)
+    if(h[i])
+      atomicAdd(&hist[i], h[i]);
+}
+
+// exclusive scan of every pass's bins, in place (one thread per bin); also resets the tile tickets
+__global__ void __launch_bounds__(OS_BINS) os_scan_kernel(unsigned int *hist, int npass, unsigned int *tickets)
+{
+  __shared__ unsigned int sm[33];
+  for(int p = 0; p < npass; p++)
+    {
+      unsigned int v = hist[p * OS_BINS + threadIdx.x], tot;
+      unsigned int ex = block_excl_scan(v, &tot, sm);
+      hist[p * OS_BINS + threadIdx.x] = ex;
+    }
+  if(threadIdx.x < OS_MAXPASS)
+    tickets[threadIdx.x] = 0;
+}
+
+#define OS_SMEM (SORT_WARPS * OS_BINS * 4 + 2 * OS_BINS * 4 + 64 * 4 + SORT_TILE * 8 + SORT_TILE * 4)
+__global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
+								    unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
+								    const unsigned int *__restrict__ binbase /* this pass's scanned histogram */,
+								    volatile unsigned int *__restrict__ status /* [tile][bin] of this pass, zeroed */,
+								    unsigned int *__restrict__ ticket, int n, int shift, unsigned int mask,
+								    unsigned int *__restrict__ capture_dest)
+{
+  extern __shared__ unsigned long long sort_dyn[];
+  unsigned long long *stage_k = sort_dyn;				// SORT_TILE keys
+  unsigned int *stage_v = (unsigned int *) (stage_k + SORT_TILE);	// SORT_TILE values
+  unsigned int (*wcnt)[OS_BINS] = (unsigned int (*)[OS_BINS]) (stage_v + SORT_TILE);	// per-warp digit counts -> warp offsets
+  unsigned int *binstart = &wcnt[0][0] + SORT_WARPS * OS_BINS;	// tile-local exclusive scan of the tile histogram
+  unsigned int *gdelta = binstart + OS_BINS;				// global start of the tile's run of a bin, minus binstart
+  unsigned int *scratch = gdelta + OS_BINS;				// 33 words for the block scan + the ticket
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if(threadIdx.x == 0)
+    scratch[40] = atomicAdd(ticket, 1u);	// (scratch[0..32] serve the block scan)
+  for(int i = threadIdx.x; i < SORT_WARPS * OS_BINS; i += SORT_THREADS)
+    (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const int tile = (int) scratch[40];
+
+  const size_t tbase = (size_t) tile * SORT_TILE;
+  const int tcount = (size_t) n - tbase < (size_t) SORT_TILE ? (int) ((size_t) n - tbase) : SORT_TILE;
+  const size_t wbase = tbase + (size_t) warp * (32 * SORT_ITEMS);
+  unsigned long long k[SORT_ITEMS];
+  unsigned int r[SORT_ITEMS];
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      k[i] = (idx < (size_t) n) ? keys_in[idx] : ~0ull;
+    }
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      bool valid = idx < (size_t) n;
+      unsigned int d = valid ? digit_of(k[i], shift, mask) : OS_BINS;	// invalid lanes match only each other
+      unsigned int peers = __match_any_sync(0xffffffffu, d);
+      unsigned int below = __popc(peers & ((1u << lane) - 1u));
+      unsigned int prev = 0;
+      int leader = __ffs(peers) - 1;
+      if(valid)
+	prev = wcnt[warp][d];	// all peers read the same counter before the leader updates it
+      __syncwarp();
+      if(valid && lane == leader)
+	wcnt[warp][d] = prev + __popc(peers);
+      __syncwarp();
+      r[i] = prev + below;
+    }
+  __syncthreads();
+  // two consecutive bins per thread: exclusive scan over warps (-> warp offsets), the tile's count, its start inside the tile
+  unsigned int run2[OS_BINS / SORT_THREADS], before2[OS_BINS / SORT_THREADS];
+  unsigned int mysum = 0;
+#pragma unroll
+  for(int q = 0; q < OS_BINS / SORT_THREADS; q++)
+    {
+      const int b = threadIdx.x * (OS_BINS / SORT_THREADS) + q;
+      unsigned int run = 0;
+#pragma unroll
+      for(int w = 0; w < SORT_WARPS; w++)
+	{
+	  unsigned int t = wcnt[w][b];
+	  wcnt[w][b] = run;
+	  run += t;
+	}
+      run2[q] = run;
+      mysum += run;
+      // publish this tile's count of the bin
+      status[(size_t) tile * OS_BINS + b] = run | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG);
+    }
+  // add up the tiles before this one (decoupled look-back), then publish the inclusive count
+#pragma unroll
+  for(int q = 0; q < OS_BINS / SORT_THREADS; q++)
+    {
+      const int b = threadIdx.x * (OS_BINS / SORT_THREADS) + q;
+      unsigned int before = 0;
+      if(tile > 0)
+	{
+	  int t = tile - 1;
+	  while(true)
+	    {
+	      const unsigned int sw = status[(size_t) t * OS_BINS + b];
+	      if(sw & OS_FLAG_INC)
+		{
+		  before += sw & OS_VALUE_MASK;
+		  break;
+		}
+	      if(sw & OS_FLAG_AGG)
+		{
+		  before += sw & OS_VALUE_MASK;
+		  t--;
+		}
+	      // else: not published yet (that tile holds a smaller ticket, so it is running): look again
+	    }
+	  status[(size_t) tile * OS_BINS + b] = (before + run2[q]) | OS_FLAG_INC;
+	}
+      before2[q] = before;
+    }
+  unsigned int blocktotal;
+  unsigned int ex = block_excl_scan(mysum, &blocktotal, scratch);
+#pragma unroll
+  for(int q = 0; q < OS_BINS / SORT_THREADS; q++)
+    {
+      const int b = threadIdx.x * (OS_BINS / SORT_THREADS) + q;
+      binstart[b] = ex;
+      gdelta[b] = binbase[b] + before2[q] - ex;
+      ex += run2[q];
+    }
+  __syncthreads();
+  // tile-sorted staging
+#pragma unroll
+  for(int i = 0; i < SORT_ITEMS; i++)
+    {
+      size_t idx = wbase + (size_t) i * 32 + lane;
+      if(idx < (size_t) n)
+	{
+	  unsigned int d = digit_of(k[i], shift, mask);
+	  unsigned int pos = binstart[d] + wcnt[warp][d] + r[i];
+	  stage_k[pos] = k[i];
+	  stage_v[pos] = vals_in[idx];
+	  if(capture_dest)		// where the element at input position idx of THIS pass ends up (coalesced: consecutive lanes, consecutive idx)
+	    capture_dest[idx] = gdelta[d] + pos;
+	}
+    }
+  __syncthreads();
+  for(int j = threadIdx.x; j < tcount; j += SORT_THREADS)
+    {
+      unsigned long long key = stage_k[j];
+      unsigned int d = digit_of(key, shift, mask);
+      unsigned int out = gdelta[d] + (unsigned int) j;
+      keys_out[out] = key;
+      vals_out[out] = stage_v[j];
+    }
+}
+
+static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io, unsigned long long *keys_alt,
+				  unsigned int *vals_alt, int begin_bit, int end_bit, int capture_shift, unsigned int *capture_dest)
+{
+  const int ntiles = g2_cdiv(n, SORT_TILE);
+  const int nbits = end_bit - begin_bit;
+  const int npass = (nbits + OS_BITS - 1) / OS_BITS;
+  if(npass > OS_MAXPASS)
+    return g2_fail(G2GPU_ERR_ARG, "sort: %d key bits need more than %d passes", nbits, OS_MAXPASS);
+  // scratch: [npass * 256] histograms | [8] tickets | [npass][ntiles][256] status words
+  const size_t need = (size_t) OS_MAXPASS * OS_BINS + 8 + (size_t) npass * ntiles * OS_BINS;
+  if(need > c->tilehist_elems)
+    return g2_fail(G2GPU_ERR_ARG, "sort: %d pairs exceed scratch", n);
+  unsigned int *hist = c->tilehist, *tickets = hist + OS_MAXPASS * OS_BINS, *status = tickets + 8;
+  cudaStream_t st = c->stream;
+  G2_CUDA(cudaMemsetAsync(c->tilehist, 0, sizeof(unsigned int) * need, st));
+  int hb = c->nsm * 8;
+  if(hb > g2_cdiv(n, 256))
+    hb = g2_cdiv(n, 256);
+  os_hist_kernel<<<hb, 256, 0, st>>>(*keys_io, n, begin_bit, nbits, npass, hist);
+  os_scan_kernel<<<1, OS_BINS, 0, st>>>(hist, npass, tickets);
+  c->launches += 2;
+  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM));
+  unsigned long long *kin = *keys_io, *kout = keys_alt;
+  unsigned int *vin = *vals_io, *vout = vals_alt;
+  for(int p = 0; p < npass; p++)
+    {
+      const int shift = begin_bit + p * OS_BITS;
+      const int bits = end_bit - shift < OS_BITS ? end_bit - shift : OS_BITS;
+      const unsigned int mask = (1u << bits) - 1u;
+      os_pass_kernel<<<ntiles, SORT_THREADS, OS_SMEM, st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n, shift,
+							    mask, shift == capture_shift ? capture_dest : nullptr);
+      c->launches++;
+      unsigned long long *tk = kin; kin = kout; kout = tk;
+      unsigned int *tv = vin; vin = vout; vout = tv;
+    }
+  G2_CUDA(cudaGetLastError());
+  *keys_io = kin;
+  *vals_io = vin;
+  return 0;
+}
+
 // Sorts n pairs by key bits [begin_bit, end_bit), stable.  *keys_io/*vals_io hold the input and are
 // updated to point at the buffers holding the result (ping-pong with keys_alt/vals_alt).
 // capture_shift >= 0: the pass that starts at that bit also writes capture_dest[i] = output position of its i-th input element.  An LSD
@@ -293,6 +523,8 @@ int g2_radix_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsig
 {
   if(n <= 1 || end_bit <= begin_bit)
     return 0;
+  if(c->sort_onesweep && (capture_shift < 0 || (capture_shift - begin_bit) % OS_BITS == 0))
+    return g2_onesweep_sort_pairs(c, n, keys_io, vals_io, keys_alt, vals_alt, begin_bit, end_bit, capture_shift, capture_dest);
   int ntiles = g2_cdiv(n, SORT_TILE);
   if((size_t) ntiles * RADIX_BINS + 1 > c->tilehist_elems)
     return g2_fail(G2GPU_ERR_ARG, "sort: %d pairs exceed scratch", n);

@@ -123,19 +123,20 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
   A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
   A.cres = c->compact ? c->cres : nullptr;
-  // the scan scratch is free once the slice is known: one slot per target for the FP64 re-walk list
-  A.border_list = (uint4 *) c->w_flags; A.border_count = (unsigned int *) (c->d_counters + 6); A.border_cap = (unsigned int) (c->cfg.max_part / 4);
-  A.redo_list = c->redo_list; A.redo_count = (unsigned int *) (c->d_counters + 6) + 1; A.redo_cap = G2_REDO_CAP;
+  // the scan scratch is free once the slice is known: the list of targets to walk again in FP64
+  A.redo_list = c->w_flags; A.redo_count = (unsigned int *) (c->d_counters + 6); A.redo_cap = (unsigned int) c->cfg.max_part;
   A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;
   A.theta2 = (float) (wp->theta * wp->theta);
   A.errtol = (float) wp->errtol_force_acc;
   A.ex = (const WalkExactParams *) c->d_exact;
   A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
-  // guard bands of the FP32 decisions (g2_walk_kernel.cuh): relative 1e-6 per compared quantity (2e-6 for the fourth-power criterion), several
-  // times the accumulated FP32 rounding of a comparison (a few 1e-7)
-  A.rel_tol = 1.0e-6f;
-  A.pos_ulp8 = (per || sr) ? (float) (8.0 * wp->boxsize * 1.1920929e-7) : 0.0f;	// per-point NEAREST: raw differences of box-scale magnitude
-  A.pos_border = 0.0f;
+  // guard bands of the FP32 decisions (g2_walk_kernel.cuh), each a few times the FP32 rounding its comparison can accumulate: a coordinate
+  // difference against a length 2e-7 -> 4e-7; an r^2 (three products of rounded differences) 3.6e-7 -> 6e-7; the opening criteria (r^4 a
+  // against M len^2) 1.1e-6 -> 1.5e-6.  Where NEAREST is applied per point the raw difference is rounded at box scale: 1e-4.
+  A.tol_pos = 4.0e-7f;
+  A.tol_r2 = 6.0e-7f;
+  A.tol_crit = 1.5e-6f;
+  A.tol_wide = 1.0e-4f;
   A.exact = c->walk_exact;
   if(sr)
     {
@@ -145,8 +146,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
       const double rmax = c->cfg.ntab / asmthfac_d;
       A.rmax2 = (float) (rmax * rmax);
-      A.rmax2_border = (float) (rmax * rmax * 1.0e-6);
-      A.rcut2_border = (float) (wp->rcut * wp->rcut * 1.0e-6);
+      A.rmax2_border = (float) (rmax * rmax * 6.0e-7);
       // a tree that follows the host's drifted nodes (g2gpu_update_tree) may hold centres of mass outside their cubes: neither the
       // geometric cull shortcut nor the per-cell image shift may then be used
       A.shift_len_max = c->tree_dynamic ? 0.0f : (float) (0.499 * wp->boxsize - 1.001 * wp->rcut);

@@ -60,15 +60,14 @@ struct WalkArgs
   float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions); +inf disables the shortcut
   float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
   // guard bands: a comparison whose two sides are closer than this is re-taken in FP64, the arithmetic the reference decides in
-  float pos_border;		// absolute, for differences of coordinates (box cull, 0.6 len test)
-  float rcut2_border, rmax2_border;	// absolute, around rcut^2 and rmax2
-  float rel_tol, pos_ulp8;	// relative tolerance of r^2-based criteria: rel_tol + pos_ulp8 / r
+  float tol_pos;		// relative, for comparisons of a coordinate difference with a length (box cull, 0.6 len test)
+  float tol_r2;			// relative, for comparisons of an r^2 (with rcut^2, h^2)
+  float tol_crit;		// relative, for the opening criteria (M len^2 vs r^4 a; len^2 vs r^2 theta^2)
+  float tol_wide;		// all of them where NEAREST is applied per point (raw differences rounded at box scale)
+  float rmax2_border;		// absolute, around rmax2
   double G, pos_fac_pre_g, pos_fac_post_g;
   const WalkExactParams *__restrict__ ex;
-  uint4 *__restrict__ border_list;	// noted borderline comparisons: slice ordinal of the target, cell / particle index, FP32 outcome
-  unsigned int *__restrict__ border_count;
-  unsigned int border_cap;
-  unsigned int *__restrict__ redo_list;	// slice ordinals of the targets whose FP32 walk deviated from the reference's decisions
+  unsigned int *__restrict__ redo_list;	// slice ordinals of the targets whose FP32 walk met a comparison inside its guard band
   unsigned int *__restrict__ redo_count;
   unsigned int redo_cap;
   int use_gravpm;

@@ -10,10 +10,10 @@
 // Per-lane interaction lists are therefore those of the reference walk; only the summation order differs.
 //
 // Decisions are taken in FP32.  The reference decides in double (forcetree.c:1628-1631), so a target that meets a comparison whose
-// two sides are closer than the FP32 rounding of their inputs allows (guard bands in WalkArgs) is flagged, and walk_redo_kernel walks
-// the tree again for the flagged targets (a fraction of a per cent) in the reference's own double arithmetic, operation by
-// operation: every target's interaction list, and with it GravCost, is then the reference's exactly.  Keeping the FP64 path out of
-// this kernel keeps its 64 registers free of spills.
+// two sides are closer than the FP32 rounding of their inputs allows (guard bands in WalkArgs) is flagged -- one predicated add per
+// visit --, and walk_redo_kernel walks the tree again for the flagged targets (about one per thousand) in the reference's own double
+// arithmetic, operation by operation: every target's interaction list, and with it GravCost, is then the reference's exactly.
+// Keeping the FP64 path out of this kernel keeps its 64 registers free of spills.
 //
 // Node records are (2+D) x 16 B, fetched with 128-bit loads (all lanes read the same address: one L1 broadcast).
 #pragma once
@@ -120,14 +120,6 @@ struct WalkShift
   float tx, ty, tz;		// target coordinate + min(shift, 0)
 };
 
-// A comparison fell inside its guard band: the FP32 decision is applied and noted in the lane state (one event per walk, a second one
-// turns it into G2_EVT_SEVERAL); the walk's epilogue hands it to walk_verify_kernel.  kind: the FP32 decision of a cell visit, or a
-// term event with the FP32 in-range bit.  Rare: a few per thousand targets.
-#define G2_EVT_NODE_TERM 0x10000
-#define G2_EVT_PART_TERM 0x20000
-#define G2_EVT_SEVERAL 0x40000	// more than one borderline comparison in one walk: the target is walked again without further ado
-#define G2_EVT_DECISION 0x80000	// | FP32 decision
-
 // per-lane state of a walk
 struct WalkLane
 {
@@ -135,8 +127,7 @@ struct WalkLane
   int tg;
   float fx, fy, fz;		// FP32 partial sums, flushed into the accumulators whenever the warp descends
   int ninter, nterms, ndec;
-  int evt_kind;			// borderline comparison met during this walk (0: none), and where (cell or particle record)
-  unsigned int evt_where;
+  int nborder;			// comparisons of this walk that fell inside their guard band
   unsigned int skip_until;
 };
 
@@ -152,6 +143,11 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
   bool open = false, done = false, outside = false, border = false;
   if(STATS)
     L.ndec++;
+  // guard bands (EXACT): a few times the FP32 rounding a comparison can accumulate.  Wide where NEAREST is applied per
+  // point (cells too large for the per-cell image shift, and periodic walks without PM): there the raw coordinate difference is
+  // rounded at box scale before the wrap.
+  const bool wide = WRAP && !(SR && q0.x < A.shift_len_max);
+  const float tol_pos = wide ? A.tol_wide : A.tol_pos, tol_r2 = wide ? A.tol_wide : A.tol_r2, tol_crit = wide ? A.tol_wide : A.tol_crit;
   float dx[D], dy[D], dz[D], r2[D], mass[D];
   float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
   const float len = q0.x;
@@ -180,7 +176,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
       outside = t > 0.0f;
       done = t > fmaf(1.0e-3f, len, A.cull_margin);
       if(EXACT)
-	border = fabsf(t) < A.rel_tol * eff;
+	border = fabsf(t) < tol_pos * eff;
     }
   if(!done)
     {
@@ -216,27 +212,22 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	{
 	  const float u = r2min - A.rcut2;
 	  if(outside)
-	    {
-	      done = u > 0.0f;
-	      if(EXACT)
-		border = border || fabsf(u) < A.rcut2_border;
-	    }
-	  else if(EXACT)
-	    border = border && u > -A.rcut2_border;	// the box test is only taken when r2min > rcut^2
+	    done = u > 0.0f;
+	  if(EXACT)		// (the box test only matters when r2min > rcut^2, the r2min test only outside the box: a superset is flagged)
+	    border = border || (outside && fabsf(u) < tol_r2 * A.rcut2);
 	}
     }
   if(!done)
     {
       // The difference of two FP32 coordinates is rounded once, to half an ulp OF THE DIFFERENCE (it is exact when the operands share a
       // binade), so an r^2 built from such differences, and the products compared below, carry a few 1e-7 of relative error whatever
-      // the magnitude of the coordinates: rel_tol covers it with a margin.
-      const float tol = (WRAP && !small_cell) ? fmaf(A.pos_ulp8, fast_rsqrt(r2min), A.rel_tol) : A.rel_tol;	// (per-point NEAREST rounds the raw difference at box scale)
+      // the magnitude of the coordinates.
       if(A.theta2 > 0.0f)
 	{			// Barnes-Hut, forcetree.c:1437-1445
 	  const float lhs = len * len, v = fmaf(-r2min, A.theta2, lhs);
 	  open = v > 0.0f;
 	  if(EXACT)
-	    border = border || fabsf(v) < tol * lhs;
+	    border = border || fabsf(v) < tol_crit * lhs;
 	}
       else
 	{			// relative criterion, forcetree.c:1446-1472
@@ -244,7 +235,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	  const float wv = fmaf(-0.60f, len, fmax3(fabsf(cxr), fabsf(cyr), fabsf(czr)));	// < 0: the target lies inside 0.6 len of the centre on every axis
 	  open = v > 0.0f || wv < 0.0f;
 	  if(EXACT)
-	    border = border || fabsf(v) < 2.0f * tol * lhs || fabsf(wv) < tol * len;
+	    border = border || fabsf(v) < tol_crit * lhs || fabsf(wv) < tol_pos * len;
 	}
     }
   float h = L.hself;
@@ -260,14 +251,9 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	      const float hv = fmaf(-h, h, r2max);
 	      open = hv < 0.0f;
 	      if(EXACT)
-		border = border || fabsf(hv) < 2.0f * A.rel_tol * r2max;
+		border = border || fabsf(hv) < tol_r2 * r2max;
 	    }
 	}
-    }
-  if(EXACT && border)
-    {
-      L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_DECISION | (done ? G2_DEC_CULL : (open ? G2_DEC_OPEN : G2_DEC_ACCEPT)));
-      L.evt_where = cur;
     }
   if(!open)
     {
@@ -282,15 +268,13 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	      if(SR)
 		{
 		  const float tv = r2[g] - A.rmax2;
-		  if(EXACT && fabsf(tv) < A.rmax2_border)
-		    {
-		      L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_NODE_TERM | (g << 8) | (tv < 0.0f ? 1 : 0));
-		      L.evt_where = cur;
-		    }
+		  if(EXACT)
+		    border = border || fabsf(tv) < A.rmax2_border;
 		  counted = counted && tv < 0.0f;
 		}
 	      const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
-	      pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
+	      if(mass[g] != 0.0f)	// a property of the cell, hence uniform: small cells often hold one species only
+		pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
 	      any |= counted;
 	      if(STATS)
 		L.nterms += counted;
@@ -299,6 +283,8 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	    L.ninter++;		// forcetree.c:1585 resp. 2031-2032
 	}
     }
+  if(EXACT)
+    L.nborder += border;	// any comparison of this visit inside its guard band: the target is walked again in FP64
   return open;
 }
 
@@ -347,11 +333,8 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 	    {
 	      const float tv = rr2 - A.rmax2;
 	      counted = tv < 0.0f;
-	      if(EXACT && fabsf(tv) < A.rmax2_border)
-		{
-		  L.evt_kind = L.evt_kind ? G2_EVT_SEVERAL : (G2_EVT_PART_TERM | (counted ? 1 : 0));
-		  L.evt_where = w.y + j;
-		}
+	      if(EXACT)
+		L.nborder += fabsf(tv) < A.rmax2_border;
 	    }
 	  pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz);
 	  L.ninter += counted;
@@ -359,6 +342,35 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 	    L.nterms += counted;
 	}
     }
+}
+
+// One whole visit of the warp at cell `cur` (decisions, vote, flush of the partial sums, particles of an opened cell); returns the
+// next cursor.  The walk loop calls the WRAP or the wrap-free instantiation by a warp-uniform test, so that the wrap-free path carries
+// no image-shift state at all.  ACC accumulators: FP64 in shared memory (acc_sh, one slot per thread) or FP32 in registers (acc_rg).
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, typename ACC>
+__device__ __forceinline__ unsigned int walk_visit(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, unsigned int cur, const float4 *__restrict__ rec,
+						   const float4 q0, const uint4 w, unsigned int t2g_packed, WalkLane &L, ACC (*acc_sh)[WALK_THREADS], ACC &ax, ACC &ay, ACC &az)
+{
+  bool open = false, small_cell = false;
+  WalkShift S;
+  if(cur >= L.skip_until)
+    open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
+  if(__ballot_sync(0xffffffffu, open) == 0u)
+    return w.x;			// nobody opens the cell: on to its sibling
+  // FP32 partial sums go into the accumulators whenever the warp descends (about every third visit): few conversions, bounded
+  // error, and flush points that depend on the traversal only (=> reproducible bits)
+  if(sizeof(ACC) == 8)
+    {
+      acc_sh[0][threadIdx.x] += (ACC) L.fx; acc_sh[1][threadIdx.x] += (ACC) L.fy; acc_sh[2][threadIdx.x] += (ACC) L.fz;
+    }
+  else
+    {
+      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+    }
+  L.fx = L.fy = L.fz = 0.0f;
+  if((w.z & 15u) != 0u)
+    walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
+  return cur + 1u;
 }
 
 // gravity_tree epilogue for one target: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   __shared__ unsigned int s_chunk[WALK_WARPS];
   // the FP64 accumulators of a lane live in shared memory (touched only when the warp descends, about every third visit): six
   // registers less keeps the kernel at 64 registers without spills
-  __shared__ ACC s_acc[3][WALK_THREADS];
+  __shared__ ACC s_acc[sizeof(ACC) == 8 ? 3 : 1][WALK_THREADS];
   if(SR)
     {
       for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
@@ -466,10 +478,12 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       L.hself = A.fsoft[ptype];
       L.fx = L.fy = L.fz = 0.0f;
       L.ninter = L.nterms = L.ndec = 0;
-      L.evt_kind = 0;
-      L.evt_where = 0u;
+      L.nborder = 0;
       L.skip_until = valid ? 0u : 0xffffffffu;
-      s_acc[0][threadIdx.x] = 0; s_acc[1][threadIdx.x] = 0; s_acc[2][threadIdx.x] = 0;
+      if(sizeof(ACC) == 8)
+	{
+	  s_acc[0][threadIdx.x] = 0; s_acc[1][threadIdx.x] = 0; s_acc[2][threadIdx.x] = 0;
+	}
       unsigned int iter = 0;
       unsigned int cur = __any_sync(0xffffffffu, valid) ? 0u : end;
       // TreePM: a target farther than rcut + len/2 (+ margins) from every face of the box needs no periodic image of a cell of size len:
@@ -485,53 +499,33 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	  nowrap_len = fminf(A.shift_len_max, 1.99f * (m - A.rcut - 2.0f * A.cull_margin));
 	}
 
+      ACC rx = 0, ry = 0, rz = 0;	// (register accumulators of the FP32 variant)
       while(cur < end)
 	{
 	  const float4 *rec = A.cells + (size_t) cur * R;
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
-	  const bool wrapv = PERIODIC && !(SR && q0.x < nowrap_len);	// uniform
-	  bool open = false, small_cell = false;
-	  WalkShift S;
-	  S.sx = S.sy = S.sz = S.tx = S.ty = S.tz = 0.0f;
-	  if(cur >= L.skip_until)
-	    {
-	      if(PERIODIC && wrapv)
-		open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
-	      else
-		open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
-	    }
 	  if(STATS)
 	    iter++;
-	  const unsigned int ball = __ballot_sync(0xffffffffu, open);
-	  if(ball != 0u)
-	    {
-	      // FP32 partial sums go into the (FP64) accumulators whenever the warp descends (about every third visit): few
-	      // conversions, bounded error, and flush points that depend on the traversal only (=> reproducible bits)
-	      s_acc[0][threadIdx.x] += (ACC) L.fx; s_acc[1][threadIdx.x] += (ACC) L.fy; s_acc[2][threadIdx.x] += (ACC) L.fz;
-	      L.fx = L.fy = L.fz = 0.0f;
-	      if(PERIODIC && wrapv)
-		walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
-	      else
-		walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
-	      cur = cur + 1u;
-	    }
+	  if(PERIODIC && !(SR && q0.x < nowrap_len))	// uniform
+	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
 	  else
-	    cur = w.x;
+	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
 	}
 
-      const ACC ax = s_acc[0][threadIdx.x] + (ACC) L.fx, ay = s_acc[1][threadIdx.x] + (ACC) L.fy, az = s_acc[2][threadIdx.x] + (ACC) L.fz;
+      const ACC ax = (sizeof(ACC) == 8 ? s_acc[0][threadIdx.x] : rx) + (ACC) L.fx, ay = (sizeof(ACC) == 8 ? s_acc[1][threadIdx.x] : ry) + (ACC) L.fy,
+	az = (sizeof(ACC) == 8 ? s_acc[2][threadIdx.x] : rz) + (ACC) L.fz;
       if(STATS && lane == 0)
 	tot_visits += iter;	// one cursor per warp: visits = loop trips
       if(valid)
 	{
 	  walk_store_result<SR, PERIODIC>(A, idx, tloc, L.px, L.py, L.pz, (float) ax, (float) ay, (float) az, (float) L.ninter);
 	  tot_inter += (unsigned long long) L.ninter;
-	  if(EXACT && L.evt_kind)
-	    {			// to walk_verify_kernel
-	      const unsigned int slot = atomicAdd(A.border_count, 1u);
-	      if(slot < A.border_cap)
-		A.border_list[slot] = make_uint4((unsigned int) tloc, L.evt_where, (unsigned int) L.evt_kind, 0u);
+	  if(EXACT && L.nborder)
+	    {			// to walk_redo_kernel
+	      const unsigned int slot = atomicAdd(A.redo_count, 1u);
+	      if(slot < A.redo_cap)
+		A.redo_list[slot] = (unsigned int) tloc;
 	    }
 	  if(STATS)
 	    {
@@ -564,38 +558,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
     }
 }
 
-// ---- every noted borderline comparison again in the reference's own double arithmetic: where the answer differs from the FP32 one
-//      that was applied, the target goes on the re-walk list (a handful per million targets) ----
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL>
-__global__ void __launch_bounds__(128) walk_verify_kernel(const WalkArgs A)
-{
-  const unsigned int n = min(*A.border_count, A.border_cap);
-  const int lo = A.slice[G2_SLICE_LO];
-  for(unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    {
-      const uint4 e = A.border_list[i];
-      const unsigned int idx = A.targets[lo + (int) e.x];
-      bool differs;
-      if(e.z & G2_EVT_SEVERAL)
-	differs = true;
-      else if(e.z & (G2_EVT_NODE_TERM | G2_EVT_PART_TERM))
-	{
-	  const G2PRec tp = A.prec[idx];
-	  const float4 q = (e.z & G2_EVT_NODE_TERM) ? __ldg(A.cells + (size_t) e.y * (2 + D) + 1 + ((e.z >> 8) & 15)) : __ldg(A.wpart + e.y);
-	  differs = term_in_range_exact<PERIODIC>(A.ex, q.x, q.y, q.z, tp.x, tp.y, tp.z) != ((e.z & 1u) != 0u);
-	}
-      else
-	differs = walk_decide_exact<D, SR, PERIODIC, UNEQUAL>(A.ex, A.cells + (size_t) e.y * (2 + D), A.prec + idx) != (int) (e.z & 3u);
-      if(differs)
-	{
-	  const unsigned int slot = atomicAdd(A.redo_count, 1u);
-	  if(slot < A.redo_cap)
-	    A.redo_list[slot] = e.x;
-	}
-    }
-}
-
-// ---- the walk of a target whose FP32 walk took a decision the reference would not have taken: ONE WARP per target, in the
+// ---- the walk of a target whose FP32 walk met a comparison inside its guard band, again: ONE WARP per target, in the
 //      reference's own arithmetic (double locals, FLOAT node and particle fields, decisions by walk_decide_exact, tabindex =
 //      (int) (asmthfac * r): forcetree.c:1244-1610 and 1623-2052 restated over the depth-first records).  The depth-first array is
 //      walked in disjoint index ranges, one per lane: lane 0 starts with the whole tree, and whenever a lane is idle a busy lane hands
@@ -619,12 +582,6 @@ __global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const W
   for(unsigned int i = blockIdx.x * WALK_REDO_WARPS + (threadIdx.x >> 5); i < nredo; i += nwarps)
     {
       const int tloc = (int) A.redo_list[i];
-      // a target that was noted twice is walked by the first of its entries only
-      bool dup = false;
-      for(unsigned int k = lane; k < i; k += 32)
-	dup = dup || A.redo_list[k] == (unsigned int) tloc;
-      if(__any_sync(0xffffffffu, dup))
-	continue;
       const unsigned int idx = A.targets[lo + tloc];
       const G2PRec tp = A.prec[idx];
       const double px = (double) tp.x, py = (double) tp.y, pz = (double) tp.z, box = E->boxsize;
@@ -766,7 +723,7 @@ __global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const W
   if(blockIdx.x == 0 && threadIdx.x == 0)
     {
       A.counters[5] = (unsigned long long) nredo;
-      A.counters[7] = (unsigned long long) *A.border_count;
+      A.counters[7] = (unsigned long long) *A.redo_count;	// flagged (> nredo: the list was full, the rest keep their FP32 walk)
     }
 }
 
@@ -778,11 +735,10 @@ static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
   walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT><<<grid, WALK_THREADS, smem, c->stream>>>(A);
   if(EXACT)
     {
-      walk_verify_kernel<D, SR, PERIODIC, UNEQUAL><<<c->nsm * 4, 128, 0, c->stream>>>(A);
       if(smem > 48 * 1024)
 	G2_CUDA(cudaFuncSetAttribute(walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-      walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK><<<c->nsm * 2, 32 * WALK_REDO_WARPS, smem, c->stream>>>(A);
-      c->launches += 2;
+      walk_redo_kernel<D, SR, PERIODIC, UNEQUAL, STOCK><<<c->nsm * 6, 32 * WALK_REDO_WARPS, smem, c->stream>>>(A);
+      c->launches++;
     }
   return 0;
 }

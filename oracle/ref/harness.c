@@ -519,6 +519,22 @@ int g2ref_potential(double *out, int nthreads)
 #endif
 }
 
+/* the shipped pair potentials by name (ngravs.c:368, 459, 672, 708, 734): they are compiled in every variant, whereas the
+ * PotentialFxns tables exist only under PMGRID / OUTPUTPOTENTIAL -- and the BAM wiring (ngravs.c:172-200) leaves NormedGreensFxns
+ * unset, so a PMGRID build with that wiring ends in a null call during set-up and cannot be run. */
+double g2ref_named_pot(int which, double pm, double m, double h, double r, long n)
+{
+  switch (which)
+    {
+    case 0: return bambam_pot(pm, m, h, r, n);
+    case 1: return sourcebaryonbam_pot(pm, m, h, r, n);
+    case 2: return sourcebambaryon_pot(pm, m, h, r, n);
+    case 3: return newtonian_pot(pm, m, h, r, n);
+    case 4: return plummer_pot(pm, m, h, r, n);
+    default: return 0.0 / 0.0;
+    }
+}
+
 /* potential pair-law probes (allvars.h:147-148) */
 double g2ref_potfxn(int tgt, int src, double pm, double m, double h, double r, long n)
 {

@@ -248,6 +248,12 @@ class RefOracle:
         self.lib.g2ref_potfxn.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
         return self.lib.g2ref_potfxn(tgt, src, pm, m, h, r, n)
 
+    def named_pot(self, which, pm, m, h, r, n=1):
+        """bambam_pot (0), sourcebaryonbam_pot (1), sourcebambaryon_pot (2), newtonian_pot (3), plummer_pot (4) called directly."""
+        self.lib.g2ref_named_pot.restype = C.c_double
+        self.lib.g2ref_named_pot.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
+        return self.lib.g2ref_named_pot(int(which), pm, m, h, r, n)
+
     def potspline(self, tgt, src, pm, m, h, r, n=1):
         self.lib.g2ref_potspline.restype = C.c_double
         self.lib.g2ref_potspline.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_long]
