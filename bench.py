@@ -269,11 +269,14 @@ def main():
     # group), so the other ranks only meet rank 0 at the barriers
     dist = None
     if world > 1:
+        import datetime
         import torch.distributed as dist
+        from torch.distributed.distributed_c10d import _get_default_store
         dist.init_process_group("gloo")
+        # no collective at the end of the run: a rank that leaves a gloo barrier first closes its sockets under the others.  Rank 0
+        # posts a key in the launcher's store when it is done and the other ranks wait for it.
         if rank != 0:
-            dist.barrier()
-            dist.barrier()
+            _get_default_store().wait(["g2gpu_bench_done"], datetime.timedelta(hours=8))
             dist.destroy_process_group()
             return
 
@@ -287,8 +290,6 @@ def main():
     config = config_of(w, n_active, args.active_frac, ngpu)
 
     if args.impl == "reference":
-        if dist is not None:
-            dist.barrier()
         r = reference_run(w, None, K, W, nthreads=ref_threads)
         line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": ngpu, "steps": K, "warmup": W, "ms_per_step": r["ms_timed_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
@@ -299,7 +300,7 @@ def main():
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=real_stdout, flush=True)
         if dist is not None:
-            dist.barrier()
+            _get_default_store().set("g2gpu_bench_done", "1")
             dist.destroy_process_group()
         return
 
@@ -362,8 +363,6 @@ def main():
         flush_l2()
         grp.step_resident(n, wp_rel)
     barrier()
-    if dist is not None:
-        dist.barrier()
     sampler.begin()
     stage = dict(domain_ms=0.0, build_ms=0.0, walk_ms=0.0, walk_kernel_ms=0.0, sort_ms=0.0)
     launches0 = grp.timings()["launches"]
@@ -569,8 +568,7 @@ def main():
     print(json.dumps(line), file=real_stdout, flush=True)
     grp.close()
     if dist is not None:
-        dist.barrier()
-        dist.barrier()
+        _get_default_store().set("g2gpu_bench_done", "1")
         dist.destroy_process_group()
 
 

@@ -568,6 +568,14 @@ extern "C" int g2gpu_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
   return g2_pm_periodic(c, pp);
 }
 
+extern "C" int g2gpu_pm_potential_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp, float *potential)
+{
+  if(!c || !pp || !potential)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_pm_potential_periodic(c, pp, potential);
+}
+
 extern "C" int g2gpu_download_gravpm(g2gpu_ctx *c, float *gravpm)
 {
   if(!c || !gravpm)

@@ -258,6 +258,7 @@ int g2_make_ewald_table(g2gpu_ctx *c, int en, double *out);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);
 int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp);
+int g2_pm_potential_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp, float *potential);
 int g2_pm_download(g2gpu_ctx *c, float *gravpm);
 void g2_pm_destroy(g2gpu_ctx *c);
 int g2_direct_sum(g2gpu_ctx *c, const g2gpu_walk_params *wp, int ntargets, const int *targets, double *acc);

@@ -444,9 +444,9 @@ static int fetch_slice_results(g2gpu_group *g, int i)
 }
 
 template <class W>
-static void scatter_threads(size_t cnt, unsigned int nthr, W work)
+static void scatter_threads(size_t cnt, unsigned int nthr, W work, size_t min_per_thread = 131072)
 {
-  nthr = std::max(1u, std::min(nthr, (unsigned int) (cnt / 131072 + 1)));
+  nthr = std::max(1u, std::min(nthr, (unsigned int) (cnt / min_per_thread + 1)));
   if(nthr == 1)
     {
       work(0, cnt);
@@ -470,12 +470,27 @@ static void rebalance(g2gpu_group *g)
     return;
   const int nb = (nt + G2_COST_BLOCK - 1) / G2_COST_BLOCK;
   g->profile.assign((size_t) nb, 0.0);
+  const unsigned int hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   for(int i = 0; i < g->n; i++)
     {
+      // blocks of the profile that overlap this device's slice, shared out over host threads (a block is summed by one thread; the
+      // block that straddles two slices is visited once per slice, and the slices are taken one after the other)
       const float *r = g->h_res[i];
-      const int lo = g->lo[i], cnt = g->hi[i] - g->lo[i];
-      for(int k = 0; k < cnt; k++)
-	g->profile[(size_t) (lo + k) / G2_COST_BLOCK] += (double) r[5 * (size_t) k + 3] + 1.0;	// + 1: a target costs something even without interactions
+      const int lo = g->lo[i], hi = g->hi[i];
+      if(hi <= lo)
+	continue;
+      const size_t b0 = (size_t) lo / G2_COST_BLOCK, b1 = (size_t) (hi - 1) / G2_COST_BLOCK + 1;
+      double *prof = g->profile.data();
+      scatter_threads(b1 - b0, hw, [=](size_t a, size_t b) {
+	for(size_t blk = b0 + a; blk < b0 + b; blk++)
+	  {
+	    const size_t t0 = std::max((size_t) lo, blk * G2_COST_BLOCK), t1 = std::min((size_t) hi, (blk + 1) * G2_COST_BLOCK);
+	    double s = 0.0;
+	    for(size_t t = t0; t < t1; t++)
+	      s += (double) r[5 * (t - (size_t) lo) + 3] + 1.0;	// + 1: a target costs something even without interactions
+	    prof[blk] += s;
+	  }
+      }, 128);
     }
   g->profile_ntargets = nt;
   double total = 0;

@@ -86,9 +86,12 @@ __device__ __forceinline__ double pm_greens(int id, double par, double k2, doubl
 
 // tab[i] = exp(-k_i^2 asmth2) / sinc(pi k_i / N)^4 for mesh index i (k_i = i > N/2 ? i - N : i): the Gaussian long-range filter and the
 // twofold CIC deconvolution of pm_periodic.c:487-513 factorise over the three dimensions; the table is filled on the host in double.
-template <int D>
+// POT (pmpotential_periodic, pm_periodic.c:1014-1063): the same filter times `scale` = G / (pi L), and the k = 0 mode is KEPT (:1033-1035).
+// The reference resets that mode only when its real part is NaN (:1060-1063); with the stock 1/k^2 it is -inf and every potential
+// comes out infinite, so here a k = 0 mode that is not finite is set to zero -- what the comment at :1058 says the reset is for.
+template <int D, bool POT>
 __global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PMGreens Gf, const double *__restrict__ tab, const double2 *__restrict__ rk,
-							 size_t kstride, double2 *__restrict__ potk)
+							 size_t kstride, double2 *__restrict__ potk, double scale)
 {
   const int nzh = N / 2 + 1;
   const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,19 +101,52 @@ __global__ void __launch_bounds__(256) pm_filter_kernel(int N, double asmth2, PM
   const double kx = x > N / 2 ? x - N : x, ky = y > N / 2 ? y - N : y, kz = z;	// pm_periodic.c:472-485
   const double k2 = kx * kx + ky * ky + kz * kz;
   double2 out = make_double2(0.0, 0.0);
-  if(k2 > 0)
+  if(POT || k2 > 0)
     {
       const double filt = -(__ldg(tab + x) * __ldg(tab + y) * __ldg(tab + z));	// :513
 #pragma unroll
       for(int nA = 0; nA < D; nA++)
 	{
-	  const double smth = pm_greens(Gf.id[nA], Gf.par[nA], k2, asmth2) * filt;
+	  if(POT && Gf.id[nA] == G2GPU_GREENS_NONE)
+	    continue;		// (0 x an infinite density mode would be NaN)
+	  const double smth = POT ? pm_greens(Gf.id[nA], Gf.par[nA], k2, asmth2) * filt * scale : pm_greens(Gf.id[nA], Gf.par[nA], k2, asmth2) * filt;
 	  const double2 r = rk[(size_t) nA * kstride + idx];
 	  out.x += r.x * smth;
 	  out.y += r.y * smth;
 	}
+      if(POT && idx == 0 && !(isfinite(out.x) && isfinite(out.y)))
+	out = make_double2(0.0, 0.0);
     }
-  potk[idx] = out;		// k = 0: zero (:525-526)
+  potk[idx] = out;		// force: k = 0 is zero (:525-526)
+}
+
+// pmpotential_periodic :1236-1267: trilinear (CIC) interpolation of the potential mesh of the particle's own species
+__global__ void __launch_bounds__(256) pm_potgather_kernel(PMArgs A, const double *__restrict__ phi_all, float *__restrict__ pot)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= A.n)
+    return;
+  const G2PRec p = A.rec[i];
+  const int N = A.N;
+  const double *__restrict__ phi = phi_all + (size_t) ((A.t2g_packed >> (4 * min(max(p.type, 0), 5))) & 7u) * N * N * N;
+  int sx, sy, sz;
+  double dx, dy, dz;
+  pm_cell(A, p.x, sx, dx);
+  pm_cell(A, p.y, sy, dy);
+  pm_cell(A, p.z, sz, dz);
+  const int sxx = sx + 1 == N ? 0 : sx + 1, syy = sy + 1 == N ? 0 : sy + 1, szz = sz + 1 == N ? 0 : sz + 1;
+#define G2_PHI(X, Y, Z) __ldg(phi + ((size_t) (X) * N + (Y)) * N + (Z))
+  // corner order and products as in pm_periodic.c:1254-1267
+  double acc = G2_PHI(sx, sy, sz) * (1.0 - dx) * (1.0 - dy) * (1.0 - dz);
+  acc += G2_PHI(sx, syy, sz) * (1.0 - dx) * dy * (1.0 - dz);
+  acc += G2_PHI(sx, sy, szz) * (1.0 - dx) * (1.0 - dy) * dz;
+  acc += G2_PHI(sx, syy, szz) * (1.0 - dx) * dy * dz;
+  acc += G2_PHI(sxx, sy, sz) * dx * (1.0 - dy) * (1.0 - dz);
+  acc += G2_PHI(sxx, syy, sz) * dx * dy * (1.0 - dz);
+  acc += G2_PHI(sxx, sy, szz) * dx * (1.0 - dy) * dz;
+  acc += G2_PHI(sxx, syy, szz) * dx * dy * dz;
+#undef G2_PHI
+  pot[i] = (float) acc;		// P[i].Potential is a FLOAT
 }
 
 // Finite differences (:726-737) + trilinear interpolation (:739-781) fused: the 4-point difference along one dimension at the 8 corners of
@@ -228,15 +264,21 @@ static int pm_reserve(g2gpu_ctx *c, int N)
 }
 
 template <int D>
-static void launch_filter(g2gpu_ctx *c, int N, double asmth2, const PMGreens &Gf)
+static void launch_filter(g2gpu_ctx *c, int N, double asmth2, const PMGreens &Gf, bool pot, double scale)
 {
   const size_t ncpx = (size_t) N * N * (N / 2 + 1);
-  pm_filter_kernel<D><<<g2_cdiv((long long) ncpx, 256), 256, 0, c->stream>>>(N, asmth2, Gf, (const double *) c->pm_tab, (const double2 *) c->pm_rk, ncpx,
-										 (double2 *) c->pm_potk);
+  if(pot)
+    pm_filter_kernel<D, true><<<g2_cdiv((long long) ncpx, 256), 256, 0, c->stream>>>(N, asmth2, Gf, (const double *) c->pm_tab, (const double2 *) c->pm_rk, ncpx,
+											     (double2 *) c->pm_potk, scale);
+  else
+    pm_filter_kernel<D, false><<<g2_cdiv((long long) ncpx, 256), 256, 0, c->stream>>>(N, asmth2, Gf, (const double *) c->pm_tab, (const double2 *) c->pm_rk, ncpx,
+											      (double2 *) c->pm_potk, scale);
 }
 
-int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
+// pmforce_periodic (potential == nullptr) or pmpotential_periodic (potential = host array of n floats, upload order)
+static int pm_run(g2gpu_ctx *c, const g2gpu_pm_params *pp, float *potential)
 {
+  const bool pot = potential != nullptr;
   if(c->stage < 1)
     return g2_fail(G2GPU_ERR_STATE, "PM: no particles uploaded");
   const int N = pp->pmgrid, n = c->npart, D = c->D;
@@ -248,7 +290,8 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
   G2_TRY(pm_reserve(c, N));
   // the result becomes the GravPM input of the next domain stage / dynamic update: both the upload-order and the current-order array
   // must exist (gather_kernel and dyn_particles_kernel write the latter)
-  G2_TRY(g2_ensure_optional_inputs(c, 0, 1));
+  if(!pot)
+    G2_TRY(g2_ensure_optional_inputs(c, 0, 1));
   cudaStream_t st = c->stream;
   G2_CUDA(cudaEventRecord(c->ev[13], st));
 
@@ -260,7 +303,8 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
     A.t2g_packed |= (unsigned int) c->type_to_grav[t] << (4 * t);
   double asmth2 = (2 * M_PI) * pp->asmth / pp->boxsize;	// pm_periodic.c:232-233
   asmth2 *= asmth2;
-  double fac = pp->G / (M_PI * pp->boxsize);	// :236-237
+  double fac = pp->G / (M_PI * pp->boxsize);	// :236-237 (force), :832 (potential)
+  const double potfac = fac;
   fac *= 1 / (2 * pp->boxsize / N);
   const size_t nreal = (size_t) N * N * N, ncpx = (size_t) N * N * (N / 2 + 1);
 
@@ -314,17 +358,32 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
 	}
       switch (D)
 	{
-	case 1: launch_filter<1>(c, N, asmth2, Gf); break;
-	case 2: launch_filter<2>(c, N, asmth2, Gf); break;
-	case 3: launch_filter<3>(c, N, asmth2, Gf); break;
-	case 4: launch_filter<4>(c, N, asmth2, Gf); break;
-	case 5: launch_filter<5>(c, N, asmth2, Gf); break;
-	case 6: launch_filter<6>(c, N, asmth2, Gf); break;
+	case 1: launch_filter<1>(c, N, asmth2, Gf, pot, potfac); break;
+	case 2: launch_filter<2>(c, N, asmth2, Gf, pot, potfac); break;
+	case 3: launch_filter<3>(c, N, asmth2, Gf, pot, potfac); break;
+	case 4: launch_filter<4>(c, N, asmth2, Gf, pot, potfac); break;
+	case 5: launch_filter<5>(c, N, asmth2, Gf, pot, potfac); break;
+	case 6: launch_filter<6>(c, N, asmth2, Gf, pot, potfac); break;
 	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
 	}
       c->launches++;
       if(cufftExecZ2D((cufftHandle) c->pm_inv, (cufftDoubleComplex *) c->pm_potk, (cufftDoubleReal *) c->pm_rho + (size_t) nB * nreal) != CUFFT_SUCCESS)
 	return g2_fail(G2GPU_ERR_CUDA, "PM: inverse FFT failed");
+    }
+  if(pot)
+    {
+      // the spectra are consumed: their storage takes the per-particle result until it is copied out
+      float *d_pot = (float *) c->pm_rk;
+      if(sizeof(float) * (size_t) n > sizeof(double2) * ncpx * D)
+	return g2_fail(G2GPU_ERR_NOMEM, "PM potential: %d particles need more staging than the %d^3 spectra provide", n, N);
+      pm_potgather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, (const double *) c->pm_rho, d_pot);
+      c->launches++;
+      G2_CUDA(cudaEventRecord(c->ev[14], st));
+      G2_CUDA(cudaGetLastError());
+      G2_CUDA(cudaMemcpyAsync(potential, d_pot, sizeof(float) * (size_t) n, cudaMemcpyDeviceToHost, st));
+      G2_CUDA(cudaStreamSynchronize(st));
+      c->d2h_bytes = sizeof(float) * (size_t) n;
+      return 0;
     }
   pm_gather_kernel<<<g2_cdiv(n, 256), 256, 0, st>>>(A, (const double *) c->pm_rho, fac, c->in_gravpm);	// writes every particle (longrange.c:67)
   c->launches++;
@@ -333,6 +392,15 @@ int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp)
   c->have_gravpm = 1;		// the next g2gpu_domain carries GravPM along for the OldAcc term of the walk (gravtree.c:318-331)
   c->pm_done = 1;
   return 0;
+}
+
+int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp) { return pm_run(c, pp, nullptr); }
+
+int g2_pm_potential_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp, float *potential)
+{
+  if(!potential)
+    return g2_fail(G2GPU_ERR_ARG, "PM potential: null output array");
+  return pm_run(c, pp, potential);
 }
 
 int g2_pm_download(g2gpu_ctx *c, float *gravpm)

@@ -24,7 +24,7 @@ EXPORTED = [
     "g2gpu_set_srtable", "g2gpu_upload", "g2gpu_upload_aos", "g2gpu_input_buffers", "g2gpu_inputs_ready", "g2gpu_bind_inputs", "g2gpu_io_bytes", "g2gpu_domain",
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings", "g2gpu_get_counts",
-    "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
+    "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_pm_potential_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
     "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table",
     "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential", "g2gpu_eval_potentials",
     "g2gpu_group_create", "g2gpu_group_destroy", "g2gpu_group_size", "g2gpu_group_ctx", "g2gpu_group_set_species", "g2gpu_group_set_laws",
@@ -354,9 +354,7 @@ class TreeGravity:
         self._chk(self.lib.g2gpu_update_tree(self.ctx, _p(l), _p(ss)))
 
     # ---- long_range_force -> pmforce_periodic (longrange.c:56, pm_periodic.c:204) --------------------------------------
-    def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None, download=True):
-        """Periodic PM long-range force of the particles uploaded last; returns GravPM[n,3] in upload order.
-        greens: a name for all pairs or a D x D nested list indexed [source][target] like GreensFxns[nA][nB]."""
+    def _pm_params(self, pmgrid, boxsize, G, asmth, greens, greens_par):
         D = self.D
         pp = PMParams()
         pp.pmgrid, pp.boxsize, pp.G = int(pmgrid), float(boxsize), float(G)
@@ -366,6 +364,19 @@ class TreeGravity:
                 name = greens if isinstance(greens, str) else greens[a][b]
                 pp.greens_id[a * D + b] = GREENS[name]
                 pp.greens_par[a * D + b] = 0.0 if greens_par is None else float(np.asarray(greens_par).reshape(D, D)[a, b])
+        return pp
+
+    def pm_potential_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None):
+        """pmpotential_periodic (pm_periodic.c:798): what it adds to P[].Potential, float32[n] in upload order."""
+        pp = self._pm_params(pmgrid, boxsize, G, asmth, greens, greens_par)
+        out = np.zeros(self.n, dtype=np.float32)
+        self._chk(self.lib.g2gpu_pm_potential_periodic(self.ctx, C.byref(pp), _p(out)))
+        return out
+
+    def pm_periodic(self, pmgrid, boxsize, G=1.0, asmth=None, greens="pgdelta", greens_par=None, download=True):
+        """Periodic PM long-range force of the particles uploaded last; returns GravPM[n,3] in upload order.
+        greens: a name for all pairs or a D x D nested list indexed [source][target] like GreensFxns[nA][nB]."""
+        pp = self._pm_params(pmgrid, boxsize, G, asmth, greens, greens_par)
         self._chk(self.lib.g2gpu_pm_periodic(self.ctx, C.byref(pp)))
         if not download:
             return None

@@ -472,6 +472,29 @@ void pm_init_periodic(void)	/* pm_periodic.c:53: no FFTW plans or slab tables to
 void pm_init_periodic_allocate(int dimprod) { (void) dimprod; }	/* the meshes live on the device */
 void pm_init_periodic_free(void) { }
 
+static void g2_fill_pm_params(g2gpu_pm_params * pp)
+{
+  int nA, nB;
+  memset(pp, 0, sizeof(*pp));
+  pp->pmgrid = PMGRID;
+  pp->boxsize = All.BoxSize;
+  pp->asmth = All.Asmth[0];
+  pp->G = All.G;
+  for(nA = 0; nA < N_GRAVS; nA++)
+    for(nB = 0; nB < N_GRAVS; nB++)
+      {
+	int id = g2_greens_id(GreensFxns[nA][nB]);
+	if(id < 0)
+	  {
+	    printf("ngravs/g2gpu: GreensFxns[%d][%d] has no device implementation.\n"
+		   "Register it in include/g2gpu.h (enum g2gpu_greens) and csrc/g2_pm.cu.\n", nA, nB);
+	    endrun(7312);
+	  }
+	pp->greens_id[nA * N_GRAVS + nB] = id;
+	pp->greens_par[nA * N_GRAVS + nB] = YUKAWA_IMASS / (2 * M_PI);	/* ngravs.c:871 */
+      }
+}
+
 /* pm_periodic.c:204.  long_range_force() (longrange.c:56) calls it before gravity_tree() (accel.c:36-46) with P[] in whatever
  * order the last domain decomposition left; the device version does not need species blocks, so P[] is uploaded as it is and
  * P[].GravPM is read back in the same order. */
@@ -479,7 +502,7 @@ void pmforce_periodic(void)
 {
   g2gpu_pm_params pp;
   float *gpm;
-  int i, nA, nB;
+  int i;
 
   if(ThisTask == 0)
     {
@@ -491,24 +514,7 @@ void pmforce_periodic(void)
       printf("g2gpu: pmforce_periodic() before force_treeallocate()\n");
       endrun(7311);
     }
-  memset(&pp, 0, sizeof(pp));
-  pp.pmgrid = PMGRID;
-  pp.boxsize = All.BoxSize;
-  pp.asmth = All.Asmth[0];
-  pp.G = All.G;
-  for(nA = 0; nA < N_GRAVS; nA++)
-    for(nB = 0; nB < N_GRAVS; nB++)
-      {
-	int id = g2_greens_id(GreensFxns[nA][nB]);
-	if(id < 0)
-	  {
-	    printf("ngravs/g2gpu: GreensFxns[%d][%d] has no device implementation.\n"
-		   "Register it in include/g2gpu.h (enum g2gpu_greens) and csrc/g2_pm.cu.\n", nA, nB);
-	    endrun(7312);
-	  }
-	pp.greens_id[nA * N_GRAVS + nB] = id;
-	pp.greens_par[nA * N_GRAVS + nB] = YUKAWA_IMASS / (2 * M_PI);	/* ngravs.c:871 */
-      }
+  g2_fill_pm_params(&pp);
   g2_push_tables();
   g2_upload(NumPart);
   g2_check(g2gpu_pm_periodic(G2, &pp), "pm_periodic");
@@ -532,10 +538,39 @@ void pmforce_periodic(void)
     }
 }
 
-void pmpotential_periodic(void)	/* pm_periodic.c:800, outside the replaced path */
+/* pm_periodic.c:798: the long-range potential, added to P[].Potential (compute_potential, potential.c:271).  One device pass
+ * (g2gpu_pm_potential_periodic); see include/g2gpu.h for the k = 0 mode. */
+void pmpotential_periodic(void)
 {
-  printf("g2gpu: pmpotential_periodic() is not provided by the shim; build with -DG2_SHIM_KEEP_REFERENCE_PM and FFTW-2 to use it.\n");
-  endrun(7313);
+  g2gpu_pm_params pp;
+  float *pot;
+  int i;
+
+  if(ThisTask == 0)
+    {
+      printf("Starting periodic PM calculation.\n");
+      fflush(stdout);
+    }
+  if(!G2)
+    {
+      printf("g2gpu: pmpotential_periodic() before force_treeallocate()\n");
+      endrun(7313);
+    }
+  g2_fill_pm_params(&pp);
+  g2_push_tables();
+  g2_upload(NumPart);
+  pot = malloc(sizeof(float) * (size_t) NumPart);
+  g2_check(g2gpu_pm_potential_periodic(G2, &pp, pot), "pm_potential_periodic");
+  for(i = 0; i < NumPart; i++)
+    P[i].Potential += pot[i];
+  free(pot);
+  All.NumForcesSinceLastDomainDecomp = 1 + All.TotNumPart * All.TreeDomainUpdateFrequency;	/* pm_periodic.c:1283 */
+  TreeReconstructFlag = 1;
+  if(ThisTask == 0)
+    {
+      printf("done PM-Potential.\n");
+      fflush(stdout);
+    }
 }
 #endif
 

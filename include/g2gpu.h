@@ -255,6 +255,13 @@ int g2gpu_download_potential(g2gpu_ctx *ctx, float *pot, double *kernel_ms);
  *      of the next g2gpu_domain/g2gpu_walk (walk_params.use_gravpm), as if it had been passed to g2gpu_upload. ---- */
 int g2gpu_pm_periodic(g2gpu_ctx *ctx, const g2gpu_pm_params *pp);
 int g2gpu_download_gravpm(g2gpu_ctx *ctx, float *gravpm);	/* P[].GravPM, n x 3, upload order */
+/* pmpotential_periodic (pm_periodic.c:798-1290; compute_potential calls it at potential.c:271, after the tree potential): the long-range
+ * potential of the particle records uploaded last.  potential[n] (host, UPLOAD order) receives what the reference's routine ADDS to
+ * P[].Potential: CIC assignment per species, FFT, -exp(-k^2 asmth^2) x GreensFxns[source][target](k) x G/(pi L) / sinc^4, inverse FFT, CIC
+ * interpolation of the potential mesh.  The k = 0 mode is kept like the reference keeps it (:1033-1035) when it is finite (Yukawa-type
+ * Green's functions); for 1/k^2 the reference leaves an infinite mode in (its reset at :1060-1063 only catches NaN) and returns infinite
+ * potentials -- here that mode is set to zero.  GravPM and the state of the force path are untouched. */
+int g2gpu_pm_potential_periodic(g2gpu_ctx *ctx, const g2gpu_pm_params *pp, float *potential);
 
 /* acc[3n] = P[].GravAccel (after the G scaling), cost[n] = P[].GravCost, oldacc[n] = P[].OldAcc, in CURRENT
  * particle order; only entries of active particles of this rank's slice are written. */

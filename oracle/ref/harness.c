@@ -620,10 +620,10 @@ size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE * stream) { return f
 /* ---- periodic PM long-range force (pm_periodic.c:204-790), single rank through the rfftwnd_mpi stand-in ----
  * P[] must be in the order domain_Decomposition() left it (species blocks, NgravLocal[] set: pm_periodic.c:251-254).
  * out: GravPM of every particle (n x 3, as double), in the current order of P[]. */
+static int pm_ready = 0;
 int g2ref_pmforce(double *out)
 {
 #if defined(PMGRID) && defined(PERIODIC)
-  static int pm_ready = 0;
   int i, k;
   if(!pm_ready)
     {
@@ -635,6 +635,30 @@ int g2ref_pmforce(double *out)
   for(i = 0; i < NumPart; i++)
     for(k = 0; k < 3; k++)
       out[3 * i + k] = P[i].GravPM[k];
+  return 0;
+#else
+  (void) out;
+  return -1;
+#endif
+}
+
+/* ---- periodic PM long-range potential (pmpotential_periodic, pm_periodic.c:798-1300), single rank.  P[].Potential is zeroed first, so
+ * out[i] is what the routine ADDS to the potential of particle i (current order of P[], species blocks). ---- */
+int g2ref_pmpotential(double *out)
+{
+#if defined(PMGRID) && defined(PERIODIC)
+  int i;
+  if(!pm_ready)
+    {
+      pm_init_periodic();
+      pm_ready = 1;
+    }
+  for(i = 0; i < NumPart; i++)
+    P[i].Potential = 0;
+  pmpotential_periodic();	/* frees and re-allocates the tree storage like pmforce_periodic */
+  TreeReconstructFlag = 1;
+  for(i = 0; i < NumPart; i++)
+    out[i] = P[i].Potential;
   return 0;
 #else
   (void) out;

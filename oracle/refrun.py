@@ -181,6 +181,14 @@ class RefOracle:
             raise RuntimeError("this oracle variant was compiled without PMGRID/PERIODIC")
         return out
 
+    def pmpotential(self):
+        """What pmpotential_periodic (pm_periodic.c:798) adds to P[].Potential, current order of P[]; PM variants only."""
+        out = np.zeros(self.n)
+        rc = self.lib.g2ref_pmpotential(out.ctypes.data_as(C.c_void_p))
+        if rc != 0:
+            raise RuntimeError("this oracle variant was compiled without PMGRID/PERIODIC")
+        return out
+
     def topnodes(self):
         nt = self.lib.g2ref_ntopnodes()
         nl = self.lib.g2ref_ntopleaves()

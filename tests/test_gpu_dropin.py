@@ -119,6 +119,32 @@ def test_reference_pm_call_runs_on_the_gpu(outdir):
     assert np.median(rel) <= 1e-5 and np.percentile(rel, 99.9) <= 1e-3
 
 
+def test_reference_pm_potential_call_runs_on_the_gpu(outdir):
+    """pmpotential_periodic() of the shim (one device pass, g2gpu_pm_potential_periodic) against the unmodified pm_periodic.c:798, in the
+    Yukawa wiring, whose k = 0 Green's function is finite (with 1/k^2 the reference's own result is infinite)."""
+    variant = "pm64_yuk_f32"
+    if not (available(variant) and available(variant, "g2shim")):
+        pytest.skip("oracle/_ref (reference and shim builds) not present")
+    _preload()
+    n, box = 32768, 100000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=17)
+    mass = (1.0 + 0.5 * np.random.default_rng(1).random(n)).astype(np.float32)
+    kw = dict(boxsize=box, softening=(box / 32 / 30.0,) * 6, gravity=g2test.GRAV_D2, G=43007.1)
+    out = {}
+    for name, prefix in (("ref", "g2ref"), ("shim", "g2shim")):
+        o = RefOracle(variant, int(1.1 * n) + 64, prefix=prefix, **kw)
+        o.load(pos, mass, ptype)
+        o.domain()
+        pot = o.pmpotential()
+        p = o.particles()
+        full = np.zeros(n); full[p["id"]] = pot
+        out[name] = full
+    scale = np.abs(out["ref"]).max()
+    assert np.isfinite(out["ref"]).all() and scale > 0
+    assert np.abs(out["shim"] - out["ref"]).max() <= 1e-5 * scale
+    assert np.median(np.abs(out["shim"] - out["ref"]) / np.maximum(np.abs(out["ref"]), 1e-30)) <= 1e-5
+
+
 def test_reference_potential_loop_runs_on_the_gpu(outdir):
     """The loop of compute_potential() (potential.c:86-97: force_treeevaluate_potential_shortrange(i, 0) for every particle) through the
     shim's entry point -- one device walk of all particles behind the reference's per-target function -- against the unmodified

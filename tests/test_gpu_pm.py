@@ -194,3 +194,79 @@ def test_full_size_treepm_total_force_against_ewald(side, ntargets, outdir):
               open(os.path.join(outdir, f"fullsize_treepm_total_vs_ewald_{side}.json"), "w"))
     print(f"TreePM total vs Ewald at {side}^3: median {np.median(err):.3e} p90 {np.percentile(err, 90):.3e} max {err.max():.3e}")
     assert np.median(err) < 1.5e-2 and err.max() < 0.15
+
+
+# ---- pmpotential_periodic (pm_periodic.c:798), g2gpu_pm_potential_periodic ------------------------------------------------------------
+def gpu_pmpot(pos, mass, ptype, grav, D, pmgrid, box, G=1.0, **kw):
+    from g2gpu import TreeGravity
+    n = len(mass)
+    tg = TreeGravity(max_part=n + 64, n_gravs=D, periodic=True, shortrange=True, unequal_softenings=False)
+    tg.set_species(grav, g2test.force_softening((1.0,) * 6))
+    tg.upload(pos, mass, ptype)
+    pot = tg.pm_potential_periodic(pmgrid, box, G=G, **kw)
+    tg.close()
+    return pot
+
+
+YUK_GREENS = [["none", "pgyukawa"], ["pgyukawa", "none"]]          # NGRAVS_YUKAWA_FORCETEST (ngravs.c:264-272)
+
+
+def yuk_par(ymass=60.0):
+    return np.full((2, 2), ymass / (2 * np.pi))                   # ngravs.c:871
+
+
+def check_pot(pot, ref):
+    """tolerance: 1e-5 of the largest |potential| and 1e-5 median relative (FP64 mesh on both sides, FLOAT result; the device sums the
+    source species in k-space and rounds once, the reference rounds after every corner of every pair, pm_periodic.c:1254-1267)."""
+    scale = np.abs(ref).max()
+    assert np.isfinite(pot).all() and scale > 0
+    assert np.abs(pot - ref).max() <= ABS_TOL * scale, np.abs(pot - ref).max() / scale
+    assert np.median(np.abs(pot - ref) / np.maximum(np.abs(ref), 1e-30)) <= MEDIAN_TOL
+
+
+def test_pm_potential_matches_reference_fixture():
+    g = np.load(os.path.join(GOLD, "pmpot_pm64_yuk_poisson4096.npz"))
+    args = (g["grav"], 2, int(g["pmgrid"]), float(g["box"]), float(g["G"]))
+    pot = gpu_pmpot(g["pos"], g["mass"], g["type"], *args, greens=YUK_GREENS, greens_par=yuk_par(float(g["yukawa_imass"])))
+    check_pot(pot, g["pmpot"])
+    perm = np.random.default_rng(3).permutation(len(g["mass"]))     # upload order must not matter
+    pot2 = gpu_pmpot(g["pos"][perm], g["mass"][perm], g["type"][perm], *args, greens=YUK_GREENS, greens_par=yuk_par(float(g["yukawa_imass"])))
+    check_pot(pot2, g["pmpot"][perm])
+
+
+def test_pm_potential_matches_reference_run():
+    if not available("pm64_yuk_f32"):
+        pytest.skip("oracle/_ref not built")
+    n, box, G = 20000, 80000.0, 43007.1
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=11)
+    mass = (1.0 + 0.5 * np.random.default_rng(1).random(n)).astype(np.float32)
+    ref = RefOracle("pm64_yuk_f32", int(1.1 * n) + 64, boxsize=box, softening=(50.0,) * 6, gravity=g2test.GRAV_D2, G=G)
+    ref.load(pos, mass, ptype)
+    ref.domain()
+    rpot = ref.pmpotential().astype(np.float32)
+    rp = ref.particles()
+    pot = gpu_pmpot(rp["pos"].astype(np.float32), rp["mass"].astype(np.float32), rp["type"], g2test.GRAV_D2, 2, 64, box, G=G, greens=YUK_GREENS, greens_par=yuk_par())
+    check_pot(pot, rpot)
+
+
+def test_pm_potential_256_mesh_against_port_and_newtonian_zero_mode():
+    """PMGRID = 256 (BASELINE config 3 mesh), 2^17 particles: Yukawa pairs against the pinned numpy restatement; and the stock 1/k^2, for
+    which the reference returns infinite potentials (tests/test_pm_oracle.py): the device result is finite and equals the port's with the
+    k = 0 mode removed -- a potential is defined up to a constant, and differences of it are what the reference's force mesh uses."""
+    n, box, N = 1 << 17, 100000.0, 256
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=5)
+    species = np.asarray(g2test.GRAV_D2)[ptype]
+    asmth = 1.25 * box / N
+    ym = 60.0 / (2 * np.pi)
+    asmth2 = ((2 * np.pi) * asmth / box) ** 2
+    yuk = lambda a, b, k2: (1.0 / (k2 + ym * ym) * np.exp(-ym * ym * asmth2)) if a != b else np.zeros_like(k2)     # noqa: E731
+    port = pm_port.pm_potential(pos, mass, species, 2, N, box, 1.0, asmth, yuk)
+    pot = gpu_pmpot(pos, mass, ptype, g2test.GRAV_D2, 2, N, box, greens=YUK_GREENS, greens_par=yuk_par())
+    check_pot(pot, port)
+
+    def newton_without_zero_mode(a, b, k2):
+        with np.errstate(divide="ignore"):
+            return np.where(k2 > 0, 1.0 / k2, 0.0)
+    port = pm_port.pm_potential(pos, mass, species, 2, N, box, 1.0, asmth, newton_without_zero_mode)
+    pot = gpu_pmpot(pos, mass, ptype, g2test.GRAV_D2, 2, N, box)
+    check_pot(pot, port)
