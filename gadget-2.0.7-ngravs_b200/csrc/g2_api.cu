@@ -65,6 +65,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->nsm = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : G2_NSM_FALLBACK;
   c->acc_double = 1;
   c->walk_exact = getenv("G2GPU_WALK_EXACT") ? atoi(getenv("G2GPU_WALK_EXACT")) != 0 : 1;
+  c->walk_defer = getenv("G2GPU_WALK_DEFER") ? atoi(getenv("G2GPU_WALK_DEFER")) != 0 : 0;	// only in a -DG2_WALK_DEFER build
   for(int t = 0; t < 6; t++)
     c->force_softening[t] = 1.0;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -143,7 +144,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->d_potcorr, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);
@@ -600,6 +601,8 @@ extern "C" int g2gpu_set_option(g2gpu_ctx *c, const char *name, int value)
     c->sort_onesweep = value != 0;
   else if(strcmp(name, "walk_exact") == 0)
     c->walk_exact = value != 0;
+  else if(strcmp(name, "walk_defer") == 0)
+    c->walk_defer = value != 0;
   else if(strcmp(name, "compact") == 0)
     {
       if(value && !c->cres)
@@ -884,6 +887,56 @@ extern "C" int g2gpu_set_lattice_tables(g2gpu_ctx *c, int en, const double *fcor
   c->lattice_ntables = nu;
   c->lattice_set = 1;
   return 0;
+}
+
+extern "C" int g2gpu_set_lattice_pot_tables(g2gpu_ctx *c, int en, const double *potcorr)
+{
+  if(!c)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  if(!potcorr)
+    {
+      c->potcorr_set = 0;
+      return 0;
+    }
+  if(!c->cfg.periodic || c->cfg.shortrange)
+    return g2_fail(G2GPU_ERR_ARG, "lattice potential tables belong to a periodic box without PM (PERIODIC && !PMGRID)");
+  if(en < 1 || en > 256)
+    return g2_fail(G2GPU_ERR_ARG, "EN must be in [1, 256]");
+  const int D = c->D;
+  const size_t n3 = (size_t) (en + 1) * (en + 1) * (en + 1);
+  int nu = 0, first[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// identical pair tables are stored once
+  for(int i = 0; i < D * D; i++)
+    {
+      int found = -1;
+      for(int u = 0; u < nu && found < 0; u++)
+	if(memcmp(potcorr + (size_t) first[u] * n3, potcorr + (size_t) i * n3, sizeof(double) * n3) == 0)
+	  found = u;
+      if(found < 0)
+	{
+	  first[nu] = i;
+	  found = nu++;
+	}
+      c->potcorr_tabmap[i] = (unsigned char) found;
+    }
+  if(c->d_potcorr)
+    cudaFree(c->d_potcorr);
+  c->d_potcorr = nullptr;
+  c->potcorr_set = 0;
+  G2_CUDA(cudaMalloc((void **) &c->d_potcorr, sizeof(double) * n3 * (size_t) nu));
+  for(int u = 0; u < nu; u++)
+    G2_CUDA(cudaMemcpy(c->d_potcorr + (size_t) u * n3, potcorr + (size_t) first[u] * n3, sizeof(double) * n3, cudaMemcpyHostToDevice));
+  c->potcorr_en = en;
+  c->potcorr_set = 1;
+  return 0;
+}
+
+extern "C" int g2gpu_make_ewald_pot_table(g2gpu_ctx *c, int en, double latticezero, double *out)
+{
+  if(!c || !out)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  G2_CUDA(cudaSetDevice(c->cfg.device));
+  return g2_make_ewald_pot_table(c, en, latticezero, out);
 }
 
 extern "C" int g2gpu_make_ewald_table(g2gpu_ctx *c, int en, double *out)

@@ -111,6 +111,9 @@ struct g2gpu_ctx
   // lattice-sum correction of a periodic box without PM (g2_lattice.cu)
   float *d_lattice;		// unique tables, (EN+1)^3 float4 (fx, fy, fz, 0) each
   int lattice_en, lattice_set, lattice_ntables;
+  double *d_potcorr;		// unique lattice-sum potential tables, (EN+1)^3 doubles each (g2gpu_set_lattice_pot_tables)
+  int potcorr_en, potcorr_set;
+  unsigned char potcorr_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   unsigned char lattice_tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   float *latt, *lattcost;	// 3n / n, current particle order (allocated on first use)
   int acc_double;		// accumulate accelerations in FP64 (default) or FP32
@@ -120,6 +123,7 @@ struct g2gpu_ctx
   int direct_ewald;		// g2gpu_direct adds the exact lattice correction of a periodic box (option "direct_ewald")
   int walk_stats;		// option "walk_stats": the instrumented walk kernel (visits, species terms, decisions in counters[2..4])
   int walk_exact;		// option "walk_exact" (default 1): borderline decisions are re-taken in FP64 (exact GravCost)
+  int walk_defer;		// option "walk_defer" (G2GPU_WALK_DEFER; -DG2_WALK_DEFER builds only): stock pair laws evaluated from the per-warp source ring
   int compact;			// option "compact": the walk writes its slice's results in target order (cres) instead of by particle index
   float *cres;			// 5 floats per target of the slice (acc[3], cost, oldacc), allocated with the option
   int slice_explicit;		// slice_frac[] instead of rank/nranks (cost-weighted slices of the group path)
@@ -255,6 +259,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp);
 int g2_make_ewald_table(g2gpu_ctx *c, int en, double *out);
+int g2_make_ewald_pot_table(g2gpu_ctx *c, int en, double latticezero, double *out);
 int g2_stage_counts(g2gpu_ctx *c);
 int g2_update_tree(g2gpu_ctx *c, const float *len, const float *s);
 int g2_pm_periodic(g2gpu_ctx *c, const g2gpu_pm_params *pp);

@@ -280,3 +280,55 @@ int g2_make_ewald_table(g2gpu_ctx *c, int en, double *out)
     return g2_fail(G2GPU_ERR_CUDA, "ewald table: %s", cudaGetErrorString(e));
   return 0;
 }
+
+// ---- ewald_psi (ngravs.c:761-816) on the same grid: potcorr of lattice_init for the stock wiring, before the division by BoxSize;
+//      the origin holds LatticeZero (forcetree.c:3699-3702) ----
+__global__ void __launch_bounds__(128) ewald_pot_table_kernel(int en, double latticezero, double *__restrict__ out)
+{
+  const int n1 = en + 1, q = blockIdx.x * blockDim.x + threadIdx.x;
+  if(q >= n1 * n1 * n1)
+    return;
+  const int i = q / (n1 * n1), j = (q / n1) % n1, k = q % n1;
+  if(q == 0)
+    {
+      out[0] = latticezero;
+      return;
+    }
+  const double alpha = 2.0, x[3] = { 0.5 * i / en, 0.5 * j / en, 0.5 * k / en };
+  double sum1 = 0.0, sum2 = 0.0;
+  for(int n0 = -4; n0 <= 4; n0++)
+    for(int n1_ = -4; n1_ <= 4; n1_++)
+      for(int n2 = -4; n2 <= 4; n2++)
+	{
+	  const double d[3] = { x[0] - n0, x[1] - n1_, x[2] - n2 };
+	  const double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+	  sum1 += erfc(alpha * r) / r;
+	}
+  for(int h0 = -4; h0 <= 4; h0++)
+    for(int h1 = -4; h1 <= 4; h1++)
+      for(int h2_ = -4; h2_ <= 4; h2_++)
+	{
+	  const int h2 = h0 * h0 + h1 * h1 + h2_ * h2_;
+	  if(h2 > 0)
+	    sum2 += 1 / (M_PI * h2) * exp(-M_PI * M_PI * h2 / (alpha * alpha)) * cos(2 * M_PI * (x[0] * h0 + x[1] * h1 + x[2] * h2_));
+	}
+  out[q] = M_PI / (alpha * alpha) - sum1 - sum2 + 1 / sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+}
+
+int g2_make_ewald_pot_table(g2gpu_ctx *c, int en, double latticezero, double *out)
+{
+  if(en < 1 || en > 256)
+    return g2_fail(G2GPU_ERR_ARG, "ewald table: EN must be in [1, 256]");
+  const size_t n3 = (size_t) (en + 1) * (en + 1) * (en + 1);
+  double *d;
+  G2_CUDA(cudaMalloc((void **) &d, sizeof(double) * n3));
+  ewald_pot_table_kernel<<<g2_cdiv((int) n3, 128), 128, 0, c->stream>>>(en, latticezero, d);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * n3, cudaMemcpyDeviceToHost, c->stream);
+  if(e == cudaSuccess)
+    e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if(e != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "ewald potential table: %s", cudaGetErrorString(e));
+  return 0;
+}

@@ -1,5 +1,6 @@
 // g2_pot.cu — the tree potential walks of compute_potential (potential.c:22-354): force_treeevaluate_potential_shortrange
-// (forcetree.c:2789-3163, TreePM) and force_treeevaluate_potential (forcetree.c:2467-2776, no PM, non-periodic).  SURVEY.md 8f-3.
+// (forcetree.c:2789-3163, TreePM) and force_treeevaluate_potential (forcetree.c:2467-2776, no PM; in a periodic box every term also
+// gets mass * lattice_pot_corr, forcetree.c:2736-2738, 2765-2767, 3895-3941: instantiation LATT).  SURVEY.md 8f-3.
 //
 // Same traversal as g2_walk.cu (one cursor per 32 tree-adjacent targets over the depth-first cell records, per-lane decisions, warp
 // vote to descend), with the potential walk's own rules, reproduced as the reference has them:
@@ -46,7 +47,30 @@ struct PotArgs
   int potfxn[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS], potspline[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
   float bam_eps[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// BAM_EPSILON (ngravs.c:45), from the parameters of g2gpu_set_laws
   const unsigned int *__restrict__ cnt;	// particle counts per species of every cell (NGRAVS_ACCUMULATOR), or null
+  // LATT: potcorr[target][source] of lattice_init (forcetree.c:52, 3697-3702, 3759), unique tables of (EN+1)^3 doubles
+  const double *__restrict__ potcorr;
+  double fac_intp;		// 2 EN / BoxSize (forcetree.c:3750)
+  int potcorr_en;
+  unsigned char potcorr_map[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
 };
+
+// lattice_pot_corr (forcetree.c:3895-3941): trilinear interpolation in the octant table, in double like the reference
+__device__ __forceinline__ double latt_pot_corr(const PotArgs &A, float dxf, float dyf, float dzf, int ij)
+{
+  const int en = A.potcorr_en, n1 = en + 1;
+  const double *__restrict__ t = A.potcorr + (size_t) A.potcorr_map[ij] * n1 * n1 * n1;
+  double u = fabs((double) dxf) * A.fac_intp, v = fabs((double) dyf) * A.fac_intp, w = fabs((double) dzf) * A.fac_intp;
+  int i = (int) u, j = (int) v, k = (int) w;
+  if(i >= en) i = en - 1;
+  if(j >= en) j = en - 1;
+  if(k >= en) k = en - 1;
+  u -= i; v -= j; w -= k;
+  const double *__restrict__ b = t + ((size_t) i * n1 + j) * n1 + k;
+  const size_t sj = (size_t) n1, si = (size_t) n1 * n1;
+  return __ldg(b) * ((1 - u) * (1 - v) * (1 - w)) + __ldg(b + 1) * ((1 - u) * (1 - v) * w) + __ldg(b + sj) * ((1 - u) * v * (1 - w)) +
+    __ldg(b + sj + 1) * ((1 - u) * v * w) + __ldg(b + si) * (u * (1 - v) * (1 - w)) + __ldg(b + si + 1) * (u * (1 - v) * w) +
+    __ldg(b + si + sj) * (u * v * (1 - w)) + __ldg(b + si + sj + 1) * (u * v * w);
+}
 
 // plummer_pot, ngravs.c:459-471 (u = r/h)
 __device__ __forceinline__ float pot_plummer(float m, float h, float r)
@@ -127,10 +151,10 @@ __device__ __forceinline__ double nearest_d(double x, double box)
   return x;
 }
 
-template <int D, bool SR, bool UNEQUAL>
-__global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const PotArgs A)
+template <int D, bool SR, bool UNEQUAL, bool LATT>
+__global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_kernel(const PotArgs A)
 {
-  constexpr bool PERIODIC = SR;	// the reference's TreePM potential walk is the periodic one
+  constexpr bool PERIODIC = SR || LATT;	// the reference's TreePM potential walk is the periodic one; LATT: periodic box without PM
   extern __shared__ float s_tab[];
   __shared__ unsigned int s_chunk[WALK_WARPS];
   if(SR)
@@ -191,7 +215,7 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 #endif
 	  if(cur >= skip_until)
 	    {
-	      float r2[D], mass[D];
+	      float r2[D], mass[D], dsp[LATT ? D : 1][3];
 	      float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
 	      const float len = q0.x;
 	      const float cxr = q0.y - px, cyr = q0.z - py, czr = q0.w - pz;
@@ -230,6 +254,10 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 		      const float dy = POT_WRAP(q.y - py, shy);
 		      const float dz = POT_WRAP(q.z - pz, shz);
 		      r2[g] = dx * dx + dy * dy + dz * dz;
+		      if(LATT)
+			{
+			  dsp[g][0] = dx; dsp[g][1] = dy; dsp[g][2] = dz;
+			}
 		      r2min = fminf(r2min, r2[g]);
 		      r2max = fmaxf(r2max, r2[g]);
 		    }
@@ -265,8 +293,12 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 #pragma unroll
 		      for(int g = 0; g < D; g++)
 			if(mass[g] != 0.0f)	// forcetree.c:3123
-			  fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0, pmass,
-					       A.cnt ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f);
+			  {
+			    fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0, pmass,
+						 A.cnt ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f);
+			    if(LATT)	// forcetree.c:2765-2767
+			      pot += (double) mass[g] * latt_pot_corr(A, dsp[g][0], dsp[g][1], dsp[g][2], tg * D + g);
+			  }
 		    }
 		}
 	    }
@@ -290,6 +322,8 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 		      const float dy = POT_WRAP(p.y - py, shy);
 		      const float dz = POT_WRAP(p.z - pz, shz);
 		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true, pmass, 1.0f);
+		      if(LATT)	// forcetree.c:2736-2738
+			pot += (double) p.w * latt_pot_corr(A, dx, dy, dz, tg * D + sg);
 		    }
 		}
 	      cur = cur + 1u;
@@ -306,13 +340,14 @@ __global__ void __launch_bounds__(WALK_THREADS, POT_BLOCKS(D)) pot_kernel(const 
 #undef POT_WRAP
 
 template <int D>
-static void launch_pot(g2gpu_ctx *c, const PotArgs &A, int grid, size_t smem, bool sr, bool unequal)
+static void launch_pot(g2gpu_ctx *c, const PotArgs &A, int grid, size_t smem, bool sr, bool unequal, bool latt)
 {
-#define G2_P(SRv, UNEv) do { \
-    if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-    pot_kernel<D, SRv, UNEv><<<grid, WALK_THREADS, smem, c->stream>>>(A); } while(0)
-  if(sr) { if(unequal) G2_P(true, true); else G2_P(true, false); }
-  else   { if(unequal) G2_P(false, true); else G2_P(false, false); }
+#define G2_P(SRv, UNEv, LATv) do { \
+    if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv, LATv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+    pot_kernel<D, SRv, UNEv, LATv><<<grid, WALK_THREADS, smem, c->stream>>>(A); } while(0)
+  if(sr) { if(unequal) G2_P(true, true, false); else G2_P(true, false, false); }
+  else if(latt) { if(unequal) G2_P(false, true, true); else G2_P(false, false, true); }
+  else   { if(unequal) G2_P(false, true, false); else G2_P(false, false, false); }
 #undef G2_P
 }
 
@@ -326,8 +361,11 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   const bool sr = c->cfg.shortrange != 0;
   if(sr && !c->pottable_set)
     return g2_fail(G2GPU_ERR_STATE, "potential: short-range potential table not set (g2gpu_set_srpot_table)");
-  if(!sr && c->cfg.periodic)
-    return g2_fail(G2GPU_ERR_ARG, "potential: a periodic box without PM needs the lattice-sum potential tables (lattice_pot_corr, forcetree.c:3895), which are not built");
+  const bool latt = !sr && c->cfg.periodic;
+  if(latt && !c->potcorr_set)
+    return g2_fail(G2GPU_ERR_STATE, "potential: a periodic box without PM needs the lattice-sum potential tables (g2gpu_set_lattice_pot_tables; lattice_pot_corr, forcetree.c:3895)");
+  if(latt && !(wp->boxsize > 0))
+    return g2_fail(G2GPU_ERR_ARG, "potential: boxsize must be positive in a periodic configuration");
   cudaStream_t st = c->stream;
   if(!c->pot)
     {
@@ -370,8 +408,15 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   for(int i = 0; i < D * D; i++)
     A.bam_eps[i] = c->laws_set ? c->laws.par[i][1] : 1.31e-6f;
   A.cnt = (c->accumulator && c->counts_valid) ? c->wcnt : nullptr;
+  if(latt)
+    {
+      A.potcorr = c->d_potcorr;
+      A.potcorr_en = c->potcorr_en;
+      A.fac_intp = 2.0 * c->potcorr_en / wp->boxsize;
+      memcpy(A.potcorr_map, c->potcorr_tabmap, sizeof(A.potcorr_map));
+    }
   const size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
-  int grid = c->nsm * POT_BLOCKS(D), need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
+  int grid = c->nsm * (latt ? 4 : POT_BLOCKS(D)), need = g2_cdiv(g2_cdiv(A.hi - A.lo, 32), WALK_WARPS);
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));
@@ -382,13 +427,13 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       switch (D)
 	{
 #ifndef G2_FAST_BUILD
-	case 1: launch_pot<1>(c, A, grid, smem, sr, uneq); break;
-	case 3: launch_pot<3>(c, A, grid, smem, sr, uneq); break;
-	case 5: launch_pot<5>(c, A, grid, smem, sr, uneq); break;
-	case 6: launch_pot<6>(c, A, grid, smem, sr, uneq); break;
+	case 1: launch_pot<1>(c, A, grid, smem, sr, uneq, latt); break;
+	case 3: launch_pot<3>(c, A, grid, smem, sr, uneq, latt); break;
+	case 5: launch_pot<5>(c, A, grid, smem, sr, uneq, latt); break;
+	case 6: launch_pot<6>(c, A, grid, smem, sr, uneq, latt); break;
 #endif
-	case 2: launch_pot<2>(c, A, grid, smem, sr, uneq); break;
-	case 4: launch_pot<4>(c, A, grid, smem, sr, uneq); break;
+	case 2: launch_pot<2>(c, A, grid, smem, sr, uneq, latt); break;
+	case 4: launch_pot<4>(c, A, grid, smem, sr, uneq, latt); break;
 	default: return g2_fail(G2GPU_ERR_ARG, "unsupported N_GRAVS %d", D);
 	}
       c->launches++;

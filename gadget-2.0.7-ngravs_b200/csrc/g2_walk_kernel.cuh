@@ -129,6 +129,23 @@ struct WalkLane
   int ninter, nterms, ndec;
   int nborder;			// comparisons of this walk that fell inside their guard band
   unsigned int skip_until;
+  unsigned int bits;		// DEFER: ring entries (staged sources) this lane still has to evaluate
+};
+
+// DEFER (stock pair laws): the terms a lane accepts are not evaluated where they are found -- a handful of lanes at a time -- but staged.
+// The SOURCE records (species centres of mass of an accepted cell, direct particles of an opened cell) go once per warp into a ring of
+// WALK_RING entries in shared memory; a lane only sets a bit per entry it has to evaluate.  When the ring is nearly full every lane
+// walks its own bits (ring_flush): lanes are busy for as many passes as the busiest lane has bits, about 45 % of the lane slots
+// against 20 % where terms are evaluated in place (counts in DESIGN.md, section 5).  Summation order is a
+// function of the traversal only, so results stay reproducible bit for bit.
+#define WALK_RING 32
+struct WalkRing
+{
+  float4 *src;			// shared memory, this warp's WALK_RING entries: x, y, z, mass
+  float *hsrc;			// (UNEQUAL) softening that comes with the source: ForceSoftening[type] of a particle, of maxsofttype for a cell
+  unsigned int fill;		// entries staged                                        } warp-uniform
+  unsigned int isp;		// bit e: entry e is a particle (its in-range test and count are taken at evaluation)
+  bool wrap;			// an entry was staged by a visit that has to consider periodic images
 };
 
 // One visit, first half: this lane's decision on the cell at the cursor and, if it accepts the cell, the D species terms.
@@ -136,9 +153,9 @@ struct WalkLane
 // than the warp's no-wrap bound): plain differences.  WRAP = true: per-cell image shift for small TreePM cells, NEAREST per point
 // otherwise.  Returns whether the lane opens the cell; shx/shy/shz/small_cell are handed on to the particle half.
 // EXACT: comparisons inside their guard band flag the target for walk_redo_kernel (L.border).
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, bool DEFER = false>
 __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, const float4 *__restrict__ rec,
-						const float4 q0, const uint4 w, unsigned int cur, WalkLane &L, WalkShift &S, bool &small_cell)
+						const float4 q0, const uint4 w, unsigned int cur, WalkLane &L, WalkShift &S, bool &small_cell, unsigned int *newbits = nullptr)
 {
   bool open = false, done = false, outside = false, border = false;
   if(STATS)
@@ -272,9 +289,14 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 		    border = border || fabsf(tv) < A.rmax2_border;
 		  counted = counted && tv < 0.0f;
 		}
-	      const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
-	      if(mass[g] != 0.0f)	// a property of the cell, hence uniform: small cells often hold one species only
-		pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
+	      if(DEFER)
+		*newbits |= (counted ? 1u : 0u) << g;	// evaluated from the ring (ring_flush)
+	      else
+		{
+		  const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
+		  if(mass[g] != 0.0f)	// a property of the cell, hence uniform: small cells often hold one species only
+		    pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
+		}
 	      any |= counted;
 	      if(STATS)
 		L.nterms += counted;
@@ -373,6 +395,132 @@ __device__ __forceinline__ unsigned int walk_visit(const WalkArgs &A, const floa
   return cur + 1u;
 }
 
+// DEFER: every lane evaluates the ring entries it holds a bit for.  WRAPF: some entry may need a periodic image; the image shift is
+// taken per point and applied in two exact steps like in walk_visit_cell, so the difference is rounded once, at its own magnitude.
+template <bool SR, bool UNEQUAL, bool STATS, bool EXACT, bool WRAPF>
+__device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, WalkLane &L, const WalkRing &R)
+{
+  unsigned int b = L.bits;
+  while(b)
+    {
+      const int e = 31 - __clz((int) b);
+      b ^= 1u << e;
+      const float4 s = R.src[e];
+      float h = L.hself;
+      if(UNEQUAL)
+	h = fmaxf(h, R.hsrc[e]);	// forcetree.c:1412-1415 (particles), 1475-1501 (cells)
+      float dx, dy, dz;
+      if(WRAPF)
+	{
+	  const float shx = A.boxsize * rint_small((s.x - L.px) * A.boxinv), shy = A.boxsize * rint_small((s.y - L.py) * A.boxinv),
+	    shz = A.boxsize * rint_small((s.z - L.pz) * A.boxinv);
+	  dx = (s.x - fmaxf(shx, 0.0f)) - (L.px + fminf(shx, 0.0f));
+	  dy = (s.y - fmaxf(shy, 0.0f)) - (L.py + fminf(shy, 0.0f));
+	  dz = (s.z - fmaxf(shz, 0.0f)) - (L.pz + fminf(shz, 0.0f));
+	}
+      else
+	{
+	  dx = s.x - L.px;
+	  dy = s.y - L.py;
+	  dz = s.z - L.pz;
+	}
+      const float r2 = dx * dx + dy * dy + dz * dz;
+      bool counted = true;
+      if(SR)
+	{			// a species term of a cell was tested when it was staged; a particle term is tested here (forcetree.c:1958-1967)
+	  const bool isp = (R.isp >> e) & 1u;
+	  const float tv = r2 - A.rmax2;
+	  counted = !isp || tv < 0.0f;
+	  if(EXACT)
+	    L.nborder += isp && fabsf(tv) < A.rmax2_border;
+	  L.ninter += isp && counted;	// forcetree.c:2031
+	  if(STATS)
+	    L.nterms += isp && counted;
+	}
+      pair_term<SR, true>(A, s_tab, s_tab_addr, L.tg, 0, 1, L.pmass, s.w, dx, dy, dz, r2, h, counted, L.fx, L.fy, L.fz);
+    }
+  L.bits = 0u;
+}
+
+template <bool SR, bool UNEQUAL, bool STATS, bool EXACT, typename ACC>
+__device__ __forceinline__ void ring_flush(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, WalkLane &L, WalkRing &R,
+					   ACC (*acc_sh)[WALK_THREADS], ACC &ax, ACC &ay, ACC &az)
+{
+  __syncwarp();			// the entries were written by other lanes
+  if(R.wrap)
+    ring_eval<SR, UNEQUAL, STATS, EXACT, true>(A, s_tab, s_tab_addr, L, R);
+  else
+    ring_eval<SR, UNEQUAL, STATS, EXACT, false>(A, s_tab, s_tab_addr, L, R);
+  // the FP32 partial sums of one ring (at most WALK_RING terms per lane) go into the accumulators
+  if(sizeof(ACC) == 8)
+    {
+      acc_sh[0][threadIdx.x] += (ACC) L.fx; acc_sh[1][threadIdx.x] += (ACC) L.fy; acc_sh[2][threadIdx.x] += (ACC) L.fz;
+    }
+  else
+    {
+      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+    }
+  L.fx = L.fy = L.fz = 0.0f;
+  R.fill = 0u;
+  R.isp = 0u;
+  R.wrap = false;
+  __syncwarp();			// nobody overwrites an entry that another lane still reads
+}
+
+// One whole visit with deferred terms: decisions, staging of the sources, vote; returns the next cursor.  The caller guarantees room for
+// D + 8 entries in the ring.
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool WRAP, bool STATS, bool EXACT>
+__device__ __forceinline__ unsigned int walk_visit_defer(const WalkArgs &A, unsigned int cur, const float4 *__restrict__ rec, const float4 q0, const uint4 w,
+							 int lane, WalkLane &L, WalkRing &R)
+{
+  bool open = false, small_cell = false;
+  unsigned int newbits = 0u;
+  WalkShift S;
+  if(cur >= L.skip_until)
+    open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, true, WRAP, STATS, EXACT, true>(A, nullptr, 0u, rec, q0, w, cur, L, S, small_cell, &newbits);
+  if(__any_sync(0xffffffffu, newbits != 0u))
+    {				// some lane uses the cell: stage its species records (lanes 0..D-1 copy one each)
+      if(lane < D)
+	{
+	  R.src[R.fill + lane] = __ldg(rec + 1 + lane);
+	  if(UNEQUAL)
+	    R.hsrc[R.fill + lane] = __uint_as_float(w.w);
+	}
+      L.bits |= newbits << R.fill;
+      R.fill += D;
+      if(WRAP)
+	R.wrap = true;
+    }
+  if(__ballot_sync(0xffffffffu, open) == 0u)
+    return w.x;			// nobody opens the cell: on to its sibling
+  const unsigned int np = w.z & 15u;
+  if(np != 0u)
+    {				// the direct particle children of the cell, for the lanes that opened it
+      if((unsigned int) lane < np)
+	{
+	  R.src[R.fill + lane] = __ldg(A.wpart + w.y + lane);
+	  if(UNEQUAL)
+	    R.hsrc[R.fill + lane] = A.fsoft[(w.z >> (4 + 3 * lane)) & 7];
+	}
+      const unsigned int m = ((1u << np) - 1u) << R.fill;
+      if(open)
+	{
+	  L.bits |= m;
+	  if(!SR)
+	    {			// without PM every particle of an opened cell counts (forcetree.c:1585)
+	      L.ninter += (int) np;
+	      if(STATS)
+		L.nterms += (int) np;
+	    }
+	}
+      R.isp |= m;
+      R.fill += np;
+      if(WRAP)
+	R.wrap = true;
+    }
+  return cur + 1u;
+}
+
 // gravity_tree epilogue for one target: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
 template <bool SR, bool PERIODIC>
 __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned int idx, int tloc, float px, float py, float pz, float fx, float fy, float fz, float ninter)
@@ -423,11 +571,13 @@ __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned in
     }
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER>
 __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
 {
   extern __shared__ float s_tab[];
   __shared__ unsigned int s_chunk[WALK_WARPS];
+  __shared__ float4 s_ring[DEFER ? WALK_WARPS * WALK_RING : 1];
+  __shared__ float s_ringh[(DEFER && UNEQUAL) ? WALK_WARPS * WALK_RING : 1];
   // the FP64 accumulators of a lane live in shared memory (touched only when the warp descends, about every third visit): six
   // registers less keeps the kernel at 64 registers without spills
   __shared__ ACC s_acc[sizeof(ACC) == 8 ? 3 : 1][WALK_THREADS];
@@ -438,7 +588,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       __syncthreads();
     }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int R = 2 + D;
+  const int RW = 2 + D;
   unsigned int s_tab_addr = (unsigned int) __cvta_generic_to_shared(s_tab);
   asm volatile("" : "+r"(s_tab_addr));	// keep the table base in a register: re-deriving it costs 4 uniform instructions per pair term
   unsigned int t2g_packed = 0;	// TypeToGrav as 6 nibbles
@@ -479,7 +629,14 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       L.fx = L.fy = L.fz = 0.0f;
       L.ninter = L.nterms = L.ndec = 0;
       L.nborder = 0;
+      L.bits = 0u;
       L.skip_until = valid ? 0u : 0xffffffffu;
+      WalkRing R;
+      R.src = s_ring + (DEFER ? warp * WALK_RING : 0);
+      R.hsrc = s_ringh + ((DEFER && UNEQUAL) ? warp * WALK_RING : 0);
+      R.fill = 0u;
+      R.isp = 0u;
+      R.wrap = false;
       if(sizeof(ACC) == 8)
 	{
 	  s_acc[0][threadIdx.x] = 0; s_acc[1][threadIdx.x] = 0; s_acc[2][threadIdx.x] = 0;
@@ -500,14 +657,32 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	}
 
       ACC rx = 0, ry = 0, rz = 0;	// (register accumulators of the FP32 variant)
-      while(cur < end)
+      while(true)
 	{
-	  const float4 *rec = A.cells + (size_t) cur * R;
+	  if(DEFER)
+	    {			// one flush site: before a visit that might not find room for its D species records and 8 particles, and at the end
+	      if(cur >= end || R.fill > (unsigned int) (WALK_RING - (D + 8)))
+		{
+		  ring_flush<SR, UNEQUAL, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, L, R, s_acc, rx, ry, rz);
+		  if(cur >= end)
+		    break;
+		}
+	    }
+	  else if(cur >= end)
+	    break;
+	  const float4 *rec = A.cells + (size_t) cur * RW;
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
 	  if(STATS)
 	    iter++;
-	  if(PERIODIC && !(SR && q0.x < nowrap_len))	// uniform
+	  if(DEFER)
+	    {
+	      if(PERIODIC && !(SR && q0.x < nowrap_len))	// uniform
+		cur = walk_visit_defer<D, SR, PERIODIC, UNEQUAL, PERIODIC, STATS, EXACT>(A, cur, rec, q0, w, lane, L, R);
+	      else
+		cur = walk_visit_defer<D, SR, PERIODIC, UNEQUAL, false, STATS, EXACT>(A, cur, rec, q0, w, lane, L, R);
+	    }
+	  else if(PERIODIC && !(SR && q0.x < nowrap_len))	// uniform
 	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
 	  else
 	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
@@ -727,12 +902,12 @@ __global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const W
     }
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER>
 static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
 {
   if(smem > 48 * 1024)
-    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT><<<grid, WALK_THREADS, smem, c->stream>>>(A);
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER><<<grid, WALK_THREADS, smem, c->stream>>>(A);
   if(EXACT)
     {
       if(smem > 48 * 1024)
@@ -746,12 +921,25 @@ static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
 static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, int acc_double, int stats)
 {
-  // exact (default): FP64 accumulators + guard bands + redo pass; otherwise the plain FP32-decision kernel with FP32 accumulators
+  // exact (default): FP64 accumulators + guard bands + redo pass; otherwise the plain FP32-decision kernel with FP32 accumulators.
+  // -DG2_WALK_DEFER builds the deferred-term variant as well (option walk_defer / G2GPU_WALK_DEFER = 1 selects it for the stock pair laws).
+  // MEASURED (B200, round 2, profiles/r2_walk_defer.txt): parity green, 4 % faster at 128^3, 4 % slower at 256^3, 57 % slower on the tree-only
+  // Hernquist walk -- the ring is evaluated at 10 of 32 lanes and ~50 instructions per pass, which is no better than evaluating in place.
+#ifdef G2_WALK_DEFER
+  if(STOCK && c->walk_defer)
+    {
+      if(stats)
+	return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, true, true, STOCK>(c, A, grid, smem);
+      if(!acc_double || !A.exact)
+	return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false, STOCK>(c, A, grid, smem);
+      return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true, STOCK>(c, A, grid, smem);
+    }
+#endif
   if(stats)			// instrumented instantiation (visits, species terms, decisions)
-    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, true, true>(c, A, grid, smem);
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, true, true, false>(c, A, grid, smem);
   if(!acc_double || !A.exact)
-    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false>(c, A, grid, smem);
-  return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true>(c, A, grid, smem);
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false, false>(c, A, grid, smem);
+  return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true, false>(c, A, grid, smem);
 }
 
 template <int D>

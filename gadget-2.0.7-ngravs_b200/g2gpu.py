@@ -25,7 +25,7 @@ EXPORTED = [
     "g2gpu_get_domain", "g2gpu_get_keys", "g2gpu_get_order", "g2gpu_get_topnodes", "g2gpu_treebuild", "g2gpu_download_tree", "g2gpu_download_extnodes", "g2gpu_download_nparticles",
     "g2gpu_walk", "g2gpu_direct", "g2gpu_download_acc", "g2gpu_slice", "g2gpu_gravity_tree", "g2gpu_set_option", "g2gpu_timings", "g2gpu_get_counts",
     "g2gpu_update_tree", "g2gpu_pm_periodic", "g2gpu_pm_potential_periodic", "g2gpu_download_gravpm", "g2gpu_reset_counters", "g2gpu_stream", "g2gpu_sync", "g2gpu_peano_keys", "g2gpu_sort_pairs", "g2gpu_eval_pairs",
-    "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table",
+    "g2gpu_set_lattice_tables", "g2gpu_make_ewald_table", "g2gpu_set_lattice_pot_tables", "g2gpu_make_ewald_pot_table",
     "g2gpu_set_potential_laws", "g2gpu_set_srpot_table", "g2gpu_potential", "g2gpu_download_potential", "g2gpu_eval_potentials",
     "g2gpu_group_create", "g2gpu_group_destroy", "g2gpu_group_size", "g2gpu_group_ctx", "g2gpu_group_set_species", "g2gpu_group_set_laws",
     "g2gpu_group_set_srtable", "g2gpu_group_set_lattice_tables", "g2gpu_group_set_option", "g2gpu_group_upload", "g2gpu_group_upload_aos",
@@ -266,6 +266,30 @@ class TreeGravity:
         """The stock wiring (LatticeForce = ewald_force for every pair, ngravs.c:131): device-made table / BoxSize^2 for all pairs."""
         t = self.make_ewald_table(en) / (boxsize * boxsize)
         self.set_lattice_tables(np.broadcast_to(t[:, None, None], (3, self.D, self.D) + t.shape[1:]).copy(), en)
+        return t
+
+    def make_ewald_pot_table(self, en=64, latticezero=float(np.float32(2.8372975))):
+        """ewald_psi (ngravs.c:761) at x = 0.5 (i,j,k)/en on the device in FP64, LatticeZero (a FLOAT, ngravs.c:133) at the origin:
+        (en+1, en+1, en+1), not yet divided by BoxSize."""
+        out = np.zeros((en + 1, en + 1, en + 1))
+        self.lib.g2gpu_make_ewald_pot_table.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        self._chk(self.lib.g2gpu_make_ewald_pot_table(self.ctx, int(en), float(latticezero), _p(out)))
+        return out
+
+    def set_lattice_pot_tables(self, potcorr, en=64):
+        """potcorr: (D, D, en+1, en+1, en+1) = potcorr[target][source] after lattice_init (divided by BoxSize), or None.  potential() of a
+        periodic box without PM needs it (lattice_pot_corr, forcetree.c:3895)."""
+        if potcorr is None:
+            self._chk(self.lib.g2gpu_set_lattice_pot_tables(self.ctx, int(en), None))
+            return
+        t = np.ascontiguousarray(potcorr, dtype=np.float64)
+        assert t.shape == (self.D, self.D, en + 1, en + 1, en + 1)
+        self._chk(self.lib.g2gpu_set_lattice_pot_tables(self.ctx, int(en), _p(t)))
+
+    def set_ewald_pot_lattice(self, boxsize, en=64):
+        """The stock wiring (LatticePotential = ewald_psi for every pair, ngravs.c:132): device-made table / BoxSize for all pairs."""
+        t = self.make_ewald_pot_table(en) / boxsize
+        self.set_lattice_pot_tables(np.broadcast_to(t, (self.D, self.D) + t.shape).copy(), en)
         return t
 
     # ---- compute_potential (potential.c:22): the tree potential of every particle -----------------------------------------

@@ -230,6 +230,14 @@ int g2gpu_set_lattice_tables(g2gpu_ctx *ctx, int en, const double *fcorr);
 /* The table lattice_init computes for the stock wiring: ewald_force (ngravs.c:1170-1236) at x = 0.5 (i,j,k)/en, FP64 on the device,
  * DIMENSIONLESS (divide by BoxSize^2 for g2gpu_set_lattice_tables); out[c * (en+1)^3 + ...], c = 0,1,2. */
 int g2gpu_make_ewald_table(g2gpu_ctx *ctx, int en, double *out);
+/* The potential of a periodic box without PM: force_treeevaluate_potential adds mass * lattice_pot_corr(dx, dy, dz, target, source) to every
+ * term (forcetree.c:2736-2738, 2765-2767; look-up forcetree.c:3895-3941).  potcorr[(target * D + source) * (en+1)^3 + (i * (en+1) + j) *
+ * (en+1) + k]: the reference's potcorr AFTER lattice_init (forcetree.c:3697-3702, 3759), i.e. LatticePotential at x = 0.5 (i,j,k)/en,
+ * LatticeZero at the origin, divided by BoxSize.  Required by g2gpu_potential when config.periodic && !config.shortrange; NULL removes it. */
+int g2gpu_set_lattice_pot_tables(g2gpu_ctx *ctx, int en, const double *potcorr);
+/* The table lattice_init computes for the stock wiring: ewald_psi (ngravs.c:761-816) at x = 0.5 (i,j,k)/en, FP64 on the device,
+ * latticezero (LatticeZero[l][m], 2.8372975 in ngravs.c:133) at the origin; NOT yet divided by BoxSize; out[(en+1)^3]. */
+int g2gpu_make_ewald_pot_table(g2gpu_ctx *ctx, int en, double latticezero, double *out);
 
 /* ---- tree potential of compute_potential (potential.c:22-354): force_treeevaluate_potential_shortrange
  *      (forcetree.c:2789-3163) when config.shortrange is set, else force_treeevaluate_potential (forcetree.c:2467-2776; non-periodic

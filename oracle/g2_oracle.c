@@ -62,6 +62,8 @@ typedef struct g2o
   double *srtab;			/* [D][D][ntab] */
   double *srpot;			/* shortrange_fourier_pot [D][D][ntab] */
   double *fcorr;			/* fcorrx/y/z after lattice_init: [3][D][D][(en+1)^3] (PERIODIC without PMGRID), or NULL */
+  double *potcorr;		/* potcorr after lattice_init: [D][D][(en+1)^3] (PERIODIC without PMGRID), or NULL */
+  int pot_en;
   int lattice_en;
   double lattice_cost;			/* sum of the lattice walk's return values (ewaldcount, gravtree.c:120) */
   int pot_id[MAXG][MAXG], potspline_id[MAXG][MAXG];	/* PotentialFxns / PotentialSplines, ids of include/g2gpu.h */
@@ -194,7 +196,7 @@ void g2o_destroy(g2o * o)
 {
   if(!o)
     return;
-  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o->srpot); free(o->pot); free(o->fcorr); free(o);
+  free(o->P); free(o->top); free(o->dni); free(o->nodes); free(o->nextnode); free(o->father); free(o->srtab); free(o->srpot); free(o->pot); free(o->fcorr); free(o->potcorr); free(o);
 }
 
 void g2o_set_species(g2o * o, const int *t2g, const double *fsoft)
@@ -883,11 +885,13 @@ void g2o_set_srpot(g2o * o, const double *tab)
 /* force_treeevaluate_potential_shortrange (forcetree.c:2789-3163) when o->shortrange, else force_treeevaluate_potential
  * (forcetree.c:2467-2776; the latter does not compile in the reference -- this branch restates what its text says, minus the
  * lattice correction of PERIODIC builds -- so it is NOT pinned against a reference run). */
+static double lattice_pot_corr_port(const g2o * o, double dx, double dy, double dz, int target, int source);
+
 static void tree_potential(g2o * o, int target)
 {
   const int D = o->D, MP = o->maxpart, SR = o->shortrange, PER = o->periodic;
   const particle *tp = &o->P[target];
-  double r2[MAXG], mass[MAXG], r, h, d[3];
+  double r2[MAXG], mass[MAXG], r, h, d[3], dsp[MAXG][3];
   double pot = 0;
   const double pos[3] = { tp->pos[0], tp->pos[1], tp->pos[2] };
   const int ptype = tp->type, pg = o->t2g[ptype];
@@ -913,6 +917,7 @@ static void tree_potential(g2o * o, int target)
 		d[k] = NEAREST(d[k]);
 	    }
 	  r2[sG] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+	  dsp[sG][0] = d[0]; dsp[sG][1] = d[1]; dsp[sG][2] = d[2];
 	  if(o->unequal)
 	    {
 	      h = o->fsoft[ptype];
@@ -936,6 +941,7 @@ static void tree_potential(g2o * o, int target)
 		    d[k] = NEAREST(d[k]);
 		}
 	      r2[g] = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+	      dsp[g][0] = d[0]; dsp[g][1] = d[1]; dsp[g][2] = d[2];
 	      if(r2[g] < r2min)
 		r2min = r2[g];
 	      if(r2[g] > r2max)
@@ -1025,6 +1031,8 @@ static void tree_potential(g2o * o, int target)
 	    }
 	  else
 	    pot += pot_spline(o, pg, g, mass[g], h, r);
+	  if(PER && !SR)	/* forcetree.c:2736-2738, 2765-2767 */
+	    pot += mass[g] * lattice_pot_corr_port(o, dsp[g][0], dsp[g][1], dsp[g][2], pg, g);
 	}
     }
   o->pot[target] = pot;		/* FLOAT store, forcetree.c:3158 */
@@ -1048,8 +1056,8 @@ int g2o_potential(g2o * o, int nthreads, float *out)
   int t;
   if(o->shortrange && !o->srpot)
     return -1;
-  if(!o->shortrange && o->periodic)
-    return -2;			/* lattice_pot_corr (forcetree.c:3895) is not restated */
+  if(!o->shortrange && o->periodic && !o->potcorr)
+    return -2;			/* a periodic box without PM needs the potcorr tables (g2o_set_lattice_pot_tables) */
   if(nthreads < 1)
     nthreads = 1;
   free(o->pot);
@@ -1077,7 +1085,7 @@ int g2o_potential_targets(g2o * o, int ntargets, const int *targets, float *out)
   int t;
   if(o->shortrange && !o->srpot)
     return -1;
-  if(!o->shortrange && o->periodic)
+  if(!o->shortrange && o->periodic && !o->potcorr)
     return -2;
   free(o->pot);
   o->pot = malloc(sizeof(float) * (o->n > 0 ? o->n : 1));
@@ -1106,7 +1114,7 @@ void g2o_set_lattice_tables(g2o * o, int en, const double *fcorr)
 
 /* ewald_force (ngravs.c:1170-1236) on the grid of lattice_init (forcetree.c:3700-3710): out[c * (en+1)^3 + (i*(en+1)+j)*(en+1)+k],
  * x = 0.5 (i,j,k)/en, dimensionless (lattice_init divides by BoxSize^2 afterwards, forcetree.c:3757-3761).  Same sums in the same order. */
-struct ewslice { int en, lo, hi; double *out; };
+struct ewslice { int en, lo, hi; double *out; double zero; };
 static void *ewald_slice(void *arg)
 {
   struct ewslice *s = arg;
@@ -1172,6 +1180,121 @@ int g2o_make_ewald_table(int en, int nthreads, double *out)
       sl[t].lo = (int) ((long long) n3 * t / nthreads);
       sl[t].hi = (int) ((long long) n3 * (t + 1) / nthreads);
       pthread_create(&th[t], NULL, ewald_slice, &sl[t]);
+    }
+  for(t = 0; t < nthreads; t++)
+    pthread_join(th[t], NULL);
+  free(sl);
+  free(th);
+  return 0;
+}
+
+/* ---- the potential of a periodic box without PM: lattice_pot_corr (forcetree.c:3895-3941) over potcorr[tgt][src] of lattice_init
+ *      (forcetree.c:3697-3702, 3759), and ewald_psi (ngravs.c:761-816), the function lattice_init tabulates for the stock wiring ---- */
+void g2o_set_lattice_pot_tables(g2o * o, int en, const double *potcorr)
+{
+  const size_t n = (size_t) o->D * o->D * (en + 1) * (en + 1) * (en + 1);
+  free(o->potcorr);
+  o->potcorr = NULL;
+  if(!potcorr)
+    return;
+  o->potcorr = malloc(sizeof(double) * n);
+  memcpy(o->potcorr, potcorr, sizeof(double) * n);
+  o->pot_en = en;
+}
+
+static double lattice_pot_corr_port(const g2o * o, double dx, double dy, double dz, int target, int source)
+{
+  const int en = o->pot_en, n1 = en + 1;
+  const double fac_intp = 2 * en / o->boxsize;	/* forcetree.c:3750 */
+  const double *t = o->potcorr + ((size_t) target * o->D + source) * n1 * n1 * n1;
+  int i, j, k;
+  double u, v, w, f1, f2, f3, f4, f5, f6, f7, f8;
+  if(dx < 0) dx = -dx;
+  if(dy < 0) dy = -dy;
+  if(dz < 0) dz = -dz;
+  u = dx * fac_intp; i = (int) u; if(i >= en) i = en - 1; u -= i;
+  v = dy * fac_intp; j = (int) v; if(j >= en) j = en - 1; v -= j;
+  w = dz * fac_intp; k = (int) w; if(k >= en) k = en - 1; w -= k;
+  f1 = (1 - u) * (1 - v) * (1 - w);
+  f2 = (1 - u) * (1 - v) * (w);
+  f3 = (1 - u) * (v) * (1 - w);
+  f4 = (1 - u) * (v) * (w);
+  f5 = (u) * (1 - v) * (1 - w);
+  f6 = (u) * (1 - v) * (w);
+  f7 = (u) * (v) * (1 - w);
+  f8 = (u) * (v) * (w);
+#define PC(a, b, c) t[((size_t) (a) * n1 + (b)) * n1 + (c)]
+  return PC(i, j, k) * f1 + PC(i, j, k + 1) * f2 + PC(i, j + 1, k) * f3 + PC(i, j + 1, k + 1) * f4 +
+    PC(i + 1, j, k) * f5 + PC(i + 1, j, k + 1) * f6 + PC(i + 1, j + 1, k) * f7 + PC(i + 1, j + 1, k + 1) * f8;
+#undef PC
+}
+
+double g2o_lattice_pot_corr(g2o * o, double dx, double dy, double dz, int target, int source)
+{
+  return o->potcorr ? lattice_pot_corr_port(o, dx, dy, dz, target, source) : 0.0 / 0.0;
+}
+
+static double ewald_psi_port(const double x[3])
+{
+  const double alpha = 2.0;
+  double r, sum1 = 0, sum2 = 0, hdotx, dx[3];
+  int i, n[3], h[3], h2;
+  for(n[0] = -4; n[0] <= 4; n[0]++)
+    for(n[1] = -4; n[1] <= 4; n[1]++)
+      for(n[2] = -4; n[2] <= 4; n[2]++)
+	{
+	  for(i = 0; i < 3; i++)
+	    dx[i] = x[i] - n[i];
+	  r = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+	  sum1 += erfc(alpha * r) / r;
+	}
+  for(h[0] = -4; h[0] <= 4; h[0]++)
+    for(h[1] = -4; h[1] <= 4; h[1]++)
+      for(h[2] = -4; h[2] <= 4; h[2]++)
+	{
+	  hdotx = x[0] * h[0] + x[1] * h[1] + x[2] * h[2];
+	  h2 = h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+	  if(h2 > 0)
+	    sum2 += 1 / (M_PI * h2) * exp(-M_PI * M_PI * h2 / (alpha * alpha)) * cos(2 * M_PI * hdotx);
+	}
+  r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  return M_PI / (alpha * alpha) - sum1 - sum2 + 1 / r;
+}
+
+static void *ewald_pot_slice(void *arg)
+{
+  struct ewslice *s = arg;
+  const int en = s->en, n1 = en + 1;
+  int q;
+  for(q = s->lo; q < s->hi; q++)
+    {
+      const int i = q / (n1 * n1), j = (q / n1) % n1, k = q % n1;
+      double x[3] = { 0.5 * ((double) i) / en, 0.5 * ((double) j) / en, 0.5 * ((double) k) / en };
+      s->out[q] = q == 0 ? s->zero : ewald_psi_port(x);	/* LatticeZero at the origin (forcetree.c:3699-3702) */
+    }
+  return NULL;
+}
+
+/* potcorr of the stock wiring BEFORE the division by BoxSize (forcetree.c:3759): out[(en+1)^3]; zero = LatticeZero[l][m] (a FLOAT:
+ * 2.8372975 rounded to float in a FLOAT = float build, ngravs.c:133) */
+int g2o_make_ewald_pot_table(int en, int nthreads, double zero, double *out)
+{
+  const int n3 = (en + 1) * (en + 1) * (en + 1);
+  pthread_t *th;
+  struct ewslice *sl;
+  int t;
+  if(nthreads < 1)
+    nthreads = 1;
+  th = malloc(sizeof(pthread_t) * nthreads);
+  sl = malloc(sizeof(struct ewslice) * nthreads);
+  for(t = 0; t < nthreads; t++)
+    {
+      sl[t].en = en;
+      sl[t].out = out;
+      sl[t].zero = zero;
+      sl[t].lo = (int) ((long long) n3 * t / nthreads);
+      sl[t].hi = (int) ((long long) n3 * (t + 1) / nthreads);
+      pthread_create(&th[t], NULL, ewald_pot_slice, &sl[t]);
     }
   for(t = 0; t < nthreads; t++)
     pthread_join(th[t], NULL);

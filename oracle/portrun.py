@@ -70,6 +70,15 @@ def make_ewald_table(en=64, nthreads=8):
     return out
 
 
+def make_ewald_pot_table(en=64, nthreads=8, latticezero=float(np.float32(2.8372975))):
+    """potcorr of the stock wiring before the division by BoxSize (forcetree.c:3697-3702): ewald_psi (ngravs.c:761) at x = 0.5 (i,j,k)/en,
+    LatticeZero (a FLOAT; ngravs.c:133) at the origin; shape (en+1, en+1, en+1)."""
+    out = np.zeros((en + 1, en + 1, en + 1))
+    rc = lib().g2o_make_ewald_pot_table(int(en), int(nthreads), C.c_double(latticezero), _p(out))
+    assert rc == 0
+    return out
+
+
 class PortOracle:
     def __init__(self, maxpart, D=2, periodic=False, shortrange=False, unequal=True, ntab=2048, boxsize=0.0, G=1.0, theta=0.5,
                  errtol=0.005, softening=(0.0, 1.0, 1.0, 1.0, 1.0, 1.0), gravity=(0, 0, 1, 0, 0, 0), tree_alloc=1.5, pmgrid=0,
@@ -124,6 +133,18 @@ class PortOracle:
         t = np.ascontiguousarray(fcorr, dtype=np.float64)
         assert t.shape == (3, self.D, self.D, en + 1, en + 1, en + 1)
         self.L.g2o_set_lattice_tables(self.h, int(en), _p(t))
+
+    def set_lattice_pot_tables(self, potcorr, en=64):
+        """potcorr[tgt][src] after lattice_init (divided by BoxSize), shape (D, D, en+1, en+1, en+1): potential() of a periodic box without
+        PM then adds mass * lattice_pot_corr per term (forcetree.c:2736-2738, 2765-2767)."""
+        t = np.ascontiguousarray(potcorr, dtype=np.float64)
+        assert t.shape == (self.D, self.D, en + 1, en + 1, en + 1)
+        self.L.g2o_set_lattice_pot_tables(self.h, int(en), _p(t))
+
+    def lattice_pot_corr(self, dx, dy, dz, tgt, src):
+        self.L.g2o_lattice_pot_corr.restype = C.c_double
+        self.L.g2o_lattice_pot_corr.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        return self.L.g2o_lattice_pot_corr(self.h, dx, dy, dz, tgt, src)
 
     def set_potential_laws(self, pot="newtonian", spline="plummer", node_table_term=False):
         """PotentialFxns / PotentialSplines [target][source]; node_table_term = a -DNGRAVS_ACCUMULATOR build (forcetree.c:3134-3140)."""

@@ -666,6 +666,19 @@ int g2ref_pmpotential(double *out)
 #endif
 }
 
+/* lattice_pot_corr (forcetree.c:3895) called directly, and the table it interpolates.  force_treeevaluate_potential, its only caller,
+ * does not compile in the reference (see the Makefile), so the look-up is what can be pinned. */
+int g2ref_potcorr_copy(double *out);
+int g2ref_get_potcorr(double *out) { return g2ref_potcorr_copy(out); }
+double g2ref_lattice_pot_corr(double dx, double dy, double dz, int target, int source)
+{
+#if defined(PERIODIC) && !defined(PMGRID)
+  return lattice_pot_corr(dx, dy, dz, target, source);
+#else
+  return 0.0 / 0.0;
+#endif
+}
+
 /* gravity_forcetest() (gravtree_forcetest.c:28) after a gravity_tree(): direct sums of the selected particles (all active ones with
  * FORCETEST = 1.0, RndTable = 0.5).  out: P[].GravAccelDirect (n x 3, post-G), current order.  forcetest.txt goes to the working directory. */
 int g2ref_forcetest(double *out)

@@ -48,3 +48,15 @@ int g2ref_lattice_copy(double *out)
   return 0;
 #endif
 }
+
+/* potcorr[tgt][src] (forcetree.c:52) after lattice_init, i.e. divided by BoxSize (forcetree.c:3759) */
+int g2ref_potcorr_copy(double *out)
+{
+#if defined(PERIODIC) && !defined(PMGRID)
+  memcpy(out, potcorr, sizeof(potcorr));
+  return NGRAVS_EN + 1;
+#else
+  (void) out;
+  return 0;
+#endif
+}

@@ -181,6 +181,18 @@ class RefOracle:
             raise RuntimeError("this oracle variant was compiled without PMGRID/PERIODIC")
         return out
 
+    def potcorr_tables(self):
+        """potcorr[tgt][src][EN+1]^3 after lattice_init (PERIODIC without PMGRID), shape (D, D, EN+1, EN+1, EN+1); else None."""
+        en1 = 65
+        out = np.zeros((self.D, self.D, en1, en1, en1))
+        got = self.lib.g2ref_get_potcorr(out.ctypes.data_as(C.c_void_p))
+        return out if got == en1 else None
+
+    def lattice_pot_corr(self, dx, dy, dz, tgt, src):
+        self.lib.g2ref_lattice_pot_corr.restype = C.c_double
+        self.lib.g2ref_lattice_pot_corr.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
+        return self.lib.g2ref_lattice_pot_corr(dx, dy, dz, tgt, src)
+
     def pmpotential(self):
         """What pmpotential_periodic (pm_periodic.c:798) adds to P[].Potential, current order of P[]; PM variants only."""
         out = np.zeros(self.n)
