@@ -225,6 +225,8 @@ extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
   // identical pair tables are stored once (stock wiring: all D*D tables are the Newtonian one)
   int nu = 0;
   int first[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];
+  memset(tabmap, 0, sizeof(tabmap));
   for(int i = 0; i < D * D; i++)
     {
       int found = -1;
@@ -236,13 +238,12 @@ extern "C" int g2gpu_set_srtable(g2gpu_ctx *c, const double *table)
 	  first[nu] = i;
 	  found = nu++;
 	}
-      c->sr_tabmap[i] = (unsigned char) found;
+      tabmap[i] = (unsigned char) found;
     }
+  // checked before any state changes: a refused call leaves the previous tables in place
   if((size_t) nu * ntab * sizeof(float) > 200 * 1024)
-    {
-      c->srtable_set = 0;
-      return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range tables do not fit in shared memory", nu);
-    }
+    return g2_fail(G2GPU_ERR_ARG, "%d distinct short-range tables do not fit in shared memory", nu);
+  memcpy(c->sr_tabmap, tabmap, sizeof(tabmap));
   c->srtable_set = 0;
   c->sr_ntables = nu;
   float *hf = (float *) malloc(sizeof(float) * (size_t) nu * ntab);

@@ -10,7 +10,7 @@
 // Per-lane interaction lists are therefore those of the reference walk; only the summation order differs.
 //
 // Decisions are taken in FP32.  The reference decides in double (forcetree.c:1628-1631), so a target that meets a comparison whose
-// two sides are closer than the FP32 rounding of their inputs allows (guard bands in WalkArgs) is flagged -- one predicated add per
+// two sides are closer than the FP32 rounding of their inputs allows (guard bands in WalkArgs) is flagged -- a running minimum per
 // visit --, and walk_redo_kernel walks the tree again for the flagged targets (about one per thousand) in the reference's own double
 // arithmetic, operation by operation: every target's interaction list, and with it GravCost, is then the reference's exactly.
 // Keeping the FP64 path out of this kernel keeps its 64 registers free of spills.
@@ -127,7 +127,7 @@ struct WalkLane
   int tg;
   float fx, fy, fz;		// FP32 partial sums, flushed into the accumulators whenever the warp descends
   int ninter, nterms, ndec;
-  int nborder;			// comparisons of this walk that fell inside their guard band
+  float bmin;			// EXACT: smallest distance of any comparison of this walk from its guard band (negative: inside)
   unsigned int skip_until;
   unsigned int bits;		// DEFER: ring entries (staged sources) this lane still has to evaluate
 };
@@ -152,12 +152,15 @@ struct WalkRing
 // WRAP = false: no periodic image can matter for this cell and this warp's targets (non-periodic run, or a TreePM cell smaller
 // than the warp's no-wrap bound): plain differences.  WRAP = true: per-cell image shift for small TreePM cells, NEAREST per point
 // otherwise.  Returns whether the lane opens the cell; shx/shy/shz/small_cell are handed on to the particle half.
-// EXACT: comparisons inside their guard band flag the target for walk_redo_kernel (L.border).
+// EXACT: comparisons inside their guard band flag the target for walk_redo_kernel (L.bmin).
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, bool DEFER = false>
 __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, const float4 *__restrict__ rec,
 						const float4 q0, const uint4 w, unsigned int cur, WalkLane &L, WalkShift &S, bool &small_cell, unsigned int *newbits = nullptr)
 {
-  bool open = false, done = false, outside = false, border = false;
+  bool open = false, done = false, outside = false;
+  // EXACT: smallest distance of a comparison of this visit from its guard band (negative: inside).  Kept as a running minimum instead of
+  // predicates so that the flagging stays straight-line code (FADD + FMNMX per comparison).
+  float bm = 3.0e38f;
   if(STATS)
     L.ndec++;
   // guard bands (EXACT): a few times the FP32 rounding a comparison can accumulate.  Wide where NEAREST is applied per
@@ -193,7 +196,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
       outside = t > 0.0f;
       done = t > fmaf(1.0e-3f, len, A.cull_margin);
       if(EXACT)
-	border = fabsf(t) < tol_pos * eff;
+	bm = fmaf(-tol_pos, eff, fabsf(t));
     }
   if(!done)
     {
@@ -231,7 +234,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	  if(outside)
 	    done = u > 0.0f;
 	  if(EXACT)		// (the box test only matters when r2min > rcut^2, the r2min test only outside the box: a superset is flagged)
-	    border = border || (outside && fabsf(u) < tol_r2 * A.rcut2);
+	    bm = fminf(bm, outside ? fmaf(-tol_r2, A.rcut2, fabsf(u)) : 3.0e38f);
 	}
     }
   if(!done)
@@ -244,7 +247,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	  const float lhs = len * len, v = fmaf(-r2min, A.theta2, lhs);
 	  open = v > 0.0f;
 	  if(EXACT)
-	    border = border || fabsf(v) < tol_crit * lhs;
+	    bm = fminf(bm, fmaf(-tol_crit, lhs, fabsf(v)));
 	}
       else
 	{			// relative criterion, forcetree.c:1446-1472
@@ -252,7 +255,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	  const float wv = fmaf(-0.60f, len, fmax3(fabsf(cxr), fabsf(cyr), fabsf(czr)));	// < 0: the target lies inside 0.6 len of the centre on every axis
 	  open = v > 0.0f || wv < 0.0f;
 	  if(EXACT)
-	    border = border || fabsf(v) < tol_crit * lhs || fabsf(wv) < tol_pos * len;
+	    bm = fminf(bm, fminf(fmaf(-tol_crit, lhs, fabsf(v)), fmaf(-tol_pos, len, fabsf(wv))));
 	}
     }
   float h = L.hself;
@@ -268,7 +271,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	      const float hv = fmaf(-h, h, r2max);
 	      open = hv < 0.0f;
 	      if(EXACT)
-		border = border || fabsf(hv) < tol_r2 * r2max;
+		bm = fminf(bm, fmaf(-tol_r2, r2max, fabsf(hv)));
 	    }
 	}
     }
@@ -286,7 +289,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 		{
 		  const float tv = r2[g] - A.rmax2;
 		  if(EXACT)
-		    border = border || fabsf(tv) < A.rmax2_border;
+		    bm = fminf(bm, fabsf(tv) - A.rmax2_border);
 		  counted = counted && tv < 0.0f;
 		}
 	      if(DEFER)
@@ -306,7 +309,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	}
     }
   if(EXACT)
-    L.nborder += border;	// any comparison of this visit inside its guard band: the target is walked again in FP64
+    L.bmin = fminf(L.bmin, bm);	// negative: some comparison of this walk fell inside its guard band and the target is walked again in FP64
   return open;
 }
 
@@ -356,7 +359,7 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 	      const float tv = rr2 - A.rmax2;
 	      counted = tv < 0.0f;
 	      if(EXACT)
-		L.nborder += fabsf(tv) < A.rmax2_border;
+		L.bmin = fminf(L.bmin, fabsf(tv) - A.rmax2_border);
 	    }
 	  pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz);
 	  L.ninter += counted;
@@ -432,7 +435,7 @@ __device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__rest
 	  const float tv = r2 - A.rmax2;
 	  counted = !isp || tv < 0.0f;
 	  if(EXACT)
-	    L.nborder += isp && fabsf(tv) < A.rmax2_border;
+	    L.bmin = fminf(L.bmin, isp ? fabsf(tv) - A.rmax2_border : 3.0e38f);
 	  L.ninter += isp && counted;	// forcetree.c:2031
 	  if(STATS)
 	    L.nterms += isp && counted;
@@ -628,7 +631,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       L.hself = A.fsoft[ptype];
       L.fx = L.fy = L.fz = 0.0f;
       L.ninter = L.nterms = L.ndec = 0;
-      L.nborder = 0;
+      L.bmin = 3.0e38f;
       L.bits = 0u;
       L.skip_until = valid ? 0u : 0xffffffffu;
       WalkRing R;
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	{
 	  walk_store_result<SR, PERIODIC>(A, idx, tloc, L.px, L.py, L.pz, (float) ax, (float) ay, (float) az, (float) L.ninter);
 	  tot_inter += (unsigned long long) L.ninter;
-	  if(EXACT && L.nborder)
+	  if(EXACT && L.bmin < 0.0f)
 	    {			// to walk_redo_kernel
 	      const unsigned int slot = atomicAdd(A.redo_count, 1u);
 	      if(slot < A.redo_cap)
@@ -937,6 +940,12 @@ static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, i
 #endif
   if(stats)			// instrumented instantiation (visits, species terms, decisions)
     return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, true, true, false>(c, A, grid, smem);
+#ifdef G2_WALK_ACC_MATRIX
+  if(!acc_double && A.exact)
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, true, false>(c, A, grid, smem);
+  if(acc_double && !A.exact)
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, false, false>(c, A, grid, smem);
+#endif
   if(!acc_double || !A.exact)
     return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false, false>(c, A, grid, smem);
   return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true, false>(c, A, grid, smem);

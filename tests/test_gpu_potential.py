@@ -162,8 +162,8 @@ def test_nonperiodic_potential_against_direct_sum_and_port():
     assert np.median(e) < 2e-3 and e.max() < 3e-2, (np.median(e), e.max())
 
 
-def test_periodic_box_without_pm_is_refused():
-    """PERIODIC without PMGRID needs lattice_pot_corr (forcetree.c:3895), which is not built: the call must fail, not approximate."""
+def test_periodic_box_without_pm_needs_its_tables():
+    """PERIODIC without PMGRID needs the potcorr tables of lattice_pot_corr (forcetree.c:3895): without them the call must fail, not approximate."""
     from g2gpu import G2Error, TreeGravity
     n, box = 5000, 1000.0
     pos, mass, ptype = g2test.periodic_poisson(n, box, seed=5)
@@ -176,6 +176,76 @@ def test_periodic_box_without_pm_is_refused():
     t.treebuild()
     with pytest.raises(G2Error):
         t.potential(t.walk_params(theta=0.5, boxsize=box))
+
+
+def test_periodic_potential_without_pm_against_port_and_ewald_sum():
+    """force_treeevaluate_potential of a PERIODIC build without PMGRID: nearest-image terms + mass * lattice_pot_corr per term
+    (forcetree.c:2736-2738, 2765-2767, 3895-3941).  The reference cannot compile that walk (oracle/ref/Makefile), so the checker is the
+    port, whose table and look-up are pinned bit for bit against the reference build (tests/test_latticepot_oracle.py), and the exact
+    periodic potential (FP64 Ewald sum).  The device tabulates ewald_psi itself (g2gpu_make_ewald_pot_table)."""
+    from g2gpu import TreeGravity
+    from portrun import make_ewald_pot_table
+    from test_latticepot_oracle import ewald_potential
+    n, box = 20000, 1000.0
+    pos, mass, ptype = g2test.periodic_poisson(n, box, seed=12)
+    mass = (mass * np.random.default_rng(4).uniform(0.5, 2.0, n)).astype(np.float32)
+    soft, grav = (box / 27 / 3000.0,) * 6, g2test.GRAV_D2        # far below the closest pair, so that the Ewald sum of point masses applies
+    o = PortOracle(int(1.1 * n) + 64, D=2, periodic=True, shortrange=False, unequal=False, boxsize=box, softening=soft, gravity=grav)
+    o.set_potential_laws("newtonian", "plummer")
+    ptab = make_ewald_pot_table(64) / box
+    o.set_lattice_pot_tables(np.broadcast_to(ptab, (2, 2, 65, 65, 65)).copy())
+    o.load(pos, mass, ptype)
+    o.domain()
+    o.treebuild()
+    p = o.particles()
+    t = TreeGravity(max_part=o.maxpart, n_gravs=2, periodic=True, shortrange=False, unequal_softenings=False)
+    t.set_species(grav, g2test.force_softening(soft))
+    t.set_laws()
+    t.set_potential_laws()
+    dtab = t.set_ewald_pot_lattice(box)
+    assert np.abs(dtab - ptab).max() <= 1e-9 * np.abs(ptab).max()          # device erfc/exp/cos against libm
+    t.upload(p["pos"], p["mass"], p["type"])
+    t.domain()
+    assert np.array_equal(t.order(), np.arange(n, dtype=np.int32))
+    t.treebuild()
+    for theta in (0.5, 0.3):
+        o.set_opening(theta, 0.005)
+        ref = o.potential(nthreads=8)
+        pot = t.potential(t.walk_params(theta=theta, errtol=0.005, boxsize=box))
+        check(pot, ref, f"port theta={theta}")
+    # relative criterion (OldAcc of a force walk)
+    acc, cost, old, perm = t.gravity_tree(p["pos"], p["mass"], p["type"], t.walk_params(theta=0.5, boxsize=box))
+    assert np.array_equal(perm, np.arange(n))
+    o.set_opening(0.0, 0.005)
+    o.load(p["pos"], p["mass"], p["type"], oldacc=old)
+    o.domain()
+    o.treebuild()
+    ref = o.potential(nthreads=8)
+    t.upload(p["pos"], p["mass"], p["type"], oldacc=old)
+    t.domain()
+    t.treebuild()
+    check(t.potential(t.walk_params(theta=0.0, errtol=0.005, boxsize=box)), ref, "port relative criterion")
+    # against the exact periodic potential (self term removed like potential.c:250-254 does, plus the m LatticeZero / L of the table origin).
+    # With an opening angle that opens every cell the walk is a direct sum over nearest images + table terms, and only the trilinear
+    # interpolation of the 65^3 table separates it from the Ewald sum.  (At theta = 0.3 the monopole potential of the reference's walk is
+    # biased by several per cent of the largest potential: every accepted cell is less bound than its particles, and nothing cancels that
+    # in a box whose mean potential is zero.)
+    tg = np.arange(0, n, 500)
+    exact = ewald_potential(p["pos"], p["mass"], tg, box)
+    h = 2.8 * soft[1]
+    pot = t.potential(t.walk_params(theta=1.0e-3, errtol=0.005, boxsize=box)).astype(np.float64)
+    noself = pot + p["mass"] * 2.8 / h - p["mass"] * float(np.float32(2.8372975)) / box
+    e = np.abs(noself[tg] - exact) / np.abs(exact).max()
+    assert e.max() < 5e-3, (np.median(e), e.max())
+    pot = t.potential(t.walk_params(theta=0.3, errtol=0.005, boxsize=box)).astype(np.float64)
+    # the reference's own table (pair [0][0] is the complete one in a FLOAT = float build) gives the same potentials
+    if available("per_d2_f32"):
+        r = RefOracle("per_d2_f32", int(1.1 * n) + 64, boxsize=box, softening=soft, gravity=grav)
+        rt = r.potcorr_tables()[0, 0]
+        t.set_lattice_pot_tables(np.broadcast_to(rt, (2, 2, 65, 65, 65)).copy())
+        pot2 = t.potential(t.walk_params(theta=0.3, errtol=0.005, boxsize=box)).astype(np.float64)
+        assert np.abs(pot2 - pot).max() <= 1e-6 * np.abs(pot).max()
+    t.close()
 
 
 def test_full_size_potential_properties(outdir):
