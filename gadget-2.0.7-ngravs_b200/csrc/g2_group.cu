@@ -325,7 +325,7 @@ extern "C" int g2gpu_group_upload_aos(g2gpu_group *g, int npart, const void *P, 
   if(off_vel >= 0 && g->n > 1)
     return g2_fail(G2GPU_ERR_ARG, "velocities (Extnodes[].vs of the host tree mirror) are served by a single-device group only");
   const unsigned int hw = std::max(1u, std::thread::hardware_concurrency());
-  const unsigned int thr = std::max(1u, std::min(16u, hw) / (unsigned int) g->n);
+  const unsigned int thr = std::max(1u, std::min(32u, hw) / (unsigned int) g->n);
   G2_TRY(run_all(g, [&](int i) {
     int lo, cnt;
     shard_of(g, npart, i, &lo, &cnt);
@@ -470,7 +470,7 @@ static void rebalance(g2gpu_group *g)
     return;
   const int nb = (nt + G2_COST_BLOCK - 1) / G2_COST_BLOCK;
   g->profile.assign((size_t) nb, 0.0);
-  const unsigned int hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  const unsigned int hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
   for(int i = 0; i < g->n; i++)
     {
       // blocks of the profile that overlap this device's slice, shared out over host threads (a block is summed by one thread; the
@@ -527,7 +527,7 @@ extern "C" int g2gpu_group_download_acc(g2gpu_group *g, float *acc, float *cost,
   if(!g)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   const unsigned int hw = std::max(1u, std::thread::hardware_concurrency());
-  const unsigned int thr = std::max(1u, std::min(16u, hw) / (unsigned int) g->n);
+  const unsigned int thr = std::max(1u, std::min(32u, hw) / (unsigned int) g->n);
   G2_TRY(run_all(g, [&](int i) {
     G2_TRY(fetch_slice_results(g, i));
     const float *r = g->h_res[i];
@@ -568,7 +568,7 @@ extern "C" int g2gpu_group_download_aos(g2gpu_group *g, void *P, size_t stride, 
   if(float_bytes != 4 && float_bytes != 8)
     return g2_fail(G2GPU_ERR_ARG, "float_bytes must be 4 or 8");
   const unsigned int hw = std::max(1u, std::thread::hardware_concurrency());
-  const unsigned int thr = std::max(1u, std::min(16u, hw) / (unsigned int) g->n);
+  const unsigned int thr = std::max(1u, std::min(32u, hw) / (unsigned int) g->n);
   double sums[G2_GROUP_MAX];
   G2_TRY(run_all(g, [&](int i) {
     G2_TRY(fetch_slice_results(g, i));
@@ -663,7 +663,18 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
   g->gather_bytes = g->n > 1 ? (long long) g->per * g->n * (long long) sizeof(G2PRec) : 0;
   G2_TRY(g2gpu_group_download_acc(g, acc, cost, oldacc_out));
   if(perm)
-    G2_TRY(g2gpu_get_order(g->ctx[0], perm));
+    {
+      // every device holds the same order: each one returns 1/N of it over its own link
+      G2_TRY(run_all(g, [&](int i) {
+	g2gpu_ctx *c = g->ctx[i];
+	const size_t lo = (size_t) npart * i / g->n, hi = (size_t) npart * (i + 1) / g->n;
+	if(hi > lo)
+	  G2_CUDA(cudaMemcpyAsync(perm + lo, c->perm + lo, sizeof(int) * (hi - lo), cudaMemcpyDeviceToHost, c->stream));
+	G2_CUDA(cudaStreamSynchronize(c->stream));
+	return 0;
+      }));
+      g->d2h_bytes += (long long) sizeof(int) * npart;
+    }
   return 0;
 }
 

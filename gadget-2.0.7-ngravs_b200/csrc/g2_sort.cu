@@ -289,6 +289,23 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_scatter_kernel(const uns
 // instead of histogram + three scan kernels + scatter (32 B per pair and pass, five launches).  The digit histograms of ALL passes are
 // counted by one kernel up front (they do not depend on the order of the pairs).  Tiles take their number from an atomic ticket, so
 // every tile a look-back waits for is already running.
+// lanes of the warp that hold the same digit (d <= OS_BINS: OS_BITS + 1 bits).  BALLOT: one vote per digit bit instead of MATCH.ANY.
+template <bool BALLOT>
+__device__ __forceinline__ unsigned int os_peers(unsigned int d)
+{
+  if(!BALLOT)
+    return __match_any_sync(0xffffffffu, d);
+  unsigned int peers = 0xffffffffu;
+#pragma unroll
+  for(int b = 0; b <= RADIX_BITS; b++)
+    {
+      const bool bit = (d >> b) & 1u;
+      const unsigned int bal = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bal : ~bal;
+    }
+  return peers;
+}
+
 #define OS_BITS RADIX_BITS		// 9 bits: 7 passes for the 56-bit (block, Peano-Hilbert) keys and for the 63-bit tree keys
 #define OS_BINS (1 << OS_BITS)
 #define OS_MAXPASS 8
@@ -334,18 +351,24 @@ __global__ void __launch_bounds__(OS_BINS) os_scan_kernel(unsigned int *hist, in
     tickets[threadIdx.x] = 0;
 }
 
-#define OS_SMEM (SORT_WARPS * OS_BINS * 4 + 2 * OS_BINS * 4 + 64 * 4 + SORT_TILE * 8 + SORT_TILE * 4)
-__global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
+#define OS_SMEM(ITEMS) (SORT_WARPS * OS_BINS * 4 + 2 * OS_BINS * 4 + 64 * 4 + (SORT_THREADS * (ITEMS)) * 8 + (SORT_THREADS * (ITEMS)) * 4)
+// ITEMS pairs per thread: 16 (4096-pair tiles, 3 CTAs per SM; default) or 8 (2048-pair tiles, 4 CTAs per SM, values loaded together with the keys;
+// G2GPU_SORT_ITEMS=8).  The pass is latency bound (ncu, profiles/r2_ospass_p256.txt: 15 % issue slots, 17 long-scoreboard stalls per issue, DRAM
+// 14 %).  MEASURED (B200, 16.8 M pairs, 7 passes): 2.25 ms with 16 items, 2.19 ms with 8 items at 4 CTAs, 2.15 ms at 5 CTAs (48 registers, spills):
+// more resident warps do not buy the pass anything, so the dependent chains inside a tile (look-back, ranking) are what to shorten next.
+template <int ITEMS, int BLOCKS, bool BALLOT>
+__global__ void __launch_bounds__(SORT_THREADS, BLOCKS) os_pass_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
 								    unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
 								    const unsigned int *__restrict__ binbase /* this pass's scanned histogram */,
 								    volatile unsigned int *__restrict__ status /* [tile][bin] of this pass, zeroed */,
 								    unsigned int *__restrict__ ticket, int n, int shift, unsigned int mask,
 								    unsigned int *__restrict__ capture_dest)
 {
+  constexpr int TILE = SORT_THREADS * ITEMS;
   extern __shared__ unsigned long long sort_dyn[];
-  unsigned long long *stage_k = sort_dyn;				// SORT_TILE keys
-  unsigned int *stage_v = (unsigned int *) (stage_k + SORT_TILE);	// SORT_TILE values
-  unsigned int (*wcnt)[OS_BINS] = (unsigned int (*)[OS_BINS]) (stage_v + SORT_TILE);	// per-warp digit counts -> warp offsets
+  unsigned long long *stage_k = sort_dyn;				// TILE keys
+  unsigned int *stage_v = (unsigned int *) (stage_k + TILE);	// TILE values
+  unsigned int (*wcnt)[OS_BINS] = (unsigned int (*)[OS_BINS]) (stage_v + TILE);	// per-warp digit counts -> warp offsets
   unsigned int *binstart = &wcnt[0][0] + SORT_WARPS * OS_BINS;	// tile-local exclusive scan of the tile histogram
   unsigned int *gdelta = binstart + OS_BINS;				// global start of the tile's run of a bin, minus binstart
   unsigned int *scratch = gdelta + OS_BINS;				// 33 words for the block scan + the ticket
@@ -357,24 +380,26 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned
   __syncthreads();
   const int tile = (int) scratch[40];
 
-  const size_t tbase = (size_t) tile * SORT_TILE;
-  const int tcount = (size_t) n - tbase < (size_t) SORT_TILE ? (int) ((size_t) n - tbase) : SORT_TILE;
-  const size_t wbase = tbase + (size_t) warp * (32 * SORT_ITEMS);
-  unsigned long long k[SORT_ITEMS];
-  unsigned int r[SORT_ITEMS];
+  const size_t tbase = (size_t) tile * TILE;
+  const int tcount = (size_t) n - tbase < (size_t) TILE ? (int) ((size_t) n - tbase) : TILE;
+  const size_t wbase = tbase + (size_t) warp * (32 * ITEMS);
+  unsigned long long k[ITEMS];
+  unsigned int r[ITEMS], v[ITEMS <= 8 ? ITEMS : 1];
 #pragma unroll
-  for(int i = 0; i < SORT_ITEMS; i++)
+  for(int i = 0; i < ITEMS; i++)
     {
       size_t idx = wbase + (size_t) i * 32 + lane;
       k[i] = (idx < (size_t) n) ? keys_in[idx] : ~0ull;
+      if(ITEMS <= 8)
+	v[i] = (idx < (size_t) n) ? vals_in[idx] : 0u;
     }
 #pragma unroll
-  for(int i = 0; i < SORT_ITEMS; i++)
+  for(int i = 0; i < ITEMS; i++)
     {
       size_t idx = wbase + (size_t) i * 32 + lane;
       bool valid = idx < (size_t) n;
       unsigned int d = valid ? digit_of(k[i], shift, mask) : OS_BINS;	// invalid lanes match only each other
-      unsigned int peers = __match_any_sync(0xffffffffu, d);
+      unsigned int peers = os_peers<BALLOT>(d);
       unsigned int below = __popc(peers & ((1u << lane) - 1u));
       unsigned int prev = 0;
       int leader = __ffs(peers) - 1;
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned
   __syncthreads();
   // tile-sorted staging
 #pragma unroll
-  for(int i = 0; i < SORT_ITEMS; i++)
+  for(int i = 0; i < ITEMS; i++)
     {
       size_t idx = wbase + (size_t) i * 32 + lane;
       if(idx < (size_t) n)
@@ -456,7 +481,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned
 	  unsigned int d = digit_of(k[i], shift, mask);
 	  unsigned int pos = binstart[d] + wcnt[warp][d] + r[i];
 	  stage_k[pos] = k[i];
-	  stage_v[pos] = vals_in[idx];
+	  stage_v[pos] = ITEMS <= 8 ? v[ITEMS <= 8 ? i : 0] : vals_in[idx];
 	  if(capture_dest)		// where the element at input position idx of THIS pass ends up (coalesced: consecutive lanes, consecutive idx)
 	    capture_dest[idx] = gdelta[d] + pos;
 	}
@@ -475,7 +500,8 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) os_pass_kernel(const unsigned
 static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys_io, unsigned int **vals_io, unsigned long long *keys_alt,
 				  unsigned int *vals_alt, int begin_bit, int end_bit, int capture_shift, unsigned int *capture_dest)
 {
-  const int ntiles = g2_cdiv(n, SORT_TILE);
+  const int items = c->sort_items == 8 ? 8 : 16;
+  const int ntiles = g2_cdiv(n, SORT_THREADS * items);
   const int nbits = end_bit - begin_bit;
   const int npass = (nbits + OS_BITS - 1) / OS_BITS;
   if(npass > OS_MAXPASS)
@@ -493,7 +519,9 @@ static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys
   os_hist_kernel<<<hb, 256, 0, st>>>(*keys_io, n, begin_bit, nbits, npass, hist);
   os_scan_kernel<<<1, OS_BINS, 0, st>>>(hist, npass, tickets);
   c->launches += 2;
-  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM));
+  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(16)));
+  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(16)));
+  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(8)));
   unsigned long long *kin = *keys_io, *kout = keys_alt;
   unsigned int *vin = *vals_io, *vout = vals_alt;
   for(int p = 0; p < npass; p++)
@@ -501,8 +529,18 @@ static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys
       const int shift = begin_bit + p * OS_BITS;
       const int bits = end_bit - shift < OS_BITS ? end_bit - shift : OS_BITS;
       const unsigned int mask = (1u << bits) - 1u;
-      os_pass_kernel<<<ntiles, SORT_THREADS, OS_SMEM, st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n, shift,
-							    mask, shift == capture_shift ? capture_dest : nullptr);
+      if(items == 8)
+	os_pass_kernel<8, 4, false><<<ntiles, SORT_THREADS, OS_SMEM(8), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
+								    shift, mask, shift == capture_shift ? capture_dest : nullptr);
+      else
+	{
+	  if(c->sort_rank_ballot)
+	  	os_pass_kernel<16, 3, true><<<ntiles, SORT_THREADS, OS_SMEM(16), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
+								      shift, mask, shift == capture_shift ? capture_dest : nullptr);
+	  else
+	  	os_pass_kernel<16, 3, false><<<ntiles, SORT_THREADS, OS_SMEM(16), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
+								      shift, mask, shift == capture_shift ? capture_dest : nullptr);
+	}
       c->launches++;
       unsigned long long *tk = kin; kin = kout; kout = tk;
       unsigned int *tv = vin; vin = vout; vout = tv;
