@@ -43,8 +43,8 @@ UNIT = "updates/s"
 # nominal FP32 peak of the CUDA cores: SMs x 128 lanes x 2 flop (FMA) x max SM clock
 FLOP_PER_TERM = {"np": 20.0, "per": 26.0, "sr": 31.0}
 # radix sort of stage 1: 7 passes x (8 B histogram read + 12 B scatter read + 12 B write) per pair
-SORT_BYTES_PER_PAIR = 7 * 32.0
-SORT_KERNELS = "sort_hist_kernel+sort_scatter_kernel (stage 1, 7 passes)"
+SORT_BYTES_PER_PAIR = 7 * 24.0 + 8.0     # one-sweep: 12 B read + 12 B written per pair and pass, keys read once more for the histograms of all passes
+SORT_KERNELS = "os_hist_kernel+os_pass_kernel (domain sort, 7 one-sweep passes of 9 bits)"
 
 
 # ------------------------------------------------------------------------------------------------ workloads -----
@@ -418,7 +418,6 @@ def main():
             acc_e, cost_e, old_e, perm_e = grp.gravity_tree(h_pos, h_mass, h_type, wp_rel, oldacc=h_old, out=outbuf)
             e_s += time.perf_counter() - t0
         h2d, d2h, gathered = grp.io_bytes()
-        d2h += 4 * n                                   # the permutation (perm) read back with the results
         e2e = {"value": n / (e_s / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e_s / K,
                "allgather_bytes_per_device": gathered, "clock": "host wall clock around g2gpu_group_gravity_tree (results in host memory on return)",
                "checksum": float(np.abs(acc_e).sum())}

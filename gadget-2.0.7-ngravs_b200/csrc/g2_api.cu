@@ -90,8 +90,9 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   // radix-sort scratch: the one-sweep sort keeps a status word per (pass, tile, bin): 7 passes x tiles x 512 bins
   c->tilehist_elems = (size_t) 8 * 512 + 16 + (size_t) 7 * ((np + 2047) / 2048) * 512;	// (2048-pair tiles: G2GPU_SORT_ITEMS=8)
   c->sort_onesweep = getenv("G2GPU_SORT_ONESWEEP") ? atoi(getenv("G2GPU_SORT_ONESWEEP")) != 0 : 1;
-  c->sort_items = getenv("G2GPU_SORT_ITEMS") ? atoi(getenv("G2GPU_SORT_ITEMS")) : 16;
+  c->sort_items = getenv("G2GPU_SORT_ITEMS") ? atoi(getenv("G2GPU_SORT_ITEMS")) : 8;
   c->sort_rank_ballot = getenv("G2GPU_SORT_RANK_BALLOT") ? atoi(getenv("G2GPU_SORT_RANK_BALLOT")) != 0 : 0;
+  c->sort_window = getenv("G2GPU_SORT_WINDOW") ? atoi(getenv("G2GPU_SORT_WINDOW")) : 4;
   rc |= dalloc(&c->tilehist, c->tilehist_elems);
   c->scan_tmp_elems = cap / 2048 + 16 + c->tilehist_elems / 2048;
   rc |= dalloc(&c->scan_tmp, c->scan_tmp_elems);

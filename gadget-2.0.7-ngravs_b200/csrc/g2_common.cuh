@@ -158,8 +158,9 @@ struct g2gpu_ctx
   unsigned long long *skey[2];
   unsigned int *sval[2];
   int sort_onesweep;		// option "sort_onesweep" (default 1): one kernel per radix digit with decoupled look-back
-  int sort_items;		// pairs per thread of a one-sweep pass: 16 (default) or 8 (G2GPU_SORT_ITEMS)
+  int sort_items;		// pairs per thread of a one-sweep pass: 8 (default) or 16 (G2GPU_SORT_ITEMS)
   int sort_rank_ballot;	// rank the digits of a tile with one warp vote per digit bit instead of MATCH.ANY (G2GPU_SORT_RANK_BALLOT)
+  int sort_window;		// predecessor tiles fetched per look-back step: 4 (default) or 8 (G2GPU_SORT_WINDOW)
   unsigned int *tilehist;	// NBINS * ntiles
   size_t tilehist_elems;
   unsigned int *scan_tmp;	// block sums for the device-wide scan

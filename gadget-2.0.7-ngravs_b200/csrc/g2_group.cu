@@ -643,11 +643,15 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
   G2_TRY(group_begin_upload(g, npart));
   if(!pos || !mass || !type)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
+  // one device and every particle a target: the walk writes its results in particle order and they are copied straight into the caller's
+  // arrays -- no compaction, no index list, no host scatter
+  const bool direct = g->n == 1 && !active;
   // one host thread per device drives its whole pipeline: no host barrier between the stages (the all-gather synchronises the devices)
   G2_TRY(run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
     int lo, cnt;
     shard_of(g, npart, i, &lo, &cnt);
+    c->compact = direct ? 0 : 1;
     G2_TRY(g2_upload_soa_shard(c, npart, lo, cnt, pos, mass, type, oldacc, active));
     G2_TRY(group_allgather(g, i, 0));
     G2_TRY(g2_stage_domain(c));
@@ -661,7 +665,21 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
   for(int i = 0; i < g->n; i++)
     g->h2d_bytes += (long long) g->ctx[i]->h2d_bytes;
   g->gather_bytes = g->n > 1 ? (long long) g->per * g->n * (long long) sizeof(G2PRec) : 0;
-  G2_TRY(g2gpu_group_download_acc(g, acc, cost, oldacc_out));
+  if(direct)
+    {
+      g2gpu_ctx *c = g->ctx[0];
+      G2_TRY(g2_fetch_slice(c));
+      g->lo[0] = c->w_lo;
+      g->hi[0] = c->w_hi;
+      g->ntargets = c->w_ntargets;
+      int rc = g2gpu_download_acc(c, acc, cost, oldacc_out);
+      c->compact = 1;
+      if(rc)
+	return rc;
+      g->d2h_bytes = (long long) c->d2h_bytes;
+    }
+  else
+    G2_TRY(g2gpu_group_download_acc(g, acc, cost, oldacc_out));
   if(perm)
     {
       // every device holds the same order: each one returns 1/N of it over its own link

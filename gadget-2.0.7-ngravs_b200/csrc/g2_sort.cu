@@ -352,11 +352,11 @@ __global__ void __launch_bounds__(OS_BINS) os_scan_kernel(unsigned int *hist, in
 }
 
 #define OS_SMEM(ITEMS) (SORT_WARPS * OS_BINS * 4 + 2 * OS_BINS * 4 + 64 * 4 + (SORT_THREADS * (ITEMS)) * 8 + (SORT_THREADS * (ITEMS)) * 4)
-// ITEMS pairs per thread: 16 (4096-pair tiles, 3 CTAs per SM; default) or 8 (2048-pair tiles, 4 CTAs per SM, values loaded together with the keys;
-// G2GPU_SORT_ITEMS=8).  The pass is latency bound (ncu, profiles/r2_ospass_p256.txt: 15 % issue slots, 17 long-scoreboard stalls per issue, DRAM
-// 14 %).  MEASURED (B200, 16.8 M pairs, 7 passes): 2.25 ms with 16 items, 2.19 ms with 8 items at 4 CTAs, 2.15 ms at 5 CTAs (48 registers, spills):
-// more resident warps do not buy the pass anything, so the dependent chains inside a tile (look-back, ranking) are what to shorten next.
-template <int ITEMS, int BLOCKS, bool BALLOT>
+// ITEMS pairs per thread: 8 (2048-pair tiles, 4 CTAs per SM, values loaded together with the keys; default) or 16 (4096-pair tiles, 3 CTAs per SM;
+// G2GPU_SORT_ITEMS=16).  The pass is latency bound (ncu, profiles/r2_ospass_p256.txt: 15 % issue slots, 17 long-scoreboard stalls per issue, DRAM 14 %).
+// MEASURED (B200, 16.8 M pairs, 7 passes of the domain sort; profiles/r2_sort_variants.txt): serial look-back 2.25 ms (16 items) / 2.19 ms (8 items);
+// windowed look-back 2.08 / 1.90 ms; a window of 8 tiles instead of 4 and ranking by warp votes instead of MATCH.ANY change nothing.
+template <int ITEMS, int BLOCKS, bool BALLOT, int WINDOW>
 __global__ void __launch_bounds__(SORT_THREADS, BLOCKS) os_pass_kernel(const unsigned long long *__restrict__ keys_in, const unsigned int *__restrict__ vals_in,
 								    unsigned long long *__restrict__ keys_out, unsigned int *__restrict__ vals_out,
 								    const unsigned int *__restrict__ binbase /* this pass's scanned histogram */,
@@ -432,34 +432,54 @@ __global__ void __launch_bounds__(SORT_THREADS, BLOCKS) os_pass_kernel(const uns
       // publish this tile's count of the bin
       status[(size_t) tile * OS_BINS + b] = run | (tile == 0 ? OS_FLAG_INC : OS_FLAG_AGG);
     }
-  // add up the tiles before this one (decoupled look-back), then publish the inclusive count
+  // add up the tiles before this one (decoupled look-back), then publish the inclusive count.  A thread owns two adjacent bins, i.e. one
+  // 8-byte word of every tile's status row; it fetches the words of WINDOW predecessor tiles at once (independent loads: the chain of L2
+  // round trips, which is what bounds the pass, becomes WINDOW times shorter) and consumes them in order up to the first one that is not
+  // published yet.
+  static_assert(OS_BINS / SORT_THREADS == 2, "two bins per thread");
+  {
+    const int b0 = threadIdx.x * 2;
+    unsigned int before0 = 0, before1 = 0;
+    if(tile > 0)
+      {
+	bool done0 = false, done1 = false;
+	int t = tile - 1;
+	while(!(done0 && done1))
+	  {
+	    unsigned long long sw[WINDOW];
 #pragma unroll
-  for(int q = 0; q < OS_BINS / SORT_THREADS; q++)
-    {
-      const int b = threadIdx.x * (OS_BINS / SORT_THREADS) + q;
-      unsigned int before = 0;
-      if(tile > 0)
-	{
-	  int t = tile - 1;
-	  while(true)
-	    {
-	      const unsigned int sw = status[(size_t) t * OS_BINS + b];
-	      if(sw & OS_FLAG_INC)
-		{
-		  before += sw & OS_VALUE_MASK;
-		  break;
-		}
-	      if(sw & OS_FLAG_AGG)
-		{
-		  before += sw & OS_VALUE_MASK;
-		  t--;
-		}
-	      // else: not published yet (that tile holds a smaller ticket, so it is running): look again
-	    }
-	  status[(size_t) tile * OS_BINS + b] = (before + run2[q]) | OS_FLAG_INC;
-	}
-      before2[q] = before;
-    }
+	    for(int w = 0; w < WINDOW; w++)
+	      sw[w] = t - w >= 0 ? *(const volatile unsigned long long *) (status + (size_t) (t - w) * OS_BINS + b0)
+		: ((unsigned long long) OS_FLAG_INC << 32 | OS_FLAG_INC);	// (before tile 0: nothing)
+	    int used = 0;
+#pragma unroll
+	    for(int w = 0; w < WINDOW; w++)
+	      {
+		const unsigned int lo = (unsigned int) sw[w], hi = (unsigned int) (sw[w] >> 32);
+		const bool ready = (done0 || (lo & (OS_FLAG_INC | OS_FLAG_AGG))) && (done1 || (hi & (OS_FLAG_INC | OS_FLAG_AGG)));
+		if(used == w && ready && !(done0 && done1))
+		  {
+		    if(!done0)
+		      {
+			before0 += lo & OS_VALUE_MASK;
+			done0 = (lo & OS_FLAG_INC) != 0u;
+		      }
+		    if(!done1)
+		      {
+			before1 += hi & OS_VALUE_MASK;
+			done1 = (hi & OS_FLAG_INC) != 0u;
+		      }
+		    used = w + 1;
+		  }
+	      }
+	    t -= used;		// (used == 0: the nearest word is not published yet -- that tile holds a smaller ticket, so it is running: look again)
+	  }
+	status[(size_t) tile * OS_BINS + b0] = (before0 + run2[0]) | OS_FLAG_INC;
+	status[(size_t) tile * OS_BINS + b0 + 1] = (before1 + run2[1]) | OS_FLAG_INC;
+      }
+    before2[0] = before0;
+    before2[1] = before1;
+  }
   unsigned int blocktotal;
   unsigned int ex = block_excl_scan(mysum, &blocktotal, scratch);
 #pragma unroll
@@ -519,9 +539,6 @@ static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys
   os_hist_kernel<<<hb, 256, 0, st>>>(*keys_io, n, begin_bit, nbits, npass, hist);
   os_scan_kernel<<<1, OS_BINS, 0, st>>>(hist, npass, tickets);
   c->launches += 2;
-  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<16, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(16)));
-  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(16)));
-  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<8, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(8)));
   unsigned long long *kin = *keys_io, *kout = keys_alt;
   unsigned int *vin = *vals_io, *vout = vals_alt;
   for(int p = 0; p < npass; p++)
@@ -529,18 +546,22 @@ static int g2_onesweep_sort_pairs(g2gpu_ctx *c, int n, unsigned long long **keys
       const int shift = begin_bit + p * OS_BITS;
       const int bits = end_bit - shift < OS_BITS ? end_bit - shift : OS_BITS;
       const unsigned int mask = (1u << bits) - 1u;
+#define G2_OS_LAUNCH(IT, BL, BA, WI) do { \
+	  G2_CUDA(cudaFuncSetAttribute(os_pass_kernel<IT, BL, BA, WI>, cudaFuncAttributeMaxDynamicSharedMemorySize, OS_SMEM(IT))); \
+	  os_pass_kernel<IT, BL, BA, WI><<<ntiles, SORT_THREADS, OS_SMEM(IT), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, \
+	      tickets + p, n, shift, mask, shift == capture_shift ? capture_dest : nullptr); } while(0)
+      const bool w8 = c->sort_window == 8;
       if(items == 8)
-	os_pass_kernel<8, 4, false><<<ntiles, SORT_THREADS, OS_SMEM(8), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
-								    shift, mask, shift == capture_shift ? capture_dest : nullptr);
+	{
+	  if(w8) G2_OS_LAUNCH(8, 4, false, 8); else G2_OS_LAUNCH(8, 4, false, 4);
+	}
+      else if(c->sort_rank_ballot)
+	G2_OS_LAUNCH(16, 3, true, 4);
       else
 	{
-	  if(c->sort_rank_ballot)
-	  	os_pass_kernel<16, 3, true><<<ntiles, SORT_THREADS, OS_SMEM(16), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
-								      shift, mask, shift == capture_shift ? capture_dest : nullptr);
-	  else
-	  	os_pass_kernel<16, 3, false><<<ntiles, SORT_THREADS, OS_SMEM(16), st>>>(kin, vin, kout, vout, hist + p * OS_BINS, status + (size_t) p * ntiles * OS_BINS, tickets + p, n,
-								      shift, mask, shift == capture_shift ? capture_dest : nullptr);
+	  if(w8) G2_OS_LAUNCH(16, 3, false, 8); else G2_OS_LAUNCH(16, 3, false, 4);
 	}
+#undef G2_OS_LAUNCH
       c->launches++;
       unsigned long long *tk = kin; kin = kout; kout = tk;
       unsigned int *tv = vin; vin = vout; vout = tv;
