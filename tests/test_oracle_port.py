@@ -12,7 +12,7 @@ import g2test
 from portrun import PortOracle, make_srtable
 from refrun import RefOracle, available
 
-GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")) if "config1" not in p and not os.path.basename(p).startswith(("pm_", "pot_", "lattice_")))   # pm_*: PM fixtures, tests/test_pm_oracle.py
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")) if "config1" not in p and not os.path.basename(p).startswith(("pm_", "pmpot_", "pot_", "lattice_")))   # pm_*: PM fixtures, tests/test_pm_oracle.py
 
 
 def port_from_fixture(g):
