@@ -124,6 +124,7 @@ struct g2gpu_ctx
   int walk_stats;		// option "walk_stats": the instrumented walk kernel (visits, species terms, decisions in counters[2..4])
   int walk_exact;		// option "walk_exact" (default 1): borderline decisions are re-taken in FP64 (exact GravCost)
   int walk_defer;		// option "walk_defer" (G2GPU_WALK_DEFER; -DG2_WALK_DEFER builds only): stock pair laws evaluated from the per-warp source ring
+  int walk_flush_mask;		// G2GPU_WALK_FLUSH_MASK (0, 1, 3, 7 = default): the FP32 partial sums of the walk go into the accumulators at descents with (cell index & mask) == 0
   int compact;			// option "compact": the walk writes its slice's results in target order (cres) instead of by particle index
   float *cres;			// 5 floats per target of the slice (acc[3], cost, oldacc), allocated with the option
   int slice_explicit;		// slice_frac[] instead of rank/nranks (cost-weighted slices of the group path)

@@ -138,6 +138,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.tol_crit = 1.5e-6f;
   A.tol_wide = 1.0e-4f;
   A.exact = c->walk_exact;
+  A.flush_mask = (unsigned int) c->walk_flush_mask;
   if(sr)
     {
       A.rcut = (float) wp->rcut; A.rcut2 = (float) (wp->rcut * wp->rcut);

@@ -72,6 +72,7 @@ struct WalkArgs
   unsigned int redo_cap;
   int use_gravpm;
   int exact;			// 0: no FP64 re-evaluation (FP32 decisions only)
+  unsigned int flush_mask;	// the FP32 partial sums are flushed into the accumulators when the warp descends at a cell with (index & mask) == 0
   float fsoft[6];
   int t2g[6];
   unsigned char tabmap[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS];	// [tgt*D+src] -> unique table

@@ -380,19 +380,23 @@ __device__ __forceinline__ unsigned int walk_visit(const WalkArgs &A, const floa
   WalkShift S;
   if(cur >= L.skip_until)
     open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
-  if(__ballot_sync(0xffffffffu, open) == 0u)
+  if(!__any_sync(0xffffffffu, open))
     return w.x;			// nobody opens the cell: on to its sibling
-  // FP32 partial sums go into the accumulators whenever the warp descends (about every third visit): few conversions, bounded
-  // error, and flush points that depend on the traversal only (=> reproducible bits)
-  if(sizeof(ACC) == 8)
+  // FP32 partial sums go into the accumulators when the warp descends at a cell whose index has its low bits clear (A.flush_mask; with 0
+  // at every descent, about every third visit): few conversions, bounded error, and flush points that depend on the traversal only
+  // (=> reproducible bits)
+  if((cur & A.flush_mask) == 0u)
     {
-      acc_sh[0][threadIdx.x] += (ACC) L.fx; acc_sh[1][threadIdx.x] += (ACC) L.fy; acc_sh[2][threadIdx.x] += (ACC) L.fz;
+      if(sizeof(ACC) == 8)
+	{
+	  acc_sh[0][threadIdx.x] += (ACC) L.fx; acc_sh[1][threadIdx.x] += (ACC) L.fy; acc_sh[2][threadIdx.x] += (ACC) L.fz;
+	}
+      else
+	{
+	  ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
+	}
+      L.fx = L.fy = L.fz = 0.0f;
     }
-  else
-    {
-      ax += (ACC) L.fx; ay += (ACC) L.fy; az += (ACC) L.fz;
-    }
-  L.fx = L.fy = L.fz = 0.0f;
   if((w.z & 15u) != 0u)
     walk_visit_particles<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT>(A, s_tab, s_tab_addr, w, open, t2g_packed, L, S, small_cell);
   return cur + 1u;
@@ -673,6 +677,8 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
 	    }
 	  else if(cur >= end)
 	    break;
+	  // (MEASURED, round 2, profiles/experiments/r2_run22.sh: a prefetch.global.L1 of the sibling's record here costs 1 ms at 256^3, and the
+	  // mere presence of the option, a uniform branch, 5 ms; a shared-memory carveout of 100 KB instead of the driver's 132 KB gains 0.5 %.)
 	  const float4 *rec = A.cells + (size_t) cur * RW;
 	  const float4 q0 = __ldg(rec);
 	  const uint4 w = __ldg((const uint4 *) (rec + 1 + D));
