@@ -400,6 +400,7 @@ extern "C" int g2gpu_group_walk(g2gpu_group *g, const g2gpu_walk_params *wp)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   return run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
+    c->compact = 1;		// (the slice downloads read the compacted results)
     c->slice_explicit = 1;
     c->slice_frac[0] = g->frac[i];
     c->slice_frac[1] = g->frac[i + 1];
@@ -706,6 +707,7 @@ extern "C" int g2gpu_group_step_resident(g2gpu_group *g, int npart, const g2gpu_
   G2_TRY(run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
     G2_TRY(g2gpu_inputs_ready(c, npart));
+    c->compact = 1;
     G2_TRY(group_allgather(g, i, 0));
     G2_TRY(g2_stage_domain(c));
     G2_TRY(g2_stage_treebuild(c));

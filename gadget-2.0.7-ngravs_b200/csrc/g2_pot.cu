@@ -305,8 +305,11 @@ __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_ke
 	  const unsigned int ball = __ballot_sync(0xffffffffu, open);
 	  if(ball != 0u)
 	    {
-	      pot += (double) fpot;
-	      fpot = 0.0f;
+	      if((cur & 7u) == 0u)	// (the FP32 partial sum goes into the FP64 accumulator at every eighth cell index, like in the force walk)
+		{
+		  pot += (double) fpot;
+		  fpot = 0.0f;
+		}
 	      const unsigned int np = w.z & 15u;
 	      for(unsigned int j = 0; j < np; j++)
 		{

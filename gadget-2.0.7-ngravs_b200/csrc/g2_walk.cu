@@ -147,6 +147,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       A.utor2wpi = (float) (1.0 / (M_PI * 4 * wp->asmth * wp->asmth));	// forcetree.c:1711
       const double rmax = c->cfg.ntab / asmthfac_d;
       A.rmax2 = (float) (rmax * rmax);
+      A.ntabm1f = (float) (c->cfg.ntab - 1);
       A.rmax2_border = (float) (rmax * rmax * 6.0e-7);
       // a tree that follows the host's drifted nodes (g2gpu_update_tree) may hold centres of mass outside their cubes: neither the
       // geometric cull shortcut nor the per-cell image shift may then be used

@@ -57,6 +57,7 @@ struct WalkArgs
   float boxsize, boxinv;
   float rcut, rcut2, asmthfac, utor2wpi;
   float rmax2;			// (NTAB / asmthfac)^2: a term counts while r^2 is below it (tabindex < NTAB, forcetree.c:1962-1967)
+  float ntabm1f;		// (float) (NTAB - 1)
   float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions); +inf disables the shortcut
   float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
   // guard bands: a comparison whose two sides are closer than this is re-taken in FP64, the arithmetic the reference decides in
@@ -122,10 +123,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 // table (tabindex < NTAB, forcetree.c:1962-1967), decided by the caller; `m != 0` is checked by the caller for node terms
 // (forcetree.c:1553, 1992).  Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the
 // rare r < h case.
-template <bool SR, bool STOCK>
+// SPL = false: the caller knows that r >= h (no softening spline needed).  asmthfac: A.asmthfac, which the walk kernel keeps in a register
+// (re-reading it from the constant bank costs an instruction per term).
+template <bool SR, bool STOCK, bool SPL = true>
 __device__ __forceinline__ void pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
 					  float pmass, float m, float dx, float dy, float dz, float r2, float h, bool counted, float &fx, float &fy, float &fz,
-					  float nn = 1.0f)	// N of forcetree.c:1563-1577 (only the non-stock laws read it)
+					  float asmthfac, float nn = 1.0f)	// nn: N of forcetree.c:1563-1577 (only the non-stock laws read it)
 {
   const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   const float r = r2 * rinv;
@@ -134,14 +137,14 @@ __device__ __forceinline__ void pair_term(const WalkArgs &A, const float *__rest
       float fac;
       if(SR)
 	{
-	  const int tabindex = min((int) (A.asmthfac * r), A.ntab - 1);	// forcetree.c:1962
+	  const int tabindex = (int) fminf(asmthfac * r, A.ntabm1f);	// forcetree.c:1962 (clamped: terms beyond the table are not counted)
 	  const float t = lds_f32(s_tab_addr + 4u * (unsigned int) tabindex);
-	  // (m/r^2 - m*utor2wpi*tab) / r   (forcetree.c:1972-1974)
-	  fac = m * rinv * fmaf(-A.utor2wpi, t, rinv * rinv);
+	  // (m/r^2 - m*utor2wpi*tab) / r   (forcetree.c:1972-1974); the stock kernel's copy of the table in shared memory holds utor2wpi * tab
+	  fac = m * rinv * (rinv * rinv - t);
 	}
       else
 	fac = m * rinv * rinv * rinv;
-      if(r < h)			// inside the softening: spline (rare)
+      if(SPL && r < h)		// inside the softening: spline (rare)
 	fac = law_plummer(m, h, r);
       fac = counted ? fac : 0.0f;
       fx = fmaf(dx, fac, fx);

@@ -130,6 +130,7 @@ struct WalkLane
   float bmin;			// EXACT: smallest distance of any comparison of this walk from its guard band (negative: inside)
   unsigned int skip_until;
   unsigned int bits;		// DEFER: ring entries (staged sources) this lane still has to evaluate
+  float k_rmax2, k_asmthfac;	// A.rmax2, A.asmthfac pinned in registers (uniform values: re-reading them from the constant bank costs instructions per term)
 };
 
 // DEFER (stock pair laws): the terms a lane accepts are not evaluated where they are found -- a handful of lanes at a time -- but staged.
@@ -280,32 +281,51 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
       L.skip_until = w.x;	// sleep until the cursor leaves this subtree
       if(!done)
 	{
-	  bool any = false;
+	  bool any = false, cnt[D];
 #pragma unroll
 	  for(int g = 0; g < D; g++)
 	    {
 	      bool counted = mass[g] != 0.0f;	// forcetree.c:1553 / 1992
 	      if(SR)
 		{
-		  const float tv = r2[g] - A.rmax2;
+		  const float tv = r2[g] - L.k_rmax2;
 		  if(EXACT)
 		    bm = fminf(bm, fabsf(tv) - A.rmax2_border);
 		  counted = counted && tv < 0.0f;
 		}
+	      cnt[g] = counted;
 	      if(DEFER)
 		*newbits |= (counted ? 1u : 0u) << g;	// evaluated from the ring (ring_flush)
-	      else
-		{
-		  const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
-		  if(mass[g] != 0.0f)	// a property of the cell, hence uniform: small cells often hold one species only
-		    pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, counted, L.fx, L.fy, L.fz, nn);
-		}
 	      any |= counted;
 	      if(STATS)
 		L.nterms += counted;
 	    }
 	  if(!SR || any)
 	    L.ninter++;		// forcetree.c:1585 resp. 2031-2032
+	  if(!DEFER)
+	    {
+	      // stock laws, TreePM: ONE test per visit whether any species term can fall inside the softening (r2min < h^2, rare) instead of one
+	      // branch per term; a species without mass is a property of the cell, hence a uniform branch (small cells often hold one species
+	      // only).  (Not for the walks without PM: nvcc 12.9 compiles the spline-free term of that instantiation to fac = 0 -- SASS checked,
+	      // caught by tests/test_gpu_tree_walk.py --, so they keep the test per term.)
+	      if(STOCK && SR && r2min >= h * h)
+		{
+#pragma unroll
+		  for(int g = 0; g < D; g++)
+		    if(mass[g] != 0.0f)
+		      pair_term<SR, STOCK, false>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac);
+		}
+	      else
+		{
+#pragma unroll
+		  for(int g = 0; g < D; g++)
+		    if(mass[g] != 0.0f)
+		      {
+			const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
+			pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac, nn);
+		      }
+		}
+	    }
 	}
     }
   if(EXACT)
@@ -319,53 +339,52 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 						     unsigned int t2g_packed, WalkLane &L, const WalkShift &S, bool small_cell)
 {
   const unsigned int np = w.z & 15u;
+  if(!open)
+    return;			// (one branch for the whole group instead of one per particle)
   for(unsigned int j = 0; j < np; j++)
     {
       const float4 p = __ldg(A.wpart + w.y + j);
-      if(open)
+      int sg = 0;
+      float h = L.hself;
+      if(UNEQUAL || !STOCK)
 	{
-	  int sg = 0;
-	  float h = L.hself;
-	  if(UNEQUAL || !STOCK)
-	    {
-	      const int stype = (w.z >> (4 + 3 * j)) & 7;
-	      sg = (t2g_packed >> (4 * stype)) & 7;
-	      if(UNEQUAL)
-		h = fmaxf(h, A.fsoft[stype]);	// forcetree.c:1412-1415
-	    }
-	  float ddx, ddy, ddz;
-	  if(!WRAP)
-	    {
-	      ddx = p.x - L.px;
-	      ddy = p.y - L.py;
-	      ddz = p.z - L.pz;
-	    }
-	  else if(small_cell)
-	    {
-	      ddx = (p.x - S.sx) - S.tx;
-	      ddy = (p.y - S.sy) - S.ty;
-	      ddz = (p.z - S.sz) - S.tz;
-	    }
-	  else
-	    {
-	      ddx = nearest<PERIODIC>(p.x - L.px, A.boxsize, A.boxinv);
-	      ddy = nearest<PERIODIC>(p.y - L.py, A.boxsize, A.boxinv);
-	      ddz = nearest<PERIODIC>(p.z - L.pz, A.boxsize, A.boxinv);
-	    }
-	  const float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
-	  bool counted = true;	// a particle term counts whatever its mass (forcetree.c:1958-1987)
-	  if(SR)
-	    {
-	      const float tv = rr2 - A.rmax2;
-	      counted = tv < 0.0f;
-	      if(EXACT)
-		L.bmin = fminf(L.bmin, fabsf(tv) - A.rmax2_border);
-	    }
-	  pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz);
-	  L.ninter += counted;
-	  if(STATS)
-	    L.nterms += counted;
+	  const int stype = (w.z >> (4 + 3 * j)) & 7;
+	  sg = (t2g_packed >> (4 * stype)) & 7;
+	  if(UNEQUAL)
+	    h = fmaxf(h, A.fsoft[stype]);   // forcetree.c:1412-1415
 	}
+      float ddx, ddy, ddz;
+      if(!WRAP)
+	{
+	  ddx = p.x - L.px;
+	  ddy = p.y - L.py;
+	  ddz = p.z - L.pz;
+	}
+      else if(small_cell)
+	{
+	  ddx = (p.x - S.sx) - S.tx;
+	  ddy = (p.y - S.sy) - S.ty;
+	  ddz = (p.z - S.sz) - S.tz;
+	}
+      else
+	{
+	  ddx = nearest<PERIODIC>(p.x - L.px, A.boxsize, A.boxinv);
+	  ddy = nearest<PERIODIC>(p.y - L.py, A.boxsize, A.boxinv);
+	  ddz = nearest<PERIODIC>(p.z - L.pz, A.boxsize, A.boxinv);
+	}
+      const float rr2 = ddx * ddx + ddy * ddy + ddz * ddz;
+      bool counted = true;  // a particle term counts whatever its mass (forcetree.c:1958-1987)
+      if(SR)
+	{
+	  const float tv = rr2 - L.k_rmax2;
+	  counted = tv < 0.0f;
+	  if(EXACT)
+	    L.bmin = fminf(L.bmin, fabsf(tv) - A.rmax2_border);
+	}
+      pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac);
+      L.ninter += counted;
+      if(STATS)
+	L.nterms += counted;
     }
 }
 
@@ -436,7 +455,7 @@ __device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__rest
       if(SR)
 	{			// a species term of a cell was tested when it was staged; a particle term is tested here (forcetree.c:1958-1967)
 	  const bool isp = (R.isp >> e) & 1u;
-	  const float tv = r2 - A.rmax2;
+	  const float tv = r2 - L.k_rmax2;
 	  counted = !isp || tv < 0.0f;
 	  if(EXACT)
 	    L.bmin = fminf(L.bmin, isp ? fabsf(tv) - A.rmax2_border : 3.0e38f);
@@ -444,7 +463,7 @@ __device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__rest
 	  if(STATS)
 	    L.nterms += isp && counted;
 	}
-      pair_term<SR, true>(A, s_tab, s_tab_addr, L.tg, 0, 1, L.pmass, s.w, dx, dy, dz, r2, h, counted, L.fx, L.fy, L.fz);
+      pair_term<SR, true>(A, s_tab, s_tab_addr, L.tg, 0, 1, L.pmass, s.w, dx, dy, dz, r2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac);
     }
   L.bits = 0u;
 }
@@ -591,7 +610,7 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   if(SR)
     {
       for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
-	s_tab[i] = A.srtable[i];
+	s_tab[i] = STOCK ? A.utor2wpi * A.srtable[i] : A.srtable[i];	// stock laws: the factor of forcetree.c:1972 goes into the table once
       __syncthreads();
     }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -636,6 +655,11 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       L.fx = L.fy = L.fz = 0.0f;
       L.ninter = L.nterms = L.ndec = 0;
       L.bmin = 3.0e38f;
+      // (a value ptxas cannot trace back to the constant bank -- threadIdx.x >> 10 is zero, which it does not know -- or it re-reads the
+      // constant at every use: LDCU + MOV per term)
+      const float opaque_zero = (float) (threadIdx.x >> 10);
+      L.k_rmax2 = A.rmax2 + opaque_zero;
+      L.k_asmthfac = A.asmthfac + opaque_zero;
       L.bits = 0u;
       L.skip_until = valid ? 0u : 0xffffffffu;
       WalkRing R;
