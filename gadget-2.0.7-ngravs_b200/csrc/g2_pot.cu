@@ -101,7 +101,8 @@ __device__ __forceinline__ float pot_bam(int id, float eps, float pm, float m, f
 }
 
 // one species term; returns the amount to ADD to pot
-template <bool SR>
+// STOCKP: every pair is wired to newtonian_pot / plummer_pot (the stock wiring, ngravs.c:149-150): no dispatch on the pair's law per term
+template <bool SR, bool STOCKP = false>
 __device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restrict__ s_tab, int ij, float m, float r2, float h, bool table_term,
 					  float pm = 0.0f, float nn = 1.0f)
 {
@@ -113,6 +114,17 @@ __device__ __forceinline__ float pot_term(const PotArgs &A, const float *__restr
       tabindex = (int) (r * A.asmthfac);
       if(tabindex >= A.ntab)
 	return 0.0f;
+    }
+  if(STOCKP)
+    {
+      if(r >= h)
+	{
+	  float p = m * rinv;
+	  if(SR && table_term)
+	    p -= A.utorwpi * s_tab[(int) A.tabmap[ij] * A.ntab + tabindex];
+	  return -p;
+	}
+      return pot_plummer(m, h, r);
     }
   if(r >= h)
     {
@@ -151,7 +163,7 @@ __device__ __forceinline__ double nearest_d(double x, double box)
   return x;
 }
 
-template <int D, bool SR, bool UNEQUAL, bool LATT>
+template <int D, bool SR, bool UNEQUAL, bool LATT, bool STOCKP>
 __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_kernel(const PotArgs A)
 {
   constexpr bool PERIODIC = SR || LATT;	// the reference's TreePM potential walk is the periodic one; LATT: periodic box without PM
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_ke
 		      for(int g = 0; g < D; g++)
 			if(mass[g] != 0.0f)	// forcetree.c:3123
 			  {
-			    fpot += pot_term<SR>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0, pmass,
+			    fpot += pot_term<SR, STOCKP>(A, s_tab, tg * D + g, mass[g], r2[g], h, A.node_table_term != 0, pmass,
 						 A.cnt ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f);
 			    if(LATT)	// forcetree.c:2765-2767
 			      pot += (double) mass[g] * latt_pot_corr(A, dsp[g][0], dsp[g][1], dsp[g][2], tg * D + g);
@@ -324,7 +336,7 @@ __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_ke
 		      const float dx = POT_WRAP(p.x - px, shx);
 		      const float dy = POT_WRAP(p.y - py, shy);
 		      const float dz = POT_WRAP(p.z - pz, shz);
-		      fpot += pot_term<SR>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true, pmass, 1.0f);
+		      fpot += pot_term<SR, STOCKP>(A, s_tab, tg * D + sg, p.w, dx * dx + dy * dy + dz * dz, h, true, pmass, 1.0f);
 		      if(LATT)	// forcetree.c:2736-2738
 			pot += (double) p.w * latt_pot_corr(A, dx, dy, dz, tg * D + sg);
 		    }
@@ -345,9 +357,17 @@ __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_ke
 template <int D>
 static void launch_pot(g2gpu_ctx *c, const PotArgs &A, int grid, size_t smem, bool sr, bool unequal, bool latt)
 {
+  bool stockp = true;
+  for(int i = 0; i < D * D; i++)
+    if(A.potfxn[i] != G2GPU_POT_NEWTONIAN || A.potspline[i] != G2GPU_POTSPLINE_PLUMMER)
+      stockp = false;
 #define G2_P(SRv, UNEv, LATv) do { \
-    if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv, LATv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-    pot_kernel<D, SRv, UNEv, LATv><<<grid, WALK_THREADS, smem, c->stream>>>(A); } while(0)
+    if(stockp) { \
+      if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv, LATv, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+      pot_kernel<D, SRv, UNEv, LATv, true><<<grid, WALK_THREADS, smem, c->stream>>>(A); \
+    } else { \
+      if(smem > 48 * 1024) cudaFuncSetAttribute(pot_kernel<D, SRv, UNEv, LATv, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+      pot_kernel<D, SRv, UNEv, LATv, false><<<grid, WALK_THREADS, smem, c->stream>>>(A); } } while(0)
   if(sr) { if(unequal) G2_P(true, true, false); else G2_P(true, false, false); }
   else if(latt) { if(unequal) G2_P(false, true, true); else G2_P(false, false, true); }
   else   { if(unequal) G2_P(false, true, false); else G2_P(false, false, false); }

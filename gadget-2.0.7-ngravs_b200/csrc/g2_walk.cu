@@ -130,13 +130,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.errtol = (float) wp->errtol_force_acc;
   A.ex = (const WalkExactParams *) c->d_exact;
   A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
-  // guard bands of the FP32 decisions (g2_walk_kernel.cuh), each a few times the FP32 rounding its comparison can accumulate: a coordinate
-  // difference against a length 2e-7 -> 4e-7; an r^2 (three products of rounded differences) 3.6e-7 -> 6e-7; the opening criteria (r^4 a
-  // against M len^2) 1.1e-6 -> 1.5e-6.  Where NEAREST is applied per point the raw difference is rounded at box scale: 1e-4.
-  A.tol_pos = 4.0e-7f;
-  A.tol_r2 = 6.0e-7f;
-  A.tol_crit = 1.5e-6f;
-  A.tol_wide = 1.0e-4f;
+  // (the guard bands of the FP32 decisions are compile-time constants of g2_walk_kernel.cuh: G2_TOL_*)
   A.exact = c->walk_exact;
   A.flush_mask = (unsigned int) c->walk_flush_mask;
   if(sr)

@@ -60,11 +60,7 @@ struct WalkArgs
   float ntabm1f;		// (float) (NTAB - 1)
   float cull_margin;		// absolute safety margin of the geometric cull shortcut (float rounding of positions); +inf disables the shortcut
   float shift_len_max;		// TreePM: cells smaller than this take the periodic image of their centre for all their points
-  // guard bands: a comparison whose two sides are closer than this is re-taken in FP64, the arithmetic the reference decides in
-  float tol_pos;		// relative, for comparisons of a coordinate difference with a length (box cull, 0.6 len test)
-  float tol_r2;			// relative, for comparisons of an r^2 (with rcut^2, h^2)
-  float tol_crit;		// relative, for the opening criteria (M len^2 vs r^4 a; len^2 vs r^2 theta^2)
-  float tol_wide;		// all of them where NEAREST is applied per point (raw differences rounded at box scale)
+  // guard bands of the FP32 decisions: G2_TOL_* in g2_walk_kernel.cuh (relative), and
   float rmax2_border;		// absolute, around rmax2
   double G, pos_fac_pre_g, pos_fac_post_g;
   const WalkExactParams *__restrict__ ex;
@@ -123,12 +119,12 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 // table (tabindex < NTAB, forcetree.c:1962-1967), decided by the caller; `m != 0` is checked by the caller for node terms
 // (forcetree.c:1553, 1992).  Stock wiring (Newton + Plummer spline for every pair, ngravs.c:109-116): branch-free except for the
 // rare r < h case.
-// SPL = false: the caller knows that r >= h (no softening spline needed).  asmthfac: A.asmthfac, which the walk kernel keeps in a register
-// (re-reading it from the constant bank costs an instruction per term).
+// SPL = false: the caller knows that r >= h (no softening spline needed).  asmthfac, ntabm1: A.asmthfac and A.ntabm1f, which the walk kernel keeps
+// in registers (re-reading them from the constant bank costs an instruction per term).
 template <bool SR, bool STOCK, bool SPL = true>
 __device__ __forceinline__ void pair_term(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, int tg, int sg, int D,
 					  float pmass, float m, float dx, float dy, float dz, float r2, float h, bool counted, float &fx, float &fy, float &fz,
-					  float asmthfac, float nn = 1.0f)	// nn: N of forcetree.c:1563-1577 (only the non-stock laws read it)
+					  float asmthfac, float ntabm1, float nn = 1.0f)	// nn: N of forcetree.c:1563-1577 (only the non-stock laws read it)
 {
   const float rinv = fast_rsqrt(fmaxf(r2, 1.0e-37f));
   const float r = r2 * rinv;
@@ -137,7 +133,7 @@ __device__ __forceinline__ void pair_term(const WalkArgs &A, const float *__rest
       float fac;
       if(SR)
 	{
-	  const int tabindex = (int) fminf(asmthfac * r, A.ntabm1f);	// forcetree.c:1962 (clamped: terms beyond the table are not counted)
+	  const int tabindex = (int) fminf(asmthfac * r, ntabm1);	// forcetree.c:1962 (clamped: terms beyond the table are not counted)
 	  const float t = lds_f32(s_tab_addr + 4u * (unsigned int) tabindex);
 	  // (m/r^2 - m*utor2wpi*tab) / r   (forcetree.c:1972-1974); the stock kernel's copy of the table in shared memory holds utor2wpi * tab
 	  fac = m * rinv * (rinv * rinv - t);

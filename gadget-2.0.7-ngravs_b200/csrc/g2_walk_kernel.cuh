@@ -19,6 +19,13 @@
 #pragma once
 #include "g2_walk_common.cuh"
 
+// guard bands of the FP32 decisions, each a few times the FP32 rounding its comparison can accumulate: a coordinate difference against a length
+// 2e-7 -> 4e-7; an r^2 (three products of rounded differences) 3.6e-7 -> 6e-7; the opening criteria (r^4 a against M len^2) 1.1e-6 -> 1.5e-6.
+// Where NEAREST is applied per point the raw difference is rounded at box scale: 1e-4.  Compile-time constants: immediates in the FFMAs.
+#define G2_TOL_POS 4.0e-7f
+#define G2_TOL_R2 6.0e-7f
+#define G2_TOL_CRIT 1.5e-6f
+#define G2_TOL_WIDE 1.0e-4f
 #define G2_DEC_CULL 0
 #define G2_DEC_ACCEPT 1
 #define G2_DEC_OPEN 2
@@ -130,7 +137,9 @@ struct WalkLane
   float bmin;			// EXACT: smallest distance of any comparison of this walk from its guard band (negative: inside)
   unsigned int skip_until;
   unsigned int bits;		// DEFER: ring entries (staged sources) this lane still has to evaluate
-  float k_rmax2, k_asmthfac;	// A.rmax2, A.asmthfac pinned in registers (uniform values: re-reading them from the constant bank costs instructions per term)
+  // kernel arguments the visit code reads at every term, copied once per chunk through an addition ptxas cannot fold away: it then keeps them in
+  // uniform registers instead of re-reading the constant bank at every use (LDCU + MOV per term)
+  float k_rmax2, k_rmax2b, k_asmthfac, k_ntabm1;	// (ptxas keeps these three in uniform registers; for the others it re-reads the constant AND adds the zero)
 };
 
 // DEFER (stock pair laws): the terms a lane accepts are not evaluated where they are found -- a handful of lanes at a time -- but staged.
@@ -168,7 +177,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
   // point (cells too large for the per-cell image shift, and periodic walks without PM): there the raw coordinate difference is
   // rounded at box scale before the wrap.
   const bool wide = WRAP && !(SR && q0.x < A.shift_len_max);
-  const float tol_pos = wide ? A.tol_wide : A.tol_pos, tol_r2 = wide ? A.tol_wide : A.tol_r2, tol_crit = wide ? A.tol_wide : A.tol_crit;
+  const float tol_pos = wide ? G2_TOL_WIDE : G2_TOL_POS, tol_r2 = wide ? G2_TOL_WIDE : G2_TOL_R2, tol_crit = wide ? G2_TOL_WIDE : G2_TOL_CRIT;
   float dx[D], dy[D], dz[D], r2[D], mass[D];
   float r2min = 3.0e38f, r2max = -1.0f, summass = 0.0f;
   const float len = q0.x;
@@ -290,7 +299,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 		{
 		  const float tv = r2[g] - L.k_rmax2;
 		  if(EXACT)
-		    bm = fminf(bm, fabsf(tv) - A.rmax2_border);
+		    bm = fminf(bm, fabsf(tv) - L.k_rmax2b);
 		  counted = counted && tv < 0.0f;
 		}
 	      cnt[g] = counted;
@@ -313,7 +322,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 #pragma unroll
 		  for(int g = 0; g < D; g++)
 		    if(mass[g] != 0.0f)
-		      pair_term<SR, STOCK, false>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac);
+		      pair_term<SR, STOCK, false>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac, L.k_ntabm1);
 		}
 	      else
 		{
@@ -322,7 +331,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 		    if(mass[g] != 0.0f)
 		      {
 			const float nn = (!STOCK && A.cnt) ? (float) __ldg(A.cnt + (size_t) cur * D + g) : 1.0f;
-			pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac, nn);
+			pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac, L.k_ntabm1, nn);
 		      }
 		}
 	    }
@@ -379,9 +388,9 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 	  const float tv = rr2 - L.k_rmax2;
 	  counted = tv < 0.0f;
 	  if(EXACT)
-	    L.bmin = fminf(L.bmin, fabsf(tv) - A.rmax2_border);
+	    L.bmin = fminf(L.bmin, fabsf(tv) - L.k_rmax2b);
 	}
-      pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac);
+      pair_term<SR, STOCK>(A, s_tab, s_tab_addr, L.tg, sg, D, L.pmass, p.w, ddx, ddy, ddz, rr2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac, L.k_ntabm1);
       L.ninter += counted;
       if(STATS)
 	L.nterms += counted;
@@ -458,12 +467,12 @@ __device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__rest
 	  const float tv = r2 - L.k_rmax2;
 	  counted = !isp || tv < 0.0f;
 	  if(EXACT)
-	    L.bmin = fminf(L.bmin, isp ? fabsf(tv) - A.rmax2_border : 3.0e38f);
+	    L.bmin = fminf(L.bmin, isp ? fabsf(tv) - L.k_rmax2b : 3.0e38f);
 	  L.ninter += isp && counted;	// forcetree.c:2031
 	  if(STATS)
 	    L.nterms += isp && counted;
 	}
-      pair_term<SR, true>(A, s_tab, s_tab_addr, L.tg, 0, 1, L.pmass, s.w, dx, dy, dz, r2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac);
+      pair_term<SR, true>(A, s_tab, s_tab_addr, L.tg, 0, 1, L.pmass, s.w, dx, dy, dz, r2, h, counted, L.fx, L.fy, L.fz, L.k_asmthfac, L.k_ntabm1);
     }
   L.bits = 0u;
 }
@@ -659,7 +668,9 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
       // constant at every use: LDCU + MOV per term)
       const float opaque_zero = (float) (threadIdx.x >> 10);
       L.k_rmax2 = A.rmax2 + opaque_zero;
+      L.k_rmax2b = A.rmax2_border + opaque_zero;
       L.k_asmthfac = A.asmthfac + opaque_zero;
+      L.k_ntabm1 = A.ntabm1f + opaque_zero;
       L.bits = 0u;
       L.skip_until = valid ? 0u : 0xffffffffu;
       WalkRing R;
