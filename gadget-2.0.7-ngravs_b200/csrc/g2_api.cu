@@ -66,6 +66,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->acc_double = 1;
   c->walk_exact = getenv("G2GPU_WALK_EXACT") ? atoi(getenv("G2GPU_WALK_EXACT")) != 0 : 1;
   c->walk_defer = getenv("G2GPU_WALK_DEFER") ? atoi(getenv("G2GPU_WALK_DEFER")) != 0 : 0;	// only in a -DG2_WALK_DEFER build
+  c->walk_sm_local = getenv("G2GPU_WALK_SM_LOCAL") ? atoi(getenv("G2GPU_WALK_SM_LOCAL")) != 0 : 1;
   // MEASURED (B200, 256^3, profiles/r2_exact_cost.txt): mask 0 / 1 / 3 / 7 -> walk 212.7 / 209.0 / 207.5 / 206.7 ms, median error against the reference
   // 1.38e-7 / - / 1.55e-7 / 1.79e-7, p99.9 and GravCost unchanged
   c->walk_flush_mask = getenv("G2GPU_WALK_FLUSH_MASK") ? atoi(getenv("G2GPU_WALK_FLUSH_MASK")) : 7;
@@ -115,7 +116,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   rc |= dalloc(&c->d_depth, (size_t) 64);
   rc |= dalloc(&c->w_targets, np); rc |= dalloc(&c->w_flags, np + 2);
   rc |= dalloc(&c->acc, 3 * np); rc |= dalloc(&c->cost, np); rc |= dalloc(&c->oldacc_out, np);
-  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256);
+  rc |= dalloc(&c->d_counters, (size_t) 8); rc |= dalloc(&c->d_slice, (size_t) 4); rc |= dalloc((char **) &c->d_exact, (size_t) 256); rc |= dalloc(&c->d_smcount, (size_t) 1024);
   if(rc)
     {
       g2gpu_destroy(c);
@@ -150,7 +151,7 @@ extern "C" void g2gpu_destroy(g2gpu_ctx *c)
     c->d_species_start, c->tm, c->ttl, c->tbase, c->tcnt, c->c_a, c->c_b, c->c_d, c->c_suns, c->c_father, c->p_parent, c->c_ready, c->c_nchild, c->c_npart,
     c->c_min1, c->c_min2, c->c_poff, c->c_refid, c->t_suns, c->t_first, c->t_last, c->t_min1, c->t_min2, c->t_ready, c->t_npart, c->t_nchild, c->t_ubase,
     c->wcells, c->wpart, c->hist2, c->hist2_scan, c->dmin, c->d_err, c->d_depth, c->w_targets, c->w_flags, c->acc, c->cost, c->oldacc_out, c->d_counters,
-    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->d_potcorr, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres };
+    c->d_srtable, c->d_srtable_f, c->d_pottable_f, c->pot, c->d_lattice, c->d_potcorr, c->latt, c->lattcost, c->wcnt, c->wsrc, c->phorder, c->d_slice, c->d_exact, c->cres, c->d_smcount };
   for(size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++)
     if(ptrs[i])
       cudaFree(ptrs[i]);

@@ -132,6 +132,8 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
   // (the guard bands of the FP32 decisions are compile-time constants of g2_walk_kernel.cuh: G2_TOL_*)
   A.exact = c->walk_exact;
+  A.sm_counter = c->d_smcount; A.nsm = c->nsm; A.sm_local = c->walk_sm_local;
+  G2_CUDA(cudaMemsetAsync(c->d_smcount, 0, sizeof(unsigned int) * 1024, st));
   A.flush_mask = (unsigned int) c->walk_flush_mask;
   if(sr)
     {

@@ -49,6 +49,8 @@ struct WalkArgs
   float *__restrict__ cres;			// ... or, when not null, compact: 5 floats (acc[3], cost, oldacc) per target of the slice, target order
   unsigned long long *__restrict__ counters;
   unsigned int *__restrict__ work_counter;
+  unsigned int *__restrict__ sm_counter;	// one chunk counter per SM (option walk_sm_local)
+  int nsm, sm_local;
   int numnodes;
   int ntab;
   int ntables;			// unique short-range tables held in shared memory

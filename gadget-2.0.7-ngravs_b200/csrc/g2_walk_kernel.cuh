@@ -635,11 +635,35 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   const unsigned int end = (unsigned int) A.numnodes;
   unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0, tot_dec = 0;
 
+  // work distribution: one chunk of 32 consecutive targets per warp.  sm_local: the chunks are dealt out in one contiguous block per SM, so that
+  // the 32 warps resident on an SM walk neighbouring targets at the same time and find each other's cell records in L1; an SM that has
+  // finished its block takes chunks from the blocks of the following SMs (each block has its own counter).
+  unsigned int mysm = 0, steal = 0;
+  asm("mov.u32 %0, %%smid;" : "=r"(mysm));
+  const unsigned int nsm = (unsigned int) A.nsm, blk = ((unsigned int) nchunks + nsm - 1u) / nsm;
+  mysm %= nsm;
   while(true)
     {
-      // dynamic work distribution: one chunk of 32 consecutive targets per warp
       if(lane == 0)
-	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+	{
+	  unsigned int ch = 0xffffffffu;
+	  if(A.sm_local)
+	    {
+	      for(; steal < nsm; steal++)
+		{
+		  const unsigned int sm = mysm + steal < nsm ? mysm + steal : mysm + steal - nsm;
+		  const unsigned int t = atomicAdd(A.sm_counter + sm, 1u);
+		  if(t < blk && sm * blk + t < (unsigned int) nchunks)
+		    {
+		      ch = sm * blk + t;
+		      break;
+		    }
+		}
+	    }
+	  else
+	    ch = atomicAdd(A.work_counter, 1u);
+	  s_chunk[warp] = ch;
+	}
       __syncwarp();
       const unsigned int chunk = s_chunk[warp];
       __syncwarp();
