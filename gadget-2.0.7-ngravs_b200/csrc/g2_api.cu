@@ -66,6 +66,7 @@ extern "C" int g2gpu_create(g2gpu_ctx **out, const g2gpu_config *cfg)
   c->acc_double = 1;
   c->walk_exact = getenv("G2GPU_WALK_EXACT") ? atoi(getenv("G2GPU_WALK_EXACT")) != 0 : 1;
   c->walk_defer = getenv("G2GPU_WALK_DEFER") ? atoi(getenv("G2GPU_WALK_DEFER")) != 0 : 0;	// only in a -DG2_WALK_DEFER build
+  c->walk_carveout = getenv("G2GPU_WALK_CARVEOUT") ? atoi(getenv("G2GPU_WALK_CARVEOUT")) : -1;
   c->walk_sm_local = getenv("G2GPU_WALK_SM_LOCAL") ? atoi(getenv("G2GPU_WALK_SM_LOCAL")) != 0 : 1;
   // MEASURED (B200, 256^3, profiles/r2_exact_cost.txt): mask 0 / 1 / 3 / 7 -> walk 212.7 / 209.0 / 207.5 / 206.7 ms, median error against the reference
   // 1.38e-7 / - / 1.55e-7 / 1.79e-7, p99.9 and GravCost unchanged

@@ -226,6 +226,7 @@ struct g2gpu_ctx
   int *d_slice, *h_slice;	// [G2_SLICE_*] on the device / pinned
   void *d_exact;		// WalkExactParams of the current walk
   unsigned int *d_smcount;	// 1024 chunk counters of the walk's per-SM work distribution
+  int walk_carveout;		// option / G2GPU_WALK_CARVEOUT: cudaFuncAttributePreferredSharedMemoryCarveout of walk_kernel in percent, -1 = driver default
   int walk_sm_local;		// option / G2GPU_WALK_SM_LOCAL (default 1): chunks dealt out in one contiguous block per SM
   int slice_pending;
   float *acc;			// 3n, current particle order

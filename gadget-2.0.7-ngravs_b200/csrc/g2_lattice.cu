@@ -28,6 +28,8 @@ struct LatticeArgs
   float *__restrict__ latt;		// 3n, current particle order
   float *__restrict__ lattcost;	// n
   unsigned int *__restrict__ work_counter;
+  unsigned int *__restrict__ sm_counter;	// ChunkDealer
+  int nsm;
   int numnodes, en;
   float theta2, errtol, boxsize, boxinv, fac_intp;
   int t2g[6];
@@ -66,10 +68,11 @@ __global__ void __launch_bounds__(WALK_THREADS, LATTICE_MINBLOCKS) lattice_kerne
   const int nchunks = (hi - lo + 31) >> 5;
   const unsigned int end = (unsigned int) A.numnodes;
 
+  unsigned int steal = 0u;	// chunk_dealer_next
   while(true)
     {
       if(lane == 0)
-	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+	s_chunk[warp] = chunk_dealer_next(A.sm_counter, A.work_counter, A.nsm, (unsigned int) nchunks, steal);
       __syncwarp();
       const unsigned int chunk = s_chunk[warp];
       __syncwarp();
@@ -185,6 +188,7 @@ int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.cells = c->wcells; A.wpart = c->wpart; A.targets = c->w_targets; A.slice = c->d_slice; A.prec = c->prec;
   A.tables = (const float4 *) c->d_lattice; A.latt = c->latt; A.lattcost = c->lattcost;
   A.work_counter = (unsigned int *) (c->d_counters + 5);
+  A.sm_counter = c->walk_sm_local ? c->d_smcount : nullptr; A.nsm = c->nsm;
   A.numnodes = c->numnodes; A.en = c->lattice_en;
   A.theta2 = (float) (wp->theta * wp->theta);
   A.errtol = (float) wp->errtol_force_acc;
@@ -197,6 +201,7 @@ int g2_stage_lattice(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));
+  G2_CUDA(cudaMemsetAsync(c->d_smcount, 0, sizeof(unsigned int) * G2_CHUNK_COUNTERS, st));
   G2_CUDA(cudaEventRecord(c->ev[18], st));
   if(grid > 0)
     {

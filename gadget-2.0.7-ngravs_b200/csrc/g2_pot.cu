@@ -37,6 +37,8 @@ struct PotArgs
   const float *__restrict__ pottable;	// unique tables, NTAB floats each
   float *__restrict__ pot;
   unsigned int *__restrict__ work_counter;
+  unsigned int *__restrict__ sm_counter;	// ChunkDealer
+  int nsm;
   int lo, hi, numnodes, ntab, ntables, node_table_term;
   float theta2, errtol, boxsize, boxinv, rcut, asmthfac, utorwpi;
   float shift_len_max;		// -DG2_POT_CELLSHIFT: cells smaller than this take the periodic image of their centre for all their points
@@ -180,10 +182,11 @@ __global__ void __launch_bounds__(WALK_THREADS, LATT ? 4 : POT_BLOCKS(D)) pot_ke
   const int nchunks = (A.hi - A.lo + 31) >> 5;
   const unsigned int end = (unsigned int) A.numnodes;
 
+  unsigned int steal = 0u;	// chunk_dealer_next
   while(true)
     {
       if(lane == 0)
-	s_chunk[warp] = atomicAdd(A.work_counter, 1u);
+	s_chunk[warp] = chunk_dealer_next(A.sm_counter, A.work_counter, A.nsm, (unsigned int) nchunks, steal);
       __syncwarp();
       const unsigned int chunk = s_chunk[warp];
       __syncwarp();
@@ -400,6 +403,7 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   const int nr = c->cfg.nranks > 0 ? c->cfg.nranks : 1, rk = c->cfg.rank;
   A.cells = c->wcells; A.wpart = c->wpart; A.order = c->phorder; A.prec = c->prec; A.pottable = c->d_pottable_f; A.pot = c->pot;
   A.work_counter = (unsigned int *) (c->d_counters + 5);
+  A.sm_counter = c->walk_sm_local ? c->d_smcount : nullptr; A.nsm = c->nsm;
   // slice boundaries at multiples of 32: the 32-target groups, and with them the result bits, do not depend on the number of ranks
   A.lo = (int) (((long long) n * rk / nr + 16) / 32 * 32); A.hi = rk == nr - 1 ? n : (int) (((long long) n * (rk + 1) / nr + 16) / 32 * 32);
   if(A.lo > n) A.lo = n;
@@ -443,6 +447,7 @@ int g2_stage_potential(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   if(grid > need)
     grid = need;
   G2_CUDA(cudaMemsetAsync(A.work_counter, 0, sizeof(unsigned int), st));
+  G2_CUDA(cudaMemsetAsync(c->d_smcount, 0, sizeof(unsigned int) * G2_CHUNK_COUNTERS, st));
   G2_CUDA(cudaEventRecord(c->ev[16], st));
   if(grid > 0)
     {

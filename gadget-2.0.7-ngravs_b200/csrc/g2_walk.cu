@@ -132,8 +132,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.boxsize = (float) wp->boxsize; A.boxinv = wp->boxsize > 0 ? (float) (1.0 / wp->boxsize) : 0.0f;
   // (the guard bands of the FP32 decisions are compile-time constants of g2_walk_kernel.cuh: G2_TOL_*)
   A.exact = c->walk_exact;
-  A.sm_counter = c->d_smcount; A.nsm = c->nsm; A.sm_local = c->walk_sm_local;
-  G2_CUDA(cudaMemsetAsync(c->d_smcount, 0, sizeof(unsigned int) * 1024, st));
+  A.sm_counter = c->walk_sm_local ? c->d_smcount : nullptr; A.nsm = c->nsm;	// (cleared right before the launch: the lattice walk uses the same counters)
   A.flush_mask = (unsigned int) c->walk_flush_mask;
   if(sr)
     {
@@ -168,8 +167,8 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   const size_t smem = sr ? sizeof(float) * (size_t) A.ntables * A.ntab : 0;
   // every CTA resident: the chunk counter balances the load.  The target count stays on the device, so the grid is sized for
   // the upper bound (all particles active); surplus CTAs find the counter exhausted and leave.
-  int grid = c->nsm * (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS);
-  const int need = g2_cdiv(g2_cdiv(c->npart, 32), WALK_WARPS);
+  int grid = c->nsm * WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS);
+  const int need = g2_cdiv(g2_cdiv(c->npart, 32), WALK_KWARPS);
   if(grid > need)
     grid = need;
   // periodic box without PM: the lattice-sum correction walk first (its result enters the epilogue of the walk kernel)
@@ -179,6 +178,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
       G2_TRY(g2_stage_lattice(c, wp));
       A.latt = c->latt; A.lattcost = c->lattcost;
     }
+  G2_CUDA(cudaMemsetAsync(c->d_smcount, 0, sizeof(unsigned int) * G2_CHUNK_COUNTERS, st));
   G2_CUDA(cudaEventRecord(c->ev[7], st));
   {
     const bool uneq = c->cfg.unequal_softenings != 0;

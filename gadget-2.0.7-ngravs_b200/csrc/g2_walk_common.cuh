@@ -16,6 +16,38 @@
 #ifndef WALK_MINBLOCKS_WIDE
 #define WALK_MINBLOCKS_WIDE 8
 #endif
+// walk_kernel's own CTA size (WALK_THREADS is shared with the potential and lattice walks).  Its warps never meet at a barrier after the table load,
+// so the CTA size only sets how many copies of the short-range table and how much shared memory an SM holds: the rest of the 256 KB array is
+// L1 for cell records.  The resident warps per SM stay the same (WALK_MINBLOCKS x WALK_THREADS threads).
+#ifndef WALK_KT
+#define WALK_KT 1024	// MEASURED (B200, 256^3, profiles/experiments/r2_run31.sh): 128 / 256 / 512 / 1024 threads -> walk 177.8 / 177.7 / 175.6 / 172.9 ms
+#endif
+#define WALK_KWARPS (WALK_KT / 32)
+#define WALK_KBLOCKS(minblocks) ((minblocks) * WALK_THREADS / WALK_KT)
+
+// Work distribution of the walks (walk_kernel, pot_kernel, lattice_kernel): one chunk of 32 consecutive targets per warp.  The chunks are dealt out in
+// one contiguous block per SM, so that the warps resident on an SM walk neighbouring targets at the same time and find each other's cell records in
+// L1 (MEASURED, B200, 256^3: L1 hit rate 43 -> 64 %, walk 185.6 -> 177.7 ms); an SM that has finished its block takes chunks from the blocks of the
+// following SMs (each block has its own counter).  sm_counter == nullptr: one global counter (option walk_sm_local = 0).
+#define G2_CHUNK_COUNTERS 1024	// >= the largest %nsmid
+// next chunk of the calling warp (lane 0 calls), >= nchunks when all are taken.  `steal` (how many blocks this warp has seen exhausted) is the only
+// state a warp keeps between calls: everything else is re-derived per chunk, once per ~60 000 warp instructions of walking.
+__device__ __forceinline__ unsigned int chunk_dealer_next(unsigned int *sm_counter, unsigned int *global_counter, int nsm_i, unsigned int nchunks, unsigned int &steal)
+{
+  if(!sm_counter)
+    return atomicAdd(global_counter, 1u);
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  const unsigned int nsm = (unsigned int) nsm_i, mysm = smid % nsm, blk = (nchunks + nsm - 1u) / nsm;
+  for(; steal < nsm; steal++)
+    {
+      const unsigned int sm = mysm + steal < nsm ? mysm + steal : mysm + steal - nsm;
+      const unsigned int t = atomicAdd(sm_counter + sm, 1u);
+      if(t < blk && sm * blk + t < nchunks)
+	return sm * blk + t;
+    }
+  return 0xffffffffu;
+}
 
 // slice[] (device memory, written by slice_kernel before the walk): the walk never needs a host round trip for the target count
 #define G2_SLICE_NTARGETS 0
@@ -49,8 +81,8 @@ struct WalkArgs
   float *__restrict__ cres;			// ... or, when not null, compact: 5 floats (acc[3], cost, oldacc) per target of the slice, target order
   unsigned long long *__restrict__ counters;
   unsigned int *__restrict__ work_counter;
-  unsigned int *__restrict__ sm_counter;	// one chunk counter per SM (option walk_sm_local)
-  int nsm, sm_local;
+  unsigned int *__restrict__ sm_counter;	// one chunk counter per SM (ChunkDealer), nullptr: the global work_counter only
+  int nsm;
   int numnodes;
   int ntab;
   int ntables;			// unique short-range tables held in shared memory

@@ -402,7 +402,7 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 // no image-shift state at all.  ACC accumulators: FP64 in shared memory (acc_sh, one slot per thread) or FP32 in registers (acc_rg).
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, typename ACC>
 __device__ __forceinline__ unsigned int walk_visit(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, unsigned int cur, const float4 *__restrict__ rec,
-						   const float4 q0, const uint4 w, unsigned int t2g_packed, WalkLane &L, ACC (*acc_sh)[WALK_THREADS], ACC &ax, ACC &ay, ACC &az)
+						   const float4 q0, const uint4 w, unsigned int t2g_packed, WalkLane &L, ACC (*acc_sh)[WALK_KT], ACC &ax, ACC &ay, ACC &az)
 {
   bool open = false, small_cell = false;
   WalkShift S;
@@ -479,7 +479,7 @@ __device__ __forceinline__ void ring_eval(const WalkArgs &A, const float *__rest
 
 template <bool SR, bool UNEQUAL, bool STATS, bool EXACT, typename ACC>
 __device__ __forceinline__ void ring_flush(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, WalkLane &L, WalkRing &R,
-					   ACC (*acc_sh)[WALK_THREADS], ACC &ax, ACC &ay, ACC &az)
+					   ACC (*acc_sh)[WALK_KT], ACC &ax, ACC &ay, ACC &az)
 {
   __syncwarp();			// the entries were written by other lanes
   if(R.wrap)
@@ -607,18 +607,18 @@ __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned in
 }
 
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER>
-__global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(WALK_KT, WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
 {
   extern __shared__ float s_tab[];
-  __shared__ unsigned int s_chunk[WALK_WARPS];
-  __shared__ float4 s_ring[DEFER ? WALK_WARPS * WALK_RING : 1];
-  __shared__ float s_ringh[(DEFER && UNEQUAL) ? WALK_WARPS * WALK_RING : 1];
+  __shared__ unsigned int s_chunk[WALK_KWARPS];
+  __shared__ float4 s_ring[DEFER ? WALK_KWARPS * WALK_RING : 1];
+  __shared__ float s_ringh[(DEFER && UNEQUAL) ? WALK_KWARPS * WALK_RING : 1];
   // the FP64 accumulators of a lane live in shared memory (touched only when the warp descends, about every third visit): six
   // registers less keeps the kernel at 64 registers without spills
-  __shared__ ACC s_acc[sizeof(ACC) == 8 ? 3 : 1][WALK_THREADS];
+  __shared__ ACC s_acc[sizeof(ACC) == 8 ? 3 : 1][WALK_KT];
   if(SR)
     {
-      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_THREADS)
+      for(int i = threadIdx.x; i < A.ntables * A.ntab; i += WALK_KT)
 	s_tab[i] = STOCK ? A.utor2wpi * A.srtable[i] : A.srtable[i];	// stock laws: the factor of forcetree.c:1972 goes into the table once
       __syncthreads();
     }
@@ -635,35 +635,11 @@ __global__ void __launch_bounds__(WALK_THREADS, (D >= WALK_WIDE_D ? WALK_MINBLOC
   const unsigned int end = (unsigned int) A.numnodes;
   unsigned long long tot_inter = 0, tot_visits = 0, tot_terms = 0, tot_dec = 0;
 
-  // work distribution: one chunk of 32 consecutive targets per warp.  sm_local: the chunks are dealt out in one contiguous block per SM, so that
-  // the 32 warps resident on an SM walk neighbouring targets at the same time and find each other's cell records in L1; an SM that has
-  // finished its block takes chunks from the blocks of the following SMs (each block has its own counter).
-  unsigned int mysm = 0, steal = 0;
-  asm("mov.u32 %0, %%smid;" : "=r"(mysm));
-  const unsigned int nsm = (unsigned int) A.nsm, blk = ((unsigned int) nchunks + nsm - 1u) / nsm;
-  mysm %= nsm;
+  unsigned int steal = 0u;	// chunk_dealer_next
   while(true)
     {
       if(lane == 0)
-	{
-	  unsigned int ch = 0xffffffffu;
-	  if(A.sm_local)
-	    {
-	      for(; steal < nsm; steal++)
-		{
-		  const unsigned int sm = mysm + steal < nsm ? mysm + steal : mysm + steal - nsm;
-		  const unsigned int t = atomicAdd(A.sm_counter + sm, 1u);
-		  if(t < blk && sm * blk + t < (unsigned int) nchunks)
-		    {
-		      ch = sm * blk + t;
-		      break;
-		    }
-		}
-	    }
-	  else
-	    ch = atomicAdd(A.work_counter, 1u);
-	  s_chunk[warp] = ch;
-	}
+	s_chunk[warp] = chunk_dealer_next(A.sm_counter, A.work_counter, A.nsm, (unsigned int) nchunks, steal);
       __syncwarp();
       const unsigned int chunk = s_chunk[warp];
       __syncwarp();
@@ -975,7 +951,9 @@ static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
 {
   if(smem > 48 * 1024)
     G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER><<<grid, WALK_THREADS, smem, c->stream>>>(A);
+  if(c->walk_carveout >= 0)	// share of the 256 KB array kept as shared memory, in percent (the rest is L1); -1: the driver's choice
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, c->walk_carveout));
+  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER><<<grid, WALK_KT, smem, c->stream>>>(A);
   if(EXACT)
     {
       if(smem > 48 * 1024)
