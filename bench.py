@@ -420,7 +420,9 @@ def main():
         h2d, d2h, gathered = grp.io_bytes()
         e2e = {"value": n / (e_s / K), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e_s / K,
                "allgather_bytes_per_device": gathered, "clock": "host wall clock around g2gpu_group_gravity_tree (results in host memory on return)",
-               "checksum": float(np.abs(acc_e).sum())}
+               "checksum": float(np.abs(acc_e).sum()),
+               "results": ("stored by the walk kernel straight into the pinned result arrays (zero-copy; d2h bytes = those stores + the particle order)"
+                           if grp.zero_copy() else "staged on the devices, downloaded and scattered by host threads")}
 
     # ---- the same through the entry point the reference calls (gravity_tree() of the host shim on the reference's P[])
     e2e_shim = None

@@ -80,6 +80,11 @@ struct G2LawTable
   float par[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS][4];
 };
 
+// slice[] (device memory, written by slice_kernel before the walk): the walk never needs a host round trip for the target count
+#define G2_SLICE_NTARGETS 0
+#define G2_SLICE_LO 1
+#define G2_SLICE_HI 2
+
 struct g2gpu_ctx
 {
   g2gpu_config cfg;
@@ -127,6 +132,7 @@ struct g2gpu_ctx
   int walk_flush_mask;		// G2GPU_WALK_FLUSH_MASK (0, 1, 3, 7 = default): the FP32 partial sums of the walk go into the accumulators at descents with (cell index & mask) == 0
   int compact;			// option "compact": the walk writes its slice's results in target order (cres) instead of by particle index
   float *cres;			// 5 floats per target of the slice (acc[3], cost, oldacc), allocated with the option
+  float *zc_acc, *zc_cost, *zc_oldacc;	// set by the multi-GPU group for one walk: device-visible pointers to the caller's pinned result arrays (WalkArgs)
   int slice_explicit;		// slice_frac[] instead of rank/nranks (cost-weighted slices of the group path)
   double slice_frac[2];
   int tree_dynamic;		// the current tree came from g2gpu_update_tree (host-drifted nodes)

@@ -52,6 +52,10 @@ struct g2gpu_group
   unsigned int *h_idx[G2_GROUP_MAX];
   size_t h_cap[G2_GROUP_MAX];
   int lo[G2_GROUP_MAX], hi[G2_GROUP_MAX], ntargets;
+  // zero-copy results: GravCost profile of a device's slice, summed on the device (cost_profile_kernel)
+  double *d_prof[G2_GROUP_MAX], *h_prof[G2_GROUP_MAX];
+  int zero_copy;		// G2GPU_ZERO_COPY (default 1): pinned result arrays of g2gpu_group_gravity_tree are written by the walk kernel itself
+  int last_zero_copy;		// the last g2gpu_group_gravity_tree took that path
   char errs[G2_GROUP_MAX][512];
   long long h2d_bytes, d2h_bytes, gather_bytes;
 };
@@ -127,12 +131,15 @@ extern "C" int g2gpu_group_create(g2gpu_group **out, const g2gpu_config *cfg, in
   g->profile_ntargets = 0;
   g->ntargets = 0;
   g->h2d_bytes = g->d2h_bytes = g->gather_bytes = 0;
+  g->zero_copy = getenv("G2GPU_ZERO_COPY") ? atoi(getenv("G2GPU_ZERO_COPY")) != 0 : 1;
+  g->last_zero_copy = 0;
   memset(&g->nccl, 0, sizeof(g->nccl));
   for(int i = 0; i < G2_GROUP_MAX; i++)
     {
       g->ctx[i] = nullptr;
       g->comm[i] = nullptr;
       g->h_res[i] = nullptr;
+      g->d_prof[i] = g->h_prof[i] = nullptr;
       g->h_idx[i] = nullptr;
       g->h_cap[i] = 0;
       g->lo[i] = g->hi[i] = 0;
@@ -196,6 +203,10 @@ extern "C" void g2gpu_group_destroy(g2gpu_group *g)
 	cudaFreeHost(g->h_res[i]);
       if(g->h_idx[i])
 	cudaFreeHost(g->h_idx[i]);
+      if(g->h_prof[i])
+	cudaFreeHost(g->h_prof[i]);
+      if(g->d_prof[i])
+	cudaFree(g->d_prof[i]);
       if(g->ctx[i])
 	g2gpu_destroy(g->ctx[i]);
     }
@@ -203,6 +214,7 @@ extern "C" void g2gpu_group_destroy(g2gpu_group *g)
 }
 
 extern "C" int g2gpu_group_size(g2gpu_group *g) { return g ? g->n : 0; }
+extern "C" int g2gpu_group_zero_copy(g2gpu_group *g) { return g ? g->last_zero_copy : 0; }
 extern "C" g2gpu_ctx *g2gpu_group_ctx(g2gpu_group *g, int i) { return (g && i >= 0 && i < g->n) ? g->ctx[i] : nullptr; }
 
 // ---- tables and options go to every device ----
@@ -461,7 +473,7 @@ static void scatter_threads(size_t cnt, unsigned int nthr, W work, size_t min_pe
 }
 
 // GravCost profile of the walk just downloaded -> slice boundaries of the next one (equal cost per device)
-static void rebalance(g2gpu_group *g)
+static void rebalance(g2gpu_group *g, bool device_profile = false)
 {
   int nt = 0;
   for(int i = 0; i < g->n; i++)
@@ -482,6 +494,12 @@ static void rebalance(g2gpu_group *g)
 	continue;
       const size_t b0 = (size_t) lo / G2_COST_BLOCK, b1 = (size_t) (hi - 1) / G2_COST_BLOCK + 1;
       double *prof = g->profile.data();
+      if(device_profile)
+	{			// summed by cost_profile_kernel: h_prof[i][k] belongs to block b0 + k
+	  for(size_t blk = b0; blk < b1; blk++)
+	    prof[blk] += g->h_prof[i][blk - b0];
+	  continue;
+	}
       scatter_threads(b1 - b0, hw, [=](size_t a, size_t b) {
 	for(size_t blk = b0 + a; blk < b0 + b; blk++)
 	  {
@@ -635,6 +653,43 @@ extern "C" int g2gpu_group_sync(g2gpu_group *g)
   return run_all(g, [&](int i) { return g2gpu_sync(g->ctx[i]); });
 }
 
+// ---- zero-copy results: pinned result arrays are written by the walk kernel itself ----
+// device-visible alias of a host pointer on the current device, or null when the memory is not pinned and mapped there
+static float *mapped_host_ptr(const void *p)
+{
+  if(!p)
+    return nullptr;
+  cudaPointerAttributes a;
+  if(cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return nullptr;
+    }
+  if(a.type != cudaMemoryTypeHost || !a.devicePointer)
+    return nullptr;
+  return (float *) a.devicePointer;
+}
+
+// GravCost (+ 1 per target) of this device's slice per block of G2_COST_BLOCK targets, from the compact results: one warp per block;
+// prof[k] belongs to block lo / G2_COST_BLOCK + k.  The slice bounds are read on the device (no host round trip before the launch).
+__global__ void __launch_bounds__(256) cost_profile_kernel(const float *__restrict__ cres, const int *__restrict__ slice, int nwarps, double *__restrict__ prof)
+{
+  const int warp = (int) ((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if(warp >= nwarps)
+    return;
+  const long long lo = slice[G2_SLICE_LO], hi = slice[G2_SLICE_HI];
+  const long long blk = lo / G2_COST_BLOCK + warp;
+  const long long t0 = blk * G2_COST_BLOCK > lo ? blk * G2_COST_BLOCK : lo, t1 = (blk + 1) * G2_COST_BLOCK < hi ? (blk + 1) * G2_COST_BLOCK : hi;
+  double s = 0.0;
+  for(long long t = t0 + lane; t < t1; t += 32)
+    s += (double) cres[5 * (t - lo) + 3] + 1.0;
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1)
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  if(lane == 0)
+    prof[warp] = s;
+}
+
 // Whole step with host buffers: sharded upload + all-gather -> domain -> treebuild -> walk of N slices -> slice downloads (the e2e path)
 extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
 					const int *active, const g2gpu_walk_params *wp, float *acc, float *cost, float *oldacc_out, int *perm)
@@ -647,6 +702,21 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
   // one device and every particle a target: the walk writes its results in particle order and they are copied straight into the caller's
   // arrays -- no compaction, no index list, no host scatter
   const bool direct = g->n == 1 && !active;
+  // pinned result arrays (cudaHostAlloc / cudaHostRegister'd, mapped on every device of the group): the epilogue of the walk kernel stores each
+  // target's results straight into them -- posted writes over PCIe spread over the whole walk -- so no download, no staging and no host scatter
+  // follow the walk; what is left for the host is the GravCost profile of the balancer, summed on the device (128 KB per device)
+  int zc = g->zero_copy && acc != nullptr;
+  float *zacc[G2_GROUP_MAX], *zcost[G2_GROUP_MAX], *zold[G2_GROUP_MAX];
+  for(int i = 0; i < g->n && zc; i++)
+    {
+      if(cudaSetDevice(g->devices[i]) != cudaSuccess)
+	return g2_fail(G2GPU_ERR_CUDA, "cudaSetDevice(%d) failed", g->devices[i]);
+      zacc[i] = mapped_host_ptr(acc); zcost[i] = mapped_host_ptr(cost); zold[i] = mapped_host_ptr(oldacc_out);
+      if(!zacc[i] || (cost && !zcost[i]) || (oldacc_out && !zold[i]))
+	zc = 0;
+    }
+  g->last_zero_copy = zc;
+  const int nbcap = g->ctx[0]->cfg.max_part / G2_COST_BLOCK + 2;
   // one host thread per device drives its whole pipeline: no host barrier between the stages (the all-gather synchronises the devices)
   G2_TRY(run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
@@ -660,13 +730,45 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
     c->slice_explicit = 1;
     c->slice_frac[0] = g->frac[i];
     c->slice_frac[1] = g->frac[i + 1];
-    return g2_stage_walk(c, wp);
+    if(!zc)
+      return g2_stage_walk(c, wp);
+    c->zc_acc = zacc[i]; c->zc_cost = zcost[i]; c->zc_oldacc = zold[i];
+    const int rc = g2_stage_walk(c, wp);
+    c->zc_acc = c->zc_cost = c->zc_oldacc = nullptr;
+    if(rc)
+      return rc;
+    const bool want_profile = g->cost_weighted && g->n > 1;
+    if(want_profile)
+      {
+	if(!g->d_prof[i])
+	  {
+	    G2_CUDA(cudaMalloc((void **) &g->d_prof[i], sizeof(double) * (size_t) nbcap));
+	    G2_CUDA(cudaMallocHost((void **) &g->h_prof[i], sizeof(double) * (size_t) nbcap));
+	  }
+	cost_profile_kernel<<<g2_cdiv(nbcap * 32, 256), 256, 0, c->stream>>>(c->cres, (const int *) c->d_slice, nbcap, g->d_prof[i]);
+	G2_CUDA(cudaMemcpyAsync(g->h_prof[i], g->d_prof[i], sizeof(double) * (size_t) nbcap, cudaMemcpyDeviceToHost, c->stream));
+      }
+    G2_TRY(g2_fetch_slice(c));	// (synchronises the stream: the results are in the caller's arrays)
+    G2_CUDA(cudaStreamSynchronize(c->stream));
+    G2_CUDA(cudaGetLastError());
+    g->lo[i] = c->w_lo;
+    g->hi[i] = c->w_hi;
+    c->d2h_bytes = (size_t) (c->w_hi - c->w_lo) * 20 + (want_profile ? sizeof(double) * (size_t) nbcap : 0);	// kernel stores into host memory + the profile
+    return 0;
   }));
   g->h2d_bytes = 0;
   for(int i = 0; i < g->n; i++)
     g->h2d_bytes += (long long) g->ctx[i]->h2d_bytes;
   g->gather_bytes = g->n > 1 ? (long long) g->per * g->n * (long long) sizeof(G2PRec) : 0;
-  if(direct)
+  if(zc)
+    {
+      g->ntargets = g->ctx[0]->w_ntargets;
+      g->d2h_bytes = 0;
+      for(int i = 0; i < g->n; i++)
+	g->d2h_bytes += (long long) g->ctx[i]->d2h_bytes;
+      rebalance(g, true);
+    }
+  else if(direct)
     {
       g2gpu_ctx *c = g->ctx[0];
       G2_TRY(g2_fetch_slice(c));
@@ -681,6 +783,8 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
     }
   else
     G2_TRY(g2gpu_group_download_acc(g, acc, cost, oldacc_out));
+  if(direct)
+    g->ctx[0]->compact = 1;
   if(perm)
     {
       // every device holds the same order: each one returns 1/N of it over its own link

@@ -49,10 +49,7 @@ __device__ __forceinline__ unsigned int chunk_dealer_next(unsigned int *sm_count
   return 0xffffffffu;
 }
 
-// slice[] (device memory, written by slice_kernel before the walk): the walk never needs a host round trip for the target count
-#define G2_SLICE_NTARGETS 0
-#define G2_SLICE_LO 1
-#define G2_SLICE_HI 2
+// (G2_SLICE_*: g2_common.cuh)
 
 // what the FP64 re-evaluation of a borderline decision needs (walk_decide_exact): kept in device memory, so that the rarely called
 // non-inlined functions take one pointer instead of a copy of the kernel arguments
@@ -79,6 +76,9 @@ struct WalkArgs
   float *__restrict__ cost;
   float *__restrict__ oldacc_out;
   float *__restrict__ cres;			// ... or, when not null, compact: 5 floats (acc[3], cost, oldacc) per target of the slice, target order
+  // zero-copy results (g2gpu_group_gravity_tree with pinned result arrays): device-visible pointers to the CALLER's host arrays, indexed by
+  // particle like acc / cost / oldacc_out; the epilogue stores there as well, so no download and no host scatter follow the walk
+  float *__restrict__ zc_acc, *__restrict__ zc_cost, *__restrict__ zc_oldacc;
   unsigned long long *__restrict__ counters;
   unsigned int *__restrict__ work_counter;
   unsigned int *__restrict__ sm_counter;	// one chunk counter per SM (ChunkDealer), nullptr: the global work_counter only

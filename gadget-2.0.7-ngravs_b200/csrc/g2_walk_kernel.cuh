@@ -591,6 +591,16 @@ __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned in
       fy = (float) ((double) fy + A.pos_fac_post_g * (double) py);
       fz = (float) ((double) fz + A.pos_fac_post_g * (double) pz);
     }
+  if(A.zc_acc)
+    {				// straight into the caller's pinned host arrays (posted writes over PCIe, spread over the whole kernel)
+      A.zc_acc[3 * (size_t) idx + 0] = fx;
+      A.zc_acc[3 * (size_t) idx + 1] = fy;
+      A.zc_acc[3 * (size_t) idx + 2] = fz;
+      if(A.zc_cost)
+	A.zc_cost[idx] = ninter;
+      if(A.zc_oldacc)
+	A.zc_oldacc[idx] = oldacc_new;
+    }
   if(A.cres)
     {				// compact results of the slice in target order (multi-GPU: only the slice travels to the host)
       float *o = A.cres + 5 * (size_t) tloc;

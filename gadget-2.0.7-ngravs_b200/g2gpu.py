@@ -31,7 +31,7 @@ EXPORTED = [
     "g2gpu_group_set_srtable", "g2gpu_group_set_lattice_tables", "g2gpu_group_set_option", "g2gpu_group_upload", "g2gpu_group_upload_aos",
     "g2gpu_group_gather_resident", "g2gpu_group_shard", "g2gpu_group_domain", "g2gpu_group_treebuild", "g2gpu_group_update_tree",
     "g2gpu_group_walk", "g2gpu_group_download_acc", "g2gpu_group_download_aos", "g2gpu_group_get_order", "g2gpu_group_gravity_tree",
-    "g2gpu_group_step_resident", "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices",
+    "g2gpu_group_step_resident", "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices", "g2gpu_group_zero_copy",
 ]
 
 
@@ -604,6 +604,10 @@ class TreeGravityGroup:
         b = np.zeros(3, dtype=np.int64)
         self._chk(self.lib.g2gpu_group_io_bytes(self.grp, _p(b)))
         return int(b[0]), int(b[1]), int(b[2])
+
+    def zero_copy(self):
+        """True when the last gravity_tree() let the walk kernel store the results straight into the (pinned) `out` arrays."""
+        return bool(self.lib.g2gpu_group_zero_copy(self.grp))
 
     def slices(self):
         lo, hi = np.zeros(self.ndev, dtype=np.int32), np.zeros(self.ndev, dtype=np.int32)

@@ -335,6 +335,10 @@ int g2gpu_group_step_resident(g2gpu_group *grp, int npart, const g2gpu_walk_para
 int g2gpu_group_sync(g2gpu_group *grp);
 int g2gpu_group_timings(g2gpu_group *grp, double ms[8], long long counters[8]);	/* times: max over devices; counters: sums */
 int g2gpu_group_io_bytes(g2gpu_group *grp, long long out[3]);	/* H2D, D2H (all devices), bytes received per device by the all-gather */
+/* 1 when the last g2gpu_group_gravity_tree found acc / cost / oldacc_out pinned and mapped on every device (cudaHostAlloc, cudaHostRegister) and let
+ * the walk kernel store the results straight into them (no download, no host scatter; replaces the export / import of results of gravtree.c:102-285);
+ * 0 when it staged and scattered them.  G2GPU_ZERO_COPY=0 forces the staged path. */
+int g2gpu_group_zero_copy(g2gpu_group *grp);
 int g2gpu_group_slices(g2gpu_group *grp, int *lo, int *hi, double *next_frac);	/* last walk's slices [N]; next walk's boundaries [N+1] */
 
 /* ---- instrumentation ---- */

@@ -98,6 +98,43 @@ def test_group_of_one_equals_single_context():
     g.close()
 
 
+def _pinned(n):
+    import torch
+    return (torch.full((n, 3), -7.0, dtype=torch.float32).pin_memory().numpy(), torch.full((n,), -7.0, dtype=torch.float32).pin_memory().numpy(),
+            torch.full((n,), -7.0, dtype=torch.float32).pin_memory().numpy(), torch.zeros(n, dtype=torch.int32).pin_memory().numpy())
+
+
+def test_zero_copy_results_equal_staged_results():
+    """Pinned result arrays are written by the walk kernel itself (g2gpu_group_zero_copy): same bits as the staged download, all targets and a
+    sparse active set (only active targets are written); pageable arrays take the staged path."""
+    from g2gpu import TreeGravityGroup
+    c = _treepm_case()
+    t, wp, (acc1, cost1, old1, perm1) = _single(c)
+    t.close()
+    active = (np.random.default_rng(5).random(c["n"]) < 0.2).astype(np.int32)
+    t, wp, (acc1s, cost1s, old1s, perm1s) = _single(c, active=active)
+    t.close()
+    g = TreeGravityGroup(max_part=int(1.1 * c["n"]) + 64, n_gravs=2, periodic=True, shortrange=True, unequal_softenings=False, ndev=1)
+    _setup(g, c)
+    g.gravity_tree(c["pos"], c["mass"], c["ptype"], wp)
+    assert not g.zero_copy()
+    out = _pinned(c["n"])
+    acc, cost, old, perm = g.gravity_tree(c["pos"], c["mass"], c["ptype"], wp, out=out)
+    assert g.zero_copy()
+    assert np.array_equal(perm, perm1)
+    assert np.array_equal(acc.view(np.uint32), acc1.view(np.uint32)) and np.array_equal(cost, cost1) and np.array_equal(old, old1)
+    h2d, d2h, _ = g.io_bytes()
+    assert d2h == 24 * c["n"]                                   # 20 B per target stored by the kernel + 4 B of the particle order
+    out = _pinned(c["n"])
+    acc, cost, old, perm = g.gravity_tree(c["pos"], c["mass"], c["ptype"], wp, active=active, out=out)
+    assert g.zero_copy()
+    act_dev = active[perm1] != 0
+    assert np.array_equal(acc[act_dev].view(np.uint32), acc1s[act_dev].view(np.uint32)) and np.array_equal(cost[act_dev], cost1s[act_dev])
+    assert np.array_equal(old[act_dev], old1s[act_dev])
+    assert np.all(cost[~act_dev] == -7.0) and np.all(acc[~act_dev] == -7.0)
+    g.close()
+
+
 def test_group_of_two_equals_one_device():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
@@ -125,4 +162,14 @@ def test_group_of_two_equals_one_device():
     # second step (slices now cut at equal GravCost): still bit-identical to one device
     acc, cost, old, perm = g.gravity_tree(c["pos"], c["mass"], c["ptype"], wp2, oldacc=oldacc)
     assert np.array_equal(acc.view(np.uint32), acc2.view(np.uint32)) and np.array_equal(cost, cost2)
+    assert not g.zero_copy()
+    # pinned result arrays: both devices store their slices straight into them; the GravCost profile of the balancer comes from the devices
+    fr_staged = g.slices()[2]
+    out = _pinned(c["n"])
+    acc, cost, old, perm = g.gravity_tree(c["pos"], c["mass"], c["ptype"], wp2, oldacc=oldacc, out=out)
+    assert g.zero_copy()
+    assert np.array_equal(acc.view(np.uint32), acc2.view(np.uint32)) and np.array_equal(cost, cost2) and np.array_equal(old, old2)
+    assert np.array_equal(perm, perm1)
+    fr = g.slices()[2]
+    assert abs(fr[1] - fr_staged[1]) < 1e-3                   # same profile, summed in another order
     g.close()
