@@ -80,6 +80,17 @@ struct G2LawTable
   float par[G2GPU_MAX_GRAVS * G2GPU_MAX_GRAVS][4];
 };
 
+// zero-copy results into an array of structures in pinned host memory (the reference's P[]): result of device-order particle i goes to
+// base + perm[i] * stride, GravAccel[3] / OldAcc as float or double, GravCost as float (g2gpu_group_bind_results_aos)
+struct G2ZcAos
+{
+  char *base;			// device-visible alias of the host array, nullptr: unused
+  const int *perm;		// device order -> index in the host array
+  unsigned long long stride;
+  int off_acc, off_cost, off_old;	// byte offsets, < 0: not written
+  int float_bytes;
+};
+
 // slice[] (device memory, written by slice_kernel before the walk): the walk never needs a host round trip for the target count
 #define G2_SLICE_NTARGETS 0
 #define G2_SLICE_LO 1
@@ -132,6 +143,7 @@ struct g2gpu_ctx
   int walk_flush_mask;		// G2GPU_WALK_FLUSH_MASK (0, 1, 3, 7 = default): the FP32 partial sums of the walk go into the accumulators at descents with (cell index & mask) == 0
   int compact;			// option "compact": the walk writes its slice's results in target order (cres) instead of by particle index
   float *cres;			// 5 floats per target of the slice (acc[3], cost, oldacc), allocated with the option
+  G2ZcAos zc_aos;		// the same for an array of structures
   float *zc_acc, *zc_cost, *zc_oldacc;	// set by the multi-GPU group for one walk: device-visible pointers to the caller's pinned result arrays (WalkArgs)
   int slice_explicit;		// slice_frac[] instead of rank/nranks (cost-weighted slices of the group path)
   double slice_frac[2];

@@ -54,11 +54,18 @@ struct g2gpu_group
   int lo[G2_GROUP_MAX], hi[G2_GROUP_MAX], ntargets;
   // zero-copy results: GravCost profile of a device's slice, summed on the device (cost_profile_kernel)
   double *d_prof[G2_GROUP_MAX], *h_prof[G2_GROUP_MAX];
+  // results bound to an array of structures in host memory (g2gpu_group_bind_results_aos)
+  void *aos_host;		// the bound array (nullptr: none), registered by this library when aos_registered
+  size_t aos_bytes;
+  int aos_registered, aos_walk;	// aos_walk: the last g2gpu_group_walk stored its results there
+  G2ZcAos aos[G2_GROUP_MAX];	// per device: mapped alias, layout
   int zero_copy;		// G2GPU_ZERO_COPY (default 1): pinned result arrays of g2gpu_group_gravity_tree are written by the walk kernel itself
   int last_zero_copy;		// the last g2gpu_group_gravity_tree took that path
   char errs[G2_GROUP_MAX][512];
   long long h2d_bytes, d2h_bytes, gather_bytes;
 };
+
+static int device_profile(g2gpu_group *g, int i);
 
 // ---- one host thread per device ----
 template <class F>
@@ -133,6 +140,8 @@ extern "C" int g2gpu_group_create(g2gpu_group **out, const g2gpu_config *cfg, in
   g->h2d_bytes = g->d2h_bytes = g->gather_bytes = 0;
   g->zero_copy = getenv("G2GPU_ZERO_COPY") ? atoi(getenv("G2GPU_ZERO_COPY")) != 0 : 1;
   g->last_zero_copy = 0;
+  g->aos_host = nullptr; g->aos_bytes = 0; g->aos_registered = 0; g->aos_walk = 0;
+  memset(g->aos, 0, sizeof(g->aos));
   memset(&g->nccl, 0, sizeof(g->nccl));
   for(int i = 0; i < G2_GROUP_MAX; i++)
     {
@@ -210,6 +219,8 @@ extern "C" void g2gpu_group_destroy(g2gpu_group *g)
       if(g->ctx[i])
 	g2gpu_destroy(g->ctx[i]);
     }
+  if(g->aos_host && g->aos_registered)
+    cudaHostUnregister(g->aos_host);
   delete g;
 }
 
@@ -410,13 +421,21 @@ extern "C" int g2gpu_group_walk(g2gpu_group *g, const g2gpu_walk_params *wp)
 {
   if(!g || !wp)
     return g2_fail(G2GPU_ERR_ARG, "null argument");
+  g->aos_walk = g->aos_host != nullptr;
   return run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
-    c->compact = 1;		// (the slice downloads read the compacted results)
+    c->compact = 1;		// (the slice downloads and the GravCost profile read the compacted results)
     c->slice_explicit = 1;
     c->slice_frac[0] = g->frac[i];
     c->slice_frac[1] = g->frac[i + 1];
-    return g2_stage_walk(c, wp);
+    if(g->aos_walk)
+      {				// results also go straight into the bound array of structures
+	c->zc_aos = g->aos[i];
+	c->zc_aos.perm = c->perm;
+      }
+    const int rc = g2_stage_walk(c, wp);
+    c->zc_aos.base = nullptr;
+    return rc;
   });
 }
 
@@ -586,9 +605,36 @@ extern "C" int g2gpu_group_download_aos(g2gpu_group *g, void *P, size_t stride, 
     return g2_fail(G2GPU_ERR_ARG, "null argument");
   if(float_bytes != 4 && float_bytes != 8)
     return g2_fail(G2GPU_ERR_ARG, "float_bytes must be 4 or 8");
+  double sums[G2_GROUP_MAX];
+  if(g->aos_walk && P == g->aos_host && stride == (size_t) g->aos[0].stride && float_bytes == g->aos[0].float_bytes && off_gravaccel == g->aos[0].off_acc
+     && off_gravcost == g->aos[0].off_cost && off_oldacc == g->aos[0].off_old)
+    {				// the walk kernel has stored the results in P[] itself: wait for the devices, take their GravCost profiles
+      G2_TRY(run_all(g, [&](int i) {
+	G2_TRY(device_profile(g, i));
+	double sum = 0.0;
+	if(g->hi[i] > g->lo[i])
+	  for(size_t k = 0, nb = (size_t) (g->hi[i] - 1) / G2_COST_BLOCK - (size_t) g->lo[i] / G2_COST_BLOCK + 1; k < nb; k++)
+	    sum += g->h_prof[i][k];
+	sums[i] = sum - (double) (g->hi[i] - g->lo[i]);	// (the profile counts + 1 per target)
+	g->ctx[i]->d2h_bytes = (size_t) (g->hi[i] - g->lo[i]) * (size_t) (float_bytes == 4 ? 20 : 36) + sizeof(double) * (size_t) (g->ctx[i]->cfg.max_part / G2_COST_BLOCK + 2);
+	return 0;
+      }));
+      if(cost_sum)
+	{
+	  *cost_sum = 0;
+	  for(int i = 0; i < g->n; i++)
+	    *cost_sum += sums[i];
+	}
+      g->d2h_bytes = 0;
+      for(int i = 0; i < g->n; i++)
+	g->d2h_bytes += (long long) g->ctx[i]->d2h_bytes;
+      g->last_zero_copy = 1;
+      rebalance(g, true);
+      return 0;
+    }
+  g->last_zero_copy = 0;
   const unsigned int hw = std::max(1u, std::thread::hardware_concurrency());
   const unsigned int thr = std::max(1u, std::min(32u, hw) / (unsigned int) g->n);
-  double sums[G2_GROUP_MAX];
   G2_TRY(run_all(g, [&](int i) {
     G2_TRY(fetch_slice_results(g, i));
     const float *r = g->h_res[i];
@@ -654,6 +700,8 @@ extern "C" int g2gpu_group_sync(g2gpu_group *g)
 }
 
 // ---- zero-copy results: pinned result arrays are written by the walk kernel itself ----
+static float *mapped_host_ptr(const void *p);
+
 // device-visible alias of a host pointer on the current device, or null when the memory is not pinned and mapped there
 static float *mapped_host_ptr(const void *p)
 {
@@ -690,6 +738,79 @@ __global__ void __launch_bounds__(256) cost_profile_kernel(const float *__restri
     prof[warp] = s;
 }
 
+// GravCost profile of device i's slice from its compact results, and the slice bounds; synchronises the device's stream
+static int device_profile(g2gpu_group *g, int i)
+{
+  g2gpu_ctx *c = g->ctx[i];
+  const int nbcap = c->cfg.max_part / G2_COST_BLOCK + 2;
+  if(!g->d_prof[i])
+    {
+      G2_CUDA(cudaMalloc((void **) &g->d_prof[i], sizeof(double) * (size_t) nbcap));
+      G2_CUDA(cudaMallocHost((void **) &g->h_prof[i], sizeof(double) * (size_t) nbcap));
+    }
+  cost_profile_kernel<<<g2_cdiv(nbcap * 32, 256), 256, 0, c->stream>>>(c->cres, (const int *) c->d_slice, nbcap, g->d_prof[i]);
+  G2_CUDA(cudaMemcpyAsync(g->h_prof[i], g->d_prof[i], sizeof(double) * (size_t) nbcap, cudaMemcpyDeviceToHost, c->stream));
+  G2_TRY(g2_fetch_slice(c));
+  G2_CUDA(cudaStreamSynchronize(c->stream));
+  G2_CUDA(cudaGetLastError());
+  g->lo[i] = c->w_lo;
+  g->hi[i] = c->w_hi;
+  return 0;
+}
+
+// Binds the results of the following g2gpu_group_walk calls to an array of structures in host memory (the reference's P[], allvars.h:548-590):
+// the walk kernel then stores GravAccel / GravCost / OldAcc of every active target straight into it (P[order[i]] for device-order particle i)
+// and g2gpu_group_download_aos only waits for the devices.  The array is page-locked here (cudaHostRegister) unless it already is; when that
+// fails, or with G2GPU_ZERO_COPY=0, nothing is bound and the download stages and scatters as before.  P == NULL removes the binding.
+extern "C" int g2gpu_group_bind_results_aos(g2gpu_group *g, void *P, size_t nelem, size_t stride, int float_bytes, int off_gravaccel, int off_gravcost, int off_oldacc)
+{
+  if(!g)
+    return g2_fail(G2GPU_ERR_ARG, "null argument");
+  if(g->aos_host)
+    {
+      G2_TRY(g2gpu_group_sync(g));
+      if(g->aos_registered)
+	cudaHostUnregister(g->aos_host);
+      g->aos_host = nullptr;
+      g->aos_registered = 0;
+    }
+  if(!P || !g->zero_copy)
+    return 0;
+  if((float_bytes != 4 && float_bytes != 8) || off_gravaccel < 0 || stride == 0 || nelem == 0)
+    return g2_fail(G2GPU_ERR_ARG, "bind_results_aos: bad layout");
+  if(cudaSetDevice(g->devices[0]) != cudaSuccess)
+    return g2_fail(G2GPU_ERR_CUDA, "cudaSetDevice(%d) failed", g->devices[0]);
+  int registered = 0;
+  if(!mapped_host_ptr(P))
+    {
+      if(cudaHostRegister(P, nelem * stride, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess)
+	{
+	  cudaGetLastError();
+	  return 0;		// cannot be page-locked: staged downloads
+	}
+      registered = 1;
+    }
+  for(int i = 0; i < g->n; i++)
+    {
+      cudaSetDevice(g->devices[i]);
+      g->aos[i].base = (char *) mapped_host_ptr(P);
+      g->aos[i].perm = nullptr;
+      g->aos[i].stride = (unsigned long long) stride;
+      g->aos[i].off_acc = off_gravaccel; g->aos[i].off_cost = off_gravcost; g->aos[i].off_old = off_oldacc;
+      g->aos[i].float_bytes = float_bytes;
+      if(!g->aos[i].base)
+	{
+	  if(registered)
+	    cudaHostUnregister(P);
+	  return 0;
+	}
+    }
+  g->aos_host = P;
+  g->aos_bytes = nelem * stride;
+  g->aos_registered = registered;
+  return 0;
+}
+
 // Whole step with host buffers: sharded upload + all-gather -> domain -> treebuild -> walk of N slices -> slice downloads (the e2e path)
 extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *pos, const float *mass, const int *type, const float *oldacc,
 					const int *active, const g2gpu_walk_params *wp, float *acc, float *cost, float *oldacc_out, int *perm)
@@ -716,7 +837,7 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
 	zc = 0;
     }
   g->last_zero_copy = zc;
-  const int nbcap = g->ctx[0]->cfg.max_part / G2_COST_BLOCK + 2;
+  const size_t nbcap = (size_t) (g->ctx[0]->cfg.max_part / G2_COST_BLOCK + 2);
   // one host thread per device drives its whole pipeline: no host barrier between the stages (the all-gather synchronises the devices)
   G2_TRY(run_all(g, [&](int i) {
     g2gpu_ctx *c = g->ctx[i];
@@ -739,20 +860,15 @@ extern "C" int g2gpu_group_gravity_tree(g2gpu_group *g, int npart, const float *
       return rc;
     const bool want_profile = g->cost_weighted && g->n > 1;
     if(want_profile)
+      G2_TRY(device_profile(g, i));
+    else
       {
-	if(!g->d_prof[i])
-	  {
-	    G2_CUDA(cudaMalloc((void **) &g->d_prof[i], sizeof(double) * (size_t) nbcap));
-	    G2_CUDA(cudaMallocHost((void **) &g->h_prof[i], sizeof(double) * (size_t) nbcap));
-	  }
-	cost_profile_kernel<<<g2_cdiv(nbcap * 32, 256), 256, 0, c->stream>>>(c->cres, (const int *) c->d_slice, nbcap, g->d_prof[i]);
-	G2_CUDA(cudaMemcpyAsync(g->h_prof[i], g->d_prof[i], sizeof(double) * (size_t) nbcap, cudaMemcpyDeviceToHost, c->stream));
+	G2_TRY(g2_fetch_slice(c));	// (synchronises the stream: the results are in the caller's arrays)
+	G2_CUDA(cudaStreamSynchronize(c->stream));
+	G2_CUDA(cudaGetLastError());
+	g->lo[i] = c->w_lo;
+	g->hi[i] = c->w_hi;
       }
-    G2_TRY(g2_fetch_slice(c));	// (synchronises the stream: the results are in the caller's arrays)
-    G2_CUDA(cudaStreamSynchronize(c->stream));
-    G2_CUDA(cudaGetLastError());
-    g->lo[i] = c->w_lo;
-    g->hi[i] = c->w_hi;
     c->d2h_bytes = (size_t) (c->w_hi - c->w_lo) * 20 + (want_profile ? sizeof(double) * (size_t) nbcap : 0);	// kernel stores into host memory + the profile
     return 0;
   }));

@@ -123,7 +123,7 @@ int g2_stage_walk(g2gpu_ctx *c, const g2gpu_walk_params *wp)
   A.gravpm = c->gravpm; A.srtable = c->d_srtable_f; A.acc = c->acc; A.cost = c->cost;
   A.oldacc_out = c->oldacc_out; A.counters = c->d_counters; A.work_counter = (unsigned int *) (c->d_counters + 3);
   A.cres = c->compact ? c->cres : nullptr;
-  A.zc_acc = c->zc_acc; A.zc_cost = c->zc_cost; A.zc_oldacc = c->zc_oldacc;
+  A.zc_acc = c->zc_acc; A.zc_cost = c->zc_cost; A.zc_oldacc = c->zc_oldacc; A.zc_aos = c->zc_aos;
   // the scan scratch is free once the slice is known: the list of targets to walk again in FP64
   A.redo_list = c->w_flags; A.redo_count = (unsigned int *) (c->d_counters + 6); A.redo_cap = (unsigned int) c->cfg.max_part;
   A.numnodes = c->numnodes; A.ntab = c->cfg.ntab;

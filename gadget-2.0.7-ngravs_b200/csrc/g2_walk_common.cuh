@@ -79,6 +79,7 @@ struct WalkArgs
   // zero-copy results (g2gpu_group_gravity_tree with pinned result arrays): device-visible pointers to the CALLER's host arrays, indexed by
   // particle like acc / cost / oldacc_out; the epilogue stores there as well, so no download and no host scatter follow the walk
   float *__restrict__ zc_acc, *__restrict__ zc_cost, *__restrict__ zc_oldacc;
+  G2ZcAos zc_aos;		// ... or to the caller's array of structures (the reference's P[]): base == nullptr when unused
   unsigned long long *__restrict__ counters;
   unsigned int *__restrict__ work_counter;
   unsigned int *__restrict__ sm_counter;	// one chunk counter per SM (ChunkDealer), nullptr: the global work_counter only

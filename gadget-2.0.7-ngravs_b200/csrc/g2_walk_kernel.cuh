@@ -601,6 +601,26 @@ __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned in
       if(A.zc_oldacc)
 	A.zc_oldacc[idx] = oldacc_new;
     }
+  if(A.zc_aos.base)
+    {				// ... or into the caller's array of structures
+      char *q = A.zc_aos.base + (size_t) A.zc_aos.perm[idx] * A.zc_aos.stride;
+      if(A.zc_aos.float_bytes == 4)
+	{
+	  float *ga = (float *) (q + A.zc_aos.off_acc);
+	  ga[0] = fx; ga[1] = fy; ga[2] = fz;
+	  if(A.zc_aos.off_old >= 0)
+	    *(float *) (q + A.zc_aos.off_old) = oldacc_new;
+	}
+      else
+	{
+	  double *ga = (double *) (q + A.zc_aos.off_acc);
+	  ga[0] = (double) fx; ga[1] = (double) fy; ga[2] = (double) fz;
+	  if(A.zc_aos.off_old >= 0)
+	    *(double *) (q + A.zc_aos.off_old) = (double) oldacc_new;
+	}
+      if(A.zc_aos.off_cost >= 0)
+	*(float *) (q + A.zc_aos.off_cost) = ninter;	// (a float in either build, allvars.h:572)
+    }
   if(A.cres)
     {				// compact results of the slice in target order (multi-GPU: only the slice travels to the host)
       float *o = A.cres + 5 * (size_t) tloc;

@@ -31,7 +31,7 @@ EXPORTED = [
     "g2gpu_group_set_srtable", "g2gpu_group_set_lattice_tables", "g2gpu_group_set_option", "g2gpu_group_upload", "g2gpu_group_upload_aos",
     "g2gpu_group_gather_resident", "g2gpu_group_shard", "g2gpu_group_domain", "g2gpu_group_treebuild", "g2gpu_group_update_tree",
     "g2gpu_group_walk", "g2gpu_group_download_acc", "g2gpu_group_download_aos", "g2gpu_group_get_order", "g2gpu_group_gravity_tree",
-    "g2gpu_group_step_resident", "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices", "g2gpu_group_zero_copy",
+    "g2gpu_group_step_resident", "g2gpu_group_sync", "g2gpu_group_timings", "g2gpu_group_io_bytes", "g2gpu_group_slices", "g2gpu_group_zero_copy", "g2gpu_group_bind_results_aos",
 ]
 
 

@@ -34,6 +34,8 @@
 #include "g2gpu.h"
 #include "g2_ph_table.h"
 
+static void *g2_bound_P = NULL;	/* P[] as bound to the walk's zero-copy results (g2_bind_results) */
+static int g2_bound_maxpart = 0;
 static g2gpu_group *G2G = NULL;	/* all GPUs of the node (or G2GPU_NGPU of them): one context + host thread per device */
 static g2gpu_ctx *G2 = NULL;	/* device 0's context: tree mirror, potential, PM, direct sums */
 static int g2_ndev = 1;
@@ -398,6 +400,7 @@ void force_treeallocate(int maxnodes, int maxpart)
       g2gpu_group_destroy(G2G);
       G2G = NULL;
       G2 = NULL;
+      g2_bound_P = NULL;
     }
   if(!G2G)
     {
@@ -986,6 +989,19 @@ static void g2_dynamic_update(int npart)
   free(len);
 }
 
+/* The results of the walk go straight into P[] (zero-copy stores of the walk kernel into page-locked host memory) whenever P[] can be
+ * page-locked; bound again when the reference has moved or resized P[]. */
+static void g2_bind_results(void)
+{
+  if(g2_bound_P == (void *) P && g2_bound_maxpart == All.MaxPart)
+    return;
+  g2_check(g2gpu_group_bind_results_aos(G2G, P, (size_t) All.MaxPart, sizeof(struct particle_data), (int) sizeof(FLOAT),
+					(int) offsetof(struct particle_data, GravAccel), (int) offsetof(struct particle_data, GravCost),
+					(int) offsetof(struct particle_data, OldAcc)), "bind_results_aos");
+  g2_bound_P = (void *) P;
+  g2_bound_maxpart = All.MaxPart;
+}
+
 /* gravtree.c:27.  Build if flagged (always from the current P[]), walk every particle with
  * Ti_endstep == All.Ti_Current on the GPU, epilogue (OldAcc, G, cosmological terms) fused into the walk kernel,
  * results written back into P[], the reference's counters and timings.txt lines kept. */
@@ -1025,6 +1041,7 @@ void gravity_tree(void)
 #endif
   tstart = second();
   g2_fill_walk_params(&wp);
+  g2_bind_results();		/* P[] page-locked once: the walk kernel writes GravAccel / GravCost / OldAcc straight into it */
   g2_check(g2gpu_group_walk(G2G, &wp), "walk");
   /* every device returns its slice of the active targets; host threads write GravAccel, GravCost and OldAcc straight into P[] */
   g2_check(g2gpu_group_download_aos(G2G, P, sizeof(struct particle_data), (int) sizeof(FLOAT), (int) offsetof(struct particle_data, GravAccel),

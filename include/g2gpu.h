@@ -339,6 +339,12 @@ int g2gpu_group_io_bytes(g2gpu_group *grp, long long out[3]);	/* H2D, D2H (all d
  * the walk kernel store the results straight into them (no download, no host scatter; replaces the export / import of results of gravtree.c:102-285);
  * 0 when it staged and scattered them.  G2GPU_ZERO_COPY=0 forces the staged path. */
 int g2gpu_group_zero_copy(g2gpu_group *grp);
+/* Binds the results of the following g2gpu_group_walk calls to an array of structures in host memory -- the reference's P[] (allvars.h:548-590):
+ * the walk kernel stores GravAccel[3] / GravCost / OldAcc of every active target straight into P[order[i]] (what gravtree.c:231-283 and 304-358
+ * do with the imported results), and g2gpu_group_download_aos with the same arguments only waits for the devices.  The array is page-locked
+ * here (cudaHostRegister, portable + mapped) unless it already is; if that fails, or with G2GPU_ZERO_COPY=0, nothing is bound and downloads are
+ * staged.  nelem = allocated elements (All.MaxPart); P == NULL removes the binding (do so before the array is freed). */
+int g2gpu_group_bind_results_aos(g2gpu_group *grp, void *P, size_t nelem, size_t stride, int float_bytes, int off_gravaccel, int off_gravcost, int off_oldacc);
 int g2gpu_group_slices(g2gpu_group *grp, int *lo, int *hi, double *next_frac);	/* last walk's slices [N]; next walk's boundaries [N+1] */
 
 /* ---- instrumentation ---- */
