@@ -140,6 +140,7 @@ struct WalkLane
   // kernel arguments the visit code reads at every term, copied once per chunk through an addition ptxas cannot fold away: it then keeps them in
   // uniform registers instead of re-reading the constant bank at every use (LDCU + MOV per term)
   float k_rmax2, k_rmax2b, k_asmthfac, k_ntabm1;	// (ptxas keeps these three in uniform registers; for the others it re-reads the constant AND adds the zero)
+  // (MEASURED, profiles/r2_walk_microvariants.txt: the same for rcut, rcut^2 and the cull margin removes four LDC per decision and is 1.4 ms SLOWER)
 };
 
 // DEFER (stock pair laws): the terms a lane accepts are not evaluated where they are found -- a handful of lanes at a time -- but staged.
@@ -163,7 +164,7 @@ struct WalkRing
 // than the warp's no-wrap bound): plain differences.  WRAP = true: per-cell image shift for small TreePM cells, NEAREST per point
 // otherwise.  Returns whether the lane opens the cell; shx/shy/shz/small_cell are handed on to the particle half.
 // EXACT: comparisons inside their guard band flag the target for walk_redo_kernel (L.bmin).
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, bool DEFER = false>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, bool DEFER = false, int CRIT = 0>
 __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, const float4 *__restrict__ rec,
 						const float4 q0, const uint4 w, unsigned int cur, WalkLane &L, WalkShift &S, bool &small_cell, unsigned int *newbits = nullptr)
 {
@@ -252,7 +253,7 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
       // The difference of two FP32 coordinates is rounded once, to half an ulp OF THE DIFFERENCE (it is exact when the operands share a
       // binade), so an r^2 built from such differences, and the products compared below, carry a few 1e-7 of relative error whatever
       // the magnitude of the coordinates.
-      if(A.theta2 > 0.0f)
+      if(CRIT == 0 && A.theta2 > 0.0f)	// (CRIT == 1: an instantiation for the relative criterion alone, without the run-time switch)
 	{			// Barnes-Hut, forcetree.c:1437-1445
 	  const float lhs = len * len, v = fmaf(-r2min, A.theta2, lhs);
 	  open = v > 0.0f;
@@ -400,16 +401,21 @@ __device__ __forceinline__ void walk_visit_particles(const WalkArgs &A, const fl
 // One whole visit of the warp at cell `cur` (decisions, vote, flush of the partial sums, particles of an opened cell); returns the
 // next cursor.  The walk loop calls the WRAP or the wrap-free instantiation by a warp-uniform test, so that the wrap-free path carries
 // no image-shift state at all.  ACC accumulators: FP64 in shared memory (acc_sh, one slot per thread) or FP32 in registers (acc_rg).
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, typename ACC>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, bool WRAP, bool STATS, bool EXACT, typename ACC, int CRIT = 0>
 __device__ __forceinline__ unsigned int walk_visit(const WalkArgs &A, const float *__restrict__ s_tab, unsigned int s_tab_addr, unsigned int cur, const float4 *__restrict__ rec,
 						   const float4 q0, const uint4 w, unsigned int t2g_packed, WalkLane &L, ACC (*acc_sh)[WALK_KT], ACC &ax, ACC &ay, ACC &az)
 {
   bool open = false, small_cell = false;
   WalkShift S;
   if(cur >= L.skip_until)
-    open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
-  if(!__any_sync(0xffffffffu, open))
-    return w.x;			// nobody opens the cell: on to its sibling
+    open = walk_visit_cell<D, SR, PERIODIC, UNEQUAL, STOCK, WRAP, STATS, EXACT, false, CRIT>(A, s_tab, s_tab_addr, rec, q0, w, cur, L, S, small_cell);
+  // The openers as a warp-uniform ballot mask, so that no per-lane flag has to survive the vote (as a bool it lived byte-packed in a register:
+  // three PRMT per visit).  MEASURED (B200, 256^3, profiles/r2_walk_microvariants.txt): 173.27 -> 170.68 ms.
+  const unsigned int openers = __ballot_sync(0xffffffffu, open);
+  if(openers == 0u)
+    return w.x;			// nobody opens the cell: on to its sibling (the lanes that are awake stay awake: skip_until <= cur < sibling)
+  open = (openers >> (threadIdx.x & 31u)) & 1u;
+  small_cell = WRAP && SR && q0.x < A.shift_len_max;
   // FP32 partial sums go into the accumulators when the warp descends at a cell whose index has its low bits clear (A.flush_mask; with 0
   // at every descent, about every third visit): few conversions, bounded error, and flush points that depend on the traversal only
   // (=> reproducible bits)
@@ -557,8 +563,19 @@ __device__ __forceinline__ unsigned int walk_visit_defer(const WalkArgs &A, unsi
 }
 
 // gravity_tree epilogue for one target: GravAccel is stored as FLOAT (forcetree.c:1592-1594), then gravtree.c:304-358
+// The epilogue is a real CALL (not inlined), so that its branches -- zero-copy targets, AoS layouts, compact slices -- cannot change the register
+// allocation and scheduling of the walk loop; it runs once per 32 targets, i.e. once per ~2 000 cell visits.  The kernel argument is
+// __grid_constant__ so that the call can take its address without a local copy.  MEASURED (B200, 256^3, profiles/r2_walk_microvariants.txt):
+// inlined 175.38 ms, as a call 173.35 ms (two runs each, +-0.03 ms); __grid_constant__ alone changes nothing.  -DG2_STORE_INLINE restores the inlined form.
+#ifndef G2_STORE_INLINE
+#define G2_STORE_ATTR __noinline__
+#define G2_STORE_GRIDCONST __grid_constant__
+#else
+#define G2_STORE_ATTR __forceinline__
+#define G2_STORE_GRIDCONST
+#endif
 template <bool SR, bool PERIODIC>
-__device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned int idx, int tloc, float px, float py, float pz, float fx, float fy, float fz, float ninter)
+__device__ G2_STORE_ATTR void walk_store_result(const WalkArgs &A, unsigned int idx, int tloc, float px, float py, float pz, float fx, float fy, float fz, float ninter)
 {
   if(PERIODIC && !SR && A.latt)
     {				// force_treeevaluate_lattice_correction adds to the FLOAT result and to GravCost (forcetree.c:2435-2438)
@@ -636,8 +653,8 @@ __device__ __forceinline__ void walk_store_result(const WalkArgs &A, unsigned in
     }
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER>
-__global__ void __launch_bounds__(WALK_KT, WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const WalkArgs A)
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER, int CRIT = 0>
+__global__ void __launch_bounds__(WALK_KT, WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_MINBLOCKS_WIDE : WALK_MINBLOCKS)) walk_kernel(const G2_STORE_GRIDCONST WalkArgs A)
 {
   extern __shared__ float s_tab[];
   __shared__ unsigned int s_chunk[WALK_KWARPS];
@@ -757,9 +774,9 @@ __global__ void __launch_bounds__(WALK_KT, WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_
 		cur = walk_visit_defer<D, SR, PERIODIC, UNEQUAL, false, STATS, EXACT>(A, cur, rec, q0, w, lane, L, R);
 	    }
 	  else if(PERIODIC && !(SR && q0.x < nowrap_len))	// uniform
-	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
+	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, PERIODIC, STATS, EXACT, ACC, CRIT>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
 	  else
-	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT, ACC>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
+	    cur = walk_visit<D, SR, PERIODIC, UNEQUAL, STOCK, false, STATS, EXACT, ACC, CRIT>(A, s_tab, s_tab_addr, cur, rec, q0, w, t2g_packed, L, s_acc, rx, ry, rz);
 	}
 
       const ACC ax = (sizeof(ACC) == 8 ? s_acc[0][threadIdx.x] : rx) + (ACC) L.fx, ay = (sizeof(ACC) == 8 ? s_acc[1][threadIdx.x] : ry) + (ACC) L.fy,
@@ -814,7 +831,7 @@ __global__ void __launch_bounds__(WALK_KT, WALK_KBLOCKS(D >= WALK_WIDE_D ? WALK_
 //      it the part of its range that lies behind the sibling of its current cell.  Partial sums are FP64 and reduced at the end. ----
 #define WALK_REDO_WARPS 4
 template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK>
-__global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const WalkArgs A)
+__global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const G2_STORE_GRIDCONST WalkArgs A)
 {
   extern __shared__ float s_tab[];
   if(SR)
@@ -976,14 +993,14 @@ __global__ void __launch_bounds__(32 * WALK_REDO_WARPS) walk_redo_kernel(const W
     }
 }
 
-template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER>
+template <int D, bool SR, bool PERIODIC, bool UNEQUAL, bool STOCK, typename ACC, bool STATS, bool EXACT, bool DEFER, int CRIT = 0>
 static int launch_one(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem)
 {
   if(smem > 48 * 1024)
-    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER, CRIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   if(c->walk_carveout >= 0)	// share of the 256 KB array kept as shared memory, in percent (the rest is L1); -1: the driver's choice
-    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, c->walk_carveout));
-  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER><<<grid, WALK_KT, smem, c->stream>>>(A);
+    G2_CUDA(cudaFuncSetAttribute(walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER, CRIT>, cudaFuncAttributePreferredSharedMemoryCarveout, c->walk_carveout));
+  walk_kernel<D, SR, PERIODIC, UNEQUAL, STOCK, ACC, STATS, EXACT, DEFER, CRIT><<<grid, WALK_KT, smem, c->stream>>>(A);
   if(EXACT)
     {
       if(smem > 48 * 1024)
@@ -1021,6 +1038,12 @@ static int launch_walk(g2gpu_ctx *c, const WalkArgs &A, int grid, size_t smem, i
 #endif
   if(!acc_double || !A.exact)
     return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, float, false, false, false>(c, A, grid, smem);
+  // The relative criterion has its own instantiation of the default kernel, without the run-time criterion switch per decision (LDCU + FSETP +
+  // BRA).  MEASURED (B200, 256^3, profiles/r2_walk_microvariants.txt): 170.68 -> 167.38 ms.  -DG2_WALK_NO_RELCRIT builds the generic kernel only.
+#ifndef G2_WALK_NO_RELCRIT
+  if(!(A.theta2 > 0.0f))
+    return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true, false, 1>(c, A, grid, smem);
+#endif
   return launch_one<D, SR, PERIODIC, UNEQUAL, STOCK, double, false, true, false>(c, A, grid, smem);
 }
 
