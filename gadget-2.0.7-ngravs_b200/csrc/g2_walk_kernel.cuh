@@ -315,14 +315,19 @@ __device__ __forceinline__ bool walk_visit_cell(const WalkArgs &A, const float *
 	  if(!DEFER)
 	    {
 	      // stock laws, TreePM: ONE test per visit whether any species term can fall inside the softening (r2min < h^2, rare) instead of one
-	      // branch per term; a species without mass is a property of the cell, hence a uniform branch (small cells often hold one species
-	      // only).  (Not for the walks without PM: nvcc 12.9 compiles the spline-free term of that instantiation to fac = 0 -- SASS checked,
+	      // branch per term.  (Not for the walks without PM: nvcc 12.9 compiles the spline-free term of that instantiation to fac = 0 -- SASS checked,
 	      // caught by tests/test_gpu_tree_walk.py --, so they keep the test per term.)
 	      if(STOCK && SR && r2min >= h * h)
 		{
 #pragma unroll
 		  for(int g = 0; g < D; g++)
+		    // (no branch around a species without mass: cnt[g] is false for it, so its term is exactly zero -- the centre of an empty species
+		    // is the finite cell centre, forcetree.c:678-683 -- and the branch, which the compiler cannot know to be warp-uniform, cost more
+		    // than the term: MEASURED, B200, 256^3, profiles/r2_walk_microvariants.txt: 167.44 -> 161.17 ms, results bit-identical;
+		    // -DG2_WALK_MASSBR restores it)
+#ifdef G2_WALK_MASSBR
 		    if(mass[g] != 0.0f)
+#endif
 		      pair_term<SR, STOCK, false>(A, s_tab, s_tab_addr, L.tg, g, D, L.pmass, mass[g], dx[g], dy[g], dz[g], r2[g], h, cnt[g], L.fx, L.fy, L.fz, L.k_asmthfac, L.k_ntabm1);
 		}
 	      else
