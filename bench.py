@@ -518,7 +518,8 @@ def main():
     for suffix in ("r2",):
         prof = os.path.join(ROOT, "profiles", f"r2_walk_{w['key']}.txt")
         if os.path.exists(prof):
-            ncu = {"source": os.path.relpath(prof, ROOT)}
+            ncu = {"source": os.path.relpath(prof, ROOT),
+                   "note": "committed capture (taken on the 172.9 ms state of the kernel at 256^3; the final kernel issues ~7 % fewer instructions, DESIGN.md section 5)"}
             for ln in open(prof):
                 f = ln.split()
                 if len(f) >= 2 and f[0] in ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
